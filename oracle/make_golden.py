@@ -1,0 +1,231 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(TuringQ/deepquantum, /root/reference/src) on CPU in the build container.
+
+Usage:  python oracle/make_golden.py            (needs /root/reference; not run on the GPU box)
+
+TEST INFRASTRUCTURE ONLY.  The fixtures are committed; the tests never need the reference again.
+Everything is seeded, but the values depend on the torch CPU kernels only to rounding.
+
+Files written
+  gate_matrices.npz   the local matrix of every gate family at fixed parameters (complex128)
+  circuits.npz        final states of seeded circuits (specs stored as JSON) in c128 and c64
+  qaoa.npz            QAOA MaxCut loss + gradient (reference autograd) at n = 6, 8, 10
+  fock.npz            Fock tensor backend (squeezer / beamsplitter / phase shifter) final states
+  dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
+"""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+from ref_loader import load_reference  # noqa: E402
+
+from deepquantum_b200 import workloads as wl  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+dq = load_reference()
+torch.manual_seed(1234)
+
+
+def all_gates_spec(n=5, seed=7):
+    """Every gate family of circuit.py:899-1537, with controls on both sides of the targets."""
+    g = torch.Generator().manual_seed(seed)
+
+    def r(k=1):
+        return (torch.rand(k, generator=g, dtype=torch.float64) * 2 * math.pi).tolist()
+
+    def runitary(k):
+        a = torch.randn(2**k, 2**k, generator=g, dtype=torch.float64) + 1j * torch.randn(
+            2**k, 2**k, generator=g, dtype=torch.float64)
+        q, _ = torch.linalg.qr(a)
+        return q.real.tolist(), q.imag.tolist()
+
+    spec = [{'g': 'hlayer'}]
+    for i, name in enumerate(['x', 'y', 'z', 'h', 's', 'sdg', 't', 'tdg']):
+        spec.append({'g': name, 'w': [i % n]})
+        spec.append({'g': name, 'w': [(i + 2) % n], 'c': [(i + 4) % n]})
+    spec.append({'g': 'x', 'w': [2], 'c': [0, 4]})
+    spec.append({'g': 'h', 'w': [0], 'c': [1, 3, 4]})
+    for name in ['rx', 'ry', 'rz', 'p']:
+        spec.append({'g': name, 'w': [1], 'p': r()})
+        spec.append({'g': name, 'w': [4], 'c': [2], 'p': r()})
+        spec.append({'g': name, 'w': [0], 'c': [3, 1], 'p': r()})
+    spec.append({'g': 'u3', 'w': [3], 'p': r(3)})
+    spec.append({'g': 'u3', 'w': [2], 'c': [4], 'p': r(3)})
+    for plane in ['xy', 'yz', 'zx']:
+        spec.append({'g': 'j', 'w': [1], 'p': r(), 'plane': plane})
+    for name in ['cx', 'cy', 'cz', 'ch', 'cs', 'csdg', 'ct', 'ctdg', 'cnot']:
+        spec.append({'g': name, 'w': [3, 0]})
+        spec.append({'g': name, 'w': [1, 4]})
+    for name in ['crx', 'cry', 'crz', 'cp']:
+        spec.append({'g': name, 'w': [4, 2], 'p': r()})
+    spec.append({'g': 'cu', 'w': [0, 3], 'p': r(3)})
+    for name in ['swap', 'iswap']:
+        spec.append({'g': name, 'w': [0, 3]})
+        spec.append({'g': name, 'w': [4, 1], 'c': [2]})
+    for name in ['rxx', 'ryy', 'rzz', 'rxy', 'rbs']:
+        spec.append({'g': name, 'w': [1, 3], 'p': r()})
+        spec.append({'g': name, 'w': [4, 0], 'p': r()})
+        spec.append({'g': name, 'w': [2, 1], 'c': [4], 'p': r()})
+    for name in ['crxx', 'cryy', 'crzz', 'crxy']:
+        spec.append({'g': name, 'w': [2, 4, 0], 'p': r()})
+    spec.append({'g': 'toffoli', 'w': [0, 2, 4]})
+    spec.append({'g': 'toffoli', 'w': [4, 1, 0]})
+    spec.append({'g': 'ccx', 'w': [3, 1, 2]})
+    spec.append({'g': 'fredkin', 'w': [1, 3, 0]})
+    spec.append({'g': 'cswap', 'w': [4, 0, 2]})
+    for k, w in [(1, [2]), (2, [3, 1]), (3, [4, 0, 2]), (4, [1, 3, 0, 4])]:
+        re, im = runitary(k)
+        spec.append({'g': 'any', 'w': w, 'u_re': re, 'u_im': im})
+    re, im = runitary(2)
+    spec.append({'g': 'any', 'w': [0, 2], 'c': [4], 'u_re': re, 'u_im': im})
+    spec += [{'g': 'xlayer', 'w': [0, 2]}, {'g': 'ylayer'}, {'g': 'zlayer', 'w': [1]}]
+    spec += [{'g': 'rxlayer', 'p': r(n)}, {'g': 'rylayer', 'w': [0, 3], 'p': r(2)}, {'g': 'rzlayer', 'p': r(n)}]
+    spec.append({'g': 'u3layer', 'w': [1, 4], 'p': r(6)})
+    spec.append({'g': 'cxlayer', 'pairs': [[0, 1], [4, 2]]})
+    spec.append({'g': 'cnot_ring'})
+    spec.append({'g': 'cnot_ring', 'minmax': [1, 4], 'step': 2, 'reverse': True})
+    return spec
+
+
+def run_ref(spec, n, double, init=None):
+    cir = dq.QubitCircuit(n) if init is None else dq.QubitCircuit(n, init_state=init)
+    wl.apply_spec(cir, spec, torch.complex128 if double else torch.complex64)
+    if double:
+        cir.to(torch.double)
+    with torch.no_grad():
+        out = cir()
+    return out.reshape(out.shape[0], -1).numpy() if out.ndim == 3 else out.reshape(-1).numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+def gate_matrices():
+    th = [0.37, 1.21, -2.05]
+    out = {}
+    for name, cls in [('x', dq.PauliX), ('y', dq.PauliY), ('z', dq.PauliZ), ('h', dq.Hadamard), ('s', dq.SGate),
+                      ('sdg', dq.SDaggerGate), ('t', dq.TGate), ('tdg', dq.TDaggerGate), ('cnot', dq.CNOT),
+                      ('swap', dq.Swap), ('iswap', dq.ImaginarySwap), ('toffoli', dq.Toffoli),
+                      ('fredkin', dq.Fredkin)]:
+        out[name] = cls().to(torch.double).matrix.numpy()
+    for name, cls in [('rx', dq.Rx), ('ry', dq.Ry), ('rz', dq.Rz), ('p', dq.PhaseShift), ('rxx', dq.Rxx),
+                      ('ryy', dq.Ryy), ('rzz', dq.Rzz), ('rxy', dq.Rxy), ('rbs', dq.ReconfigurableBeamSplitter)]:
+        gate = cls(inputs=th[0]).to(torch.double)
+        out[name] = gate.update_matrix().detach().numpy()
+        out[name + '_inv'] = gate.inverse().update_matrix().detach().numpy()
+    u3 = dq.U3Gate(inputs=th).to(torch.double)
+    out['u3'] = u3.update_matrix().detach().numpy()
+    out['u3_inv'] = u3.inverse().update_matrix().detach().numpy()
+    for plane in ['xy', 'yz', 'zx']:
+        out['j_' + plane] = dq.gate.ProjectionJ(inputs=th[0], plane=plane).to(torch.double).update_matrix().numpy()
+    out['theta'] = np.array(th)
+    np.savez_compressed(os.path.join(OUT, 'gate_matrices.npz'), **out)
+    print('gate_matrices', len(out))
+
+
+def circuits():
+    cases = {}
+    cases['all_gates_n5'] = (5, all_gates_spec(5, 7))
+    cases['all_gates_n5_b'] = (5, all_gates_spec(5, 11)[::-1])
+    cases['c1_plumbing_n12'] = (12, wl.c1_plumbing_spec(12))
+    for n, depth in [(3, 6), (6, 8), (9, 10), (12, 12), (14, 40)]:
+        cases[f'random_n{n}_d{depth}'] = (n, wl.random_clifford_rx_spec(n, depth))
+    cases['random_cx_n10_d10'] = (10, wl.random_clifford_rx_spec(10, 10, seed=5, two_qubit='cx'))
+    out = {}
+    for name, (n, spec) in cases.items():
+        out[name + '/spec'] = np.array(json.dumps({'n': n, 'spec': spec}))
+        out[name + '/c128'] = run_ref(spec, n, True)
+        out[name + '/c64'] = run_ref(spec, n, False)
+        print(name, n, len(spec), float(np.linalg.norm(out[name + '/c128'])))
+    # batched initial state + non-trivial initial state (circuit.py:199-226)
+    g = torch.Generator().manual_seed(99)
+    n = 6
+    init = torch.randn(3, 2**n, generator=g, dtype=torch.float64) + 1j * torch.randn(3, 2**n, generator=g,
+                                                                                      dtype=torch.float64)
+    init = init / init.norm(dim=-1, keepdim=True)
+    spec = wl.random_clifford_rx_spec(n, 5, seed=3)
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec)
+    cir.to(torch.double)
+    with torch.no_grad():
+        res = cir(state=init.unsqueeze(-1))
+    out['batched_n6/spec'] = np.array(json.dumps({'n': n, 'spec': spec}))
+    out['batched_n6/init'] = init.numpy()
+    out['batched_n6/c128'] = res.reshape(3, -1).numpy()
+    np.savez_compressed(os.path.join(OUT, 'circuits.npz'), **out)
+
+
+def qaoa():
+    out = {}
+    for n, p in [(6, 2), (8, 4), (10, 3)]:
+        edges, weights, layout = wl.qaoa_maxcut_structure(n, p, seed=wl.SEED + n)
+        cir = dq.QubitCircuit(n)
+        wl.build_qaoa(cir, edges, p, barriers=False)  # reference Barrier breaks .to(double)
+        cir.to(torch.double)
+        params = torch.tensor([0.1 + 0.05 * k for k in range(p)] + [1.0 - 0.1 * k for k in range(p)],
+                              dtype=torch.float64, requires_grad=True)
+        data = wl.qaoa_data(params, weights, layout)
+        state = cir(data)
+        exp = cir.expectation()
+        w = torch.tensor(weights, dtype=torch.float64)
+        loss = 0.5 * (w * (exp.reshape(-1) - 1)).sum()  # examples/qaoa.py:55-57 (negative cut value)
+        loss.backward()
+        out[f'n{n}_p{p}/meta'] = np.array(json.dumps({'n': n, 'p': p, 'edges': edges, 'weights': weights,
+                                                       'seed': wl.SEED + n}))
+        out[f'n{n}_p{p}/params'] = params.detach().numpy()
+        out[f'n{n}_p{p}/state'] = state.detach().reshape(-1).numpy()
+        out[f'n{n}_p{p}/expectation'] = exp.detach().reshape(-1).numpy()
+        out[f'n{n}_p{p}/loss'] = loss.detach().numpy()
+        out[f'n{n}_p{p}/grad'] = params.grad.numpy()
+        print('qaoa', n, p, float(loss), params.grad.tolist())
+    np.savez_compressed(os.path.join(OUT, 'qaoa.npz'), **out)
+
+
+def fock():
+    out = {}
+    for nmode, cutoff in [(2, 5), (3, 4), (4, 6), (5, 8)]:
+        spec = wl.fock_interferometer_spec(nmode, seed=wl.SEED + nmode)
+        spec.append({'g': 'ps', 'w': [0], 'p': [0.77]})
+        for double in (True, False):
+            cir = dq.QumodeCircuit(nmode, 'vac', cutoff=cutoff, backend='fock', basis=False)
+            for e in spec:
+                if e['g'] == 's':
+                    cir.s(e['w'][0], r=e['p'][0], theta=e['p'][1])
+                elif e['g'] == 'bs':
+                    cir.bs(e['w'], e['p'])
+                elif e['g'] == 'ps':
+                    cir.ps(e['w'][0], e['p'][0])
+            if double:
+                cir.to(torch.double)
+            with torch.no_grad():
+                st = cir()
+            out[f'm{nmode}_c{cutoff}/' + ('c128' if double else 'c64')] = st.reshape(-1).numpy()
+        out[f'm{nmode}_c{cutoff}/spec'] = np.array(json.dumps({'nmode': nmode, 'cutoff': cutoff, 'spec': spec}))
+        # local gate matrices (photonic/gate.py:192-194, 347-374, 1091-1114) for the oracle pin
+        s = dq.photonic.Squeezing(inputs=[0.31, 1.3], nmode=1, wires=[0], cutoff=cutoff).to(torch.double)
+        out[f'm{nmode}_c{cutoff}/s_matrix'] = s.update_matrix_state().detach().numpy()
+        b = dq.photonic.BeamSplitter(inputs=[0.6, 2.2], nmode=2, wires=[0, 1], cutoff=cutoff).to(torch.double)
+        out[f'm{nmode}_c{cutoff}/bs_matrix'] = b.update_matrix_state().detach().numpy()
+        print('fock', nmode, cutoff, float(np.linalg.norm(out[f'm{nmode}_c{cutoff}/c128'])))
+    np.savez_compressed(os.path.join(OUT, 'fock.npz'), **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock']
+    if 'gates' in which:
+        gate_matrices()
+    if 'circuits' in which:
+        circuits()
+    if 'qaoa' in which:
+        qaoa()
+    if 'fock' in which:
+        fock()

@@ -1,0 +1,21 @@
+"""deepquantum_b200 -- the DeepQuantum statevector gate-application path as hand-written sm_100a kernels.
+
+Same names as the reference package for everything on that path (`QubitCircuit`, the gate and layer
+classes, `QubitState`, `evolve_state`, `setup_distributed`, `DistributedQubitCircuit`), so
+``import deepquantum_b200 as dq`` is a drop-in for circuits that stay on the statevector path.
+Importing the package does not need the GPU; the first compute call loads `lib/libb200q.so` and
+fails loudly if it (or an sm_100 device) is missing -- there is no CPU fallback.
+"""
+__version__ = '0.1.0'
+
+from . import _lib, engine, workloads  # noqa: F401
+from ._lib import B200QError  # noqa: F401
+from .circuit import QubitCircuit  # noqa: F401
+from .gate import (Barrier, CNOT, Fredkin, Hadamard, Identity, ImaginarySwap, LatentGate, PauliX, PauliY,  # noqa: F401
+                   PauliZ, PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz,
+                   SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
+from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer,  # noqa: F401
+                    YLayer, ZLayer)
+from .operation import Gate, Layer, Operation, dtype_map  # noqa: F401
+from .qmath import evolve_state, evolve_state_controlled, inverse_permutation, multi_kron  # noqa: F401
+from .state import QubitState, amplitude_encoding  # noqa: F401

@@ -1,0 +1,69 @@
+"""Autograd through the fused engine by the adjoint (reversible) method (reference adjoint.py:19-83).
+
+The reference's single-device circuits rely on PyTorch autograd through permute/mm/cat, which saves
+one full state per gate -- impossible at 30 qubits.  Here the backward
+pass un-applies the gates from the final state while propagating the cotangent, so only three
+states are alive (psi, lambda, and the saved output).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import engine
+
+
+class ExpectationZFunction(torch.autograd.Function):
+    """[batch, n_masks] = sum_i |psi_i|^2 (-1)^popcount(i & mask)  with its exact cotangent."""
+
+    @staticmethod
+    def forward(ctx, state, nqubit, masks, batch):
+        ctx.save_for_backward(state, masks)
+        ctx.nqubit, ctx.batch = nqubit, batch
+        return engine.expectation_z(state, nqubit, masks, batch)
+
+    @staticmethod
+    def backward(ctx, grad):
+        state, masks = ctx.saved_tensors
+        # d/d(conj psi_i) of sum_k g_k sum_i |psi_i|^2 s_k(i), in PyTorch's convention (dL/dRe + i dL/dIm)
+        lam = engine.apply_z_weights(state.detach().contiguous(), ctx.nqubit, masks, 2.0 * grad.contiguous(),
+                                     ctx.batch)
+        return lam.reshape(state.shape), None, None, None
+
+
+def expectation_z(state: torch.Tensor, nqubit: int, masks: torch.Tensor, batch: int) -> torch.Tensor:
+    state = state.contiguous()
+    if torch.is_grad_enabled() and state.requires_grad:
+        return ExpectationZFunction.apply(state, nqubit, masks, batch)
+    return engine.expectation_z(state, nqubit, masks, batch)
+
+
+class CircuitFunction(torch.autograd.Function):
+    """y = U(mats) x for a whole fused program; backward by un-computation."""
+
+    @staticmethod
+    def forward(ctx, x, mats, prog, batch, mbs):
+        y = x.detach().clone()
+        md = mats.detach()
+        prog.plan(y.dtype).run(y, md, batch, mbs)
+        ctx.save_for_backward(y, md)
+        ctx.prog, ctx.batch, ctx.mbs = prog, batch, mbs
+        ctx.x_needs_grad = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        y, mats = ctx.saved_tensors
+        prog = ctx.prog
+        if ctx.batch != 1:
+            raise NotImplementedError('adjoint differentiation of batched circuits is not implemented yet')
+        plan = prog.plan(y.dtype)
+        psi = y.clone()
+        lam = grad_y.contiguous().clone()
+        grad_m = torch.zeros_like(mats)
+        lib = L.load()
+        L.check(lib.b200q_adjoint_run(plan._h, psi.data_ptr(), lam.data_ptr(), mats.data_ptr(), grad_m.data_ptr(),
+                                      None, engine._stream(psi)))
+        return (lam.reshape(grad_y.shape) if ctx.x_needs_grad else None), grad_m, None, None, None

@@ -1,0 +1,45 @@
+"""Builds lib/libb200q.so in-tree with nvcc for sm_100a (no GPU needed: nvcc cross-compiles)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIBDIR = os.path.join(HERE, 'lib')
+LIB = os.path.join(LIBDIR, 'libb200q.so')
+SOURCES = ['b200q_lib.cu', 'b200q_planner.cpp']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
+              '-shared', '--threads', '4']
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), 'include',
+                                                                              'b200q.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ['-o', LIB]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,584 @@
+"""QubitCircuit with the reference's builder / forward / expectation interface (circuit.py:81-1622),
+executed as fused passes of hand-written sm_100a kernels.
+
+`cir.h(0); cir.cnot(0, 1); cir.rx(1, 0.2); cir()` is a drop-in: the builder methods create the same
+gate modules (same names, arguments and matrices), `forward` lowers `self.operators` to a gate
+program once (cached), computes every gate matrix with a handful of vectorised torch calls (still
+differentiable), and runs the program through `libb200q.so` -- the state is read and written once
+per fused group instead of at least twice per gate (reference qmath.py:503-504).
+"""
+from __future__ import annotations
+
+from copy import copy
+from typing import Any
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import engine
+from .gate import (Barrier, CNOT, Fredkin, Hadamard, ImaginarySwap, LatentGate, PauliX, PauliY, PauliZ, PhaseShift,
+                   ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz, SDaggerGate, SGate, Swap,
+                   TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
+from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer, YLayer,
+                    ZLayer)
+from .operation import Gate, Layer, Lowering, Operation
+from .state import QubitState, amplitude_encoding
+
+# planner options used by every circuit (overridable for A/B measurements in bench.py)
+PLAN_OPTIONS = {'chunk_bits': 0, 'low_bits': 0, 'max_rounds': 0, 'fuse': True}
+
+
+class _Program:
+    """Lowered gate program of a circuit + its fused plans per dtype."""
+
+    def __init__(self, nqubit: int, ops, inverse: bool = False):
+        self.low = Lowering(nqubit)
+        seq = list(ops)
+        for op in (reversed(seq) if inverse else seq):
+            op._lower(self.low, inverse)
+        self.structs = self.low.finalize()
+        self.plans = {}
+
+    def plan(self, dtype: torch.dtype) -> engine.FusedPlan:
+        key = (dtype, tuple(sorted(PLAN_OPTIONS.items())))
+        if key not in self.plans:
+            self.plans[key] = engine.FusedPlan(self.low.nqubit, dtype, self.structs, **PLAN_OPTIONS)
+        return self.plans[key]
+
+    @property
+    def ngates(self) -> int:
+        return len(self.structs)
+
+
+class QubitCircuit(Operation):
+    """Quantum circuit on n qubits (statevector only)."""
+
+    def __init__(self, nqubit: int, init_state: Any = 'zeros', name: str | None = None, den_mat: bool = False,
+                 reupload: bool = False, mps: bool = False, chi: int | None = None, shots: int = 1024) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=None, den_mat=den_mat)
+        if mps:
+            raise NotImplementedError('the MPS back-end is outside the accelerated path (SURVEY.md section 2, #12)')
+        self.reupload = reupload
+        self.mps = mps
+        self.chi = chi
+        self.shots = shots
+        self.set_init_state(init_state)
+        self.operators = nn.Sequential()
+        self.encoders = []
+        self.observables = nn.ModuleList()
+        self.state = None
+        self.ndata = 0
+        self.depth = np.array([0] * nqubit)
+        self.wires_measure = []
+        self.wires_condition = []
+        self._program = None
+        self._program_len = -1
+
+    # ---------------------------------------------------------------------------------------------
+    def set_init_state(self, init_state: Any) -> None:
+        if isinstance(init_state, QubitState):
+            assert self.nqubit == init_state.nqubit
+            self.init_state = init_state
+        else:
+            self.init_state = QubitState(nqubit=self.nqubit, state=init_state)
+
+    def __add__(self, rhs: 'QubitCircuit') -> 'QubitCircuit':
+        assert self.nqubit == rhs.nqubit
+        cir = QubitCircuit(nqubit=self.nqubit, init_state=self.init_state, name=self.name, reupload=self.reupload)
+        cir.operators = self.operators + rhs.operators
+        cir.encoders = self.encoders + rhs.encoders
+        cir.observables = rhs.observables
+        cir.npara = self.npara + rhs.npara
+        cir.ndata = self.ndata + rhs.ndata
+        cir.depth = self.depth + rhs.depth
+        cir.wires_measure = rhs.wires_measure
+        return cir
+
+    # ---------------------------------------------------------------------------------------------
+    def _get_program(self) -> _Program:
+        if self._program is None or self._program_len != len(self.operators):
+            self._program = _Program(self.nqubit, self.operators)
+            self._program_len = len(self.operators)
+        return self._program
+
+    def forward(self, data: torch.Tensor | None = None, state: Any = None) -> torch.Tensor:
+        """Run the circuit; returns the final state `[2^n, 1]` (or `[batch, 2^n, 1]`), like the reference
+        (circuit.py:180-242).  2-D `data` is an explicit batch (the reference uses `vmap` here)."""
+        if state is None:
+            state = self.init_state
+        lazy_zero = isinstance(state, QubitState) and state.kind == 'zeros'
+        if lazy_zero:   # never materialise |0...0>: the engine fills it with a kernel
+            state_t = torch.empty(0, 1, dtype=state.dtype, device=state.device)
+        else:
+            state_t = state.state if isinstance(state, QubitState) else state
+        if self.ndata == 0:
+            data = None
+        if data is None or data.ndim == 1:
+            self.encode(data)
+            out = self._run(state_t, None, lazy_zero)
+        else:
+            assert data.ndim == 2
+            assert lazy_zero or state_t.ndim in (2, 3)
+            self._encode_batched(data)
+            try:
+                out = self._run(state_t, data.shape[0], lazy_zero)
+            finally:
+                for op in self.encoders:
+                    for g in (op.gates if isinstance(op, Layer) else [op]):
+                        g._batched = None
+            self.encode(data[-1])
+        self.state = out
+        return out
+
+    def _run(self, state_t: torch.Tensor, data_batch: int | None, lazy_zero: bool) -> torch.Tensor:
+        n = self.nqubit
+        engine.require_cuda(state_t, 'the circuit state (move the circuit with cir.to("cuda"))')
+        cdtype = state_t.dtype
+        prog = self._get_program()
+        mats = prog.low.build_matrices(cdtype, state_t.device)
+        batched_state = state_t.ndim == 3 and not lazy_zero
+        nb_state = state_t.shape[0] if batched_state else 1
+        batch = data_batch if data_batch is not None else nb_state
+        if data_batch is not None and batched_state:
+            assert nb_state == data_batch
+        if lazy_zero:
+            x = torch.empty(batch, 2**n, dtype=cdtype, device=state_t.device)
+            engine.init_basis_(x, n, batch, 0)
+        else:
+            x = state_t.reshape(nb_state, 2**n)
+            if nb_state != batch:
+                x = x.expand(batch, -1)
+            x = x.contiguous()
+        mbs = mats.shape[-1] if mats.ndim == 2 else 0
+        if mats.ndim == 2 and mats.shape[0] != batch:
+            raise ValueError('batch of data and batch of states differ')
+        if torch.is_grad_enabled() and (mats.requires_grad or x.requires_grad):
+            from .adjoint import CircuitFunction
+            y = CircuitFunction.apply(x, mats, prog, batch, mbs)
+        else:
+            y = x if lazy_zero else x.clone()
+            prog.plan(cdtype).run(y, mats, batch, mbs)
+        y = y.reshape(batch, 2**n, 1)
+        if data_batch is None and not batched_state:
+            y = y.squeeze(0)
+        return y
+
+    # ---------------------------------------------------------------------------------------------
+    def encode(self, data: torch.Tensor | None) -> None:
+        """Route `data` slices into the encoder gates (reference circuit.py:265-293)."""
+        if data is None:
+            return
+        if not self.reupload:
+            assert len(data) >= self.ndata, 'The circuit needs more data, or consider data re-uploading'
+        count = 0
+        for op in self.encoders:
+            count_up = count + op.npara
+            if self.reupload and count_up > len(data):
+                n = int(np.ceil(count_up / len(data)))
+                op.init_para(torch.cat([data] * n)[count:count_up])
+            else:
+                op.init_para(data[count:count_up])
+            count = count_up % len(data)
+
+    def _encode_batched(self, data: torch.Tensor) -> None:
+        """2-D data: every encoder gate gets a `[batch, npara]` column block (explicit batch instead of the
+        reference's vmap, circuit.py:227-241)."""
+        width = data.shape[1]
+        if not self.reupload:
+            assert width >= self.ndata, 'The circuit needs more data, or consider data re-uploading'
+        count = 0
+        for op in self.encoders:
+            gates = op.gates if isinstance(op, Layer) else [op]
+            for g in gates:
+                count_up = count + g.npara
+                if count_up > width:
+                    idx = [i % width for i in range(count, count_up)]
+                    g._batched = data[:, idx]
+                else:
+                    g._batched = data[:, count:count_up]
+                count = count_up % width
+
+    def init_para(self) -> None:
+        for op in self.operators:
+            op.init_para()
+
+    def init_encoder(self) -> None:
+        for op in self.encoders:
+            op.init_para()
+
+    def reset_circuit(self, init_state: Any = 'zeros') -> None:
+        self.set_init_state(init_state)
+        self.operators = nn.Sequential()
+        self.encoders = []
+        self.observables = nn.ModuleList()
+        self.state = None
+        self.ndata = 0
+        self.npara = 0
+        self.depth = np.array([0] * self.nqubit)
+        self.wires_measure = []
+        self._program = None
+
+    def amplitude_encoding(self, data: Any) -> torch.Tensor:
+        return amplitude_encoding(data, self.nqubit)
+
+    # ---------------------------------------------------------------------------------------------
+    def observable(self, wires=None, basis: str = 'z') -> None:
+        self.observables.append(Observable(nqubit=self.nqubit, wires=wires, basis=basis, tsr_mode=False))
+
+    def reset_observable(self) -> None:
+        self.observables = nn.ModuleList()
+
+    def expectation(self, shots: int | None = None) -> torch.Tensor:
+        """Exact expectation values of the Pauli-string observables on the final state: `[n_obs]` or
+        `[batch, n_obs]` (reference circuit.py:381-428, qmath.py:830-860).  Z-strings are reduced by ONE fused
+        kernel pass over the state for all observables; X/Y factors are rotated to Z on a copy first."""
+        assert len(self.observables) > 0, 'There is no observable'
+        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        if shots is not None:
+            raise NotImplementedError('sampled expectation values are outside the accelerated path')
+        from .adjoint import expectation_z
+        n = self.nqubit
+        st = self.state
+        batched = st.ndim == 3
+        flat = st.reshape(-1, 2**n)
+        batch = flat.shape[0]
+        groups = {}
+        for k, ob in enumerate(self.observables):
+            rot = tuple(sorted((w[0], b) for w, b in zip(ob.wires, ob.basis) if b != 'z'))
+            mask = 0
+            for w in ob.wires:
+                mask |= 1 << (n - 1 - w[0])
+            groups.setdefault(rot, []).append((k, mask))
+        out = [None] * len(self.observables)
+        for rot, items in groups.items():
+            phi = flat
+            if rot:
+                basis_cir = QubitCircuit(n)
+                for w, b in rot:
+                    if b == 'y':
+                        basis_cir.sdg(w)
+                    basis_cir.h(w)
+                basis_cir.to(flat.device, flat.real.dtype)
+                phi = basis_cir(state=flat.reshape(batch, 2**n, 1)).reshape(batch, 2**n)
+            masks = torch.tensor([m for _, m in items], dtype=torch.int64, device=flat.device)
+            vals = expectation_z(phi, n, masks, batch)           # [batch, n_items] float64
+            for j, (k, _) in enumerate(items):
+                out[k] = vals[:, j]
+        res = torch.stack(out, dim=-1).to(flat.real.dtype)
+        return res if batched else res.squeeze(0)
+
+    def measure(self, shots: int | None = None, with_prob: bool = False, wires=None, block_size: int = 2**24):
+        """Sampling (reference circuit.py:338-379 / qmath.py:568-638) is the step AFTER the hot path
+        (SURVEY.md section 8f); provided with plain torch ops for API completeness at moderate n."""
+        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        shots = self.shots if shots is None else shots
+        n = self.nqubit
+        wires = list(range(n)) if wires is None else self._convert_indices(wires)
+        self.wires_measure = wires
+        flat = self.state.reshape(-1, 2**n)
+        results = []
+        for b in range(flat.shape[0]):
+            probs = (flat[b].real**2 + flat[b].imag**2).double()
+            probs = probs.reshape([2] * n)
+            keep = sorted(wires)
+            drop = [i for i in range(n) if i not in keep]
+            if drop:
+                probs = probs.sum(dim=drop)
+            perm = [keep.index(w) for w in wires]
+            probs = probs.permute(perm).reshape(-1)
+            idx = torch.multinomial(probs / probs.sum(), shots, replacement=True)
+            vals, counts = torch.unique(idx, return_counts=True)
+            d = {}
+            for v, c in zip(vals.tolist(), counts.tolist()):
+                key = format(v, f'0{len(wires)}b')
+                d[key] = (c, float(probs[v])) if with_prob else c
+            results.append(d)
+        return results[0] if self.state.ndim == 2 else results
+
+    def get_unitary(self) -> torch.Tensor:
+        """Global unitary (small n): the circuit applied to the identity (reference circuit.py:467-477)."""
+        dim = 2**self.nqubit
+        ref = self.init_state.state
+        eye = torch.eye(dim, dtype=ref.dtype, device=ref.device)
+        prog = self._get_program()
+        mats = prog.low.build_matrices(eye.dtype, eye.device)
+        y = eye.contiguous().clone()
+        prog.plan(eye.dtype).run(y, mats, dim, 0)
+        return y.T
+
+    def get_amplitude(self, bits: str) -> torch.Tensor:
+        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        assert len(bits) == self.nqubit
+        idx = int(bits, 2)
+        return self.state.reshape(-1, 2**self.nqubit)[:, idx].squeeze(0) if self.state.ndim == 3 else \
+            self.state.reshape(-1)[idx]
+
+    def get_prob(self, bits: str, wires=None) -> torch.Tensor:
+        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        n = self.nqubit
+        wires = list(range(n)) if wires is None else self._convert_indices(wires)
+        assert len(bits) == len(wires)
+        flat = self.state.reshape(-1, *([2] * n))
+        sel = [slice(None)] * (n + 1)
+        for w, b in zip(wires, bits):
+            sel[w + 1] = int(b)
+        sub = flat[tuple(sel)].reshape(flat.shape[0], -1)
+        p = (sub.real**2 + sub.imag**2).sum(-1)
+        return p if self.state.ndim == 3 else p.squeeze(0)
+
+    def inverse(self, encode: bool = False) -> 'QubitCircuit':
+        """Inverse circuit (reference circuit.py:530-555): reversed operators, each `op.inverse()`."""
+        cir = QubitCircuit(nqubit=self.nqubit, name=self.name, reupload=self.reupload)
+        for op in reversed(self.operators):
+            op_inv = op.inverse()
+            cir.operators.append(op_inv)
+            if encode and op in self.encoders:
+                cir.encoders.append(op_inv)
+        cir.npara, cir.ndata = (self.npara, self.ndata) if encode else (self.npara + self.ndata, 0)
+        cir.depth = self.depth.copy()
+        ref = self.init_state.state
+        cir.to(ref.device, ref.real.dtype)
+        return cir
+
+    def max_depth(self) -> int:
+        return int(max(self.depth))
+
+    # ---------------------------------------------------------------------------------------------
+    def add(self, op: Operation, encode: bool = False, wires=None, controls=None) -> None:
+        """Append a gate, a layer or another circuit (reference circuit.py:820-897)."""
+        assert isinstance(op, Operation)
+        self._program = None
+        if wires is not None:
+            assert isinstance(op, Gate)
+            controls = [] if controls is None else controls
+            wires = self._convert_indices(wires)
+            controls = self._convert_indices(controls)
+            for wire in wires:
+                assert wire not in controls, 'Use repeated wires'
+            assert len(wires) == len(op.wires), 'Invalid input'
+            op = copy(op)
+            op.wires = wires
+            op.controls = controls
+        if isinstance(op, QubitCircuit):
+            assert self.nqubit == op.nqubit
+            self.operators += op.operators
+            self.encoders += op.encoders
+            self.observables = op.observables
+            self.npara += op.npara
+            self.ndata += op.ndata
+            self.depth += op.depth
+            self.wires_measure = op.wires_measure
+            return
+        op.tsr_mode = True
+        if isinstance(op, Gate):
+            self.operators.append(op)
+            for i in op.wires + op.controls:
+                self.depth[i] += 1
+        elif isinstance(op, Layer):
+            self.operators.extend(op.gates)
+            for wire in op.wires:
+                for i in wire:
+                    self.depth[i] += 1
+        else:
+            raise NotImplementedError(f'{type(op).__name__} is outside the accelerated statevector path')
+        if encode:
+            assert not op.requires_grad, 'Please set requires_grad of the operation to be False'
+            self.encoders.append(op)
+            self.ndata += op.npara
+        else:
+            self.npara += op.npara
+
+    # ---- builders (reference circuit.py:899-1622) ------------------------------------------------
+    def _fixed(self, cls, wires, controls=None, condition=False):
+        self.add(cls(nqubit=self.nqubit, wires=wires, controls=controls, condition=condition))
+
+    def _param(self, cls, wires, inputs, controls=None, condition=False, encode=False, **kw):
+        requires_grad = (not encode) and inputs is None
+        self.add(cls(inputs=inputs, nqubit=self.nqubit, wires=wires, controls=controls, condition=condition,
+                     requires_grad=requires_grad, **kw), encode=encode)
+
+    def u3(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(U3Gate, wires, inputs, controls, condition, encode)
+
+    def cu(self, control, target, inputs=None, encode=False):
+        self._param(U3Gate, [target], inputs, [control], False, encode)
+
+    def p(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(PhaseShift, wires, inputs, controls, condition, encode)
+
+    def cp(self, control, target, inputs=None, encode=False):
+        self._param(PhaseShift, [target], inputs, [control], False, encode)
+
+    def x(self, wires, controls=None, condition=False):
+        self._fixed(PauliX, wires, controls, condition)
+
+    def y(self, wires, controls=None, condition=False):
+        self._fixed(PauliY, wires, controls, condition)
+
+    def z(self, wires, controls=None, condition=False):
+        self._fixed(PauliZ, wires, controls, condition)
+
+    def h(self, wires, controls=None, condition=False):
+        self._fixed(Hadamard, wires, controls, condition)
+
+    def s(self, wires, controls=None, condition=False):
+        self._fixed(SGate, wires, controls, condition)
+
+    def sdg(self, wires, controls=None, condition=False):
+        self._fixed(SDaggerGate, wires, controls, condition)
+
+    def t(self, wires, controls=None, condition=False):
+        self._fixed(TGate, wires, controls, condition)
+
+    def tdg(self, wires, controls=None, condition=False):
+        self._fixed(TDaggerGate, wires, controls, condition)
+
+    def ch(self, control, target):
+        self._fixed(Hadamard, [target], [control])
+
+    def cs(self, control, target):
+        self._fixed(SGate, [target], [control])
+
+    def csdg(self, control, target):
+        self._fixed(SDaggerGate, [target], [control])
+
+    def ct(self, control, target):
+        self._fixed(TGate, [target], [control])
+
+    def ctdg(self, control, target):
+        self._fixed(TDaggerGate, [target], [control])
+
+    def rx(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Rx, wires, inputs, controls, condition, encode)
+
+    def ry(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Ry, wires, inputs, controls, condition, encode)
+
+    def rz(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Rz, wires, inputs, controls, condition, encode)
+
+    def crx(self, control, target, inputs=None, encode=False):
+        self._param(Rx, [target], inputs, [control], False, encode)
+
+    def cry(self, control, target, inputs=None, encode=False):
+        self._param(Ry, [target], inputs, [control], False, encode)
+
+    def crz(self, control, target, inputs=None, encode=False):
+        self._param(Rz, [target], inputs, [control], False, encode)
+
+    def j(self, wires, inputs=None, plane='xy', controls=None, condition=False, encode=False):
+        self._param(ProjectionJ, wires, inputs, controls, condition, encode, plane=plane)
+
+    def cnot(self, control, target):
+        self.add(CNOT(nqubit=self.nqubit, wires=[control, target]))
+
+    def cx(self, control, target):
+        self._fixed(PauliX, [target], [control])
+
+    def cy(self, control, target):
+        self._fixed(PauliY, [target], [control])
+
+    def cz(self, control, target):
+        self._fixed(PauliZ, [target], [control])
+
+    def swap(self, wires, controls=None, condition=False):
+        self._fixed(Swap, wires, controls, condition)
+
+    def iswap(self, wires, controls=None, condition=False):
+        self._fixed(ImaginarySwap, wires, controls, condition)
+
+    def rxx(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Rxx, wires, inputs, controls, condition, encode)
+
+    def ryy(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Ryy, wires, inputs, controls, condition, encode)
+
+    def rzz(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Rzz, wires, inputs, controls, condition, encode)
+
+    def rxy(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(Rxy, wires, inputs, controls, condition, encode)
+
+    def rbs(self, wires, inputs=None, controls=None, condition=False, encode=False):
+        self._param(ReconfigurableBeamSplitter, wires, inputs, controls, condition, encode)
+
+    def crxx(self, control, target1, target2, inputs=None, encode=False):
+        self._param(Rxx, [target1, target2], inputs, [control], False, encode)
+
+    def cryy(self, control, target1, target2, inputs=None, encode=False):
+        self._param(Ryy, [target1, target2], inputs, [control], False, encode)
+
+    def crzz(self, control, target1, target2, inputs=None, encode=False):
+        self._param(Rzz, [target1, target2], inputs, [control], False, encode)
+
+    def crxy(self, control, target1, target2, inputs=None, encode=False):
+        self._param(Rxy, [target1, target2], inputs, [control], False, encode)
+
+    def toffoli(self, control1, control2, target):
+        self.add(Toffoli(nqubit=self.nqubit, wires=[control1, control2, target]))
+
+    def ccx(self, control1, control2, target):
+        self._fixed(PauliX, [target], [control1, control2])
+
+    def fredkin(self, control, target1, target2):
+        self.add(Fredkin(nqubit=self.nqubit, wires=[control, target1, target2]))
+
+    def cswap(self, control, target1, target2):
+        self._fixed(Swap, [target1, target2], [control])
+
+    def any(self, unitary, wires=None, minmax=None, controls=None, name='uany'):
+        self.add(UAnyGate(unitary=unitary, nqubit=self.nqubit, wires=wires, minmax=minmax, controls=controls,
+                          name=name))
+
+    def latent(self, wires=None, minmax=None, inputs=None, controls=None, encode=False, name='latent'):
+        requires_grad = (not encode) and inputs is None
+        self.add(LatentGate(inputs=inputs, nqubit=self.nqubit, wires=wires, minmax=minmax, controls=controls,
+                            name=name, requires_grad=requires_grad), encode=encode)
+
+    def hamiltonian(self, *args, **kwargs):
+        raise NotImplementedError('HamiltonianGate is not part of the accelerated path yet (SURVEY.md section 8f)')
+
+    def _const_layer(self, cls, wires):
+        self.add(cls(nqubit=self.nqubit, wires=wires))
+
+    def _param_layer(self, cls, wires, inputs, encode):
+        requires_grad = (not encode) and inputs is None
+        self.add(cls(nqubit=self.nqubit, wires=wires, inputs=inputs, requires_grad=requires_grad), encode=encode)
+
+    def xlayer(self, wires=None):
+        self._const_layer(XLayer, wires)
+
+    def ylayer(self, wires=None):
+        self._const_layer(YLayer, wires)
+
+    def zlayer(self, wires=None):
+        self._const_layer(ZLayer, wires)
+
+    def hlayer(self, wires=None):
+        self._const_layer(HLayer, wires)
+
+    def rxlayer(self, wires=None, inputs=None, encode=False):
+        self._param_layer(RxLayer, wires, inputs, encode)
+
+    def rylayer(self, wires=None, inputs=None, encode=False):
+        self._param_layer(RyLayer, wires, inputs, encode)
+
+    def rzlayer(self, wires=None, inputs=None, encode=False):
+        self._param_layer(RzLayer, wires, inputs, encode)
+
+    def u3layer(self, wires=None, inputs=None, encode=False):
+        self._param_layer(U3Layer, wires, inputs, encode)
+
+    def cxlayer(self, wires=None):
+        self.add(CnotLayer(nqubit=self.nqubit, wires=wires))
+
+    def cnot_ring(self, minmax=None, step=1, reverse=False):
+        self.add(CnotRing(nqubit=self.nqubit, minmax=minmax, step=step, reverse=reverse))
+
+    def barrier(self, wires=None):
+        self.add(Barrier(nqubit=self.nqubit, wires=wires))
+
+    def reset(self, *args, **kwargs):
+        raise NotImplementedError('Reset is non-unitary and outside the accelerated path')

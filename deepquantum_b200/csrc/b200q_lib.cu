@@ -1,0 +1,488 @@
+// sm_100a kernels and the extern "C" entry points declared in include/b200q.h.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200q.h"
+#include "b200q_planner.h"
+#include "b200q_tile_body.h"
+
+using namespace b200q;
+
+struct b200q_plan {
+  Plan* p;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_err(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused tile kernel
+// ------------------------------------------------------------------------------------------------
+template <int CB> struct TileCfg {
+  static constexpr int kThreads = 1 << (CB - B200Q_REG_CHUNK_BITS);
+  static constexpr int kMinBlocks = CB >= 13 ? 1 : (CB == 12 ? 2 : 4);
+};
+
+template <typename Real, int CB>
+__global__ void __launch_bounds__(TileCfg<CB>::kThreads, TileCfg<CB>::kMinBlocks)
+b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ state,
+                  const cx<Real>* __restrict__ mats, uint64_t chunks_per_state, int64_t mat_batch_stride) {
+  using chunk = typename Traits<Real>::chunk;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  chunk* tile = reinterpret_cast<chunk*>(smem_raw);
+  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(16) << CB));
+  const int tid = threadIdx.x;
+  const int nthreads = TileCfg<CB>::kThreads;
+  const uint64_t cta_base = tile_base(P, blockIdx.x);
+  chunk* gstate = state + uint64_t(blockIdx.y) * chunks_per_state;
+  const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
+
+  if (P.pool_elems) {
+    fill_pool<Real>(P, tid, nthreads, pool, m);
+    __syncthreads();
+  }
+  const int nr = P.n_rounds;
+  for (int r = 0; r < nr; ++r) {
+    const b200q_round_t& Rd = P.rounds[r];
+    if (Rd.direct) {
+      for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
+        run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile, pool);
+        __syncthreads();
+      }
+    } else {
+      run_round<Real>(P, Rd, tid, cta_base, tile, pool, gstate, chunks_per_state);
+      if (r + 1 < nr) __syncthreads();
+    }
+  }
+}
+
+template <typename Real, int CB>
+int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubits, int64_t batch,
+                int64_t mat_batch_stride, cudaStream_t stream) {
+  using chunk = typename Traits<Real>::chunk;
+  constexpr int VS = Traits<Real>::VS;
+  const size_t smem = (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>);
+  auto kern = b200q_tile_kernel<Real, CB>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute");
+    if (rc) return rc;
+    attr_set[dev] = true;
+  }
+  const uint64_t chunks_per_state = (1ull << n_qubits) >> VS;
+  const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
+  if (ntiles > 0x7fffffffull) return set_err(B200Q_EUNSUPPORTED, "too many tiles for one launch");
+  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, batch - b0);
+    dim3 grid((unsigned)ntiles, (unsigned)nb, 1);
+    kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(
+        P, reinterpret_cast<chunk*>(state) + uint64_t(b0) * chunks_per_state,
+        reinterpret_cast<const cx<Real>*>(mats) + b0 * mat_batch_stride, chunks_per_state, mat_batch_stride);
+  }
+  return cuda_err(cudaGetLastError(), "tile kernel launch");
+}
+
+int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const void* mats, int64_t batch,
+                    int64_t mbs, cudaStream_t stream) {
+  const int cb = pl.opt.chunk_bits;
+  if (pl.dtype == B200Q_C64) {
+    switch (cb) {
+      case 11: return launch_pass<float, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 12: return launch_pass<float, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 13: return launch_pass<float, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+    }
+  } else {
+    switch (cb) {
+      case 11: return launch_pass<double, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 12: return launch_pass<double, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 13: return launch_pass<double, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+    }
+  }
+  return set_err(B200Q_EUNSUPPORTED, "chunk_bits must be 11, 12 or 13");
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum_atomic(double (&v)[NV], double* out) {
+  __shared__ double sh[NV][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) sh[k][w] = s;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = lane < nw ? sh[k][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) atomicAdd(out + k, s);
+    }
+  }
+}
+
+// grid: (blocks, batch).  Real2 = float2 / double2 amplitudes.
+template <typename Real>
+__global__ void __launch_bounds__(256) norm2_kernel(const cx<Real>* __restrict__ st, uint64_t n_amps, double* out) {
+  const cx<Real>* s = st + uint64_t(blockIdx.y) * n_amps;
+  double acc[1] = {0.0};
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += uint64_t(gridDim.x) * blockDim.x) {
+    const cx<Real> a = s[i];
+    acc[0] += double(a.x) * double(a.x) + double(a.y) * double(a.y);
+  }
+  block_sum_atomic<1>(acc, out + blockIdx.y);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+inner_kernel(const cx<Real>* __restrict__ bra, const cx<Real>* __restrict__ ket, uint64_t n_amps, double* out) {
+  const cx<Real>* a = bra + uint64_t(blockIdx.y) * n_amps;
+  const cx<Real>* b = ket + uint64_t(blockIdx.y) * n_amps;
+  double acc[2] = {0.0, 0.0};
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += uint64_t(gridDim.x) * blockDim.x) {
+    const cx<Real> x = a[i], y = b[i];
+    acc[0] += double(x.x) * double(y.x) + double(x.y) * double(y.y);  // conj(x) * y
+    acc[1] += double(x.x) * double(y.y) - double(x.y) * double(y.x);
+  }
+  block_sum_atomic<2>(acc, out + 2 * blockIdx.y);
+}
+
+// Z-string expectations.  Each thread strides over amplitudes; masks are processed in groups of 8
+// accumulators so the state is re-read once per 8 masks only when n_masks > 8 (L2 absorbs nothing at
+// 2^30 amplitudes, hence the grouping is done INSIDE the amplitude loop: |a|^2 is computed once).
+constexpr int kZGroup = 16;
+template <typename Real>
+__global__ void __launch_bounds__(256)
+expz_kernel(const cx<Real>* __restrict__ st, uint64_t n_amps, const uint64_t* __restrict__ masks, int n_masks,
+            int mask0, uint64_t index_offset, double* out) {
+  const cx<Real>* s = st + uint64_t(blockIdx.y) * n_amps;
+  uint64_t mk[kZGroup];
+#pragma unroll
+  for (int k = 0; k < kZGroup; ++k) mk[k] = (mask0 + k < n_masks) ? masks[mask0 + k] : 0ull;
+  double acc[kZGroup];
+#pragma unroll
+  for (int k = 0; k < kZGroup; ++k) acc[k] = 0.0;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += uint64_t(gridDim.x) * blockDim.x) {
+    const cx<Real> a = s[i];
+    const double p = double(a.x) * double(a.x) + double(a.y) * double(a.y);
+    const uint64_t idx = i | index_offset;
+#pragma unroll
+    for (int k = 0; k < kZGroup; ++k) acc[k] += (__popcll(idx & mk[k]) & 1) ? -p : p;
+  }
+  double* o = out + uint64_t(blockIdx.y) * n_masks + mask0;
+  __shared__ double sh[kZGroup][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kZGroup; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sh[k][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kZGroup && mask0 + (int)threadIdx.x < n_masks) {
+    double v = 0.0;
+    for (int j = 0; j < 8; ++j) v += sh[threadIdx.x][j];
+    atomicAdd(o + threadIdx.x, v);
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+zweights_kernel(const cx<Real>* __restrict__ st, cx<Real>* __restrict__ lam, uint64_t n_amps,
+                const uint64_t* __restrict__ masks, const double* __restrict__ weights, int n_masks,
+                uint64_t index_offset) {
+  extern __shared__ unsigned char zw_raw[];
+  uint64_t* smk = reinterpret_cast<uint64_t*>(zw_raw);
+  double* sw = reinterpret_cast<double*>(smk + n_masks);
+  for (int k = threadIdx.x; k < n_masks; k += blockDim.x) {
+    smk[k] = masks[k];
+    sw[k] = weights[uint64_t(blockIdx.y) * n_masks + k];
+  }
+  __syncthreads();
+  const cx<Real>* s = st + uint64_t(blockIdx.y) * n_amps;
+  cx<Real>* l = lam + uint64_t(blockIdx.y) * n_amps;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t idx = i | index_offset;
+    double f = 0.0;
+    for (int k = 0; k < n_masks; ++k) f += (__popcll(idx & smk[k]) & 1) ? -sw[k] : sw[k];
+    const cx<Real> a = s[i];
+    cx<Real> r;
+    r.x = Real(double(a.x) * f);
+    r.y = Real(double(a.y) * f);
+    l[i] = r;
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) init_basis_kernel(cx<Real>* st, uint64_t n_amps, uint64_t basis) {
+  cx<Real>* s = st + uint64_t(blockIdx.y) * n_amps;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_amps; i += uint64_t(gridDim.x) * blockDim.x) {
+    cx<Real> v;
+    v.x = (i == basis) ? Real(1) : Real(0);
+    v.y = Real(0);
+    s[i] = v;
+  }
+}
+
+inline unsigned reduce_blocks(uint64_t n_amps) {
+  const uint64_t want = (n_amps + 256 * 8 - 1) / (256 * 8);
+  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, 148ull * 8));
+}
+
+int check_state_args(const void* state, int n_qubits, int dtype, int64_t batch) {
+  if (!state) return set_err(B200Q_EINVAL, "null state pointer");
+  if (n_qubits < 1 || n_qubits > B200Q_MAX_QUBITS - 2) return set_err(B200Q_EINVAL, "n_qubits out of range");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return set_err(B200Q_EINVAL, "bad dtype");
+  if (batch < 1 || batch > 65535) return set_err(B200Q_EINVAL, "batch must be in 1..65535");
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+const char* b200q_version(void) { return "b200q 0.1.0 (sm_100a)"; }
+const char* b200q_last_error(void) { return g_err.c_str(); }
+
+int b200q_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_err(B200Q_ENODEVICE, "no CUDA device visible; b200q has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return set_err(B200Q_ENODEVICE, "device index out of range");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (major != 10) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "device %d is sm_%d%d; b200q is built for sm_100a only", device, major, minor);
+    return set_err(B200Q_ENODEVICE, buf);
+  }
+  return 0;
+}
+
+int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
+                      const b200q_plan_options_t* options, b200q_plan_t** plan_out) {
+  if (!plan_out) return set_err(B200Q_EINVAL, "plan_out is null");
+  *plan_out = nullptr;
+  PlanOptions opt;
+  if (options) {
+    if (options->chunk_bits) opt.chunk_bits = options->chunk_bits;
+    if (options->low_bits) opt.low_bits = options->low_bits;
+    if (options->max_rounds) opt.max_rounds = options->max_rounds;
+    opt.fuse = options->fuse;
+  }
+  if (opt.chunk_bits < 11 || opt.chunk_bits > 13) return set_err(B200Q_EINVAL, "chunk_bits must be 11, 12 or 13");
+  std::string err;
+  Plan* p = make_plan(n_qubits, dtype, gates, n_gates, opt, &err);
+  if (!p) return set_err(B200Q_EINVAL, err);
+  *plan_out = new b200q_plan{p};
+  return 0;
+}
+
+void b200q_plan_destroy(b200q_plan_t* plan) {
+  if (!plan) return;
+  delete plan->p;
+  delete plan;
+}
+
+int b200q_plan_get_stats(const b200q_plan_t* plan, b200q_plan_stats_t* s) {
+  if (!plan || !s) return set_err(B200Q_EINVAL, "null argument");
+  const Plan& p = *plan->p;
+  s->n_gates = p.stats.n_gates;
+  s->n_passes = p.stats.n_passes;
+  s->n_rounds = p.stats.n_rounds;
+  s->n_ops = p.stats.n_ops;
+  s->n_direct_ops = p.stats.n_direct;
+  s->tile_bits = std::min(p.opt.chunk_bits + (p.dtype == B200Q_C64 ? 1 : 0), p.n_bits);
+  s->threads_per_cta = 1 << (p.opt.chunk_bits - B200Q_REG_CHUNK_BITS);
+  s->smem_bytes = (16 << p.opt.chunk_bits) + B200Q_POOL_MAX * (p.dtype == B200Q_C64 ? 8 : 16);
+  return 0;
+}
+
+int b200q_plan_pass_gates(const b200q_plan_t* plan, int i) {
+  if (!plan || i < 0 || i >= (int)plan->p->passes.size()) return set_err(B200Q_EINVAL, "bad pass index");
+  return plan->p->pass_gate_count[i];
+}
+
+int b200q_plan_export(const b200q_plan_t* plan, void* buf, size_t buf_size, size_t* needed) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  const size_t need = plan->p->passes.size() * sizeof(b200q_pass_t);
+  if (needed) *needed = need;
+  if (buf && buf_size >= need && need) std::memcpy(buf, plan->p->passes.data(), need);
+  return 0;
+}
+
+int b200q_plan_run_range(const b200q_plan_t* plan, int first, int last, void* state, const void* matrices,
+                         int64_t batch, int64_t mbs, void* stream) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  const Plan& p = *plan->p;
+  int rc = check_state_args(state, p.n_qubits, p.dtype, batch);
+  if (rc) return rc;
+  if (first < 0 || last > (int)p.passes.size() || first > last) return set_err(B200Q_EINVAL, "bad pass range");
+  if (!matrices && p.stats.n_ops) {
+    bool need = false;
+    for (const auto& ps : p.passes) need |= ps.pool_elems != 0;
+    if (need) return set_err(B200Q_EINVAL, "null matrix buffer");
+  }
+  for (int i = first; i < last; ++i) {
+    rc = launch_pass_any(p, p.passes[i], state, matrices, batch, mbs, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200q_plan_run(const b200q_plan_t* plan, void* state, const void* matrices, int64_t batch, int64_t mbs,
+                   void* stream) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  return b200q_plan_run_range(plan, 0, (int)plan->p->passes.size(), state, matrices, batch, mbs, stream);
+}
+
+int b200q_apply_gate(void* state, int n_qubits, int dtype, int kind, const void* matrix, const int32_t* targets,
+                     int n_targets, const int32_t* controls, int n_controls, int adjoint, int64_t batch, int64_t mbs,
+                     void* stream) {
+  int rc = check_state_args(state, n_qubits, dtype, batch);
+  if (rc) return rc;
+  if (!targets || n_targets < 1 || n_targets > B200Q_MAX_TARGETS) return set_err(B200Q_EINVAL, "bad targets");
+  if (n_controls < 0 || (n_controls > 0 && !controls)) return set_err(B200Q_EINVAL, "bad controls");
+  b200q_gate_t g;
+  std::memset(&g, 0, sizeof g);
+  g.kind = kind;
+  g.n_targets = n_targets;
+  for (int j = 0; j < n_targets; ++j) g.targets[j] = targets[j];
+  for (int j = 0; j < n_controls; ++j) {
+    if (controls[j] < 0 || controls[j] >= n_qubits) return set_err(B200Q_EINVAL, "control out of range");
+    g.controls |= 1ull << controls[j];
+  }
+  g.flags = adjoint ? B200Q_GATE_ADJOINT : 0;
+  PlanOptions opt;
+  std::string err;
+  Plan* p = make_plan(n_qubits, dtype, &g, 1, opt, &err);
+  if (!p) return set_err(B200Q_EINVAL, err);
+  for (const auto& ps : p->passes) {
+    rc = launch_pass_any(*p, ps, state, matrix, batch, mbs, (cudaStream_t)stream);
+    if (rc) break;
+  }
+  delete p;
+  return rc;
+}
+
+#define B200Q_DISPATCH_REAL(dtype, CALL)          \
+  do {                                            \
+    if ((dtype) == B200Q_C64) { using Real = float; CALL; } \
+    else { using Real = double; CALL; }           \
+  } while (0)
+
+int b200q_norm2(const void* state, int n_qubits, int dtype, int64_t batch, double* out_dev, void* stream) {
+  int rc = check_state_args(state, n_qubits, dtype, batch);
+  if (rc) return rc;
+  if (!out_dev) return set_err(B200Q_EINVAL, "null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t n = 1ull << n_qubits;
+  rc = cuda_err(cudaMemsetAsync(out_dev, 0, sizeof(double) * batch, s), "memset");
+  if (rc) return rc;
+  dim3 grid(reduce_blocks(n), (unsigned)batch);
+  B200Q_DISPATCH_REAL(dtype, (norm2_kernel<Real><<<grid, 256, 0, s>>>((const cx<Real>*)state, n, out_dev)));
+  return cuda_err(cudaGetLastError(), "norm2 launch");
+}
+
+int b200q_inner_product(const void* bra, const void* ket, int n_qubits, int dtype, int64_t batch, double* out_dev,
+                        void* stream) {
+  int rc = check_state_args(bra, n_qubits, dtype, batch);
+  if (rc) return rc;
+  if (!ket || !out_dev) return set_err(B200Q_EINVAL, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t n = 1ull << n_qubits;
+  rc = cuda_err(cudaMemsetAsync(out_dev, 0, 2 * sizeof(double) * batch, s), "memset");
+  if (rc) return rc;
+  dim3 grid(reduce_blocks(n), (unsigned)batch);
+  B200Q_DISPATCH_REAL(dtype, (inner_kernel<Real><<<grid, 256, 0, s>>>((const cx<Real>*)bra, (const cx<Real>*)ket, n,
+                                                                      out_dev)));
+  return cuda_err(cudaGetLastError(), "inner product launch");
+}
+
+int b200q_expectation_z(const void* state, int n_qubits, int dtype, int64_t batch, const uint64_t* masks_dev,
+                        int n_masks, uint64_t index_offset, double* out_dev, void* stream) {
+  int rc = check_state_args(state, n_qubits, dtype, batch);
+  if (rc) return rc;
+  if (!masks_dev || !out_dev || n_masks < 1) return set_err(B200Q_EINVAL, "bad mask arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t n = 1ull << n_qubits;
+  rc = cuda_err(cudaMemsetAsync(out_dev, 0, sizeof(double) * batch * n_masks, s), "memset");
+  if (rc) return rc;
+  dim3 grid(reduce_blocks(n), (unsigned)batch);
+  for (int m0 = 0; m0 < n_masks; m0 += kZGroup) {
+    B200Q_DISPATCH_REAL(dtype, (expz_kernel<Real><<<grid, 256, 0, s>>>((const cx<Real>*)state, n, masks_dev, n_masks,
+                                                                       m0, index_offset, out_dev)));
+  }
+  return cuda_err(cudaGetLastError(), "expectation_z launch");
+}
+
+int b200q_apply_z_weights(const void* state, void* lambda_out, int n_qubits, int dtype, int64_t batch,
+                          const uint64_t* masks_dev, const double* weights_dev, int n_masks, uint64_t index_offset,
+                          void* stream) {
+  int rc = check_state_args(state, n_qubits, dtype, batch);
+  if (rc) return rc;
+  if (!lambda_out || !masks_dev || !weights_dev || n_masks < 1 || n_masks > 2048)
+    return set_err(B200Q_EINVAL, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t n = 1ull << n_qubits;
+  dim3 grid(reduce_blocks(n), (unsigned)batch);
+  const size_t sm = size_t(n_masks) * 16;
+  B200Q_DISPATCH_REAL(dtype, (zweights_kernel<Real><<<grid, 256, sm, s>>>((const cx<Real>*)state, (cx<Real>*)lambda_out,
+                                                                          n, masks_dev, weights_dev, n_masks,
+                                                                          index_offset)));
+  return cuda_err(cudaGetLastError(), "apply_z_weights launch");
+}
+
+int b200q_init_basis(void* state, int n_qubits, int dtype, int64_t batch, uint64_t basis_index, void* stream) {
+  int rc = check_state_args(state, n_qubits, dtype, batch);
+  if (rc) return rc;
+  const uint64_t n = 1ull << n_qubits;
+  if (basis_index >= n) return set_err(B200Q_EINVAL, "basis index out of range");
+  dim3 grid(reduce_blocks(n), (unsigned)batch);
+  B200Q_DISPATCH_REAL(dtype,
+                      (init_basis_kernel<Real><<<grid, 256, 0, (cudaStream_t)stream>>>((cx<Real>*)state, n, basis_index)));
+  return cuda_err(cudaGetLastError(), "init_basis launch");
+}
+
+int b200q_adjoint_run(const b200q_plan_t*, void*, void*, const void*, void*, const uint8_t*, void*) {
+  return set_err(B200Q_EUNSUPPORTED, "b200q_adjoint_run: not built yet");
+}
+
+int b200q_qudit_apply(void*, int, int, int, const void*, const int32_t*, int, int64_t, void*) {
+  return set_err(B200Q_EUNSUPPORTED, "b200q_qudit_apply: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,413 @@
+// Fusion planner (host).  See b200q_program.h for the pass / round / op model.
+//
+// The reference walks its nn.Sequential one gate at a time (circuit.py:261) and each gate moves the
+// whole state through memory at least twice (qmath.py:503-504).  Here consecutive gates are grouped
+// so that the state is read and written once per *pass*:
+//   1. pick the tile bits of the next pass greedily: the set of index bits that lets the longest
+//      run of pending gates execute (only NON-diagonal targets have to be tile bits -- controls and
+//      diagonal gates act on any bit, they become per-thread / per-CTA predicates and phases);
+//   2. inside the tile, pick register slots round by round the same way;
+//   3. gates are reordered only across gates they commute with (two gates commute if on every
+//      shared qubit both act diagonally -- as control or diagonal target).
+#include "b200q_planner.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace b200q {
+namespace {
+
+struct IGate {
+  int kind = 0, k = 0;
+  int t[B200Q_MAX_TARGETS] = {0};
+  uint64_t ctrl = 0;
+  uint64_t tmask = 0;  // bits acted on non-diagonally
+  uint64_t dmask = 0;  // bits acted on diagonally (controls, diagonal targets)
+  int64_t mat = 0;
+  int flags = 0;
+  bool reg_kind = false;  // executable inside a register round
+  int op_kind = 0;
+  int pool = 0;
+};
+
+inline int popc(uint64_t x) { return __builtin_popcountll(x); }
+constexpr int kScanWindow = 2048;  // pending gates inspected per scheduling decision
+
+struct Builder {
+  int n_qubits, n_bits, vs, rb, rc, na, t_full, dtype;
+  PlanOptions opt;
+  std::vector<IGate> g;
+  std::vector<char> done;
+  int first_undone = 0;
+  uint64_t all_bits;
+
+  // Gates executable (in order) when non-diagonal targets must lie in `allowed`.
+  //   mode 0: tile choice  (every kind counts)
+  //   mode 1: register round (register kinds execute; MATK gates block)
+  //   mode 2: direct round (only MATK gates execute; register kinds block)
+  int scan(uint64_t allowed, int mode, int limit, int pool_left, std::vector<int>* out) const {
+    uint64_t bfull = 0, bdiag = 0;
+    int cnt = 0, visited = 0;
+    for (int i = first_undone; i < (int)g.size(); ++i) {
+      if (done[i]) continue;
+      if ((bfull & all_bits) == all_bits) break;
+      if (++visited > kScanWindow) break;
+      const IGate& a = g[i];
+      bool ok = !(a.tmask & (bfull | bdiag)) && !(a.dmask & bfull) && !(a.tmask & ~allowed);
+      if (ok && mode == 1 && !a.reg_kind) ok = false;
+      if (ok && mode == 2 && a.reg_kind) ok = false;
+      if (ok && a.pool > pool_left) ok = false;
+      if (ok) {
+        ++cnt;
+        pool_left -= a.pool;
+        if (out) out->push_back(i);
+        if (cnt >= limit) break;
+      } else {
+        bfull |= a.tmask;
+        bdiag |= a.dmask;
+      }
+    }
+    return cnt;
+  }
+
+  int first_missing_bit(uint64_t s) const {
+    for (int i = first_undone; i < (int)g.size(); ++i) {
+      if (done[i]) continue;
+      const uint64_t miss = g[i].tmask & ~s;
+      if (miss) return __builtin_ctzll(miss);
+    }
+    return -1;
+  }
+};
+
+}  // namespace
+
+Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, const PlanOptions& opt_in,
+                std::string* err) {
+  auto fail = [&](const std::string& m) -> Plan* {
+    if (err) *err = m;
+    return nullptr;
+  };
+  if (n_qubits < 1 || n_qubits > B200Q_MAX_QUBITS - 2) return fail("n_qubits out of range");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return fail("dtype must be B200Q_C64 or B200Q_C128");
+  if (n_gates < 0 || (n_gates > 0 && !gates)) return fail("bad gate list");
+
+  Builder B;
+  B.opt = opt_in;
+  if (B.opt.chunk_bits < 8 || B.opt.chunk_bits > 13) return fail("chunk_bits must be in 8..13");
+  B.dtype = dtype;
+  B.vs = dtype == B200Q_C64 ? 1 : 0;
+  B.rc = B200Q_REG_CHUNK_BITS;
+  B.rb = B.rc + B.vs;
+  B.na = 1 << B.rb;
+  B.t_full = B.opt.chunk_bits + B.vs;
+  B.n_qubits = n_qubits;
+  B.n_bits = std::max(n_qubits, B.rb);
+  B.all_bits = (1ull << n_qubits) - 1ull;
+  if (B.opt.low_bits <= 0) B.opt.low_bits = 5 + B.vs;  // 512-byte contiguous runs
+  if (B.opt.max_rounds < 3 || B.opt.max_rounds > B200Q_MAX_ROUNDS) B.opt.max_rounds = B200Q_MAX_ROUNDS;
+  if (B.opt.max_ops <= 0 || B.opt.max_ops > B200Q_MAX_OPS) B.opt.max_ops = B200Q_MAX_OPS;
+  const int t_eff = std::min(B.t_full, B.n_bits);
+
+  // ---- validate and classify ------------------------------------------------------------------
+  B.g.resize(n_gates);
+  for (int i = 0; i < n_gates; ++i) {
+    const b200q_gate_t& s = gates[i];
+    IGate& a = B.g[i];
+    a.kind = s.kind;
+    a.k = s.n_targets;
+    a.ctrl = s.controls;
+    a.mat = s.mat_offset;
+    a.flags = s.flags;
+    if (a.k < 1 || a.k > B200Q_MAX_TARGETS) return fail("gate " + std::to_string(i) + ": bad n_targets");
+    if (s.mat_offset < 0 || s.mat_offset > 0xffffffffll) return fail("gate matrix offset out of range");
+    uint64_t tm = 0;
+    for (int j = 0; j < a.k; ++j) {
+      a.t[j] = s.targets[j];
+      if (a.t[j] < 0 || a.t[j] >= n_qubits) return fail("gate " + std::to_string(i) + ": target out of range");
+      if (tm >> a.t[j] & 1) return fail("gate " + std::to_string(i) + ": repeated target");
+      tm |= 1ull << a.t[j];
+    }
+    if (a.ctrl & tm) return fail("gate " + std::to_string(i) + ": control equals target");
+    if (a.ctrl & ~B.all_bits) return fail("gate " + std::to_string(i) + ": control out of range");
+    switch (a.kind) {
+      case B200Q_GATE_X:
+        if (a.k != 1) return fail("X gate needs exactly one target");
+        a.reg_kind = true; a.op_kind = B200Q_OP_X; a.tmask = tm; a.dmask = a.ctrl; a.pool = 0;
+        break;
+      case B200Q_GATE_MAT:
+        if (a.k == 1) { a.reg_kind = true; a.op_kind = B200Q_OP_MAT1; a.pool = 4; }
+        else if (a.k <= B200Q_MATK_MAX) { a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); }
+        else return fail("dense gates on more than 4 targets are not supported by the tile kernel");
+        a.tmask = tm; a.dmask = a.ctrl;
+        break;
+      case B200Q_GATE_DIAG:
+        if (a.k <= 2) { a.reg_kind = true; a.op_kind = B200Q_OP_DIAG; a.pool = 4; a.tmask = 0; a.dmask = tm | a.ctrl; }
+        else if (a.k <= B200Q_MATK_MAX) {
+          a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); a.tmask = tm; a.dmask = a.ctrl;
+        } else return fail("diagonal gates on more than 4 targets are not supported");
+        break;
+      default:
+        return fail("unknown gate kind");
+    }
+  }
+  B.done.assign(n_gates, 0);
+
+  Plan* plan = new Plan();
+  plan->n_qubits = n_qubits;
+  plan->n_bits = B.n_bits;
+  plan->dtype = dtype;
+  plan->opt = B.opt;
+  plan->stats.n_gates = n_gates;
+
+  const int min_chunk_loc = std::max(0, std::min(3, (t_eff - B.vs) - B.rc));  // coalescing: lanes own chunk bits 0..2
+  const int min_loc = min_chunk_loc + B.vs;
+
+  while (true) {
+    while (B.first_undone < n_gates && B.done[B.first_undone]) ++B.first_undone;
+    if (B.first_undone >= n_gates) break;
+    const IGate& g0 = B.g[B.first_undone];
+    const int op_cap = B.opt.fuse ? B.opt.max_ops : 1;
+
+    // ---- 1. tile bits ---------------------------------------------------------------------------
+    uint64_t S = g0.tmask;
+    if (B.vs) S |= 1ull;
+    for (int b = 0; b < B.opt.low_bits && b < B.n_bits && popc(S) < t_eff; ++b) S |= 1ull << b;
+    int cur = B.scan(S, 0, op_cap, B200Q_POOL_MAX, nullptr);
+    while (popc(S) < t_eff) {
+      int best = -1, bestc = cur;
+      if (cur < op_cap) {
+        for (int b = 0; b < n_qubits; ++b) {
+          if (S >> b & 1) continue;
+          const int c = B.scan(S | (1ull << b), 0, op_cap, B200Q_POOL_MAX, nullptr);
+          if (c > bestc) { bestc = c; best = b; }
+        }
+      }
+      if (best < 0) {
+        best = cur < op_cap ? B.first_missing_bit(S) : -1;
+        if (best < 0)
+          for (int b = 0; b < B.n_bits; ++b)
+            if (!(S >> b & 1)) { best = b; break; }
+        bestc = B.scan(S | (1ull << best), 0, op_cap, B200Q_POOL_MAX, nullptr);
+      }
+      S |= 1ull << best;
+      cur = bestc;
+    }
+
+    b200q_pass_t P;
+    std::memset(&P, 0, sizeof(P));
+    P.n_bits = (uint8_t)B.n_bits;
+    P.tile_bits = (uint8_t)t_eff;
+    int loc_of[64];
+    for (int b = 0, j = 0, q = 0; b < B.n_bits; ++b) {
+      loc_of[b] = -1;
+      if (S >> b & 1) { loc_of[b] = j; P.tile_phys[j++] = (uint8_t)b; }
+      else P.nontile_phys[q++] = (uint8_t)b;
+    }
+    P.n_nontile = (uint8_t)(B.n_bits - t_eff);
+
+    int n_ops = 0, pool = 0, n_rounds = 0, gates_in_pass = 0;
+
+    // choose the register slots of one round; returns physical-bit mask R and the executable gates
+    auto choose_round = [&](bool restricted, uint64_t* R_out, std::vector<int>* list) {
+      const int limit = op_cap - gates_in_pass;
+      const int pool_left = B200Q_POOL_MAX - pool;
+      uint64_t R = B.vs ? 1ull : 0ull;
+      uint64_t cand = 0;
+      for (int j = B.vs; j < t_eff; ++j)
+        if (!restricted || j >= min_loc) cand |= 1ull << P.tile_phys[j];
+      int cnt = limit > 0 ? B.scan(R, 1, limit, pool_left, nullptr) : 0;
+      for (int s = 0; s < B.rc && limit > 0; ++s) {
+        int best = -1, bestc = cnt;
+        for (int j = B.vs; j < t_eff; ++j) {
+          const uint64_t bit = 1ull << P.tile_phys[j];
+          if (!(cand & bit) || (R & bit)) continue;
+          const int c = B.scan(R | bit, 1, limit, pool_left, nullptr);
+          if (c > bestc) { bestc = c; best = j; }
+        }
+        if (best < 0) break;
+        R |= 1ull << P.tile_phys[best];
+        cnt = bestc;
+      }
+      // fill the remaining slots with the highest free candidate bits
+      for (int j = t_eff - 1; j >= B.vs && popc(R) < B.rb; --j) {
+        const uint64_t bit = 1ull << P.tile_phys[j];
+        if ((cand & bit) && !(R & bit)) R |= bit;
+      }
+      for (int j = t_eff - 1; j >= B.vs && popc(R) < B.rb; --j) {  // tiny tiles: take anything
+        const uint64_t bit = 1ull << P.tile_phys[j];
+        if (!(R & bit)) R |= bit;
+      }
+      list->clear();
+      if (limit > 0) B.scan(R, 1, limit, pool_left, list);
+      *R_out = R;
+    };
+
+    auto is_restricted_ok = [&](uint64_t R) {
+      for (int j = B.vs; j < min_loc; ++j)
+        if (R >> P.tile_phys[j] & 1) return false;
+      return true;
+    };
+
+    auto emit_round = [&](uint64_t R, const std::vector<int>& list, bool src_global) -> b200q_round_t* {
+      b200q_round_t& Rd = P.rounds[n_rounds++];
+      std::memset(&Rd, 0, sizeof(Rd));
+      Rd.src_global = src_global;
+      Rd.dst_global = 0;
+      int slot_of[64];
+      for (int b = 0; b < 64; ++b) slot_of[b] = -1;
+      int ns = 0;
+      for (int j = 0; j < t_eff; ++j)
+        if (R >> P.tile_phys[j] & 1) { slot_of[P.tile_phys[j]] = ns; Rd.slot_bit[ns++] = (uint8_t)j; }
+      // item-index bits: ascending; for tile<->tile rounds move three bits with distinct chunk-bit
+      // residues mod 3 to the front so that quarter-warps are bank-conflict free under swz()
+      std::vector<int> nr;
+      for (int j = 0; j < t_eff; ++j)
+        if (!(R >> P.tile_phys[j] & 1)) nr.push_back(j);
+      Rd.op_begin = (uint16_t)n_ops;
+      for (int gi : list) {
+        const IGate& a = B.g[gi];
+        b200q_op_t& op = P.ops[n_ops++];
+        std::memset(&op, 0, sizeof(op));
+        op.kind = (uint8_t)a.op_kind;
+        op.flags = (uint8_t)((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0);
+        op.mat_src = (uint32_t)a.mat;
+        op.gate_id = (uint32_t)gi;
+        op.k = (uint8_t)a.k;
+        for (uint64_t c = a.ctrl; c; c &= c - 1) {
+          const int b = __builtin_ctzll(c);
+          if (slot_of[b] >= 0) op.ctrl_reg |= 1u << slot_of[b];
+          else if (loc_of[b] >= 0) op.ctrl_loc |= 1u << loc_of[b];
+          else op.ctrl_glob |= 1ull << b;
+        }
+        if (a.op_kind == B200Q_OP_MAT1 || a.op_kind == B200Q_OP_X) {
+          op.slot = (uint8_t)slot_of[a.t[0]];
+        } else if (a.op_kind == B200Q_OP_DIAG) {
+          for (int j = 0; j < a.k; ++j) {
+            const int b = a.t[j];
+            if (slot_of[b] >= 0) {
+              uint32_t bm = 0;
+              for (int i = 0; i < B.na; ++i)
+                if (i >> slot_of[b] & 1) bm |= 1u << i;
+              op.dsel_reg[j] = bm;
+            } else if (loc_of[b] >= 0) op.dsel_loc[j] = 1u << loc_of[b];
+            else op.dsel_glob[j] = 1ull << b;
+          }
+        }
+        if (a.pool) {
+          op.pool_off = (uint16_t)pool;
+          op.pool_n = (uint16_t)a.pool;
+          pool += a.pool;
+        }
+        B.done[gi] = 1;
+        ++gates_in_pass;
+      }
+      Rd.op_end = (uint16_t)n_ops;
+      for (size_t k = 0; k < nr.size(); ++k) Rd.nonreg_bit[k] = (uint8_t)nr[k];
+      return &Rd;
+    };
+
+    auto reorder_for_banks = [&](b200q_round_t* Rd) {
+      const int nn = t_eff - B.rb;
+      if (nn < 3) return;
+      std::vector<int> nr(Rd->nonreg_bit, Rd->nonreg_bit + nn), front, rest;
+      bool used[3] = {false, false, false};
+      for (int j : nr) {
+        const int res = (j - B.vs) % 3;
+        if (front.size() < 3 && !used[res]) { used[res] = true; front.push_back(j); }
+        else rest.push_back(j);
+      }
+      front.insert(front.end(), rest.begin(), rest.end());
+      for (int k = 0; k < nn; ++k) Rd->nonreg_bit[k] = (uint8_t)front[k];
+    };
+
+    std::vector<int> list, list2;
+    uint64_t R = 0, R2 = 0;
+    bool first = true;
+    b200q_round_t* last = nullptr;
+    bool last_restricted_ok = false;
+    while (true) {
+      if (n_rounds >= B.opt.max_rounds - 1) break;
+      if (gates_in_pass >= op_cap) break;
+      if (first) {
+        choose_round(true, &R, &list);
+        if (list.empty()) {
+          choose_round(false, &R2, &list2);
+          std::vector<int> mk;
+          const bool any_mid = !list2.empty() || B.scan(S, 2, 1, B200Q_POOL_MAX - pool, &mk) > 0;
+          if (!any_mid) break;
+          last = emit_round(R, list, true);  // plain load round
+          last_restricted_ok = true;
+          first = false;
+          continue;
+        }
+        last = emit_round(R, list, true);
+        last_restricted_ok = true;
+        first = false;
+        continue;
+      }
+      choose_round(false, &R, &list);
+      if (!list.empty()) {
+        last = emit_round(R, list, false);
+        last_restricted_ok = is_restricted_ok(R);
+        continue;
+      }
+      // a dense multi-target gate, applied in place in shared memory
+      std::vector<int> mk;
+      if (B.scan(S, 2, 1, B200Q_POOL_MAX - pool, &mk) == 0 || n_ops >= B200Q_MAX_OPS) break;
+      {
+        const IGate& a = B.g[mk[0]];
+        b200q_round_t& Rd = P.rounds[n_rounds++];
+        std::memset(&Rd, 0, sizeof(Rd));
+        Rd.direct = 1;
+        Rd.op_begin = (uint16_t)n_ops;
+        b200q_op_t& op = P.ops[n_ops++];
+        std::memset(&op, 0, sizeof(op));
+        op.kind = B200Q_OP_MATK;
+        op.k = (uint8_t)a.k;
+        op.flags = (uint8_t)((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0);
+        op.mat_src = (uint32_t)a.mat;
+        op.gate_id = (uint32_t)mk[0];
+        for (int j = 0; j < a.k; ++j) op.tk[j] = (uint8_t)loc_of[a.t[j]];
+        for (uint64_t c = a.ctrl; c; c &= c - 1) {
+          const int b = __builtin_ctzll(c);
+          if (loc_of[b] >= 0) op.ctrl_loc |= 1u << loc_of[b];
+          else op.ctrl_glob |= 1ull << b;
+        }
+        op.pool_off = (uint16_t)pool;
+        op.pool_n = (uint16_t)a.pool;
+        pool += a.pool;
+        Rd.op_end = (uint16_t)n_ops;
+        B.done[mk[0]] = 1;
+        ++gates_in_pass;
+        ++plan->stats.n_direct;
+        last = &Rd;
+        last_restricted_ok = false;
+      }
+    }
+    if (n_rounds == 0 || gates_in_pass == 0) {
+      delete plan;
+      return fail("planner made no progress (internal error)");
+    }
+    if (last && !last->direct && last_restricted_ok) {
+      last->dst_global = 1;
+    } else {
+      choose_round(true, &R, &list);
+      last = emit_round(R, list, false);
+      last->dst_global = 1;
+    }
+    for (int r = 0; r < n_rounds; ++r)
+      if (!P.rounds[r].direct && !P.rounds[r].src_global && !P.rounds[r].dst_global) reorder_for_banks(&P.rounds[r]);
+    P.n_rounds = (uint8_t)n_rounds;
+    P.n_ops = (uint8_t)n_ops;
+    P.pool_elems = (uint16_t)pool;
+    plan->passes.push_back(P);
+    plan->pass_gate_count.push_back(gates_in_pass);
+    plan->stats.n_rounds += n_rounds;
+    plan->stats.n_ops += n_ops;
+  }
+  plan->stats.n_passes = (int)plan->passes.size();
+  return plan;
+}
+
+}  // namespace b200q

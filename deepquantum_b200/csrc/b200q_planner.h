@@ -1,0 +1,41 @@
+// Host-side fusion planner: turns an ordered gate list into a list of passes (b200q_program.h).
+// Pure host C++ (no CUDA), so it is unit-tested on CPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b200q.h"
+#include "b200q_program.h"
+
+namespace b200q {
+
+struct PlanOptions {
+  int chunk_bits = 12;    // log2(16-byte chunks per tile): 12 -> 64 KiB tiles, 256 threads per CTA
+  int low_bits = -1;      // contiguous low amplitude bits forced into every tile (-1: default per dtype)
+  int max_rounds = B200Q_MAX_ROUNDS;
+  int max_ops = B200Q_MAX_OPS;
+  int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
+};
+
+struct PlanStats {
+  int n_gates = 0, n_passes = 0, n_rounds = 0, n_ops = 0, n_direct = 0;
+};
+
+class Plan {
+ public:
+  int n_qubits = 0;       // physical local qubits
+  int n_bits = 0;         // padded index bits (>= register slots)
+  int dtype = 0;          // B200Q_C64 / B200Q_C128
+  PlanOptions opt;
+  std::vector<b200q_pass_t> passes;
+  std::vector<int> pass_gate_count;
+  PlanStats stats;
+  std::string error;
+};
+
+// Returns nullptr and fills `err` on invalid input.
+Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, const PlanOptions& opt,
+                std::string* err);
+
+}  // namespace b200q

@@ -1,0 +1,76 @@
+// Pass / round / op descriptors shared by the host planner and the sm_100a tile kernel.
+//
+// One *pass* = one kernel launch that reads every amplitude of the (local) statevector once and
+// writes it once.  A pass owns a set of `tile_bits` physical index bits (the *tile bits*): every CTA
+// stages the 2^tile_bits amplitudes that differ only in those bits (64 KiB by default) and applies a
+// whole group of gates to them before writing back -- the fused replacement for one
+// `permute -> reshape(copy) -> mm` per gate in the reference (qmath.py:497-506).
+//
+// Inside a pass the tile is processed in *rounds*.  In a round every thread holds 16 chunks of 16
+// bytes (32 complex64 or 16 complex128 amplitudes) in registers: the amplitudes that differ only in
+// the round's *register slots* (5 index bits for complex64 -- bit 0 is always slot 0 because a
+// 16-byte chunk holds amplitudes 2m and 2m+1 -- 4 bits for complex128).  All ops of the round whose
+// targets are register slots are applied in registers; between rounds the tile is transposed through
+// shared memory.  The first round reads straight from global memory, the last one writes straight
+// back, so a pass whose gates fit one round never touches shared memory.
+#pragma once
+#include <stdint.h>
+
+#define B200Q_REG_CHUNK_BITS 4  /* 16 chunks of 16 B per thread */
+#define B200Q_MAX_TILE_BITS 14  /* amplitude bits per tile (complex64, 13 chunk bits) */
+#define B200Q_MAX_ROUNDS 8
+#define B200Q_MAX_OPS 44
+#define B200Q_POOL_MAX 512      /* complex elements of gate matrices staged in shared memory */
+#define B200Q_MAX_QUBITS 40
+#define B200Q_MATK_MAX 4        /* dense k-target ops applied inside a tile */
+
+enum {
+  B200Q_OP_MAT1 = 0,  // dense 2x2 on a register slot (+controls)
+  B200Q_OP_X = 1,     // amplitude swap on a register slot (+controls): X, CNOT, Toffoli, ...
+  B200Q_OP_DIAG = 2,  // diagonal over <= 2 selector bits anywhere in the index (+controls)
+  B200Q_OP_MATK = 3   // dense 2^k x 2^k, k = 2..4, on arbitrary tile bits, applied from shared memory
+};
+
+#define B200Q_FLAG_ADJOINT 1u /* use the conjugate transpose of the stored matrix */
+
+typedef struct {
+  uint8_t kind;
+  uint8_t slot;      // MAT1 / X: register slot of the target
+  uint8_t k;         // DIAG: number of selector bits (1..2); MATK: number of targets (2..4)
+  uint8_t flags;
+  uint16_t pool_off; // first element of this op's matrix in the shared-memory pool (multiple of 4)
+  uint16_t pool_n;   // elements in the pool (multiple of 4)
+  uint32_t mat_src;  // element offset of the dense 2^k x 2^k row-major matrix in the device buffer
+  uint32_t ctrl_reg; // controls that are register slots: mask over the register amplitude index
+  uint32_t ctrl_loc; // controls that are tile bits but not register slots: mask over tile-local bits
+  uint32_t dsel_reg[2]; // DIAG selector j as a bitmap over register amplitude indices (bit i = value)
+  uint32_t dsel_loc[2]; // DIAG selector j as a single tile-local bit mask (0 if not thread-level)
+  uint64_t ctrl_glob;   // controls outside the tile: mask over physical index bits
+  uint64_t dsel_glob[2];// DIAG selector j as a single physical bit mask outside the tile (or 0)
+  uint8_t tk[4];     // MATK: tile-local bit of matrix-index bit j (j = 0 is the LSB)
+  uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
+} b200q_op_t;
+
+typedef struct {
+  uint8_t src_global;  // 1: gather from global memory, 0: from the shared-memory tile
+  uint8_t dst_global;  // 1: scatter to global memory, 0: to the shared-memory tile
+  uint8_t direct;      // 1: MATK ops applied in place in shared memory (no register gather)
+  uint8_t pad;
+  uint16_t op_begin, op_end;
+  uint8_t slot_bit[5];     // tile-local amplitude bit of each register slot
+  uint8_t nonreg_bit[11];  // tile-local amplitude bits enumerated by the thread's item index
+} b200q_round_t;
+
+typedef struct {
+  uint8_t n_bits;     // physical index bits of the (padded) local state
+  uint8_t tile_bits;  // amplitude bits per tile
+  uint8_t n_rounds;
+  uint8_t n_ops;
+  uint16_t pool_elems;
+  uint8_t n_nontile;
+  uint8_t pad;
+  uint8_t tile_phys[B200Q_MAX_TILE_BITS];   // physical bit of tile-local bit j (ascending)
+  uint8_t nontile_phys[B200Q_MAX_QUBITS];   // physical bits enumerated by the tile (CTA) index
+  b200q_round_t rounds[B200Q_MAX_ROUNDS];
+  b200q_op_t ops[B200Q_MAX_OPS];
+} b200q_pass_t;

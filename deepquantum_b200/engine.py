@@ -1,0 +1,167 @@
+"""Thin Python layer over the C ABI (include/b200q.h): plans, single-gate application, reductions.
+
+PyTorch is used for device memory and streams only; every compute call goes to libb200q.so on the
+current CUDA stream.  There is no CPU fallback: CPU tensors are rejected with B200QError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import B200QError
+
+_checked_devices = set()
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.complex64:
+        return L.C64
+    if dtype == torch.complex128:
+        return L.C128
+    raise B200QError(f'unsupported state dtype {dtype}; expected complex64 or complex128')
+
+
+def require_cuda(t: torch.Tensor, what: str = 'state') -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise B200QError(f'{what} must be a CUDA tensor: deepquantum_b200 runs its gate kernels on sm_100a only and '
+                         'has no CPU fallback (use the reference package for CPU simulation)')
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in _checked_devices:
+        L.check(L.load().b200q_device_check(dev))
+        _checked_devices.add(dev)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def wires_to_targets(nqubit: int, wires) -> list[int]:
+    """Reference wires (wires[0] = most significant matrix bit, qmath.py:497-504) -> bit position of each
+    matrix-index bit, least significant first."""
+    return [nqubit - 1 - w for w in reversed(list(wires))]
+
+
+class FusedPlan:
+    """A fused pass schedule for a fixed gate *structure* (kinds, targets, controls); the matrix values are
+    supplied at run time from a device buffer."""
+
+    def __init__(self, nqubit: int, dtype: torch.dtype, gates: list, chunk_bits: int = 0, low_bits: int = 0,
+                 max_rounds: int = 0, fuse: bool = True):
+        lib = L.load()
+        self.nqubit = nqubit
+        self.dtype = dtype
+        self.ngates = len(gates)
+        arr = (L.GateStruct * max(1, len(gates)))(*gates)
+        opt = L.PlanOptions()
+        opt.chunk_bits, opt.low_bits, opt.max_rounds, opt.fuse = chunk_bits, low_bits, max_rounds, int(fuse)
+        handle = C.c_void_p()
+        L.check(lib.b200q_plan_create(nqubit, dtype_code(dtype), arr, len(gates), C.byref(opt), C.byref(handle)))
+        self._h = handle
+        st = L.PlanStats()
+        L.check(lib.b200q_plan_get_stats(self._h, C.byref(st)))
+        self.stats = {n: getattr(st, n) for n, _ in L.PlanStats._fields_}
+
+    @property
+    def n_passes(self) -> int:
+        return self.stats['n_passes']
+
+    def pass_gates(self, i: int) -> int:
+        return L.load().b200q_plan_pass_gates(self._h, i)
+
+    def export(self) -> bytes:
+        need = C.c_size_t()
+        lib = L.load()
+        L.check(lib.b200q_plan_export(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        L.check(lib.b200q_plan_export(self._h, buf, need.value, C.byref(need)))
+        return buf.raw
+
+    def run(self, state: torch.Tensor, mats: torch.Tensor | None, batch: int = 1, mat_batch_stride: int = 0,
+            first: int | None = None, last: int | None = None) -> None:
+        """Apply the plan IN PLACE to `state` (contiguous, batch * 2^n complex elements)."""
+        require_cuda(state)
+        if state.dtype != self.dtype or not state.is_contiguous() or state.numel() != batch << self.nqubit:
+            raise B200QError('state must be a contiguous tensor of batch * 2^n elements of the plan dtype')
+        mptr = None
+        if mats is not None:
+            if mats.dtype != self.dtype or not mats.is_contiguous() or mats.device != state.device:
+                raise B200QError('matrix buffer must be contiguous, of the plan dtype, on the state device')
+            mptr = mats.data_ptr()
+        lib = L.load()
+        if first is None and last is None:
+            rc = lib.b200q_plan_run(self._h, state.data_ptr(), mptr, batch, mat_batch_stride, _stream(state))
+        else:
+            rc = lib.b200q_plan_run_range(self._h, first or 0, self.n_passes if last is None else last,
+                                          state.data_ptr(), mptr, batch, mat_batch_stride, _stream(state))
+        L.check(rc)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                L.load().b200q_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def apply_gate_(state: torch.Tensor, nqubit: int, matrix: torch.Tensor | None, targets, controls=(), kind=L.GATE_MAT,
+                adjoint: bool = False, batch: int = 1, mat_batch_stride: int = 0) -> None:
+    """In-place single gate: the kernel behind `evolve_state` / `Gate.op_state_control`."""
+    require_cuda(state)
+    if not state.is_contiguous() or state.numel() != batch << nqubit:
+        raise B200QError('state must be contiguous with batch * 2^n elements')
+    t = (C.c_int32 * len(targets))(*[int(x) for x in targets])
+    c = (C.c_int32 * max(1, len(controls)))(*[int(x) for x in controls]) if len(controls) else None
+    mptr = None
+    if matrix is not None:
+        if matrix.dtype != state.dtype:
+            matrix = matrix.to(state.dtype)
+        matrix = matrix.contiguous()
+        mptr = matrix.data_ptr()
+    L.check(L.load().b200q_apply_gate(state.data_ptr(), nqubit, dtype_code(state.dtype), kind, mptr, t, len(targets), c,
+                                      len(controls), int(adjoint), batch, mat_batch_stride, _stream(state)))
+
+
+def norm2(state: torch.Tensor, nqubit: int, batch: int = 1) -> torch.Tensor:
+    require_cuda(state)
+    out = torch.empty(batch, dtype=torch.float64, device=state.device)
+    L.check(L.load().b200q_norm2(state.data_ptr(), nqubit, dtype_code(state.dtype), batch, out.data_ptr(),
+                                 _stream(state)))
+    return out
+
+
+def inner_product(bra: torch.Tensor, ket: torch.Tensor, nqubit: int, batch: int = 1) -> torch.Tensor:
+    require_cuda(bra)
+    require_cuda(ket)
+    out = torch.empty(batch, 2, dtype=torch.float64, device=bra.device)
+    L.check(L.load().b200q_inner_product(bra.data_ptr(), ket.data_ptr(), nqubit, dtype_code(bra.dtype), batch,
+                                         out.data_ptr(), _stream(bra)))
+    return torch.view_as_complex(out)
+
+
+def expectation_z(state: torch.Tensor, nqubit: int, masks: torch.Tensor, batch: int = 1,
+                  index_offset: int = 0) -> torch.Tensor:
+    """[batch, n_masks] float64: sum_i |psi_i|^2 (-1)^popcount(i & mask)."""
+    require_cuda(state)
+    out = torch.empty(batch, masks.numel(), dtype=torch.float64, device=state.device)
+    L.check(L.load().b200q_expectation_z(state.data_ptr(), nqubit, dtype_code(state.dtype), batch, masks.data_ptr(),
+                                         masks.numel(), index_offset, out.data_ptr(), _stream(state)))
+    return out
+
+
+def apply_z_weights(state: torch.Tensor, nqubit: int, masks: torch.Tensor, weights: torch.Tensor, batch: int = 1,
+                    index_offset: int = 0) -> torch.Tensor:
+    require_cuda(state)
+    out = torch.empty_like(state)
+    weights = weights.to(torch.float64).contiguous()
+    L.check(L.load().b200q_apply_z_weights(state.data_ptr(), out.data_ptr(), nqubit, dtype_code(state.dtype), batch,
+                                           masks.data_ptr(), weights.data_ptr(), masks.numel(), index_offset,
+                                           _stream(state)))
+    return out
+
+
+def init_basis_(state: torch.Tensor, nqubit: int, batch: int = 1, index: int = 0) -> None:
+    require_cuda(state)
+    L.check(L.load().b200q_init_basis(state.data_ptr(), nqubit, dtype_code(state.dtype), batch, index, _stream(state)))

@@ -1,0 +1,656 @@
+"""The gate zoo with the reference's class names, constructor signatures and matrices (gate.py).
+
+Every class keeps the reference conventions -- constant matrices are complex64 buffers that `.to()`
+widens (so the complex128 path carries float32-rounded constants exactly like the reference,
+gate.py:841-1367), parameters are float32 unless a tensor is passed (gate.py:384-391) -- and adds
+the *structure class* the fusion planner may rely on (dense / diagonal / Pauli-X permutation).
+Permutation gates (CNOT, Toffoli, Swap, Fredkin) are lowered to controlled-X records: the result is
+bit-identical to multiplying by the reference's dense 0/1 matrix.
+"""
+from __future__ import annotations
+
+from copy import copy
+from typing import Any
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .operation import Gate, Lowering
+
+
+# -------------------------------------------------------------------------------------------------
+# bases
+# -------------------------------------------------------------------------------------------------
+class SingleGate(Gate):
+    def __init__(self, name=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+        assert len(self.wires) == 1
+
+
+class DoubleGate(Gate):
+    def __init__(self, name=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False) -> None:
+        if wires is None:
+            wires = [0, 1]
+        assert len(wires) == 2
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+
+
+class DoubleControlGate(DoubleGate):
+    def __init__(self, name=None, nqubit=2, wires=None, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=None, condition=False, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+
+
+class TripleGate(Gate):
+    def __init__(self, name=None, nqubit=3, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False) -> None:
+        if wires is None:
+            wires = [0, 1, 2]
+        assert len(wires) == 3
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+
+
+class ArbitraryGate(Gate):
+    def __init__(self, name=None, nqubit=1, wires=None, minmax=None, controls=None, den_mat=False,
+                 tsr_mode=False) -> None:
+        self.nqubit = nqubit
+        if wires is None:
+            if minmax is None:
+                minmax = [0, nqubit - 1]
+            self._check_minmax(minmax)
+            wires = list(range(minmax[0], minmax[1] + 1))
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=controls, condition=False, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.minmax = [min(self.wires), max(self.wires)]
+        self.inv_mode = False
+
+    def inverse(self) -> 'ArbitraryGate':
+        gate = copy(self)
+        gate.inv_mode = not self.inv_mode
+        gate.name = self.name + '_dagger' if isinstance(self.name, str) else self.name
+        return gate
+
+
+class _Parametric:
+    """Shared behaviour of parametric gates (reference gate.py:341-520): parameters are scalar tensors
+    (`nn.Parameter` or buffer), `inverse()` is a shallow copy with `inv_mode` flipped."""
+
+    _matrix_source = 'group'
+    _pnames = ('theta',)
+
+    def _setup_parametric(self, inputs, requires_grad):
+        self.npara = len(self._pnames)
+        self.requires_grad = requires_grad
+        self.inv_mode = False
+        self._batched = None
+        self.init_para(inputs)
+
+    def inputs_to_tensor(self, inputs: Any = None) -> torch.Tensor:
+        while isinstance(inputs, list):
+            inputs = inputs[0]
+        if inputs is None:
+            inputs = torch.rand(1)[0] * 4 * torch.pi
+        elif not isinstance(inputs, (torch.Tensor, nn.Parameter)):
+            inputs = torch.tensor(inputs, dtype=torch.float)
+        return inputs
+
+    def _set(self, name, value):
+        if self.requires_grad:
+            setattr(self, name, nn.Parameter(value))
+        else:
+            if name in self._parameters:
+                del self._parameters[name]
+            self.register_buffer(name, value)
+
+    def init_para(self, inputs: Any = None) -> None:
+        self._batched = None
+        self._set('theta', self.inputs_to_tensor(inputs))
+        self.update_matrix()
+
+    def _signed(self):
+        """Parameter tensors with `inv_mode` applied (gate.py:395-400)."""
+        return [-self.theta if self.inv_mode else self.theta]
+
+    def _param_list(self):
+        if self._batched is not None:  # [batch, npara] set by QubitCircuit for 2-D data
+            cols = [self._batched[:, i] for i in range(self._batched.shape[1])]
+            return self._signed_cols(cols)
+        return [t.reshape(()) for t in self._signed()]
+
+    def _signed_cols(self, cols):
+        return [-c for c in cols] if self.inv_mode else cols
+
+    def update_matrix(self) -> torch.Tensor:
+        p = torch.stack([t.reshape(()) for t in self._signed()])
+        matrix = self._batched_matrix(p.unsqueeze(0))[0]
+        self.matrix = matrix.detach()
+        return matrix
+
+    def get_matrix(self, *inputs) -> torch.Tensor:
+        p = torch.stack([self.inputs_to_tensor(x).reshape(()) for x in inputs])
+        return self._batched_matrix(p.unsqueeze(0))[0]
+
+    def get_derivative(self, *inputs) -> torch.Tensor:
+        """d(matrix)/d(parameters) via the jacobian of the small matrix (reference gate.py:402-406)."""
+        from torch.autograd.functional import jacobian
+        p = torch.stack([self.inputs_to_tensor(x).reshape(()) for x in inputs]).detach()
+        jac = jacobian(lambda q: torch.view_as_real(self._batched_matrix(q.unsqueeze(0))[0]), p)
+        out = jac[..., 0, :] + 1j * jac[..., 1, :]   # [d, d, npara]
+        return out.squeeze(-1) if out.shape[-1] == 1 else out.permute(2, 0, 1)
+
+    def inverse(self):
+        gate = copy(self)
+        gate.inv_mode = not self.inv_mode
+        return gate
+
+    def extra_repr(self) -> str:
+        vals = ', '.join(f'{n}={t.item():.6g}' for n, t in zip(self._pnames, self._signed()))
+        s = f'wires={self.wires}, {vals}'
+        return s if self.controls == [] else s + f', controls={self.controls}'
+
+
+class ParametricSingleGate(_Parametric, SingleGate):
+    def __init__(self, name=None, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        SingleGate.__init__(self, name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                            den_mat=den_mat, tsr_mode=tsr_mode)
+        self._setup_parametric(inputs, requires_grad)
+
+
+class ParametricDoubleGate(_Parametric, DoubleGate):
+    def __init__(self, name=None, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        DoubleGate.__init__(self, name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                            den_mat=den_mat, tsr_mode=tsr_mode)
+        self._setup_parametric(inputs, requires_grad)
+
+
+def _cplx(re, im=None):
+    return torch.complex(re, torch.zeros_like(re) if im is None else im)
+
+
+def _mat(entries, d):
+    """entries: list of d*d tensors [..., N] -> [..., N, d, d]."""
+    return torch.stack(entries, dim=-1).reshape(*entries[0].shape, d, d)
+
+
+# -------------------------------------------------------------------------------------------------
+# single-qubit gates
+# -------------------------------------------------------------------------------------------------
+class U3Gate(ParametricSingleGate):
+    """U3(theta, phi, lambda) (reference gate.py:523-674)."""
+
+    _pnames = ('theta', 'phi', 'lambd')
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='U3Gate', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    def inputs_to_tensor(self, inputs: Any = None):
+        if inputs is None:
+            theta = torch.rand(1)[0] * torch.pi
+            phi = torch.rand(1)[0] * 2 * torch.pi
+            lambd = torch.rand(1)[0] * 2 * torch.pi
+            return theta, phi, lambd
+        if isinstance(inputs, (torch.Tensor, nn.Parameter)) and inputs.ndim == 0:
+            return inputs
+        if not isinstance(inputs, (torch.Tensor, nn.Parameter)) and not isinstance(inputs, (list, tuple)):
+            return torch.tensor(inputs, dtype=torch.float)
+        out = []
+        for x in inputs:
+            out.append(x if isinstance(x, (torch.Tensor, nn.Parameter)) else torch.tensor(x, dtype=torch.float))
+        return tuple(out)
+
+    def init_para(self, inputs: Any = None) -> None:
+        self._batched = None
+        theta, phi, lambd = self.inputs_to_tensor(inputs)
+        self._set('theta', theta)
+        self._set('phi', phi)
+        self._set('lambd', lambd)
+        self.update_matrix()
+
+    def _signed(self):
+        if self.inv_mode:  # gate.py:606-609
+            return [-self.theta, -self.lambd, -self.phi]
+        return [self.theta, self.phi, self.lambd]
+
+    def _signed_cols(self, cols):
+        return [-cols[0], -cols[2], -cols[1]] if self.inv_mode else cols
+
+    def get_matrix(self, theta, phi, lambd) -> torch.Tensor:
+        p = torch.stack([torch.as_tensor(x, dtype=torch.float).reshape(()) if not isinstance(x, torch.Tensor)
+                         else x.reshape(()) for x in (theta, phi, lambd)])
+        return self._batched_matrix(p.unsqueeze(0))[0]
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta, phi, lambd = p[..., 0], p[..., 1], p[..., 2]
+        c, s = _cplx(torch.cos(theta / 2)), _cplx(torch.sin(theta / 2))
+        e_il = torch.exp(1j * lambd)
+        e_ip = torch.exp(1j * phi)
+        e_ipl = torch.exp(1j * (phi + lambd))
+        return _mat([c, -e_il * s, e_ip * s, e_ipl * c], 2)
+
+
+class PhaseShift(ParametricSingleGate):
+    """diag(1, e^{i theta}) (reference gate.py:677-753)."""
+
+    _kind = L.GATE_DIAG
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='PhaseShift', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        one = _cplx(torch.ones_like(theta))
+        zero = torch.zeros_like(one)
+        return _mat([one, zero, zero, torch.exp(1j * theta)], 2)
+
+
+class _ConstSingle(SingleGate):
+    _matrix_entries = None
+    _default_name = None
+
+    def __init__(self, nqubit=1, wires=None, controls=None, condition=False, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name=self._default_name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+        self.register_buffer('matrix', self._make_matrix())
+
+    @classmethod
+    def _make_matrix(cls):
+        return torch.tensor(cls._matrix_entries, dtype=torch.cfloat)
+
+
+class Identity(Gate):
+    def __init__(self, nqubit=1, wires=None, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='Identity', nqubit=nqubit, wires=wires, controls=None, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.register_buffer('matrix', torch.eye(2**self.nqubit, dtype=torch.cfloat))
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        return
+
+    def get_unitary(self) -> torch.Tensor:
+        return self.matrix
+
+    def forward(self, x: Any) -> Any:
+        return x
+
+
+class PauliX(_ConstSingle):
+    _kind = L.GATE_X
+    _default_name = 'PauliX'
+    _matrix_entries = [[0, 1], [1, 0]]
+
+
+class PauliY(_ConstSingle):
+    _default_name = 'PauliY'
+    _matrix_entries = [[0, -1j], [1j, 0]]
+
+
+class PauliZ(_ConstSingle):
+    _kind = L.GATE_DIAG
+    _default_name = 'PauliZ'
+    _matrix_entries = [[1, 0], [0, -1]]
+
+
+class Hadamard(_ConstSingle):
+    _default_name = 'Hadamard'
+
+    @classmethod
+    def _make_matrix(cls):  # gate.py:1069: complex64 tensor divided by a Python float
+        return torch.tensor([[1, 1], [1, -1]], dtype=torch.cfloat) / 2**0.5
+
+
+class SGate(_ConstSingle):
+    _kind = L.GATE_DIAG
+    _default_name = 'SGate'
+    _matrix_entries = [[1, 0], [0, 1j]]
+
+    def inverse(self):
+        return SDaggerGate(nqubit=self.nqubit, wires=self.wires, controls=self.controls, tsr_mode=self.tsr_mode).to(
+            self.matrix.device, self.matrix.real.dtype)
+
+
+class SDaggerGate(_ConstSingle):
+    _kind = L.GATE_DIAG
+    _default_name = 'SDaggerGate'
+    _matrix_entries = [[1, 0], [0, -1j]]
+
+    def inverse(self):
+        return SGate(nqubit=self.nqubit, wires=self.wires, controls=self.controls, tsr_mode=self.tsr_mode).to(
+            self.matrix.device, self.matrix.real.dtype)
+
+
+class TGate(_ConstSingle):
+    _kind = L.GATE_DIAG
+    _default_name = 'TGate'
+    _matrix_entries = [[1, 0], [0, (1 + 1j) / 2**0.5]]
+
+    def inverse(self):
+        return TDaggerGate(nqubit=self.nqubit, wires=self.wires, controls=self.controls, tsr_mode=self.tsr_mode).to(
+            self.matrix.device, self.matrix.real.dtype)
+
+
+class TDaggerGate(_ConstSingle):
+    _kind = L.GATE_DIAG
+    _default_name = 'TDaggerGate'
+    _matrix_entries = [[1, 0], [0, (1 - 1j) / 2**0.5]]
+
+    def inverse(self):
+        return TGate(nqubit=self.nqubit, wires=self.wires, controls=self.controls, tsr_mode=self.tsr_mode).to(
+            self.matrix.device, self.matrix.real.dtype)
+
+
+class Rx(ParametricSingleGate):
+    """exp(-i theta X / 2) (reference gate.py:1389-1480)."""
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Rx', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c = _cplx(torch.cos(theta / 2))
+        misin = _cplx(torch.zeros_like(theta), -torch.sin(theta / 2))
+        return _mat([c, misin, misin, c], 2)
+
+
+class Ry(ParametricSingleGate):
+    def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Ry', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c, s = torch.cos(theta / 2), torch.sin(theta / 2)
+        return _mat([_cplx(c), _cplx(-s), _cplx(s), _cplx(c)], 2)
+
+
+class Rz(ParametricSingleGate):
+    _kind = L.GATE_DIAG
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Rz', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        em, ep = torch.exp(-1j * theta / 2), torch.exp(1j * theta / 2)
+        zero = torch.zeros_like(em)
+        return _mat([em, zero, zero, ep], 2)
+
+
+class ProjectionJ(ParametricSingleGate):
+    """Measurement-plane rotation J (reference gate.py:1674-1787)."""
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, plane='xy', controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        self.plane = plane.lower()
+        assert self.plane in ('xy', 'yx', 'yz', 'zy', 'zx', 'xz'), f'Unsupported measurement plane: {plane}'
+        super().__init__(name='ProjectionJ', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    _matrix_source = 'dyn'   # the plane is per instance, so no per-class batching
+
+    def update_matrix(self) -> torch.Tensor:
+        theta = -self.theta if self.inv_mode else self.theta  # the reference's convention (gate.py:395-400)
+        matrix = self._plane_matrix(theta.reshape(1))[0]
+        self.matrix = matrix.detach()
+        return matrix
+
+    def get_matrix(self, theta) -> torch.Tensor:
+        return self._plane_matrix(self.inputs_to_tensor(theta).reshape(1))[0]
+
+    def _plane_matrix(self, theta):
+        if self.plane in ('xy', 'yx'):
+            one = _cplx(torch.ones_like(theta))
+            e = torch.exp(-1j * theta)
+            return _mat([one, e, one, -e], 2) / 2**0.5
+        if self.plane in ('yz', 'zy'):
+            cps = _cplx(torch.cos(theta / 2) + torch.sin(theta / 2))
+            cms = _cplx(torch.cos(theta / 2) - torch.sin(theta / 2))
+            return _mat([cps, -1j * cms, cms, 1j * cps], 2) / 2**0.5
+        c, s = _cplx(torch.cos(theta / 2)), _cplx(torch.sin(theta / 2))
+        return _mat([c, s, s, -c], 2)
+
+
+# -------------------------------------------------------------------------------------------------
+# two- and three-qubit gates
+# -------------------------------------------------------------------------------------------------
+class CNOT(DoubleControlGate):
+    """Dense 4x4 CNOT on [control, target] (reference gate.py:1906-1960); a permutation, lowered to a
+    controlled amplitude swap."""
+
+    def __init__(self, nqubit=2, wires=None, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='CNOT', nqubit=nqubit, wires=wires, den_mat=den_mat, tsr_mode=tsr_mode)
+        self.register_buffer('matrix', torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]]) + 0j)
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        low.add(self, L.GATE_X, [self.wires[1]], [self.wires[0]])
+
+
+class Swap(DoubleGate):
+    def __init__(self, nqubit=2, wires=None, controls=None, condition=False, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='Swap', nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+        self.register_buffer('matrix', torch.tensor([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) + 0j)
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        a, b = self.wires
+        for c, t in ((a, b), (b, a), (a, b)):
+            low.add(self, L.GATE_X, [t], [c] + self.controls)
+
+
+class ImaginarySwap(DoubleGate):
+    def __init__(self, nqubit=2, wires=None, controls=None, condition=False, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='ImaginarySwap', nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+        self.register_buffer('matrix', torch.tensor([[1, 0, 0, 0], [0, 0, 1j, 0], [0, 1j, 0, 0], [0, 0, 0, 1]]))
+
+
+def _diag4(a, b, c, d):
+    z = torch.zeros_like(a)
+    return _mat([a, z, z, z, z, b, z, z, z, z, c, z, z, z, z, d], 4)
+
+
+class Rxx(ParametricDoubleGate):
+    def __init__(self, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Rxx', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c = _cplx(torch.cos(theta / 2))
+        s = _cplx(torch.zeros_like(theta), -torch.sin(theta / 2))
+        z = torch.zeros_like(c)
+        return _mat([c, z, z, s, z, c, s, z, z, s, c, z, s, z, z, c], 4)
+
+
+class Ryy(ParametricDoubleGate):
+    def __init__(self, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Ryy', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c = _cplx(torch.cos(theta / 2))
+        s = _cplx(torch.zeros_like(theta), torch.sin(theta / 2))
+        z = torch.zeros_like(c)
+        return _mat([c, z, z, s, z, c, -s, z, z, -s, c, z, s, z, z, c], 4)
+
+
+class Rzz(ParametricDoubleGate):
+    _kind = L.GATE_DIAG
+
+    def __init__(self, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Rzz', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        em, ep = torch.exp(-1j * theta / 2), torch.exp(1j * theta / 2)
+        return _diag4(em, ep, ep, em)
+
+
+class Rxy(ParametricDoubleGate):
+    def __init__(self, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='Rxy', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
+                         condition=condition, den_mat=den_mat, tsr_mode=tsr_mode, requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c = _cplx(torch.cos(theta / 2))
+        s = _cplx(torch.zeros_like(theta), -torch.sin(theta / 2))
+        z, o = torch.zeros_like(c), torch.ones_like(c)
+        return _mat([o, z, z, z, z, c, s, z, z, s, c, z, z, z, z, o], 4)
+
+
+class ReconfigurableBeamSplitter(ParametricDoubleGate):
+    def __init__(self, inputs=None, nqubit=2, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name='ReconfigurableBeamSplitter', inputs=inputs, nqubit=nqubit, wires=wires,
+                         controls=controls, condition=condition, den_mat=den_mat, tsr_mode=tsr_mode,
+                         requires_grad=requires_grad)
+
+    @staticmethod
+    def _batched_matrix(p):
+        theta = p[..., 0]
+        c, s = _cplx(torch.cos(theta)), _cplx(torch.sin(theta))
+        z, o = torch.zeros_like(c), torch.ones_like(c)
+        return _mat([o, z, z, z, z, c, s, z, z, -s, c, z, z, z, z, o], 4)
+
+
+def _perm8(swap):
+    m = torch.eye(8)
+    m[[swap[0], swap[1]]] = m[[swap[1], swap[0]]]
+    return m + 0j
+
+
+class Toffoli(TripleGate):
+    """Dense 8x8 CCX on [control1, control2, target] (reference gate.py:2482-2649)."""
+
+    def __init__(self, nqubit=3, wires=None, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='Toffoli', nqubit=nqubit, wires=wires, controls=None, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.register_buffer('matrix', _perm8((6, 7)))
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        low.add(self, L.GATE_X, [self.wires[2]], [self.wires[0], self.wires[1]])
+
+
+class Fredkin(TripleGate):
+    """Dense 8x8 controlled-SWAP on [control, target1, target2] (reference gate.py:2652-2742)."""
+
+    def __init__(self, nqubit=3, wires=None, den_mat=False, tsr_mode=False) -> None:
+        super().__init__(name='Fredkin', nqubit=nqubit, wires=wires, controls=None, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.register_buffer('matrix', _perm8((5, 6)))
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        c0, a, b = self.wires
+        for c, t in ((a, b), (b, a), (a, b)):
+            low.add(self, L.GATE_X, [t], [c, c0])
+
+
+class UAnyGate(ArbitraryGate):
+    """Arbitrary unitary on `wires` (reference gate.py:2745-2788)."""
+
+    def __init__(self, unitary, nqubit=1, wires=None, minmax=None, controls=None, name='UAnyGate', den_mat=False,
+                 tsr_mode=False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=wires, minmax=minmax, controls=controls, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        if not isinstance(unitary, torch.Tensor):
+            unitary = torch.tensor(unitary, dtype=torch.cfloat).reshape(-1, 2 ** len(self.wires))
+        assert unitary.dtype in (torch.cfloat, torch.cdouble)
+        assert unitary.shape[-1] == unitary.shape[-2] == 2 ** len(self.wires)
+        err = (unitary @ unitary.mH - torch.eye(unitary.shape[-1], dtype=unitary.dtype, device=unitary.device)).abs()
+        assert float(err.max()) < 1e-4, 'Please check the unitary matrix'
+        self.register_buffer('matrix', unitary)
+
+    def update_matrix(self) -> torch.Tensor:
+        return self.matrix.mH if self.inv_mode else self.matrix
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        low.add(self, self._kind, self.wires, self.controls, adjoint=inverse != self.inv_mode)
+
+
+class LatentGate(ArbitraryGate):
+    """Unitary obtained from the SVD of a trainable latent matrix (reference gate.py:2791-2864)."""
+
+    _matrix_source = 'dyn'
+
+    def __init__(self, inputs=None, nqubit=1, wires=None, minmax=None, controls=None, name='LatentGate',
+                 den_mat=False, tsr_mode=False, requires_grad=False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=wires, minmax=minmax, controls=controls, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.requires_grad = requires_grad
+        self.init_para(inputs)
+
+    def inputs_to_tensor(self, inputs=None) -> torch.Tensor:
+        dim = 2 ** len(self.wires)
+        if inputs is None:
+            inputs = torch.randn(dim, dim)
+        elif not isinstance(inputs, (torch.Tensor, nn.Parameter)):
+            inputs = torch.tensor(inputs, dtype=torch.float)
+        assert inputs.shape[-1] == inputs.shape[-2] == dim
+        return inputs
+
+    def get_matrix(self, inputs) -> torch.Tensor:
+        latent = self.inputs_to_tensor(inputs) + 0j
+        u, _, vh = torch.linalg.svd(latent)
+        return u @ vh
+
+    def update_matrix(self) -> torch.Tensor:
+        latent = self.latent.mH if self.inv_mode else self.latent
+        matrix = self.get_matrix(latent)
+        self.matrix = matrix.detach()
+        return matrix
+
+    def init_para(self, inputs=None) -> None:
+        latent = self.inputs_to_tensor(inputs)
+        if self.requires_grad:
+            self.latent = nn.Parameter(latent)
+        else:
+            self.register_buffer('latent', latent)
+        self.update_matrix()
+        self.npara = self.latent.numel()
+
+
+class Barrier(Gate):
+    """No-op (reference gate.py:3097-3126); never a fusion barrier."""
+
+    def __init__(self, nqubit=1, wires=None, name='Barrier') -> None:
+        if wires is None:
+            wires = list(range(nqubit))
+        super().__init__(name=name, nqubit=nqubit, wires=wires)
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        return
+
+    def forward(self, x: Any) -> Any:
+        return x

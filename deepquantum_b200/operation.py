@@ -1,0 +1,346 @@
+"""Operation / Gate base classes with the reference's interface (operation.py:16-409), lowered to
+the b200q C ABI instead of permute/reshape/matmul.
+
+Only the statevector path is implemented (`den_mat=False`, no MPS): that is the hot path this package
+replaces.  Density-matrix / MPS arguments are accepted for signature
+compatibility and rejected with NotImplementedError.
+"""
+from __future__ import annotations
+
+from copy import copy
+from typing import Any
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import engine
+
+dtype_map = {torch.float: torch.cfloat, torch.double: torch.cdouble}  # reference __init__.py:115-118
+
+
+def apply_complex_fix(fn: Any, tensors: dict) -> dict:
+    """`.to()` / `.double()` semantics of the reference (utils.py:45-50): probe which real dtype and
+    device `fn` maps to and move complex buffers to the matching complex dtype."""
+    first = next(iter(tensors.values()))
+    probe = fn(torch.empty(0, dtype=first.real.dtype, device=first.device))
+    target = dtype_map.get(probe.dtype, probe.dtype)
+    return {k: v.to(probe.device, target) for k, v in tensors.items()}
+
+
+class Operation(nn.Module):
+    """Base class of quantum operations (reference operation.py:16-113)."""
+
+    def __init__(self, name=None, nqubit: int = 1, wires=None, den_mat: bool = False, tsr_mode: bool = False) -> None:
+        super().__init__()
+        if den_mat:
+            raise NotImplementedError('deepquantum_b200 accelerates the statevector path only (den_mat=False)')
+        self.name = name
+        self.nqubit = nqubit
+        self.wires = wires
+        self.den_mat = den_mat
+        self.tsr_mode = tsr_mode
+        self.npara = 0
+
+    def tensor_rep(self, x: torch.Tensor) -> torch.Tensor:
+        """[..., 2^n(,1)] -> [batch, 2, ..., 2] (reference operation.py:45-55)."""
+        if x.ndim == 1:
+            assert x.shape[-1] == 2**self.nqubit
+        else:
+            assert x.shape[-1] == 2**self.nqubit or x.shape[-2] == 2**self.nqubit
+        return x.reshape([-1] + [2] * self.nqubit)
+
+    def vector_rep(self, x: torch.Tensor) -> torch.Tensor:
+        return x.reshape(-1, 2**self.nqubit, 1)
+
+    def get_unitary(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def init_para(self) -> None:
+        pass
+
+    def set_nqubit(self, nqubit: int) -> None:
+        self.nqubit = nqubit
+
+    def set_wires(self, wires) -> None:
+        self.wires = self._convert_indices(wires)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.tensor_rep(x) if self.tsr_mode else self.vector_rep(x)
+
+    def _convert_indices(self, indices) -> list[int]:
+        if isinstance(indices, int):
+            indices = [indices]
+        assert isinstance(indices, list), 'Invalid input type'
+        assert all(isinstance(i, int) for i in indices), 'Invalid input type'
+        if len(indices) > 0:
+            assert min(indices) > -1 and max(indices) < self.nqubit, 'Invalid input'
+        assert len(set(indices)) == len(indices), 'Invalid input'
+        return indices
+
+    def _check_minmax(self, minmax: list[int]) -> None:
+        assert isinstance(minmax, list)
+        assert len(minmax) == 2
+        assert all(isinstance(i, int) for i in minmax)
+        assert -1 < minmax[0] <= minmax[1] < self.nqubit
+
+
+class Lowering:
+    """Collects the C-ABI gate records of a sequence of gates plus where each record's matrix comes
+    from: a constant buffer, a per-forward `update_matrix()` call, or a batched per-class evaluation
+    of all gates of one parametric class (one vectorised torch call instead of one per gate)."""
+
+    def __init__(self, nqubit: int):
+        self.nqubit = nqubit
+        self.records = []      # (kind, targets, controls, adjoint, block, index, size)
+        self.const = []        # tensors
+        self.dynamic = []      # gates whose update_matrix() is evaluated every forward
+        self.groups = {}       # class -> list of gates
+        self.sources = []      # gate object per record (None for X records)
+
+    def add(self, gate: 'Gate', kind: int, wires, controls, adjoint: bool = False, matrix_of: 'Gate | None' = None):
+        n = self.nqubit
+        targets = engine.wires_to_targets(n, wires)
+        ctrl = [n - 1 - c for c in controls]
+        size = 4 ** len(wires)
+        src = matrix_of if matrix_of is not None else gate
+        if kind == L.GATE_X:
+            block, idx = 'none', 0
+        elif src._matrix_source == 'const':
+            block, idx = 'const', len(self.const)
+            self.const.append(src.matrix)
+        elif src._matrix_source == 'group':
+            lst = self.groups.setdefault(type(src), [])
+            block, idx = type(src), len(lst)
+            lst.append(src)
+        else:
+            block, idx = 'dyn', len(self.dynamic)
+            self.dynamic.append(src)
+        self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size))
+        self.sources.append(src if kind != L.GATE_X else None)
+
+    def finalize(self):
+        """Assign matrix-buffer offsets; returns (GateStruct list, layout description)."""
+        sizes = {'const': [0] * len(self.const), 'dyn': [0] * len(self.dynamic)}
+        for cls, lst in self.groups.items():
+            sizes[cls] = [0] * len(lst)
+        for kind, _t, _c, _a, block, idx, size in self.records:
+            if block != 'none':
+                sizes[block][idx] = size
+        bases, offs, total = {}, {}, 0
+        for block in ['const', 'dyn'] + list(self.groups):
+            bases[block] = total
+            acc, lst = 0, []
+            for s in sizes[block]:
+                lst.append(acc)
+                acc += s
+            offs[block] = lst
+            total += acc
+        structs = []
+        for kind, targets, ctrl, adj, block, idx, _size in self.records:
+            off = 0 if block == 'none' else bases[block] + offs[block][idx]
+            structs.append(L.make_gate(kind, targets, ctrl, off, adj))
+        self.offsets = [0 if r[4] == 'none' else bases[r[4]] + offs[r[4]][r[5]] for r in self.records]
+        self.total = max(total, 1)
+        return structs
+
+    def structure_key(self):
+        return tuple(r[:4] + (r[6],) for r in self.records)
+
+    def build_matrices(self, cdtype: torch.dtype, device, batch: int | None = None) -> torch.Tensor:
+        """Flat device buffer of every matrix ([total] or [batch, total]); differentiable w.r.t. the gate
+        parameters."""
+        parts = []
+        if self.const:
+            parts.append(torch.cat([m.reshape(-1) for m in self.const]).to(device=device, dtype=cdtype))
+        if self.dynamic:
+            parts.append(torch.cat([g.update_matrix().reshape(-1) for g in self.dynamic]).to(device=device,
+                                                                                             dtype=cdtype))
+        batched = False
+        for cls, lst in self.groups.items():
+            plist = [t for g in lst for t in g._param_list()]
+            p = torch.stack(plist)                       # [N*npara] or [N*npara, batch]
+            if p.ndim == 2:
+                batched = True
+                p = p.transpose(0, 1).reshape(p.shape[1], len(lst), -1)
+            else:
+                p = p.reshape(len(lst), -1)
+            m = cls._batched_matrix(p.to(device))        # [..., N, d, d]
+            parts.append(m.reshape(*m.shape[:-3], -1).to(cdtype))
+        if not parts:
+            return torch.zeros(1, dtype=cdtype, device=device)
+        if batched:
+            nb = next(x.shape[0] for x in parts if x.ndim == 2)
+            parts = [x if x.ndim == 2 else x.unsqueeze(0).expand(nb, -1) for x in parts]
+            return torch.cat(parts, dim=-1).contiguous()
+        return torch.cat(parts)
+
+
+class Gate(Operation):
+    """Base class of gates (reference operation.py:116-409).
+
+    Class attributes consumed by the lowering:
+      _kind           B200Q gate kind the planner may assume (structure only, never values)
+      _matrix_source  'const' (registered `matrix` buffer), 'group' (`_batched_matrix` over all gates of
+                      the class) or 'dyn' (`update_matrix()` every forward)
+    """
+
+    _kind = L.GATE_MAT
+    _matrix_source = 'const'
+
+    def __init__(self, name=None, nqubit: int = 1, wires=None, controls=None, condition: bool = False,
+                 den_mat: bool = False, tsr_mode: bool = False) -> None:
+        self.nqubit = nqubit
+        if wires is None:
+            wires = [0]
+        if controls is None:
+            controls = []
+        wires = self._convert_indices(wires)
+        controls = self._convert_indices(controls)
+        for wire in wires:
+            assert wire not in controls, 'Use repeated wires'
+        if condition:
+            raise NotImplementedError('conditional measurement (condition=True) is outside the accelerated path')
+        super().__init__(name=name, nqubit=nqubit, wires=wires, den_mat=den_mat, tsr_mode=tsr_mode)
+        self.controls = controls
+        self.condition = condition
+
+    # ---- dtype / device moves: complex buffers follow the real dtype (operation.py:156-169) ---------
+    def _apply(self, fn: Any) -> 'Gate':
+        if self.npara > 0:
+            super()._apply(fn)
+        else:
+            tensor = self._buffers.pop('matrix') if 'matrix' in self._buffers else None
+            super()._apply(fn)
+            if tensor is not None:
+                self.register_buffer('matrix', apply_complex_fix(fn, {'matrix': tensor})['matrix'])
+        return self
+
+    def set_controls(self, controls) -> None:
+        self.controls = self._convert_indices(controls)
+
+    def get_matrix(self, inputs: Any) -> torch.Tensor:
+        return self.matrix
+
+    def update_matrix(self) -> torch.Tensor:
+        return self.matrix
+
+    def get_derivative(self, inputs: Any) -> torch.Tensor:
+        return torch.zeros_like(self.matrix)
+
+    def get_unitary(self) -> torch.Tensor:
+        """Global 2^n x 2^n unitary (small n only), built column by column like the non-local branch of
+        the reference (gate.py:326-331): apply the gate to the identity."""
+        dim = 2**self.nqubit
+        matrix = self.update_matrix()
+        eye = torch.eye(dim, dtype=matrix.dtype, device=matrix.device)
+        out = self._apply_to_batch(eye.contiguous().clone(), dim)
+        return out.T
+
+    # ---- lowering -----------------------------------------------------------------------------------
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        low.add(self, self._kind, self.wires, self.controls, adjoint=inverse)
+
+    def _apply_to_batch(self, flat: torch.Tensor, batch: int) -> torch.Tensor:
+        """Apply this gate in place to a contiguous [batch, 2^n] tensor."""
+        low = Lowering(self.nqubit)
+        self._lower(low)
+        low.finalize()
+        mats = low.build_matrices(flat.dtype, flat.device)
+        for (kind, targets, ctrl, adj, block, _i, size), off in zip(low.records, low.offsets):
+            m = None if block == 'none' else mats[off:off + size]
+            engine.apply_gate_(flat, self.nqubit, m, targets, ctrl, kind, adj, batch)
+        return flat
+
+    def op_state(self, x: torch.Tensor) -> torch.Tensor:
+        """Out-of-place application to a `[batch, 2, ..., 2]` tensor (reference operation.py:191-197)."""
+        shape = x.shape
+        flat = x.reshape(-1, 2**self.nqubit).contiguous().clone()
+        flat = self._apply_to_batch(flat, flat.shape[0])
+        x = flat.reshape(shape)
+        if not self.tsr_mode:
+            x = self.vector_rep(x).squeeze(0)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor):
+            return self.op_dist_state(x)
+        if not self.tsr_mode:
+            x = self.tensor_rep(x)
+        assert x.ndim == self.nqubit + 1
+        return self.op_state(x)
+
+    def op_dist_state(self, x):
+        """Sharded state (reference operation.py:265-272): delegated to the distributed state object."""
+        return x.apply_gate(self)
+
+    def inverse(self) -> 'Gate':
+        return self
+
+    def extra_repr(self) -> str:
+        s = f'wires={self.wires}'
+        return s if self.controls == [] else s + f', controls={self.controls}'
+
+
+class Layer(Operation):
+    """A set of gates on disjoint wires (reference operation.py:412-522)."""
+
+    def __init__(self, name=None, nqubit: int = 1, wires=None, den_mat: bool = False, tsr_mode: bool = False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=None, den_mat=den_mat, tsr_mode=tsr_mode)
+        self.nqubit = nqubit
+        if wires is None:
+            wires = [[0]]
+        self.wires = self._convert_indices(wires)
+        self.gates = nn.Sequential()
+
+    def _convert_indices(self, indices) -> list[list[int]]:
+        if isinstance(indices, int):
+            indices = [[indices]]
+        assert isinstance(indices, list), 'Invalid input type'
+        if all(isinstance(i, int) for i in indices):
+            indices = [[i] for i in indices]
+        assert all(isinstance(i, list) for i in indices), 'Invalid input type'
+        for idx in indices:  # per-gate checks only: rings may reuse a wire across gates (operation.py:496-507)
+            assert all(isinstance(i, int) for i in idx), 'Invalid input type'
+            assert min(idx) > -1 and max(idx) < self.nqubit, 'Invalid input'
+            assert len(set(idx)) == len(idx), 'Invalid input'
+        return indices
+
+    def set_nqubit(self, nqubit: int) -> None:
+        self.nqubit = nqubit
+        for g in self.gates:
+            g.nqubit = nqubit
+
+    def init_para(self, inputs: Any = None) -> None:
+        count = 0
+        for g in self.gates:
+            if inputs is None:
+                g.init_para()
+            else:
+                g.init_para(inputs[count:count + g.npara])
+            count += g.npara
+
+    def update_npara(self) -> None:
+        self.npara = sum(g.npara for g in self.gates)
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        for g in (reversed(self.gates) if inverse else self.gates):
+            g._lower(low, inverse)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.tsr_mode:
+            x = self.tensor_rep(x)
+        shape = x.shape
+        flat = x.reshape(-1, 2**self.nqubit).contiguous().clone()
+        for g in self.gates:
+            g._apply_to_batch(flat, flat.shape[0])
+        x = flat.reshape(shape)
+        if not self.tsr_mode:
+            return self.vector_rep(x).squeeze(0)
+        return x
+
+    def inverse(self) -> 'Layer':
+        return self
+
+
+__all__ = ['Operation', 'Gate', 'Layer', 'Lowering', 'apply_complex_fix', 'dtype_map', 'copy']

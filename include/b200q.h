@@ -1,0 +1,141 @@
+/* b200q -- C ABI of the B200-native statevector gate-application engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of TuringQ/deepquantum (v4.5.0 @ 727c44d) that
+ * this repository accelerates: the dense statevector gate-application loop driven by
+ * QubitCircuit.forward.  The reference has no FFI of its own (it is pure Python on PyTorch); the
+ * functions below are what a binding for that path replaces, each cited as file:line relative to
+ * the reference tree.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - All `state`, `matrices`, `*_dev` pointers are DEVICE pointers owned by the caller (PyTorch
+ *     tensors); the library never allocates or frees state memory.  `stream` is a cudaStream_t.
+ *   - A state of n qubits is 2^n interleaved complex numbers (complex64: dtype 0, complex128: 1);
+ *     `batch` states are contiguous.  Qubit *bit* b is bit b of the flat amplitude index; reference
+ *     wire w is bit n-1-w (operation.py:45-55, distributed.py:18).
+ *   - Gate matrices are dense row-major 2^k x 2^k complex arrays in device memory (they may be
+ *     autograd outputs: the library never reads them on the host).  Matrix index bit j (j = 0 the
+ *     least significant) acts on `targets[j]`; the reference enumerates wires with wires[0] as the
+ *     MOST significant matrix bit (qmath.py:497-504), i.e. targets[j] = n-1-wires[k-1-j].
+ *   - Every function returns 0 on success, a negative B200Q_E* code on invalid arguments, or a
+ *     positive cudaError_t.  b200q_last_error() returns the message (thread-local).
+ *   - Only sm_100 devices are accepted (b200q_device_check); there is no CPU fallback.
+ */
+#ifndef B200Q_H
+#define B200Q_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_C64 0
+#define B200Q_C128 1
+
+#define B200Q_EINVAL (-1)
+#define B200Q_EUNSUPPORTED (-2)
+#define B200Q_ENODEVICE (-3)
+
+/* gate kinds (what the planner may assume about the matrix *structure*; values stay on device) */
+#define B200Q_GATE_MAT 0  /* dense 2^k x 2^k                                 (gate.py get_matrix)   */
+#define B200Q_GATE_DIAG 1 /* diagonal 2^k x 2^k: Z,S,T,P,Rz,Rzz,...   (gate.py:737,1634,2295 ...)   */
+#define B200Q_GATE_X 2    /* Pauli-X on one target (+controls): X, CNOT, Toffoli (gate.py:841,1934)  */
+
+#define B200Q_GATE_ADJOINT 1 /* flags bit 0: apply the conjugate transpose (Gate.inverse, gate.py:417) */
+
+#define B200Q_MAX_TARGETS 6
+
+typedef struct b200q_gate {
+  int32_t kind;                       /* B200Q_GATE_*                                              */
+  int32_t n_targets;                  /* k                                                         */
+  int32_t targets[B200Q_MAX_TARGETS]; /* bit position of matrix-index bit j                        */
+  uint64_t controls;                  /* mask of control bit positions (operation.py:203-219)      */
+  int64_t mat_offset;                 /* element offset of this gate's matrix in the matrix buffer */
+  int32_t flags;
+  int32_t reserved;
+} b200q_gate_t;
+
+typedef struct b200q_plan_options {
+  int32_t chunk_bits; /* log2 of 16-byte chunks per tile (11..13); 0 = default (12, 64 KiB tiles)  */
+  int32_t low_bits;   /* contiguous low index bits kept in every tile; 0 = default                */
+  int32_t max_rounds; /* register rounds per pass; 0 = default                                     */
+  int32_t fuse;       /* 1 = fuse gates into passes (default), 0 = one gate per pass              */
+  int32_t reserved[4];
+} b200q_plan_options_t;
+
+typedef struct b200q_plan_stats {
+  int32_t n_gates, n_passes, n_rounds, n_ops, n_direct_ops, tile_bits, threads_per_cta, smem_bytes;
+} b200q_plan_stats_t;
+
+typedef struct b200q_plan b200q_plan_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* b200q_version(void);
+const char* b200q_last_error(void);
+/* 0 if `device` is an sm_100 (B200) GPU, B200Q_ENODEVICE otherwise. */
+int b200q_device_check(int device);
+
+/* ---- planner (host only): replaces the per-gate nn.Sequential walk of
+ *      QubitCircuit._forward_helper (circuit.py:244-263) by a fused pass schedule --------------- */
+int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
+                      const b200q_plan_options_t* options, b200q_plan_t** plan_out);
+void b200q_plan_destroy(b200q_plan_t* plan);
+int b200q_plan_get_stats(const b200q_plan_t* plan, b200q_plan_stats_t* stats_out);
+/* Number of gates executed by pass `pass_index` (for per-pass reporting). */
+int b200q_plan_pass_gates(const b200q_plan_t* plan, int pass_index);
+/* Copies the raw pass descriptors (b200q_pass_t, csrc/b200q_program.h) for inspection by tests.
+ * `*needed_out` receives the byte size; copies only if buf_size is large enough. */
+int b200q_plan_export(const b200q_plan_t* plan, void* buf, size_t buf_size, size_t* needed_out);
+
+/* ---- execution: replaces qmath.evolve_state (qmath.py:485-506) and Gate.op_state_control
+ *      (operation.py:203-219) for every gate of the plan, in place ----------------------------- */
+int b200q_plan_run(const b200q_plan_t* plan, void* state, const void* matrices, int64_t batch,
+                   int64_t matrix_batch_stride, void* stream);
+/* Run passes [first, last) only (per-pass timing in bench.py, overlap with exchanges). */
+int b200q_plan_run_range(const b200q_plan_t* plan, int first_pass, int last_pass, void* state,
+                         const void* matrices, int64_t batch, int64_t matrix_batch_stride, void* stream);
+/* One gate, no plan object: the direct counterpart of
+ *   evolve_state(state, matrix, nqudit, wires)            (qmath.py:485)      controls == NULL
+ *   Gate.op_state_control(x, matrix)                      (operation.py:203)  controls != NULL  */
+int b200q_apply_gate(void* state, int n_qubits, int dtype, int kind, const void* matrix, const int32_t* targets,
+                     int n_targets, const int32_t* controls, int n_controls, int adjoint, int64_t batch,
+                     int64_t matrix_batch_stride, void* stream);
+
+/* ---- reductions: qmath.expectation (qmath.py:830-860), inner_product_dist (distributed.py:288) */
+/* out_dev[b] = sum_i |state[b][i]|^2 */
+int b200q_norm2(const void* state, int n_qubits, int dtype, int64_t batch, double* out_dev, void* stream);
+/* out_dev[2b], out_dev[2b+1] = Re, Im of <bra[b]|ket[b]> */
+int b200q_inner_product(const void* bra, const void* ket, int n_qubits, int dtype, int64_t batch, double* out_dev,
+                        void* stream);
+/* out_dev[b*n_masks + m] = sum_i |state[b][i]|^2 * (-1)^popcount(i & masks[m])   (Z-string observables,
+ * layer.py:127-165 with basis 'z').  `masks_dev` is a device array of n_masks uint64.
+ * `index_offset` is OR-ed into i (rank offset of a shard, distributed.py:18). */
+int b200q_expectation_z(const void* state, int n_qubits, int dtype, int64_t batch, const uint64_t* masks_dev,
+                        int n_masks, uint64_t index_offset, double* out_dev, void* stream);
+/* lambda[i] = state[i] * sum_m w[m] * (-1)^popcount(i & masks[m]): the seed of the adjoint backward pass
+ * (adjoint.py:47-56) for a weighted sum of Z-string observables.  weights_dev: batch x n_masks doubles. */
+int b200q_apply_z_weights(const void* state, void* lambda_out, int n_qubits, int dtype, int64_t batch,
+                          const uint64_t* masks_dev, const double* weights_dev, int n_masks,
+                          uint64_t index_offset, void* stream);
+/* state[b][i] = (i == basis_index) ? 1 : 0    (QubitState 'zeros', state.py:31-44) */
+int b200q_init_basis(void* state, int n_qubits, int dtype, int64_t batch, uint64_t basis_index, void* stream);
+
+/* ---- adjoint differentiation (adjoint.py:47-83) ----------------------------------------------
+ * For the gates of `plan` taken in REVERSE order: psi <- U_g^dagger psi, then
+ *   grad_out[g][r][c] += sum_rest conj(lambda[r,rest]) * psi[c,rest]     (2^k x 2^k per gate)
+ * then lambda <- U_g^dagger lambda.  `grad_out` is a device buffer laid out like the matrix buffer
+ * (same offsets); gates with need_grad[g] == 0 are skipped in the accumulation. */
+int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const void* matrices, void* grad_out,
+                      const uint8_t* need_grad_host, void* stream);
+
+/* ---- qudit (Fock tensor) path: evolve_state(..., qudit = cutoff) as called by
+ *      photonic/operation.py:142-146.  `state` is [batch, d^n]; digit 0 is the MOST significant
+ *      (mode 0), `modes[0]` is the most significant digit of the matrix index (reference order). */
+int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
+                      int n_targets, int64_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H */

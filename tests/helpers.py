@@ -1,0 +1,98 @@
+"""Shared test helpers: lowering oracle ops to C-ABI gate records (test-side, classification by
+matrix structure) and loading the host emulator."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from deepquantum_b200 import _lib as L  # noqa: E402
+
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+def classify(matrix):
+    m = np.asarray(matrix)
+    if m.shape == (2, 2) and np.array_equal(m, _X):
+        return L.GATE_X
+    if np.count_nonzero(m - np.diag(np.diagonal(m))) == 0:
+        return L.GATE_DIAG
+    return L.GATE_MAT
+
+
+def lower_ops(ops, nqubit, dtype=np.complex128, split_big_diag=True):
+    """(matrix, wires, controls) triples -> (GateStruct array, flat matrix buffer)."""
+    gates, mats, off = [], [], 0
+    for matrix, wires, controls in ops:
+        m = np.asarray(matrix, dtype=dtype)
+        kind = classify(m)
+        k = len(wires)
+        targets = [nqubit - 1 - w for w in reversed(wires)]   # matrix LSB first
+        ctr = [nqubit - 1 - c for c in controls]
+        gates.append(L.make_gate(kind, targets, ctr, off))
+        mats.append(m.reshape(-1))
+        off += m.size
+    arr = (L.GateStruct * max(1, len(gates)))(*gates)
+    buf = np.concatenate(mats) if mats else np.zeros(1, dtype=dtype)
+    return arr, len(gates), np.ascontiguousarray(buf.astype(dtype))
+
+
+_emu = None
+
+
+def hostemu():
+    global _emu
+    if _emu is None:
+        sys.path.insert(0, os.path.join(ROOT, 'tests', 'native'))
+        import build as emu_build
+        lib = C.CDLL(emu_build.build())
+        lib.hostemu_run.restype = C.c_int
+        lib.hostemu_run.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int),
+                                    C.c_char_p, C.c_int]
+        _emu = lib
+    return _emu
+
+
+def emu_run(ops, nqubit, cdtype, state=None, chunk_bits=0, low_bits=0, max_rounds=0, fuse=1, batch=1):
+    """Run lowered ops through planner + CPU-stepped kernel body; returns (state, stats)."""
+    arr, ng, mats = lower_ops(ops, nqubit, cdtype)
+    if state is None:
+        state = np.zeros((batch, 2**nqubit), dtype=cdtype)
+        state[:, 0] = 1
+    else:
+        state = np.ascontiguousarray(np.asarray(state, dtype=cdtype).reshape(batch, 2**nqubit)).copy()
+    stats = (C.c_int * 4)()
+    err = C.create_string_buffer(256)
+    rc = hostemu().hostemu_run(nqubit, L.C64 if cdtype == np.complex64 else L.C128, arr, ng, chunk_bits, low_bits,
+                               max_rounds, fuse, state.ctypes.data, mats.ctypes.data, batch, 0, stats, err, 256)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return state, {'passes': stats[0], 'rounds': stats[1], 'ops': stats[2], 'direct': stats[3]}
+
+
+def emu_run_program(prog, nqubit, cdtype, state=None, batch=1, **opts):
+    """Run a product-side lowered program (`deepquantum_b200.circuit._Program`) through the CPU-stepped
+    kernel body.  TEST-ONLY executor for the host logic (lowering, matrix assembly, plan)."""
+    import torch
+    tdt = torch.complex64 if cdtype == np.complex64 else torch.complex128
+    mats_t = prog.low.build_matrices(tdt, 'cpu').detach()
+    mbs = mats_t.shape[-1] if mats_t.ndim == 2 else 0
+    mats = np.ascontiguousarray(mats_t.numpy())
+    arr = (L.GateStruct * max(1, len(prog.structs)))(*prog.structs)
+    if state is None:
+        state = np.zeros((batch, 2**nqubit), dtype=cdtype)
+        state[:, 0] = 1
+    else:
+        state = np.ascontiguousarray(np.asarray(state, dtype=cdtype).reshape(batch, 2**nqubit)).copy()
+    stats = (C.c_int * 4)()
+    err = C.create_string_buffer(256)
+    rc = hostemu().hostemu_run(nqubit, L.C64 if cdtype == np.complex64 else L.C128, arr, len(prog.structs),
+                               opts.get('chunk_bits', 0), opts.get('low_bits', 0), opts.get('max_rounds', 0),
+                               opts.get('fuse', 1), state.ctypes.data, mats.ctypes.data, batch, mbs, stats, err, 256)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return state, {'passes': stats[0], 'rounds': stats[1], 'ops': stats[2], 'direct': stats[3]}

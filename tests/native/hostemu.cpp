@@ -1,0 +1,79 @@
+// TEST-ONLY: steps the tile-kernel body (csrc/b200q_tile_body.h) thread by thread on the CPU so the
+// planner output and the kernel's index logic can be checked against the oracle without a GPU.
+// Never linked into libb200q.so; built by tests/native/build.py into tests/native/_build/.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../deepquantum_b200/csrc/b200q_planner.h"
+#include "../../deepquantum_b200/csrc/b200q_tile_body.h"
+
+using namespace b200q;
+
+namespace {
+template <typename Real>
+void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* mats_v, int64_t batch, int64_t mbs) {
+  using chunk = typename Traits<Real>::chunk;
+  constexpr int VS = Traits<Real>::VS;
+  const int cb = pl.opt.chunk_bits;
+  const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
+  std::vector<chunk> tile(size_t(1) << cb);
+  std::vector<cx<Real>> pool(B200Q_POOL_MAX);
+  const uint64_t chunks_per_state = (1ull << pl.n_qubits) >> VS;
+  const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
+  for (int64_t b = 0; b < batch; ++b) {
+    chunk* gstate = reinterpret_cast<chunk*>(state_v) + uint64_t(b) * chunks_per_state;
+    const cx<Real>* m = reinterpret_cast<const cx<Real>*>(mats_v) + b * mbs;
+    for (uint64_t t = 0; t < ntiles; ++t) {
+      const uint64_t cta_base = tile_base(P, t);
+      // poison the tile so that a read of an unwritten slot is caught
+      std::memset(tile.data(), 0xff, tile.size() * sizeof(chunk));
+      if (P.pool_elems)
+        for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m);
+      for (int r = 0; r < P.n_rounds; ++r) {
+        const b200q_round_t& Rd = P.rounds[r];
+        if (Rd.direct) {
+          for (int o = Rd.op_begin; o < Rd.op_end; ++o)
+            for (int tid = 0; tid < nthreads; ++tid)
+              run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile.data(), pool.data());
+        } else {
+          for (int tid = 0; tid < nthreads; ++tid)
+            run_round<Real>(P, Rd, tid, cta_base, tile.data(), pool.data(), gstate, chunks_per_state);
+        }
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
+                           int low_bits, int max_rounds, int fuse, void* state, const void* mats, int64_t batch,
+                           int64_t mbs, int* stats_out, char* err_out, int err_len) {
+  PlanOptions opt;
+  if (chunk_bits) opt.chunk_bits = chunk_bits;
+  if (low_bits) opt.low_bits = low_bits;
+  if (max_rounds) opt.max_rounds = max_rounds;
+  opt.fuse = fuse;
+  std::string err;
+  Plan* pl = make_plan(n_qubits, dtype, gates, n_gates, opt, &err);
+  if (!pl) {
+    if (err_out && err_len > 0) {
+      std::strncpy(err_out, err.c_str(), err_len - 1);
+      err_out[err_len - 1] = 0;
+    }
+    return -1;
+  }
+  for (const auto& P : pl->passes) {
+    if (dtype == B200Q_C64) run_pass<float>(*pl, P, state, mats, batch, mbs);
+    else run_pass<double>(*pl, P, state, mats, batch, mbs);
+  }
+  if (stats_out) {
+    stats_out[0] = pl->stats.n_passes;
+    stats_out[1] = pl->stats.n_rounds;
+    stats_out[2] = pl->stats.n_ops;
+    stats_out[3] = pl->stats.n_direct;
+  }
+  delete pl;
+  return 0;
+}

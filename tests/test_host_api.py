@@ -1,0 +1,138 @@
+"""Host side of the product package on CPU: gate matrices, lowering, matrix assembly, plan caching,
+`.to()` semantics, batching -- executed through the TEST-ONLY CPU emulator of the kernel body and
+compared with fixtures from the unmodified reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import deepquantum_b200 as dq
+from conftest import GOLDEN
+from deepquantum_b200 import workloads as wl
+from helpers import emu_run_program
+
+
+def _g(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def test_gate_matrices_match_reference():
+    g = _g('gate_matrices.npz')
+    th = g['theta']
+    consts = {'x': dq.PauliX, 'y': dq.PauliY, 'z': dq.PauliZ, 'h': dq.Hadamard, 's': dq.SGate, 'sdg': dq.SDaggerGate,
+              't': dq.TGate, 'tdg': dq.TDaggerGate, 'cnot': dq.CNOT, 'swap': dq.Swap, 'iswap': dq.ImaginarySwap,
+              'toffoli': dq.Toffoli, 'fredkin': dq.Fredkin}
+    for name, cls in consts.items():
+        m = cls().to(torch.double).matrix.numpy()
+        assert np.array_equal(m, g[name]), name
+    params = {'rx': dq.Rx, 'ry': dq.Ry, 'rz': dq.Rz, 'p': dq.PhaseShift, 'rxx': dq.Rxx, 'ryy': dq.Ryy,
+              'rzz': dq.Rzz, 'rxy': dq.Rxy, 'rbs': dq.ReconfigurableBeamSplitter}
+    for name, cls in params.items():
+        gate = cls(inputs=float(th[0])).to(torch.double)
+        np.testing.assert_allclose(gate.update_matrix().numpy(), g[name], atol=1e-15, err_msg=name)
+        np.testing.assert_allclose(gate.inverse().update_matrix().numpy(), g[name + '_inv'], atol=1e-15)
+    u3 = dq.U3Gate(inputs=[float(x) for x in th]).to(torch.double)
+    np.testing.assert_allclose(u3.update_matrix().numpy(), g['u3'], atol=1e-15)
+    np.testing.assert_allclose(u3.inverse().update_matrix().numpy(), g['u3_inv'], atol=1e-15)
+    for plane in ('xy', 'yz', 'zx'):
+        j = dq.ProjectionJ(inputs=float(th[0]), plane=plane).to(torch.double)
+        np.testing.assert_allclose(j.update_matrix().numpy(), g['j_' + plane], atol=1e-15)
+
+
+def _cases():
+    g = _g('circuits.npz')
+    return sorted({k.split('/')[0] for k in g.files if k.endswith('/spec') and not k.startswith('batched')})
+
+
+@pytest.mark.parametrize('case', _cases())
+def test_circuit_lowering_matches_reference(case):
+    g = _g('circuits.npz')
+    meta = json.loads(str(g[case + '/spec']))
+    n, spec = meta['n'], meta['spec']
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec, torch.complex128)
+    cir.to(torch.double)
+    out, stats = emu_run_program(cir._get_program(), n, np.complex128, chunk_bits=11 if n > 12 else 0)
+    ref = g[case + '/c128']
+    err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
+    assert err < 1e-12, (err, stats)
+    cir32 = dq.QubitCircuit(n)
+    wl.apply_spec(cir32, spec)
+    out32, _ = emu_run_program(cir32._get_program(), n, np.complex64, chunk_bits=11 if n > 12 else 0)
+    assert np.linalg.norm(out32[0] - ref) / np.linalg.norm(ref) < 3e-6
+
+
+def test_inverse_circuit_roundtrip():
+    n = 6
+    spec = wl.random_clifford_rx_spec(n, 6, seed=11)
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec)
+    cir.u3(2, [0.3, 0.2, 0.1], controls=[4])
+    cir.to(torch.double)
+    full = cir + cir.inverse()
+    out, _ = emu_run_program(full._get_program(), n, np.complex128)
+    expect = np.zeros(2**n)
+    expect[0] = 1
+    # constants are float32-rounded even in the complex128 path (like the reference), so H*H != 1 exactly
+    np.testing.assert_allclose(out[0], expect, atol=5e-6)
+
+
+def test_batched_data_matrices():
+    """2-D data: one matrix set per sample (the reference vmaps `_forward_helper`, circuit.py:227-241)."""
+    n = 4
+    cir = dq.QubitCircuit(n)
+    cir.hlayer()
+    cir.rxlayer(encode=True)
+    cir.cnot_ring()
+    cir.rz(1, encode=True)
+    cir.to(torch.double)
+    data = torch.tensor([[0.1, 0.2, 0.3, 0.4, 0.5], [1.1, 1.2, 1.3, 1.4, 1.5], [2.1, 2.2, 2.3, 2.4, 2.5]],
+                        dtype=torch.float64)
+    cir._encode_batched(data)
+    out, _ = emu_run_program(cir._get_program(), n, np.complex128, batch=3)
+    for b in range(3):
+        single = dq.QubitCircuit(n)
+        single.hlayer()
+        single.rxlayer(inputs=data[b, :4].tolist())
+        single.cnot_ring()
+        single.rz(1, float(data[b, 4]))
+        single.to(torch.double)
+        for gate, v in zip([op for op in single.operators if op.npara], data[b]):
+            gate.init_para(v)   # exact float64 angles
+        ref, _ = emu_run_program(single._get_program(), n, np.complex128)
+        np.testing.assert_allclose(out[b], ref[0], atol=1e-14)
+
+
+def test_plan_is_cached_and_invalidated():
+    cir = dq.QubitCircuit(5)
+    cir.hlayer()
+    p1 = cir._get_program()
+    assert cir._get_program() is p1
+    cir.cnot(0, 1)
+    assert cir._get_program() is not p1
+
+
+def test_to_double_and_state_dict():
+    cir = dq.QubitCircuit(3)
+    cir.h(0)
+    cir.rx(1)
+    cir.rz(2, 0.5)
+    assert cir.init_state.state.dtype == torch.complex64
+    cir.to(torch.double)
+    assert cir.init_state.state.dtype == torch.complex128
+    assert cir.operators[0].matrix.dtype == torch.complex128
+    assert cir.operators[1].theta.dtype == torch.float64
+    assert isinstance(cir.operators[1].theta, torch.nn.Parameter)      # trainable (circuit.py:1047-1051)
+    assert not isinstance(cir.operators[2].theta, torch.nn.Parameter)  # fixed input -> buffer
+    assert cir.npara == 2 and cir.ndata == 0
+    sd = cir.state_dict()
+    assert 'operators.1.theta' in sd and 'init_state.state' in sd
+
+
+def test_lazy_zero_state_is_not_materialised():
+    st = dq.QubitState(30)
+    assert 'state' not in st._buffers
+    st.to(torch.double)
+    assert st.dtype == torch.complex128

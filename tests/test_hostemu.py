@@ -1,0 +1,88 @@
+"""Planner + tile-kernel body, stepped on the CPU (tests/native/hostemu.cpp), against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gates_np
+import statevec_oracle as so
+from conftest import GOLDEN
+from helpers import emu_run
+
+
+def _golden_cases():
+    g = np.load(os.path.join(GOLDEN, 'circuits.npz'))
+    return sorted({k.split('/')[0] for k in g.files if k.endswith('/spec') and not k.startswith('batched')})
+
+
+@pytest.mark.parametrize('case', _golden_cases())
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_golden_circuits(case, cdtype):
+    g = np.load(os.path.join(GOLDEN, 'circuits.npz'))
+    meta = json.loads(str(g[case + '/spec']))
+    n, spec = meta['n'], meta['spec']
+    ops = gates_np.lower_spec(spec, n)
+    out, stats = emu_run(ops, n, cdtype, chunk_bits=11 if n > 12 else 0)
+    ref = g[case + '/c128']
+    err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
+    assert err < (1e-12 if cdtype == np.complex128 else 3e-6), (err, stats)
+    assert stats['passes'] >= 1
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 5, 6, 7])
+def test_tiny_states(n, cdtype):
+    rng = np.random.default_rng(n)
+    ops = []
+    for _ in range(12):
+        w = int(rng.integers(n))
+        ops.append((gates_np.u3(*rng.uniform(0, 6, 3)), [w], []))
+        if n > 1:
+            c = int((w + 1 + rng.integers(n - 1)) % n)
+            ops.append((gates_np.X, [w], [c]))
+            ops.append((gates_np.rz(0.3), [c], [w]))
+    ref = so.run_circuit(ops, n)
+    out, _ = emu_run(ops, n, cdtype)
+    assert np.linalg.norm(out[0] - ref) < (1e-12 if cdtype == np.complex128 else 2e-6)
+
+
+@pytest.mark.parametrize('fuse', [0, 1])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_every_bit_position_and_unfused(fuse, cdtype):
+    """1-target, controlled, diagonal and dense k-target gates on every wire of a 14/15-qubit state
+    (more than one tile with the smallest tile size), fused and one-gate-per-pass."""
+    n = 14 if cdtype == np.complex128 else 15
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    ops = []
+    for w in range(n):
+        ops.append((gates_np.u3(*rng.uniform(0, 6, 3)), [w], []))
+        ops.append((gates_np.X, [w], [(w + 3) % n, (w + 7) % n]))
+        ops.append((gates_np.rz(0.7 + w), [w], []))
+        ops.append((gates_np.rzz(0.2 + w), [w, (w + 5) % n], [(w + 1) % n]))
+        ops.append((gates_np.ry(0.4 + w), [(w + 2) % n], [w]))
+    q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+    ops.append((q, [n - 1, 2], []))
+    ops.append((q, [0, n - 2], [5]))
+    q3, _ = np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))
+    ops.append((q3, [1, n - 1, 6], []))
+    q4, _ = np.linalg.qr(rng.normal(size=(16, 16)) + 1j * rng.normal(size=(16, 16)))
+    ops.append((q4, [3, 0, n - 3, 8], [1]))
+    ref = so.run_circuit(ops, n, state=psi)
+    out, stats = emu_run(ops, n, cdtype, state=psi, chunk_bits=11, fuse=fuse)
+    err = np.linalg.norm(out[0] - ref)
+    assert err < (1e-12 if cdtype == np.complex128 else 3e-6), (err, stats)
+    if fuse:
+        assert stats['passes'] < len(ops) / 3
+    else:
+        assert stats['passes'] == len(ops)
+
+
+def test_batched_states():
+    g = np.load(os.path.join(GOLDEN, 'circuits.npz'))
+    meta = json.loads(str(g['batched_n6/spec']))
+    ops = gates_np.lower_spec(meta['spec'], meta['n'])
+    out, _ = emu_run(ops, meta['n'], np.complex128, state=g['batched_n6/init'], batch=3)
+    np.testing.assert_allclose(out, g['batched_n6/c128'], atol=1e-13)

@@ -96,6 +96,12 @@ class QubitCircuit(Operation):
         cir.wires_measure = rhs.wires_measure
         return cir
 
+    def _apply(self, fn):
+        super()._apply(fn)
+        if self._program is not None:
+            self._program.low._const_cache.clear()
+        return self
+
     # ---------------------------------------------------------------------------------------------
     def _get_program(self) -> _Program:
         if self._program is None or self._program_len != len(self.operators):
@@ -300,8 +306,7 @@ class QubitCircuit(Operation):
     def get_unitary(self) -> torch.Tensor:
         """Global unitary (small n): the circuit applied to the identity (reference circuit.py:467-477)."""
         dim = 2**self.nqubit
-        ref = self.init_state.state
-        eye = torch.eye(dim, dtype=ref.dtype, device=ref.device)
+        eye = torch.eye(dim, dtype=self.init_state.dtype, device=self.init_state.device)
         prog = self._get_program()
         mats = prog.low.build_matrices(eye.dtype, eye.device)
         y = eye.contiguous().clone()
@@ -338,8 +343,7 @@ class QubitCircuit(Operation):
                 cir.encoders.append(op_inv)
         cir.npara, cir.ndata = (self.npara, self.ndata) if encode else (self.npara + self.ndata, 0)
         cir.depth = self.depth.copy()
-        ref = self.init_state.state
-        cir.to(ref.device, ref.real.dtype)
+        cir.to(self.init_state.device, torch.empty(0, dtype=self.init_state.dtype).real.dtype)
         return cir
 
     def max_depth(self) -> int:

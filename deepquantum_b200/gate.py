@@ -258,6 +258,7 @@ class PhaseShift(ParametricSingleGate):
 
 
 class _ConstSingle(SingleGate):
+    _shared_const = True
     _matrix_entries = None
     _default_name = None
 

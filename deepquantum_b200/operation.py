@@ -97,6 +97,8 @@ class Lowering:
         self.dynamic = []      # gates whose update_matrix() is evaluated every forward
         self.groups = {}       # class -> list of gates
         self.sources = []      # gate object per record (None for X records)
+        self._const_index = {}
+        self._const_cache = {}
 
     def add(self, gate: 'Gate', kind: int, wires, controls, adjoint: bool = False, matrix_of: 'Gate | None' = None):
         n = self.nqubit
@@ -107,8 +109,12 @@ class Lowering:
         if kind == L.GATE_X:
             block, idx = 'none', 0
         elif src._matrix_source == 'const':
-            block, idx = 'const', len(self.const)
-            self.const.append(src.matrix)
+            # gates of a class with a class-wide constant matrix (H, S, T, ...) share one buffer entry
+            key = type(src) if getattr(src, '_shared_const', False) else id(src)
+            if key not in self._const_index:
+                self._const_index[key] = len(self.const)
+                self.const.append(src)
+            block, idx = 'const', self._const_index[key]
         elif src._matrix_source == 'group':
             lst = self.groups.setdefault(type(src), [])
             block, idx = type(src), len(lst)
@@ -152,7 +158,11 @@ class Lowering:
         parameters."""
         parts = []
         if self.const:
-            parts.append(torch.cat([m.reshape(-1) for m in self.const]).to(device=device, dtype=cdtype))
+            key = (cdtype, str(device))
+            if key not in self._const_cache:   # invalidated by QubitCircuit._apply (dtype / device moves)
+                self._const_cache[key] = torch.cat([g.matrix.reshape(-1).to(device=device, dtype=cdtype)
+                                                    for g in self.const])
+            parts.append(self._const_cache[key])
         if self.dynamic:
             parts.append(torch.cat([g.update_matrix().reshape(-1) for g in self.dynamic]).to(device=device,
                                                                                              dtype=cdtype))

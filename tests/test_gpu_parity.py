@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI / the product API) with the CPU oracle and the
+reference-generated fixtures.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gates_np
+import statevec_oracle as so
+from conftest import GOLDEN
+from helpers import lower_ops
+
+import deepquantum_b200 as dq
+from deepquantum_b200 import _lib as L
+from deepquantum_b200 import engine
+from deepquantum_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+# tolerances: complex128 engine vs complex128 reference rel-L2 <= 1e-10;
+# complex64 engine vs complex128 reference rel-L2 <= 2e-6 at depth <= 40 (the reference's own complex64
+# path sits at 6-8e-7 there).
+TOL = {np.complex128: 1e-10, np.complex64: 2e-6}
+
+
+def _golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _cases():
+    g = _golden('circuits.npz')
+    return sorted({k.split('/')[0] for k in g.files if k.endswith('/spec') and not k.startswith('batched')})
+
+
+def _run_ops_gpu(ops, n, cdtype, state=None, batch=1, **opts):
+    arr, ng, mats = lower_ops(ops, n, cdtype)
+    tdt = torch.complex64 if cdtype == np.complex64 else torch.complex128
+    if state is None:
+        st = torch.zeros(batch, 2**n, dtype=tdt, device='cuda')
+        st[:, 0] = 1
+    else:
+        st = torch.tensor(np.asarray(state).reshape(batch, 2**n), dtype=tdt, device='cuda').contiguous()
+    plan = engine.FusedPlan(n, tdt, list(arr)[:ng], **opts)
+    plan.run(st, torch.tensor(mats, device='cuda'), batch, 0)
+    torch.cuda.synchronize()
+    return st.cpu().numpy(), plan
+
+
+@pytest.mark.parametrize('case', _cases())
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_golden_circuits_product_api(case, rdtype):
+    g = _golden('circuits.npz')
+    meta = json.loads(str(g[case + '/spec']))
+    n, spec = meta['n'], meta['spec']
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec, torch.complex128 if rdtype == torch.float64 else torch.complex64)
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy()
+    ref = g[case + '/c128']
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < (1e-10 if rdtype == torch.float64 else 2e-6), err
+    if rdtype == torch.float32:   # and against the reference's own complex64 result
+        assert np.linalg.norm(out - g[case + '/c64']) / np.linalg.norm(ref) < 3e-6
+
+
+@pytest.mark.parametrize('chunk_bits', [11, 12, 13])
+@pytest.mark.parametrize('fuse', [True, False])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_every_bit_position(chunk_bits, fuse, cdtype):
+    n = 16
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    ops = []
+    for w in range(n):
+        ops.append((gates_np.u3(*rng.uniform(0, 6, 3)), [w], []))
+        ops.append((gates_np.X, [w], [(w + 3) % n, (w + 7) % n]))
+        ops.append((gates_np.rz(0.7 + w), [w], []))
+        ops.append((gates_np.rzz(0.2 + w), [w, (w + 5) % n], [(w + 1) % n]))
+        ops.append((gates_np.ry(0.4 + w), [(w + 2) % n], [w]))
+    for k, wires, ctr in [(2, [n - 1, 2], []), (2, [0, n - 2], [5]), (3, [1, n - 1, 6], []), (4, [3, 0, n - 3, 8], [1])]:
+        q, _ = np.linalg.qr(rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k)))
+        ops.append((q, wires, ctr))
+    ref = so.run_circuit(ops, n, state=psi)
+    out, plan = _run_ops_gpu(ops, n, cdtype, state=psi, chunk_bits=chunk_bits, fuse=fuse)
+    err = np.linalg.norm(out[0] - ref)
+    assert err < TOL[cdtype], (err, plan.stats)
+    assert plan.n_passes == (len(ops) if not fuse else plan.n_passes)
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 8])
+def test_tiny_states(n, cdtype):
+    rng = np.random.default_rng(n)
+    ops = []
+    for _ in range(10):
+        w = int(rng.integers(n))
+        ops.append((gates_np.u3(*rng.uniform(0, 6, 3)), [w], []))
+        if n > 1:
+            c = int((w + 1 + rng.integers(n - 1)) % n)
+            ops.append((gates_np.X, [w], [c]))
+            ops.append((gates_np.rz(0.3), [c], [w]))
+    ref = so.run_circuit(ops, n)
+    out, _ = _run_ops_gpu(ops, n, cdtype)
+    assert np.linalg.norm(out[0] - ref) < TOL[cdtype]
+
+
+def test_batched_initial_states():
+    g = _golden('circuits.npz')
+    meta = json.loads(str(g['batched_n6/spec']))
+    n = meta['n']
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, meta['spec'])
+    cir.to('cuda', torch.double)
+    init = torch.tensor(g['batched_n6/init'], device='cuda').unsqueeze(-1)
+    out = cir(state=init)
+    assert out.shape == (3, 2**n, 1)
+    np.testing.assert_allclose(out.squeeze(-1).cpu().numpy(), g['batched_n6/c128'], atol=1e-12)
+
+
+def test_batched_data():
+    n = 5
+    cir = dq.QubitCircuit(n)
+    cir.hlayer()
+    cir.rxlayer(encode=True)
+    cir.cnot_ring()
+    cir.rzz([0, 3], encode=True)
+    cir.to('cuda', torch.double)
+    data = torch.rand(4, 6, dtype=torch.float64, device='cuda')
+    out = cir(data)
+    assert out.shape == (4, 2**n, 1)
+    for b in range(4):
+        ops = [(gates_np.H, [q], []) for q in range(n)]
+        ops += [(gates_np.rx(float(data[b, q])), [q], []) for q in range(n)]
+        ops += [(gates_np.CNOT, [q, (q + 1) % n], []) for q in range(n)]
+        ops += [(gates_np.rzz(float(data[b, 5])), [0, 3], [])]
+        ref = so.run_circuit(ops, n)
+        np.testing.assert_allclose(out[b, :, 0].cpu().numpy(), ref, atol=1e-12)
+
+
+def test_evolve_state_boundary_noncontiguous():
+    """qmath.evolve_state semantics: any strides in, same shape out, input untouched."""
+    n = 7
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=(2, 2**n)) + 1j * rng.normal(size=(2, 2**n))
+    u = gates_np.u3(0.3, 0.9, -1.2)
+    x = torch.tensor(psi, device='cuda').reshape([2] + [2] * n).permute(0, 3, 1, 2, 4, 5, 6, 7)
+    keep = x.clone()
+    # undo the permutation logically: wire order of x is (2,0,1,3,...)
+    y = dq.evolve_state(x, torch.tensor(u, device='cuda'), n, [1])
+    assert y.shape == x.shape and torch.equal(x, keep)
+    ref = so.evolve_state(np.ascontiguousarray(keep.cpu().numpy()).reshape(2, -1), u, n, [1])
+    np.testing.assert_allclose(y.reshape(2, -1).cpu().numpy(), ref, atol=1e-13)
+    q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+    y2 = dq.evolve_state(torch.tensor(psi, device='cuda').reshape([2] + [2] * n), torch.tensor(q, device='cuda'), n,
+                         [5, 2])
+    np.testing.assert_allclose(y2.reshape(2, -1).cpu().numpy(), so.evolve_state(psi, q, n, [5, 2]), atol=1e-13)
+
+
+def test_gate_modules_standalone():
+    """`dq.Rx(theta)(state)` style use (tutorials/basics.ipynb cells 9-18 of the reference)."""
+    one = torch.tensor([0, 1], dtype=torch.cfloat, device='cuda')
+    out = dq.PauliX().to('cuda')(one)
+    np.testing.assert_allclose(out.reshape(-1).cpu().numpy(), [1, 0], atol=1e-7)
+    out = dq.Rx(torch.pi / 2).to('cuda')(one)
+    np.testing.assert_allclose(out.reshape(-1).cpu().numpy(), [-0.70710678j, 0.70710678], atol=1e-6)
+    st = torch.zeros(4, dtype=torch.cfloat, device='cuda')
+    st[0] = 1
+    out = dq.Swap(nqubit=2, wires=[0, 1]).to('cuda')(dq.PauliX(nqubit=2, wires=[1]).to('cuda')(st))
+    np.testing.assert_allclose(out.reshape(-1).cpu().numpy(), [0, 0, 1, 0], atol=1e-7)
+
+
+def test_expectation_pauli_strings():
+    n = 9
+    spec = wl.random_clifford_rx_spec(n, 6, seed=21)
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec)
+    obs = [([0], 'z'), ([1, 5], 'zz'), ([2, 3, 8], 'xyz'), ([4], 'y'), ([7, 6], 'xx'), ([0, 4, 8], 'zzz')]
+    for w, b in obs:
+        cir.observable(w, b)
+    cir.to('cuda', torch.double)
+    psi = cir().reshape(-1).cpu().numpy()
+    ref = so.run_circuit(gates_np.lower_spec(spec, n), n)
+    assert np.linalg.norm(psi - ref) < 1e-10
+    exp = cir.expectation().cpu().numpy()
+    want = [so.expectation_pauli(ref, n, w, b) for w, b in obs]
+    np.testing.assert_allclose(exp, want, atol=1e-10)
+
+
+def test_reductions():
+    n = 18
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    b = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    for tdt, tol in ((torch.complex128, 1e-12), (torch.complex64, 1e-5)):
+        ta, tb = torch.tensor(a, dtype=tdt, device='cuda'), torch.tensor(b, dtype=tdt, device='cuda')
+        assert abs(float(engine.norm2(ta, n)[0]) / np.vdot(a, a).real - 1) < tol
+        ip = complex(engine.inner_product(ta, tb, n)[0])
+        assert abs(ip - np.vdot(a, b)) / abs(np.vdot(a, b)) < max(tol, 1e-4 if tdt == torch.complex64 else 0)
+
+
+@pytest.mark.parametrize('rdtype,n', [(torch.float32, 26), (torch.float64, 25)])
+def test_large_state_properties(rdtype, n):
+    """Full-size behaviour through size-independent properties: norm preservation and the
+    circuit + inverse round trip back to |0...0> (exact inverses only: rotations and CX)."""
+    g = torch.Generator().manual_seed(3)
+    cir = dq.QubitCircuit(n)
+    for _ in range(3):
+        ang = (torch.rand(n, 3, generator=g) * 6).tolist()
+        for q in range(n):
+            cir.u3(q, ang[q])
+        perm = torch.randperm(n, generator=g).tolist()
+        for i in range(0, n - 1, 2):
+            cir.cx(perm[i], perm[i + 1])
+        cir.rzz([perm[0], perm[-1]], 0.3)
+    cir.to('cuda', rdtype)
+    psi = cir()
+    tol = 1e-4 if rdtype == torch.float32 else 1e-11
+    assert abs(float(engine.norm2(psi.reshape(-1), n)[0]) - 1) < tol
+    full = cir + cir.inverse()
+    back = full().reshape(-1)
+    assert abs(abs(complex(back[0])) - 1) < tol
+    assert float(engine.norm2(back, n)[0]) - abs(complex(back[0]))**2 < tol

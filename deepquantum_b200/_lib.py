@@ -12,6 +12,8 @@ import os
 C64, C128 = 0, 1
 GATE_MAT, GATE_DIAG, GATE_X = 0, 1, 2
 GATE_ADJOINT = 1
+GATE_REAL = 2
+GATE_RXLIKE = 4
 MAX_TARGETS = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libb200q.so')
@@ -104,7 +106,7 @@ def check(rc: int):
         raise B200QError(f'b200q error {rc}: {msg}')
 
 
-def make_gate(kind, targets, controls=(), mat_offset=0, adjoint=False) -> GateStruct:
+def make_gate(kind, targets, controls=(), mat_offset=0, adjoint=False, hint=0) -> GateStruct:
     g = GateStruct()
     g.kind = kind
     g.n_targets = len(targets)
@@ -115,5 +117,5 @@ def make_gate(kind, targets, controls=(), mat_offset=0, adjoint=False) -> GateSt
         mask |= 1 << int(c)
     g.controls = mask
     g.mat_offset = int(mat_offset)
-    g.flags = GATE_ADJOINT if adjoint else 0
+    g.flags = (GATE_ADJOINT if adjoint else 0) | hint
     return g

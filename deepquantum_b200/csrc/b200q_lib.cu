@@ -53,7 +53,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
   const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
 
   if (P.pool_elems) {
-    fill_pool<Real>(P, tid, nthreads, pool, m);
+    fill_pool<Real>(P, tid, nthreads, pool, m, false);
     __syncthreads();
   }
   const int nr = P.n_rounds;
@@ -117,6 +117,69 @@ int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const vo
     }
   }
   return set_err(B200Q_EUNSUPPORTED, "chunk_bits must be 11, 12 or 13");
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint (reverse) sweep kernel: two tiles (psi, lambda) per CTA
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int CB>
+__global__ void __launch_bounds__(TileCfg<CB>::kThreads, 1)
+b200q_adjoint_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ psi,
+                     typename Traits<Real>::chunk* __restrict__ lam, const cx<Real>* __restrict__ mats,
+                     double* __restrict__ grad, uint64_t want_mask, uint64_t chunks_per_state) {
+  using chunk = typename Traits<Real>::chunk;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  chunk* tile_psi = reinterpret_cast<chunk*>(smem_raw);
+  chunk* tile_lam = reinterpret_cast<chunk*>(smem_raw + (size_t(16) << CB));
+  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(32) << CB));
+  double* acc = reinterpret_cast<double*>(smem_raw + (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>));
+  const int tid = threadIdx.x;
+  const int nthreads = TileCfg<CB>::kThreads;
+  const uint64_t cta_base = tile_base(P, blockIdx.x);
+  for (int e = tid; e < int(P.n_ops) * B200Q_ACC_PER_OP; e += nthreads) acc[e] = 0.0;
+  if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, mats, true);
+  __syncthreads();
+  for (int r = int(P.n_rounds) - 1; r >= 0; --r) {
+    const b200q_round_t& Rd = P.rounds[r];
+    if (Rd.direct) {
+      for (int o = int(Rd.op_end) - 1; o >= int(Rd.op_begin); --o) {
+        run_direct_op_adjoint<Real>(P, P.ops[o], tid, nthreads, cta_base, tile_psi, tile_lam, pool,
+                                    (want_mask >> o) & 1ull, acc + o * B200Q_ACC_PER_OP);
+        __syncthreads();
+      }
+    } else {
+      run_round_adjoint<Real>(P, Rd, tid, cta_base, tile_psi, tile_lam, pool, psi, lam, chunks_per_state, want_mask,
+                              acc);
+      __syncthreads();
+    }
+  }
+  if (want_mask) flush_grad(P, tid, nthreads, want_mask, acc, grad, [](double* p, double v) { atomicAdd(p, v); });
+}
+
+template <typename Real, int CB>
+int launch_adjoint_pass(const b200q_pass_t& P, void* psi, void* lam, const void* mats, void* grad, uint64_t want_mask,
+                        int n_qubits, cudaStream_t stream) {
+  using chunk = typename Traits<Real>::chunk;
+  constexpr int VS = Traits<Real>::VS;
+  const size_t smem = (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>) +
+                      size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP * sizeof(double);
+  auto kern = b200q_adjoint_kernel<Real, CB>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute(adjoint)");
+    if (rc) return rc;
+    attr_set[dev] = true;
+  }
+  const uint64_t chunks_per_state = (1ull << n_qubits) >> VS;
+  const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
+  if (ntiles > 0x7fffffffull) return set_err(B200Q_EUNSUPPORTED, "too many tiles for one launch");
+  kern<<<(unsigned)ntiles, TileCfg<CB>::kThreads, smem, stream>>>(
+      P, reinterpret_cast<chunk*>(psi), reinterpret_cast<chunk*>(lam), reinterpret_cast<const cx<Real>*>(mats),
+      reinterpret_cast<double*>(grad), want_mask, chunks_per_state);
+  return cuda_err(cudaGetLastError(), "adjoint kernel launch");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -477,8 +540,39 @@ int b200q_init_basis(void* state, int n_qubits, int dtype, int64_t batch, uint64
   return cuda_err(cudaGetLastError(), "init_basis launch");
 }
 
-int b200q_adjoint_run(const b200q_plan_t*, void*, void*, const void*, void*, const uint8_t*, void*) {
-  return set_err(B200Q_EUNSUPPORTED, "b200q_adjoint_run: not built yet");
+int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const void* matrices, void* grad_out,
+                      const uint8_t* need_grad_host, void* stream) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  const Plan& p = *plan->p;
+  int rc = check_state_args(psi, p.n_qubits, p.dtype, 1);
+  if (rc) return rc;
+  if (!lambda || !matrices || !grad_out) return set_err(B200Q_EINVAL, "null argument");
+  const int cb = p.opt.chunk_bits;
+  if (cb > 12) return set_err(B200Q_EUNSUPPORTED, "the adjoint sweep holds two tiles per CTA: plan with chunk_bits <= 12");
+  for (int i = (int)p.passes.size() - 1; i >= 0; --i) {
+    const b200q_pass_t& P = p.passes[i];
+    uint64_t want = 0;
+    for (int o = 0; o < P.n_ops; ++o) {
+      const b200q_op_t& op = P.ops[o];
+      if (op.kind == B200Q_OP_X) continue;
+      const bool need = need_grad_host ? need_grad_host[op.gate_id] != 0 : true;
+      if (!need) continue;
+      if (op.kind == B200Q_OP_MATK && op.k > 2) {
+        if (need_grad_host) return set_err(B200Q_EUNSUPPORTED, "gradient of dense gates on more than 2 targets");
+        continue;
+      }
+      want |= 1ull << o;
+    }
+    if (p.dtype == B200Q_C64) {
+      rc = cb == 11 ? launch_adjoint_pass<float, 11>(P, psi, lambda, matrices, grad_out, want, p.n_qubits, (cudaStream_t)stream)
+                    : launch_adjoint_pass<float, 12>(P, psi, lambda, matrices, grad_out, want, p.n_qubits, (cudaStream_t)stream);
+    } else {
+      rc = cb == 11 ? launch_adjoint_pass<double, 11>(P, psi, lambda, matrices, grad_out, want, p.n_qubits, (cudaStream_t)stream)
+                    : launch_adjoint_pass<double, 12>(P, psi, lambda, matrices, grad_out, want, p.n_qubits, (cudaStream_t)stream);
+    }
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int b200q_qudit_apply(void*, int, int, int, const void*, const int32_t*, int, int64_t, void*) {

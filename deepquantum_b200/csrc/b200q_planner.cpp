@@ -270,10 +270,13 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         b200q_op_t& op = P.ops[n_ops++];
         std::memset(&op, 0, sizeof(op));
         op.kind = (uint8_t)a.op_kind;
-        op.flags = (uint8_t)((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0);
+        op.flags = (uint8_t)(((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0) |
+                             ((a.flags & B200Q_GATE_REAL) ? B200Q_FLAG_REAL : 0) |
+                             ((a.flags & B200Q_GATE_RXLIKE) ? B200Q_FLAG_RXLIKE : 0));
         op.mat_src = (uint32_t)a.mat;
         op.gate_id = (uint32_t)gi;
         op.k = (uint8_t)a.k;
+        op.dsel_slot[0] = op.dsel_slot[1] = 0xff;
         for (uint64_t c = a.ctrl; c; c &= c - 1) {
           const int b = __builtin_ctzll(c);
           if (slot_of[b] >= 0) op.ctrl_reg |= 1u << slot_of[b];
@@ -285,12 +288,8 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         } else if (a.op_kind == B200Q_OP_DIAG) {
           for (int j = 0; j < a.k; ++j) {
             const int b = a.t[j];
-            if (slot_of[b] >= 0) {
-              uint32_t bm = 0;
-              for (int i = 0; i < B.na; ++i)
-                if (i >> slot_of[b] & 1) bm |= 1u << i;
-              op.dsel_reg[j] = bm;
-            } else if (loc_of[b] >= 0) op.dsel_loc[j] = 1u << loc_of[b];
+            if (slot_of[b] >= 0) op.dsel_slot[j] = (uint8_t)slot_of[b];
+            else if (loc_of[b] >= 0) op.dsel_loc[j] = 1u << loc_of[b];
             else op.dsel_glob[j] = 1ull << b;
           }
         }
@@ -303,7 +302,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         ++gates_in_pass;
       }
       Rd.op_end = (uint16_t)n_ops;
-      for (size_t k = 0; k < nr.size(); ++k) Rd.nonreg_bit[k] = (uint8_t)nr[k];
+      for (size_t k = 0; k < nr.size() && k < sizeof(Rd.nonreg_bit); ++k) Rd.nonreg_bit[k] = (uint8_t)nr[k];
       return &Rd;
     };
 
@@ -318,7 +317,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         else rest.push_back(j);
       }
       front.insert(front.end(), rest.begin(), rest.end());
-      for (int k = 0; k < nn; ++k) Rd->nonreg_bit[k] = (uint8_t)front[k];
+      for (int k = 0; k < nn && k < (int)sizeof(Rd->nonreg_bit); ++k) Rd->nonreg_bit[k] = (uint8_t)front[k];
     };
 
     std::vector<int> list, list2;
@@ -368,6 +367,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         op.flags = (uint8_t)((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0);
         op.mat_src = (uint32_t)a.mat;
         op.gate_id = (uint32_t)mk[0];
+        op.dsel_slot[0] = op.dsel_slot[1] = 0xff;
         for (int j = 0; j < a.k; ++j) op.tk[j] = (uint8_t)loc_of[a.t[j]];
         for (uint64_t c = a.ctrl; c; c &= c - 1) {
           const int b = __builtin_ctzll(c);
@@ -407,6 +407,12 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     plan->stats.n_ops += n_ops;
   }
   plan->stats.n_passes = (int)plan->passes.size();
+  // complex64: the state BETWEEN passes is kept in the SoA chunk format (see b200q_program.h)
+  if (dtype == B200Q_C64) {
+    const int np = (int)plan->passes.size();
+    for (int i = 0; i < np; ++i)
+      plan->passes[i].layout = (uint8_t)((i > 0 ? B200Q_LAYOUT_SRC_SOA : 0) | (i + 1 < np ? B200Q_LAYOUT_DST_SOA : 0));
+  }
   return plan;
 }
 

@@ -13,6 +13,11 @@
 // targets are register slots are applied in registers; between rounds the tile is transposed through
 // shared memory.  The first round reads straight from global memory, the last one writes straight
 // back, so a pass whose gates fit one round never touches shared memory.
+//
+// complex64 chunks have two formats: AoS (re0, im0, re1, im1) -- the caller-visible layout of the
+// state -- and SoA (re0, re1, im0, im1), which a multi-pass plan uses for the state BETWEEN its
+// passes and always inside shared memory, so that a 128-bit load lands directly in the register
+// pairs that the packed FFMA2 arithmetic (two amplitudes per instruction) consumes.
 #pragma once
 #include <stdint.h>
 
@@ -31,7 +36,12 @@ enum {
   B200Q_OP_MATK = 3   // dense 2^k x 2^k, k = 2..4, on arbitrary tile bits, applied from shared memory
 };
 
-#define B200Q_FLAG_ADJOINT 1u /* use the conjugate transpose of the stored matrix */
+#define B200Q_FLAG_ADJOINT 1u  /* use the conjugate transpose of the stored matrix */
+#define B200Q_FLAG_REAL 2u     /* MAT1: every entry is real (H, Ry, ...)                      */
+#define B200Q_FLAG_RXLIKE 4u   /* MAT1: diagonal real, off-diagonal purely imaginary (Rx)    */
+
+#define B200Q_LAYOUT_SRC_SOA 1u /* pass reads complex64 chunks as (re0,re1,im0,im1) */
+#define B200Q_LAYOUT_DST_SOA 2u /* pass writes them so */
 
 typedef struct {
   uint8_t kind;
@@ -43,11 +53,12 @@ typedef struct {
   uint32_t mat_src;  // element offset of the dense 2^k x 2^k row-major matrix in the device buffer
   uint32_t ctrl_reg; // controls that are register slots: mask over the register amplitude index
   uint32_t ctrl_loc; // controls that are tile bits but not register slots: mask over tile-local bits
-  uint32_t dsel_reg[2]; // DIAG selector j as a bitmap over register amplitude indices (bit i = value)
   uint32_t dsel_loc[2]; // DIAG selector j as a single tile-local bit mask (0 if not thread-level)
   uint64_t ctrl_glob;   // controls outside the tile: mask over physical index bits
   uint64_t dsel_glob[2];// DIAG selector j as a single physical bit mask outside the tile (or 0)
   uint8_t tk[4];     // MATK: tile-local bit of matrix-index bit j (j = 0 is the LSB)
+  uint8_t dsel_slot[2]; // DIAG selector j: register slot index, or 0xff if not a register slot
+  uint8_t pad[2];
   uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
 } b200q_op_t;
 
@@ -68,7 +79,7 @@ typedef struct {
   uint8_t n_ops;
   uint16_t pool_elems;
   uint8_t n_nontile;
-  uint8_t pad;
+  uint8_t layout;     // B200Q_LAYOUT_* (complex64 only)
   uint8_t tile_phys[B200Q_MAX_TILE_BITS];   // physical bit of tile-local bit j (ascending)
   uint8_t nontile_phys[B200Q_MAX_QUBITS];   // physical bits enumerated by the tile (CTA) index
   b200q_round_t rounds[B200Q_MAX_ROUNDS];

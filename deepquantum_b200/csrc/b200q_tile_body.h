@@ -1,9 +1,17 @@
 // Per-thread body of the fused tile kernel, written as __host__ __device__ templates so that the
 // exact index logic that runs on sm_100a can also be stepped thread-by-thread on the CPU by the
-// test-only emulator (tests/native/hostemu.cpp).  No CUDA-only intrinsic appears in this file.
+// test-only emulator (tests/native/hostemu.cpp).
 //
 // Replaces: qmath.evolve_state (qmath.py:485-506) and Gate.op_state_control (operation.py:203-219)
 // for every gate of a fused group, applied in place.
+//
+// Register model.  A thread holds 16 *elements* (one per 16-byte chunk), indexed by 4 chunk-level
+// register slots.  For complex128 an element is one amplitude (re, im doubles).  For complex64 an
+// element is the PAIR of amplitudes (2m, 2m+1) that share a chunk, kept as two packed float2
+// registers re = (re0, re1), im = (im0, im1): every op on a chunk-level slot is then a 2-wide SIMD
+// op issued as Blackwell packed-FP32 instructions (FFMA2 / FMUL2: `__ffma2_rn`), half the
+// instruction count of scalar FFMA.  The extra complex64 slot 0 (index bit 0) lives across the two
+// lanes of the pair ("lane slot").
 #pragma once
 #include "b200q_program.h"
 
@@ -16,113 +24,335 @@
 namespace b200q {
 
 template <typename Real> struct cx { Real x, y; };
-struct alignas(16) chunk_f { float x, y, z, w; };  // two complex64 amplitudes (2m, 2m+1)
-struct alignas(16) chunk_d { double x, y; };        // one complex128 amplitude
+
+// Two float lanes in ONE 64-bit register (an aligned even/odd pair): the operand format of the
+// Blackwell packed-FP32 instructions.  On the device the carrier is a 64-bit integer so that the
+// register allocator keeps the pair together and FFMA2 needs no packing moves.
+#if defined(__CUDA_ARCH__)
+struct alignas(8) pk { unsigned long long u; };
+__device__ __forceinline__ pk pk_make(float x, float y) {
+  pk r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(x), "f"(y)); return r;
+}
+__device__ __forceinline__ float pk_x(pk a) { return __uint_as_float((unsigned)(a.u & 0xffffffffull)); }
+__device__ __forceinline__ float pk_y(pk a) { return __uint_as_float((unsigned)(a.u >> 32)); }
+__device__ __forceinline__ pk vmul(pk a, pk b) {
+  pk r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r;
+}
+__device__ __forceinline__ pk vfma(pk a, pk b, pk c) {
+  pk r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u)); return r;
+}
+__device__ __forceinline__ pk vneg(pk a) { pk r; r.u = a.u ^ 0x8000000080000000ull; return r; }
+#else
+struct alignas(8) pk { float x, y; };
+inline pk pk_make(float x, float y) { pk r; r.x = x; r.y = y; return r; }
+inline float pk_x(pk a) { return a.x; }
+inline float pk_y(pk a) { return a.y; }
+inline pk vmul(pk a, pk b) { return pk_make(a.x * b.x, a.y * b.y); }
+inline pk vfma(pk a, pk b, pk c) { return pk_make(a.x * b.x + c.x, a.y * b.y + c.y); }
+inline pk vneg(pk a) { return pk_make(-a.x, -a.y); }
+#endif
+struct alignas(16) chunk_f { pk lo, hi; };   // two complex64 amplitudes (AoS or SoA, see program.h)
+struct alignas(16) chunk_d { double x, y; };  // one complex128 amplitude
+
+// ---- 2-wide / scalar vector primitives -----------------------------------------------------------
+B200Q_HD pk vset(float a, pk*) { return pk_make(a, a); }
+B200Q_HD double vset(double a, double*) { return a; }
+B200Q_HD double vneg(double a) { return -a; }
+B200Q_HD double vmul(double a, double b) { return a * b; }
+B200Q_HD double vfma(double a, double b, double c) { return a * b + c; }
+// keep lane 0 of `old`, take lane 1 of `nw` (control on index bit 0)
+B200Q_HD pk vblend1(pk old, pk nw) { return pk_make(pk_x(old), pk_y(nw)); }
+B200Q_HD double vblend1(double, double nw) { return nw; }
+B200Q_HD double vhsum(pk a) { return double(pk_x(a)) + double(pk_y(a)); }
+B200Q_HD double vhsum(double a) { return a; }
+B200Q_HD double vlane1(pk a) { return double(pk_y(a)); }
+B200Q_HD double vlane1(double a) { return a; }
+B200Q_HD pk vzero(pk*) { return pk_make(0.f, 0.f); }
+B200Q_HD double vzero(double*) { return 0.0; }
+B200Q_HD pk vmake(float a0, float a1, pk*) { return pk_make(a0, a1); }
+B200Q_HD double vmake(double a0, double, double*) { return a0; }
+B200Q_HD float vget(pk a, int l) { return l ? pk_y(a) : pk_x(a); }
+B200Q_HD double vget(double a, int) { return a; }
 
 template <typename Real> struct Traits;
 template <> struct Traits<float> {
   static constexpr int VS = 1;   // log2(amplitudes per 16-byte chunk)
   static constexpr int RB = 5;   // register slots (amplitude bits held per thread)
-  static constexpr int NA = 32;  // amplitudes per thread
   using chunk = chunk_f;
+  using V = pk;
 };
 template <> struct Traits<double> {
   static constexpr int VS = 0;
   static constexpr int RB = 4;
-  static constexpr int NA = 16;
   using chunk = chunk_d;
+  using V = double;
 };
+constexpr int NE = 16;  // register elements (chunks) per thread
 
 // XOR swizzle of the chunk index inside the shared-memory tile: the low 3 bits (the 8 x 16-byte bank
 // groups of a 128-byte wavefront) are xor-ed with every higher 3-bit group, so a quarter-warp whose
 // lanes differ in ANY three chunk-index bits with distinct positions mod 3 is conflict free.
 B200Q_HD uint32_t swz(uint32_t c) { return c ^ (((c >> 3) ^ (c >> 6) ^ (c >> 9) ^ (c >> 12)) & 7u); }
 
-B200Q_HD void unpack(const chunk_f& v, float* ar, float* ai, int c) {
-  ar[2 * c] = v.x; ai[2 * c] = v.y; ar[2 * c + 1] = v.z; ai[2 * c + 1] = v.w;
+// chunk <-> registers.  `soa` selects the complex64 chunk format; shared memory is always SoA.
+B200Q_HD void unpack(const chunk_f& v, pk& re, pk& im, bool soa) {
+  if (soa) { re = v.lo; im = v.hi; }
+  else { re = pk_make(pk_x(v.lo), pk_x(v.hi)); im = pk_make(pk_y(v.lo), pk_y(v.hi)); }
 }
-B200Q_HD void unpack(const chunk_d& v, double* ar, double* ai, int c) { ar[c] = v.x; ai[c] = v.y; }
-B200Q_HD chunk_f pack(const float* ar, const float* ai, int c, chunk_f*) {
-  chunk_f v; v.x = ar[2 * c]; v.y = ai[2 * c]; v.z = ar[2 * c + 1]; v.w = ai[2 * c + 1]; return v;
+B200Q_HD void unpack(const chunk_d& v, double& re, double& im, bool) { re = v.x; im = v.y; }
+B200Q_HD chunk_f pack(const pk& re, const pk& im, bool soa, chunk_f*) {
+  chunk_f v;
+  if (soa) { v.lo = re; v.hi = im; }
+  else { v.lo = pk_make(pk_x(re), pk_x(im)); v.hi = pk_make(pk_y(re), pk_y(im)); }
+  return v;
 }
-B200Q_HD chunk_d pack(const double* ar, const double* ai, int c, chunk_d*) {
-  chunk_d v; v.x = ar[c]; v.y = ai[c]; return v;
-}
-B200Q_HD chunk_f zero_chunk(chunk_f*) { chunk_f v; v.x = v.y = v.z = v.w = 0.f; return v; }
+B200Q_HD chunk_d pack(const double& re, const double& im, bool, chunk_d*) { chunk_d v; v.x = re; v.y = im; return v; }
+B200Q_HD chunk_f zero_chunk(chunk_f*) { chunk_f v; v.lo = pk_make(0.f, 0.f); v.hi = v.lo; return v; }
 B200Q_HD chunk_d zero_chunk(chunk_d*) { chunk_d v; v.x = v.y = 0.0; return v; }
 
 // ------------------------------------------------------------------------------------------------
-// register ops
+// dense 2x2 on a chunk-level slot
 // ------------------------------------------------------------------------------------------------
-template <typename Real, int NA, int S>
-B200Q_HD void op_mat1(Real* ar, Real* ai, const cx<Real>* m, uint32_t creg) {
-  const Real m00r = m[0].x, m00i = m[0].y, m01r = m[1].x, m01i = m[1].y;
-  const Real m10r = m[2].x, m10i = m[2].y, m11r = m[3].x, m11i = m[3].y;
+enum { VAR_GENERAL = 0, VAR_REAL = 1, VAR_RXLIKE = 2 };
+
+template <typename V> struct Coef {  // broadcast coefficients (and negated imaginary parts)
+  V r00, i00, r01, i01, r10, i10, r11, i11, n00, n01, n10, n11;
+};
+template <typename Real, typename V>
+B200Q_HD Coef<V> make_coef(const cx<Real>* m) {
+  Coef<V> c;
+  c.r00 = vset(m[0].x, (V*)nullptr); c.i00 = vset(m[0].y, (V*)nullptr);
+  c.r01 = vset(m[1].x, (V*)nullptr); c.i01 = vset(m[1].y, (V*)nullptr);
+  c.r10 = vset(m[2].x, (V*)nullptr); c.i10 = vset(m[2].y, (V*)nullptr);
+  c.r11 = vset(m[3].x, (V*)nullptr); c.i11 = vset(m[3].y, (V*)nullptr);
+  c.n00 = vneg(c.i00); c.n01 = vneg(c.i01); c.n10 = vneg(c.i10); c.n11 = vneg(c.i11);
+  return c;
+}
+
+template <typename V, int S, int VAR, bool CTRL>
+B200Q_HD void mat1_chunk(V* re, V* im, const Coef<V>& m, uint32_t cm, bool lane_ctrl) {
 #pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    if (i & (1 << S)) continue;
-    if ((uint32_t(i) & creg) != creg) continue;
-    const int j = i | (1 << S);
-    const Real xr = ar[i], xi = ai[i], yr = ar[j], yi = ai[j];
-    ar[i] = m00r * xr - m00i * xi + m01r * yr - m01i * yi;
-    ai[i] = m00r * xi + m00i * xr + m01r * yi + m01i * yr;
-    ar[j] = m10r * xr - m10i * xi + m11r * yr - m11i * yi;
-    ai[j] = m10r * xi + m10i * xr + m11r * yi + m11i * yr;
+  for (int c = 0; c < NE; ++c) {
+    if (c & (1 << S)) continue;
+    if (CTRL && (uint32_t(c) & cm) != cm) continue;
+    const int d = c | (1 << S);
+    const V ar = re[c], ai = im[c], br = re[d], bi = im[d];
+    V x0, y0, x1, y1;
+    if (VAR == VAR_REAL) {
+      x0 = vfma(m.r01, br, vmul(m.r00, ar));
+      y0 = vfma(m.r01, bi, vmul(m.r00, ai));
+      x1 = vfma(m.r11, br, vmul(m.r10, ar));
+      y1 = vfma(m.r11, bi, vmul(m.r10, ai));
+    } else if (VAR == VAR_RXLIKE) {
+      x0 = vfma(m.n01, bi, vmul(m.r00, ar));
+      y0 = vfma(m.i01, br, vmul(m.r00, ai));
+      x1 = vfma(m.n10, ai, vmul(m.r11, br));
+      y1 = vfma(m.i10, ar, vmul(m.r11, bi));
+    } else {
+      x0 = vfma(m.n01, bi, vfma(m.r01, br, vfma(m.n00, ai, vmul(m.r00, ar))));
+      y0 = vfma(m.i01, br, vfma(m.r01, bi, vfma(m.i00, ar, vmul(m.r00, ai))));
+      x1 = vfma(m.n11, bi, vfma(m.r11, br, vfma(m.n10, ai, vmul(m.r10, ar))));
+      y1 = vfma(m.i11, br, vfma(m.r11, bi, vfma(m.i10, ar, vmul(m.r10, ai))));
+    }
+    if (CTRL && lane_ctrl) {
+      re[c] = vblend1(ar, x0); im[c] = vblend1(ai, y0); re[d] = vblend1(br, x1); im[d] = vblend1(bi, y1);
+    } else {
+      re[c] = x0; im[c] = y0; re[d] = x1; im[d] = y1;
+    }
   }
 }
 
-template <typename Real, int NA, int S>
-B200Q_HD void op_x(Real* ar, Real* ai, uint32_t creg) {
-#pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    if (i & (1 << S)) continue;
-    if ((uint32_t(i) & creg) != creg) continue;
-    const int j = i | (1 << S);
-    const Real tr = ar[i], ti = ai[i];
-    ar[i] = ar[j]; ai[i] = ai[j];
-    ar[j] = tr; ai[j] = ti;
+template <typename V, int VAR, bool CTRL>
+B200Q_HD void mat1_chunk_slot(int s, V* re, V* im, const Coef<V>& m, uint32_t cm, bool lane_ctrl) {
+  switch (s) {
+    case 0: mat1_chunk<V, 0, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
+    case 1: mat1_chunk<V, 1, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
+    case 2: mat1_chunk<V, 2, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
+    default: mat1_chunk<V, 3, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
   }
 }
 
-template <typename Real, int NA>
-B200Q_HD void op_diag(Real* ar, Real* ai, const cx<Real>* d, uint32_t sel_base, uint32_t r0, uint32_t r1,
-                      uint32_t creg) {
-  const cx<Real> d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+// dense 2x2 across the two lanes of every element (complex64 index bit 0)
+template <typename Real>
+B200Q_HD void mat1_lane(pk* re, pk* im, const cx<Real>* m, uint32_t cm) {
+  const float m00r = m[0].x, m00i = m[0].y, m01r = m[1].x, m01i = m[1].y;
+  const float m10r = m[2].x, m10i = m[2].y, m11r = m[3].x, m11i = m[3].y;
 #pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    if ((uint32_t(i) & creg) != creg) continue;
-    const uint32_t idx = sel_base | ((r0 >> i) & 1u) | (((r1 >> i) & 1u) << 1);
-    const cx<Real> lo = (idx & 1u) ? d1 : d0;
-    const cx<Real> hi = (idx & 1u) ? d3 : d2;
-    const cx<Real> p = (idx & 2u) ? hi : lo;
-    const Real xr = ar[i], xi = ai[i];
-    ar[i] = p.x * xr - p.y * xi;
-    ai[i] = p.x * xi + p.y * xr;
+  for (int c = 0; c < NE; ++c) {
+    if ((uint32_t(c) & cm) != cm) continue;
+    const float ar = pk_x(re[c]), ai = pk_x(im[c]), br = pk_y(re[c]), bi = pk_y(im[c]);
+    re[c] = pk_make(m00r * ar - m00i * ai + m01r * br - m01i * bi, m10r * ar - m10i * ai + m11r * br - m11i * bi);
+    im[c] = pk_make(m00r * ai + m00i * ar + m01r * bi + m01i * br, m10r * ai + m10i * ar + m11r * bi + m11i * br);
+  }
+}
+template <typename Real>
+B200Q_HD void mat1_lane(double*, double*, const cx<Real>*, uint32_t) {}
+
+// MAT1 dispatch.  `slot` is the amplitude-level register slot.
+template <typename Real>
+B200Q_HD void apply_mat1(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
+                         const cx<Real>* m) {
+  using V = typename Traits<Real>::V;
+  constexpr int VS = Traits<Real>::VS;
+  const uint32_t cm = op.ctrl_reg >> VS;
+  const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+  if (VS && op.slot == 0) { mat1_lane<Real>(re, im, m, cm); return; }
+  const int s = int(op.slot) - VS;
+  const Coef<V> k = make_coef<Real, V>(m);
+  const bool ctrl = cm != 0 || lane_ctrl;
+  const int var = (op.flags & B200Q_FLAG_REAL) ? VAR_REAL : ((op.flags & B200Q_FLAG_RXLIKE) ? VAR_RXLIKE : VAR_GENERAL);
+  if (!ctrl) {
+    if (var == VAR_REAL) mat1_chunk_slot<V, VAR_REAL, false>(s, re, im, k, 0, false);
+    else if (var == VAR_RXLIKE) mat1_chunk_slot<V, VAR_RXLIKE, false>(s, re, im, k, 0, false);
+    else mat1_chunk_slot<V, VAR_GENERAL, false>(s, re, im, k, 0, false);
+  } else {
+    mat1_chunk_slot<V, VAR_GENERAL, true>(s, re, im, k, cm, lane_ctrl);
   }
 }
 
-template <typename Real, int NA, int RB>
-B200Q_HD void dispatch_mat1(int slot, Real* ar, Real* ai, const cx<Real>* m, uint32_t creg) {
-  switch (slot) {
-    case 0: op_mat1<Real, NA, 0>(ar, ai, m, creg); break;
-    case 1: op_mat1<Real, NA, 1>(ar, ai, m, creg); break;
-    case 2: op_mat1<Real, NA, 2>(ar, ai, m, creg); break;
-    case 3: op_mat1<Real, NA, 3>(ar, ai, m, creg); break;
-    default:
-      if (RB > 4) op_mat1<Real, NA, (RB > 4 ? 4 : 0)>(ar, ai, m, creg);
-      break;
+// ------------------------------------------------------------------------------------------------
+// X (amplitude swap)
+// ------------------------------------------------------------------------------------------------
+template <typename V, int S>
+B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, bool lane_ctrl) {
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    if (c & (1 << S)) continue;
+    if ((uint32_t(c) & cm) != cm) continue;
+    const int d = c | (1 << S);
+    const V ar = re[c], ai = im[c], br = re[d], bi = im[d];
+    if (lane_ctrl) {
+      re[c] = vblend1(ar, br); im[c] = vblend1(ai, bi); re[d] = vblend1(br, ar); im[d] = vblend1(bi, ai);
+    } else {
+      re[c] = br; im[c] = bi; re[d] = ar; im[d] = ai;
+    }
   }
 }
-template <typename Real, int NA, int RB>
-B200Q_HD void dispatch_x(int slot, Real* ar, Real* ai, uint32_t creg) {
-  switch (slot) {
-    case 0: op_x<Real, NA, 0>(ar, ai, creg); break;
-    case 1: op_x<Real, NA, 1>(ar, ai, creg); break;
-    case 2: op_x<Real, NA, 2>(ar, ai, creg); break;
-    case 3: op_x<Real, NA, 3>(ar, ai, creg); break;
-    default:
-      if (RB > 4) op_x<Real, NA, (RB > 4 ? 4 : 0)>(ar, ai, creg);
-      break;
+B200Q_HD void x_lane(pk* re, pk* im, uint32_t cm) {
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    if ((uint32_t(c) & cm) != cm) continue;
+    re[c] = pk_make(pk_y(re[c]), pk_x(re[c]));
+    im[c] = pk_make(pk_y(im[c]), pk_x(im[c]));
+  }
+}
+B200Q_HD void x_lane(double*, double*, uint32_t) {}
+
+template <typename Real>
+B200Q_HD void apply_x(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
+  using V = typename Traits<Real>::V;
+  constexpr int VS = Traits<Real>::VS;
+  const uint32_t cm = op.ctrl_reg >> VS;
+  const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+  if (VS && op.slot == 0) { x_lane(re, im, cm); return; }
+  switch (int(op.slot) - VS) {
+    case 0: x_chunk<V, 0>(re, im, cm, lane_ctrl); break;
+    case 1: x_chunk<V, 1>(re, im, cm, lane_ctrl); break;
+    case 2: x_chunk<V, 2>(re, im, cm, lane_ctrl); break;
+    default: x_chunk<V, 3>(re, im, cm, lane_ctrl); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagonal ops
+// ------------------------------------------------------------------------------------------------
+template <typename V>
+B200Q_HD void cmul_inplace(V& re, V& im, V pr, V pi, V npi) {
+  const V x = vfma(npi, im, vmul(pr, re));
+  const V y = vfma(pi, re, vmul(pr, im));
+  re = x; im = y;
+}
+
+// elements with slot bit 0 are multiplied by p0, with bit 1 by p1 (p == 1 is skipped)
+template <typename Real, typename V, int S>
+B200Q_HD void diag_chunk(V* re, V* im, cx<Real> p0, cx<Real> p1) {
+  const bool do0 = !(p0.x == Real(1) && p0.y == Real(0));
+  const bool do1 = !(p1.x == Real(1) && p1.y == Real(0));
+  const V p0r = vset(p0.x, (V*)nullptr), p0i = vset(p0.y, (V*)nullptr), n0i = vset(-p0.y, (V*)nullptr);
+  const V p1r = vset(p1.x, (V*)nullptr), p1i = vset(p1.y, (V*)nullptr), n1i = vset(-p1.y, (V*)nullptr);
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    if (c & (1 << S)) { if (do1) cmul_inplace(re[c], im[c], p1r, p1i, n1i); }
+    else { if (do0) cmul_inplace(re[c], im[c], p0r, p0i, n0i); }
+  }
+}
+
+// per-lane phase vectors (complex64): lane l of every element is multiplied by q[l]
+B200Q_HD void diag_lanes(pk* re, pk* im, cx<float> q0, cx<float> q1) {
+  const pk pr = pk_make(q0.x, q1.x), pi = pk_make(q0.y, q1.y), npi = pk_make(-q0.y, -q1.y);
+#pragma unroll
+  for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
+}
+B200Q_HD void diag_lanes(double*, double*, cx<double>, cx<double>) {}
+
+// fully general (slow) path: any mix of register / lane selectors and register controls
+template <typename Real>
+B200Q_HD void diag_generic(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
+                           const cx<Real>* d, uint32_t tsel) {
+  using V = typename Traits<Real>::V;
+  constexpr int VS = Traits<Real>::VS;
+  constexpr int NL = 1 << VS;
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    Real lr[2] = {Real(1), Real(1)}, li[2] = {Real(0), Real(0)};
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const uint32_t i = (uint32_t(c) << VS) | uint32_t(l);  // amplitude-level register index
+      if ((i & op.ctrl_reg) != op.ctrl_reg) continue;
+      uint32_t idx = tsel;
+      if (op.dsel_slot[0] != 0xff) idx |= (i >> op.dsel_slot[0]) & 1u;
+      if (op.dsel_slot[1] != 0xff) idx |= ((i >> op.dsel_slot[1]) & 1u) << 1;
+      lr[l] = d[idx].x; li[l] = d[idx].y;
+    }
+    const V pr = vmake(lr[0], lr[1], (V*)nullptr), pi = vmake(li[0], li[1], (V*)nullptr);
+    const V npi = vmake(-li[0], -li[1], (V*)nullptr);
+    cmul_inplace(re[c], im[c], pr, pi, npi);
+  }
+}
+
+// DIAG dispatch.  FOLD: phases that are uniform over the thread's registers are accumulated into the
+// scalar (rho_r, rho_i) and applied once per round.
+template <typename Real, bool FOLD>
+B200Q_HD void apply_diag(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
+                         const cx<Real>* d, uint32_t tsel, Real& rho_r, Real& rho_i, bool& rho_dirty) {
+  using V = typename Traits<Real>::V;
+  constexpr int VS = Traits<Real>::VS;
+  const int s0 = op.dsel_slot[0], s1 = op.dsel_slot[1];
+  const int nreg = (s0 != 0xff) + (s1 != 0xff);
+  const uint32_t cm = op.ctrl_reg >> VS;
+  const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+  if (nreg == 2 || cm != 0) {
+    diag_generic<Real>(op, re, im, d, tsel);
+    return;
+  }
+  if (nreg == 0) {
+    const cx<Real> p = d[tsel];
+    if (lane_ctrl) {  // control on index bit 0: only lane 1 is multiplied
+      cx<Real> one; one.x = Real(1); one.y = Real(0);
+      diag_lanes(re, im, one, p);
+      return;
+    }
+    if (FOLD) {
+      const Real r = rho_r * p.x - rho_i * p.y, i = rho_r * p.y + rho_i * p.x;
+      rho_r = r; rho_i = i; rho_dirty = true;
+    } else {
+      const V pr = vset(p.x, (V*)nullptr), pi = vset(p.y, (V*)nullptr), npi = vset(-p.y, (V*)nullptr);
+#pragma unroll
+      for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
+    }
+    return;
+  }
+  // exactly one register selector
+  const int j = (s0 != 0xff) ? 0 : 1;
+  const int slot = j == 0 ? s0 : s1;
+  const cx<Real> p0 = d[tsel], p1 = d[tsel | (1u << j)];
+  if (VS && slot == 0) { diag_lanes(re, im, p0, p1); return; }
+  if (lane_ctrl) { diag_generic<Real>(op, re, im, d, tsel); return; }
+  switch (slot - VS) {
+    case 0: diag_chunk<Real, V, 0>(re, im, p0, p1); break;
+    case 1: diag_chunk<Real, V, 1>(re, im, p0, p1); break;
+    case 2: diag_chunk<Real, V, 2>(re, im, p0, p1); break;
+    default: diag_chunk<Real, V, 3>(re, im, p0, p1); break;
   }
 }
 
@@ -138,9 +368,11 @@ B200Q_HD uint64_t tile_base(const b200q_pass_t& P, uint64_t tile_id) {
 }
 
 // Stage the pass's gate matrices into the shared-memory pool.  Thread `tid` handles quads
-// tid, tid + nthreads, ...; a quad is 4 consecutive pool elements of one op.
+// tid, tid + nthreads, ...; a quad is 4 consecutive pool elements of one op.  `flip_adjoint` makes
+// the pool hold U^dagger of every op (the reverse sweep).
 template <typename Real>
-B200Q_HD void fill_pool(const b200q_pass_t& P, int tid, int nthreads, cx<Real>* pool, const cx<Real>* mats) {
+B200Q_HD void fill_pool(const b200q_pass_t& P, int tid, int nthreads, cx<Real>* pool, const cx<Real>* mats,
+                        bool flip_adjoint) {
   const int nquads = P.pool_elems >> 2;
   for (int q = tid; q < nquads; q += nthreads) {
     const int e0 = q << 2;
@@ -150,7 +382,7 @@ B200Q_HD void fill_pool(const b200q_pass_t& P, int tid, int nthreads, cx<Real>* 
       if (P.ops[t].pool_n != 0 && e0 >= off && e0 < off + P.ops[t].pool_n) o = t;
     }
     const b200q_op_t& op = P.ops[o];
-    const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+    const bool adj = ((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint;
     const cx<Real>* src = mats + op.mat_src;
     const int dim = 1 << (op.kind == B200Q_OP_MAT1 ? 1 : int(op.k));
 #pragma unroll
@@ -169,6 +401,97 @@ B200Q_HD void fill_pool(const b200q_pass_t& P, int tid, int nthreads, cx<Real>* 
   }
 }
 
+// Addressing of one thread's 16 elements in a round.
+template <typename Real> struct RoundAddr {
+  uint32_t lb;       // tile-local amplitude index of the item (register bits zero)
+  uint64_t gbase;    // chunk index in global memory
+  uint32_t sbase;    // swizzled chunk index in the tile
+  uint64_t gst[4];   // global chunk stride of each chunk-level slot
+  uint32_t sst[4];   // swizzled tile stride of each chunk-level slot
+  bool active;
+};
+
+template <typename Real>
+B200Q_HD RoundAddr<Real> round_addr(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base) {
+  constexpr int VS = Traits<Real>::VS, RB = Traits<Real>::RB;
+  RoundAddr<Real> A;
+  const int item_bits = int(P.tile_bits) - RB;
+  A.active = tid < (1 << item_bits);
+  uint32_t lb = 0;
+  uint64_t pb = cta_base;
+  for (int k = 0; k < item_bits; ++k) {
+    const uint32_t bit = (uint32_t(tid) >> k) & 1u;
+    const int loc = Rd.nonreg_bit[k];
+    lb |= bit << loc;
+    pb |= uint64_t(bit) << P.tile_phys[loc];
+  }
+  A.lb = lb;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int loc = Rd.slot_bit[s + VS];
+    A.gst[s] = 1ull << (int(P.tile_phys[loc]) - VS);
+    A.sst[s] = swz(1u << (loc - VS));
+  }
+  A.gbase = pb >> VS;
+  A.sbase = swz(lb >> VS);
+  return A;
+}
+
+template <typename Real>
+B200Q_HD uint64_t gidx(const RoundAddr<Real>& A, int c) {
+  return A.gbase + ((c & 1) ? A.gst[0] : 0) + ((c & 2) ? A.gst[1] : 0) + ((c & 4) ? A.gst[2] : 0) +
+         ((c & 8) ? A.gst[3] : 0);
+}
+template <typename Real>
+B200Q_HD uint32_t sidx(const RoundAddr<Real>& A, int c) {
+  return A.sbase ^ ((c & 1) ? A.sst[0] : 0) ^ ((c & 2) ? A.sst[1] : 0) ^ ((c & 4) ? A.sst[2] : 0) ^
+         ((c & 8) ? A.sst[3] : 0);
+}
+
+template <typename Real>
+B200Q_HD void gather(const RoundAddr<Real>& A, bool from_global, bool soa_global,
+                     const typename Traits<Real>::chunk* tile, const typename Traits<Real>::chunk* gstate,
+                     uint64_t total_chunks, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
+  using chunk = typename Traits<Real>::chunk;
+  if (from_global) {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) {
+      const uint64_t idx = gidx(A, c);
+      chunk v = zero_chunk((chunk*)nullptr);
+      if (idx < total_chunks) v = gstate[idx];
+      unpack(v, re[c], im[c], soa_global);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) unpack(tile[sidx(A, c)], re[c], im[c], true);
+  }
+}
+
+template <typename Real>
+B200Q_HD void scatter(const RoundAddr<Real>& A, bool to_global, bool soa_global, typename Traits<Real>::chunk* tile,
+                      typename Traits<Real>::chunk* gstate, uint64_t total_chunks,
+                      const typename Traits<Real>::V* re, const typename Traits<Real>::V* im) {
+  using chunk = typename Traits<Real>::chunk;
+  if (to_global) {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) {
+      const uint64_t idx = gidx(A, c);
+      if (idx < total_chunks) gstate[idx] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) tile[sidx(A, c)] = pack(re[c], im[c], true, (chunk*)nullptr);
+  }
+}
+
+// thread-level selector value of a DIAG op
+B200Q_HD uint32_t diag_tsel(const b200q_op_t& op, uint64_t cta_base, uint32_t lb) {
+  uint32_t sel = 0;
+  if ((cta_base & op.dsel_glob[0]) | uint64_t(lb & op.dsel_loc[0])) sel |= 1u;
+  if ((cta_base & op.dsel_glob[1]) | uint64_t(lb & op.dsel_loc[1])) sel |= 2u;
+  return sel;
+}
+
 // ------------------------------------------------------------------------------------------------
 // one register round of one thread
 // ------------------------------------------------------------------------------------------------
@@ -176,95 +499,61 @@ template <typename Real>
 B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base,
                         typename Traits<Real>::chunk* tile, const cx<Real>* pool,
                         typename Traits<Real>::chunk* gstate, uint64_t total_chunks) {
-  using Tr = Traits<Real>;
-  using chunk = typename Tr::chunk;
-  constexpr int VS = Tr::VS, RB = Tr::RB, NA = Tr::NA;
-  const int item_bits = int(P.tile_bits) - RB;
-  if (tid >= (1 << item_bits)) return;
+  using V = typename Traits<Real>::V;
+  const RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  if (!A.active) return;
+  V re[NE], im[NE];
+  gather<Real>(A, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
 
-  uint32_t lb = 0;   // tile-local amplitude index of this thread's item (register bits zero)
-  uint64_t pb = cta_base;  // the same as a physical index
-  for (int k = 0; k < item_bits; ++k) {
-    const uint32_t bit = (uint32_t(tid) >> k) & 1u;
-    const int loc = Rd.nonreg_bit[k];
-    lb |= bit << loc;
-    pb |= uint64_t(bit) << P.tile_phys[loc];
-  }
-
-  Real ar[NA], ai[NA];
-  uint64_t gst[4];   // chunk stride of each chunk-level register slot in global memory
-  uint32_t sst[4];   // swizzled stride of each chunk-level register slot in the tile
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int loc = Rd.slot_bit[s + VS];
-    gst[s] = 1ull << (int(P.tile_phys[loc]) - VS);
-    sst[s] = swz(1u << (loc - VS));
-  }
-  const uint64_t gbase = pb >> VS;
-  const uint32_t sbase = swz(lb >> VS);
-
-  if (Rd.src_global) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint64_t idx = gbase + ((c & 1) ? gst[0] : 0) + ((c & 2) ? gst[1] : 0) + ((c & 4) ? gst[2] : 0) +
-                           ((c & 8) ? gst[3] : 0);
-      chunk v = zero_chunk((chunk*)nullptr);
-      if (idx < total_chunks) v = gstate[idx];
-      unpack(v, ar, ai, c);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint32_t idx = sbase ^ ((c & 1) ? sst[0] : 0) ^ ((c & 2) ? sst[1] : 0) ^ ((c & 4) ? sst[2] : 0) ^
-                           ((c & 8) ? sst[3] : 0);
-      unpack(tile[idx], ar, ai, c);
-    }
-  }
-
+  Real rho_r = Real(1), rho_i = Real(0);
+  bool rho_dirty = false;
   for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
     const b200q_op_t& op = P.ops[o];
     if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
-    if ((lb & op.ctrl_loc) != op.ctrl_loc) continue;
+    if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;
     const cx<Real>* m = pool + op.pool_off;
     switch (op.kind) {
-      case B200Q_OP_MAT1: dispatch_mat1<Real, NA, RB>(op.slot, ar, ai, m, op.ctrl_reg); break;
-      case B200Q_OP_X: dispatch_x<Real, NA, RB>(op.slot, ar, ai, op.ctrl_reg); break;
-      case B200Q_OP_DIAG: {
-        uint32_t sel = 0;
-        if ((cta_base & op.dsel_glob[0]) | uint64_t(lb & op.dsel_loc[0])) sel |= 1u;
-        if ((cta_base & op.dsel_glob[1]) | uint64_t(lb & op.dsel_loc[1])) sel |= 2u;
-        op_diag<Real, NA>(ar, ai, m, sel, op.dsel_reg[0], op.dsel_reg[1], op.ctrl_reg);
+      case B200Q_OP_MAT1: apply_mat1<Real>(op, re, im, m); break;
+      case B200Q_OP_X: apply_x<Real>(op, re, im); break;
+      case B200Q_OP_DIAG:
+        apply_diag<Real, true>(op, re, im, m, diag_tsel(op, cta_base, A.lb), rho_r, rho_i, rho_dirty);
         break;
-      }
       default: break;
     }
   }
-
-  if (Rd.dst_global) {
+  if (rho_dirty) {
+    const V pr = vset(rho_r, (V*)nullptr), pi = vset(rho_i, (V*)nullptr), npi = vset(-rho_i, (V*)nullptr);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint64_t idx = gbase + ((c & 1) ? gst[0] : 0) + ((c & 2) ? gst[1] : 0) + ((c & 4) ? gst[2] : 0) +
-                           ((c & 8) ? gst[3] : 0);
-      if (idx < total_chunks) gstate[idx] = pack(ar, ai, c, (chunk*)nullptr);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint32_t idx = sbase ^ ((c & 1) ? sst[0] : 0) ^ ((c & 2) ? sst[1] : 0) ^ ((c & 4) ? sst[2] : 0) ^
-                           ((c & 8) ? sst[3] : 0);
-      tile[idx] = pack(ar, ai, c, (chunk*)nullptr);
-    }
+    for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
+  scatter<Real>(A, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, re, im);
 }
 
 // ------------------------------------------------------------------------------------------------
 // dense k-target op applied in place in the shared-memory tile (k = 2..4)
 // ------------------------------------------------------------------------------------------------
-template <typename Real>
-B200Q_HD cx<Real>* tile_amp(typename Traits<Real>::chunk* tile, uint32_t loc) {
-  constexpr int VS = Traits<Real>::VS;
-  cx<Real>* base = reinterpret_cast<cx<Real>*>(tile);
-  return base + ((swz(loc >> VS) << VS) | (loc & ((1u << VS) - 1u)));
+// Amplitude `loc` of the (SoA) tile as separate re / im scalars.
+template <typename Real> struct TileAmp { Real* re; Real* im; };
+B200Q_HD TileAmp<float> tile_amp(chunk_f* tile, uint32_t loc) {
+  float* base = reinterpret_cast<float*>(tile + swz(loc >> 1));
+  TileAmp<float> a; a.re = base + (loc & 1u); a.im = base + 2 + (loc & 1u);
+  return a;
+}
+B200Q_HD TileAmp<double> tile_amp(chunk_d* tile, uint32_t loc) {
+  double* base = reinterpret_cast<double*>(tile + swz(loc));
+  TileAmp<double> a; a.re = base; a.im = base + 1;
+  return a;
+}
+
+template <int K>
+B200Q_HD void sort_targets(const b200q_op_t& op, int* srt) {
+#pragma unroll
+  for (int j = 0; j < K; ++j) srt[j] = op.tk[j];
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int b = a + 1; b < K; ++b)
+      if (srt[b] < srt[a]) { const int t = srt[a]; srt[a] = srt[b]; srt[b] = t; }
 }
 
 template <typename Real, int K>
@@ -273,13 +562,7 @@ B200Q_HD void run_matk(const b200q_pass_t& P, const b200q_op_t& op, int tid, int
   constexpr int D = 1 << K;
   if ((cta_base & op.ctrl_glob) != op.ctrl_glob) return;
   int srt[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) srt[j] = op.tk[j];
-#pragma unroll
-  for (int a = 0; a < K; ++a)
-#pragma unroll
-    for (int b = a + 1; b < K; ++b)
-      if (srt[b] < srt[a]) { const int t = srt[a]; srt[a] = srt[b]; srt[b] = t; }
+  sort_targets<K>(op, srt);
   const cx<Real>* m = pool + op.pool_off;
   const int ngroups = 1 << (int(P.tile_bits) - K);
   for (int g = tid; g < ngroups; g += nthreads) {
@@ -287,27 +570,27 @@ B200Q_HD void run_matk(const b200q_pass_t& P, const b200q_op_t& op, int tid, int
 #pragma unroll
     for (int j = 0; j < K; ++j) base = ((base >> srt[j]) << (srt[j] + 1)) | (base & ((1u << srt[j]) - 1u));
     if ((base & op.ctrl_loc) != op.ctrl_loc) continue;
-    cx<Real> x[D];
-    cx<Real>* ptr[D];
+    Real xr[D], xi[D];
+    TileAmp<Real> ptr[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       uint32_t off = base;
 #pragma unroll
       for (int j = 0; j < K; ++j) off |= ((uint32_t(i) >> j) & 1u) << op.tk[j];
-      ptr[i] = tile_amp<Real>(tile, off);
-      x[i] = *ptr[i];
+      ptr[i] = tile_amp(tile, off);
+      xr[i] = *ptr[i].re; xi[i] = *ptr[i].im;
     }
 #pragma unroll
     for (int r = 0; r < D; ++r) {
-      Real yr = Real(0), yi = Real(0);
+      Real yr = m[r * D].x * xr[0] - m[r * D].y * xi[0];
+      Real yi = m[r * D].x * xi[0] + m[r * D].y * xr[0];
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
+      for (int c = 1; c < D; ++c) {
         const cx<Real> w = m[r * D + c];
-        yr += w.x * x[c].x - w.y * x[c].y;
-        yi += w.x * x[c].y + w.y * x[c].x;
+        yr += w.x * xr[c] - w.y * xi[c];
+        yi += w.x * xi[c] + w.y * xr[c];
       }
-      cx<Real> y; y.x = yr; y.y = yi;
-      *ptr[r] = y;
+      *ptr[r].re = yr; *ptr[r].im = yi;
     }
   }
 }
@@ -320,6 +603,297 @@ B200Q_HD void run_direct_op(const b200q_pass_t& P, const b200q_op_t& op, int tid
     case 3: run_matk<Real, 3>(P, op, tid, nthreads, cta_base, tile, pool); break;
     case 4: run_matk<Real, 4>(P, op, tid, nthreads, cta_base, tile, pool); break;
     default: break;
+  }
+}
+
+// ================================================================================================
+// Adjoint (reverse) sweep: psi <- U^dagger psi, G += lambda (x) conj(psi), lambda <- U^dagger lambda
+// for the ops of a pass taken in reverse (reference adjoint.py:47-83, generalised from one scalar
+// parameter to the full cotangent of every gate matrix so that PyTorch autograd chains it to any
+// parametrisation).  PyTorch convention: grad_M[r][c] = sum_rest lambda_out[r,rest] conj(psi_in[c,rest]).
+// ================================================================================================
+#define B200Q_ACC_PER_OP 32 /* doubles of gradient accumulator per op (2x2: 8 used, 4x4: 32 used) */
+
+// acc[2*(2r+c)], acc[2*(2r+c)+1] += Re, Im of sum lambda[r] conj(psi[c]) over the controlled pairs
+template <typename V, int S>
+B200Q_HD void accum_mat1_chunk(const V* pr, const V* pi, const V* lr, const V* li, uint32_t cm, bool lane_ctrl,
+                               double* acc) {
+  V a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = vzero((V*)nullptr);
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    if (c & (1 << S)) continue;
+    if ((uint32_t(c) & cm) != cm) continue;
+    const int d = c | (1 << S);
+    // G[r][q] += l_r * conj(p_q):  re = lr*pr + li*pi ; im = li*pr - lr*pi
+    a[0] = vfma(li[c], pi[c], vfma(lr[c], pr[c], a[0])); a[1] = vfma(vneg(lr[c]), pi[c], vfma(li[c], pr[c], a[1]));
+    a[2] = vfma(li[c], pi[d], vfma(lr[c], pr[d], a[2])); a[3] = vfma(vneg(lr[c]), pi[d], vfma(li[c], pr[d], a[3]));
+    a[4] = vfma(li[d], pi[c], vfma(lr[d], pr[c], a[4])); a[5] = vfma(vneg(lr[d]), pi[c], vfma(li[d], pr[c], a[5]));
+    a[6] = vfma(li[d], pi[d], vfma(lr[d], pr[d], a[6])); a[7] = vfma(vneg(lr[d]), pi[d], vfma(li[d], pr[d], a[7]));
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = lane_ctrl ? vlane1(a[k]) : vhsum(a[k]);
+}
+
+B200Q_HD void accum_mat1_lane(const pk* pr, const pk* pi, const pk* lr, const pk* li, uint32_t cm, double* acc) {
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+    if ((uint32_t(c) & cm) != cm) continue;
+    const float p0r = pk_x(pr[c]), p0i = pk_x(pi[c]), p1r = pk_y(pr[c]), p1i = pk_y(pi[c]);
+    const float l0r = pk_x(lr[c]), l0i = pk_x(li[c]), l1r = pk_y(lr[c]), l1i = pk_y(li[c]);
+    a[0] += l0r * p0r + l0i * p0i; a[1] += l0i * p0r - l0r * p0i;
+    a[2] += l0r * p1r + l0i * p1i; a[3] += l0i * p1r - l0r * p1i;
+    a[4] += l1r * p0r + l1i * p0i; a[5] += l1i * p0r - l1r * p0i;
+    a[6] += l1r * p1r + l1i * p1i; a[7] += l1i * p1r - l1r * p1i;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = double(a[k]);
+}
+B200Q_HD void accum_mat1_lane(const double*, const double*, const double*, const double*, uint32_t, double*) {}
+
+template <typename Real>
+B200Q_HD void accum_mat1(const b200q_op_t& op, const typename Traits<Real>::V* pr, const typename Traits<Real>::V* pi,
+                         const typename Traits<Real>::V* lr, const typename Traits<Real>::V* li, double* acc) {
+  using V = typename Traits<Real>::V;
+  constexpr int VS = Traits<Real>::VS;
+  const uint32_t cm = op.ctrl_reg >> VS;
+  const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+  if (VS && op.slot == 0) { accum_mat1_lane(pr, pi, lr, li, cm, acc); return; }
+  switch (int(op.slot) - VS) {
+    case 0: accum_mat1_chunk<V, 0>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
+    case 1: accum_mat1_chunk<V, 1>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
+    case 2: accum_mat1_chunk<V, 2>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
+    default: accum_mat1_chunk<V, 3>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
+  }
+}
+
+// acc[2*idx], acc[2*idx+1] += Re, Im of sum lambda conj(psi) over the amplitudes whose selector value is idx
+template <typename Real>
+B200Q_HD void accum_diag(const b200q_op_t& op, uint32_t tsel, const typename Traits<Real>::V* pr,
+                         const typename Traits<Real>::V* pi, const typename Traits<Real>::V* lr,
+                         const typename Traits<Real>::V* li, double* acc) {
+  constexpr int VS = Traits<Real>::VS;
+  constexpr int NL = 1 << VS;
+  Real a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < NE; ++c) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const uint32_t i = (uint32_t(c) << VS) | uint32_t(l);
+      if ((i & op.ctrl_reg) != op.ctrl_reg) continue;
+      uint32_t idx = tsel;
+      if (op.dsel_slot[0] != 0xff) idx |= (i >> op.dsel_slot[0]) & 1u;
+      if (op.dsel_slot[1] != 0xff) idx |= ((i >> op.dsel_slot[1]) & 1u) << 1;
+      const Real plr = Real(vget(pr[c], l)), pli = Real(vget(pi[c], l));
+      const Real llr = Real(vget(lr[c], l)), lli = Real(vget(li[c], l));
+      const Real gr = llr * plr + lli * pli;
+      const Real gi = lli * plr - llr * pli;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[2 * k] += idx == uint32_t(k) ? gr : Real(0);
+        a[2 * k + 1] += idx == uint32_t(k) ? gi : Real(0);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = double(a[k]);
+}
+
+// Accumulator hook: on the device the per-thread partials are warp-reduced and added to the CTA's
+// shared accumulator; the host emulator adds directly.
+#if defined(__CUDA_ARCH__)
+template <int NV>
+__device__ __forceinline__ void cta_accumulate(double* cta_acc, const double* v) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(cta_acc + k, s);
+  }
+}
+#else
+template <int NV>
+inline void cta_accumulate(double* cta_acc, const double* v) {
+  for (int k = 0; k < NV; ++k) cta_acc[k] += v[k];
+}
+#endif
+
+// One register round of the reverse sweep.  The roles of src/dst (and of the pass layouts) are
+// swapped with respect to the forward round.  Every thread of the CTA must call this (the gradient
+// reduction inside is warp-collective).
+template <typename Real>
+B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base,
+                                typename Traits<Real>::chunk* tile_psi, typename Traits<Real>::chunk* tile_lam,
+                                const cx<Real>* pool, typename Traits<Real>::chunk* gpsi,
+                                typename Traits<Real>::chunk* glam, uint64_t total_chunks, uint64_t want_mask,
+                                double* cta_acc) {
+  using V = typename Traits<Real>::V;
+  const RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  V pr[NE], pi[NE], lr[NE], li[NE];
+  const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;
+  if (A.active) {
+    gather<Real>(A, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
+    gather<Real>(A, Rd.dst_global, soa_in, tile_lam, glam, total_chunks, lr, li);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) {
+      pr[c] = pi[c] = lr[c] = li[c] = vzero((V*)nullptr);
+    }
+  }
+  Real dummy_r = Real(1), dummy_i = Real(0);
+  bool dummy_d = false;
+  for (int o = int(Rd.op_end) - 1; o >= int(Rd.op_begin); --o) {
+    const b200q_op_t& op = P.ops[o];
+    if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;   // CTA-uniform
+    const bool on = A.active && ((A.lb & op.ctrl_loc) == op.ctrl_loc);
+    const bool want = (want_mask >> o) & 1ull;
+    const cx<Real>* w = pool + op.pool_off;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    switch (op.kind) {
+      case B200Q_OP_MAT1:
+        if (on) {
+          apply_mat1<Real>(op, pr, pi, w);
+          if (want) accum_mat1<Real>(op, pr, pi, lr, li, acc);
+          apply_mat1<Real>(op, lr, li, w);
+        }
+        if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
+        break;
+      case B200Q_OP_X:
+        if (on) { apply_x<Real>(op, pr, pi); apply_x<Real>(op, lr, li); }
+        break;
+      case B200Q_OP_DIAG: {
+        const uint32_t tsel = diag_tsel(op, cta_base, A.lb);
+        if (on) {
+          apply_diag<Real, false>(op, pr, pi, w, tsel, dummy_r, dummy_i, dummy_d);
+          if (want) accum_diag<Real>(op, tsel, pr, pi, lr, li, acc);
+          apply_diag<Real, false>(op, lr, li, w, tsel, dummy_r, dummy_i, dummy_d);
+        }
+        if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
+        break;
+      }
+      default: break;
+    }
+  }
+  if (!A.active) return;
+  scatter<Real>(A, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, pr, pi);
+  scatter<Real>(A, Rd.src_global, soa_out, tile_lam, glam, total_chunks, lr, li);
+}
+
+// Dense k-target op of the reverse sweep, in place in both shared-memory tiles.  Gradient
+// accumulation is provided for k = 2 (the parametric two-qubit gates); k >= 3 gates are applied but
+// must not require a gradient (checked on the host).
+template <typename Real, int K>
+B200Q_HD void run_matk_adjoint(const b200q_pass_t& P, const b200q_op_t& op, int tid, int nthreads, uint64_t cta_base,
+                               typename Traits<Real>::chunk* tile_psi, typename Traits<Real>::chunk* tile_lam,
+                               const cx<Real>* pool, bool want, double* cta_acc_op) {
+  constexpr int D = 1 << K;
+  constexpr int NACC = (K == 2) ? 32 : 1;
+  if ((cta_base & op.ctrl_glob) != op.ctrl_glob) return;
+  int srt[K];
+  sort_targets<K>(op, srt);
+  const cx<Real>* w = pool + op.pool_off;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  const int ngroups = 1 << (int(P.tile_bits) - K);
+  for (int g = tid; g < ngroups; g += nthreads) {
+    uint32_t base = uint32_t(g);
+#pragma unroll
+    for (int j = 0; j < K; ++j) base = ((base >> srt[j]) << (srt[j] + 1)) | (base & ((1u << srt[j]) - 1u));
+    if ((base & op.ctrl_loc) != op.ctrl_loc) continue;
+    Real xr[D], xi[D], lr[D], li[D], yr[D], yi[D];
+    TileAmp<Real> pp[D], lp[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      uint32_t off = base;
+#pragma unroll
+      for (int j = 0; j < K; ++j) off |= ((uint32_t(i) >> j) & 1u) << op.tk[j];
+      pp[i] = tile_amp(tile_psi, off);
+      lp[i] = tile_amp(tile_lam, off);
+      xr[i] = *pp[i].re; xi[i] = *pp[i].im;
+      lr[i] = *lp[i].re; li[i] = *lp[i].im;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      Real sr = Real(0), si = Real(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const cx<Real> m = w[r * D + c];
+        sr += m.x * xr[c] - m.y * xi[c];
+        si += m.x * xi[c] + m.y * xr[c];
+      }
+      yr[r] = sr; yi[r] = si;
+      *pp[r].re = sr; *pp[r].im = si;
+    }
+    if (K == 2 && want) {
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          acc[(2 * (r * D + c)) % NACC] += double(lr[r] * yr[c] + li[r] * yi[c]);
+          acc[(2 * (r * D + c) + 1) % NACC] += double(li[r] * yr[c] - lr[r] * yi[c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      Real sr = Real(0), si = Real(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const cx<Real> m = w[r * D + c];
+        sr += m.x * lr[c] - m.y * li[c];
+        si += m.x * li[c] + m.y * lr[c];
+      }
+      *lp[r].re = sr; *lp[r].im = si;
+    }
+  }
+  if (K == 2 && want) cta_accumulate<NACC>(cta_acc_op, acc);
+}
+
+template <typename Real>
+B200Q_HD void run_direct_op_adjoint(const b200q_pass_t& P, const b200q_op_t& op, int tid, int nthreads,
+                                    uint64_t cta_base, typename Traits<Real>::chunk* tile_psi,
+                                    typename Traits<Real>::chunk* tile_lam, const cx<Real>* pool, bool want,
+                                    double* cta_acc_op) {
+  switch (op.k) {
+    case 2: run_matk_adjoint<Real, 2>(P, op, tid, nthreads, cta_base, tile_psi, tile_lam, pool, want, cta_acc_op); break;
+    case 3: run_matk_adjoint<Real, 3>(P, op, tid, nthreads, cta_base, tile_psi, tile_lam, pool, false, cta_acc_op); break;
+    case 4: run_matk_adjoint<Real, 4>(P, op, tid, nthreads, cta_base, tile_psi, tile_lam, pool, false, cta_acc_op); break;
+    default: break;
+  }
+}
+
+// Flush one CTA's accumulators into the global gradient buffer (complex128, laid out like the
+// matrix buffer).  `add(ptr, v)` is atomicAdd on the device.
+template <typename AddFn>
+B200Q_HD void flush_grad(const b200q_pass_t& P, int tid, int nthreads, uint64_t want_mask, const double* cta_acc,
+                         double* grad, AddFn add) {
+  for (int e = tid; e < int(P.n_ops) * B200Q_ACC_PER_OP; e += nthreads) {
+    const int o = e / B200Q_ACC_PER_OP, q = e % B200Q_ACC_PER_OP;
+    if (!((want_mask >> o) & 1ull)) continue;
+    const b200q_op_t& op = P.ops[o];
+    const int comp = q & 1, ent = q >> 1;
+    const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+    int dst;
+    if (op.kind == B200Q_OP_MAT1) {
+      if (ent >= 4) continue;
+      const int r = ent >> 1, c = ent & 1;
+      dst = adj ? c * 2 + r : r * 2 + c;
+    } else if (op.kind == B200Q_OP_DIAG) {
+      const int dim = 1 << op.k;
+      if (ent >= dim) continue;
+      dst = ent * (dim + 1);
+    } else if (op.kind == B200Q_OP_MATK && op.k == 2) {
+      const int r = ent >> 2, c = ent & 3;
+      dst = adj ? c * 4 + r : r * 4 + c;
+    } else {
+      continue;
+    }
+    double v = cta_acc[e];
+    if (adj && comp == 1) v = -v;   // grad wrt M where U = M^dagger: conjugate (and transpose above)
+    if (v != 0.0) add(grad + 2 * (uint64_t(op.mat_src) + dst) + comp, v);
   }
 }
 

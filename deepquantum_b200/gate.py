@@ -295,6 +295,7 @@ class PauliX(_ConstSingle):
 
 
 class PauliY(_ConstSingle):
+    _hint = L.GATE_RXLIKE
     _default_name = 'PauliY'
     _matrix_entries = [[0, -1j], [1j, 0]]
 
@@ -306,6 +307,7 @@ class PauliZ(_ConstSingle):
 
 
 class Hadamard(_ConstSingle):
+    _hint = L.GATE_REAL
     _default_name = 'Hadamard'
 
     @classmethod
@@ -356,6 +358,8 @@ class TDaggerGate(_ConstSingle):
 class Rx(ParametricSingleGate):
     """exp(-i theta X / 2) (reference gate.py:1389-1480)."""
 
+    _hint = L.GATE_RXLIKE
+
     def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
                  tsr_mode=False, requires_grad=False) -> None:
         super().__init__(name='Rx', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,
@@ -370,6 +374,8 @@ class Rx(ParametricSingleGate):
 
 
 class Ry(ParametricSingleGate):
+    _hint = L.GATE_REAL
+
     def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
                  tsr_mode=False, requires_grad=False) -> None:
         super().__init__(name='Ry', inputs=inputs, nqubit=nqubit, wires=wires, controls=controls,

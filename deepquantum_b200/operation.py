@@ -122,7 +122,8 @@ class Lowering:
         else:
             block, idx = 'dyn', len(self.dynamic)
             self.dynamic.append(src)
-        self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size))
+        hint = getattr(src, '_hint', 0) if (kind == L.GATE_MAT and len(wires) == 1) else 0
+        self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size, hint))
         self.sources.append(src if kind != L.GATE_X else None)
 
     def finalize(self):
@@ -130,7 +131,7 @@ class Lowering:
         sizes = {'const': [0] * len(self.const), 'dyn': [0] * len(self.dynamic)}
         for cls, lst in self.groups.items():
             sizes[cls] = [0] * len(lst)
-        for kind, _t, _c, _a, block, idx, size in self.records:
+        for kind, _t, _c, _a, block, idx, size, _h in self.records:
             if block != 'none':
                 sizes[block][idx] = size
         bases, offs, total = {}, {}, 0
@@ -143,15 +144,15 @@ class Lowering:
             offs[block] = lst
             total += acc
         structs = []
-        for kind, targets, ctrl, adj, block, idx, _size in self.records:
+        for kind, targets, ctrl, adj, block, idx, _size, hint in self.records:
             off = 0 if block == 'none' else bases[block] + offs[block][idx]
-            structs.append(L.make_gate(kind, targets, ctrl, off, adj))
+            structs.append(L.make_gate(kind, targets, ctrl, off, adj, hint))
         self.offsets = [0 if r[4] == 'none' else bases[r[4]] + offs[r[4]][r[5]] for r in self.records]
         self.total = max(total, 1)
         return structs
 
     def structure_key(self):
-        return tuple(r[:4] + (r[6],) for r in self.records)
+        return tuple(r[:4] + (r[6], r[7]) for r in self.records)
 
     def build_matrices(self, cdtype: torch.dtype, device, batch: int | None = None) -> torch.Tensor:
         """Flat device buffer of every matrix ([total] or [batch, total]); differentiable w.r.t. the gate
@@ -197,6 +198,7 @@ class Gate(Operation):
 
     _kind = L.GATE_MAT
     _matrix_source = 'const'
+    _hint = 0   # B200Q_GATE_REAL / B200Q_GATE_RXLIKE structure hint of the class's 2x2 matrix
 
     def __init__(self, name=None, nqubit: int = 1, wires=None, controls=None, condition: bool = False,
                  den_mat: bool = False, tsr_mode: bool = False) -> None:
@@ -257,7 +259,7 @@ class Gate(Operation):
         self._lower(low)
         low.finalize()
         mats = low.build_matrices(flat.dtype, flat.device)
-        for (kind, targets, ctrl, adj, block, _i, size), off in zip(low.records, low.offsets):
+        for (kind, targets, ctrl, adj, block, _i, size, _h), off in zip(low.records, low.offsets):
             m = None if block == 'none' else mats[off:off + size]
             engine.apply_gate_(flat, self.nqubit, m, targets, ctrl, kind, adj, batch)
         return flat

@@ -43,6 +43,10 @@ extern "C" {
 #define B200Q_GATE_X 2    /* Pauli-X on one target (+controls): X, CNOT, Toffoli (gate.py:841,1934)  */
 
 #define B200Q_GATE_ADJOINT 1 /* flags bit 0: apply the conjugate transpose (Gate.inverse, gate.py:417) */
+/* Optional structure hints for 1-target dense gates (by gate CLASS, never by value); the kernel then
+ * skips the multiplications by the structural zeros. */
+#define B200Q_GATE_REAL 2    /* every entry real: Hadamard, Ry (gate.py:1069, 1538)                     */
+#define B200Q_GATE_RXLIKE 4  /* diagonal real, off-diagonal purely imaginary: Rx, Pauli-Y (gate.py:1443) */
 
 #define B200Q_MAX_TARGETS 6
 
@@ -122,10 +126,13 @@ int b200q_apply_z_weights(const void* state, void* lambda_out, int n_qubits, int
 int b200q_init_basis(void* state, int n_qubits, int dtype, int64_t batch, uint64_t basis_index, void* stream);
 
 /* ---- adjoint differentiation (adjoint.py:47-83) ----------------------------------------------
- * For the gates of `plan` taken in REVERSE order: psi <- U_g^dagger psi, then
- *   grad_out[g][r][c] += sum_rest conj(lambda[r,rest]) * psi[c,rest]     (2^k x 2^k per gate)
- * then lambda <- U_g^dagger lambda.  `grad_out` is a device buffer laid out like the matrix buffer
- * (same offsets); gates with need_grad[g] == 0 are skipped in the accumulation. */
+ * Reverse sweep over the gates of `plan`: for g = last .. first
+ *   psi <- U_g^dagger psi                      (psi enters as the final state, leaves as the initial one)
+ *   grad_out[g][r][c] += sum_rest lambda[r,rest] * conj(psi[c,rest])        (PyTorch cotangent of U_g)
+ *   lambda <- U_g^dagger lambda                (lambda enters as dL/d(final state), leaves as dL/d(initial))
+ * `grad_out` is a ZEROED device buffer of complex128 laid out like the matrix buffer (same element
+ * offsets, always double precision).  need_grad_host[g] == 0 skips gate g (NULL: accumulate all gates
+ * the kernel supports: 1-target dense, diagonal, 2-target dense).  batch = 1. */
 int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const void* matrices, void* grad_out,
                       const uint8_t* need_grad_host, void* stream);
 

@@ -23,7 +23,7 @@ def classify(matrix):
     return L.GATE_MAT
 
 
-def lower_ops(ops, nqubit, dtype=np.complex128, split_big_diag=True):
+def lower_ops(ops, nqubit, dtype=np.complex128, hints=True):
     """(matrix, wires, controls) triples -> (GateStruct array, flat matrix buffer)."""
     gates, mats, off = [], [], 0
     for matrix, wires, controls in ops:
@@ -32,7 +32,13 @@ def lower_ops(ops, nqubit, dtype=np.complex128, split_big_diag=True):
         k = len(wires)
         targets = [nqubit - 1 - w for w in reversed(wires)]   # matrix LSB first
         ctr = [nqubit - 1 - c for c in controls]
-        gates.append(L.make_gate(kind, targets, ctr, off))
+        hint = 0
+        if kind == L.GATE_MAT and k == 1 and hints:
+            if np.all(m.imag == 0):
+                hint = L.GATE_REAL
+            elif m[0, 0].imag == 0 and m[1, 1].imag == 0 and m[0, 1].real == 0 and m[1, 0].real == 0:
+                hint = L.GATE_RXLIKE
+        gates.append(L.make_gate(kind, targets, ctr, off, False, hint))
         mats.append(m.reshape(-1))
         off += m.size
     arr = (L.GateStruct * max(1, len(gates)))(*gates)
@@ -96,3 +102,26 @@ def emu_run_program(prog, nqubit, cdtype, state=None, batch=1, **opts):
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return state, {'passes': stats[0], 'rounds': stats[1], 'ops': stats[2], 'direct': stats[3]}
+
+
+def emu_adjoint(ops, nqubit, cdtype, psi_final, lam_final, chunk_bits=0, need=None):
+    """Reverse sweep through the CPU-stepped kernel body.  Returns (psi_initial, lam_initial, grad) with grad a
+    complex128 array laid out like the matrix buffer."""
+    arr, ng, mats = lower_ops(ops, nqubit, cdtype)
+    psi = np.ascontiguousarray(np.asarray(psi_final, dtype=cdtype)).copy()
+    lam = np.ascontiguousarray(np.asarray(lam_final, dtype=cdtype)).copy()
+    grad = np.zeros(mats.size, dtype=np.complex128)
+    lib = hostemu()
+    lib.hostemu_adjoint.restype = C.c_int
+    lib.hostemu_adjoint.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    err = C.create_string_buffer(256)
+    needp = None
+    if need is not None:
+        need = np.ascontiguousarray(np.asarray(need, dtype=np.uint8))
+        needp = need.ctypes.data
+    rc = lib.hostemu_adjoint(nqubit, L.C64 if cdtype == np.complex64 else L.C128, arr, ng, chunk_bits,
+                             psi.ctypes.data, lam.ctypes.data, mats.ctypes.data, grad.ctypes.data, needp, err, 256)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return psi, lam, grad

@@ -2,6 +2,7 @@
 // planner output and the kernel's index logic can be checked against the oracle without a GPU.
 // Never linked into libb200q.so; built by tests/native/build.py into tests/native/_build/.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,7 +31,7 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
       // poison the tile so that a read of an unwritten slot is caught
       std::memset(tile.data(), 0xff, tile.size() * sizeof(chunk));
       if (P.pool_elems)
-        for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m);
+        for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m, false);
       for (int r = 0; r < P.n_rounds; ++r) {
         const b200q_round_t& Rd = P.rounds[r];
         if (Rd.direct) {
@@ -46,6 +47,76 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
   }
 }
 }  // namespace
+
+namespace {
+template <typename Real>
+void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* lam_v, const void* mats_v,
+                      double* grad, const unsigned char* need) {
+  using chunk = typename Traits<Real>::chunk;
+  constexpr int VS = Traits<Real>::VS;
+  const int cb = pl.opt.chunk_bits;
+  const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
+  std::vector<chunk> tp(size_t(1) << cb), tl(size_t(1) << cb);
+  std::vector<cx<Real>> pool(B200Q_POOL_MAX);
+  std::vector<double> acc(size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP);
+  const uint64_t chunks_per_state = (1ull << pl.n_qubits) >> VS;
+  const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
+  uint64_t want = 0;
+  for (int o = 0; o < P.n_ops; ++o) {
+    const b200q_op_t& op = P.ops[o];
+    if (op.kind == B200Q_OP_X) continue;
+    if (need && !need[op.gate_id]) continue;
+    if (op.kind == B200Q_OP_MATK && op.k > 2) continue;
+    want |= 1ull << o;
+  }
+  chunk* gpsi = reinterpret_cast<chunk*>(psi_v);
+  chunk* glam = reinterpret_cast<chunk*>(lam_v);
+  const cx<Real>* m = reinterpret_cast<const cx<Real>*>(mats_v);
+  for (uint64_t t = 0; t < ntiles; ++t) {
+    const uint64_t cta_base = tile_base(P, t);
+    std::memset(tp.data(), 0xff, tp.size() * sizeof(chunk));
+    std::memset(tl.data(), 0xff, tl.size() * sizeof(chunk));
+    std::fill(acc.begin(), acc.end(), 0.0);
+    if (P.pool_elems)
+      for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m, true);
+    for (int r = int(P.n_rounds) - 1; r >= 0; --r) {
+      const b200q_round_t& Rd = P.rounds[r];
+      if (Rd.direct) {
+        for (int o = int(Rd.op_end) - 1; o >= int(Rd.op_begin); --o)
+          for (int tid = 0; tid < nthreads; ++tid)
+            run_direct_op_adjoint<Real>(P, P.ops[o], tid, nthreads, cta_base, tp.data(), tl.data(), pool.data(),
+                                        (want >> o) & 1ull, acc.data() + o * B200Q_ACC_PER_OP);
+      } else {
+        for (int tid = 0; tid < nthreads; ++tid)
+          run_round_adjoint<Real>(P, Rd, tid, cta_base, tp.data(), tl.data(), pool.data(), gpsi, glam,
+                                  chunks_per_state, want, acc.data());
+      }
+    }
+    for (int tid = 0; tid < nthreads; ++tid)
+      flush_grad(P, tid, nthreads, want, acc.data(), grad, [](double* p, double v) { *p += v; });
+  }
+}
+}  // namespace
+
+// psi: final state (in/out), lam: cotangent of the final state (in/out), grad: zeroed complex128 buffer
+extern "C" int hostemu_adjoint(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
+                               void* psi, void* lam, const void* mats, double* grad, const unsigned char* need,
+                               char* err_out, int err_len) {
+  PlanOptions opt;
+  if (chunk_bits) opt.chunk_bits = chunk_bits;
+  std::string err;
+  Plan* pl = make_plan(n_qubits, dtype, gates, n_gates, opt, &err);
+  if (!pl) {
+    if (err_out && err_len > 0) { std::strncpy(err_out, err.c_str(), err_len - 1); err_out[err_len - 1] = 0; }
+    return -1;
+  }
+  for (int i = (int)pl->passes.size() - 1; i >= 0; --i) {
+    if (dtype == B200Q_C64) run_pass_adjoint<float>(*pl, pl->passes[i], psi, lam, mats, grad, need);
+    else run_pass_adjoint<double>(*pl, pl->passes[i], psi, lam, mats, grad, need);
+  }
+  delete pl;
+  return 0;
+}
 
 extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
                            int low_bits, int max_rounds, int fuse, void* state, const void* mats, int64_t batch,

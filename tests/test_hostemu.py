@@ -86,3 +86,63 @@ def test_batched_states():
     ops = gates_np.lower_spec(meta['spec'], meta['n'])
     out, _ = emu_run(ops, meta['n'], np.complex128, state=g['batched_n6/init'], batch=3)
     np.testing.assert_allclose(out, g['batched_n6/c128'], atol=1e-13)
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_adjoint_sweep_matches_torch_autograd(cdtype):
+    """Reverse sweep (un-compute + cotangent of every gate matrix + cotangent of the input state) against
+    PyTorch autograd through the CPU port of the reference's own contraction (oracle/torch_port.py)."""
+    import torch
+
+    import torch_port
+    from helpers import emu_adjoint, lower_ops
+
+    n = 13 if cdtype == np.complex128 else 14      # two tiles at chunk_bits = 11... and multi-pass
+    rng = np.random.default_rng(7)
+    ops = []
+    # exactly unitary H: the un-computation applies U^dagger, which inverts U only if U is unitary
+    # (the reference's float32-rounded constant H is unitary to 6e-8 only)
+    hmat = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2.0)
+    for w in range(n):
+        ops.append((gates_np.u3(*rng.uniform(0, 6, 3)), [w], []))
+        ops.append((gates_np.rx(0.3 + w), [(w + 4) % n], []))
+        ops.append((hmat, [(w + 2) % n], [(w + 5) % n]))
+        ops.append((gates_np.X, [w], [(w + 3) % n]))
+        ops.append((gates_np.rz(0.7 + w), [w], []))
+        ops.append((gates_np.rzz(0.2 + w), [w, (w + 5) % n], []))
+        ops.append((gates_np.p(0.4 + w), [(w + 1) % n], [w]))
+        ops.append((gates_np.ry(0.4 + w), [(w + 2) % n], [w, (w + 6) % n]))
+    ops.append((gates_np.rxx(0.8), [n - 1, 2], []))
+    ops.append((gates_np.rxy(0.5), [0, n - 2], [5]))
+    psi0 = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi0 /= np.linalg.norm(psi0)
+    wvec = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)   # L = Re <w|psi> + <psi|D|psi>
+    diag = rng.normal(size=2**n)
+
+    tm = [torch.tensor(np.asarray(m, dtype=np.complex128), requires_grad=True) for m, _, _ in ops]
+    x0 = torch.tensor(psi0, requires_grad=True)
+    x = x0.reshape([1] + [2] * n)
+    for (m, wires, ctr), t in zip(ops, tm):
+        x = torch_port.evolve_state_controlled(x, t, n, wires, ctr) if ctr else torch_port.evolve_state(x, t, n, wires)
+    psi = x.reshape(-1)
+    loss = (torch.tensor(wvec).conj() * psi).sum().real + (torch.tensor(diag) * (psi.real**2 + psi.imag**2)).sum()
+    loss.backward()
+    lam_final = wvec + 2 * diag * psi.detach().numpy()           # PyTorch cotangent dL/dRe + i dL/dIm
+    tol = 1e-10 if cdtype == np.complex128 else 3e-4
+
+    psi_in, lam_in, grad = emu_adjoint(ops, n, cdtype, psi.detach().numpy(), lam_final, chunk_bits=11)
+    assert np.linalg.norm(psi_in - psi0) < (1e-10 if cdtype == np.complex128 else 1e-4)
+    assert np.linalg.norm(lam_in - x0.grad.numpy()) / np.linalg.norm(x0.grad.numpy()) < tol
+    off = 0
+    for (m, wires, ctr), t in zip(ops, tm):
+        m = np.asarray(m)
+        g = grad[off:off + m.size].reshape(m.shape)
+        ref = t.grad.numpy()
+        if np.array_equal(m, gates_np.X):
+            off += m.size
+            continue
+        if np.count_nonzero(m - np.diag(np.diagonal(m))) == 0:      # diagonal gates: only the diagonal is read
+            g, ref = np.diagonal(g), np.diagonal(ref)
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(g - ref).max() / scale < tol, (wires, ctr, g, ref)
+        off += m.size

@@ -33,7 +33,11 @@ def synthetic(n, tdt, kinds, bits, chunk_bits):
     for i, k in enumerate(kinds):
         b = bits[i % len(bits)]
         if k == 'h':
-            gates.append(L.make_gate(L.GATE_MAT, [b], [], 0))
+            gates.append(L.make_gate(L.GATE_MAT, [b], [], 0, False, L.GATE_REAL))
+        elif k == 'r':
+            gates.append(L.make_gate(L.GATE_MAT, [b], [], 8, False, L.GATE_RXLIKE))
+        elif k == 'u':
+            gates.append(L.make_gate(L.GATE_MAT, [b], [], 12))
         elif k == 'd':
             gates.append(L.make_gate(L.GATE_DIAG, [b], [], 4))
         else:
@@ -49,7 +53,9 @@ def main():
         st[0] = 1
         h = torch.tensor([[1, 1], [1, -1]], dtype=tdt, device=dev) / 2**0.5
         s = torch.tensor([[1, 0], [0, 1j]], dtype=tdt, device=dev)
-        mats = torch.cat([h.reshape(-1), s.reshape(-1)])
+        rx = torch.tensor([[0.8, -0.6j], [-0.6j, 0.8]], dtype=tdt, device=dev)
+        u = torch.tensor([[0.6, 0.8j], [0.8j, 0.6]], dtype=tdt, device=dev) * (0.6 + 0.8j)
+        mats = torch.cat([h.reshape(-1), s.reshape(-1), rx.reshape(-1), u.reshape(-1)])
         bytes_pass = 2 * st.numel() * st.element_size()
         # plain copy for reference
         dst = torch.empty_like(st)
@@ -68,10 +74,11 @@ def main():
         hi = [n - 1, n - 2, n - 3, n - 4]          # high bits: single global->global round
         lo = [1, 2, 3, 4]                          # low bits: needs the shared-memory transpose
         mid = [8, 9, 10, 11]
-        for cb in (11, 12, 13):
-            for label, bits in (('hi', hi), ('lo', lo), ('mid', mid)):
-                for kind in ('h', 'd', 'x'):
-                    for nops in (1, 4, 8, 16, 32):
+        quick = '--quick' in sys.argv
+        for cb in ((12,) if quick else (11, 12, 13)):
+            for label, bits in ((('hi', hi), ('lo', lo)) if quick else (('hi', hi), ('lo', lo), ('mid', mid))):
+                for kind in ('h', 'r', 'u', 'd', 'x'):
+                    for nops in ((1, 8, 32) if quick else (1, 4, 8, 16, 32)):
                         plan = synthetic(n, tdt, [kind] * nops, bits, cb)
                         t = time_plan(plan, st, mats)
                         print(json.dumps({'exp': 'synthetic', 'dtype': str(tdt), 'n': n, 'chunk_bits': cb,
@@ -85,7 +92,7 @@ def main():
     # the C2 circuit end to end for each tile size, fused and unfused
     n, depth = 28, 40
     spec = wl.random_clifford_rx_spec(n, depth)
-    for cb in (11, 12, 13):
+    for cb in ((11, 12) if '--quick' in sys.argv else (11, 12, 13)):
         for fuse in (True, False):
             if not fuse and cb != 12:
                 continue

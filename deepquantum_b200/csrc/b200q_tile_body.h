@@ -118,95 +118,152 @@ enum { VAR_GENERAL = 0, VAR_REAL = 1, VAR_RXLIKE = 2 };
 template <typename V> struct Coef {  // broadcast coefficients (and negated imaginary parts)
   V r00, i00, r01, i01, r10, i10, r11, i11, n00, n01, n10, n11;
 };
+// `flip`: the slot's two register halves hold the logical values 1 and 0 (X relabelling, see run_round):
+// use X M X, i.e. entry (r, c) -> (r^1, c^1).
 template <typename Real, typename V>
-B200Q_HD Coef<V> make_coef(const cx<Real>* m) {
+B200Q_HD Coef<V> make_coef(const cx<Real>* m, uint32_t flip) {
   Coef<V> c;
-  c.r00 = vset(m[0].x, (V*)nullptr); c.i00 = vset(m[0].y, (V*)nullptr);
-  c.r01 = vset(m[1].x, (V*)nullptr); c.i01 = vset(m[1].y, (V*)nullptr);
-  c.r10 = vset(m[2].x, (V*)nullptr); c.i10 = vset(m[2].y, (V*)nullptr);
-  c.r11 = vset(m[3].x, (V*)nullptr); c.i11 = vset(m[3].y, (V*)nullptr);
+  const uint32_t f = flip ? 3u : 0u;
+  c.r00 = vset(m[0 ^ f].x, (V*)nullptr); c.i00 = vset(m[0 ^ f].y, (V*)nullptr);
+  c.r01 = vset(m[1 ^ f].x, (V*)nullptr); c.i01 = vset(m[1 ^ f].y, (V*)nullptr);
+  c.r10 = vset(m[2 ^ f].x, (V*)nullptr); c.i10 = vset(m[2 ^ f].y, (V*)nullptr);
+  c.r11 = vset(m[3 ^ f].x, (V*)nullptr); c.i11 = vset(m[3 ^ f].y, (V*)nullptr);
   c.n00 = vneg(c.i00); c.n01 = vneg(c.i01); c.n10 = vneg(c.i10); c.n11 = vneg(c.i11);
   return c;
 }
 
+// In-place 2x2 butterflies.  Every output is finished by ONE fma whose destination is the register
+// of its own input (x0 = r00*ar + t0 overwrites ar, ...): all partial sums t0..t3 are formed first,
+// so no output ever needs a move to reach its canonical register.  On the device the complex64
+// version is written in PTX on 64-bit operands (fma.rn.f32x2) with tied in/out registers -- with
+// plain C++ the register allocator cannot keep the 16-element arrays in place across the slot
+// `switch` and spends more instructions on MOVs than on arithmetic (measured with ncu).
+template <int VAR, typename V>
+B200Q_HD void bfly(V& ar, V& ai, V& br, V& bi, const Coef<V>& m) {
+  if (VAR == VAR_REAL) {
+    const V t0 = vmul(m.r01, br), t1 = vmul(m.r01, bi), t2 = vmul(m.r10, ar), t3 = vmul(m.r10, ai);
+    ar = vfma(m.r00, ar, t0); ai = vfma(m.r00, ai, t1); br = vfma(m.r11, br, t2); bi = vfma(m.r11, bi, t3);
+  } else if (VAR == VAR_RXLIKE) {
+    const V t0 = vmul(m.n01, bi), t1 = vmul(m.i01, br), t2 = vmul(m.n10, ai), t3 = vmul(m.i10, ar);
+    ar = vfma(m.r00, ar, t0); ai = vfma(m.r00, ai, t1); br = vfma(m.r11, br, t2); bi = vfma(m.r11, bi, t3);
+  } else {
+    const V t0 = vfma(m.n01, bi, vfma(m.r01, br, vmul(m.n00, ai)));
+    const V t1 = vfma(m.i01, br, vfma(m.r01, bi, vmul(m.i00, ar)));
+    const V t2 = vfma(m.n11, bi, vfma(m.n10, ai, vmul(m.r10, ar)));
+    const V t3 = vfma(m.i11, br, vfma(m.i10, ar, vmul(m.r10, ai)));
+    ar = vfma(m.r00, ar, t0); ai = vfma(m.r00, ai, t1); br = vfma(m.r11, br, t2); bi = vfma(m.r11, bi, t3);
+  }
+}
+#if defined(__CUDA_ARCH__)
+template <int VAR>
+__device__ __forceinline__ void bfly_pk(pk& ar, pk& ai, pk& br, pk& bi, const Coef<pk>& m) {
+  if (VAR == VAR_REAL) {
+    asm("{\n .reg .b64 t0, t1, t2, t3;\n"
+        " mul.rn.f32x2 t0, %5, %2;\n mul.rn.f32x2 t1, %5, %3;\n"
+        " mul.rn.f32x2 t2, %6, %0;\n mul.rn.f32x2 t3, %6, %1;\n"
+        " fma.rn.f32x2 %0, %4, %0, t0;\n fma.rn.f32x2 %1, %4, %1, t1;\n"
+        " fma.rn.f32x2 %2, %7, %2, t2;\n fma.rn.f32x2 %3, %7, %3, t3;\n}"
+        : "+l"(ar.u), "+l"(ai.u), "+l"(br.u), "+l"(bi.u)
+        : "l"(m.r00.u), "l"(m.r01.u), "l"(m.r10.u), "l"(m.r11.u));
+  } else if (VAR == VAR_RXLIKE) {
+    asm("{\n .reg .b64 t0, t1, t2, t3;\n"
+        " mul.rn.f32x2 t0, %6, %3;\n mul.rn.f32x2 t1, %5, %2;\n"
+        " mul.rn.f32x2 t2, %8, %1;\n mul.rn.f32x2 t3, %7, %0;\n"
+        " fma.rn.f32x2 %0, %4, %0, t0;\n fma.rn.f32x2 %1, %4, %1, t1;\n"
+        " fma.rn.f32x2 %2, %9, %2, t2;\n fma.rn.f32x2 %3, %9, %3, t3;\n}"
+        : "+l"(ar.u), "+l"(ai.u), "+l"(br.u), "+l"(bi.u)
+        : "l"(m.r00.u), "l"(m.i01.u), "l"(m.n01.u), "l"(m.i10.u), "l"(m.n10.u), "l"(m.r11.u));
+  } else {
+    asm("{\n .reg .b64 t0, t1, t2, t3;\n"
+        " mul.rn.f32x2 t0, %6, %1;\n mul.rn.f32x2 t1, %5, %0;\n"
+        " mul.rn.f32x2 t2, %10, %0;\n mul.rn.f32x2 t3, %10, %1;\n"
+        " fma.rn.f32x2 t0, %7, %2, t0;\n fma.rn.f32x2 t1, %7, %3, t1;\n"
+        " fma.rn.f32x2 t2, %12, %1, t2;\n fma.rn.f32x2 t3, %11, %0, t3;\n"
+        " fma.rn.f32x2 t0, %9, %3, t0;\n fma.rn.f32x2 t1, %8, %2, t1;\n"
+        " fma.rn.f32x2 t2, %15, %3, t2;\n fma.rn.f32x2 t3, %14, %2, t3;\n"
+        " fma.rn.f32x2 %0, %4, %0, t0;\n fma.rn.f32x2 %1, %4, %1, t1;\n"
+        " fma.rn.f32x2 %2, %13, %2, t2;\n fma.rn.f32x2 %3, %13, %3, t3;\n}"
+        : "+l"(ar.u), "+l"(ai.u), "+l"(br.u), "+l"(bi.u)
+        : "l"(m.r00.u), "l"(m.i00.u), "l"(m.n00.u), "l"(m.r01.u), "l"(m.i01.u), "l"(m.n01.u), "l"(m.r10.u),
+          "l"(m.i10.u), "l"(m.n10.u), "l"(m.r11.u), "l"(m.i11.u), "l"(m.n11.u));
+  }
+}
+template <int VAR>
+__device__ __forceinline__ void bfly_dispatch(pk& ar, pk& ai, pk& br, pk& bi, const Coef<pk>& m) {
+  bfly_pk<VAR>(ar, ai, br, bi, m);
+}
+template <int VAR>
+__device__ __forceinline__ void bfly_dispatch(double& ar, double& ai, double& br, double& bi, const Coef<double>& m) {
+  bfly<VAR, double>(ar, ai, br, bi, m);
+}
+#else
+template <int VAR, typename V>
+inline void bfly_dispatch(V& ar, V& ai, V& br, V& bi, const Coef<V>& m) { bfly<VAR, V>(ar, ai, br, bi, m); }
+#endif
+
 template <typename V, int S, int VAR, bool CTRL>
-B200Q_HD void mat1_chunk(V* re, V* im, const Coef<V>& m, uint32_t cm, bool lane_ctrl) {
+B200Q_HD void mat1_chunk(V* re, V* im, const Coef<V>& m, uint32_t cm, uint32_t cv, bool lane_ctrl) {
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
     if (c & (1 << S)) continue;
-    if (CTRL && (uint32_t(c) & cm) != cm) continue;
+    if (CTRL && (uint32_t(c) & cm) != cv) continue;
     const int d = c | (1 << S);
-    const V ar = re[c], ai = im[c], br = re[d], bi = im[d];
-    V x0, y0, x1, y1;
-    if (VAR == VAR_REAL) {
-      x0 = vfma(m.r01, br, vmul(m.r00, ar));
-      y0 = vfma(m.r01, bi, vmul(m.r00, ai));
-      x1 = vfma(m.r11, br, vmul(m.r10, ar));
-      y1 = vfma(m.r11, bi, vmul(m.r10, ai));
-    } else if (VAR == VAR_RXLIKE) {
-      x0 = vfma(m.n01, bi, vmul(m.r00, ar));
-      y0 = vfma(m.i01, br, vmul(m.r00, ai));
-      x1 = vfma(m.n10, ai, vmul(m.r11, br));
-      y1 = vfma(m.i10, ar, vmul(m.r11, bi));
-    } else {
-      x0 = vfma(m.n01, bi, vfma(m.r01, br, vfma(m.n00, ai, vmul(m.r00, ar))));
-      y0 = vfma(m.i01, br, vfma(m.r01, bi, vfma(m.i00, ar, vmul(m.r00, ai))));
-      x1 = vfma(m.n11, bi, vfma(m.r11, br, vfma(m.n10, ai, vmul(m.r10, ar))));
-      y1 = vfma(m.i11, br, vfma(m.r11, bi, vfma(m.i10, ar, vmul(m.r10, ai))));
-    }
     if (CTRL && lane_ctrl) {
-      re[c] = vblend1(ar, x0); im[c] = vblend1(ai, y0); re[d] = vblend1(br, x1); im[d] = vblend1(bi, y1);
+      V ar = re[c], ai = im[c], br = re[d], bi = im[d];
+      bfly_dispatch<VAR>(ar, ai, br, bi, m);
+      re[c] = vblend1(re[c], ar); im[c] = vblend1(im[c], ai); re[d] = vblend1(re[d], br); im[d] = vblend1(im[d], bi);
     } else {
-      re[c] = x0; im[c] = y0; re[d] = x1; im[d] = y1;
+      bfly_dispatch<VAR>(re[c], im[c], re[d], im[d], m);
     }
   }
 }
 
 template <typename V, int VAR, bool CTRL>
-B200Q_HD void mat1_chunk_slot(int s, V* re, V* im, const Coef<V>& m, uint32_t cm, bool lane_ctrl) {
+B200Q_HD void mat1_chunk_slot(int s, V* re, V* im, const Coef<V>& m, uint32_t cm, uint32_t cv, bool lane_ctrl) {
   switch (s) {
-    case 0: mat1_chunk<V, 0, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
-    case 1: mat1_chunk<V, 1, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
-    case 2: mat1_chunk<V, 2, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
-    default: mat1_chunk<V, 3, VAR, CTRL>(re, im, m, cm, lane_ctrl); break;
+    case 0: mat1_chunk<V, 0, VAR, CTRL>(re, im, m, cm, cv, lane_ctrl); break;
+    case 1: mat1_chunk<V, 1, VAR, CTRL>(re, im, m, cm, cv, lane_ctrl); break;
+    case 2: mat1_chunk<V, 2, VAR, CTRL>(re, im, m, cm, cv, lane_ctrl); break;
+    default: mat1_chunk<V, 3, VAR, CTRL>(re, im, m, cm, cv, lane_ctrl); break;
   }
 }
 
 // dense 2x2 across the two lanes of every element (complex64 index bit 0)
 template <typename Real>
-B200Q_HD void mat1_lane(pk* re, pk* im, const cx<Real>* m, uint32_t cm) {
+B200Q_HD void mat1_lane(pk* re, pk* im, const cx<Real>* m, uint32_t cm, uint32_t cv) {
   const float m00r = m[0].x, m00i = m[0].y, m01r = m[1].x, m01i = m[1].y;
   const float m10r = m[2].x, m10i = m[2].y, m11r = m[3].x, m11i = m[3].y;
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
-    if ((uint32_t(c) & cm) != cm) continue;
+    if ((uint32_t(c) & cm) != cv) continue;
     const float ar = pk_x(re[c]), ai = pk_x(im[c]), br = pk_y(re[c]), bi = pk_y(im[c]);
     re[c] = pk_make(m00r * ar - m00i * ai + m01r * br - m01i * bi, m10r * ar - m10i * ai + m11r * br - m11i * bi);
     im[c] = pk_make(m00r * ai + m00i * ar + m01r * bi + m01i * br, m10r * ai + m10i * ar + m11r * bi + m11i * br);
   }
 }
 template <typename Real>
-B200Q_HD void mat1_lane(double*, double*, const cx<Real>*, uint32_t) {}
+B200Q_HD void mat1_lane(double*, double*, const cx<Real>*, uint32_t, uint32_t) {}
 
-// MAT1 dispatch.  `slot` is the amplitude-level register slot.
+// MAT1 dispatch.  `slot` is the amplitude-level register slot; `xm` is the thread's X relabelling mask
+// over the chunk-level slots (register element c holds the logical element c ^ xm).
 template <typename Real>
 B200Q_HD void apply_mat1(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
-                         const cx<Real>* m) {
+                         const cx<Real>* m, uint32_t xm) {
   using V = typename Traits<Real>::V;
   constexpr int VS = Traits<Real>::VS;
-  const uint32_t cm = op.ctrl_reg >> VS;
+  const uint32_t cm = op.ctrl_reg >> VS, cv = cm & ~xm;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
-  if (VS && op.slot == 0) { mat1_lane<Real>(re, im, m, cm); return; }
+  if (VS && op.slot == 0) { mat1_lane<Real>(re, im, m, cm, cv); return; }
   const int s = int(op.slot) - VS;
-  const Coef<V> k = make_coef<Real, V>(m);
+  const Coef<V> k = make_coef<Real, V>(m, (xm >> s) & 1u);
   const bool ctrl = cm != 0 || lane_ctrl;
   const int var = (op.flags & B200Q_FLAG_REAL) ? VAR_REAL : ((op.flags & B200Q_FLAG_RXLIKE) ? VAR_RXLIKE : VAR_GENERAL);
   if (!ctrl) {
-    if (var == VAR_REAL) mat1_chunk_slot<V, VAR_REAL, false>(s, re, im, k, 0, false);
-    else if (var == VAR_RXLIKE) mat1_chunk_slot<V, VAR_RXLIKE, false>(s, re, im, k, 0, false);
-    else mat1_chunk_slot<V, VAR_GENERAL, false>(s, re, im, k, 0, false);
+    if (var == VAR_REAL) mat1_chunk_slot<V, VAR_REAL, false>(s, re, im, k, 0, 0, false);
+    else if (var == VAR_RXLIKE) mat1_chunk_slot<V, VAR_RXLIKE, false>(s, re, im, k, 0, 0, false);
+    else mat1_chunk_slot<V, VAR_GENERAL, false>(s, re, im, k, 0, 0, false);
   } else {
-    mat1_chunk_slot<V, VAR_GENERAL, true>(s, re, im, k, cm, lane_ctrl);
+    mat1_chunk_slot<V, VAR_GENERAL, true>(s, re, im, k, cm, cv, lane_ctrl);
   }
 }
 
@@ -214,11 +271,11 @@ B200Q_HD void apply_mat1(const b200q_op_t& op, typename Traits<Real>::V* re, typ
 // X (amplitude swap)
 // ------------------------------------------------------------------------------------------------
 template <typename V, int S>
-B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, bool lane_ctrl) {
+B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, uint32_t cv, bool lane_ctrl) {
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
     if (c & (1 << S)) continue;
-    if ((uint32_t(c) & cm) != cm) continue;
+    if ((uint32_t(c) & cm) != cv) continue;
     const int d = c | (1 << S);
     const V ar = re[c], ai = im[c], br = re[d], bi = im[d];
     if (lane_ctrl) {
@@ -228,39 +285,54 @@ B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, bool lane_ctrl) {
     }
   }
 }
-B200Q_HD void x_lane(pk* re, pk* im, uint32_t cm) {
+B200Q_HD void x_lane(pk* re, pk* im, uint32_t cm, uint32_t cv) {
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
-    if ((uint32_t(c) & cm) != cm) continue;
+    if ((uint32_t(c) & cm) != cv) continue;
     re[c] = pk_make(pk_y(re[c]), pk_x(re[c]));
     im[c] = pk_make(pk_y(im[c]), pk_x(im[c]));
   }
 }
-B200Q_HD void x_lane(double*, double*, uint32_t) {}
+B200Q_HD void x_lane(double*, double*, uint32_t, uint32_t) {}
 
+// X on a chunk-level slot whose controls are not register slots is a pure relabelling: it only toggles the
+// thread's mask `xm` (register element c then holds logical element c ^ xm) -- no data moves at all; the
+// mask is folded into the scatter address at the end of the round.
 template <typename Real>
-B200Q_HD void apply_x(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
+B200Q_HD void apply_x(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im, uint32_t& xm) {
   using V = typename Traits<Real>::V;
   constexpr int VS = Traits<Real>::VS;
-  const uint32_t cm = op.ctrl_reg >> VS;
+  const uint32_t cm = op.ctrl_reg >> VS, cv = cm & ~xm;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
-  if (VS && op.slot == 0) { x_lane(re, im, cm); return; }
-  switch (int(op.slot) - VS) {
-    case 0: x_chunk<V, 0>(re, im, cm, lane_ctrl); break;
-    case 1: x_chunk<V, 1>(re, im, cm, lane_ctrl); break;
-    case 2: x_chunk<V, 2>(re, im, cm, lane_ctrl); break;
-    default: x_chunk<V, 3>(re, im, cm, lane_ctrl); break;
+  if (VS && op.slot == 0) { x_lane(re, im, cm, cv); return; }
+  const int s = int(op.slot) - VS;
+  if (op.ctrl_reg == 0) { xm ^= 1u << s; return; }
+  switch (s) {
+    case 0: x_chunk<V, 0>(re, im, cm, cv, lane_ctrl); break;
+    case 1: x_chunk<V, 1>(re, im, cm, cv, lane_ctrl); break;
+    case 2: x_chunk<V, 2>(re, im, cm, cv, lane_ctrl); break;
+    default: x_chunk<V, 3>(re, im, cm, cv, lane_ctrl); break;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // diagonal ops
 // ------------------------------------------------------------------------------------------------
-template <typename V>
-B200Q_HD void cmul_inplace(V& re, V& im, V pr, V pi, V npi) {
-  const V x = vfma(npi, im, vmul(pr, re));
-  const V y = vfma(pi, re, vmul(pr, im));
-  re = x; im = y;
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void cmul_inplace(pk& re, pk& im, pk pr, pk pi, pk npi) {
+  asm("{\n .reg .b64 t0, t1;\n mul.rn.f32x2 t0, %4, %1;\n mul.rn.f32x2 t1, %3, %0;\n"
+      " fma.rn.f32x2 %0, %2, %0, t0;\n fma.rn.f32x2 %1, %2, %1, t1;\n}"
+      : "+l"(re.u), "+l"(im.u) : "l"(pr.u), "l"(pi.u), "l"(npi.u));
+}
+#else
+inline void cmul_inplace(pk& re, pk& im, pk pr, pk pi, pk npi) {
+  const pk t0 = vmul(npi, im), t1 = vmul(pi, re);
+  re = vfma(pr, re, t0); im = vfma(pr, im, t1);
+}
+#endif
+B200Q_HD void cmul_inplace(double& re, double& im, double pr, double pi, double npi) {
+  const double t0 = npi * im, t1 = pi * re;
+  re = pr * re + t0; im = pr * im + t1;
 }
 
 // elements with slot bit 0 are multiplied by p0, with bit 1 by p1 (p == 1 is skipped)
@@ -288,7 +360,7 @@ B200Q_HD void diag_lanes(double*, double*, cx<double>, cx<double>) {}
 // fully general (slow) path: any mix of register / lane selectors and register controls
 template <typename Real>
 B200Q_HD void diag_generic(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
-                           const cx<Real>* d, uint32_t tsel) {
+                           const cx<Real>* d, uint32_t tsel, uint32_t xm) {
   using V = typename Traits<Real>::V;
   constexpr int VS = Traits<Real>::VS;
   constexpr int NL = 1 << VS;
@@ -297,7 +369,7 @@ B200Q_HD void diag_generic(const b200q_op_t& op, typename Traits<Real>::V* re, t
     Real lr[2] = {Real(1), Real(1)}, li[2] = {Real(0), Real(0)};
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const uint32_t i = (uint32_t(c) << VS) | uint32_t(l);  // amplitude-level register index
+      const uint32_t i = ((uint32_t(c) ^ xm) << VS) | uint32_t(l);  // LOGICAL amplitude-level register index
       if ((i & op.ctrl_reg) != op.ctrl_reg) continue;
       uint32_t idx = tsel;
       if (op.dsel_slot[0] != 0xff) idx |= (i >> op.dsel_slot[0]) & 1u;
@@ -314,7 +386,7 @@ B200Q_HD void diag_generic(const b200q_op_t& op, typename Traits<Real>::V* re, t
 // scalar (rho_r, rho_i) and applied once per round.
 template <typename Real, bool FOLD>
 B200Q_HD void apply_diag(const b200q_op_t& op, typename Traits<Real>::V* re, typename Traits<Real>::V* im,
-                         const cx<Real>* d, uint32_t tsel, Real& rho_r, Real& rho_i, bool& rho_dirty) {
+                         const cx<Real>* d, uint32_t tsel, uint32_t xm, Real& rho_r, Real& rho_i, bool& rho_dirty) {
   using V = typename Traits<Real>::V;
   constexpr int VS = Traits<Real>::VS;
   const int s0 = op.dsel_slot[0], s1 = op.dsel_slot[1];
@@ -322,7 +394,7 @@ B200Q_HD void apply_diag(const b200q_op_t& op, typename Traits<Real>::V* re, typ
   const uint32_t cm = op.ctrl_reg >> VS;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
   if (nreg == 2 || cm != 0) {
-    diag_generic<Real>(op, re, im, d, tsel);
+    diag_generic<Real>(op, re, im, d, tsel, xm);
     return;
   }
   if (nreg == 0) {
@@ -345,9 +417,10 @@ B200Q_HD void apply_diag(const b200q_op_t& op, typename Traits<Real>::V* re, typ
   // exactly one register selector
   const int j = (s0 != 0xff) ? 0 : 1;
   const int slot = j == 0 ? s0 : s1;
-  const cx<Real> p0 = d[tsel], p1 = d[tsel | (1u << j)];
-  if (VS && slot == 0) { diag_lanes(re, im, p0, p1); return; }
-  if (lane_ctrl) { diag_generic<Real>(op, re, im, d, tsel); return; }
+  if (VS && slot == 0) { diag_lanes(re, im, d[tsel], d[tsel | (1u << j)]); return; }
+  if (lane_ctrl) { diag_generic<Real>(op, re, im, d, tsel, xm); return; }
+  const uint32_t fl = (xm >> (slot - VS)) & 1u;   // X relabelling: the register halves hold logical 1 / 0
+  const cx<Real> p0 = d[fl ? (tsel | (1u << j)) : tsel], p1 = d[fl ? tsel : (tsel | (1u << j))];
   switch (slot - VS) {
     case 0: diag_chunk<Real, V, 0>(re, im, p0, p1); break;
     case 1: diag_chunk<Real, V, 1>(re, im, p0, p1); break;
@@ -439,13 +512,21 @@ B200Q_HD RoundAddr<Real> round_addr(const b200q_pass_t& P, const b200q_round_t& 
 
 template <typename Real>
 B200Q_HD uint64_t gidx(const RoundAddr<Real>& A, int c) {
-  return A.gbase + ((c & 1) ? A.gst[0] : 0) + ((c & 2) ? A.gst[1] : 0) + ((c & 4) ? A.gst[2] : 0) +
+  return A.gbase ^ ((c & 1) ? A.gst[0] : 0) ^ ((c & 2) ? A.gst[1] : 0) ^ ((c & 4) ? A.gst[2] : 0) ^
          ((c & 8) ? A.gst[3] : 0);
 }
 template <typename Real>
 B200Q_HD uint32_t sidx(const RoundAddr<Real>& A, int c) {
   return A.sbase ^ ((c & 1) ? A.sst[0] : 0) ^ ((c & 2) ? A.sst[1] : 0) ^ ((c & 4) ? A.sst[2] : 0) ^
          ((c & 8) ? A.sst[3] : 0);
+}
+
+// Fold the X relabelling mask into the base addresses: register element c is written to logical c ^ xm.
+template <typename Real>
+B200Q_HD void relabel(RoundAddr<Real>& A, uint32_t xm) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+    if ((xm >> s) & 1u) { A.gbase ^= A.gst[s]; A.sbase ^= A.sst[s]; }
 }
 
 template <typename Real>
@@ -500,23 +581,24 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid,
                         typename Traits<Real>::chunk* tile, const cx<Real>* pool,
                         typename Traits<Real>::chunk* gstate, uint64_t total_chunks) {
   using V = typename Traits<Real>::V;
-  const RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
   if (!A.active) return;
   V re[NE], im[NE];
   gather<Real>(A, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
 
   Real rho_r = Real(1), rho_i = Real(0);
   bool rho_dirty = false;
+  uint32_t xm = 0;   // X relabelling mask over the chunk-level register slots
   for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
     const b200q_op_t& op = P.ops[o];
     if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
     if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;
     const cx<Real>* m = pool + op.pool_off;
     switch (op.kind) {
-      case B200Q_OP_MAT1: apply_mat1<Real>(op, re, im, m); break;
-      case B200Q_OP_X: apply_x<Real>(op, re, im); break;
+      case B200Q_OP_MAT1: apply_mat1<Real>(op, re, im, m, xm); break;
+      case B200Q_OP_X: apply_x<Real>(op, re, im, xm); break;
       case B200Q_OP_DIAG:
-        apply_diag<Real, true>(op, re, im, m, diag_tsel(op, cta_base, A.lb), rho_r, rho_i, rho_dirty);
+        apply_diag<Real, true>(op, re, im, m, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i, rho_dirty);
         break;
       default: break;
     }
@@ -526,6 +608,7 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid,
 #pragma unroll
     for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
+  relabel<Real>(A, xm);
   scatter<Real>(A, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, re, im);
 }
 
@@ -616,15 +699,15 @@ B200Q_HD void run_direct_op(const b200q_pass_t& P, const b200q_op_t& op, int tid
 
 // acc[2*(2r+c)], acc[2*(2r+c)+1] += Re, Im of sum lambda[r] conj(psi[c]) over the controlled pairs
 template <typename V, int S>
-B200Q_HD void accum_mat1_chunk(const V* pr, const V* pi, const V* lr, const V* li, uint32_t cm, bool lane_ctrl,
-                               double* acc) {
+B200Q_HD void accum_mat1_chunk(const V* pr, const V* pi, const V* lr, const V* li, uint32_t cm, uint32_t cv,
+                               bool lane_ctrl, double* acc) {
   V a[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = vzero((V*)nullptr);
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
     if (c & (1 << S)) continue;
-    if ((uint32_t(c) & cm) != cm) continue;
+    if ((uint32_t(c) & cm) != cv) continue;
     const int d = c | (1 << S);
     // G[r][q] += l_r * conj(p_q):  re = lr*pr + li*pi ; im = li*pr - lr*pi
     a[0] = vfma(li[c], pi[c], vfma(lr[c], pr[c], a[0])); a[1] = vfma(vneg(lr[c]), pi[c], vfma(li[c], pr[c], a[1]));
@@ -636,11 +719,12 @@ B200Q_HD void accum_mat1_chunk(const V* pr, const V* pi, const V* lr, const V* l
   for (int k = 0; k < 8; ++k) acc[k] = lane_ctrl ? vlane1(a[k]) : vhsum(a[k]);
 }
 
-B200Q_HD void accum_mat1_lane(const pk* pr, const pk* pi, const pk* lr, const pk* li, uint32_t cm, double* acc) {
+B200Q_HD void accum_mat1_lane(const pk* pr, const pk* pi, const pk* lr, const pk* li, uint32_t cm, uint32_t cv,
+                              double* acc) {
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
-    if ((uint32_t(c) & cm) != cm) continue;
+    if ((uint32_t(c) & cm) != cv) continue;
     const float p0r = pk_x(pr[c]), p0i = pk_x(pi[c]), p1r = pk_y(pr[c]), p1i = pk_y(pi[c]);
     const float l0r = pk_x(lr[c]), l0i = pk_x(li[c]), l1r = pk_y(lr[c]), l1i = pk_y(li[c]);
     a[0] += l0r * p0r + l0i * p0i; a[1] += l0i * p0r - l0r * p0i;
@@ -651,27 +735,37 @@ B200Q_HD void accum_mat1_lane(const pk* pr, const pk* pi, const pk* lr, const pk
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = double(a[k]);
 }
-B200Q_HD void accum_mat1_lane(const double*, const double*, const double*, const double*, uint32_t, double*) {}
+B200Q_HD void accum_mat1_lane(const double*, const double*, const double*, const double*, uint32_t, uint32_t,
+                              double*) {}
 
 template <typename Real>
-B200Q_HD void accum_mat1(const b200q_op_t& op, const typename Traits<Real>::V* pr, const typename Traits<Real>::V* pi,
-                         const typename Traits<Real>::V* lr, const typename Traits<Real>::V* li, double* acc) {
+B200Q_HD void accum_mat1(const b200q_op_t& op, uint32_t xm, const typename Traits<Real>::V* pr,
+                         const typename Traits<Real>::V* pi, const typename Traits<Real>::V* lr,
+                         const typename Traits<Real>::V* li, double* acc) {
   using V = typename Traits<Real>::V;
   constexpr int VS = Traits<Real>::VS;
-  const uint32_t cm = op.ctrl_reg >> VS;
+  const uint32_t cm = op.ctrl_reg >> VS, cv = cm & ~xm;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
-  if (VS && op.slot == 0) { accum_mat1_lane(pr, pi, lr, li, cm, acc); return; }
-  switch (int(op.slot) - VS) {
-    case 0: accum_mat1_chunk<V, 0>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
-    case 1: accum_mat1_chunk<V, 1>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
-    case 2: accum_mat1_chunk<V, 2>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
-    default: accum_mat1_chunk<V, 3>(pr, pi, lr, li, cm, lane_ctrl, acc); break;
+  if (VS && op.slot == 0) { accum_mat1_lane(pr, pi, lr, li, cm, cv, acc); return; }
+  const int s = int(op.slot) - VS;
+  switch (s) {
+    case 0: accum_mat1_chunk<V, 0>(pr, pi, lr, li, cm, cv, lane_ctrl, acc); break;
+    case 1: accum_mat1_chunk<V, 1>(pr, pi, lr, li, cm, cv, lane_ctrl, acc); break;
+    case 2: accum_mat1_chunk<V, 2>(pr, pi, lr, li, cm, cv, lane_ctrl, acc); break;
+    default: accum_mat1_chunk<V, 3>(pr, pi, lr, li, cm, cv, lane_ctrl, acc); break;
+  }
+  if ((xm >> s) & 1u) {   // the register halves hold logical 1 / 0: entry (r, c) <-> (r^1, c^1)
+    double t;
+    t = acc[0]; acc[0] = acc[6]; acc[6] = t;
+    t = acc[1]; acc[1] = acc[7]; acc[7] = t;
+    t = acc[2]; acc[2] = acc[4]; acc[4] = t;
+    t = acc[3]; acc[3] = acc[5]; acc[5] = t;
   }
 }
 
 // acc[2*idx], acc[2*idx+1] += Re, Im of sum lambda conj(psi) over the amplitudes whose selector value is idx
 template <typename Real>
-B200Q_HD void accum_diag(const b200q_op_t& op, uint32_t tsel, const typename Traits<Real>::V* pr,
+B200Q_HD void accum_diag(const b200q_op_t& op, uint32_t tsel, uint32_t xm, const typename Traits<Real>::V* pr,
                          const typename Traits<Real>::V* pi, const typename Traits<Real>::V* lr,
                          const typename Traits<Real>::V* li, double* acc) {
   constexpr int VS = Traits<Real>::VS;
@@ -681,7 +775,7 @@ B200Q_HD void accum_diag(const b200q_op_t& op, uint32_t tsel, const typename Tra
   for (int c = 0; c < NE; ++c) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const uint32_t i = (uint32_t(c) << VS) | uint32_t(l);
+      const uint32_t i = ((uint32_t(c) ^ xm) << VS) | uint32_t(l);   // logical register index
       if ((i & op.ctrl_reg) != op.ctrl_reg) continue;
       uint32_t idx = tsel;
       if (op.dsel_slot[0] != 0xff) idx |= (i >> op.dsel_slot[0]) & 1u;
@@ -731,8 +825,9 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
                                 typename Traits<Real>::chunk* glam, uint64_t total_chunks, uint64_t want_mask,
                                 double* cta_acc) {
   using V = typename Traits<Real>::V;
-  const RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
   V pr[NE], pi[NE], lr[NE], li[NE];
+  uint32_t xm = 0;
   const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;
   if (A.active) {
     gather<Real>(A, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
@@ -755,21 +850,21 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
     switch (op.kind) {
       case B200Q_OP_MAT1:
         if (on) {
-          apply_mat1<Real>(op, pr, pi, w);
-          if (want) accum_mat1<Real>(op, pr, pi, lr, li, acc);
-          apply_mat1<Real>(op, lr, li, w);
+          apply_mat1<Real>(op, pr, pi, w, xm);
+          if (want) accum_mat1<Real>(op, xm, pr, pi, lr, li, acc);
+          apply_mat1<Real>(op, lr, li, w, xm);
         }
         if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
         break;
       case B200Q_OP_X:
-        if (on) { apply_x<Real>(op, pr, pi); apply_x<Real>(op, lr, li); }
+        if (on) { uint32_t xm2 = xm; apply_x<Real>(op, pr, pi, xm); apply_x<Real>(op, lr, li, xm2); }
         break;
       case B200Q_OP_DIAG: {
         const uint32_t tsel = diag_tsel(op, cta_base, A.lb);
         if (on) {
-          apply_diag<Real, false>(op, pr, pi, w, tsel, dummy_r, dummy_i, dummy_d);
-          if (want) accum_diag<Real>(op, tsel, pr, pi, lr, li, acc);
-          apply_diag<Real, false>(op, lr, li, w, tsel, dummy_r, dummy_i, dummy_d);
+          apply_diag<Real, false>(op, pr, pi, w, tsel, xm, dummy_r, dummy_i, dummy_d);
+          if (want) accum_diag<Real>(op, tsel, xm, pr, pi, lr, li, acc);
+          apply_diag<Real, false>(op, lr, li, w, tsel, xm, dummy_r, dummy_i, dummy_d);
         }
         if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
         break;
@@ -778,6 +873,7 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
     }
   }
   if (!A.active) return;
+  relabel<Real>(A, xm);
   scatter<Real>(A, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, pr, pi);
   scatter<Real>(A, Rd.src_global, soa_out, tile_lam, glam, total_chunks, lr, li);
 }

@@ -94,6 +94,42 @@ constexpr int NE = 16;  // register elements (chunks) per thread
 // lanes differ in ANY three chunk-index bits with distinct positions mod 3 is conflict free.
 B200Q_HD uint32_t swz(uint32_t c) { return c ^ (((c >> 3) ^ (c >> 6) ^ (c >> 9) ^ (c >> 12)) & 7u); }
 
+// Opaque re-definition of a register value: keeps the register allocator from splitting the live ranges
+// of the 16-element arrays across the op loop's back edge (it otherwise rotates them through a second
+// set of registers with ~60 MOVs per op, measured in SASS).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void vpin(pk& a) { asm volatile("" : "+l"(a.u)); }
+__device__ __forceinline__ void vpin(double& a) { asm volatile("" : "+d"(a)); }
+#else
+inline void vpin(pk&) {}
+inline void vpin(double&) {}
+#endif
+
+// In-place swaps with tied operands: written in PTX so that the compiler sees two values updated in
+// place instead of two values crossing over (the latter makes it rotate the whole register arrays
+// through copies at the head of the op loop -- ~46 MOVs per op, measured in SASS).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void vswap(pk& a, pk& b) {
+  asm("{\n .reg .b64 t;\n mov.b64 t, %0;\n mov.b64 %0, %1;\n mov.b64 %1, t;\n}" : "+l"(a.u), "+l"(b.u));
+}
+__device__ __forceinline__ void vswap_lane1(pk& a, pk& b) {   // swap the high lanes only
+  asm("{\n .reg .b32 al, ah, bl, bh;\n mov.b64 {al, ah}, %0;\n mov.b64 {bl, bh}, %1;\n"
+      " mov.b64 %0, {al, bh};\n mov.b64 %1, {bl, ah};\n}" : "+l"(a.u), "+l"(b.u));
+}
+__device__ __forceinline__ void vswap_lanes(pk& a) {           // swap the two lanes of one register pair
+  asm("{\n .reg .b32 al, ah;\n mov.b64 {al, ah}, %0;\n mov.b64 %0, {ah, al};\n}" : "+l"(a.u));
+}
+__device__ __forceinline__ void vswap(double& a, double& b) {
+  asm("{\n .reg .f64 t;\n mov.f64 t, %0;\n mov.f64 %0, %1;\n mov.f64 %1, t;\n}" : "+d"(a), "+d"(b));
+}
+#else
+inline void vswap(pk& a, pk& b) { const pk t = a; a = b; b = t; }
+inline void vswap_lane1(pk& a, pk& b) { const float t = a.y; a.y = b.y; b.y = t; }
+inline void vswap_lanes(pk& a) { const float t = a.x; a.x = a.y; a.y = t; }
+inline void vswap(double& a, double& b) { const double t = a; a = b; b = t; }
+#endif
+B200Q_HD void vswap_lane1(double& a, double& b) { vswap(a, b); }
+
 // chunk <-> registers.  `soa` selects the complex64 chunk format; shared memory is always SoA.
 B200Q_HD void unpack(const chunk_f& v, pk& re, pk& im, bool soa) {
   if (soa) { re = v.lo; im = v.hi; }
@@ -253,7 +289,9 @@ B200Q_HD void apply_mat1(const b200q_op_t& op, typename Traits<Real>::V* re, typ
   constexpr int VS = Traits<Real>::VS;
   const uint32_t cm = op.ctrl_reg >> VS, cv = cm & ~xm;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+#ifndef EXP_NO_LANE
   if (VS && op.slot == 0) { mat1_lane<Real>(re, im, m, cm, cv); return; }
+#endif
   const int s = int(op.slot) - VS;
   const Coef<V> k = make_coef<Real, V>(m, (xm >> s) & 1u);
   const bool ctrl = cm != 0 || lane_ctrl;
@@ -263,7 +301,9 @@ B200Q_HD void apply_mat1(const b200q_op_t& op, typename Traits<Real>::V* re, typ
     else if (var == VAR_RXLIKE) mat1_chunk_slot<V, VAR_RXLIKE, false>(s, re, im, k, 0, 0, false);
     else mat1_chunk_slot<V, VAR_GENERAL, false>(s, re, im, k, 0, 0, false);
   } else {
+#ifndef EXP_NO_CTRLMAT
     mat1_chunk_slot<V, VAR_GENERAL, true>(s, re, im, k, cm, cv, lane_ctrl);
+#endif
   }
 }
 
@@ -277,20 +317,16 @@ B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, uint32_t cv, bool lane_ctrl) {
     if (c & (1 << S)) continue;
     if ((uint32_t(c) & cm) != cv) continue;
     const int d = c | (1 << S);
-    const V ar = re[c], ai = im[c], br = re[d], bi = im[d];
-    if (lane_ctrl) {
-      re[c] = vblend1(ar, br); im[c] = vblend1(ai, bi); re[d] = vblend1(br, ar); im[d] = vblend1(bi, ai);
-    } else {
-      re[c] = br; im[c] = bi; re[d] = ar; im[d] = ai;
-    }
+    if (lane_ctrl) { vswap_lane1(re[c], re[d]); vswap_lane1(im[c], im[d]); }
+    else { vswap(re[c], re[d]); vswap(im[c], im[d]); }
   }
 }
 B200Q_HD void x_lane(pk* re, pk* im, uint32_t cm, uint32_t cv) {
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
     if ((uint32_t(c) & cm) != cv) continue;
-    re[c] = pk_make(pk_y(re[c]), pk_x(re[c]));
-    im[c] = pk_make(pk_y(im[c]), pk_x(im[c]));
+    vswap_lanes(re[c]);
+    vswap_lanes(im[c]);
   }
 }
 B200Q_HD void x_lane(double*, double*, uint32_t, uint32_t) {}
@@ -304,9 +340,14 @@ B200Q_HD void apply_x(const b200q_op_t& op, typename Traits<Real>::V* re, typena
   constexpr int VS = Traits<Real>::VS;
   const uint32_t cm = op.ctrl_reg >> VS, cv = cm & ~xm;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
+#ifndef EXP_NO_LANE
   if (VS && op.slot == 0) { x_lane(re, im, cm, cv); return; }
+#endif
   const int s = int(op.slot) - VS;
   if (op.ctrl_reg == 0) { xm ^= 1u << s; return; }
+#ifdef EXP_NO_XCHUNK
+  return;
+#endif
   switch (s) {
     case 0: x_chunk<V, 0>(re, im, cm, cv, lane_ctrl); break;
     case 1: x_chunk<V, 1>(re, im, cm, cv, lane_ctrl); break;
@@ -394,7 +435,9 @@ B200Q_HD void apply_diag(const b200q_op_t& op, typename Traits<Real>::V* re, typ
   const uint32_t cm = op.ctrl_reg >> VS;
   const bool lane_ctrl = VS && (op.ctrl_reg & 1u);
   if (nreg == 2 || cm != 0) {
+#ifndef EXP_NO_DIAGGEN
     diag_generic<Real>(op, re, im, d, tsel, xm);
+#endif
     return;
   }
   if (nreg == 0) {
@@ -590,6 +633,8 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid,
   bool rho_dirty = false;
   uint32_t xm = 0;   // X relabelling mask over the chunk-level register slots
   for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
+#pragma unroll
+    for (int c = 0; c < NE; ++c) { vpin(re[c]); vpin(im[c]); }
     const b200q_op_t& op = P.ops[o];
     if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
     if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;

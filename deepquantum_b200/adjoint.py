@@ -62,8 +62,15 @@ class CircuitFunction(torch.autograd.Function):
         plan = prog.plan(y.dtype)
         psi = y.clone()
         lam = grad_y.contiguous().clone()
-        grad_m = torch.zeros_like(mats)
+        # cotangent of the matrix buffer, always accumulated in double precision
+        grad_m = torch.zeros(mats.shape, dtype=torch.complex128, device=mats.device)
+        # only gates whose matrix is computed from parameters / data need a gradient
+        need = (C.c_uint8 * max(1, len(prog.low.records)))(*[0 if r[4] in ('none', 'const') else 1
+                                                             for r in prog.low.records])
+        if not ctx.needs_input_grad[1]:
+            need = (C.c_uint8 * max(1, len(prog.low.records)))()
         lib = L.load()
         L.check(lib.b200q_adjoint_run(plan._h, psi.data_ptr(), lam.data_ptr(), mats.data_ptr(), grad_m.data_ptr(),
-                                      None, engine._stream(psi)))
-        return (lam.reshape(grad_y.shape) if ctx.x_needs_grad else None), grad_m, None, None, None
+                                      need, engine._stream(psi)))
+        gm = grad_m.to(mats.dtype) if ctx.needs_input_grad[1] else None
+        return (lam.reshape(grad_y.shape) if ctx.x_needs_grad else None), gm, None, None, None

@@ -321,6 +321,30 @@ B200Q_HD void x_chunk(V* re, V* im, uint32_t cm, uint32_t cv, bool lane_ctrl) {
     else { vswap(re[c], re[d]); vswap(im[c], im[d]); }
   }
 }
+// CX with exactly one chunk-level control slot CS (and no lane control): the elements to swap are those
+// whose REGISTER bit CS equals `cval` -- one thread-level branch, compile-time indices inside.
+template <typename V, int S, int CS>
+B200Q_HD void x_chunk_c1(V* re, V* im, bool cval) {
+  if (cval) {
+#pragma unroll
+    for (int c = 0; c < NE; ++c)
+      if (!(c & (1 << S)) && (c & (1 << CS))) { vswap(re[c], re[c | (1 << S)]); vswap(im[c], im[c | (1 << S)]); }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NE; ++c)
+      if (!(c & (1 << S)) && !(c & (1 << CS))) { vswap(re[c], re[c | (1 << S)]); vswap(im[c], im[c | (1 << S)]); }
+  }
+}
+template <typename V, int S>
+B200Q_HD void x_chunk_c1_cs(int cs, V* re, V* im, bool cval) {
+  switch (cs) {
+    case 0: if (S != 0) x_chunk_c1<V, S, (S != 0 ? 0 : 1)>(re, im, cval); break;
+    case 1: if (S != 1) x_chunk_c1<V, S, (S != 1 ? 1 : 0)>(re, im, cval); break;
+    case 2: if (S != 2) x_chunk_c1<V, S, (S != 2 ? 2 : 0)>(re, im, cval); break;
+    default: if (S != 3) x_chunk_c1<V, S, (S != 3 ? 3 : 0)>(re, im, cval); break;
+  }
+}
+
 B200Q_HD void x_lane(pk* re, pk* im, uint32_t cm, uint32_t cv) {
 #pragma unroll
   for (int c = 0; c < NE; ++c) {
@@ -345,9 +369,17 @@ B200Q_HD void apply_x(const b200q_op_t& op, typename Traits<Real>::V* re, typena
 #endif
   const int s = int(op.slot) - VS;
   if (op.ctrl_reg == 0) { xm ^= 1u << s; return; }
-#ifdef EXP_NO_XCHUNK
-  return;
-#endif
+  if (!lane_ctrl && (cm & (cm - 1)) == 0) {   // exactly one chunk-level control
+    const int cs = (cm & 1) ? 0 : ((cm & 2) ? 1 : ((cm & 4) ? 2 : 3));
+    const bool cval = ((xm >> cs) & 1u) == 0;
+    switch (s) {
+      case 0: x_chunk_c1_cs<V, 0>(cs, re, im, cval); break;
+      case 1: x_chunk_c1_cs<V, 1>(cs, re, im, cval); break;
+      case 2: x_chunk_c1_cs<V, 2>(cs, re, im, cval); break;
+      default: x_chunk_c1_cs<V, 3>(cs, re, im, cval); break;
+    }
+    return;
+  }
   switch (s) {
     case 0: x_chunk<V, 0>(re, im, cm, cv, lane_ctrl); break;
     case 1: x_chunk<V, 1>(re, im, cm, cv, lane_ctrl); break;

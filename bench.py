@@ -8,8 +8,8 @@ bandwidth of the fused tile kernel, next to the reference's CPU PyTorch path tim
 One *step* = one full pass of the hot path over one synthetic circuit: |0...0> is (re)initialised
 on the device and every gate of the circuit is applied.
   N = 1 : BASELINE config 2 -- 28 qubits, depth 40, complex64 (1 680 gate applications, 2 GiB state).
-  N > 1 : BASELINE config 4 shape -- the high-order qubit index is sharded over the N ranks
-          (30 local qubits per GPU, i.e. 30 + log2 N qubits in total: weak scaling), depth 30.
+  N > 1 : the SAME circuit with the high-order qubit index sharded over the N ranks (strong scaling);
+          `--nqubit 33 --depth 30` runs the BASELINE config-4 size.
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -45,17 +45,11 @@ def parse():
 
 
 def workload(args):
-    n_gpus = args.gpus
-    if n_gpus == 1:
-        n = args.nqubit or 28
-        depth = args.depth or 40
-        name = f'config2: {n}-qubit random Clifford+RX, depth {depth}, complex64, single B200'
-    else:
-        g = n_gpus.bit_length() - 1
-        n = args.nqubit or (30 + g)
-        depth = args.depth or 30
-        name = (f'config4 shape: {n}-qubit random Clifford+RX, depth {depth}, complex64, high-order index sharded '
-                f'over {n_gpus} ranks ({n - g} local qubits)')
+    n = args.nqubit or 28
+    depth = args.depth or 40
+    name = f'config2: {n}-qubit random Clifford+RX, depth {depth}, complex64, single B200'
+    if args.gpus > 1:
+        name += f' -- sharded over {args.gpus} ranks'
     return n, depth, name
 
 
@@ -140,7 +134,7 @@ def run_reference(args):
     base = vals[-1]
     base['value'] = v
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * ngates / v, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': 1e3 * ngates / v, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
             'config': {'workload': name, 'gates': ngates, 'note': 'each step is a time-boxed sample of the circuit; '
                        'ms_per_step is extrapolated to the full circuit'},
@@ -237,7 +231,7 @@ def run_single(args):
     achieved = n_passes * args.steps * bytes_pass / (kern_ms * 1e-3) / 1e9
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64',
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c64',
         'data': 'synthetic',
         'config': {'workload': name, 'gates': ngates, 'passes': n_passes, 'gates_per_pass': ngates / n_passes,
                    'state_bytes': state_bytes, 'l2': 'state (2 GiB) is larger than L2 (126 MB): no flush needed',

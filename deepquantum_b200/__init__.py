@@ -10,7 +10,10 @@ __version__ = '0.1.0'
 
 from . import _lib, engine, workloads  # noqa: F401
 from ._lib import B200QError  # noqa: F401
-from .circuit import QubitCircuit  # noqa: F401
+from .circuit import DistributedQubitCircuit, QubitCircuit  # noqa: F401
+from .communication import (cleanup_distributed, comm_exchange_arrays, comm_get_rank, comm_get_world_size,  # noqa: F401
+                            setup_distributed)
+from .distributed import DistributedQubitState  # noqa: F401
 from .gate import (Barrier, CNOT, Fredkin, Hadamard, Identity, ImaginarySwap, LatentGate, PauliX, PauliY,  # noqa: F401
                    PauliZ, PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz,
                    SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
@@ -19,3 +22,5 @@ from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, R
 from .operation import Gate, Layer, Operation, dtype_map  # noqa: F401
 from .qmath import evolve_state, evolve_state_controlled, inverse_permutation, multi_kron  # noqa: F401
 from .state import QubitState, amplitude_encoding  # noqa: F401
+from . import photonic  # noqa: F401,E402
+from .photonic import QumodeCircuit  # noqa: F401,E402

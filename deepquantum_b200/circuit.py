@@ -586,3 +586,73 @@ class QubitCircuit(Operation):
 
     def reset(self, *args, **kwargs):
         raise NotImplementedError('Reset is non-unitary and outside the accelerated path')
+
+
+class DistributedQubitCircuit(QubitCircuit):
+    """Circuit on a statevector sharded over the ranks of the default process group (reference
+    circuit.py:1625-1770).  `forward` is in place and `no_grad`, like the reference; it returns the
+    `DistributedQubitState` whose `.amps` is this rank's slice of the final state in the reference layout."""
+
+    def __init__(self, nqubit: int, name: str | None = None, reupload: bool = False, shots: int = 1024) -> None:
+        super().__init__(nqubit=nqubit, init_state='zeros', name=name, reupload=reupload, shots=shots)
+        self._sharded = None
+        self._executor = None
+
+    def set_init_state(self, init_state='zeros') -> None:
+        from .distributed import DistributedQubitState
+        if isinstance(init_state, DistributedQubitState):
+            self.init_state = init_state
+        else:
+            self.init_state = DistributedQubitState(self.nqubit)
+
+    def _apply(self, fn):
+        nn.Module._apply(self, fn)
+        if self._program is not None:
+            self._program.low._const_cache.clear()
+        return self
+
+    @torch.no_grad()
+    def forward(self, data: torch.Tensor | None = None, state=None):
+        from .distributed import CudaExecutor, ShardedProgram
+        if state is None:
+            self.init_state.reset()
+        else:
+            self.init_state = state
+        st = self.init_state
+        with torch.enable_grad():
+            self.encode(data)
+        prog = self._get_program()
+        if self._sharded is None or self._sharded.low is not prog.low:
+            self._sharded = ShardedProgram(prog.low, self.nqubit, st.world_size, st.rank)
+        if self._executor is None:
+            engine.require_cuda(st.amps, 'the distributed state (move the circuit with cir.to(f"cuda:{local_rank}"))')
+            self._executor = CudaExecutor()
+        mats = prog.low.build_matrices(st.amps.dtype, st.amps.device).detach()
+        self._sharded.run(st, mats, self._executor, getattr(self, '_marks', None))
+        self.state = st
+        return st
+
+    def expectation(self, shots: int | None = None) -> torch.Tensor:
+        """Z-string observables: local fused reduction + one all-reduce (reference distributed.py:288-294)."""
+        import torch.distributed as dist
+        assert len(self.observables) > 0, 'There is no observable'
+        st = self.state
+        n, nl = self.nqubit, st.log_num_amps_per_node
+        masks = []
+        for ob in self.observables:
+            assert set(ob.basis) == {'z'}, 'only Z-string observables are implemented for the sharded state'
+            m = 0
+            for w in ob.wires:
+                m |= 1 << (n - 1 - w[0])
+            masks.append(m)
+        mt = torch.tensor(masks, dtype=torch.int64, device=st.amps.device)
+        vals = engine.expectation_z(st.amps, nl, mt, 1, index_offset=st.rank << nl).reshape(-1)
+        if dist.is_initialized() and st.world_size > 1:
+            dist.all_reduce(vals)
+        return vals.to(st.amps.real.dtype)
+
+    def cnot(self, control: int, target: int) -> None:
+        self.cx(control, target)      # reference circuit.py:1764-1766: global controls then need no exchange
+
+    def toffoli(self, control1: int, control2: int, target: int) -> None:
+        self.ccx(control1, control2, target)

@@ -16,10 +16,8 @@ struct b200q_plan {
   Plan* p;
 };
 
-namespace {
-
+namespace b200q {
 thread_local std::string g_err;
-
 int set_err(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -29,6 +27,9 @@ int cuda_err(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return (int)e;
 }
+}  // namespace b200q
+
+namespace {
 
 // ------------------------------------------------------------------------------------------------
 // fused tile kernel
@@ -573,10 +574,6 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
     if (rc) return rc;
   }
   return 0;
-}
-
-int b200q_qudit_apply(void*, int, int, int, const void*, const int32_t*, int, int64_t, void*) {
-  return set_err(B200Q_EUNSUPPORTED, "b200q_qudit_apply: not built yet");
 }
 
 }  // extern "C"

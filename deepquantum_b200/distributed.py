@@ -1,0 +1,270 @@
+"""Sharded statevector: the high-order qubit index is split over the ranks (reference state.py:342-383,
+distributed.py:57-202, circuit.py:1625-1770), re-designed around ONE rule: the local fused engine only ever
+sees local qubits.
+
+  * rank r holds flat indices [r * 2^(n-g), (r+1) * 2^(n-g)), g = log2(world size) (wires 0..g-1 global);
+  * a persistent logical -> physical qubit map replaces the reference's swap-in / apply / swap-out
+    (distributed.py:194-201): gates run fused on the local shard while their non-diagonal targets are
+    local; controls and diagonal gates on global qubits need NO data exchange (they become per-rank
+    predicates / phases, distributed.py:84-93);
+  * when the front of the circuit is blocked by global targets, ONE all-to-all block transpose swaps all g
+    global qubits with the top g local qubits (each rank sends (W-1)/W of its shard once);
+  * the map is restored before the state is handed back, so `.amps` has the reference layout.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import engine
+from .communication import block_transpose, comm_get_rank, comm_get_world_size
+from .operation import Lowering, apply_complex_fix
+
+
+class DistributedQubitState(nn.Module):
+    """Per-rank shard `amps` plus a same-size `buffer` (reference state.py:342-383)."""
+
+    def __init__(self, nqubit: int) -> None:
+        super().__init__()
+        self.world_size = comm_get_world_size()
+        self.rank = comm_get_rank()
+        assert self.world_size & (self.world_size - 1) == 0
+        assert 2**nqubit >= self.world_size
+        self.nqubit = nqubit
+        self.log_num_nodes = self.world_size.bit_length() - 1
+        self.log_num_amps_per_node = nqubit - self.log_num_nodes
+        self.num_amps_per_node = 2**self.log_num_amps_per_node
+        self.register_buffer('amps', torch.zeros(self.num_amps_per_node) + 0j)
+        self.register_buffer('buffer', torch.zeros(self.num_amps_per_node) + 0j)
+        self.reset()
+
+    def _apply(self, fn):
+        tensors = {k: self._buffers.pop(k) for k in ('amps', 'buffer')}
+        super()._apply(fn)
+        for key, value in apply_complex_fix(fn, tensors).items():
+            self.register_buffer(key, value)
+        return self
+
+    def reset(self) -> None:
+        self.amps.zero_()
+        if self.rank == 0:
+            self.amps[0] = 1.0
+
+
+class CudaExecutor:
+    """Runs one local segment (a fused plan over the shard) on the GPU through the C ABI."""
+
+    def make_plan(self, nlocal, dtype, structs):
+        return engine.FusedPlan(nlocal, dtype, structs)
+
+    def run_plan(self, plan, amps, mats):
+        plan.run(amps, mats, 1, 0)
+
+
+class ShardedProgram:
+    """Per-rank execution schedule of a lowered gate program: local segments separated by block transposes."""
+
+    def __init__(self, low: Lowering, nqubit: int, world_size: int, rank: int):
+        self.low, self.n, self.world, self.rank = low, nqubit, world_size, rank
+        self.g = world_size.bit_length() - 1
+        self.nl = nqubit - self.g
+        self.plans = {}
+        self._schedule()
+
+    def _schedule(self):
+        """Greedy list scheduling with commutation (same rule as the C++ planner) + Belady-style eviction."""
+        n, g, nl = self.n, self.g, self.nl
+        recs = self.low.records
+        phys = list(range(n))                # logical bit -> physical bit
+        done = [False] * len(recs)
+        steps = []                           # ('seg', [localised records / ('pswap', a, b)]) | ('swap',)
+        remaining = len(recs)
+        nswaps = 0
+        INF = 1 << 60
+
+        def acts(rec):
+            kind, targets, ctrl = rec[0], rec[1], rec[2]
+            tmask = sum(1 << t for t in targets)
+            dense_diag = kind == L.GATE_DIAG and len(targets) > 2   # lowered as a dense gate by the planner
+            tm = tmask if (kind != L.GATE_DIAG or dense_diag) else 0
+            dm = sum(1 << c for c in ctrl) | (tmask if tm == 0 else 0)
+            return tm, dm
+
+        def local_swaps(seg, wanted):
+            """wanted: {physical position: logical bit}; emit physical SWAPs until satisfied."""
+            for pos, b in wanted.items():
+                if phys[b] != pos:
+                    other = phys.index(pos)
+                    seg.append(('pswap', phys[b], pos))
+                    phys[other], phys[b] = phys[b], pos
+
+        def transpose():
+            nonlocal nswaps
+            inv = {p: b for b, p in enumerate(phys)}
+            for jj in range(g):
+                a, b = inv[nl + jj], inv[nl - g + jj]
+                phys[a], phys[b] = phys[b], phys[a]
+            steps.append(('swap',))
+            nswaps += 1
+
+        while remaining:
+            glob_mask = sum(1 << b for b in range(n) if phys[b] >= nl)
+            seg, bfull, bdiag, first_blocked = [], 0, 0, None
+            for i, rec in enumerate(recs):
+                if done[i]:
+                    continue
+                tm, dm = acts(rec)
+                ok = not (tm & (bfull | bdiag)) and not (dm & bfull) and not (tm & glob_mask)
+                if ok:
+                    seg.append(self._localise(i, rec, phys))
+                    done[i] = True
+                    remaining -= 1
+                else:
+                    if first_blocked is None and (tm & glob_mask) and not (tm & (bfull | bdiag)) and not (dm & bfull):
+                        first_blocked = tm
+                    bfull |= tm
+                    bdiag |= dm
+            if remaining:
+                if g == 0 or first_blocked is None:
+                    raise RuntimeError('sharded scheduler stalled (internal error)')
+                # evict the g local qubits whose next non-diagonal use is farthest away (never a target of the
+                # gate we are unblocking), move them to the top g local positions, then block-transpose
+                next_use = [INF] * n
+                for i in range(len(recs) - 1, -1, -1):
+                    if not done[i]:
+                        tm, _ = acts(recs[i])
+                        for b in range(n):
+                            if tm >> b & 1:
+                                next_use[b] = i
+                cand = [b for b in range(n) if phys[b] < nl and not (first_blocked >> b & 1)]
+                if len(cand) < g:
+                    raise RuntimeError('not enough local qubits to unblock a gate: it needs more than n_local - g targets')
+                cand.sort(key=lambda b: (-next_use[b], -phys[b]))
+                victims = cand[:g]
+                # keep victims that already sit in the top positions where they are
+                tops = [nl - g + jj for jj in range(g)]
+                placed = {phys[b]: b for b in victims if phys[b] in tops}
+                free = [t for t in tops if t not in placed]
+                wanted = dict(placed)
+                for b in victims:
+                    if phys[b] not in tops:
+                        wanted[free.pop()] = b
+                local_swaps(seg, wanted)
+            if seg:
+                steps.append(('seg', seg))
+            if remaining:
+                transpose()
+        # ---- restore the reference layout (logical bit b at physical bit b) -------------------------------
+        if phys != list(range(n)):
+            should_glob = list(range(nl, n))
+            if any(phys[b] != b for b in should_glob):
+                seg = []
+                if any(phys[b] >= nl for b in should_glob):
+                    # bring every currently-global qubit in, evicting only qubits that belong to the local part
+                    cand = [b for b in range(nl) if phys[b] < nl]
+                    cand.sort(key=lambda b: -phys[b])
+                    tops = [nl - g + jj for jj in range(g)]
+                    victims = cand[:g]
+                    placed = {phys[b]: b for b in victims if phys[b] in tops}
+                    free = [t for t in tops if t not in placed]
+                    wanted = dict(placed)
+                    for b in victims:
+                        if phys[b] not in tops:
+                            wanted[free.pop()] = b
+                    local_swaps(seg, wanted)
+                    if seg:
+                        steps.append(('seg', seg))
+                    transpose()
+                    seg = []
+                local_swaps(seg, {nl - g + jj: nl + jj for jj in range(g)})
+                if seg:
+                    steps.append(('seg', seg))
+                transpose()
+            seg = []
+            local_swaps(seg, {b: b for b in range(nl)})
+            if seg:
+                steps.append(('seg', seg))
+        assert phys == list(range(n)), phys
+        self.steps, self.n_swaps = steps, nswaps
+        self.n_segments = sum(1 for s in steps if s[0] == 'seg')
+
+    def _localise(self, i, rec, phys):
+        """Rewrite record i for this rank: physical local bits, global controls resolved against the rank,
+        global diagonal selectors folded into a per-rank derived matrix."""
+        kind, targets, ctrl, adj, block, idx, size, hint = rec
+        nl, rank = self.nl, self.rank
+        local_ctrl, active = [], True
+        for c in ctrl:
+            p = phys[c]
+            if p >= nl:
+                if not (rank >> (p - nl)) & 1:
+                    active = False
+            else:
+                local_ctrl.append(p)
+        pt = [phys[t] for t in targets]
+        fix = None
+        if kind == L.GATE_DIAG and any(p >= nl for p in pt):
+            # selector bits on rank bits are constants for this rank
+            fix = [(j, (rank >> (p - nl)) & 1) for j, p in enumerate(pt) if p >= nl]
+            pt = [p for p in pt if p < nl]
+        return (i, kind, tuple(pt), tuple(local_ctrl), adj, active, fix, hint)
+
+    def run(self, state: DistributedQubitState, mats: torch.Tensor, executor, marks=None) -> None:
+        """`marks`: optional list receiving (kind, start_event, end_event) per step (bench.py timing)."""
+        nl = self.nl
+        for si, step in enumerate(self.steps):
+            ev0 = None
+            if marks is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            if step[0] == 'swap':
+                block_transpose(state.amps, state.buffer)
+                state.amps, state.buffer = state.buffer, state.amps
+                if marks is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev1.record()
+                    marks.append(('swap', ev0, ev1))
+                continue
+            structs, extra, off_extra = [], [], mats.numel()
+            for item in step[1]:
+                if item[0] == 'pswap':       # physical SWAP of two local bits = three CX relabellings
+                    a, b = item[1], item[2]
+                    structs += [L.make_gate(L.GATE_X, [b], [a]), L.make_gate(L.GATE_X, [a], [b]),
+                                L.make_gate(L.GATE_X, [b], [a])]
+                    continue
+                (i, kind, pt, ctrl, adj, active, fix, hint) = item
+                if not active:
+                    continue
+                off = self.low.offsets[i]
+                if fix is not None:
+                    k = len(self.low.records[i][1])
+                    d = torch.diagonal(mats[off:off + 4**k].reshape(2**k, 2**k))
+                    sel = d.reshape([2] * k)         # index order: matrix bit k-1 ... bit 0
+                    for j, bit in sorted(fix):   # ascending j = last axis first, so earlier axes keep their index
+                        sel = sel.select(k - 1 - j, bit)
+                    vals = sel.reshape(-1)
+                    if len(pt) == 0:
+                        # a pure per-rank phase: a diagonal gate on local bit 0 with both entries equal
+                        pt, vals = (0,), vals.repeat(2)
+                    extra.append(torch.diag(vals).reshape(-1))
+                    structs.append(L.make_gate(L.GATE_DIAG, pt, ctrl, off_extra, adj))
+                    off_extra += extra[-1].numel()
+                else:
+                    structs.append(L.make_gate(kind, pt, ctrl, off, adj, hint))
+            if not structs:
+                continue
+            m = torch.cat([mats] + extra) if extra else mats
+            key = (si, state.amps.dtype)
+            if key not in self.plans:
+                self.plans[key] = executor.make_plan(nl, state.amps.dtype, structs)
+            executor.run_plan(self.plans[key], state.amps, m)
+            if marks is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                marks.append(('seg', ev0, ev1))
+
+    def stats(self):
+        """(gates, local passes, segments, block transposes) of this rank's schedule (after a first run)."""
+        passes = sum(getattr(p, 'n_passes', 0) for p in self.plans.values())
+        return {'gates': len(self.low.records), 'passes': passes, 'segments': self.n_segments, 'swaps': self.n_swaps}

@@ -11,7 +11,7 @@ LIB = os.path.join(OUT, 'libb200q_hostemu.so')
 def build(force=False):
     srcs = [os.path.join(HERE, 'hostemu.cpp'), os.path.join(ROOT, 'deepquantum_b200', 'csrc', 'b200q_planner.cpp')]
     deps = srcs + [os.path.join(ROOT, 'deepquantum_b200', 'csrc', f)
-                   for f in ('b200q_tile_body.h', 'b200q_program.h', 'b200q_planner.h')] + [
+                   for f in ('b200q_tile_body.h', 'b200q_program.h', 'b200q_planner.h', 'b200q_qudit_geom.h')] + [
         os.path.join(ROOT, 'include', 'b200q.h')]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB

@@ -148,3 +148,46 @@ extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, i
   delete pl;
   return 0;
 }
+
+// ---- qudit (Fock tensor) kernel: same geometry helpers, dense contraction -----------------------------
+#include "../../deepquantum_b200/csrc/b200q_qudit_geom.h"
+#include <complex>
+
+template <typename Real>
+static void emu_qudit(std::complex<Real>* st, const QuditGeom& g, const std::complex<Real>* m, int64_t batch) {
+  const int D = g.D, G = g.G;
+  std::vector<std::complex<Real>> xs(size_t(D) * G), ys(size_t(D) * G);
+  const long long nblocks = (g.n_rest + G - 1) / G;
+  for (int64_t b = 0; b < batch; ++b) {
+    std::complex<Real>* s = st + b * g.state_size;
+    for (long long blk = 0; blk < nblocks; ++blk) {
+      const long long r0 = blk * G;
+      for (int e = 0; e < G * D; ++e) {
+        int gi, t;
+        qudit_elem(g, e, &gi, &t);
+        xs[size_t(t) * G + gi] = (r0 + gi < g.n_rest) ? s[qudit_offset(g, r0 + gi, t)] : std::complex<Real>(0);
+      }
+      for (int r = 0; r < D; ++r)
+        for (int gi = 0; gi < G; ++gi) {
+          std::complex<Real> acc(0);
+          for (int c = 0; c < D; ++c) acc += m[r * D + c] * xs[size_t(c) * G + gi];
+          ys[size_t(r) * G + gi] = acc;
+        }
+      for (int e = 0; e < G * D; ++e) {
+        int gi, t;
+        qudit_elem(g, e, &gi, &t);
+        if (r0 + gi < g.n_rest) s[qudit_offset(g, r0 + gi, t)] = ys[size_t(t) * G + gi];
+      }
+    }
+  }
+}
+
+extern "C" int hostemu_qudit(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
+                             int n_targets, int64_t batch) {
+  QuditGeom g;
+  const char* err = "";
+  if (qudit_make_geom(n_modes, d, modes, n_targets, dtype == B200Q_C64 ? 8 : 16, &g, &err)) return -1;
+  if (dtype == B200Q_C64) emu_qudit<float>((std::complex<float>*)state, g, (const std::complex<float>*)matrix, batch);
+  else emu_qudit<double>((std::complex<double>*)state, g, (const std::complex<double>*)matrix, batch);
+  return 0;
+}

@@ -250,14 +250,27 @@ def test_qaoa_loss_and_gradient_match_reference_autograd():
         np.testing.assert_allclose(params.grad.cpu().numpy(), g[key + '/grad'], atol=1e-7, rtol=1e-7)
 
 
+@pytest.mark.parametrize('with_h', [False, True])
 @pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
-def test_state_autograd_matches_dense_torch(rdtype):
-    """Autograd of an arbitrary real function of the output state w.r.t. gate parameters AND the input state."""
+def test_state_autograd_matches_dense_torch(rdtype, with_h):
+    """Autograd of an arbitrary real function of the output state w.r.t. gate parameters AND the input state.
+
+    The backward pass un-computes the state with U^dagger, which inverts U only as far as U is unitary.  With
+    exactly unitary gates the complex128 gradient matches dense autograd to 1e-9; the reference's Hadamard is a
+    float32-rounded constant even in its complex128 path (gate.py:1069, unitary to 6e-8 only), which bounds
+    the gradient accuracy at ~1e-6 -- the same floor as the reference's own adjoint (adjoint.py:60)."""
     import torch_port
     n = 12
     g = torch.Generator().manual_seed(5)
+
+    def first_layer(c):
+        if with_h:
+            c.hlayer()
+        else:
+            c.rzlayer()
+
     cir = dq.QubitCircuit(n)
-    cir.hlayer()
+    first_layer(cir)
     cir.rxlayer()
     cir.cnot_ring()
     cir.u3layer()
@@ -282,7 +295,8 @@ def test_state_autograd_matches_dense_torch(rdtype):
     prog = cir._get_program()
     params = {name: p.detach().cpu().double().requires_grad_(True) for name, p in cir.named_parameters()}
     cpu = dq.QubitCircuit(n)
-    cpu.hlayer(); cpu.rxlayer(); cpu.cnot_ring(); cpu.u3layer(); cpu.rzz([0, 5]); cpu.rxx([n - 1, 3])
+    first_layer(cpu)
+    cpu.rxlayer(); cpu.cnot_ring(); cpu.u3layer(); cpu.rzz([0, 5]); cpu.rxx([n - 1, 3])
     cpu.crz(2, 7); cpu.cx(4, 9); cpu.rylayer()
     cpu.to(torch.double)
     with torch.no_grad():
@@ -301,8 +315,51 @@ def test_state_autograd_matches_dense_torch(rdtype):
     o = x.reshape(-1)
     ref_loss = (wvec.cpu().to(torch.complex128).conj() * o).sum().real + (o.real**2 * torch.arange(2**n) / 2**n).sum()
     ref_loss.backward()
-    tol = 1e-9 if rdtype == torch.float64 else 2e-4
-    assert abs(float(loss) - float(ref_loss)) < tol * 10
+    tol = (2e-6 if with_h else 1e-9) if rdtype == torch.float64 else 3e-4
+    assert abs(float(loss) - float(ref_loss)) < max(tol * 10, 1e-8)
     for (name, p) in cpu.named_parameters():
         assert abs(float(p.grad) - float(got[name])) < tol * max(1.0, abs(float(p.grad))), name
     assert (got_psi.to(torch.complex128) - x0.grad).norm() / x0.grad.norm() < tol
+
+
+@pytest.mark.parametrize('key', ['m2_c5', 'm3_c4', 'm4_c6', 'm5_c8'])
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_fock_tensor_path(key, rdtype):
+    """Config 5 shape: squeezers + beamsplitter mesh + phase shifter on the Fock tensor, against the reference."""
+    g = _golden('fock.npz')
+    meta = json.loads(str(g[key + '/spec']))
+    n, d = meta['nmode'], meta['cutoff']
+    cir = dq.QumodeCircuit(n, 'vac', cutoff=d, backend='fock', basis=False)
+    for e in meta['spec']:
+        if e['g'] == 's':
+            cir.s(e['w'][0], e['p'][0], e['p'][1])
+        elif e['g'] == 'bs':
+            cir.bs(e['w'], e['p'])
+        else:
+            cir.ps(e['w'][0], e['p'][0])
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy()
+    ref = g[key + '/c128']
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < (1e-10 if rdtype == torch.float64 else 2e-6), err
+    # the qudit boundary function: evolve_state(..., qudit=cutoff)
+    rng = np.random.default_rng(0)
+    psi = rng.normal(size=(2, d**n)) + 1j * rng.normal(size=(2, d**n))
+    m = rng.normal(size=(d * d, d * d)) + 1j * rng.normal(size=(d * d, d * d))
+    y = dq.evolve_state(torch.tensor(psi, device='cuda').reshape([2] + [d] * n), torch.tensor(m, device='cuda'), n,
+                        [n - 1, 0], d)
+    np.testing.assert_allclose(y.reshape(2, -1).cpu().numpy(), so.evolve_state(psi, m, n, [n - 1, 0], d), atol=1e-10)
+
+
+def test_sharded_two_gpus():
+    """The sharded path over NCCL on 2 GPUs against the single-GPU engine (skipped on a 1-GPU box)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29571', os.path.join(root, 'tests', 'dist_gpu_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'SHARDED_OK' in out.stdout

@@ -173,20 +173,29 @@ class QubitCircuit(Operation):
 
     # ---------------------------------------------------------------------------------------------
     def encode(self, data: torch.Tensor | None) -> None:
-        """Route `data` slices into the encoder gates (reference circuit.py:265-293)."""
+        """Route `data` slices into the encoder gates (reference circuit.py:265-293).  Each gate also remembers
+        which elements of `data` it took, so the matrix assembly can gather all angles of a gate class with one
+        index_select instead of stacking hundreds of 0-d views."""
         if data is None:
             return
         if not self.reupload:
             assert len(data) >= self.ndata, 'The circuit needs more data, or consider data re-uploading'
         count = 0
+        ndat = len(data)
         for op in self.encoders:
             count_up = count + op.npara
-            if self.reupload and count_up > len(data):
-                n = int(np.ceil(count_up / len(data)))
+            if self.reupload and count_up > ndat:
+                n = int(np.ceil(count_up / ndat))
                 op.init_para(torch.cat([data] * n)[count:count_up])
+                idx = [i % ndat for i in range(count, count_up)]
             else:
                 op.init_para(data[count:count_up])
-            count = count_up % len(data)
+                idx = list(range(count, count_up))
+            k = 0
+            for g in (op.gates if isinstance(op, Layer) else [op]):
+                g._data_ref = (data, tuple(idx[k:k + g.npara]))
+                k += g.npara
+            count = count_up % ndat
 
     def _encode_batched(self, data: torch.Tensor) -> None:
         """2-D data: every encoder gate gets a `[batch, npara]` column block (explicit batch instead of the

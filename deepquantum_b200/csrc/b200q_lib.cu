@@ -47,16 +47,16 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chunk* tile = reinterpret_cast<chunk*>(smem_raw);
   cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(16) << CB));
+  RoundTab* tabs = reinterpret_cast<RoundTab*>(smem_raw + (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>));
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
   const uint64_t cta_base = tile_base(P, blockIdx.x);
   chunk* gstate = state + uint64_t(blockIdx.y) * chunks_per_state;
   const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
 
-  if (P.pool_elems) {
-    fill_pool<Real>(P, tid, nthreads, pool, m, false);
-    __syncthreads();
-  }
+  fill_round_tabs<Real>(P, tid, nthreads, tabs);
+  if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, m, false);
+  __syncthreads();
   const int nr = P.n_rounds;
   for (int r = 0; r < nr; ++r) {
     const b200q_round_t& Rd = P.rounds[r];
@@ -66,7 +66,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
         __syncthreads();
       }
     } else {
-      run_round<Real>(P, Rd, tid, cta_base, tile, pool, gstate, chunks_per_state);
+      run_round<Real>(P, Rd, tabs[r], tid, cta_base, tile, pool, gstate, chunks_per_state);
       if (r + 1 < nr) __syncthreads();
     }
   }
@@ -77,7 +77,7 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
                 int64_t mat_batch_stride, cudaStream_t stream) {
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
-  const size_t smem = (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>);
+  const size_t smem = (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>) + sizeof(RoundTab) * B200Q_MAX_ROUNDS;
   auto kern = b200q_tile_kernel<Real, CB>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -134,10 +134,12 @@ b200q_adjoint_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Rea
   chunk* tile_lam = reinterpret_cast<chunk*>(smem_raw + (size_t(16) << CB));
   cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(32) << CB));
   double* acc = reinterpret_cast<double*>(smem_raw + (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>));
+  RoundTab* tabs = reinterpret_cast<RoundTab*>(acc + size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP);
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
   const uint64_t cta_base = tile_base(P, blockIdx.x);
   for (int e = tid; e < int(P.n_ops) * B200Q_ACC_PER_OP; e += nthreads) acc[e] = 0.0;
+  fill_round_tabs<Real>(P, tid, nthreads, tabs);
   if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, mats, true);
   __syncthreads();
   for (int r = int(P.n_rounds) - 1; r >= 0; --r) {
@@ -149,8 +151,8 @@ b200q_adjoint_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Rea
         __syncthreads();
       }
     } else {
-      run_round_adjoint<Real>(P, Rd, tid, cta_base, tile_psi, tile_lam, pool, psi, lam, chunks_per_state, want_mask,
-                              acc);
+      run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tile_psi, tile_lam, pool, psi, lam, chunks_per_state,
+                              want_mask, acc);
       __syncthreads();
     }
   }
@@ -163,7 +165,7 @@ int launch_adjoint_pass(const b200q_pass_t& P, void* psi, void* lam, const void*
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
   const size_t smem = (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>) +
-                      size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP * sizeof(double);
+                      size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP * sizeof(double) + sizeof(RoundTab) * B200Q_MAX_ROUNDS;
   auto kern = b200q_adjoint_kernel<Real, CB>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -391,7 +393,8 @@ int b200q_plan_get_stats(const b200q_plan_t* plan, b200q_plan_stats_t* s) {
   s->n_direct_ops = p.stats.n_direct;
   s->tile_bits = std::min(p.opt.chunk_bits + (p.dtype == B200Q_C64 ? 1 : 0), p.n_bits);
   s->threads_per_cta = 1 << (p.opt.chunk_bits - B200Q_REG_CHUNK_BITS);
-  s->smem_bytes = (16 << p.opt.chunk_bits) + B200Q_POOL_MAX * (p.dtype == B200Q_C64 ? 8 : 16);
+  s->smem_bytes = (16 << p.opt.chunk_bits) + B200Q_POOL_MAX * (p.dtype == B200Q_C64 ? 8 : 16) +
+                  (int)sizeof(RoundTab) * B200Q_MAX_ROUNDS;
   return 0;
 }
 

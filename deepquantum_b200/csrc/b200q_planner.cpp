@@ -304,6 +304,17 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
           op.pool_n = (uint16_t)a.pool;
           pool += a.pool;
         }
+        // pre-decoded dispatch code
+        op.tctrl = (op.ctrl_loc != 0 || op.ctrl_glob != 0) ? 1 : 0;
+        const bool lane_slot = B.vs && op.slot == 0;
+        if (a.op_kind == B200Q_OP_MAT1) {
+          if (op.ctrl_reg == 0 && !lane_slot) {
+            const int var = (op.flags & B200Q_FLAG_REAL) ? 0 : ((op.flags & B200Q_FLAG_RXLIKE) ? 1 : 2);
+            op.code = (uint8_t)(B200Q_CODE_MAT1_FAST + 4 * var + (op.slot - B.vs));
+          } else op.code = B200Q_CODE_MAT1_SLOW;
+        } else if (a.op_kind == B200Q_OP_X) {
+          op.code = (op.ctrl_reg == 0 && !lane_slot) ? B200Q_CODE_X_RELABEL : B200Q_CODE_X_SLOW;
+        } else op.code = B200Q_CODE_DIAG;
         B.done[gi] = 1;
         ++gates_in_pass;
       }
@@ -383,6 +394,8 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         op.pool_off = (uint16_t)pool;
         op.pool_n = (uint16_t)a.pool;
         pool += a.pool;
+        op.code = B200Q_CODE_NONE;
+        op.tctrl = 1;
         Rd.op_end = (uint16_t)n_ops;
         B.done[mk[0]] = 1;
         ++gates_in_pass;

@@ -36,6 +36,14 @@ enum {
   B200Q_OP_MATK = 3   // dense 2^k x 2^k, k = 2..4, on arbitrary tile bits, applied from shared memory
 };
 
+/* pre-decoded dispatch codes: 4*variant + chunk slot for un-controlled dense 2x2 ops on a chunk-level slot */
+#define B200Q_CODE_MAT1_FAST 0   /* 0..11: variant (0 real, 1 rx-like, 2 general) * 4 + chunk slot */
+#define B200Q_CODE_MAT1_SLOW 12  /* register-slot controls or the lane slot */
+#define B200Q_CODE_X_RELABEL 13  /* chunk-level slot, no register-slot control: toggles the relabelling mask */
+#define B200Q_CODE_X_SLOW 14
+#define B200Q_CODE_DIAG 15
+#define B200Q_CODE_NONE 16
+
 #define B200Q_FLAG_ADJOINT 1u  /* use the conjugate transpose of the stored matrix */
 #define B200Q_FLAG_REAL 2u     /* MAT1: every entry is real (H, Ry, ...)                      */
 #define B200Q_FLAG_RXLIKE 4u   /* MAT1: diagonal real, off-diagonal purely imaginary (Rx)    */
@@ -58,7 +66,8 @@ typedef struct {
   uint64_t dsel_glob[2];// DIAG selector j as a single physical bit mask outside the tile (or 0)
   uint8_t tk[4];     // MATK: tile-local bit of matrix-index bit j (j = 0 is the LSB)
   uint8_t dsel_slot[2]; // DIAG selector j: register slot index, or 0xff if not a register slot
-  uint8_t pad[2];
+  uint8_t code;      // pre-decoded dispatch code (B200Q_CODE_*), filled by the planner
+  uint8_t tctrl;     // 1 if the op has thread-level or global controls (ctrl_loc / ctrl_glob non-zero)
   uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
 } b200q_op_t;
 

@@ -559,27 +559,60 @@ template <typename Real> struct RoundAddr {
   bool active;
 };
 
+// Per-round address tables, built once per CTA in shared memory (the per-thread bit-deposit loops they replace
+// were 13 % of all executed instructions): the item index tid is split into its low 4 and high 5 bits, each
+// looked up in a small table of deposited local / physical offsets.
+struct RoundTab {
+  uint32_t lb_lo[16], lb_hi[32];   // tile-local amplitude offset
+  uint64_t pb_lo[16], pb_hi[32];   // physical amplitude offset
+  uint64_t gst[4];                 // global chunk stride of each chunk-level slot
+  uint32_t sst[4];                 // swizzled tile stride of each chunk-level slot
+};
+
 template <typename Real>
-B200Q_HD RoundAddr<Real> round_addr(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base) {
+B200Q_HD void fill_round_tabs(const b200q_pass_t& P, int tid, int nthreads, RoundTab* tabs) {
+  constexpr int VS = Traits<Real>::VS, RB = Traits<Real>::RB;
+  const int item_bits = int(P.tile_bits) - RB;
+  const int per_round = 16 + 32 + 4;
+  for (int e = tid; e < int(P.n_rounds) * per_round; e += nthreads) {
+    const int r = e / per_round, j = e % per_round;
+    const b200q_round_t& Rd = P.rounds[r];
+    RoundTab& T = tabs[r];
+    if (Rd.direct) continue;
+    if (j < 48) {
+      const int lo = j < 16;
+      const int v = lo ? j : j - 16;
+      const int k0 = lo ? 0 : 4, k1 = lo ? 4 : 9;
+      uint32_t lb = 0;
+      uint64_t pb = 0;
+      for (int k = k0; k < k1 && k < item_bits; ++k) {
+        const uint32_t bit = (uint32_t(v) >> (k - k0)) & 1u;
+        const int loc = Rd.nonreg_bit[k];
+        lb |= bit << loc;
+        pb |= uint64_t(bit) << P.tile_phys[loc];
+      }
+      if (lo) { T.lb_lo[v] = lb; T.pb_lo[v] = pb; } else { T.lb_hi[v] = lb; T.pb_hi[v] = pb; }
+    } else {
+      const int s = j - 48;
+      const int loc = Rd.slot_bit[s + VS];
+      T.gst[s] = 1ull << (int(P.tile_phys[loc]) - VS);
+      T.sst[s] = swz(1u << (loc - VS));
+    }
+  }
+}
+
+template <typename Real>
+B200Q_HD RoundAddr<Real> round_addr(const b200q_pass_t& P, const RoundTab& T, int tid, uint64_t cta_base) {
   constexpr int VS = Traits<Real>::VS, RB = Traits<Real>::RB;
   RoundAddr<Real> A;
   const int item_bits = int(P.tile_bits) - RB;
   A.active = tid < (1 << item_bits);
-  uint32_t lb = 0;
-  uint64_t pb = cta_base;
-  for (int k = 0; k < item_bits; ++k) {
-    const uint32_t bit = (uint32_t(tid) >> k) & 1u;
-    const int loc = Rd.nonreg_bit[k];
-    lb |= bit << loc;
-    pb |= uint64_t(bit) << P.tile_phys[loc];
-  }
+  const int lo = tid & 15, hi = (tid >> 4) & 31;
+  const uint32_t lb = T.lb_lo[lo] | T.lb_hi[hi];
+  const uint64_t pb = cta_base | T.pb_lo[lo] | T.pb_hi[hi];
   A.lb = lb;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int loc = Rd.slot_bit[s + VS];
-    A.gst[s] = 1ull << (int(P.tile_phys[loc]) - VS);
-    A.sst[s] = swz(1u << (loc - VS));
-  }
+  for (int s = 0; s < 4; ++s) { A.gst[s] = T.gst[s]; A.sst[s] = T.sst[s]; }
   A.gbase = pb >> VS;
   A.sbase = swz(lb >> VS);
   return A;
@@ -652,11 +685,11 @@ B200Q_HD uint32_t diag_tsel(const b200q_op_t& op, uint64_t cta_base, uint32_t lb
 // one register round of one thread
 // ------------------------------------------------------------------------------------------------
 template <typename Real>
-B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base,
+B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const RoundTab& T, int tid, uint64_t cta_base,
                         typename Traits<Real>::chunk* tile, const cx<Real>* pool,
                         typename Traits<Real>::chunk* gstate, uint64_t total_chunks) {
   using V = typename Traits<Real>::V;
-  RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   if (!A.active) return;
   V re[NE], im[NE];
   gather<Real>(A, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
@@ -664,21 +697,34 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, int tid,
   Real rho_r = Real(1), rho_i = Real(0);
   bool rho_dirty = false;
   uint32_t xm = 0;   // X relabelling mask over the chunk-level register slots
+  constexpr int VS = Traits<Real>::VS;
   for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
-#pragma unroll
-    for (int c = 0; c < NE; ++c) { vpin(re[c]); vpin(im[c]); }
     const b200q_op_t& op = P.ops[o];
-    if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
-    if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;
+    if (op.tctrl) {
+      if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
+      if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;
+    }
     const cx<Real>* m = pool + op.pool_off;
-    switch (op.kind) {
-      case B200Q_OP_MAT1: apply_mat1<Real>(op, re, im, m, xm); break;
-      case B200Q_OP_X: apply_x<Real>(op, re, im, xm); break;
-      case B200Q_OP_DIAG:
+#define B200Q_FAST(CV, VAR, S)                                                          \
+  case B200Q_CODE_MAT1_FAST + 4 * CV + S: {                                              \
+    const Coef<V> k = make_coef<Real, V>(m, (xm >> S) & 1u);                             \
+    mat1_chunk<V, S, VAR, false>(re, im, k, 0, 0, false);                                \
+    break;                                                                               \
+  }
+    switch (op.code) {
+      B200Q_FAST(0, VAR_REAL, 0) B200Q_FAST(0, VAR_REAL, 1) B200Q_FAST(0, VAR_REAL, 2) B200Q_FAST(0, VAR_REAL, 3)
+      B200Q_FAST(1, VAR_RXLIKE, 0) B200Q_FAST(1, VAR_RXLIKE, 1) B200Q_FAST(1, VAR_RXLIKE, 2) B200Q_FAST(1, VAR_RXLIKE, 3)
+      B200Q_FAST(2, VAR_GENERAL, 0) B200Q_FAST(2, VAR_GENERAL, 1) B200Q_FAST(2, VAR_GENERAL, 2)
+      B200Q_FAST(2, VAR_GENERAL, 3)
+      case B200Q_CODE_MAT1_SLOW: apply_mat1<Real>(op, re, im, m, xm); break;
+      case B200Q_CODE_X_RELABEL: xm ^= 1u << (int(op.slot) - VS); break;
+      case B200Q_CODE_X_SLOW: apply_x<Real>(op, re, im, xm); break;
+      case B200Q_CODE_DIAG:
         apply_diag<Real, true>(op, re, im, m, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i, rho_dirty);
         break;
       default: break;
     }
+#undef B200Q_FAST
   }
   if (rho_dirty) {
     const V pr = vset(rho_r, (V*)nullptr), pi = vset(rho_i, (V*)nullptr), npi = vset(-rho_i, (V*)nullptr);
@@ -896,13 +942,14 @@ inline void cta_accumulate(double* cta_acc, const double* v) {
 // swapped with respect to the forward round.  Every thread of the CTA must call this (the gradient
 // reduction inside is warp-collective).
 template <typename Real>
-B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, int tid, uint64_t cta_base,
+B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, const RoundTab& T, int tid,
+                                uint64_t cta_base,
                                 typename Traits<Real>::chunk* tile_psi, typename Traits<Real>::chunk* tile_lam,
                                 const cx<Real>* pool, typename Traits<Real>::chunk* gpsi,
                                 typename Traits<Real>::chunk* glam, uint64_t total_chunks, uint64_t want_mask,
                                 double* cta_acc) {
   using V = typename Traits<Real>::V;
-  RoundAddr<Real> A = round_addr<Real>(P, Rd, tid, cta_base);
+  RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   V pr[NE], pi[NE], lr[NE], li[NE];
   uint32_t xm = 0;
   const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;

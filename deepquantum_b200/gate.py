@@ -111,7 +111,19 @@ class _Parametric:
     def init_para(self, inputs: Any = None) -> None:
         self._batched = None
         self._set('theta', self.inputs_to_tensor(inputs))
-        self.update_matrix()
+        self._matrix_cache = None     # `matrix` is refreshed lazily: encode() re-parametrises hundreds of gates
+
+    @property
+    def matrix(self) -> torch.Tensor:
+        """Detached local matrix of the current parameters (the reference refreshes it eagerly in init_para,
+        gate.py:411-415; here it is computed on first access so that `encode` costs no kernel launches)."""
+        if self.__dict__.get('_matrix_cache') is None:
+            self.update_matrix()
+        return self.__dict__['_matrix_cache']
+
+    @matrix.setter
+    def matrix(self, value) -> None:
+        self.__dict__['_matrix_cache'] = value
 
     def _signed(self):
         """Parameter tensors with `inv_mode` applied (gate.py:395-400)."""
@@ -214,7 +226,7 @@ class U3Gate(ParametricSingleGate):
         self._set('theta', theta)
         self._set('phi', phi)
         self._set('lambd', lambd)
-        self.update_matrix()
+        self._matrix_cache = None
 
     def _signed(self):
         if self.inv_mode:  # gate.py:606-609

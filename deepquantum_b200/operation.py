@@ -99,6 +99,7 @@ class Lowering:
         self.sources = []      # gate object per record (None for X records)
         self._const_index = {}
         self._const_cache = {}
+        self._idx_cache = {}
 
     def add(self, gate: 'Gate', kind: int, wires, controls, adjoint: bool = False, matrix_of: 'Gate | None' = None):
         n = self.nqubit
@@ -151,6 +152,29 @@ class Lowering:
         self.total = max(total, 1)
         return structs
 
+    def _gather_from_data(self, cls, lst):
+        """All parameters of a gate class as ONE gather from the encoded data vector, when every gate of the class
+        took its parameters from the same `data` tensor in the last `encode` (and is not inverted / batched)."""
+        ref = getattr(lst[0], '_data_ref', None)
+        if ref is None:
+            return None
+        data = ref[0]
+        idx = []
+        for g in lst:
+            r = getattr(g, '_data_ref', None)
+            if r is None or r[0] is not data or g._batched is not None or getattr(g, 'inv_mode', False):
+                return None
+            if len(g._pnames) != len(r[1]) or any(getattr(g, nm).data_ptr() != data[i].data_ptr()
+                                                  for nm, i in zip(g._pnames[:1], r[1][:1])):
+                return None
+            idx.extend(r[1])
+        key = (cls, tuple(idx), str(data.device))
+        cached = self._idx_cache.get(cls)
+        if cached is None or cached[0] != key[1] or cached[1].device != data.device:
+            cached = (key[1], torch.tensor(idx, dtype=torch.int64, device=data.device))
+            self._idx_cache[cls] = cached
+        return data.index_select(0, cached[1])
+
     def structure_key(self):
         return tuple(r[:4] + (r[6], r[7]) for r in self.records)
 
@@ -169,8 +193,10 @@ class Lowering:
                                                                                              dtype=cdtype))
         batched = False
         for cls, lst in self.groups.items():
-            plist = [t for g in lst for t in g._param_list()]
-            p = torch.stack(plist)                       # [N*npara] or [N*npara, batch]
+            p = self._gather_from_data(cls, lst)
+            if p is None:
+                plist = [t for g in lst for t in g._param_list()]
+                p = torch.stack(plist)                   # [N*npara] or [N*npara, batch]
             if p.ndim == 2:
                 batched = True
                 p = p.transpose(0, 1).reshape(p.shape[1], len(lst), -1)

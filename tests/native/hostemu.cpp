@@ -30,6 +30,8 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
       const uint64_t cta_base = tile_base(P, t);
       // poison the tile so that a read of an unwritten slot is caught
       std::memset(tile.data(), 0xff, tile.size() * sizeof(chunk));
+      std::vector<RoundTab> tabs(B200Q_MAX_ROUNDS);
+      for (int tid = 0; tid < nthreads; ++tid) fill_round_tabs<Real>(P, tid, nthreads, tabs.data());
       if (P.pool_elems)
         for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m, false);
       for (int r = 0; r < P.n_rounds; ++r) {
@@ -40,7 +42,7 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
               run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile.data(), pool.data());
         } else {
           for (int tid = 0; tid < nthreads; ++tid)
-            run_round<Real>(P, Rd, tid, cta_base, tile.data(), pool.data(), gstate, chunks_per_state);
+            run_round<Real>(P, Rd, tabs[r], tid, cta_base, tile.data(), pool.data(), gstate, chunks_per_state);
         }
       }
     }
@@ -77,6 +79,8 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
     std::memset(tp.data(), 0xff, tp.size() * sizeof(chunk));
     std::memset(tl.data(), 0xff, tl.size() * sizeof(chunk));
     std::fill(acc.begin(), acc.end(), 0.0);
+    std::vector<RoundTab> tabs(B200Q_MAX_ROUNDS);
+    for (int tid = 0; tid < nthreads; ++tid) fill_round_tabs<Real>(P, tid, nthreads, tabs.data());
     if (P.pool_elems)
       for (int tid = 0; tid < nthreads; ++tid) fill_pool<Real>(P, tid, nthreads, pool.data(), m, true);
     for (int r = int(P.n_rounds) - 1; r >= 0; --r) {
@@ -88,7 +92,7 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
                                         (want >> o) & 1ull, acc.data() + o * B200Q_ACC_PER_OP);
       } else {
         for (int tid = 0; tid < nthreads; ++tid)
-          run_round_adjoint<Real>(P, Rd, tid, cta_base, tp.data(), tl.data(), pool.data(), gpsi, glam,
+          run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tp.data(), tl.data(), pool.data(), gpsi, glam,
                                   chunks_per_state, want, acc.data());
       }
     }

@@ -65,17 +65,23 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
   const int D = g.D, G = g.G, GP = G + 1;
   cxq<Real>* xs = reinterpret_cast<cxq<Real>*>(smem_raw);   // [D][GP]
   cxq<Real>* ys = xs + size_t(D) * GP;                       // [D][GP]
+  long long* gbase = reinterpret_cast<long long*>(ys + size_t(D) * GP);   // [G]  flat offset of each group
+  long long* toff = gbase + G;                                            // [D]  flat offset of each digit combo
   cxq<Real>* st = state + (long long)blockIdx.y * g.state_size;
   const long long r0 = (long long)blockIdx.x * G;
   const int width = hdr->width;
   const int total = G * D;
+  // the 64-bit divisions of the index expansion are done once per group / digit combo, not per element
+  for (int i = threadIdx.x; i < G; i += kThreads) gbase[i] = (r0 + i < g.n_rest) ? expand_rest(g, r0 + i) : -1;
+  for (int t = threadIdx.x; t < D; t += kThreads) toff[t] = qudit_offset(g, 0, t) - expand_rest(g, 0);
+  __syncthreads();
   // ---- load: element e -> (group gi, matrix digit combo t) ordered for coalescing --------------------
   for (int e = threadIdx.x; e < total; e += kThreads) {
     int gi, t;
     qudit_elem(g, e, &gi, &t);
-    const long long rest = r0 + gi;
     cxq<Real> v; v.x = v.y = Real(0);
-    if (rest < g.n_rest) v = st[qudit_offset(g, rest, t)];
+    const long long b = gbase[gi];
+    if (b >= 0) v = st[b + toff[t]];
     xs[t * GP + gi] = v;
   }
   __syncthreads();
@@ -99,8 +105,8 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
   for (int e = threadIdx.x; e < total; e += kThreads) {
     int gi, t;
     qudit_elem(g, e, &gi, &t);
-    const long long rest = r0 + gi;
-    if (rest < g.n_rest) st[qudit_offset(g, rest, t)] = ys[t * GP + gi];
+    const long long b = gbase[gi];
+    if (b >= 0) st[b + toff[t]] = ys[t * GP + gi];
   }
 }
 
@@ -130,10 +136,14 @@ int run_qudit(void* state, const QuditGeom& g, const void* matrix, int64_t batch
   int rc = get_workspace(dev, &w);
   if (rc) return rc;
   build_ell_kernel<Real><<<1, kMaxD, 0, s>>>((const cxq<Real>*)matrix, g.D, (cxq<Real>*)w->vals, w->cols, w->hdr);
-  const size_t smem = size_t(2) * g.D * (g.G + 1) * sizeof(cxq<Real>);
+  const size_t smem = size_t(2) * g.D * (g.G + 1) * sizeof(cxq<Real>) + size_t(g.G + g.D) * sizeof(long long);
   auto kern = qudit_apply_kernel<Real>;
-  rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
-  if (rc) return rc;
+  static size_t smem_set[64] = {0};
+  if (smem > smem_set[dev]) {
+    rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+    if (rc) return rc;
+    smem_set[dev] = smem;
+  }
   const long long nblocks = (g.n_rest + g.G - 1) / g.G;
   if (nblocks > 0x7fffffffLL) return set_err(B200Q_EUNSUPPORTED, "state too large for one launch");
   dim3 grid((unsigned)nblocks, (unsigned)batch);

@@ -554,10 +554,8 @@ template <typename Real> struct RoundAddr {
   uint32_t lb;       // tile-local amplitude index of the item (register bits zero)
   uint64_t gbase;    // chunk index in global memory
   uint32_t sbase;    // swizzled chunk index in the tile
-  uint64_t gst[4];   // global chunk stride of each chunk-level slot
-  uint32_t sst[4];   // swizzled tile stride of each chunk-level slot
   bool active;
-};
+};   // the slot strides stay in the shared-memory RoundTab: keeping them in registers across the op loop spilled
 
 // Per-round address tables, built once per CTA in shared memory (the per-thread bit-deposit loops they replace
 // were 13 % of all executed instructions): the item index tid is split into its low 4 and high 5 bits, each
@@ -611,65 +609,72 @@ B200Q_HD RoundAddr<Real> round_addr(const b200q_pass_t& P, const RoundTab& T, in
   const uint32_t lb = T.lb_lo[lo] | T.lb_hi[hi];
   const uint64_t pb = cta_base | T.pb_lo[lo] | T.pb_hi[hi];
   A.lb = lb;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) { A.gst[s] = T.gst[s]; A.sst[s] = T.sst[s]; }
   A.gbase = pb >> VS;
   A.sbase = swz(lb >> VS);
   return A;
 }
 
-template <typename Real>
-B200Q_HD uint64_t gidx(const RoundAddr<Real>& A, int c) {
-  return A.gbase ^ ((c & 1) ? A.gst[0] : 0) ^ ((c & 2) ? A.gst[1] : 0) ^ ((c & 4) ? A.gst[2] : 0) ^
-         ((c & 8) ? A.gst[3] : 0);
+B200Q_HD uint64_t gidx(uint64_t gbase, const uint64_t* gst, int c) {
+  return gbase ^ ((c & 1) ? gst[0] : 0) ^ ((c & 2) ? gst[1] : 0) ^ ((c & 4) ? gst[2] : 0) ^ ((c & 8) ? gst[3] : 0);
 }
-template <typename Real>
-B200Q_HD uint32_t sidx(const RoundAddr<Real>& A, int c) {
-  return A.sbase ^ ((c & 1) ? A.sst[0] : 0) ^ ((c & 2) ? A.sst[1] : 0) ^ ((c & 4) ? A.sst[2] : 0) ^
-         ((c & 8) ? A.sst[3] : 0);
+B200Q_HD uint32_t sidx(uint32_t sbase, const uint32_t* sst, int c) {
+  return sbase ^ ((c & 1) ? sst[0] : 0) ^ ((c & 2) ? sst[1] : 0) ^ ((c & 4) ? sst[2] : 0) ^ ((c & 8) ? sst[3] : 0);
 }
 
 // Fold the X relabelling mask into the base addresses: register element c is written to logical c ^ xm.
 template <typename Real>
-B200Q_HD void relabel(RoundAddr<Real>& A, uint32_t xm) {
+B200Q_HD void relabel(RoundAddr<Real>& A, const RoundTab& T, uint32_t xm) {
 #pragma unroll
   for (int s = 0; s < 4; ++s)
-    if ((xm >> s) & 1u) { A.gbase ^= A.gst[s]; A.sbase ^= A.sst[s]; }
+    if ((xm >> s) & 1u) { A.gbase ^= T.gst[s]; A.sbase ^= T.sst[s]; }
 }
 
 template <typename Real>
-B200Q_HD void gather(const RoundAddr<Real>& A, bool from_global, bool soa_global,
+B200Q_HD void gather(const RoundAddr<Real>& A, const RoundTab& T, bool from_global, bool soa_global,
                      const typename Traits<Real>::chunk* tile, const typename Traits<Real>::chunk* gstate,
                      uint64_t total_chunks, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
   using chunk = typename Traits<Real>::chunk;
   if (from_global) {
+    uint64_t gst[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) gst[s] = T.gst[s];
 #pragma unroll
     for (int c = 0; c < NE; ++c) {
-      const uint64_t idx = gidx(A, c);
+      const uint64_t idx = gidx(A.gbase, gst, c);
       chunk v = zero_chunk((chunk*)nullptr);
       if (idx < total_chunks) v = gstate[idx];
       unpack(v, re[c], im[c], soa_global);
     }
   } else {
+    uint32_t sst[4];
 #pragma unroll
-    for (int c = 0; c < NE; ++c) unpack(tile[sidx(A, c)], re[c], im[c], true);
+    for (int s = 0; s < 4; ++s) sst[s] = T.sst[s];
+#pragma unroll
+    for (int c = 0; c < NE; ++c) unpack(tile[sidx(A.sbase, sst, c)], re[c], im[c], true);
   }
 }
 
 template <typename Real>
-B200Q_HD void scatter(const RoundAddr<Real>& A, bool to_global, bool soa_global, typename Traits<Real>::chunk* tile,
+B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_global, bool soa_global,
+                      typename Traits<Real>::chunk* tile,
                       typename Traits<Real>::chunk* gstate, uint64_t total_chunks,
                       const typename Traits<Real>::V* re, const typename Traits<Real>::V* im) {
   using chunk = typename Traits<Real>::chunk;
   if (to_global) {
+    uint64_t gst[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) gst[s] = T.gst[s];
 #pragma unroll
     for (int c = 0; c < NE; ++c) {
-      const uint64_t idx = gidx(A, c);
+      const uint64_t idx = gidx(A.gbase, gst, c);
       if (idx < total_chunks) gstate[idx] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
     }
   } else {
+    uint32_t sst[4];
 #pragma unroll
-    for (int c = 0; c < NE; ++c) tile[sidx(A, c)] = pack(re[c], im[c], true, (chunk*)nullptr);
+    for (int s = 0; s < 4; ++s) sst[s] = T.sst[s];
+#pragma unroll
+    for (int c = 0; c < NE; ++c) tile[sidx(A.sbase, sst, c)] = pack(re[c], im[c], true, (chunk*)nullptr);
   }
 }
 
@@ -692,7 +697,7 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   if (!A.active) return;
   V re[NE], im[NE];
-  gather<Real>(A, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
+  gather<Real>(A, T, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
 
   Real rho_r = Real(1), rho_i = Real(0);
   bool rho_dirty = false;
@@ -731,8 +736,8 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
 #pragma unroll
     for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
-  relabel<Real>(A, xm);
-  scatter<Real>(A, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, re, im);
+  relabel<Real>(A, T, xm);
+  scatter<Real>(A, T, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, re, im);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -954,8 +959,8 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
   uint32_t xm = 0;
   const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;
   if (A.active) {
-    gather<Real>(A, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
-    gather<Real>(A, Rd.dst_global, soa_in, tile_lam, glam, total_chunks, lr, li);
+    gather<Real>(A, T, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
+    gather<Real>(A, T, Rd.dst_global, soa_in, tile_lam, glam, total_chunks, lr, li);
   } else {
 #pragma unroll
     for (int c = 0; c < NE; ++c) {
@@ -997,9 +1002,9 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
     }
   }
   if (!A.active) return;
-  relabel<Real>(A, xm);
-  scatter<Real>(A, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, pr, pi);
-  scatter<Real>(A, Rd.src_global, soa_out, tile_lam, glam, total_chunks, lr, li);
+  relabel<Real>(A, T, xm);
+  scatter<Real>(A, T, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, pr, pi);
+  scatter<Real>(A, T, Rd.src_global, soa_out, tile_lam, glam, total_chunks, lr, li);
 }
 
 // Dense k-target op of the reverse sweep, in place in both shared-memory tiles.  Gradient

@@ -14,6 +14,8 @@ GATE_MAT, GATE_DIAG, GATE_X = 0, 1, 2
 GATE_ADJOINT = 1
 GATE_REAL = 2
 GATE_RXLIKE = 4
+GATE_HADAMARD = 8
+GATE_ROTATION = 16
 MAX_TARGETS = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libb200q.so')

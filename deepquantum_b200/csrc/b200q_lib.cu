@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,37 +40,74 @@ template <int CB> struct TileCfg {
   static constexpr int kMinBlocks = CB >= 13 ? 1 : (CB == 12 ? 2 : 4);
 };
 
-template <typename Real, int CB>
+// Shared memory: tile | cx pool (DIAG / MATK / slow MAT1 matrices) | MAT1 coefficient records | round tables.
+template <typename Real, int CB> struct TileSmem {
+  static constexpr size_t kTile = size_t(16) << CB;
+  static constexpr size_t kPool = size_t(B200Q_POOL_MAX) * sizeof(cx<Real>);
+  static constexpr size_t kCoef = size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP * sizeof(Real);
+  static constexpr size_t kTabs = sizeof(RoundTab) * B200Q_MAX_ROUNDS;
+  static constexpr size_t kWords = sizeof(OpWord) * (B200Q_MAX_OPS + 1);
+  static constexpr size_t kTotal = kTile + kPool + kCoef + kTabs + kWords;
+};
+
+// Persistent CTAs: the prologue (matrix staging, coefficient records, round address tables) runs once per
+// CTA; the CTA then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A work item is (tile, state of the
+// batch); with per-state matrices (mat_batch_stride != 0) the batch is on blockIdx.y instead.
+template <typename Real, int CB, bool LEAN>
 __global__ void __launch_bounds__(TileCfg<CB>::kThreads, TileCfg<CB>::kMinBlocks)
 b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ state,
-                  const cx<Real>* __restrict__ mats, uint64_t chunks_per_state, int64_t mat_batch_stride) {
+                  const cx<Real>* __restrict__ mats, uint64_t chunks_per_state, int64_t mat_batch_stride,
+                  uint32_t tile_shift, uint64_t n_work) {
   using chunk = typename Traits<Real>::chunk;
+  using SM = TileSmem<Real, CB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chunk* tile = reinterpret_cast<chunk*>(smem_raw);
-  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(16) << CB));
-  RoundTab* tabs = reinterpret_cast<RoundTab*>(smem_raw + (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>));
+  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + SM::kTile);
+  Real* coef = reinterpret_cast<Real*>(smem_raw + SM::kTile + SM::kPool);
+  RoundTab* tabs = reinterpret_cast<RoundTab*>(smem_raw + SM::kTile + SM::kPool + SM::kCoef);
+  OpWord* words = reinterpret_cast<OpWord*>(smem_raw + SM::kTile + SM::kPool + SM::kCoef + SM::kTabs);
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
-  const uint64_t cta_base = tile_base(P, blockIdx.x);
-  chunk* gstate = state + uint64_t(blockIdx.y) * chunks_per_state;
   const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
 
   fill_round_tabs<Real>(P, tid, nthreads, tabs);
   if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, m, false);
+  fill_coefs<Real>(P, tid, nthreads, coef, m);
+  fill_opwords(P, tid, nthreads, words);
+  const Real gscale = P.has_scale ? Real(pass_scale<Real>(P, m)) : Real(1);
   __syncthreads();
   const int nr = P.n_rounds;
-  for (int r = 0; r < nr; ++r) {
-    const b200q_round_t& Rd = P.rounds[r];
-    if (Rd.direct) {
-      for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
-        run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile, pool);
-        __syncthreads();
+  const uint64_t tile_mask = (1ull << tile_shift) - 1ull;
+  for (uint64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const uint64_t cta_base = tile_base(P, w & tile_mask);
+    const uint64_t enabled = tile_enabled(P, cta_base);
+    chunk* gstate = state + (uint64_t(blockIdx.y) + (w >> tile_shift)) * chunks_per_state;
+    for (int r = 0; r < nr; ++r) {
+      const b200q_round_t& Rd = P.rounds[r];
+      if (Rd.direct) {
+        for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
+          run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile, pool);
+          __syncthreads();
+        }
+      } else {
+        run_round<Real, LEAN>(P, Rd, tabs[r], tid, cta_base, enabled, tile, pool, coef, words, gscale, gstate,
+                              chunks_per_state);
+        if (r + 1 < nr) __syncthreads();
       }
-    } else {
-      run_round<Real>(P, Rd, tabs[r], tid, cta_base, tile, pool, gstate, chunks_per_state);
-      if (r + 1 < nr) __syncthreads();
     }
+    if (nr > 1) __syncthreads();   // the next tile's first round overwrites the shared-memory tile
   }
+}
+
+inline int sm_count(int dev) {
+  static int cache[64] = {0};
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev] = v;
+  }
+  return cache[dev];
 }
 
 template <typename Real, int CB>
@@ -77,26 +115,42 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
                 int64_t mat_batch_stride, cudaStream_t stream) {
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
-  const size_t smem = (size_t(16) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>) + sizeof(RoundTab) * B200Q_MAX_ROUNDS;
-  auto kern = b200q_tile_kernel<Real, CB>;
+  const size_t smem = TileSmem<Real, CB>::kTotal;
+  auto kern = P.lean ? b200q_tile_kernel<Real, CB, true> : b200q_tile_kernel<Real, CB, false>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    int rc = cuda_err(cudaFuncSetAttribute(b200q_tile_kernel<Real, CB, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute");
+    if (!rc)
+      rc = cuda_err(cudaFuncSetAttribute(b200q_tile_kernel<Real, CB, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "cudaFuncSetAttribute");
     if (rc) return rc;
     attr_set[dev] = true;
   }
   const uint64_t chunks_per_state = (1ull << n_qubits) >> VS;
-  const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
-  if (ntiles > 0x7fffffffull) return set_err(B200Q_EUNSUPPORTED, "too many tiles for one launch");
-  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
-    const int64_t nb = std::min<int64_t>(32768, batch - b0);
-    dim3 grid((unsigned)ntiles, (unsigned)nb, 1);
-    kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(
-        P, reinterpret_cast<chunk*>(state) + uint64_t(b0) * chunks_per_state,
-        reinterpret_cast<const cx<Real>*>(mats) + b0 * mat_batch_stride, chunks_per_state, mat_batch_stride);
+  const int tile_shift = int(P.n_bits) - int(P.tile_bits);
+  const uint64_t ntiles = 1ull << tile_shift;
+  const uint64_t resident = uint64_t(sm_count(dev)) * TileCfg<CB>::kMinBlocks;
+  if (mat_batch_stride == 0) {
+    const uint64_t n_work = ntiles * uint64_t(batch);
+    dim3 grid((unsigned)std::min<uint64_t>(n_work, resident), 1, 1);
+    kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(P, reinterpret_cast<chunk*>(state),
+                                                        reinterpret_cast<const cx<Real>*>(mats), chunks_per_state, 0,
+                                                        (uint32_t)tile_shift, n_work);
+  } else {
+    const uint64_t gx = std::min<uint64_t>(ntiles, std::max<uint64_t>(1, resident / uint64_t(std::min<int64_t>(batch, (int64_t)resident))));
+    for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+      const int64_t nb = std::min<int64_t>(32768, batch - b0);
+      dim3 grid((unsigned)gx, (unsigned)nb, 1);
+      kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(
+          P, reinterpret_cast<chunk*>(state) + uint64_t(b0) * chunks_per_state,
+          reinterpret_cast<const cx<Real>*>(mats) + b0 * mat_batch_stride, chunks_per_state, mat_batch_stride,
+          (uint32_t)tile_shift, ntiles);
+    }
   }
   return cuda_err(cudaGetLastError(), "tile kernel launch");
 }
@@ -368,6 +422,7 @@ int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_
     if (options->low_bits) opt.low_bits = options->low_bits;
     if (options->max_rounds) opt.max_rounds = options->max_rounds;
     opt.fuse = options->fuse;
+    if (options->reserved[0]) opt.structured = 0;   // A/B switch: general op codes only
   }
   if (opt.chunk_bits < 11 || opt.chunk_bits > 13) return set_err(B200Q_EINVAL, "chunk_bits must be 11, 12 or 13");
   std::string err;
@@ -394,7 +449,7 @@ int b200q_plan_get_stats(const b200q_plan_t* plan, b200q_plan_stats_t* s) {
   s->tile_bits = std::min(p.opt.chunk_bits + (p.dtype == B200Q_C64 ? 1 : 0), p.n_bits);
   s->threads_per_cta = 1 << (p.opt.chunk_bits - B200Q_REG_CHUNK_BITS);
   s->smem_bytes = (16 << p.opt.chunk_bits) + B200Q_POOL_MAX * (p.dtype == B200Q_C64 ? 8 : 16) +
-                  (int)sizeof(RoundTab) * B200Q_MAX_ROUNDS;
+                  B200Q_MAX_OPS * B200Q_COEF_PER_OP * (p.dtype == B200Q_C64 ? 4 : 8) + 16 * (B200Q_MAX_OPS + 1) + (int)sizeof(RoundTab) * B200Q_MAX_ROUNDS;
   return 0;
 }
 

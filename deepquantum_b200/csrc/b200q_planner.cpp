@@ -273,12 +273,14 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
       Rd.op_begin = (uint16_t)n_ops;
       for (int gi : list) {
         const IGate& a = B.g[gi];
-        b200q_op_t& op = P.ops[n_ops++];
+        b200q_op_t op;
         std::memset(&op, 0, sizeof(op));
         op.kind = (uint8_t)a.op_kind;
         op.flags = (uint8_t)(((a.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0) |
                              ((a.flags & B200Q_GATE_REAL) ? B200Q_FLAG_REAL : 0) |
-                             ((a.flags & B200Q_GATE_RXLIKE) ? B200Q_FLAG_RXLIKE : 0));
+                             ((a.flags & B200Q_GATE_RXLIKE) ? B200Q_FLAG_RXLIKE : 0) |
+                             ((a.flags & B200Q_GATE_HADAMARD) ? B200Q_FLAG_HAD : 0) |
+                             ((a.flags & B200Q_GATE_ROTATION) ? B200Q_FLAG_ROT : 0));
         op.mat_src = (uint32_t)a.mat;
         op.gate_id = (uint32_t)gi;
         op.k = (uint8_t)a.k;
@@ -299,6 +301,39 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
             else op.dsel_glob[j] = 1ull << b;
           }
         }
+        // complex64: an op that touches the lane slot (index bit 0: the two amplitudes of a 16-byte chunk) is
+        // wrapped in two LSWAP ops that exchange the lane with a chunk-level slot the op does not use, so that
+        // it runs through the ordinary chunk-slot code (the scalar lane paths were 3x more expensive).
+        int lswap = -1;
+        if (B.vs && B.opt.structured) {
+          uint32_t used = op.ctrl_reg;   // amplitude-level slot mask
+          if (a.op_kind == B200Q_OP_MAT1 || a.op_kind == B200Q_OP_X) used |= 1u << op.slot;
+          for (int j = 0; j < 2; ++j)
+            if (op.dsel_slot[j] != 0xff) used |= 1u << op.dsel_slot[j];
+          if (used & 1u) {
+            for (int cs = B.rc - 1; cs >= 0 && lswap < 0; --cs)
+              if (!((used >> (cs + 1)) & 1u)) lswap = cs;
+          }
+          if (lswap >= 0) {
+            const int as = lswap + 1;   // amplitude-level slot index of the partner chunk slot
+            if (op.ctrl_reg & 1u) op.ctrl_reg = (op.ctrl_reg & ~1u) | (1u << as);
+            if ((a.op_kind == B200Q_OP_MAT1 || a.op_kind == B200Q_OP_X) && op.slot == 0) op.slot = (uint8_t)as;
+            for (int j = 0; j < 2; ++j)
+              if (op.dsel_slot[j] == 0) op.dsel_slot[j] = (uint8_t)as;
+          }
+        }
+        const int need = lswap >= 0 ? 3 : 1;
+        if (n_ops + need > B200Q_MAX_OPS) break;   // the rest of the list stays pending
+        auto push_lswap = [&]() {
+          b200q_op_t& w = P.ops[n_ops++];
+          std::memset(&w, 0, sizeof(w));
+          w.kind = B200Q_OP_LSWAP;
+          w.slot = (uint8_t)(lswap + 1);
+          w.code = (uint8_t)(B200Q_CODE_LSWAP + lswap);
+          w.dsel_slot[0] = w.dsel_slot[1] = 0xff;
+          w.gate_id = (uint32_t)gi;
+        };
+        if (lswap >= 0) push_lswap();
         if (a.pool) {
           op.pool_off = (uint16_t)pool;
           op.pool_n = (uint16_t)a.pool;
@@ -307,14 +342,42 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         // pre-decoded dispatch code
         op.tctrl = (op.ctrl_loc != 0 || op.ctrl_glob != 0) ? 1 : 0;
         const bool lane_slot = B.vs && op.slot == 0;
+        const bool lane_ctrl = B.vs && (op.ctrl_reg & 1u);
+        const int nsel = (op.dsel_slot[0] != 0xff) + (op.dsel_slot[1] != 0xff);
         if (a.op_kind == B200Q_OP_MAT1) {
           if (op.ctrl_reg == 0 && !lane_slot) {
             const int var = (op.flags & B200Q_FLAG_REAL) ? 0 : ((op.flags & B200Q_FLAG_RXLIKE) ? 1 : 2);
             op.code = (uint8_t)(B200Q_CODE_MAT1_FAST + 4 * var + (op.slot - B.vs));
+            if ((op.flags & B200Q_FLAG_HAD) && !op.tctrl && B.opt.structured) {
+              op.code = (uint8_t)(B200Q_CODE_MAT1_HAD + (op.slot - B.vs));
+              P.has_scale = 1;
+            } else if ((op.flags & B200Q_FLAG_ROT) && var < 2 && B.opt.structured) {
+              op.code = (uint8_t)((var == 1 ? B200Q_CODE_MAT1_ROTX : B200Q_CODE_MAT1_ROTY) + (op.slot - B.vs));
+              if (!op.tctrl) P.has_scale = 1;
+            }
           } else op.code = B200Q_CODE_MAT1_SLOW;
         } else if (a.op_kind == B200Q_OP_X) {
-          op.code = (op.ctrl_reg == 0 && !lane_slot) ? B200Q_CODE_X_RELABEL : B200Q_CODE_X_SLOW;
-        } else op.code = B200Q_CODE_DIAG;
+          const uint32_t cm = op.ctrl_reg >> B.vs;
+          if (op.ctrl_reg == 0 && !lane_slot) { op.code = B200Q_CODE_X_RELABEL; op.arg = (uint8_t)(op.slot - B.vs); }
+          else if (!lane_slot && !lane_ctrl && cm != 0 && (cm & (cm - 1)) == 0 && B.opt.structured) {
+            op.code = B200Q_CODE_X_C1;
+            op.arg = (uint8_t)(4 * (op.slot - B.vs) + __builtin_ctz(cm));
+          } else op.code = B200Q_CODE_X_SLOW;
+        } else {
+          op.code = B200Q_CODE_DIAG;
+          const bool lane_sel = B.vs && (op.dsel_slot[0] == 0 || op.dsel_slot[1] == 0);
+          if (B.opt.structured && op.ctrl_reg == 0 && !lane_sel) {
+            if (nsel == 0) op.code = B200Q_CODE_DIAG_T;
+            else if (nsel == 1) {
+              const int j = op.dsel_slot[0] != 0xff ? 0 : 1;
+              op.code = (uint8_t)(B200Q_CODE_DIAG_R + (op.dsel_slot[j] - B.vs));
+              op.arg = (uint8_t)j;
+            }
+          }
+        }
+        P.ops[n_ops++] = op;
+        if (op.ctrl_glob) P.gctrl_ops[P.n_gctrl++] = (uint8_t)(n_ops - 1);
+        if (lswap >= 0) push_lswap();
         B.done[gi] = 1;
         ++gates_in_pass;
       }
@@ -345,6 +408,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     while (true) {
       if (n_rounds >= B.opt.max_rounds - 1) break;
       if (gates_in_pass >= op_cap) break;
+      if (n_ops + 3 > B200Q_MAX_OPS) break;
       if (first) {
         choose_round(true, &R, &list);
         if (list.empty()) {
@@ -419,6 +483,9 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
       if (!P.rounds[r].direct && !P.rounds[r].src_global && !P.rounds[r].dst_global) reorder_for_banks(&P.rounds[r]);
     P.n_rounds = (uint8_t)n_rounds;
     P.n_ops = (uint8_t)n_ops;
+    P.lean = 1;
+    for (int o = 0; o < n_ops; ++o)
+      if (P.ops[o].code >= B200Q_CODE_LEAN_END) P.lean = 0;
     P.pool_elems = (uint16_t)pool;
     plan->passes.push_back(P);
     plan->pass_gate_count.push_back(gates_in_pass);

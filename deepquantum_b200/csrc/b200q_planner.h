@@ -15,6 +15,7 @@ struct PlanOptions {
   int low_bits = -1;      // contiguous low amplitude bits forced into every tile (-1: default per dtype)
   int max_rounds = B200Q_MAX_ROUNDS;
   int max_ops = B200Q_MAX_OPS;
+  int structured = 1;     // Hadamard / rotation hints select the in-place add-sub and three-shear butterflies
   int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
 };
 

@@ -24,7 +24,7 @@
 #define B200Q_REG_CHUNK_BITS 4  /* 16 chunks of 16 B per thread */
 #define B200Q_MAX_TILE_BITS 14  /* amplitude bits per tile (complex64, 13 chunk bits) */
 #define B200Q_MAX_ROUNDS 8
-#define B200Q_MAX_OPS 44
+#define B200Q_MAX_OPS 48
 #define B200Q_POOL_MAX 512      /* complex elements of gate matrices staged in shared memory */
 #define B200Q_MAX_QUBITS 40
 #define B200Q_MATK_MAX 4        /* dense k-target ops applied inside a tile */
@@ -33,20 +33,35 @@ enum {
   B200Q_OP_MAT1 = 0,  // dense 2x2 on a register slot (+controls)
   B200Q_OP_X = 1,     // amplitude swap on a register slot (+controls): X, CNOT, Toffoli, ...
   B200Q_OP_DIAG = 2,  // diagonal over <= 2 selector bits anywhere in the index (+controls)
-  B200Q_OP_MATK = 3   // dense 2^k x 2^k, k = 2..4, on arbitrary tile bits, applied from shared memory
+  B200Q_OP_MATK = 3,  // dense 2^k x 2^k, k = 2..4, on arbitrary tile bits, applied from shared memory
+  B200Q_OP_LSWAP = 4  // complex64: exchange the lane bit (index bit 0) with register slot `slot` (planner-made)
 };
 
-/* pre-decoded dispatch codes: 4*variant + chunk slot for un-controlled dense 2x2 ops on a chunk-level slot */
-#define B200Q_CODE_MAT1_FAST 0   /* 0..11: variant (0 real, 1 rx-like, 2 general) * 4 + chunk slot */
-#define B200Q_CODE_MAT1_SLOW 12  /* register-slot controls or the lane slot */
-#define B200Q_CODE_X_RELABEL 13  /* chunk-level slot, no register-slot control: toggles the relabelling mask */
-#define B200Q_CODE_X_SLOW 14
-#define B200Q_CODE_DIAG 15
-#define B200Q_CODE_NONE 16
+/* Pre-decoded dispatch codes, filled by the planner.
+ * LEAN codes (< B200Q_CODE_LEAN_END) are temp-free in-place register updates; a pass made only of them runs in
+ * the lean instantiation of the tile kernel (no spills, small instruction footprint).  The other codes are the
+ * general fallbacks (dense 2x2 with temporaries, register-slot-controlled ops, two-register-selector diagonals). */
+#define B200Q_CODE_MAT1_HAD 0    /*  0..3 : un-controlled x*[[1,1],[1,-1]] on chunk slot 0..3 (scalar deferred)      */
+#define B200Q_CODE_MAT1_ROTX 4   /*  4..7 : [[c, i q], [i q, c]], c^2 + q^2 = 1 (Rx) as three in-place shears         */
+#define B200Q_CODE_MAT1_ROTY 8   /*  8..11: [[c, -y], [y, c]],   c^2 + y^2 = 1 (Ry) as three in-place shears         */
+#define B200Q_CODE_DIAG_R 12     /* 12..15: diagonal with ONE selector on chunk slot 0..3 (other selector, if any,
+                                            thread-level): unit-modulus phases as three in-place shears            */
+#define B200Q_CODE_LSWAP 16      /* 16..19: exchange the complex64 lane bit with chunk slot 0..3 (in registers)    */
+#define B200Q_CODE_X_RELABEL 20  /* chunk-level slot, no register-slot control: toggles the relabelling mask       */
+#define B200Q_CODE_X_C1 21       /* chunk-level target, exactly one chunk-level control (arg = 4*target + control) */
+#define B200Q_CODE_DIAG_T 22     /* diagonal with thread-level / global selectors only: folds into the phase rho   */
+#define B200Q_CODE_NONE 23
+#define B200Q_CODE_LEAN_END 24
+#define B200Q_CODE_MAT1_FAST 24  /* 24..35: variant (0 real, 1 rx-like, 2 general) * 4 + chunk slot, temporaries    */
+#define B200Q_CODE_MAT1_SLOW 36  /* register-slot controls or the lane slot */
+#define B200Q_CODE_X_SLOW 37
+#define B200Q_CODE_DIAG 38       /* any diagonal (generic path) */
 
 #define B200Q_FLAG_ADJOINT 1u  /* use the conjugate transpose of the stored matrix */
 #define B200Q_FLAG_REAL 2u     /* MAT1: every entry is real (H, Ry, ...)                      */
 #define B200Q_FLAG_RXLIKE 4u   /* MAT1: diagonal real, off-diagonal purely imaginary (Rx)    */
+#define B200Q_FLAG_HAD 8u      /* MAT1: x * [[1, 1], [1, -1]] with x real (Hadamard)          */
+#define B200Q_FLAG_ROT 16u     /* MAT1: unit-determinant rotation (with RXLIKE: Rx, with REAL: Ry) */
 
 #define B200Q_LAYOUT_SRC_SOA 1u /* pass reads complex64 chunks as (re0,re1,im0,im1) */
 #define B200Q_LAYOUT_DST_SOA 2u /* pass writes them so */
@@ -68,6 +83,8 @@ typedef struct {
   uint8_t dsel_slot[2]; // DIAG selector j: register slot index, or 0xff if not a register slot
   uint8_t code;      // pre-decoded dispatch code (B200Q_CODE_*), filled by the planner
   uint8_t tctrl;     // 1 if the op has thread-level or global controls (ctrl_loc / ctrl_glob non-zero)
+  uint8_t arg;       // code-specific: X_C1 4*target + control chunk slots; DIAG_R index j of the register selector
+  uint8_t pad[3];
   uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
 } b200q_op_t;
 
@@ -89,6 +106,10 @@ typedef struct {
   uint16_t pool_elems;
   uint8_t n_nontile;
   uint8_t layout;     // B200Q_LAYOUT_* (complex64 only)
+  uint8_t lean;       // every op has a LEAN code: run the lean kernel instantiation
+  uint8_t has_scale;  // the pass has ops with a deferred common scalar (pass_scale), applied by the last round
+  uint8_t n_gctrl;    // ops with controls outside the tile (evaluated once per tile, see tile_enabled)
+  uint8_t gctrl_ops[B200Q_MAX_OPS];
   uint8_t tile_phys[B200Q_MAX_TILE_BITS];   // physical bit of tile-local bit j (ascending)
   uint8_t nontile_phys[B200Q_MAX_QUBITS];   // physical bits enumerated by the tile (CTA) index
   b200q_round_t rounds[B200Q_MAX_ROUNDS];

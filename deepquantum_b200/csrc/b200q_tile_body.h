@@ -687,11 +687,361 @@ B200Q_HD uint32_t diag_tsel(const b200q_op_t& op, uint64_t cta_base, uint32_t lb
 }
 
 // ------------------------------------------------------------------------------------------------
-// one register round of one thread
+// forward path: coefficient records, per-tile setup, one register round of one thread
 // ------------------------------------------------------------------------------------------------
+// Coefficient record of a MAT1 op in shared memory, built ONCE per CTA (fill_coefs): 2 flip states x 16
+// scalars, indexed by the op's position in the pass.  The op loop only issues one to three 128-bit
+// shared loads per op (packing 12 broadcast coefficients per op per thread, with flip-dependent indexing
+// and sign flips, was 25 % of all executed instructions).  Layouts (per flip state):
+//   dense    [r00 r01 r10 r11 | i01 n01 i10 n10 | i00 n00 i11 n11]      (n = negated imaginary part;
+//            REAL ops read the first quad, RXLIKE ops the first two, GENERAL ops all three)
+//   rotation [u, -u, v, -v | neg, ...]  three in-place shears  a += U b; b += V a; a += U b  with
+//            U = e01 / (1 + c), V = e10 (U = i u, V = i v for the Rx family; u, v real for the Ry family),
+//            after the matrix has been negated if c = e00 < 0 (`neg` = 1: the sign goes to the pass scalar
+//            or, for controlled ops, to the thread's phase rho).  No temporaries: the register allocator
+//            has nothing to shuffle back at the op-loop back edge.
+#define B200Q_COEF_PER_FLIP 16
+#define B200Q_COEF_PER_OP 32
+
+B200Q_HD bool code_is_rot(int code) { return code >= B200Q_CODE_MAT1_ROTX && code < B200Q_CODE_MAT1_ROTY + 4; }
+B200Q_HD bool code_is_had(int code) { return code >= B200Q_CODE_MAT1_HAD && code < B200Q_CODE_MAT1_HAD + 4; }
+
+// effective 2x2 entry (row-major idx) of a MAT1 op for flip state f, adjoint folded in
 template <typename Real>
+B200Q_HD cx<Real> mat1_entry(const b200q_op_t& op, const cx<Real>* mats, int idx, int f) {
+  if (f) idx ^= 3;   // X M X: entry (r, c) -> (r^1, c^1)
+  const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+  if (adj && (idx == 1 || idx == 2)) idx ^= 3;   // transpose
+  cx<Real> v = mats[op.mat_src + idx];
+  if (adj) v.y = -v.y;
+  return v;
+}
+
+// Shear form of a multiplication by the unit-modulus phase d: (x, y) <- (x + t y, ...) three times, after d has
+// been negated if Re d < 0.  mode: 0 identity, 1 shears, 2 shears + negate, 3 negate only, 4 not unit modulus
+// (general complex multiply from the raw value).
+template <typename Real>
+B200Q_HD void phase_shears(cx<Real> d, Real* out) {
+  const Real tol = sizeof(Real) == 4 ? Real(1e-6) : Real(1e-13);
+  const Real dev = d.x * d.x + d.y * d.y - Real(1);
+  Real t = Real(0), s = Real(0), mode;
+  if (dev > tol || dev < -tol) mode = Real(4);
+  else if (d.y == Real(0)) mode = d.x > Real(0) ? Real(0) : Real(3);
+  else {
+    const Real sg = d.x < Real(0) ? Real(-1) : Real(1);
+    const Real c = sg * d.x, si = sg * d.y;
+    t = -si / (Real(1) + c);
+    s = si;
+    mode = sg < Real(0) ? Real(2) : Real(1);
+  }
+  out[0] = t; out[1] = s; out[2] = mode; out[3] = Real(0);
+}
+
+template <typename Real>
+B200Q_HD void fill_coefs(const b200q_pass_t& P, int tid, int nthreads, Real* coef, const cx<Real>* mats) {
+  for (int e = tid; e < int(P.n_ops) * 2; e += nthreads) {
+    const int o = e >> 1, f = e & 1;
+    const b200q_op_t& op = P.ops[o];
+    Real* k = coef + o * B200Q_COEF_PER_OP + f * B200Q_COEF_PER_FLIP;
+    if (op.kind == B200Q_OP_DIAG) {
+      // [0..15]: shear entries (t, s, mode, 0) of the 4 diagonal values; [16..23]: the raw values
+      const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+      const int dim = 1 << int(op.k);
+      for (int i = 2 * f; i < 2 * f + 2; ++i) {
+        cx<Real> d;
+        d.x = Real(1); d.y = Real(0);
+        if (i < dim) { d = mats[op.mat_src + i * (dim + 1)]; if (adj) d.y = -d.y; }
+        phase_shears<Real>(d, coef + o * B200Q_COEF_PER_OP + 4 * i);
+        coef[o * B200Q_COEF_PER_OP + 16 + 2 * i] = d.x;
+        coef[o * B200Q_COEF_PER_OP + 17 + 2 * i] = d.y;
+      }
+      continue;
+    }
+    if (op.kind != B200Q_OP_MAT1) continue;
+    const cx<Real> m00 = mat1_entry(op, mats, 0, f), m01 = mat1_entry(op, mats, 1, f);
+    const cx<Real> m10 = mat1_entry(op, mats, 2, f), m11 = mat1_entry(op, mats, 3, f);
+    if (code_is_rot(op.code)) {
+      const bool isx = op.code < B200Q_CODE_MAT1_ROTY;
+      const Real sg = m00.x < Real(0) ? Real(-1) : Real(1);
+      const Real c = sg * m00.x;
+      const Real e01 = sg * (isx ? m01.y : m01.x), e10 = sg * (isx ? m10.y : m10.x);
+      const Real u = e01 / (Real(1) + c), v = e10;
+      k[0] = u; k[1] = -u; k[2] = v; k[3] = -v;
+      k[4] = sg < Real(0) ? Real(1) : Real(0);
+      for (int j = 5; j < B200Q_COEF_PER_FLIP; ++j) k[j] = Real(0);
+    } else {
+      k[0] = m00.x; k[1] = m01.x; k[2] = m10.x; k[3] = m11.x;
+      k[4] = m01.y; k[5] = -m01.y; k[6] = m10.y; k[7] = -m10.y;
+      k[8] = m00.y; k[9] = -m00.y; k[10] = m11.y; k[11] = -m11.y;
+      for (int j = 12; j < B200Q_COEF_PER_FLIP; ++j) k[j] = Real(0);
+    }
+  }
+}
+
+// Op words: the per-op fields the round loop needs, 16 bytes per op in shared memory (one 128-bit load,
+// prefetched one op ahead) instead of a handful of indexed constant-bank loads per op.
+struct alignas(16) OpWord {
+  uint32_t x;   // code | arg << 8 | flags << 16 | op index << 24
+  uint32_t y;   // thread-level control mask (tile-local bits)
+  uint32_t z;   // DIAG: tile-local selector masks, dsel_loc[0] | dsel_loc[1] << 16
+  uint32_t w;
+};
+#define B200Q_OW_CTRL_LOC 0x10000u
+#define B200Q_OW_CTRL_GLOB 0x20000u
+#define B200Q_OW_DSEL_GLOB0 0x40000u
+#define B200Q_OW_DSEL_GLOB1 0x80000u
+
+B200Q_HD void fill_opwords(const b200q_pass_t& P, int tid, int nthreads, OpWord* words) {
+  for (int o = tid; o <= int(P.n_ops); o += nthreads) {
+    OpWord w;
+    w.x = B200Q_CODE_NONE; w.y = 0; w.z = 0; w.w = 0;
+    if (o < int(P.n_ops)) {
+      const b200q_op_t& op = P.ops[o];
+      uint32_t fl = 0;
+      if (op.ctrl_loc) fl |= B200Q_OW_CTRL_LOC;
+      if (op.ctrl_glob) fl |= B200Q_OW_CTRL_GLOB;
+      if (op.dsel_glob[0]) fl |= B200Q_OW_DSEL_GLOB0;
+      if (op.dsel_glob[1]) fl |= B200Q_OW_DSEL_GLOB1;
+      w.x = uint32_t(op.code) | (uint32_t(op.arg) << 8) | fl | (uint32_t(o) << 24);
+      w.y = op.ctrl_loc;
+      w.z = (op.dsel_loc[0] & 0xffffu) | (op.dsel_loc[1] << 16);
+    }
+    words[o] = w;
+  }
+}
+
+// Product of the deferred common scalars of the pass: entry (0,0) of every Hadamard-structured op and the
+// sign of every UN-controlled rotation op whose matrix was negated.  Applied by the last round of the pass.
+template <typename Real>
+B200Q_HD double pass_scale(const b200q_pass_t& P, const cx<Real>* mats) {
+  double g = 1.0;
+  for (int o = 0; o < int(P.n_ops); ++o) {
+    const b200q_op_t& op = P.ops[o];
+    if (code_is_had(op.code)) g *= double(mats[op.mat_src].x);
+    else if (code_is_rot(op.code) && !op.tctrl && mats[op.mat_src].x < Real(0)) g = -g;
+  }
+  return g;
+}
+
+// Per-tile, CTA-uniform: which ops pass their global (outside-the-tile) controls.
+B200Q_HD uint64_t tile_enabled(const b200q_pass_t& P, uint64_t cta_base) {
+  uint64_t en = ~0ull;
+  for (int i = 0; i < int(P.n_gctrl); ++i) {
+    const int o = P.gctrl_ops[i];
+    if ((cta_base & P.ops[o].ctrl_glob) != P.ops[o].ctrl_glob) en &= ~(1ull << o);
+  }
+  return en;
+}
+
+template <typename Real> struct alignas(16) CoefQuad;
+template <> struct alignas(16) CoefQuad<float> { float a, b, c, d; };
+template <> struct alignas(16) CoefQuad<double> { double a, b; };
+B200Q_HD void load_quad(const float* k, int q, float* out) {
+  const CoefQuad<float> v = reinterpret_cast<const CoefQuad<float>*>(k)[q];
+  out[0] = v.a; out[1] = v.b; out[2] = v.c; out[3] = v.d;
+}
+B200Q_HD void load_quad(const double* k, int q, double* out) {
+  const CoefQuad<double> v0 = reinterpret_cast<const CoefQuad<double>*>(k)[2 * q];
+  const CoefQuad<double> v1 = reinterpret_cast<const CoefQuad<double>*>(k)[2 * q + 1];
+  out[0] = v0.a; out[1] = v0.b; out[2] = v1.a; out[3] = v1.b;
+}
+
+template <typename Real, int S, int VAR>
+B200Q_HD void mat1_fast(typename Traits<Real>::V* re, typename Traits<Real>::V* im, const Real* k) {
+  using V = typename Traits<Real>::V;
+  Coef<V> c;
+  Real q[4];
+  load_quad(k, 0, q);
+  c.r00 = vset(q[0], (V*)nullptr); c.r01 = vset(q[1], (V*)nullptr);
+  c.r10 = vset(q[2], (V*)nullptr); c.r11 = vset(q[3], (V*)nullptr);
+  if (VAR != VAR_REAL) {
+    load_quad(k, 1, q);
+    c.i01 = vset(q[0], (V*)nullptr); c.n01 = vset(q[1], (V*)nullptr);
+    c.i10 = vset(q[2], (V*)nullptr); c.n10 = vset(q[3], (V*)nullptr);
+  }
+  if (VAR == VAR_GENERAL) {
+    load_quad(k, 2, q);
+    c.i00 = vset(q[0], (V*)nullptr); c.n00 = vset(q[1], (V*)nullptr);
+    c.i11 = vset(q[2], (V*)nullptr); c.n11 = vset(q[3], (V*)nullptr);
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    if (e & (1 << S)) continue;
+    bfly_dispatch<VAR>(re[e], im[e], re[e | (1 << S)], im[e | (1 << S)], c);
+  }
+}
+
+// x += k * y, in place
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void axpy_inplace(pk& x, pk k, pk y) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x.u) : "l"(k.u), "l"(y.u));
+}
+#else
+inline void axpy_inplace(pk& x, pk k, pk y) { x = vfma(k, y, x); }
+#endif
+B200Q_HD void axpy_inplace(double& x, double k, double y) { x = k * y + x; }
+
+// Rotation-structured op as three in-place shears (see the record layout above).  ISX: the Rx family
+// (imaginary shears), else the Ry family (real shears).
+template <typename Real, int S, bool ISX>
+B200Q_HD void rot_fast(typename Traits<Real>::V* re, typename Traits<Real>::V* im, const Real* k, bool& neg) {
+  using V = typename Traits<Real>::V;
+  Real q[4], q1[4];
+  load_quad(k, 0, q);
+  load_quad(k, 1, q1);
+  neg = q1[0] != Real(0);
+  const V u = vset(q[0], (V*)nullptr), nu = vset(q[1], (V*)nullptr);
+  const V v = vset(q[2], (V*)nullptr), nv = vset(q[3], (V*)nullptr);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    if (e & (1 << S)) continue;
+    V& ar = re[e]; V& ai = im[e]; V& br = re[e | (1 << S)]; V& bi = im[e | (1 << S)];
+    if (ISX) {
+      axpy_inplace(ar, nu, bi); axpy_inplace(ai, u, br);
+      axpy_inplace(br, nv, ai); axpy_inplace(bi, v, ar);
+      axpy_inplace(ar, nu, bi); axpy_inplace(ai, u, br);
+    } else {
+      axpy_inplace(ar, u, br); axpy_inplace(ai, u, bi);
+      axpy_inplace(br, v, ar); axpy_inplace(bi, v, ai);
+      axpy_inplace(ar, u, br); axpy_inplace(ai, u, bi);
+    }
+  }
+}
+
+// Hadamard-structured op x * [[1, 1], [1, -1]]: two in-place packed instructions per component
+// (a += b; b = a - 2b); the common scalar x is applied once per pass (pass_scale).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void had_inplace(pk& ar, pk& ai, pk& br, pk& bi, pk m2) {
+  asm("add.rn.f32x2 %0, %0, %2;\n add.rn.f32x2 %1, %1, %3;\n"
+      " fma.rn.f32x2 %2, %4, %2, %0;\n fma.rn.f32x2 %3, %4, %3, %1;"
+      : "+l"(ar.u), "+l"(ai.u), "+l"(br.u), "+l"(bi.u) : "l"(m2.u));
+}
+#else
+inline void had_inplace(pk& ar, pk& ai, pk& br, pk& bi, pk m2) {
+  ar = pk_make(ar.x + br.x, ar.y + br.y); ai = pk_make(ai.x + bi.x, ai.y + bi.y);
+  br = vfma(m2, br, ar); bi = vfma(m2, bi, ai);
+}
+#endif
+B200Q_HD void had_inplace(double& ar, double& ai, double& br, double& bi, double m2) {
+  ar += br; ai += bi; br = m2 * br + ar; bi = m2 * bi + ai;
+}
+template <typename Real, int S>
+B200Q_HD void had_fast(typename Traits<Real>::V* re, typename Traits<Real>::V* im, bool flip) {
+  using V = typename Traits<Real>::V;
+  const V m2 = vset(Real(-2), (V*)nullptr);
+  if (flip) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (!(e & (1 << S))) had_inplace(re[e | (1 << S)], im[e | (1 << S)], re[e], im[e], m2);
+  } else {
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (!(e & (1 << S))) had_inplace(re[e], im[e], re[e | (1 << S)], im[e | (1 << S)], m2);
+  }
+}
+
+// complex64: exchange the lane bit with chunk slot S, in registers.  A = element with slot bit 0, B = with slot
+// bit 1; un-flipped: A' = (A.x, B.x), B' = (A.y, B.y); with the slot relabelled (flip) A holds logical 1:
+// A' = (B.x, A.x), B' = (B.y, A.y).  Afterwards the slot (the old lane bit) is un-flipped.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void lane_xpose(pk& a, pk& b, bool flip) {
+  if (flip)
+    asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
+        " mov.b64 %0, {b0, a0};\n mov.b64 %1, {b1, a1};\n}" : "+l"(a.u), "+l"(b.u));
+  else
+    asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
+        " mov.b64 %0, {a0, b0};\n mov.b64 %1, {a1, b1};\n}" : "+l"(a.u), "+l"(b.u));
+}
+#else
+inline void lane_xpose(pk& a, pk& b, bool flip) {
+  const pk A = a, Bv = b;
+  if (flip) { a = pk_make(Bv.x, A.x); b = pk_make(Bv.y, A.y); }
+  else { a = pk_make(A.x, Bv.x); b = pk_make(A.y, Bv.y); }
+}
+#endif
+B200Q_HD void lane_xpose(double&, double&, bool) {}
+
+template <typename V, int S>
+B200Q_HD void lane_swap(V* re, V* im, uint32_t& xm) {
+  const bool flip = ((xm >> S) & 1u) != 0;
+  if (flip) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (!(e & (1 << S))) { lane_xpose(re[e], re[e | (1 << S)], true); lane_xpose(im[e], im[e | (1 << S)], true); }
+  } else {
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (!(e & (1 << S))) { lane_xpose(re[e], re[e | (1 << S)], false); lane_xpose(im[e], im[e | (1 << S)], false); }
+  }
+  xm &= ~(1u << S);
+}
+
+// One half (slot bit == H) of a register-slot diagonal: phase in shear form (see phase_shears).
+template <typename Real, int S, int H>
+B200Q_HD void diag_half(typename Traits<Real>::V* re, typename Traits<Real>::V* im, const Real* ent, const Real* raw) {
+  using V = typename Traits<Real>::V;
+  Real q[4];
+  load_quad(ent, 0, q);
+  const int mode = int(q[2]);
+  if (mode == 0) return;
+  if (mode == 4) {
+    const V pr = vset(raw[0], (V*)nullptr), pi = vset(raw[1], (V*)nullptr), npi = vset(-raw[1], (V*)nullptr);
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (((e >> S) & 1) == H) cmul_inplace(re[e], im[e], pr, pi, npi);
+    return;
+  }
+  if (mode <= 2) {
+    const V t = vset(q[0], (V*)nullptr), s = vset(q[1], (V*)nullptr);
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (((e >> S) & 1) == H) { axpy_inplace(re[e], t, im[e]); axpy_inplace(im[e], s, re[e]); axpy_inplace(re[e], t, im[e]); }
+  }
+  if (mode >= 2) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (((e >> S) & 1) == H) { re[e] = vneg(re[e]); im[e] = vneg(im[e]); }
+  }
+}
+
+// thread-level value of DIAG selector j (tile-local bit of the thread's item, or a bit outside the tile)
+B200Q_HD uint32_t dsel_value(const b200q_pass_t& P, const OpWord& w, int j, uint32_t lb, uint64_t cta_base) {
+  const uint32_t loc = j ? (w.z >> 16) : (w.z & 0xffffu);
+  uint32_t v = (lb & loc) ? 1u : 0u;
+  if (w.x & (j ? B200Q_OW_DSEL_GLOB1 : B200Q_OW_DSEL_GLOB0))
+    v |= (cta_base & P.ops[w.x >> 24].dsel_glob[j]) ? 1u : 0u;
+  return v;
+}
+
+template <typename Real, int S>
+B200Q_HD void diag_reg(const b200q_pass_t& P, const OpWord& w, typename Traits<Real>::V* re,
+                       typename Traits<Real>::V* im, const Real* rec, uint32_t lb, uint64_t cta_base, uint32_t xm) {
+  const int j = (w.x >> 8) & 1, other = j ^ 1;
+  const uint32_t base = dsel_value(P, w, other, lb, cta_base) << other;
+  const uint32_t f = (xm >> S) & 1u;
+  const uint32_t i0 = base | (f << j), i1 = base | ((f ^ 1u) << j);
+  diag_half<Real, S, 0>(re, im, rec + 4 * i0, rec + 16 + 2 * i0);
+  diag_half<Real, S, 1>(re, im, rec + 4 * i1, rec + 16 + 2 * i1);
+}
+
+// X on chunk slot S controlled by chunk slot CS (arg = 4 S + CS)
+template <typename V>
+B200Q_HD void x_c1(int arg, V* re, V* im, uint32_t xm) {
+  const int cs = arg & 3;
+  const bool cval = ((xm >> cs) & 1u) == 0;
+  switch (arg >> 2) {
+    case 0: x_chunk_c1_cs<V, 0>(cs, re, im, cval); break;
+    case 1: x_chunk_c1_cs<V, 1>(cs, re, im, cval); break;
+    case 2: x_chunk_c1_cs<V, 2>(cs, re, im, cval); break;
+    default: x_chunk_c1_cs<V, 3>(cs, re, im, cval); break;
+  }
+}
+
+// One register round of one thread.  LEAN: only the temp-free op codes are compiled in (b200q_program.h).
+template <typename Real, bool LEAN>
 B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const RoundTab& T, int tid, uint64_t cta_base,
-                        typename Traits<Real>::chunk* tile, const cx<Real>* pool,
+                        uint64_t enabled, typename Traits<Real>::chunk* tile, const cx<Real>* pool,
+                        const Real* coef, const OpWord* words, Real gscale,
                         typename Traits<Real>::chunk* gstate, uint64_t total_chunks) {
   using V = typename Traits<Real>::V;
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
@@ -702,35 +1052,73 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
   Real rho_r = Real(1), rho_i = Real(0);
   bool rho_dirty = false;
   uint32_t xm = 0;   // X relabelling mask over the chunk-level register slots
-  constexpr int VS = Traits<Real>::VS;
-  for (int o = Rd.op_begin; o < Rd.op_end; ++o) {
-    const b200q_op_t& op = P.ops[o];
-    if (op.tctrl) {
-      if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;
-      if ((A.lb & op.ctrl_loc) != op.ctrl_loc) continue;
+  const OpWord* W = words + Rd.op_begin;
+  const int n = int(Rd.op_end) - int(Rd.op_begin);
+  OpWord nx = W[0];
+  for (int i = 0; i < n; ++i) {
+    const OpWord cur = nx;
+    nx = W[i + 1];   // prefetch (the table has a sentinel entry)
+    const uint32_t o = cur.x >> 24;
+    if (cur.x & (B200Q_OW_CTRL_LOC | B200Q_OW_CTRL_GLOB)) {
+      if ((A.lb & cur.y) != cur.y) continue;
+      if ((cur.x & B200Q_OW_CTRL_GLOB) && !((enabled >> o) & 1ull)) continue;
     }
-    const cx<Real>* m = pool + op.pool_off;
-#define B200Q_FAST(CV, VAR, S)                                                          \
-  case B200Q_CODE_MAT1_FAST + 4 * CV + S: {                                              \
-    const Coef<V> k = make_coef<Real, V>(m, (xm >> S) & 1u);                             \
-    mat1_chunk<V, S, VAR, false>(re, im, k, 0, 0, false);                                \
-    break;                                                                               \
-  }
-    switch (op.code) {
-      B200Q_FAST(0, VAR_REAL, 0) B200Q_FAST(0, VAR_REAL, 1) B200Q_FAST(0, VAR_REAL, 2) B200Q_FAST(0, VAR_REAL, 3)
-      B200Q_FAST(1, VAR_RXLIKE, 0) B200Q_FAST(1, VAR_RXLIKE, 1) B200Q_FAST(1, VAR_RXLIKE, 2) B200Q_FAST(1, VAR_RXLIKE, 3)
-      B200Q_FAST(2, VAR_GENERAL, 0) B200Q_FAST(2, VAR_GENERAL, 1) B200Q_FAST(2, VAR_GENERAL, 2)
-      B200Q_FAST(2, VAR_GENERAL, 3)
-      case B200Q_CODE_MAT1_SLOW: apply_mat1<Real>(op, re, im, m, xm); break;
-      case B200Q_CODE_X_RELABEL: xm ^= 1u << (int(op.slot) - VS); break;
-      case B200Q_CODE_X_SLOW: apply_x<Real>(op, re, im, xm); break;
-      case B200Q_CODE_DIAG:
-        apply_diag<Real, true>(op, re, im, m, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i, rho_dirty);
+    const Real* rec = coef + o * B200Q_COEF_PER_OP;
+#define B200Q_KREC(S) (rec + ((xm >> S) & 1u) * B200Q_COEF_PER_FLIP)
+#define B200Q_FAST(CV, VAR, S) \
+  case B200Q_CODE_MAT1_FAST + 4 * CV + S: mat1_fast<Real, S, VAR>(re, im, B200Q_KREC(S)); break;
+#define B200Q_PERSLOT(S)                                                                         \
+  case B200Q_CODE_MAT1_HAD + S: had_fast<Real, S>(re, im, ((xm >> S) & 1u) != 0); break;        \
+  case B200Q_CODE_MAT1_ROTX + S: {                                                               \
+    bool neg;                                                                                    \
+    rot_fast<Real, S, true>(re, im, B200Q_KREC(S), neg);                                         \
+    if (neg && (cur.x & (B200Q_OW_CTRL_LOC | B200Q_OW_CTRL_GLOB))) { rho_r = -rho_r; rho_i = -rho_i; rho_dirty = true; } \
+    break;                                                                                       \
+  }                                                                                              \
+  case B200Q_CODE_MAT1_ROTY + S: {                                                               \
+    bool neg;                                                                                    \
+    rot_fast<Real, S, false>(re, im, B200Q_KREC(S), neg);                                        \
+    if (neg && (cur.x & (B200Q_OW_CTRL_LOC | B200Q_OW_CTRL_GLOB))) { rho_r = -rho_r; rho_i = -rho_i; rho_dirty = true; } \
+    break;                                                                                       \
+  }                                                                                              \
+  case B200Q_CODE_DIAG_R + S: diag_reg<Real, S>(P, cur, re, im, rec, A.lb, cta_base, xm); break; \
+  case B200Q_CODE_LSWAP + S: lane_swap<V, S>(re, im, xm); break;
+    switch (cur.x & 0xffu) {
+      B200Q_PERSLOT(0) B200Q_PERSLOT(1) B200Q_PERSLOT(2) B200Q_PERSLOT(3)
+      case B200Q_CODE_X_RELABEL: xm ^= 1u << ((cur.x >> 8) & 3u); break;
+      case B200Q_CODE_X_C1: x_c1<V>(int((cur.x >> 8) & 15u), re, im, xm); break;
+      case B200Q_CODE_DIAG_T: {
+        const uint32_t idx = dsel_value(P, cur, 0, A.lb, cta_base) | (dsel_value(P, cur, 1, A.lb, cta_base) << 1);
+        const Real dr = rec[16 + 2 * idx], di = rec[17 + 2 * idx];
+        const Real r = rho_r * dr - rho_i * di, im2 = rho_r * di + rho_i * dr;
+        rho_r = r; rho_i = im2; rho_dirty = true;
         break;
-      default: break;
+      }
+      default:
+        if (!LEAN) {
+          const b200q_op_t& op = P.ops[o];
+          switch (cur.x & 0xffu) {
+            B200Q_FAST(0, VAR_REAL, 0) B200Q_FAST(0, VAR_REAL, 1) B200Q_FAST(0, VAR_REAL, 2) B200Q_FAST(0, VAR_REAL, 3)
+            B200Q_FAST(1, VAR_RXLIKE, 0) B200Q_FAST(1, VAR_RXLIKE, 1) B200Q_FAST(1, VAR_RXLIKE, 2)
+            B200Q_FAST(1, VAR_RXLIKE, 3)
+            B200Q_FAST(2, VAR_GENERAL, 0) B200Q_FAST(2, VAR_GENERAL, 1) B200Q_FAST(2, VAR_GENERAL, 2)
+            B200Q_FAST(2, VAR_GENERAL, 3)
+            case B200Q_CODE_MAT1_SLOW: apply_mat1<Real>(op, re, im, pool + op.pool_off, xm); break;
+            case B200Q_CODE_X_SLOW: apply_x<Real>(op, re, im, xm); break;
+            case B200Q_CODE_DIAG:
+              apply_diag<Real, true>(op, re, im, pool + op.pool_off, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i,
+                                     rho_dirty);
+              break;
+            default: break;
+          }
+        }
+        break;
     }
 #undef B200Q_FAST
+#undef B200Q_PERSLOT
+#undef B200Q_KREC
   }
+  if (Rd.dst_global && P.has_scale && gscale != Real(1)) { rho_r *= gscale; rho_i *= gscale; rho_dirty = true; }
   if (rho_dirty) {
     const V pr = vset(rho_r, (V*)nullptr), pi = vset(rho_i, (V*)nullptr), npi = vset(-rho_i, (V*)nullptr);
 #pragma unroll
@@ -957,6 +1345,7 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   V pr[NE], pi[NE], lr[NE], li[NE];
   uint32_t xm = 0;
+  constexpr int VS_ = Traits<Real>::VS;
   const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;
   if (A.active) {
     gather<Real>(A, T, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
@@ -987,6 +1376,17 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
         break;
       case B200Q_OP_X:
         if (on) { uint32_t xm2 = xm; apply_x<Real>(op, pr, pi, xm); apply_x<Real>(op, lr, li, xm2); }
+        break;
+      case B200Q_OP_LSWAP:
+        if (A.active) {
+          uint32_t xm2 = xm;
+          switch (int(op.slot) - VS_) {
+            case 0: lane_swap<V, 0>(pr, pi, xm); lane_swap<V, 0>(lr, li, xm2); break;
+            case 1: lane_swap<V, 1>(pr, pi, xm); lane_swap<V, 1>(lr, li, xm2); break;
+            case 2: lane_swap<V, 2>(pr, pi, xm); lane_swap<V, 2>(lr, li, xm2); break;
+            default: lane_swap<V, 3>(pr, pi, xm); lane_swap<V, 3>(lr, li, xm2); break;
+          }
+        }
         break;
       case B200Q_OP_DIAG: {
         const uint32_t tsel = diag_tsel(op, cta_base, A.lb);

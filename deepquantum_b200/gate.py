@@ -319,7 +319,7 @@ class PauliZ(_ConstSingle):
 
 
 class Hadamard(_ConstSingle):
-    _hint = L.GATE_REAL
+    _hint = L.GATE_REAL | L.GATE_HADAMARD
     _default_name = 'Hadamard'
 
     @classmethod
@@ -370,7 +370,7 @@ class TDaggerGate(_ConstSingle):
 class Rx(ParametricSingleGate):
     """exp(-i theta X / 2) (reference gate.py:1389-1480)."""
 
-    _hint = L.GATE_RXLIKE
+    _hint = L.GATE_RXLIKE | L.GATE_ROTATION
 
     def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
                  tsr_mode=False, requires_grad=False) -> None:
@@ -386,7 +386,7 @@ class Rx(ParametricSingleGate):
 
 
 class Ry(ParametricSingleGate):
-    _hint = L.GATE_REAL
+    _hint = L.GATE_REAL | L.GATE_ROTATION
 
     def __init__(self, inputs=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
                  tsr_mode=False, requires_grad=False) -> None:

@@ -47,6 +47,9 @@ extern "C" {
  * skips the multiplications by the structural zeros. */
 #define B200Q_GATE_REAL 2    /* every entry real: Hadamard, Ry (gate.py:1069, 1538)                     */
 #define B200Q_GATE_RXLIKE 4  /* diagonal real, off-diagonal purely imaginary: Rx, Pauli-Y (gate.py:1443) */
+#define B200Q_GATE_HADAMARD 8 /* x * [[1, 1], [1, -1]], x real (set together with REAL): Hadamard (gate.py:1069) */
+#define B200Q_GATE_ROTATION 16 /* unit-determinant rotation [[c, x], [y, c]], c^2 - x y = 1: with RXLIKE Rx
+                                  (gate.py:1443), with REAL Ry (gate.py:1538)                              */
 
 #define B200Q_MAX_TARGETS 6
 

@@ -36,8 +36,14 @@ def lower_ops(ops, nqubit, dtype=np.complex128, hints=True):
         if kind == L.GATE_MAT and k == 1 and hints:
             if np.all(m.imag == 0):
                 hint = L.GATE_REAL
+                if m[0, 0] != 0 and m[0, 0] == m[0, 1] == m[1, 0] == -m[1, 1]:
+                    hint |= L.GATE_HADAMARD
+                elif m[0, 0] == m[1, 1] and m[0, 1] == -m[1, 0] and abs(np.linalg.det(m) - 1) < 1e-6:
+                    hint |= L.GATE_ROTATION
             elif m[0, 0].imag == 0 and m[1, 1].imag == 0 and m[0, 1].real == 0 and m[1, 0].real == 0:
                 hint = L.GATE_RXLIKE
+                if m[0, 0] == m[1, 1] and m[0, 1] == m[1, 0] and abs(np.linalg.det(m) - 1) < 1e-6:
+                    hint |= L.GATE_ROTATION
         gates.append(L.make_gate(kind, targets, ctr, off, False, hint))
         mats.append(m.reshape(-1))
         off += m.size

@@ -21,13 +21,19 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
   const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
   std::vector<chunk> tile(size_t(1) << cb);
   std::vector<cx<Real>> pool(B200Q_POOL_MAX);
+  std::vector<Real> coef(size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP);
   const uint64_t chunks_per_state = (1ull << pl.n_qubits) >> VS;
   const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
   for (int64_t b = 0; b < batch; ++b) {
     chunk* gstate = reinterpret_cast<chunk*>(state_v) + uint64_t(b) * chunks_per_state;
     const cx<Real>* m = reinterpret_cast<const cx<Real>*>(mats_v) + b * mbs;
+    for (int tid = 0; tid < nthreads; ++tid) fill_coefs<Real>(P, tid, nthreads, coef.data(), m);
+    std::vector<OpWord> words(B200Q_MAX_OPS + 1);
+    for (int tid = 0; tid < nthreads; ++tid) fill_opwords(P, tid, nthreads, words.data());
+    const Real gscale = P.has_scale ? Real(pass_scale<Real>(P, m)) : Real(1);
     for (uint64_t t = 0; t < ntiles; ++t) {
       const uint64_t cta_base = tile_base(P, t);
+      const uint64_t enabled = tile_enabled(P, cta_base);
       // poison the tile so that a read of an unwritten slot is caught
       std::memset(tile.data(), 0xff, tile.size() * sizeof(chunk));
       std::vector<RoundTab> tabs(B200Q_MAX_ROUNDS);
@@ -42,7 +48,12 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
               run_direct_op<Real>(P, P.ops[o], tid, nthreads, cta_base, tile.data(), pool.data());
         } else {
           for (int tid = 0; tid < nthreads; ++tid)
-            run_round<Real>(P, Rd, tabs[r], tid, cta_base, tile.data(), pool.data(), gstate, chunks_per_state);
+            if (P.lean)
+              run_round<Real, true>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
+                                    words.data(), gscale, gstate, chunks_per_state);
+            else
+              run_round<Real, false>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
+                                     words.data(), gscale, gstate, chunks_per_state);
         }
       }
     }
@@ -129,7 +140,8 @@ extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, i
   if (chunk_bits) opt.chunk_bits = chunk_bits;
   if (low_bits) opt.low_bits = low_bits;
   if (max_rounds) opt.max_rounds = max_rounds;
-  opt.fuse = fuse;
+  opt.fuse = fuse & 1;
+  opt.structured = (fuse & 2) ? 0 : 1;   // test hook: bit 1 selects the general (un-structured) op codes
   std::string err;
   Plan* pl = make_plan(n_qubits, dtype, gates, n_gates, opt, &err);
   if (!pl) {

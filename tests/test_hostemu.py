@@ -146,3 +146,58 @@ def test_adjoint_sweep_matches_torch_autograd(cdtype):
         scale = max(1.0, np.abs(ref).max())
         assert np.abs(g - ref).max() / scale < tol, (wires, ctr, g, ref)
         off += m.size
+
+
+@pytest.mark.parametrize('fuse', [1, 3])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_structured_butterflies(seed, cdtype, fuse):
+    """Hadamard (add/sub + deferred scalar) and rotation (three in-place shears, matrix negated when
+    cos < 0) fast paths: angles over the full 4*pi period, mixed with CNOT relabelling (flip states),
+    thread-level / global controls (sign goes to the thread phase) and inverses."""
+    n = 15 if cdtype == np.complex64 else 14
+    rng = np.random.default_rng(100 + seed)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    ops = []
+    for _ in range(160):
+        w = int(rng.integers(n))
+        c = int((w + 1 + rng.integers(n - 1)) % n)
+        th = float(rng.uniform(0, 4 * np.pi))
+        kind = int(rng.integers(9))
+        if rng.integers(5) == 0:
+            w = n - 1   # index bit 0: the complex64 lane slot
+            c = int(rng.integers(n - 1))
+        elif rng.integers(5) == 0:
+            c = n - 1
+            w = int(rng.integers(n - 1))
+        if kind == 0:
+            ops.append((gates_np.H, [w], []))
+        elif kind == 1:
+            ops.append((gates_np.rx(th), [w], []))
+        elif kind == 2:
+            ops.append((gates_np.ry(th), [w], []))
+        elif kind == 3:
+            ops.append((gates_np.X, [w], [c]))
+        elif kind == 4:
+            ops.append((gates_np.rx(th), [w], [c]))
+        elif kind == 5:
+            ops.append((gates_np.ry(th), [w], [c]))
+        elif kind == 6:
+            ops.append((gates_np.H, [w], [c]))
+        elif kind == 7:
+            ops.append((gates_np.rx(th).conj().T, [w], []))
+        elif kind == 8:
+            ops.append((gates_np.S, [w], []))
+        if rng.integers(4) == 0:
+            ops.append((gates_np.rz(th), [w], [c] if rng.integers(2) else []))
+        if rng.integers(6) == 0:
+            ops.append((gates_np.p(th), [c], [w]))
+        if rng.integers(8) == 0:
+            ops.append((np.diag([1, 1, 1, -1]).astype(complex), [w, c], []))
+        if rng.integers(8) == 0:
+            ops.append((gates_np.rzz(th), [c, w], []))
+    ref = so.run_circuit(ops, n, psi)
+    out, stats = emu_run(ops, n, cdtype, state=psi, chunk_bits=11, fuse=fuse)
+    err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
+    assert err < (1e-12 if cdtype == np.complex128 else 3e-6), (err, stats)

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -39,6 +40,16 @@ template <int CB> struct TileCfg {
   static constexpr int kThreads = 1 << (CB - B200Q_REG_CHUNK_BITS);
   static constexpr int kMinBlocks = CB >= 13 ? 1 : (CB == 12 ? 2 : 4);
 };
+// Resident CTAs per SM of the forward kernel.  The lean complex64 instantiation is latency-bound on warps
+// (measured: 1 -> 2 CTAs/SM is 1.58x) and its shared memory (74 KiB) would allow THREE 64 KiB tiles per SM, but
+// the 80-register budget that requires spills the 64 data registers in the op loop: measured 4.2 ms per pass
+// instead of 2.3 ms.  Kept as a compile-time switch.
+#ifndef B200Q_LEAN_BLOCKS
+#define B200Q_LEAN_BLOCKS 2
+#endif
+template <typename Real, int CB, bool LEAN> struct FwdCfg {
+  static constexpr int kMinBlocks = (LEAN && CB == 12 && sizeof(Real) == 4) ? B200Q_LEAN_BLOCKS : TileCfg<CB>::kMinBlocks;
+};
 
 // Shared memory: tile | cx pool (DIAG / MATK / slow MAT1 matrices) | MAT1 coefficient records | round tables.
 template <typename Real, int CB> struct TileSmem {
@@ -47,14 +58,15 @@ template <typename Real, int CB> struct TileSmem {
   static constexpr size_t kCoef = size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP * sizeof(Real);
   static constexpr size_t kTabs = sizeof(RoundTab) * B200Q_MAX_ROUNDS;
   static constexpr size_t kWords = sizeof(OpWord) * (B200Q_MAX_OPS + 1);
-  static constexpr size_t kTotal = kTile + kPool + kCoef + kTabs + kWords;
+  static constexpr size_t kBase = kTile + kCoef + kTabs + kWords;   // the cx pool comes last: only passes with
+  static constexpr size_t kTotal = kBase + kPool;                   // dense / general ops allocate it
 };
 
 // Persistent CTAs: the prologue (matrix staging, coefficient records, round address tables) runs once per
 // CTA; the CTA then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A work item is (tile, state of the
 // batch); with per-state matrices (mat_batch_stride != 0) the batch is on blockIdx.y instead.
 template <typename Real, int CB, bool LEAN>
-__global__ void __launch_bounds__(TileCfg<CB>::kThreads, TileCfg<CB>::kMinBlocks)
+__global__ void __launch_bounds__(TileCfg<CB>::kThreads, FwdCfg<Real, CB, LEAN>::kMinBlocks)
 b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ state,
                   const cx<Real>* __restrict__ mats, uint64_t chunks_per_state, int64_t mat_batch_stride,
                   uint32_t tile_shift, uint64_t n_work) {
@@ -62,16 +74,16 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
   using SM = TileSmem<Real, CB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chunk* tile = reinterpret_cast<chunk*>(smem_raw);
-  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + SM::kTile);
-  Real* coef = reinterpret_cast<Real*>(smem_raw + SM::kTile + SM::kPool);
-  RoundTab* tabs = reinterpret_cast<RoundTab*>(smem_raw + SM::kTile + SM::kPool + SM::kCoef);
-  OpWord* words = reinterpret_cast<OpWord*>(smem_raw + SM::kTile + SM::kPool + SM::kCoef + SM::kTabs);
+  Real* coef = reinterpret_cast<Real*>(smem_raw + SM::kTile);
+  RoundTab* tabs = reinterpret_cast<RoundTab*>(smem_raw + SM::kTile + SM::kCoef);
+  OpWord* words = reinterpret_cast<OpWord*>(smem_raw + SM::kTile + SM::kCoef + SM::kTabs);
+  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + SM::kBase);
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
   const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
 
   fill_round_tabs<Real>(P, tid, nthreads, tabs);
-  if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, m, false);
+  if (P.needs_pool) fill_pool<Real>(P, tid, nthreads, pool, m, false);
   fill_coefs<Real>(P, tid, nthreads, coef, m);
   fill_opwords(P, tid, nthreads, words);
   const Real gscale = P.has_scale ? Real(pass_scale<Real>(P, m)) : Real(1);
@@ -115,18 +127,20 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
                 int64_t mat_batch_stride, cudaStream_t stream) {
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
-  const size_t smem = TileSmem<Real, CB>::kTotal;
+  const size_t smem_max = TileSmem<Real, CB>::kTotal;
+  const size_t smem = P.needs_pool ? smem_max : TileSmem<Real, CB>::kBase;
   auto kern = P.lean ? b200q_tile_kernel<Real, CB, true> : b200q_tile_kernel<Real, CB, false>;
+  const int blocks_per_sm = P.lean ? FwdCfg<Real, CB, true>::kMinBlocks : FwdCfg<Real, CB, false>::kMinBlocks;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     int rc = cuda_err(cudaFuncSetAttribute(b200q_tile_kernel<Real, CB, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max),
                       "cudaFuncSetAttribute");
     if (!rc)
       rc = cuda_err(cudaFuncSetAttribute(b200q_tile_kernel<Real, CB, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max),
                     "cudaFuncSetAttribute");
     if (rc) return rc;
     attr_set[dev] = true;
@@ -134,7 +148,8 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
   const uint64_t chunks_per_state = (1ull << n_qubits) >> VS;
   const int tile_shift = int(P.n_bits) - int(P.tile_bits);
   const uint64_t ntiles = 1ull << tile_shift;
-  const uint64_t resident = uint64_t(sm_count(dev)) * TileCfg<CB>::kMinBlocks;
+  static const int ctas_env = [] { const char* e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const uint64_t resident = uint64_t(sm_count(dev)) * (ctas_env > 0 ? ctas_env : blocks_per_sm);
   if (mat_batch_stride == 0) {
     const uint64_t n_work = ntiles * uint64_t(batch);
     dim3 grid((unsigned)std::min<uint64_t>(n_work, resident), 1, 1);

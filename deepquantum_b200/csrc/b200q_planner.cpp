@@ -200,6 +200,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     b200q_pass_t P;
     std::memset(&P, 0, sizeof(P));
     P.n_bits = (uint8_t)B.n_bits;
+    P.n_qubits = (uint8_t)n_qubits;
     P.tile_bits = (uint8_t)t_eff;
     int loc_of[64];
     for (int b = 0, j = 0, q = 0; b < B.n_bits; ++b) {
@@ -310,7 +311,10 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
           if (a.op_kind == B200Q_OP_MAT1 || a.op_kind == B200Q_OP_X) used |= 1u << op.slot;
           for (int j = 0; j < 2; ++j)
             if (op.dsel_slot[j] != 0xff) used |= 1u << op.dsel_slot[j];
-          if (used & 1u) {
+          // X on the lane with chunk-level controls only is a physical lane swap (X_LANE), not wrapped: an X
+          // relabelling between two LSWAPs would leave the lane flipped
+          const bool x_on_lane = a.op_kind == B200Q_OP_X && op.slot == 0 && !(op.ctrl_reg & 1u);
+          if ((used & 1u) && !x_on_lane) {
             for (int cs = B.rc - 1; cs >= 0 && lswap < 0; --cs)
               if (!((used >> (cs + 1)) & 1u)) lswap = cs;
           }
@@ -359,6 +363,7 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         } else if (a.op_kind == B200Q_OP_X) {
           const uint32_t cm = op.ctrl_reg >> B.vs;
           if (op.ctrl_reg == 0 && !lane_slot) { op.code = B200Q_CODE_X_RELABEL; op.arg = (uint8_t)(op.slot - B.vs); }
+          else if (lane_slot && !lane_ctrl && B.opt.structured) { op.code = B200Q_CODE_X_LANE; op.arg = (uint8_t)cm; }
           else if (!lane_slot && !lane_ctrl && cm != 0 && (cm & (cm - 1)) == 0 && B.opt.structured) {
             op.code = B200Q_CODE_X_C1;
             op.arg = (uint8_t)(4 * (op.slot - B.vs) + __builtin_ctz(cm));
@@ -484,8 +489,11 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     P.n_rounds = (uint8_t)n_rounds;
     P.n_ops = (uint8_t)n_ops;
     P.lean = 1;
-    for (int o = 0; o < n_ops; ++o)
+    for (int o = 0; o < n_ops; ++o) {
       if (P.ops[o].code >= B200Q_CODE_LEAN_END) P.lean = 0;
+      if (P.ops[o].kind == B200Q_OP_MATK) P.needs_pool = 1;
+    }
+    if (!P.lean) P.needs_pool = 1;
     P.pool_elems = (uint16_t)pool;
     plan->passes.push_back(P);
     plan->pass_gate_count.push_back(gates_in_pass);

@@ -50,12 +50,13 @@ enum {
 #define B200Q_CODE_X_RELABEL 20  /* chunk-level slot, no register-slot control: toggles the relabelling mask       */
 #define B200Q_CODE_X_C1 21       /* chunk-level target, exactly one chunk-level control (arg = 4*target + control) */
 #define B200Q_CODE_DIAG_T 22     /* diagonal with thread-level / global selectors only: folds into the phase rho   */
-#define B200Q_CODE_NONE 23
-#define B200Q_CODE_LEAN_END 24
-#define B200Q_CODE_MAT1_FAST 24  /* 24..35: variant (0 real, 1 rx-like, 2 general) * 4 + chunk slot, temporaries    */
-#define B200Q_CODE_MAT1_SLOW 36  /* register-slot controls or the lane slot */
-#define B200Q_CODE_X_SLOW 37
-#define B200Q_CODE_DIAG 38       /* any diagonal (generic path) */
+#define B200Q_CODE_X_LANE 23     /* complex64: X on the lane bit (arg = mask of chunk-level control slots)         */
+#define B200Q_CODE_NONE 24
+#define B200Q_CODE_LEAN_END 25
+#define B200Q_CODE_MAT1_FAST 25  /* 25..36: variant (0 real, 1 rx-like, 2 general) * 4 + chunk slot, temporaries    */
+#define B200Q_CODE_MAT1_SLOW 37  /* register-slot controls or the lane slot */
+#define B200Q_CODE_X_SLOW 38
+#define B200Q_CODE_DIAG 39       /* any diagonal (generic path) */
 
 #define B200Q_FLAG_ADJOINT 1u  /* use the conjugate transpose of the stored matrix */
 #define B200Q_FLAG_REAL 2u     /* MAT1: every entry is real (H, Ry, ...)                      */
@@ -100,6 +101,7 @@ typedef struct {
 
 typedef struct {
   uint8_t n_bits;     // physical index bits of the (padded) local state
+  uint8_t n_qubits;   // index bits of the state itself (< n_bits only for states smaller than the register bits)
   uint8_t tile_bits;  // amplitude bits per tile
   uint8_t n_rounds;
   uint8_t n_ops;
@@ -107,6 +109,7 @@ typedef struct {
   uint8_t n_nontile;
   uint8_t layout;     // B200Q_LAYOUT_* (complex64 only)
   uint8_t lean;       // every op has a LEAN code: run the lean kernel instantiation
+  uint8_t needs_pool; // some op reads the dense matrix pool in shared memory (MATK, general MAT1 / X / DIAG paths)
   uint8_t has_scale;  // the pass has ops with a deferred common scalar (pass_scale), applied by the last round
   uint8_t n_gctrl;    // ops with controls outside the tile (evaluated once per tile, see tile_enabled)
   uint8_t gctrl_ops[B200Q_MAX_OPS];

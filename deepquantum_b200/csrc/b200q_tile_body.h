@@ -109,8 +109,13 @@ inline void vpin(double&) {}
 // place instead of two values crossing over (the latter makes it rotate the whole register arrays
 // through copies at the head of the op loop -- ~46 MOVs per op, measured in SASS).
 #if defined(__CUDA_ARCH__)
+// 64-bit swap as two in-place 32-bit xor swaps: with moves through a temporary the register allocator
+// renames instead of swapping and pays the copies back at the op-loop back edge (2x the instructions).
 __device__ __forceinline__ void vswap(pk& a, pk& b) {
-  asm("{\n .reg .b64 t;\n mov.b64 t, %0;\n mov.b64 %0, %1;\n mov.b64 %1, t;\n}" : "+l"(a.u), "+l"(b.u));
+  asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
+      " xor.b32 a0, a0, b0;\n xor.b32 b0, b0, a0;\n xor.b32 a0, a0, b0;\n"
+      " xor.b32 a1, a1, b1;\n xor.b32 b1, b1, a1;\n xor.b32 a1, a1, b1;\n"
+      " mov.b64 %0, {a0, a1};\n mov.b64 %1, {b0, b1};\n}" : "+l"(a.u), "+l"(b.u));
 }
 __device__ __forceinline__ void vswap_lane1(pk& a, pk& b) {   // swap the high lanes only
   asm("{\n .reg .b32 al, ah, bl, bh;\n mov.b64 {al, ah}, %0;\n mov.b64 {bl, bh}, %1;\n"
@@ -621,29 +626,43 @@ B200Q_HD uint32_t sidx(uint32_t sbase, const uint32_t* sst, int c) {
   return sbase ^ ((c & 1) ? sst[0] : 0) ^ ((c & 2) ? sst[1] : 0) ^ ((c & 4) ? sst[2] : 0) ^ ((c & 8) ? sst[3] : 0);
 }
 
-// Fold the X relabelling mask into the base addresses: register element c is written to logical c ^ xm.
-template <typename Real>
-B200Q_HD void relabel(RoundAddr<Real>& A, const RoundTab& T, uint32_t xm) {
+// Global addressing without bounds checks (the state is not padded): the register-slot bits of gbase are zero,
+// so element c lives at base + sum of the strides of its set bits -- 64-bit pointer adds shared between the 16
+// elements instead of a 64-bit XOR chain, compare and select per element.  `sgn` makes stride s negative
+// (scatter with the slot relabelled: the base then already contains the stride).
+template <typename Real, typename Ptr>
+B200Q_HD void element_ptrs(Ptr base, const uint64_t* gst, uint32_t sgn, Ptr* p) {
+  p[0] = base;
 #pragma unroll
-  for (int s = 0; s < 4; ++s)
-    if ((xm >> s) & 1u) { A.gbase ^= T.gst[s]; A.sbase ^= T.sst[s]; }
+  for (int c = 1; c < NE; ++c) {
+    const int s = (c & 1) ? 0 : ((c & 2) ? 1 : ((c & 4) ? 2 : 3));   // lowest set bit
+    const int64_t st = ((sgn >> s) & 1u) ? -int64_t(gst[s]) : int64_t(gst[s]);
+    p[c] = p[c & (c - 1)] + st;
+  }
 }
 
 template <typename Real>
 B200Q_HD void gather(const RoundAddr<Real>& A, const RoundTab& T, bool from_global, bool soa_global,
                      const typename Traits<Real>::chunk* tile, const typename Traits<Real>::chunk* gstate,
-                     uint64_t total_chunks, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
+                     uint64_t total_chunks, bool padded, typename Traits<Real>::V* re, typename Traits<Real>::V* im) {
   using chunk = typename Traits<Real>::chunk;
   if (from_global) {
     uint64_t gst[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) gst[s] = T.gst[s];
+    if (!padded) {
+      const chunk* p[NE];
+      element_ptrs<Real, const chunk*>(gstate + A.gbase, gst, 0u, p);
 #pragma unroll
-    for (int c = 0; c < NE; ++c) {
-      const uint64_t idx = gidx(A.gbase, gst, c);
-      chunk v = zero_chunk((chunk*)nullptr);
-      if (idx < total_chunks) v = gstate[idx];
-      unpack(v, re[c], im[c], soa_global);
+      for (int c = 0; c < NE; ++c) unpack(*p[c], re[c], im[c], soa_global);
+    } else {
+#pragma unroll
+      for (int c = 0; c < NE; ++c) {
+        const uint64_t idx = gidx(A.gbase, gst, c);
+        chunk v = zero_chunk((chunk*)nullptr);
+        if (idx < total_chunks) v = gstate[idx];
+        unpack(v, re[c], im[c], soa_global);
+      }
     }
   } else {
     uint32_t sst[4];
@@ -654,27 +673,43 @@ B200Q_HD void gather(const RoundAddr<Real>& A, const RoundTab& T, bool from_glob
   }
 }
 
+// `xm`: X relabelling mask -- register element c is written to logical element c ^ xm.
 template <typename Real>
 B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_global, bool soa_global,
                       typename Traits<Real>::chunk* tile,
-                      typename Traits<Real>::chunk* gstate, uint64_t total_chunks,
+                      typename Traits<Real>::chunk* gstate, uint64_t total_chunks, bool padded, uint32_t xm,
                       const typename Traits<Real>::V* re, const typename Traits<Real>::V* im) {
   using chunk = typename Traits<Real>::chunk;
   if (to_global) {
     uint64_t gst[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) gst[s] = T.gst[s];
+    uint64_t gbase = A.gbase;
 #pragma unroll
-    for (int c = 0; c < NE; ++c) {
-      const uint64_t idx = gidx(A.gbase, gst, c);
-      if (idx < total_chunks) gstate[idx] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+    for (int s = 0; s < 4; ++s)
+      if ((xm >> s) & 1u) gbase ^= gst[s];
+    if (!padded) {
+      chunk* p[NE];
+      element_ptrs<Real, chunk*>(gstate + gbase, gst, xm, p);
+#pragma unroll
+      for (int c = 0; c < NE; ++c) *p[c] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+    } else {
+#pragma unroll
+      for (int c = 0; c < NE; ++c) {
+        const uint64_t idx = gidx(gbase, gst, c);
+        if (idx < total_chunks) gstate[idx] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+      }
     }
   } else {
     uint32_t sst[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) sst[s] = T.sst[s];
+    uint32_t sbase = A.sbase;
 #pragma unroll
-    for (int c = 0; c < NE; ++c) tile[sidx(A.sbase, sst, c)] = pack(re[c], im[c], true, (chunk*)nullptr);
+    for (int s = 0; s < 4; ++s)
+      if ((xm >> s) & 1u) sbase ^= sst[s];
+#pragma unroll
+    for (int c = 0; c < NE; ++c) tile[sidx(sbase, sst, c)] = pack(re[c], im[c], true, (chunk*)nullptr);
   }
 }
 
@@ -700,8 +735,8 @@ B200Q_HD uint32_t diag_tsel(const b200q_op_t& op, uint64_t cta_base, uint32_t lb
 //            after the matrix has been negated if c = e00 < 0 (`neg` = 1: the sign goes to the pass scalar
 //            or, for controlled ops, to the thread's phase rho).  No temporaries: the register allocator
 //            has nothing to shuffle back at the op-loop back edge.
-#define B200Q_COEF_PER_FLIP 16
-#define B200Q_COEF_PER_OP 32
+#define B200Q_COEF_PER_FLIP 12
+#define B200Q_COEF_PER_OP 24
 
 B200Q_HD bool code_is_rot(int code) { return code >= B200Q_CODE_MAT1_ROTX && code < B200Q_CODE_MAT1_ROTY + 4; }
 B200Q_HD bool code_is_had(int code) { return code >= B200Q_CODE_MAT1_HAD && code < B200Q_CODE_MAT1_HAD + 4; }
@@ -940,40 +975,30 @@ B200Q_HD void had_fast(typename Traits<Real>::V* re, typename Traits<Real>::V* i
   }
 }
 
-// complex64: exchange the lane bit with chunk slot S, in registers.  A = element with slot bit 0, B = with slot
-// bit 1; un-flipped: A' = (A.x, B.x), B' = (A.y, B.y); with the slot relabelled (flip) A holds logical 1:
-// A' = (B.x, A.x), B' = (B.y, A.y).  Afterwards the slot (the old lane bit) is un-flipped.
+// complex64: exchange the lane bit with chunk slot S, in registers: A = element with slot bit 0, B = with slot
+// bit 1; A' = (A.x, B.x), B' = (A.y, B.y), i.e. A.y <-> B.x, written as an in-place xor swap (with moves the
+// register allocator copies the whole 64-register state to fresh registers and back).  The relabelling
+// (flip) state of the slot travels with the data: bit S of xm is exchanged with the lane-flip bit 4; the
+// planner brackets every lane-touching op between two LSWAPs and never puts an X relabelling in between,
+// so the lane-flip bit is zero outside the brackets.
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void lane_xpose(pk& a, pk& b, bool flip) {
-  if (flip)
-    asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
-        " mov.b64 %0, {b0, a0};\n mov.b64 %1, {b1, a1};\n}" : "+l"(a.u), "+l"(b.u));
-  else
-    asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
-        " mov.b64 %0, {a0, b0};\n mov.b64 %1, {a1, b1};\n}" : "+l"(a.u), "+l"(b.u));
+__device__ __forceinline__ void lane_xpose(pk& a, pk& b) {
+  asm("{\n .reg .b32 a0, a1, b0, b1;\n mov.b64 {a0, a1}, %0;\n mov.b64 {b0, b1}, %1;\n"
+      " xor.b32 a1, a1, b0;\n xor.b32 b0, b0, a1;\n xor.b32 a1, a1, b0;\n"
+      " mov.b64 %0, {a0, a1};\n mov.b64 %1, {b0, b1};\n}" : "+l"(a.u), "+l"(b.u));
 }
 #else
-inline void lane_xpose(pk& a, pk& b, bool flip) {
-  const pk A = a, Bv = b;
-  if (flip) { a = pk_make(Bv.x, A.x); b = pk_make(Bv.y, A.y); }
-  else { a = pk_make(A.x, Bv.x); b = pk_make(A.y, Bv.y); }
-}
+inline void lane_xpose(pk& a, pk& b) { const float t = a.y; a.y = b.x; b.x = t; }
 #endif
-B200Q_HD void lane_xpose(double&, double&, bool) {}
+B200Q_HD void lane_xpose(double&, double&) {}
 
 template <typename V, int S>
 B200Q_HD void lane_swap(V* re, V* im, uint32_t& xm) {
-  const bool flip = ((xm >> S) & 1u) != 0;
-  if (flip) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (!(e & (1 << S))) { lane_xpose(re[e], re[e | (1 << S)], true); lane_xpose(im[e], im[e | (1 << S)], true); }
-  } else {
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (!(e & (1 << S))) { lane_xpose(re[e], re[e | (1 << S)], false); lane_xpose(im[e], im[e | (1 << S)], false); }
-  }
-  xm &= ~(1u << S);
+  for (int e = 0; e < NE; ++e)
+    if (!(e & (1 << S))) { lane_xpose(re[e], re[e | (1 << S)]); lane_xpose(im[e], im[e | (1 << S)]); }
+  const uint32_t d = ((xm >> S) ^ (xm >> 4)) & 1u;
+  xm ^= (d << S) | (d << 4);
 }
 
 // One half (slot bit == H) of a register-slot diagonal: phase in shear form (see phase_shears).
@@ -1047,7 +1072,9 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   if (!A.active) return;
   V re[NE], im[NE];
-  gather<Real>(A, T, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, re, im);
+  const bool padded = int(P.n_bits) != int(P.n_qubits);   // tiny states: index space padded to the register bits
+  gather<Real>(A, T, Rd.src_global, (P.layout & B200Q_LAYOUT_SRC_SOA) != 0, tile, gstate, total_chunks, padded, re,
+               im);
 
   Real rho_r = Real(1), rho_i = Real(0);
   bool rho_dirty = false;
@@ -1083,36 +1110,42 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
   }                                                                                              \
   case B200Q_CODE_DIAG_R + S: diag_reg<Real, S>(P, cur, re, im, rec, A.lb, cta_base, xm); break; \
   case B200Q_CODE_LSWAP + S: lane_swap<V, S>(re, im, xm); break;
-    switch (cur.x & 0xffu) {
-      B200Q_PERSLOT(0) B200Q_PERSLOT(1) B200Q_PERSLOT(2) B200Q_PERSLOT(3)
-      case B200Q_CODE_X_RELABEL: xm ^= 1u << ((cur.x >> 8) & 3u); break;
-      case B200Q_CODE_X_C1: x_c1<V>(int((cur.x >> 8) & 15u), re, im, xm); break;
-      case B200Q_CODE_DIAG_T: {
+    const uint32_t code = cur.x & 0xffu;
+    if (code >= B200Q_CODE_X_RELABEL) {   // light ops first: their cost is the dispatch itself
+      if (code == B200Q_CODE_X_RELABEL) {
+        xm ^= 1u << ((cur.x >> 8) & 3u);
+      } else if (code == B200Q_CODE_DIAG_T) {
         const uint32_t idx = dsel_value(P, cur, 0, A.lb, cta_base) | (dsel_value(P, cur, 1, A.lb, cta_base) << 1);
         const Real dr = rec[16 + 2 * idx], di = rec[17 + 2 * idx];
         const Real r = rho_r * dr - rho_i * di, im2 = rho_r * di + rho_i * dr;
         rho_r = r; rho_i = im2; rho_dirty = true;
-        break;
-      }
-      default:
-        if (!LEAN) {
-          const b200q_op_t& op = P.ops[o];
-          switch (cur.x & 0xffu) {
-            B200Q_FAST(0, VAR_REAL, 0) B200Q_FAST(0, VAR_REAL, 1) B200Q_FAST(0, VAR_REAL, 2) B200Q_FAST(0, VAR_REAL, 3)
-            B200Q_FAST(1, VAR_RXLIKE, 0) B200Q_FAST(1, VAR_RXLIKE, 1) B200Q_FAST(1, VAR_RXLIKE, 2)
-            B200Q_FAST(1, VAR_RXLIKE, 3)
-            B200Q_FAST(2, VAR_GENERAL, 0) B200Q_FAST(2, VAR_GENERAL, 1) B200Q_FAST(2, VAR_GENERAL, 2)
-            B200Q_FAST(2, VAR_GENERAL, 3)
-            case B200Q_CODE_MAT1_SLOW: apply_mat1<Real>(op, re, im, pool + op.pool_off, xm); break;
-            case B200Q_CODE_X_SLOW: apply_x<Real>(op, re, im, xm); break;
-            case B200Q_CODE_DIAG:
-              apply_diag<Real, true>(op, re, im, pool + op.pool_off, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i,
-                                     rho_dirty);
-              break;
-            default: break;
-          }
+      } else if (code == B200Q_CODE_X_C1) {
+        x_c1<V>(int((cur.x >> 8) & 15u), re, im, xm);
+      } else if (code == B200Q_CODE_X_LANE) {   // X on the lane bit, chunk-slot controls in arg: swaps the two lanes
+        const uint32_t cm = (cur.x >> 8) & 15u;
+        x_lane(re, im, cm, cm & ~xm);
+      } else if (!LEAN) {
+        const b200q_op_t& op = P.ops[o];
+        switch (code) {
+          B200Q_FAST(0, VAR_REAL, 0) B200Q_FAST(0, VAR_REAL, 1) B200Q_FAST(0, VAR_REAL, 2) B200Q_FAST(0, VAR_REAL, 3)
+          B200Q_FAST(1, VAR_RXLIKE, 0) B200Q_FAST(1, VAR_RXLIKE, 1) B200Q_FAST(1, VAR_RXLIKE, 2)
+          B200Q_FAST(1, VAR_RXLIKE, 3)
+          B200Q_FAST(2, VAR_GENERAL, 0) B200Q_FAST(2, VAR_GENERAL, 1) B200Q_FAST(2, VAR_GENERAL, 2)
+          B200Q_FAST(2, VAR_GENERAL, 3)
+          case B200Q_CODE_MAT1_SLOW: apply_mat1<Real>(op, re, im, pool + op.pool_off, xm); break;
+          case B200Q_CODE_X_SLOW: apply_x<Real>(op, re, im, xm); break;
+          case B200Q_CODE_DIAG:
+            apply_diag<Real, true>(op, re, im, pool + op.pool_off, diag_tsel(op, cta_base, A.lb), xm, rho_r, rho_i,
+                                   rho_dirty);
+            break;
+          default: break;
         }
-        break;
+      }
+    } else {
+      switch (code) {
+        B200Q_PERSLOT(0) B200Q_PERSLOT(1) B200Q_PERSLOT(2) B200Q_PERSLOT(3)
+        default: break;
+      }
     }
 #undef B200Q_FAST
 #undef B200Q_PERSLOT
@@ -1124,8 +1157,8 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
 #pragma unroll
     for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
-  relabel<Real>(A, T, xm);
-  scatter<Real>(A, T, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, re, im);
+  scatter<Real>(A, T, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, padded, xm,
+                re, im);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1348,8 +1381,8 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
   constexpr int VS_ = Traits<Real>::VS;
   const bool soa_in = (P.layout & B200Q_LAYOUT_DST_SOA) != 0, soa_out = (P.layout & B200Q_LAYOUT_SRC_SOA) != 0;
   if (A.active) {
-    gather<Real>(A, T, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, pr, pi);
-    gather<Real>(A, T, Rd.dst_global, soa_in, tile_lam, glam, total_chunks, lr, li);
+    gather<Real>(A, T, Rd.dst_global, soa_in, tile_psi, gpsi, total_chunks, true, pr, pi);
+    gather<Real>(A, T, Rd.dst_global, soa_in, tile_lam, glam, total_chunks, true, lr, li);
   } else {
 #pragma unroll
     for (int c = 0; c < NE; ++c) {
@@ -1402,9 +1435,8 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
     }
   }
   if (!A.active) return;
-  relabel<Real>(A, T, xm);
-  scatter<Real>(A, T, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, pr, pi);
-  scatter<Real>(A, T, Rd.src_global, soa_out, tile_lam, glam, total_chunks, lr, li);
+  scatter<Real>(A, T, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, true, xm, pr, pi);
+  scatter<Real>(A, T, Rd.src_global, soa_out, tile_lam, glam, total_chunks, true, xm, lr, li);
 }
 
 // Dense k-target op of the reverse sweep, in place in both shared-memory tiles.  Gradient

@@ -80,6 +80,11 @@ _SIGNATURES = {
                                     C.POINTER(C.c_uint8), C.c_void_p]),
     'b200q_qudit_apply': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                     C.c_int64, C.c_void_p]),
+    'b200q_block_mass': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    'b200q_sample_blocks': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p]),
+    'b200q_marginal_probs': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libb200q.so')
-SOURCES = ['b200q_lib.cu', 'b200q_qudit.cu', 'b200q_planner.cpp']
+SOURCES = ['b200q_lib.cu', 'b200q_qudit.cu', 'b200q_sample.cu', 'b200q_planner.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
               '-shared', '--threads', '4']
 

@@ -285,32 +285,17 @@ class QubitCircuit(Operation):
         return res if batched else res.squeeze(0)
 
     def measure(self, shots: int | None = None, with_prob: bool = False, wires=None, block_size: int = 2**24):
-        """Sampling (reference circuit.py:338-379 / qmath.py:568-638) is the step AFTER the hot path
-        (SURVEY.md section 8f); provided with plain torch ops for API completeness at moderate n."""
-        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        """Measure the final state (reference circuit.py:338-379 -> qmath.measure, qmath.py:568-638): sampled on
+        the device by the two-level inverse-CDF kernels (csrc/b200q_sample.cu)."""
+        from .qmath import measure as _measure
         shots = self.shots if shots is None else shots
-        n = self.nqubit
-        wires = list(range(n)) if wires is None else self._convert_indices(wires)
+        self.shots = shots
+        wires = list(range(self.nqubit)) if wires is None else self._convert_indices(wires)
         self.wires_measure = wires
-        flat = self.state.reshape(-1, 2**n)
-        results = []
-        for b in range(flat.shape[0]):
-            probs = (flat[b].real**2 + flat[b].imag**2).double()
-            probs = probs.reshape([2] * n)
-            keep = sorted(wires)
-            drop = [i for i in range(n) if i not in keep]
-            if drop:
-                probs = probs.sum(dim=drop)
-            perm = [keep.index(w) for w in wires]
-            probs = probs.permute(perm).reshape(-1)
-            idx = torch.multinomial(probs / probs.sum(), shots, replacement=True)
-            vals, counts = torch.unique(idx, return_counts=True)
-            d = {}
-            for v, c in zip(vals.tolist(), counts.tolist()):
-                key = format(v, f'0{len(wires)}b')
-                d[key] = (c, float(probs[v])) if with_prob else c
-            results.append(d)
-        return results[0] if self.state.ndim == 2 else results
+        if self.state is None:
+            return None
+        assert isinstance(self.state, torch.Tensor), 'There is no final state'
+        return _measure(self.state, shots=shots, with_prob=with_prob, wires=wires, block_size=block_size)
 
     def get_unitary(self) -> torch.Tensor:
         """Global unitary (small n): the circuit applied to the identity (reference circuit.py:467-477)."""

@@ -132,6 +132,49 @@ def norm2(state: torch.Tensor, nqubit: int, batch: int = 1) -> torch.Tensor:
     return out
 
 
+SAMPLE_BLOCK_BITS = 12   # 4 096 amplitudes (32 KiB of complex64) per block of the two-level inverse CDF
+
+
+def block_mass(state: torch.Tensor, nqubit: int, batch: int = 1, block_bits: int | None = None) -> torch.Tensor:
+    """[batch, 2^(n - block_bits)] float64: sum of |a|^2 over consecutive blocks (one read of the state)."""
+    require_cuda(state)
+    bb = min(SAMPLE_BLOCK_BITS if block_bits is None else block_bits, nqubit)
+    out = torch.empty(batch, 1 << (nqubit - bb), dtype=torch.float64, device=state.device)
+    L.check(L.load().b200q_block_mass(state.data_ptr(), nqubit, dtype_code(state.dtype), batch, bb, out.data_ptr(),
+                                      _stream(state)))
+    return out
+
+
+def sample_indices(state: torch.Tensor, nqubit: int, uniforms: torch.Tensor, block_bits: int | None = None,
+                   mass: torch.Tensor | None = None) -> torch.Tensor:
+    """Inverse-CDF sampling of basis-state indices of ONE state (2^n amplitudes) from float64 uniforms in
+    [0, 1): index = first i with sum_{j<=i} |a_j|^2 > u * sum_j |a_j|^2 (reference: torch.multinomial in
+    qmath.block_sample, qmath.py:543-565; same distribution, explicit randomness)."""
+    require_cuda(state)
+    bb = min(SAMPLE_BLOCK_BITS if block_bits is None else block_bits, nqubit)
+    if mass is None:
+        mass = block_mass(state, nqubit, 1, bb)[0]
+    cdf = torch.cumsum(mass, 0)
+    u = uniforms.to(device=state.device, dtype=torch.float64).contiguous() * cdf[-1]
+    blk = torch.searchsorted(cdf, u, right=True).clamp_(max=cdf.numel() - 1)
+    residual = (u - (cdf[blk] - mass[blk])).contiguous()
+    out = torch.empty(u.numel(), dtype=torch.int64, device=state.device)
+    L.check(L.load().b200q_sample_blocks(state.data_ptr(), nqubit, dtype_code(state.dtype), bb, blk.data_ptr(),
+                                         residual.data_ptr(), u.numel(), out.data_ptr(), _stream(state)))
+    return out
+
+
+def marginal_probs(state: torch.Tensor, nqubit: int, mask: int, keys_sorted: torch.Tensor) -> torch.Tensor:
+    """float64 [n_keys]: sum of |a_i|^2 over the indices with (i & mask) == key, keys sorted ascending."""
+    require_cuda(state)
+    out = torch.empty(keys_sorted.numel(), dtype=torch.float64, device=state.device)
+    for k0 in range(0, keys_sorted.numel(), 2048):
+        part = keys_sorted[k0:k0 + 2048].contiguous()
+        L.check(L.load().b200q_marginal_probs(state.data_ptr(), nqubit, dtype_code(state.dtype), mask, part.data_ptr(),
+                                              part.numel(), out[k0:].data_ptr(), _stream(state)))
+    return out
+
+
 def inner_product(bra: torch.Tensor, ket: torch.Tensor, nqubit: int, batch: int = 1) -> torch.Tensor:
     require_cuda(bra)
     require_cuda(ket)

@@ -145,6 +145,23 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
 int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
                       int n_targets, int64_t batch, void* stream);
 
+/* ---- sampling: qmath.measure + block_sample (qmath.py:543-638), the step after the path -----------
+ * Inverse-CDF sampling in two levels.  The caller (Python) draws `shots` uniforms, searches them in the
+ * prefix sum of the block masses and passes, per shot, the block and the residual mass inside it.
+ *   b200q_block_mass:     mass_dev[b * n_blocks + k] = sum of |a|^2 over block k (2^block_bits amplitudes) of
+ *                         state b; double accumulation, deterministic (no atomics); one read of the state.
+ *   b200q_sample_blocks:  out_index_dev[s] = first amplitude index i of block block_idx_dev[s] whose running
+ *                         mass (in index order, double) exceeds residual_dev[s]; one warp per shot.
+ *   b200q_marginal_probs: out_dev[j] = sum of |a_i|^2 over all i with (i & mask) == keys_sorted_dev[j]
+ *                         (exact marginal probability of the sampled outcomes on a wire subset, the
+ *                         `with_prob=True` branch of qmath.py:629-632); n_keys <= 2048. */
+int b200q_block_mass(const void* state, int n_qubits, int dtype, int64_t batch, int block_bits, double* mass_dev,
+                     void* stream);
+int b200q_sample_blocks(const void* state, int n_qubits, int dtype, int block_bits, const int64_t* block_idx_dev,
+                        const double* residual_dev, int64_t shots, int64_t* out_index_dev, void* stream);
+int b200q_marginal_probs(const void* state, int n_qubits, int dtype, uint64_t mask, const uint64_t* keys_sorted_dev,
+                         int n_keys, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,8 @@ Files written
   circuits.npz        final states of seeded circuits (specs stored as JSON) in c128 and c64
   qaoa.npz            QAOA MaxCut loss + gradient (reference autograd) at n = 6, 8, 10
   fock.npz            Fock tensor backend (squeezer / beamsplitter / phase shifter) final states
+  measure.npz         qmath.measure(with_prob=True): states, measured wires and the probabilities the reference
+                      attaches to every outcome it drew (all wires, wire subsets, batched states)
   dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
 """
 import json
@@ -219,8 +221,34 @@ def fock():
     np.savez_compressed(os.path.join(OUT, 'fock.npz'), **out)
 
 
+def measure():
+    """Reference qmath.measure (qmath.py:568-638) with with_prob=True: the counts are random, the attached
+    probabilities and the key convention (sorted wires, wire 0 first) are what the oracle is pinned to."""
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    cases = [('all5', 5, None, 1), ('sub6', 6, [4, 1, 3], 1), ('one7', 7, 2, 1), ('batch5', 5, [0, 3], 3)]
+    for name, n, wires, batch in cases:
+        st = torch.randn(batch, 2**n, generator=g, dtype=torch.float64) + 1j * torch.randn(
+            batch, 2**n, generator=g, dtype=torch.float64)
+        st = st / st.norm(dim=-1, keepdim=True)
+        arg = st[0] if batch == 1 else st
+        res = dq.qmath.measure(arg, shots=4096, with_prob=True, wires=wires)
+        res = [res] if batch == 1 else res
+        out[name + '/state'] = st.numpy()
+        out[name + '/meta'] = json.dumps({'n': n, 'wires': wires, 'batch': batch})
+        for b, d in enumerate(res):
+            keys = sorted(d)
+            out[f'{name}/keys{b}'] = np.array(keys)
+            out[f'{name}/counts{b}'] = np.array([d[k][0] for k in keys])
+            out[f'{name}/probs{b}'] = np.array([float(d[k][1]) for k in keys])
+    np.savez_compressed(os.path.join(OUT, 'measure.npz'), **out)
+    print('measure.npz:', len(out), 'arrays')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure']
+    if 'measure' in which:
+        measure()
     if 'gates' in which:
         gate_matrices()
     if 'circuits' in which:

@@ -645,6 +645,18 @@ class DistributedQubitCircuit(QubitCircuit):
             dist.all_reduce(vals)
         return vals.to(st.amps.real.dtype)
 
+    def measure(self, shots: int | None = None, with_prob: bool = False, wires=None, block_size: int = 2**24):
+        """Measure the sharded final state (reference circuit.py:1677-1704 -> measure_dist)."""
+        from .distributed import measure_dist
+        shots = self.shots if shots is None else shots
+        self.shots = shots
+        wires = list(range(self.nqubit)) if wires is None else self._convert_indices(wires)
+        self.wires_measure = wires
+        if self.state is None:
+            return None
+        return measure_dist(self.state, shots=shots, with_prob=with_prob, wires=wires, block_size=block_size,
+                            executor=self._executor)
+
     def cnot(self, control: int, target: int) -> None:
         self.cx(control, target)      # reference circuit.py:1764-1766: global controls then need no exchange
 

@@ -61,6 +61,16 @@ class CudaExecutor:
     def run_plan(self, plan, amps, mats):
         plan.run(amps, mats, 1, 0)
 
+    # local pieces of measure_dist (csrc/b200q_sample.cu)
+    def block_mass(self, amps, nlocal):
+        return engine.block_mass(amps, nlocal, 1)[0]
+
+    def sample_indices(self, amps, nlocal, uniforms, mass):
+        return engine.sample_indices(amps, nlocal, uniforms, mass=mass)
+
+    def marginal_probs(self, amps, nlocal, mask, keys_sorted):
+        return engine.marginal_probs(amps, nlocal, mask, keys_sorted)
+
 
 class ShardedProgram:
     """Per-rank execution schedule of a lowered gate program: local segments separated by block transposes."""
@@ -268,3 +278,87 @@ class ShardedProgram:
         """(gates, local passes, segments, block transposes) of this rank's schedule (after a first run)."""
         passes = sum(getattr(p, 'n_passes', 0) for p in self.plans.values())
         return {'gates': len(self.low.records), 'passes': passes, 'segments': self.n_segments, 'swaps': self.n_swaps}
+
+
+def measure_dist(state: DistributedQubitState, shots: int = 1024, with_prob: bool = False, wires=None,
+                 block_size: int = 2**24, executor=None, generator: torch.Generator | None = None) -> dict:
+    """Measure a sharded statevector (reference distributed.py:205-285).  Returns the result dict on rank 0 and
+    `{}` on the other ranks, like the reference.
+
+    No amplitudes move: every rank reduces its shard to block masses (one read), the W shard totals are
+    all-gathered, rank 0 draws the uniforms and broadcasts them, every rank runs the inverse CDF for the shots
+    that fall into its own mass interval, and only (key, count[, probability]) pairs are gathered.  The
+    reference instead swaps measured global wires into the shard (`dist_swap_gate`) and all-reduces a 2^k
+    probability tensor."""
+    import torch.distributed as dist
+    from .qmath import measure as _measure
+    ex = executor or CudaExecutor()
+    if state.world_size == 1 and executor is None:
+        return _measure(state.amps, shots, with_prob, wires, False, block_size, generator=generator)
+    n, nl, rank, world = state.nqubit, state.log_num_amps_per_node, state.rank, state.world_size
+    if isinstance(wires, int):
+        wires = [wires]
+    meas = list(range(n)) if wires is None else sorted(wires)
+    nbits = len(meas)
+    amps = state.amps
+    dev = amps.device
+    mass = ex.block_mass(amps, nl)
+    totals = torch.zeros(world, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(totals, mass.sum().reshape(1))
+    else:
+        totals[0] = mass.sum()
+    u = torch.rand(shots, dtype=torch.float64, generator=generator).to(dev)
+    if world > 1:
+        dist.broadcast(u, src=0)
+    cdf = torch.cumsum(totals, 0)
+    t = u * cdf[-1]
+    owner = torch.searchsorted(cdf, t, right=True).clamp_(max=world - 1)
+    mine = owner == rank
+    local = {}
+    if bool(mine.any()):
+        before = cdf[rank] - totals[rank]
+        ul = ((t[mine] - before) / totals[rank]).clamp_(0.0, 1.0 - 2.0**-53)
+        idx = ex.sample_indices(amps, nl, ul, mass) | (rank << nl)
+        keys = idx if nbits == n else torch.zeros_like(idx)
+        if nbits != n:
+            for j, w in enumerate(meas):
+                keys |= ((idx >> (n - 1 - w)) & 1) << (nbits - 1 - j)
+        vals, counts = torch.unique(keys, return_counts=True)
+        local = dict(zip(vals.tolist(), counts.tolist()))
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, local)
+    else:
+        gathered = [local]
+    merged = {}
+    for d in gathered:
+        for k, c in d.items():
+            merged[k] = merged.get(k, 0) + c
+    probs = None
+    if with_prob:
+        allkeys = sorted(merged)
+        kt = torch.tensor(allkeys, dtype=torch.int64, device=dev)
+        dep = torch.zeros_like(kt)        # key bits deposited at the measured GLOBAL index bits
+        mask = 0
+        for j, w in enumerate(meas):
+            dep |= ((kt >> (nbits - 1 - j)) & 1) << (n - 1 - w)
+            mask |= 1 << (n - 1 - w)
+        lmask = mask & ((1 << nl) - 1)
+        gmask = mask >> nl                                # measured rank bits
+        on_rank = ((dep >> nl) & gmask) == (rank & gmask)
+        part = torch.zeros(len(allkeys), dtype=torch.float64, device=dev)
+        if bool(on_rank.any()):
+            ldep = (dep[on_rank] & lmask)
+            uniq, inv = torch.unique(ldep, return_inverse=True)      # sorted; several keys may share a local part
+            part[on_rank] = ex.marginal_probs(amps, nl, lmask, uniq.contiguous())[inv]
+        if world > 1:
+            dist.all_reduce(part)
+        probs = dict(zip(allkeys, part.tolist()))
+    if rank != 0:
+        return {}
+    out = {}
+    for k in sorted(merged):
+        key = format(k, f'0{nbits}b')
+        out[key] = (merged[k], probs[k]) if with_prob else merged[k]
+    return out

@@ -29,6 +29,8 @@ def main():
         cir.to(dev, torch.double)
         st = cir()
         exp = cir.expectation()
+        torch.manual_seed(3)
+        meas = cir.measure(shots=400, with_prob=True, wires=[0, 1, n - 1])   # wires 0.. are global (rank bits)
         shards = [torch.empty_like(st.amps) for _ in range(world)]
         dist.all_gather(shards, st.amps.contiguous())
         full = torch.cat(shards)
@@ -50,6 +52,15 @@ def main():
             print(f'n={n} world={world} |sharded - dense| = {err:.3e}  expectation diff {e_err:.3e} '
                   f'schedule {cir._sharded.stats()}')
             ok = ok and err < 1e-10 and e_err < 1e-10
+            # measure_dist against the oracle's inverse CDF of the gathered state with the same uniforms
+            import sampling_oracle as smp
+            torch.manual_seed(3)
+            u = torch.rand(400, dtype=torch.float64).numpy()
+            want = smp.measure(full.cpu().numpy(), n, u, wires=[0, 1, n - 1], with_prob=True)
+            m_ok = set(want) == set(meas) and all(
+                abs(meas[k][0] - c) <= 1 and abs(meas[k][1] - p) < 1e-10 for k, (c, p) in want.items())
+            print(f'n={n} measure_dist keys {len(meas)} ok={m_ok}')
+            ok = ok and m_ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dq.cleanup_distributed()

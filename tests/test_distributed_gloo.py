@@ -36,6 +36,21 @@ class EmuExecutor:
                                    1, a.ctypes.data, m.ctypes.data, 1, 0, None, err, 256)
         assert rc == 0, err.value.decode()
 
+    # local pieces of measure_dist: the numpy oracle stands in for csrc/b200q_sample.cu
+    def block_mass(self, amps, nlocal):
+        p = np.abs(amps.numpy())**2
+        bb = min(12, nlocal)
+        return torch.from_numpy(p.reshape(-1, 2**bb).sum(1))
+
+    def sample_indices(self, amps, nlocal, uniforms, mass):
+        import sampling_oracle as smp
+        return torch.from_numpy(smp.sample_indices(amps.numpy(), uniforms.numpy()).astype(np.int64))
+
+    def marginal_probs(self, amps, nlocal, mask, keys_sorted):
+        p = np.abs(amps.numpy())**2
+        idx = np.arange(p.size) & mask
+        return torch.tensor([p[idx == int(k)].sum() for k in keys_sorted.tolist()], dtype=torch.float64)
+
 
 def _build(cir, n):
     """A circuit that exercises every sharded case: global 1-target gates, global / local controls, global
@@ -91,9 +106,15 @@ def _worker(rank, world, port, n, outdir):
             dist.all_gather(shards, st.amps.contiguous())
         else:
             shards = [st.amps]
+        import json
+        meas = {}
+        for name, wires in (('all', None), ('sub', [n - 1, 0, 2]), ('glob', [0])):
+            torch.manual_seed(5)     # rank 0 draws the uniforms
+            meas[name] = cir.measure(shots=300, with_prob=True, wires=wires)
+            assert rank == 0 or meas[name] == {}
         if rank == 0:
             np.savez(os.path.join(outdir, 'out.npz'), state=torch.cat(shards).numpy(),
-                     steps=np.array([s[0] for s in cir._sharded.steps]))
+                     steps=np.array([s[0] for s in cir._sharded.steps]), measure=json.dumps(meas))
     finally:
         dq.cleanup_distributed()
 
@@ -138,6 +159,19 @@ def test_sharded_circuit_matches_dense_oracle(world, tmp_path):
     assert np.linalg.norm(got - ref) < 1e-12, np.linalg.norm(got - ref)
     if world > 1:
         assert 'swap' in list(res['steps'])      # the circuit does target global qubits
+    # measure_dist: same uniforms (seeded on rank 0) -> the oracle's inverse-CDF counts and marginal probabilities
+    import json
+
+    import sampling_oracle as smp
+    meas = json.loads(str(res['measure']))
+    torch.manual_seed(5)
+    u = torch.rand(300, dtype=torch.float64).numpy()
+    for name, wires in (('all', None), ('sub', [n - 1, 0, 2]), ('glob', [0])):
+        exp = smp.measure(ref, n, u, wires=wires, with_prob=True)
+        got_m = meas[name]
+        assert set(got_m) == set(exp), name
+        for k, (c, p) in exp.items():
+            assert got_m[k][0] == c and abs(got_m[k][1] - p) < 1e-12, (name, k, got_m[k], (c, p))
 
 
 if __name__ == '__main__':

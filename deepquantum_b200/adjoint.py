@@ -65,8 +65,10 @@ class CircuitFunction(torch.autograd.Function):
         # cotangent of the matrix buffer, always accumulated in double precision
         grad_m = torch.zeros(mats.shape, dtype=torch.complex128, device=mats.device)
         # only gates whose matrix is computed from parameters / data need a gradient
-        need = (C.c_uint8 * max(1, len(prog.low.records)))(*[0 if r[4] in ('none', 'const') else 1
-                                                             for r in prog.low.records])
+        def _needs(r):
+            block = prog.low.derived[r[5]][4] if r[4] == 'derived' else r[4]
+            return 0 if block in ('none', 'const') else 1
+        need = (C.c_uint8 * max(1, len(prog.low.records)))(*[_needs(r) for r in prog.low.records])
         if not ctx.needs_input_grad[1]:
             need = (C.c_uint8 * max(1, len(prog.low.records)))()
         lib = L.load()

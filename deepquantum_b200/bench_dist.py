@@ -37,7 +37,7 @@ def run(args):
     cir.to(dev)
     data_host = torch.tensor(angles, dtype=torch.float32).pin_memory()
     data_dev = data_host.to(dev)
-    ngates = len(cir._get_program().low.records)
+    ngates = cir._get_program().ngates
 
     def sync():
         torch.cuda.synchronize()

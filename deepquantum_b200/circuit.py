@@ -49,7 +49,8 @@ class _Program:
 
     @property
     def ngates(self) -> int:
-        return len(self.structs)
+        """Gate applications of the SOURCE circuit (the lowering may fuse `cnot; rz; cnot` into one diagonal)."""
+        return self.low.n_source_gates
 
 
 class QubitCircuit(Operation):

@@ -469,6 +469,10 @@ int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_
     if (options->max_rounds) opt.max_rounds = options->max_rounds;
     opt.fuse = options->fuse;
     if (options->reserved[0]) opt.structured = 0;   // A/B switch: general op codes only
+    if (options->reserved[1]) opt.coalesce_bits = options->reserved[1] - 1;   // experiment: 1 + lane-owned chunk bits
+  }
+  if (const char* e = getenv("B200Q_COALESCE_BITS")) {
+    opt.coalesce_bits = atoi(e);
   }
   if (opt.chunk_bits < 11 || opt.chunk_bits > 13) return set_err(B200Q_EINVAL, "chunk_bits must be 11, 12 or 13");
   std::string err;

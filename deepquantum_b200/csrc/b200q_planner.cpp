@@ -163,7 +163,8 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
   plan->opt = B.opt;
   plan->stats.n_gates = n_gates;
 
-  const int min_chunk_loc = std::max(0, std::min(3, (t_eff - B.vs) - B.rc));  // coalescing: lanes own chunk bits 0..2
+  // coalescing of the global rounds: lanes own the lowest `coalesce_bits` chunk bits (3: 128-byte runs)
+  const int min_chunk_loc = std::max(0, std::min(B.opt.coalesce_bits, (t_eff - B.vs) - B.rc));
   const int min_loc = min_chunk_loc + B.vs;
 
   while (true) {

@@ -16,6 +16,9 @@ struct PlanOptions {
   int max_rounds = B200Q_MAX_ROUNDS;
   int max_ops = B200Q_MAX_OPS;
   int structured = 1;     // Hadamard / rotation hints select the in-place add-sub and three-shear butterflies
+  int coalesce_bits = 1;  // chunk-index bits that stay lane bits in the rounds that touch global memory (1: every
+                          // warp-level access uses whole 32-byte sectors; measured equal to 3 = 128-byte runs, with
+                          // fewer rounds: a single gate on a low qubit is then ONE round at the copy bandwidth)
   int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
 };
 

@@ -100,6 +100,8 @@ class Lowering:
         self._const_index = {}
         self._const_cache = {}
         self._idx_cache = {}
+        self.derived = []      # (source record index): 4x4 diagonals built from a 2x2 diagonal, see _peephole
+        self.n_source_gates = 0
 
     def add(self, gate: 'Gate', kind: int, wires, controls, adjoint: bool = False, matrix_of: 'Gate | None' = None):
         n = self.nqubit
@@ -127,16 +129,47 @@ class Lowering:
         self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size, hint))
         self.sources.append(src if kind != L.GATE_X else None)
 
+    FUSE_CX_DIAG_CX = True
+
+    def _peephole(self):
+        """CX(a->b) . D(b) . CX(a->b)  ==  diag(d0, d1, d1, d0) on (b, a) for a 1-target diagonal D = diag(d0, d1):
+        the `cnot; rz; cnot` idiom of the reference's QAOA / ZZ-feature-map circuits (examples/qaoa.py:36-40)
+        becomes ONE diagonal op -- no amplitude moves, no tile-bit requirement -- whose matrix entries are
+        gathered from D's matrix in `build_matrices` (so autograd, forward and adjoint, chains through D)."""
+        recs, srcs, out_r, out_s = self.records, self.sources, [], []
+        i = 0
+        while i < len(recs):
+            a = recs[i]
+            if (self.FUSE_CX_DIAG_CX and i + 2 < len(recs) and a[0] == L.GATE_X and len(a[2]) == 1
+                    and recs[i + 2][:3] == a[:3] and recs[i + 1][0] == L.GATE_DIAG and recs[i + 1][1] == a[1]
+                    and recs[i + 1][2] == () and recs[i + 1][4] != 'none'):
+                d = recs[i + 1]
+                # matrix-index bit 0 acts on the target b, bit 1 on the control a
+                out_r.append((L.GATE_DIAG, (a[1][0], a[2][0]), (), d[3], 'derived', len(self.derived), 16, 0))
+                out_s.append(srcs[i + 1])
+                self.derived.append(d)
+                i += 3
+            else:
+                out_r.append(a)
+                out_s.append(srcs[i])
+                i += 1
+        self.records, self.sources = out_r, out_s
+
     def finalize(self):
         """Assign matrix-buffer offsets; returns (GateStruct list, layout description)."""
+        self.n_source_gates = len(self.records)
+        self._peephole()
         sizes = {'const': [0] * len(self.const), 'dyn': [0] * len(self.dynamic)}
         for cls, lst in self.groups.items():
             sizes[cls] = [0] * len(lst)
+        sizes['derived'] = [16] * len(self.derived)
         for kind, _t, _c, _a, block, idx, size, _h in self.records:
             if block != 'none':
                 sizes[block][idx] = size
+        for _k, _t, _c, _a, block, idx, size, _h in self.derived:   # the source matrices must be laid out too
+            sizes[block][idx] = size
         bases, offs, total = {}, {}, 0
-        for block in ['const', 'dyn'] + list(self.groups):
+        for block in ['const', 'dyn'] + list(self.groups) + ['derived']:
             bases[block] = total
             acc, lst = 0, []
             for s in sizes[block]:
@@ -150,6 +183,19 @@ class Lowering:
             structs.append(L.make_gate(kind, targets, ctrl, off, adj, hint))
         self.offsets = [0 if r[4] == 'none' else bases[r[4]] + offs[r[4]][r[5]] for r in self.records]
         self.total = max(total, 1)
+        # gather indices of the derived diagonals: entry (j, j) of diag(d0, d1, d1, d0) <- source (0,0) / (1,1);
+        # the off-diagonal entries (never read by the kernel) <- source (0,1), a structural zero
+        self._derived_src = None
+        if self.derived:
+            idx = []
+            for d in self.derived:
+                so = bases[d[4]] + offs[d[4]][d[5]]
+                blockidx = [so + 1] * 16
+                for j, e in ((0, 0), (1, 3), (2, 3), (3, 0)):
+                    blockidx[5 * j] = so + e
+                idx.extend(blockidx)
+            self._derived_src = idx
+            self.n_primary = bases['derived']
         return structs
 
     def _gather_from_data(self, cls, lst):
@@ -211,8 +257,15 @@ class Lowering:
         if batched:
             nb = next(x.shape[0] for x in parts if x.ndim == 2)
             parts = [x if x.ndim == 2 else x.unsqueeze(0).expand(nb, -1) for x in parts]
-            return torch.cat(parts, dim=-1).contiguous()
-        return torch.cat(parts)
+            flat = torch.cat(parts, dim=-1).contiguous()
+        else:
+            flat = torch.cat(parts)
+        if self._derived_src:
+            key = ('derived', str(device))
+            if key not in self._idx_cache:
+                self._idx_cache[key] = torch.tensor(self._derived_src, dtype=torch.int64, device=device)
+            flat = torch.cat([flat, flat.index_select(-1, self._idx_cache[key])], dim=-1)
+        return flat
 
 
 class Gate(Operation):

@@ -136,3 +136,61 @@ def test_lazy_zero_state_is_not_materialised():
     assert 'state' not in st._buffers
     st.to(torch.double)
     assert st.dtype == torch.complex128
+
+
+def test_cx_diag_cx_peephole():
+    """`cnot; rz; cnot` (examples/qaoa.py:36-40) is lowered to ONE 2-target diagonal whose entries are gathered from
+    the Rz matrix: same state as the un-fused lowering and as the oracle, also for the inverse circuit, with the
+    gradient flowing through the gather."""
+    import gates_np
+    import statevec_oracle as so
+    from deepquantum_b200.operation import Lowering
+    n = 7
+    th = [0.3, 1.1, -2.0, 0.7]
+
+    def build():
+        cir = dq.QubitCircuit(n)
+        cir.hlayer()
+        for i, (a, b) in enumerate([(0, 1), (2, 5), (6, 0), (3, 4)]):
+            cir.cnot(a, b)
+            cir.rz(b, th[i])
+            cir.cnot(a, b)
+            cir.rx(a, 0.4 + i)
+        cir.cnot(1, 2)
+        cir.s(2)                 # constant diagonal in the middle: fused too
+        cir.cnot(1, 2)
+        cir.cnot(1, 3)
+        cir.rz(2, 0.9)           # different target: NOT the pattern
+        cir.cnot(1, 3)
+        return cir
+
+    cir = build()
+    cir.to(torch.double)
+    prog = cir._get_program()
+    assert prog.ngates == len(cir.operators) and len(prog.structs) == prog.ngates - 2 * 5
+    out, _ = emu_run_program(prog, n, np.complex128)
+    ops = [(op.update_matrix().detach().numpy(), op.wires, op.controls) for op in cir.operators]
+    ref = so.run_circuit(ops, n)
+    assert np.linalg.norm(out[0] - ref) < 1e-13
+    Lowering.FUSE_CX_DIAG_CX = False
+    try:
+        plain = build()
+        plain.to(torch.double)
+        p2 = plain._get_program()
+        assert len(p2.structs) == p2.ngates
+        out2, _ = emu_run_program(p2, n, np.complex128)
+    finally:
+        Lowering.FUSE_CX_DIAG_CX = True
+    assert np.linalg.norm(out[0] - out2[0]) < 1e-13
+    inv = cir.inverse()
+    inv.to(torch.double)
+    back, _ = emu_run_program(inv._get_program(), n, np.complex128, state=out[0])
+    e0 = np.zeros(2**n)
+    e0[0] = 1
+    assert np.linalg.norm(back[0] - e0) < 1e-6   # the float32-rounded Hadamard constant (gate.py:1069) is not unitary
+    # the derived block is a differentiable gather of the Rz matrix
+    rz = [op for op in cir.operators if isinstance(op, dq.Rz)][0]
+    rz.theta.requires_grad_(True)
+    m = prog.low.build_matrices(torch.complex128, 'cpu')
+    m[prog.low.n_primary:].abs().sum().backward()
+    assert rz.theta.grad is not None

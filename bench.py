@@ -203,6 +203,22 @@ def run_single(args):
         total_ms = ev_all[0].elapsed_time(ev_all[1])
         kern_ms = sum(a.elapsed_time(b) for a, b in ev_k)
         norm = float(engine.norm2(state, n)[0])
+
+        # the same kernel in its HBM-bound regime: ONE gate per pass (what b200q_apply_gate, the evolve_state
+        # drop-in, launches) -- reported next to the fused number, which is issue-bound by design
+        from deepquantum_b200 import _lib as L
+        single = engine.FusedPlan(n, torch.complex64, [L.make_gate(L.GATE_MAT, [n // 2], [], 0, False,
+                                                                    L.GATE_REAL | L.GATE_HADAMARD)])
+        hmat = (torch.tensor([[1, 1], [1, -1]], dtype=torch.complex64, device=dev) / 2**0.5).reshape(-1)
+        for _ in range(3):
+            single.run(state, hmat, 1, 0)
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        es[0].record()
+        for _ in range(10):
+            single.run(state, hmat, 1, 0)
+        es[1].record()
+        torch.cuda.synchronize()
+        single_ms = es[0].elapsed_time(es[1]) / 10
         del state
 
         # ---- end to end through the public API: pinned host angles -> cir(data) -> expectation -> host
@@ -229,6 +245,11 @@ def run_single(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = n_passes * args.steps * bytes_pass / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))['tile_kernel_c64_28q_bytes_per_launch']
+    except Exception:
+        pass
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c64',
@@ -237,13 +258,17 @@ def run_single(args):
                    'state_bytes': state_bytes, 'l2': 'state (2 GiB) is larger than L2 (126 MB): no flush needed',
                    'tile_bytes': 16 << (args.chunk_bits or 12), 'fused': not args.no_fuse, 'norm2_check': norm},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'kernel': 'b200q_tile_kernel<float,12>',
-                     'peak_source': 'MEASURED_PEAKS.json (measured copy)' if peaks else 'fallback 6650',
-                     'bytes_per_launch': bytes_pass, 'ms_per_launch': kern_ms / (n_passes * args.steps)},
+                     'traffic': traffic, 'kernel': 'b200q_tile_kernel<float,12,lean>',
+                     'peak_source': 'MEASURED_PEAKS.json (measured copy, burst)' if peaks else 'fallback 6650',
+                     'bytes_per_launch': bytes_pass, 'ms_per_launch': kern_ms / (n_passes * args.steps),
+                     'note': 'fused passes (~40 gates each) are issue-bound, not HBM-bound; the same kernel with one '
+                             'gate per pass is HBM-bound: see single_gate_pass',
+                     'single_gate_pass': {'ms': single_ms, 'achieved': bytes_pass / (single_ms * 1e-3) / 1e9,
+                                          'frac': bytes_pass / (single_ms * 1e-3) / 1e9 / peak}},
         'e2e': {'value': ngates * args.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': data_host.numel() * 4,
                 'd2h_bytes_per_step': int(res.numel() * res.element_size()),
                 'note': 'cir(data) from pinned host angles + expectation() read back, wall clock'},
-        'gpu_launches': args.steps * (n_passes + 1),
+        'gpu_launches': args.steps * (n_passes + 1),   # tile kernel per pass + init_basis, timed region only
         'clocks': clocks.summary(),
     }
     if not args.no_cpu_baseline:

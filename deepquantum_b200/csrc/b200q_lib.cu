@@ -223,25 +223,49 @@ int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const vo
 // ------------------------------------------------------------------------------------------------
 // adjoint (reverse) sweep kernel: two tiles (psi, lambda) per CTA
 // ------------------------------------------------------------------------------------------------
+template <typename Real, int CB> struct AdjSmem {
+  static constexpr size_t kTiles = size_t(32) << CB;
+  static constexpr size_t kPool = size_t(B200Q_POOL_MAX) * sizeof(cx<Real>);
+  static constexpr size_t kAcc = size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP * sizeof(double);
+  static constexpr size_t kGfac = size_t(B200Q_MAX_OPS) * sizeof(double);
+  static constexpr size_t kWacc = size_t(TileCfg<CB>::kThreads / 32) * B200Q_MAX_OPS * B200Q_WACC_PER_OP * sizeof(double);
+  static constexpr size_t kTabs = sizeof(RoundTab) * B200Q_MAX_ROUNDS;
+  static constexpr size_t kCoef = size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP * sizeof(Real);
+  static constexpr size_t kWords = sizeof(OpWord) * (B200Q_MAX_OPS + 1);
+  static constexpr size_t kTotal = kTiles + kPool + kAcc + kGfac + kWacc + kTabs + kCoef + kWords;
+};
+
 template <typename Real, int CB>
 __global__ void __launch_bounds__(TileCfg<CB>::kThreads, 1)
 b200q_adjoint_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ psi,
                      typename Traits<Real>::chunk* __restrict__ lam, const cx<Real>* __restrict__ mats,
                      double* __restrict__ grad, uint64_t want_mask, uint64_t chunks_per_state) {
   using chunk = typename Traits<Real>::chunk;
+  using SM = AdjSmem<Real, CB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chunk* tile_psi = reinterpret_cast<chunk*>(smem_raw);
   chunk* tile_lam = reinterpret_cast<chunk*>(smem_raw + (size_t(16) << CB));
-  cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + (size_t(32) << CB));
-  double* acc = reinterpret_cast<double*>(smem_raw + (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>));
-  RoundTab* tabs = reinterpret_cast<RoundTab*>(acc + size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP);
+  unsigned char* q = smem_raw + SM::kTiles;
+  cx<Real>* pool = reinterpret_cast<cx<Real>*>(q); q += SM::kPool;
+  double* acc = reinterpret_cast<double*>(q); q += SM::kAcc;
+  double* gfac = reinterpret_cast<double*>(q); q += SM::kGfac;
+  double* wacc = reinterpret_cast<double*>(q); q += SM::kWacc;
+  RoundTab* tabs = reinterpret_cast<RoundTab*>(q); q += SM::kTabs;
+  Real* coef = reinterpret_cast<Real*>(q); q += SM::kCoef;
+  OpWord* words = reinterpret_cast<OpWord*>(q);
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
   const uint64_t cta_base = tile_base(P, blockIdx.x);
   for (int e = tid; e < int(P.n_ops) * B200Q_ACC_PER_OP; e += nthreads) acc[e] = 0.0;
+  for (int e = tid; e < int(SM::kWacc / sizeof(double)); e += nthreads) wacc[e] = 0.0;
   fill_round_tabs<Real>(P, tid, nthreads, tabs);
   if (P.pool_elems) fill_pool<Real>(P, tid, nthreads, pool, mats, true);
+  fill_coefs<Real>(P, tid, nthreads, coef, mats, true);
+  fill_opwords(P, tid, nthreads, words);
+  __shared__ double gscale_sh;
+  if (tid == 0) gscale_sh = adjoint_scales<Real>(P, mats, want_mask, gfac);
   __syncthreads();
+  const Real gscale = Real(gscale_sh);
   for (int r = int(P.n_rounds) - 1; r >= 0; --r) {
     const b200q_round_t& Rd = P.rounds[r];
     if (Rd.direct) {
@@ -251,12 +275,17 @@ b200q_adjoint_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Rea
         __syncthreads();
       }
     } else {
-      run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tile_psi, tile_lam, pool, psi, lam, chunks_per_state,
-                              want_mask, acc);
+      run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tile_psi, tile_lam, pool, coef, words, gscale, psi, lam,
+                              chunks_per_state, want_mask, wacc);
       __syncthreads();
     }
   }
-  if (want_mask) flush_grad(P, tid, nthreads, want_mask, acc, grad, [](double* p, double v) { atomicAdd(p, v); });
+  if (want_mask) {
+    merge_warp_acc(P, tid, nthreads, nthreads / 32, wacc, acc);
+    __syncthreads();
+  }
+  if (want_mask)
+    flush_grad(P, tid, nthreads, want_mask, acc, gfac, grad, [](double* p, double v) { atomicAdd(p, v); });
 }
 
 template <typename Real, int CB>
@@ -264,8 +293,7 @@ int launch_adjoint_pass(const b200q_pass_t& P, void* psi, void* lam, const void*
                         int n_qubits, cudaStream_t stream) {
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
-  const size_t smem = (size_t(32) << CB) + size_t(B200Q_POOL_MAX) * sizeof(cx<Real>) +
-                      size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP * sizeof(double) + sizeof(RoundTab) * B200Q_MAX_ROUNDS;
+  const size_t smem = AdjSmem<Real, CB>::kTotal;
   auto kern = b200q_adjoint_kernel<Real, CB>;
   static bool attr_set[64] = {false};
   int dev = 0;

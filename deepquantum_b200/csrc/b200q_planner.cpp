@@ -47,7 +47,11 @@ struct Builder {
   //   mode 2: direct round (only MATK gates execute; register kinds block)
   // strict_x: an X gate whose control is a register slot needs a physical amplitude swap (~100 MOVs) instead of
   // the free relabelling; in strict mode such gates wait for a round where the control is thread-level.
-  int scan(uint64_t allowed, int mode, int limit, int pool_left, std::vector<int>* out, bool strict_x = false) const {
+  // avoid_rr: a diagonal gate with two (or more) selectors on register slots has no in-place code path (it runs
+  // through the generic diagonal of the non-lean kernel); diagonal gates can run in ANY round, so it waits for a
+  // round where at most one of its qubits is a register slot.
+  int scan(uint64_t allowed, int mode, int limit, int pool_left, std::vector<int>* out, bool strict_x = false,
+           bool avoid_rr = false) const {
     uint64_t bfull = 0, bdiag = 0;
     int cnt = 0, visited = 0;
     for (int i = first_undone; i < (int)g.size(); ++i) {
@@ -59,6 +63,7 @@ struct Builder {
       if (ok && mode == 1 && !a.reg_kind) ok = false;
       if (ok && strict_x && a.op_kind == B200Q_OP_X && (a.ctrl & allowed)) ok = false;
       if (ok && mode == 2 && a.reg_kind) ok = false;
+      if (ok && avoid_rr && mode == 1 && a.op_kind == B200Q_OP_DIAG && popc((a.dmask & ~a.ctrl) & allowed) >= 2) ok = false;
       if (ok && a.pool > pool_left) ok = false;
       if (ok) {
         ++cnt;
@@ -214,20 +219,20 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     int n_ops = 0, pool = 0, n_rounds = 0, gates_in_pass = 0;
 
     // choose the register slots of one round; returns physical-bit mask R and the executable gates
-    auto choose_round_impl = [&](bool restricted, bool strict, uint64_t* R_out, std::vector<int>* list) {
+    auto choose_round_impl = [&](bool restricted, bool strict, bool avoid_rr, uint64_t* R_out, std::vector<int>* list) {
       const int limit = op_cap - gates_in_pass;
       const int pool_left = B200Q_POOL_MAX - pool;
       uint64_t R = B.vs ? 1ull : 0ull;
       uint64_t cand = 0;
       for (int j = B.vs; j < t_eff; ++j)
         if (!restricted || j >= min_loc) cand |= 1ull << P.tile_phys[j];
-      int cnt = limit > 0 ? B.scan(R, 1, limit, pool_left, nullptr, strict) : 0;
+      int cnt = limit > 0 ? B.scan(R, 1, limit, pool_left, nullptr, strict, avoid_rr) : 0;
       for (int s = 0; s < B.rc && limit > 0; ++s) {
         int best = -1, bestc = cnt;
         for (int j = B.vs; j < t_eff; ++j) {
           const uint64_t bit = 1ull << P.tile_phys[j];
           if (!(cand & bit) || (R & bit)) continue;
-          const int c = B.scan(R | bit, 1, limit, pool_left, nullptr, strict);
+          const int c = B.scan(R | bit, 1, limit, pool_left, nullptr, strict, avoid_rr);
           if (c > bestc) { bestc = c; best = j; }
         }
         if (best < 0) break;
@@ -244,11 +249,13 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         if (!(R & bit)) R |= bit;
       }
       list->clear();
-      if (limit > 0) B.scan(R, 1, limit, pool_left, list, strict);
+      if (limit > 0) B.scan(R, 1, limit, pool_left, list, strict, avoid_rr);
       *R_out = R;
     };
     auto choose_round = [&](bool restricted, uint64_t* R_out, std::vector<int>* list) {
-      choose_round_impl(restricted, false, R_out, list);  // strict X placement fragments rounds (153 -> 285): off
+      // strict X placement fragments rounds (153 -> 285): off
+      choose_round_impl(restricted, false, B.opt.structured != 0, R_out, list);
+      if (list->empty() && B.opt.structured) choose_round_impl(restricted, false, false, R_out, list);
     };
 
     auto is_restricted_ok = [&](uint64_t R) {

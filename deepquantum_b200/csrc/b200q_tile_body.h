@@ -743,9 +743,9 @@ B200Q_HD bool code_is_had(int code) { return code >= B200Q_CODE_MAT1_HAD && code
 
 // effective 2x2 entry (row-major idx) of a MAT1 op for flip state f, adjoint folded in
 template <typename Real>
-B200Q_HD cx<Real> mat1_entry(const b200q_op_t& op, const cx<Real>* mats, int idx, int f) {
+B200Q_HD cx<Real> mat1_entry(const b200q_op_t& op, const cx<Real>* mats, int idx, int f, bool flip_adjoint = false) {
   if (f) idx ^= 3;   // X M X: entry (r, c) -> (r^1, c^1)
-  const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+  const bool adj = ((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint;
   if (adj && (idx == 1 || idx == 2)) idx ^= 3;   // transpose
   cx<Real> v = mats[op.mat_src + idx];
   if (adj) v.y = -v.y;
@@ -772,15 +772,17 @@ B200Q_HD void phase_shears(cx<Real> d, Real* out) {
   out[0] = t; out[1] = s; out[2] = mode; out[3] = Real(0);
 }
 
+// `flip_adjoint`: build the records of U^dagger for every op (the reverse sweep).
 template <typename Real>
-B200Q_HD void fill_coefs(const b200q_pass_t& P, int tid, int nthreads, Real* coef, const cx<Real>* mats) {
+B200Q_HD void fill_coefs(const b200q_pass_t& P, int tid, int nthreads, Real* coef, const cx<Real>* mats,
+                         bool flip_adjoint = false) {
   for (int e = tid; e < int(P.n_ops) * 2; e += nthreads) {
     const int o = e >> 1, f = e & 1;
     const b200q_op_t& op = P.ops[o];
     Real* k = coef + o * B200Q_COEF_PER_OP + f * B200Q_COEF_PER_FLIP;
     if (op.kind == B200Q_OP_DIAG) {
       // [0..15]: shear entries (t, s, mode, 0) of the 4 diagonal values; [16..23]: the raw values
-      const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+      const bool adj = ((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint;
       const int dim = 1 << int(op.k);
       for (int i = 2 * f; i < 2 * f + 2; ++i) {
         cx<Real> d;
@@ -793,8 +795,8 @@ B200Q_HD void fill_coefs(const b200q_pass_t& P, int tid, int nthreads, Real* coe
       continue;
     }
     if (op.kind != B200Q_OP_MAT1) continue;
-    const cx<Real> m00 = mat1_entry(op, mats, 0, f), m01 = mat1_entry(op, mats, 1, f);
-    const cx<Real> m10 = mat1_entry(op, mats, 2, f), m11 = mat1_entry(op, mats, 3, f);
+    const cx<Real> m00 = mat1_entry(op, mats, 0, f, flip_adjoint), m01 = mat1_entry(op, mats, 1, f, flip_adjoint);
+    const cx<Real> m10 = mat1_entry(op, mats, 2, f, flip_adjoint), m11 = mat1_entry(op, mats, 3, f, flip_adjoint);
     if (code_is_rot(op.code)) {
       const bool isx = op.code < B200Q_CODE_MAT1_ROTY;
       const Real sg = m00.x < Real(0) ? Real(-1) : Real(1);
@@ -1364,18 +1366,120 @@ inline void cta_accumulate(double* cta_acc, const double* v) {
 }
 #endif
 
+// Per-warp accumulators (one slice of shared memory per warp): warp-reduce, lane 0 adds WITHOUT an atomic
+// (shared-memory double atomics are compare-and-swap loops: they were 11 % of the reverse sweep's samples).
+// `warp_accumulate_idx`: only entry pair `idx` of the thread is non-zero (thread-level diagonal); when the
+// whole warp agrees on idx (selectors outside the lane bits, 2/3 of the cases) two reductions replace eight.
+#if defined(__CUDA_ARCH__)
+template <int NV>
+__device__ __forceinline__ void warp_accumulate(double* warp_acc, const double* v) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_acc[k] += s;
+  }
+}
+__device__ __forceinline__ void warp_accumulate_idx(double* warp_acc, uint32_t idx, bool on, double sr, double si) {
+  int uniform;
+  __match_all_sync(0xffffffffu, on ? idx : 0xffu, &uniform);
+  if (uniform) {
+    if (!on) return;
+    double v[2] = {sr, si};
+    warp_accumulate<2>(warp_acc + 2 * idx, v);
+  } else {
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (on) { v[2 * idx] = sr; v[2 * idx + 1] = si; }
+    warp_accumulate<8>(warp_acc, v);
+  }
+}
+#else
+template <int NV>
+inline void warp_accumulate(double* warp_acc, const double* v) {
+  for (int k = 0; k < NV; ++k) warp_acc[k] += v[k];
+}
+inline void warp_accumulate_idx(double* warp_acc, uint32_t idx, bool on, double sr, double si) {
+  if (on) { warp_acc[2 * idx] += sr; warp_acc[2 * idx + 1] += si; }
+}
+#endif
+#define B200Q_WACC_PER_OP 8
+
+// ---- reverse sweep on the lean op set ---------------------------------------------------------------------
+// U^dagger is applied with the same in-place ops as the forward kernel (records built with flip_adjoint).
+// Two things may stay PENDING on the pair (psi, lambda), because the cotangent G = lambda (x) conj(psi) of the
+// other ops does not care or can be fixed afterwards:
+//   * a common unit-modulus phase `rho` per thread (thread-level diagonals, signs of controlled rotations):
+//     both states carry it, it cancels in lambda * conj(psi); applied once per round;
+//   * the real scalar x of every Hadamard-structured op (applied as the bare add/sub butterfly): op o then sees
+//     psi and lambda both short of  prod x_j  over the Hadamard ops j > o of the pass -- its G is multiplied by
+//     gfac[o] = prod x_j^2 at flush time, the states by the full product in the last (global) round.
+// Hadamard ops whose own gradient is requested take the general (scaled) path and do not count.
+
+// gfac[o] for every op of the pass; returns the scalar the states are short of at the end of the pass
+template <typename Real>
+B200Q_HD double adjoint_scales(const b200q_pass_t& P, const cx<Real>* mats, uint64_t want_mask, double* gfac) {
+  double g = 1.0, sign = 1.0;
+  for (int o = int(P.n_ops) - 1; o >= 0; --o) {
+    gfac[o] = g * g;
+    const b200q_op_t& op = P.ops[o];
+    if (code_is_had(op.code) && !((want_mask >> o) & 1ull)) g *= double(mats[op.mat_src].x);
+    else if (code_is_rot(op.code) && !op.tctrl && mats[op.mat_src].x < Real(0)) sign = -sign;
+  }
+  return g * sign;
+}
+
+// (sr, si) = sum over the elements e with ((e >> S) & 1) == H (S < 0: all) of lambda_e * conj(psi_e)
+template <typename V, int S, int H>
+B200Q_HD void dot_lam_conj_psi(const V* pr, const V* pi, const V* lr, const V* li, double& sr, double& si) {
+  V ar = vzero((V*)nullptr), ai = vzero((V*)nullptr);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    if (S >= 0 && ((e >> (S < 0 ? 0 : S)) & 1) != H) continue;
+    ar = vfma(li[e], pi[e], vfma(lr[e], pr[e], ar));
+    ai = vfma(vneg(lr[e]), pi[e], vfma(li[e], pr[e], ai));
+  }
+  sr = vhsum(ar); si = vhsum(ai);
+}
+
+template <typename Real, int S>
+B200Q_HD void diag_reg_adjoint(const b200q_pass_t& P, const OpWord& w, typename Traits<Real>::V* pr,
+                               typename Traits<Real>::V* pi, typename Traits<Real>::V* lr,
+                               typename Traits<Real>::V* li, const Real* rec, uint32_t lb, uint64_t cta_base,
+                               uint32_t xm, bool want, double* acc) {
+  using V = typename Traits<Real>::V;
+  const int j = (w.x >> 8) & 1, other = j ^ 1;
+  const uint32_t base = dsel_value(P, w, other, lb, cta_base) << other;
+  const uint32_t f = (xm >> S) & 1u;
+  const uint32_t i0 = base | (f << j), i1 = base | ((f ^ 1u) << j);
+  diag_half<Real, S, 0>(pr, pi, rec + 4 * i0, rec + 16 + 2 * i0);
+  diag_half<Real, S, 1>(pr, pi, rec + 4 * i1, rec + 16 + 2 * i1);
+  if (want) {   // G[idx] = sum lambda_out conj(psi_in) over the half with selector value idx
+    double sr, si;
+    dot_lam_conj_psi<V, S, 0>(pr, pi, lr, li, sr, si);
+    acc[2 * i0] += sr; acc[2 * i0 + 1] += si;
+    dot_lam_conj_psi<V, S, 1>(pr, pi, lr, li, sr, si);
+    acc[2 * i1] += sr; acc[2 * i1 + 1] += si;
+  }
+  diag_half<Real, S, 0>(lr, li, rec + 4 * i0, rec + 16 + 2 * i0);
+  diag_half<Real, S, 1>(lr, li, rec + 4 * i1, rec + 16 + 2 * i1);
+}
+
 // One register round of the reverse sweep.  The roles of src/dst (and of the pass layouts) are
 // swapped with respect to the forward round.  Every thread of the CTA must call this (the gradient
-// reduction inside is warp-collective).
+// reduction inside is warp-collective).  `coef`: records of U^dagger (fill_coefs with flip_adjoint);
+// `gscale`: adjoint_scales(), applied by the round that writes back to global memory.
 template <typename Real>
 B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, const RoundTab& T, int tid,
                                 uint64_t cta_base,
                                 typename Traits<Real>::chunk* tile_psi, typename Traits<Real>::chunk* tile_lam,
-                                const cx<Real>* pool, typename Traits<Real>::chunk* gpsi,
+                                const cx<Real>* pool, const Real* coef, const OpWord* words, Real gscale,
+                                typename Traits<Real>::chunk* gpsi,
                                 typename Traits<Real>::chunk* glam, uint64_t total_chunks, uint64_t want_mask,
-                                double* cta_acc) {
+                                double* wacc_base) {
   using V = typename Traits<Real>::V;
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
+  double* wacc = wacc_base + size_t(tid >> 5) * (B200Q_MAX_OPS * B200Q_WACC_PER_OP);   // this warp's slice
   V pr[NE], pi[NE], lr[NE], li[NE];
   uint32_t xm = 0;
   constexpr int VS_ = Traits<Real>::VS;
@@ -1391,13 +1495,86 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
   }
   Real dummy_r = Real(1), dummy_i = Real(0);
   bool dummy_d = false;
+  Real rho_r = Real(1), rho_i = Real(0);   // pending common phase of (psi, lambda)
+  bool rho_dirty = false;
   for (int o = int(Rd.op_end) - 1; o >= int(Rd.op_begin); --o) {
     const b200q_op_t& op = P.ops[o];
     if ((cta_base & op.ctrl_glob) != op.ctrl_glob) continue;   // CTA-uniform
     const bool on = A.active && ((A.lb & op.ctrl_loc) == op.ctrl_loc);
     const bool want = (want_mask >> o) & 1ull;
     const cx<Real>* w = pool + op.pool_off;
+    const OpWord cur = words[o];
+    const Real* rec = coef + o * B200Q_COEF_PER_OP;
+    const uint32_t code = op.code;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define B200Q_KREC(S) (rec + ((xm >> S) & 1u) * B200Q_COEF_PER_FLIP)
+#define B200Q_ADJ_ROT(S, ISX)                                                                  \
+  {                                                                                            \
+    if (on) {                                                                                  \
+      bool neg;                                                                                \
+      rot_fast<Real, S, ISX>(pr, pi, B200Q_KREC(S), neg);                                      \
+      if (want) accum_mat1<Real>(op, xm, pr, pi, lr, li, acc);                                 \
+      if (want && neg) {   /* psi already carries the sign of the negated matrix, lambda not yet */ \
+        for (int k = 0; k < 8; ++k) acc[k] = -acc[k];                                          \
+      }                                                                                        \
+      rot_fast<Real, S, ISX>(lr, li, B200Q_KREC(S), neg);                                      \
+      if (neg && op.tctrl) { rho_r = -rho_r; rho_i = -rho_i; rho_dirty = true; }               \
+    }                                                                                          \
+    if (want) warp_accumulate<8>(wacc + o * B200Q_WACC_PER_OP, acc);                          \
+  }
+#define B200Q_ADJ_PERSLOT(S)                                                                   \
+  case B200Q_CODE_MAT1_HAD + S:                                                                \
+    if (on) { had_fast<Real, S>(pr, pi, ((xm >> S) & 1u) != 0); had_fast<Real, S>(lr, li, ((xm >> S) & 1u) != 0); } \
+    break;                                                                                     \
+  case B200Q_CODE_MAT1_ROTX + S: B200Q_ADJ_ROT(S, true) break;                                 \
+  case B200Q_CODE_MAT1_ROTY + S: B200Q_ADJ_ROT(S, false) break;                                \
+  case B200Q_CODE_DIAG_R + S:                                                                  \
+    if (on) diag_reg_adjoint<Real, S>(P, cur, pr, pi, lr, li, rec, A.lb, cta_base, xm, want, acc); \
+    if (want) warp_accumulate<8>(wacc + o * B200Q_WACC_PER_OP, acc);                          \
+    break;                                                                                     \
+  case B200Q_CODE_LSWAP + S:                                                                   \
+    if (A.active) { uint32_t xm2 = xm; lane_swap<V, S>(pr, pi, xm); lane_swap<V, S>(lr, li, xm2); } \
+    break;
+    const bool lean_had = code_is_had(int(code)) && !want;
+    if (code < B200Q_CODE_X_RELABEL && (lean_had || !code_is_had(int(code)))) {
+      switch (code) {
+        B200Q_ADJ_PERSLOT(0) B200Q_ADJ_PERSLOT(1) B200Q_ADJ_PERSLOT(2) B200Q_ADJ_PERSLOT(3)
+        default: break;
+      }
+      continue;
+    }
+#undef B200Q_ADJ_PERSLOT
+#undef B200Q_ADJ_ROT
+#undef B200Q_KREC
+    if (code == B200Q_CODE_X_RELABEL) {
+      if (on) xm ^= 1u << ((cur.x >> 8) & 3u);
+      continue;
+    }
+    if (code == B200Q_CODE_X_C1) {
+      if (on) { x_c1<V>(int((cur.x >> 8) & 15u), pr, pi, xm); x_c1<V>(int((cur.x >> 8) & 15u), lr, li, xm); }
+      continue;
+    }
+    if (code == B200Q_CODE_X_LANE) {
+      if (on) { const uint32_t cm = (cur.x >> 8) & 15u; x_lane(pr, pi, cm, cm & ~xm); x_lane(lr, li, cm, cm & ~xm); }
+      continue;
+    }
+    if (code == B200Q_CODE_DIAG_T) {
+      const uint32_t idx = dsel_value(P, cur, 0, A.lb, cta_base) | (dsel_value(P, cur, 1, A.lb, cta_base) << 1);
+      double gr = 0.0, gi = 0.0;
+      if (on) {
+        const Real dr = rec[16 + 2 * idx], di = rec[17 + 2 * idx];   // entry of U^dagger = conj(d)
+        if (want) {   // G[idx] = d * sum lambda conj(psi)  (the pending phases cancel)
+          double sr, si;
+          dot_lam_conj_psi<V, -1, 0>(pr, pi, lr, li, sr, si);
+          gr = double(dr) * sr + double(di) * si;
+          gi = double(dr) * si - double(di) * sr;
+        }
+        const Real r = rho_r * dr - rho_i * di, im2 = rho_r * di + rho_i * dr;
+        rho_r = r; rho_i = im2; rho_dirty = true;
+      }
+      if (want) warp_accumulate_idx(wacc + o * B200Q_WACC_PER_OP, idx, on, gr, gi);
+      continue;
+    }
     switch (op.kind) {
       case B200Q_OP_MAT1:
         if (on) {
@@ -1405,7 +1582,7 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
           if (want) accum_mat1<Real>(op, xm, pr, pi, lr, li, acc);
           apply_mat1<Real>(op, lr, li, w, xm);
         }
-        if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
+        if (want) warp_accumulate<8>(wacc + o * B200Q_WACC_PER_OP, acc);
         break;
       case B200Q_OP_X:
         if (on) { uint32_t xm2 = xm; apply_x<Real>(op, pr, pi, xm); apply_x<Real>(op, lr, li, xm2); }
@@ -1428,13 +1605,19 @@ B200Q_HD void run_round_adjoint(const b200q_pass_t& P, const b200q_round_t& Rd, 
           if (want) accum_diag<Real>(op, tsel, xm, pr, pi, lr, li, acc);
           apply_diag<Real, false>(op, lr, li, w, tsel, xm, dummy_r, dummy_i, dummy_d);
         }
-        if (want) cta_accumulate<8>(cta_acc + o * B200Q_ACC_PER_OP, acc);
+        if (want) warp_accumulate<8>(wacc + o * B200Q_WACC_PER_OP, acc);
         break;
       }
       default: break;
     }
   }
   if (!A.active) return;
+  if (Rd.src_global && gscale != Real(1)) { rho_r *= gscale; rho_i *= gscale; rho_dirty = true; }
+  if (rho_dirty) {
+    const V qr = vset(rho_r, (V*)nullptr), qi = vset(rho_i, (V*)nullptr), nqi = vset(-rho_i, (V*)nullptr);
+#pragma unroll
+    for (int c = 0; c < NE; ++c) { cmul_inplace(pr[c], pi[c], qr, qi, nqi); cmul_inplace(lr[c], li[c], qr, qi, nqi); }
+  }
   scatter<Real>(A, T, Rd.src_global, soa_out, tile_psi, gpsi, total_chunks, true, xm, pr, pi);
   scatter<Real>(A, T, Rd.src_global, soa_out, tile_lam, glam, total_chunks, true, xm, lr, li);
 }
@@ -1522,11 +1705,22 @@ B200Q_HD void run_direct_op_adjoint(const b200q_pass_t& P, const b200q_op_t& op,
   }
 }
 
+// Add the per-warp accumulators of the register rounds into the CTA accumulator (entries 0..7 of every op).
+B200Q_HD void merge_warp_acc(const b200q_pass_t& P, int tid, int nthreads, int nwarps, const double* wacc,
+                             double* cta_acc) {
+  for (int e = tid; e < int(P.n_ops) * B200Q_WACC_PER_OP; e += nthreads) {
+    const int o = e / B200Q_WACC_PER_OP, k = e % B200Q_WACC_PER_OP;
+    double v = 0.0;
+    for (int w = 0; w < nwarps; ++w) v += wacc[size_t(w) * (B200Q_MAX_OPS * B200Q_WACC_PER_OP) + e];
+    cta_acc[o * B200Q_ACC_PER_OP + k] += v;
+  }
+}
+
 // Flush one CTA's accumulators into the global gradient buffer (complex128, laid out like the
 // matrix buffer).  `add(ptr, v)` is atomicAdd on the device.
 template <typename AddFn>
 B200Q_HD void flush_grad(const b200q_pass_t& P, int tid, int nthreads, uint64_t want_mask, const double* cta_acc,
-                         double* grad, AddFn add) {
+                         const double* gfac, double* grad, AddFn add) {
   for (int e = tid; e < int(P.n_ops) * B200Q_ACC_PER_OP; e += nthreads) {
     const int o = e / B200Q_ACC_PER_OP, q = e % B200Q_ACC_PER_OP;
     if (!((want_mask >> o) & 1ull)) continue;
@@ -1548,7 +1742,7 @@ B200Q_HD void flush_grad(const b200q_pass_t& P, int tid, int nthreads, uint64_t 
     } else {
       continue;
     }
-    double v = cta_acc[e];
+    double v = cta_acc[e] * gfac[o];
     if (adj && comp == 1) v = -v;   // grad wrt M where U = M^dagger: conjugate (and transpose above)
     if (v != 0.0) add(grad + 2 * (uint64_t(op.mat_src) + dst) + comp, v);
   }

@@ -71,7 +71,9 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
   const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
   std::vector<chunk> tp(size_t(1) << cb), tl(size_t(1) << cb);
   std::vector<cx<Real>> pool(B200Q_POOL_MAX);
-  std::vector<double> acc(size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP);
+  std::vector<double> acc(size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP), gfac(B200Q_MAX_OPS);
+  std::vector<Real> coef(size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP);
+  std::vector<OpWord> words(B200Q_MAX_OPS + 1);
   const uint64_t chunks_per_state = (1ull << pl.n_qubits) >> VS;
   const uint64_t ntiles = 1ull << (int(P.n_bits) - int(P.tile_bits));
   uint64_t want = 0;
@@ -85,11 +87,16 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
   chunk* gpsi = reinterpret_cast<chunk*>(psi_v);
   chunk* glam = reinterpret_cast<chunk*>(lam_v);
   const cx<Real>* m = reinterpret_cast<const cx<Real>*>(mats_v);
+  for (int tid = 0; tid < nthreads; ++tid) fill_coefs<Real>(P, tid, nthreads, coef.data(), m, true);
+  for (int tid = 0; tid < nthreads; ++tid) fill_opwords(P, tid, nthreads, words.data());
+  const Real gscale = Real(adjoint_scales<Real>(P, m, want, gfac.data()));
   for (uint64_t t = 0; t < ntiles; ++t) {
     const uint64_t cta_base = tile_base(P, t);
     std::memset(tp.data(), 0xff, tp.size() * sizeof(chunk));
     std::memset(tl.data(), 0xff, tl.size() * sizeof(chunk));
     std::fill(acc.begin(), acc.end(), 0.0);
+    const int nwarps = (nthreads + 31) / 32;
+    std::vector<double> wacc(size_t(nwarps) * B200Q_MAX_OPS * B200Q_WACC_PER_OP, 0.0);
     std::vector<RoundTab> tabs(B200Q_MAX_ROUNDS);
     for (int tid = 0; tid < nthreads; ++tid) fill_round_tabs<Real>(P, tid, nthreads, tabs.data());
     if (P.pool_elems)
@@ -103,12 +110,13 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
                                         (want >> o) & 1ull, acc.data() + o * B200Q_ACC_PER_OP);
       } else {
         for (int tid = 0; tid < nthreads; ++tid)
-          run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tp.data(), tl.data(), pool.data(), gpsi, glam,
-                                  chunks_per_state, want, acc.data());
+          run_round_adjoint<Real>(P, Rd, tabs[r], tid, cta_base, tp.data(), tl.data(), pool.data(), coef.data(),
+                                  words.data(), gscale, gpsi, glam, chunks_per_state, want, wacc.data());
       }
     }
+    for (int tid = 0; tid < nthreads; ++tid) merge_warp_acc(P, tid, nthreads, nwarps, wacc.data(), acc.data());
     for (int tid = 0; tid < nthreads; ++tid)
-      flush_grad(P, tid, nthreads, want, acc.data(), grad, [](double* p, double v) { *p += v; });
+      flush_grad(P, tid, nthreads, want, acc.data(), gfac.data(), grad, [](double* p, double v) { *p += v; });
   }
 }
 }  // namespace

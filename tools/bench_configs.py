@@ -102,3 +102,5 @@ if __name__ == '__main__':
         c5()
     if 'c3' in which:
         c3()
+    if 'c3small' in which:      # profiling size
+        c3(n=24)

@@ -76,13 +76,27 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
   for (int t = threadIdx.x; t < D; t += kThreads) toff[t] = qudit_offset(g, 0, t) - expand_rest(g, 0);
   __syncthreads();
   // ---- load: element e -> (group gi, matrix digit combo t) ordered for coalescing --------------------
-  for (int e = threadIdx.x; e < total; e += kThreads) {
-    int gi, t;
-    qudit_elem(g, e, &gi, &t);
-    cxq<Real> v; v.x = v.y = Real(0);
-    const long long b = gbase[gi];
-    if (b >= 0) v = st[b + toff[t]];
-    xs[t * GP + gi] = v;
+  // (four independent global loads in flight per thread before the first shared store: the loop was
+  // latency-bound with one load per iteration -- 26 % of the samples sat on the store waiting for its load)
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kThreads) {
+    cxq<Real> v[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kThreads;
+      v[u].x = v[u].y = Real(0);
+      dst[u] = -1;
+      if (e < total) {
+        int gi, t;
+        qudit_elem(g, e, &gi, &t);
+        const long long b = gbase[gi];
+        if (b >= 0) v[u] = st[b + toff[t]];
+        dst[u] = t * GP + gi;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u] >= 0) xs[dst[u]] = v[u];
   }
   __syncthreads();
   // ---- contract: y[r][gi] = sum_j vals[r][j] * x[cols[r][j]][gi] ---------------------------------------

@@ -499,6 +499,9 @@ int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_
     if (options->reserved[0]) opt.structured = 0;   // A/B switch: general op codes only
     if (options->reserved[1]) opt.coalesce_bits = options->reserved[1] - 1;   // experiment: 1 + lane-owned chunk bits
   }
+  if (const char* e = getenv("B200Q_DEFER_DIAG")) opt.defer_diag = atoi(e);
+  if (const char* e = getenv("B200Q_MIN_ROUND_GATES")) opt.min_round_gates = atoi(e);
+  if (const char* e = getenv("B200Q_XC1_PENALTY")) opt.xc1_penalty = atoi(e);
   if (const char* e = getenv("B200Q_COALESCE_BITS")) {
     opt.coalesce_bits = atoi(e);
   }

@@ -39,6 +39,7 @@ struct Builder {
   std::vector<IGate> g;
   std::vector<char> done;
   int first_undone = 0;
+  mutable int last_xc1 = 0;   // X gates of the last scan() whose control is a register slot
   uint64_t all_bits;
 
   // Gates executable (in order) when non-diagonal targets must lie in `allowed`.
@@ -54,6 +55,7 @@ struct Builder {
            bool avoid_rr = false) const {
     uint64_t bfull = 0, bdiag = 0;
     int cnt = 0, visited = 0;
+    last_xc1 = 0;
     for (int i = first_undone; i < (int)g.size(); ++i) {
       if (done[i]) continue;
       if ((bfull & all_bits) == all_bits) break;
@@ -67,6 +69,7 @@ struct Builder {
       if (ok && a.pool > pool_left) ok = false;
       if (ok) {
         ++cnt;
+        if (mode == 1 && a.op_kind == B200Q_OP_X && (a.ctrl & allowed)) ++last_xc1;   // needs a register swap
         pool_left -= a.pool;
         if (out) out->push_back(i);
         if (cnt >= limit) break;
@@ -226,24 +229,35 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
       uint64_t cand = 0;
       for (int j = B.vs; j < t_eff; ++j)
         if (!restricted || j >= min_loc) cand |= 1ull << P.tile_phys[j];
-      int cnt = limit > 0 ? B.scan(R, 1, limit, pool_left, nullptr, strict, avoid_rr) : 0;
+      // score of a slot set: executable gates, minus a penalty per CNOT whose control is a slot too (a register
+      // swap, ~3x the cost of the relabelling it is when the control stays a thread-level bit)
+      const int W = 4, PEN = B.opt.xc1_penalty;
+      auto score = [&](uint64_t Rs) {
+        const int c = B.scan(Rs, 1, limit, pool_left, nullptr, strict, avoid_rr);
+        return W * c - PEN * B.last_xc1;
+      };
+      int cnt = limit > 0 ? score(R) : 0;
       for (int s = 0; s < B.rc && limit > 0; ++s) {
         int best = -1, bestc = cnt;
         for (int j = B.vs; j < t_eff; ++j) {
           const uint64_t bit = 1ull << P.tile_phys[j];
           if (!(cand & bit) || (R & bit)) continue;
-          const int c = B.scan(R | bit, 1, limit, pool_left, nullptr, strict, avoid_rr);
+          const int c = score(R | bit);
           if (c > bestc) { bestc = c; best = j; }
         }
         if (best < 0) break;
         R |= 1ull << P.tile_phys[best];
         cnt = bestc;
       }
-      // fill the remaining slots with the highest free candidate bits
-      for (int j = t_eff - 1; j >= B.vs && popc(R) < B.rb; --j) {
-        const uint64_t bit = 1ull << P.tile_phys[j];
-        if ((cand & bit) && !(R & bit)) R |= bit;
-      }
+      // fill the remaining slots with free candidate bits, highest first, preferring bits that do not turn a
+      // relabelling CNOT into a register swap
+      for (int pass2 = 0; pass2 < 2; ++pass2)
+        for (int j = t_eff - 1; j >= B.vs && popc(R) < B.rb; --j) {
+          const uint64_t bit = 1ull << P.tile_phys[j];
+          if (!(cand & bit) || (R & bit)) continue;
+          if (pass2 == 0 && PEN > 0 && limit > 0 && score(R | bit) < cnt) continue;
+          R |= bit;
+        }
       for (int j = t_eff - 1; j >= B.vs && popc(R) < B.rb; --j) {  // tiny tiles: take anything
         const uint64_t bit = 1ull << P.tile_phys[j];
         if (!(R & bit)) R |= bit;
@@ -280,7 +294,33 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
       for (int j = 0; j < t_eff; ++j)
         if (!(R >> P.tile_phys[j] & 1)) nr.push_back(j);
       Rd.op_begin = (uint16_t)n_ops;
+      // A 1-selector diagonal whose qubit is a register slot of THIS round costs a sweep over half the registers;
+      // outside the registers it is one scalar multiply of the thread's phase.  Diagonal gates can run in any
+      // round: leave such a gate pending (a later round / pass usually finds its qubit outside the registers)
+      // unless a later gate of this round needs it done (acts non-diagonally on its qubit).
+      std::vector<char> skip(list.size(), 0);
+      if (B.opt.structured && B.opt.defer_diag) {
+        int kept = 0;
+        for (size_t li = 0; li < list.size(); ++li) {
+          const IGate& a = B.g[list[li]];
+          bool defer = false;
+          if (a.op_kind == B200Q_OP_DIAG && a.ctrl == 0) {
+            int nreg = 0;
+            for (int j = 0; j < a.k; ++j) nreg += slot_of[a.t[j]] >= 0;
+            if (nreg >= 1) {
+              defer = true;
+              for (size_t lj = li + 1; lj < list.size() && defer; ++lj)
+                if (B.g[list[lj]].tmask & a.dmask) defer = false;
+            }
+          }
+          skip[li] = defer;
+          kept += !defer;
+        }
+        if (kept == 0) std::fill(skip.begin(), skip.end(), 0);
+      }
+      size_t list_pos = 0;
       for (int gi : list) {
+        if (skip[list_pos++]) continue;
         const IGate& a = B.g[gi];
         b200q_op_t op;
         std::memset(&op, 0, sizeof(op));
@@ -440,6 +480,18 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         continue;
       }
       choose_round(false, &R, &list);
+      if (!list.empty() && B.opt.structured && B.opt.defer_diag >= 2) {
+        // a round of diagonal gates only is not worth a transpose of the tile: they run (for free) in the
+        // first round of the next pass, or in this pass's write-back round if one has to be added anyway
+        bool only_diag = true;
+        for (int gi : list) only_diag = only_diag && B.g[gi].op_kind == B200Q_OP_DIAG;
+        if (only_diag) break;
+      }
+      // a late round with very few gates costs a whole tile transpose: end the pass instead, the next pass picks
+      // tile bits and slots afresh
+      if (!list.empty() && n_rounds >= 2 && (int)list.size() < B.opt.min_round_gates &&
+          gates_in_pass >= 4 * B.opt.min_round_gates)
+        break;
       if (!list.empty()) {
         last = emit_round(R, list, false);
         last_restricted_ok = is_restricted_ok(R);

@@ -19,6 +19,11 @@ struct PlanOptions {
   int coalesce_bits = 1;  // chunk-index bits that stay lane bits in the rounds that touch global memory (1: every
                           // warp-level access uses whole 32-byte sectors; measured equal to 3 = 128-byte runs, with
                           // fewer rounds: a single gate on a low qubit is then ONE round at the copy bandwidth)
+  int defer_diag = 2;     // 1: leave register-slot diagonals pending when nothing in the round depends on them;
+                          // 2: and never spend a round on diagonal gates alone (measured +4.6 % on C2)
+  int min_round_gates = 4;  // a later round with fewer executable gates ends the pass (1: off; measured +2 % on C2)
+  int xc1_penalty = 0;    // slot choice: penalty (in quarter gates) per CNOT whose control becomes a register slot
+                          // (measured neutral on C2: fewer register swaps, more rounds; off)
   int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
 };
 

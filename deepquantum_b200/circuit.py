@@ -183,7 +183,18 @@ class QubitCircuit(Operation):
             assert len(data) >= self.ndata, 'The circuit needs more data, or consider data re-uploading'
         count = 0
         ndat = len(data)
+        singles = data.split(1) if isinstance(data, torch.Tensor) and data.ndim == 1 else None   # all [1] views at once
         for op in self.encoders:
+            # fast path (hundreds of one-parameter encoder gates per forward): same effect as op.init_para(data[i:i+1])
+            # for a buffer-backed parameter, without nn.Module.__setattr__ / register_buffer per gate
+            if (singles is not None and op.npara == 1 and count < ndat and getattr(op, '_fast_encode', False)
+                    and not op.requires_grad and 'theta' in op._buffers):
+                op._batched = None
+                op._buffers['theta'] = singles[count]
+                op.__dict__['_matrix_cache'] = None
+                op._data_ref = (data, (count,))
+                count = (count + 1) % ndat
+                continue
             count_up = count + op.npara
             if self.reupload and count_up > ndat:
                 n = int(np.ceil(count_up / ndat))

@@ -83,6 +83,7 @@ class _Parametric:
 
     _matrix_source = 'group'
     _pnames = ('theta',)
+    _fast_encode = True      # QubitCircuit.encode may set the buffer directly (classes overriding init_para opt out)
 
     def _setup_parametric(self, inputs, requires_grad):
         self.npara = len(self._pnames)
@@ -219,6 +220,8 @@ class U3Gate(ParametricSingleGate):
         for x in inputs:
             out.append(x if isinstance(x, (torch.Tensor, nn.Parameter)) else torch.tensor(x, dtype=torch.float))
         return tuple(out)
+
+    _fast_encode = False
 
     def init_para(self, inputs: Any = None) -> None:
         self._batched = None

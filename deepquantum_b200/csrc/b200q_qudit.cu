@@ -27,6 +27,7 @@ namespace {
 
 constexpr int kMaxD = 256;      // d^k of the gate
 constexpr int kThreads = 256;
+constexpr int kLoadUnroll = 4;
 
 template <typename Real> struct cxq { Real x, y; };
 
@@ -76,13 +77,14 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
   for (int t = threadIdx.x; t < D; t += kThreads) toff[t] = qudit_offset(g, 0, t) - expand_rest(g, 0);
   __syncthreads();
   // ---- load: element e -> (group gi, matrix digit combo t) ordered for coalescing --------------------
-  // (four independent global loads in flight per thread before the first shared store: the loop was
-  // latency-bound with one load per iteration -- 26 % of the samples sat on the store waiting for its load)
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kThreads) {
-    cxq<Real> v[4];
-    int dst[4];
+  // (kLoadUnroll independent global loads in flight per thread before the first shared store: with one load per
+  // iteration the loop was latency-bound -- 26 % of the samples sat on the store waiting for its load -- and a
+  // B200 needs ~40 KB in flight per SM to reach its HBM bandwidth)
+  for (int e0 = threadIdx.x; e0 < total; e0 += kLoadUnroll * kThreads) {
+    cxq<Real> v[kLoadUnroll];
+    int dst[kLoadUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kLoadUnroll; ++u) {
       const int e = e0 + u * kThreads;
       v[u].x = v[u].y = Real(0);
       dst[u] = -1;
@@ -95,7 +97,7 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < kLoadUnroll; ++u)
       if (dst[u] >= 0) xs[dst[u]] = v[u];
   }
   __syncthreads();

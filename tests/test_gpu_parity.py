@@ -363,3 +363,50 @@ def test_sharded_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'SHARDED_OK' in out.stdout
+
+
+@pytest.mark.parametrize('structured', [True, False])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_structured_and_general_op_codes(cdtype, structured):
+    """The lean op set (Hadamard add/sub, three-shear rotations, shear phases, lane transpositions, xor swaps)
+    and the general fallbacks of the non-lean kernel, on the same circuit, against the oracle: rotations over
+    the full 4*pi period, gates on index bit 0 (the complex64 lane), thread-level and register-slot controls,
+    1- and 2-selector diagonals."""
+    n = 17
+    rng = np.random.default_rng(23)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+    ops = []
+    for _ in range(220):
+        w = int(rng.integers(n))
+        c = int((w + 1 + rng.integers(n - 1)) % n)
+        if rng.integers(5) == 0:
+            w, c = n - 1, int(rng.integers(n - 1))
+        elif rng.integers(5) == 0:
+            c, w = n - 1, int(rng.integers(n - 1))
+        th = float(rng.uniform(0, 4 * np.pi))
+        kind = int(rng.integers(10))
+        if kind == 0:
+            ops.append((gates_np.H, [w], []))
+        elif kind == 1:
+            ops.append((gates_np.rx(th), [w], []))
+        elif kind == 2:
+            ops.append((gates_np.ry(th), [w], []))
+        elif kind == 3:
+            ops.append((gates_np.X, [w], [c]))
+        elif kind == 4:
+            ops.append((gates_np.rx(th), [w], [c]))
+        elif kind == 5:
+            ops.append((gates_np.S, [w], []))
+        elif kind == 6:
+            ops.append((gates_np.rz(th), [w], [c] if rng.integers(2) else []))
+        elif kind == 7:
+            ops.append((gates_np.rzz(th), [c, w], []))
+        elif kind == 8:
+            ops.append((gates_np.H, [w], [c]))
+        else:
+            ops.append((gates_np.rx(th).conj().T, [w], []))
+    ref = so.run_circuit(ops, n, psi)
+    out, plan = _run_ops_gpu(ops, n, cdtype, state=psi, structured=structured)
+    err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
+    assert err < TOL[cdtype], (err, plan.stats)

@@ -102,6 +102,11 @@ def run(args):
                                    f'over {world} ranks ({nl} local qubits); same circuit as the 1-GPU headline',
                        'gates': ngates, 'local_passes': st['passes'], 'segments': st['segments'],
                        'block_transposes': st['swaps'], 'shard_bytes': shard_bytes,
+                       'fused_pass_exchanges': getattr(cir._sharded, 'fused_exchanges', 0),
+                       'exchange_path': ('last pass of each segment stores into the peers\' receive buffers over NVLink '
+                                         '(symmetric memory), one 4-byte all-reduce per transpose'
+                                         if getattr(cir._sharded, 'fused_exchanges', 0) else
+                                         'NCCL grouped send/recv: ' + str(cir.state.__dict__.get('_peer_error', ''))),
                        'l2': 'every pass streams the whole shard; shard > L2 for n_local >= 25 complex64',
                        'ms_local_kernels': float(parts[0]) / args.steps, 'ms_exchange': float(parts[1]) / args.steps,
                        'exchange_bytes_per_rank_per_transpose': shard_bytes * (world - 1) // world},

@@ -70,7 +70,7 @@ template <typename Real, int CB, bool LEAN>
 __global__ void __launch_bounds__(TileCfg<CB>::kThreads, FwdCfg<Real, CB, LEAN>::kMinBlocks)
 b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>::chunk* __restrict__ state,
                   const cx<Real>* __restrict__ mats, uint64_t chunks_per_state, int64_t mat_batch_stride,
-                  uint32_t tile_shift, uint64_t n_work) {
+                  uint32_t tile_shift, uint64_t n_work, const __grid_constant__ b200q_remote_t remote) {
   using chunk = typename Traits<Real>::chunk;
   using SM = TileSmem<Real, CB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +129,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
         }
       } else {
         run_round<Real, LEAN>(P, Rd, tabs[r], tid, cta_base, enabled, tile, pool, coef, words, gscale, gstate,
-                              chunks_per_state);
+                              chunks_per_state, &remote);
         if (r + 1 < nr) __syncthreads();
       }
     }
@@ -148,9 +148,14 @@ inline int sm_count(int dev) {
   return cache[dev];
 }
 
+static_assert(sizeof(b200q_pass_t) + sizeof(b200q_remote_t) + 64 <= 4096, "kernel parameters must stay below 4 KB");
+
 template <typename Real, int CB>
 int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubits, int64_t batch,
-                int64_t mat_batch_stride, cudaStream_t stream) {
+                int64_t mat_batch_stride, cudaStream_t stream, const b200q_remote_t* remote_in = nullptr) {
+  b200q_remote_t remote;
+  std::memset(&remote, 0, sizeof remote);
+  if (remote_in) remote = *remote_in;
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
   const size_t smem_max = TileSmem<Real, CB>::kTotal;
@@ -186,7 +191,7 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
     dim3 grid((unsigned)std::min<uint64_t>(n_work, resident), 1, 1);
     kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(P, reinterpret_cast<chunk*>(state),
                                                         reinterpret_cast<const cx<Real>*>(mats), chunks_per_state, 0,
-                                                        (uint32_t)tile_shift, n_work);
+                                                        (uint32_t)tile_shift, n_work, remote);
   } else {
     const uint64_t gx = std::min<uint64_t>(ntiles, std::max<uint64_t>(1, resident / uint64_t(std::min<int64_t>(batch, (int64_t)resident))));
     for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
@@ -195,26 +200,26 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
       kern<<<grid, TileCfg<CB>::kThreads, smem, stream>>>(
           P, reinterpret_cast<chunk*>(state) + uint64_t(b0) * chunks_per_state,
           reinterpret_cast<const cx<Real>*>(mats) + b0 * mat_batch_stride, chunks_per_state, mat_batch_stride,
-          (uint32_t)tile_shift, ntiles);
+          (uint32_t)tile_shift, ntiles, remote);
     }
   }
   return cuda_err(cudaGetLastError(), "tile kernel launch");
 }
 
 int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const void* mats, int64_t batch,
-                    int64_t mbs, cudaStream_t stream) {
+                    int64_t mbs, cudaStream_t stream, const b200q_remote_t* remote = nullptr) {
   const int cb = pl.opt.chunk_bits;
   if (pl.dtype == B200Q_C64) {
     switch (cb) {
-      case 11: return launch_pass<float, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream);
-      case 12: return launch_pass<float, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream);
-      case 13: return launch_pass<float, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 11: return launch_pass<float, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
+      case 12: return launch_pass<float, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
+      case 13: return launch_pass<float, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
     }
   } else {
     switch (cb) {
-      case 11: return launch_pass<double, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream);
-      case 12: return launch_pass<double, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream);
-      case 13: return launch_pass<double, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream);
+      case 11: return launch_pass<double, 11>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
+      case 12: return launch_pass<double, 12>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
+      case 13: return launch_pass<double, 13>(P, state, mats, pl.n_qubits, batch, mbs, stream, remote);
     }
   }
   return set_err(B200Q_EUNSUPPORTED, "chunk_bits must be 11, 12 or 13");
@@ -577,6 +582,38 @@ int b200q_plan_run_range(const b200q_plan_t* plan, int first, int last, void* st
   }
   for (int i = first; i < last; ++i) {
     rc = launch_pass_any(p, p.passes[i], state, matrices, batch, mbs, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* matrices, void* const* peer_buffers,
+                            int n_ranks, int rank, void* stream) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  const Plan& p = *plan->p;
+  int rc = check_state_args(state, p.n_qubits, p.dtype, 1);
+  if (rc) return rc;
+  if (!peer_buffers || n_ranks < 2 || n_ranks > B200Q_MAX_RANKS || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks)
+    return set_err(B200Q_EINVAL, "bad rank arguments (2, 4 or 8 ranks)");
+  int g = 0;
+  while ((1 << g) < n_ranks) ++g;
+  const int vs = p.dtype == B200Q_C64 ? 1 : 0;
+  if (p.n_qubits - g - vs < 0 || p.n_bits != p.n_qubits) return set_err(B200Q_EUNSUPPORTED, "shard too small for a fused exchange");
+  if (p.passes.empty()) return set_err(B200Q_EINVAL, "empty plan");
+  b200q_remote_t R;
+  std::memset(&R, 0, sizeof R);
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!peer_buffers[r]) return set_err(B200Q_EINVAL, "null peer buffer");
+    R.peer[r] = peer_buffers[r];
+  }
+  R.rank = rank;
+  R.chunk_shift = p.n_qubits - g - vs;
+  R.enabled = 1;
+  const int last = (int)p.passes.size() - 1;
+  if (p.dtype == B200Q_C64 && (p.passes[last].layout & B200Q_LAYOUT_DST_SOA))
+    return set_err(B200Q_EUNSUPPORTED, "last pass does not write the caller layout");
+  for (int i = 0; i <= last; ++i) {
+    rc = launch_pass_any(p, p.passes[i], state, matrices, 1, 0, (cudaStream_t)stream, i == last ? &R : nullptr);
     if (rc) return rc;
   }
   return 0;

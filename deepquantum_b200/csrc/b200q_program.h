@@ -89,6 +89,20 @@ typedef struct {
   uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
 } b200q_op_t;
 
+/* Fused pass + exchange (sharded path): the round that writes back to global memory stores every chunk straight
+ * into the receive buffer of the rank that owns it after the block transpose -- over NVLink peer mappings for
+ * the other ranks -- instead of the local shard.  The transpose swaps the rank bits with the top `rank_bits`
+ * local index bits: chunk index  c = (dest << chunk_shift) | low  of rank r lands at  (r << chunk_shift) | low
+ * of rank `dest`. */
+#define B200Q_MAX_RANKS 8
+typedef struct {
+  void* peer[B200Q_MAX_RANKS];  // base of every rank's receive buffer (peer-mapped device pointers)
+  int32_t rank;                 // this rank
+  int32_t chunk_shift;          // log2(16-byte chunks per exchanged block) = n_local - rank_bits - VS
+  int32_t enabled;              // 0: ordinary in-place scatter
+  int32_t pad;
+} b200q_remote_t;
+
 typedef struct {
   uint8_t src_global;  // 1: gather from global memory, 0: from the shared-memory tile
   uint8_t dst_global;  // 1: scatter to global memory, 0: to the shared-memory tile

@@ -678,7 +678,8 @@ template <typename Real>
 B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_global, bool soa_global,
                       typename Traits<Real>::chunk* tile,
                       typename Traits<Real>::chunk* gstate, uint64_t total_chunks, bool padded, uint32_t xm,
-                      const typename Traits<Real>::V* re, const typename Traits<Real>::V* im) {
+                      const typename Traits<Real>::V* re, const typename Traits<Real>::V* im,
+                      const b200q_remote_t* remote = nullptr) {
   using chunk = typename Traits<Real>::chunk;
   if (to_global) {
     uint64_t gst[4];
@@ -688,6 +689,20 @@ B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_globa
 #pragma unroll
     for (int s = 0; s < 4; ++s)
       if ((xm >> s) & 1u) gbase ^= gst[s];
+    if (remote != nullptr && remote->enabled) {
+      // fused exchange: chunk (dest << shift) | low goes to rank `dest`, position (rank << shift) | low
+      const int sh = remote->chunk_shift;
+      const uint64_t low_mask = (1ull << sh) - 1ull, mine = uint64_t(remote->rank) << sh;
+#pragma unroll
+      for (int c = 0; c < NE; ++c) {
+        const uint64_t idx = gidx(gbase, gst, c);
+        if (idx < total_chunks) {
+          chunk* dst = reinterpret_cast<chunk*>(remote->peer[idx >> sh]);
+          dst[mine | (idx & low_mask)] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+        }
+      }
+      return;
+    }
     if (!padded) {
       chunk* p[NE];
       element_ptrs<Real, chunk*>(gstate + gbase, gst, xm, p);
@@ -1069,7 +1084,8 @@ template <typename Real, bool LEAN>
 B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const RoundTab& T, int tid, uint64_t cta_base,
                         uint64_t enabled, typename Traits<Real>::chunk* tile, const cx<Real>* pool,
                         const Real* coef, const OpWord* words, Real gscale,
-                        typename Traits<Real>::chunk* gstate, uint64_t total_chunks) {
+                        typename Traits<Real>::chunk* gstate, uint64_t total_chunks,
+                        const b200q_remote_t* remote = nullptr) {
   using V = typename Traits<Real>::V;
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   if (!A.active) return;
@@ -1160,7 +1176,7 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
     for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
   scatter<Real>(A, T, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, padded, xm,
-                re, im);
+                re, im, remote);
 }
 
 // ------------------------------------------------------------------------------------------------

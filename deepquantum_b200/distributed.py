@@ -51,6 +51,57 @@ class DistributedQubitState(nn.Module):
         if self.rank == 0:
             self.amps[0] = 1.0
 
+    # ---- peer mappings for the fused pass + exchange -----------------------------------------------------------
+    def enable_peer_exchange(self) -> bool:
+        """Re-home `amps` and `buffer` in symmetric memory (torch.distributed._symmetric_memory: one allocation per
+        rank, mapped into every other rank of the node over NVLink) so that the last pass of a local segment can
+        store straight into the peers' receive buffers.  Collective; returns False (and keeps the NCCL transpose)
+        when symmetric memory is not available.  `B200Q_PEER_EXCHANGE=0` disables it."""
+        import os
+
+        import torch.distributed as dist
+        peer = self.__dict__.get('_peer')
+        if isinstance(peer, dict) and self.amps.data_ptr() in peer and self.buffer.data_ptr() in peer:
+            return True
+        if peer is False and self.__dict__.get('_peer_key') == (self.amps.dtype, str(self.amps.device)):
+            return False
+        self.__dict__['_peer_key'] = (self.amps.dtype, str(self.amps.device))
+        ok = (self.world_size > 1 and self.world_size <= 8 and self.amps.is_cuda and dist.is_initialized()
+              and dist.get_backend() == 'nccl' and os.environ.get('B200Q_PEER_EXCHANGE', '1') != '0')
+        err = ''
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                group = dist.group.WORLD
+                a = symm.empty(self.num_amps_per_node, dtype=self.amps.dtype, device=self.amps.device)
+                b = symm.empty(self.num_amps_per_node, dtype=self.amps.dtype, device=self.amps.device)
+                ha = symm.rendezvous(a, group)
+                hb = symm.rendezvous(b, group)
+                a.copy_(self.amps)
+                b.zero_()
+                peers = {a.data_ptr(): [int(x) for x in ha.buffer_ptrs], b.data_ptr(): [int(x) for x in hb.buffer_ptrs]}
+                assert len(peers[a.data_ptr()]) == self.world_size
+            except Exception as e:       # noqa: BLE001 -- any failure keeps the NCCL path
+                ok, err = False, f'{type(e).__name__}: {e}'
+        # every rank must take the same path
+        flag = torch.tensor([1 if ok else 0], device=self.amps.device if self.amps.is_cuda else 'cpu')
+        if dist.is_initialized() and self.world_size > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            self.__dict__['_peer'] = False
+            self.__dict__['_peer_error'] = err or 'disabled or unavailable on some rank'
+            return False
+        self.register_buffer('amps', a)
+        self.register_buffer('buffer', b)
+        self.__dict__['_peer'] = peers
+        self.__dict__['_peer_handles'] = (ha, hb)     # keep the mappings alive
+        return True
+
+    def peer_buffer_ptrs(self):
+        """Device pointers, valid on this device, of every rank's CURRENT receive buffer (all ranks swap the roles
+        of `amps` and `buffer` at the same steps, so the parity is the same everywhere)."""
+        return self.__dict__['_peer'][self.buffer.data_ptr()]
+
 
 class CudaExecutor:
     """Runs one local segment (a fused plan over the shard) on the GPU through the C ABI."""
@@ -60,6 +111,10 @@ class CudaExecutor:
 
     def run_plan(self, plan, amps, mats):
         plan.run(amps, mats, 1, 0)
+
+    def run_plan_exchange(self, plan, amps, mats, peer_ptrs, rank):
+        """The segment's plan with its last pass storing into the peers' receive buffers (b200q_plan_run_exchange)."""
+        plan.run_exchange(amps, mats, peer_ptrs, rank)
 
     # local pieces of measure_dist (csrc/b200q_sample.cu)
     def block_mass(self, amps, nlocal):
@@ -222,12 +277,20 @@ class ShardedProgram:
 
     def run(self, state: DistributedQubitState, mats: torch.Tensor, executor, marks=None) -> None:
         """`marks`: optional list receiving (kind, start_event, end_event) per step (bench.py timing)."""
+        import torch.distributed as dist
         nl = self.nl
+        fuse_exchange = (hasattr(executor, 'run_plan_exchange') and self.world > 1 and nl - self.g >= 1
+                         and state.enable_peer_exchange())
+        self.fused_exchanges = 0
+        skip_swap = False
         for si, step in enumerate(self.steps):
             ev0 = None
             if marks is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            if step[0] == 'swap' and skip_swap:      # already done by the fused last pass of the previous segment
+                skip_swap = False
+                continue
             if step[0] == 'swap':
                 block_transpose(state.amps, state.buffer)
                 state.amps, state.buffer = state.buffer, state.amps
@@ -268,11 +331,29 @@ class ShardedProgram:
             key = (si, state.amps.dtype)
             if key not in self.plans:
                 self.plans[key] = executor.make_plan(nl, state.amps.dtype, structs)
-            executor.run_plan(self.plans[key], state.amps, m)
+            next_is_swap = si + 1 < len(self.steps) and self.steps[si + 1][0] == 'swap'
+            if fuse_exchange and next_is_swap:
+                # fused pass + exchange: the segment's last pass stores into the peers' receive buffers over NVLink;
+                # a tiny all-reduce orders the ranks (stores are complete when the kernels have finished everywhere),
+                # then shard and receive buffer swap roles
+                executor.run_plan_exchange(self.plans[key], state.amps, m, state.peer_buffer_ptrs(), self.rank)
+                dist.all_reduce(self._sync_token(state.amps.device))
+                state.amps, state.buffer = state.buffer, state.amps
+                skip_swap = True
+                self.fused_exchanges += 1
+            else:
+                executor.run_plan(self.plans[key], state.amps, m)
             if marks is not None:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
                 marks.append(('seg', ev0, ev1))
+
+    def _sync_token(self, device):
+        tok = self.__dict__.get('_tok')
+        if tok is None or tok.device != device:
+            tok = torch.zeros(1, dtype=torch.int32, device=device)
+            self.__dict__['_tok'] = tok
+        return tok
 
     def stats(self):
         """(gates, local passes, segments, block transposes) of this rank's schedule (after a first run)."""

@@ -14,7 +14,8 @@ using namespace b200q;
 
 namespace {
 template <typename Real>
-void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* mats_v, int64_t batch, int64_t mbs) {
+void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* mats_v, int64_t batch, int64_t mbs,
+              const b200q_remote_t* remote = nullptr) {
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
   const int cb = pl.opt.chunk_bits;
@@ -50,10 +51,10 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
           for (int tid = 0; tid < nthreads; ++tid)
             if (P.lean)
               run_round<Real, true>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
-                                    words.data(), gscale, gstate, chunks_per_state);
+                                    words.data(), gscale, gstate, chunks_per_state, remote);
             else
               run_round<Real, false>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
-                                     words.data(), gscale, gstate, chunks_per_state);
+                                     words.data(), gscale, gstate, chunks_per_state, remote);
         }
       }
     }
@@ -168,6 +169,38 @@ extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, i
     stats_out[1] = pl->stats.n_rounds;
     stats_out[2] = pl->stats.n_ops;
     stats_out[3] = pl->stats.n_direct;
+  }
+  delete pl;
+  return 0;
+}
+
+// Fused pass + exchange, all ranks in one address space: rank r runs its plan on states[r]; the last pass scatters
+// into buffers[0..W-1] exactly like the kernel does through the NVLink peer mappings.
+extern "C" int hostemu_run_exchange(int n_local, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
+                                    void** states, void** buffers, const void* mats, int n_ranks, char* err_out,
+                                    int err_len) {
+  PlanOptions opt;
+  if (chunk_bits) opt.chunk_bits = chunk_bits;
+  std::string err;
+  Plan* pl = make_plan(n_local, dtype, gates, n_gates, opt, &err);
+  if (!pl) {
+    if (err_out && err_len > 0) { std::strncpy(err_out, err.c_str(), err_len - 1); err_out[err_len - 1] = 0; }
+    return -1;
+  }
+  int g = 0;
+  while ((1 << g) < n_ranks) ++g;
+  for (int r = 0; r < n_ranks; ++r) {
+    b200q_remote_t R;
+    std::memset(&R, 0, sizeof R);
+    for (int q = 0; q < n_ranks; ++q) R.peer[q] = buffers[q];
+    R.rank = r;
+    R.chunk_shift = n_local - g - (dtype == B200Q_C64 ? 1 : 0);
+    R.enabled = 1;
+    for (size_t i = 0; i < pl->passes.size(); ++i) {
+      const b200q_remote_t* rp = i + 1 == pl->passes.size() ? &R : nullptr;
+      if (dtype == B200Q_C64) run_pass<float>(*pl, pl->passes[i], states[r], mats, 1, 0, rp);
+      else run_pass<double>(*pl, pl->passes[i], states[r], mats, 1, 0, rp);
+    }
   }
   delete pl;
   return 0;

@@ -256,3 +256,46 @@ def test_adjoint_lean_ops_with_pending_scalars(cdtype):
             g, ref = np.diagonal(g), np.diagonal(ref)
         scale = max(1.0, np.abs(ref).max())
         assert np.abs(g - ref).max() / scale < tol, (wires, ctr, g, ref)
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_fused_pass_and_block_transpose(cdtype, world):
+    """`b200q_plan_run_exchange`: the last pass of a local segment scatters every chunk straight into the receive
+    buffer of the rank that owns it after the block transpose.  All ranks emulated in one address space; expected
+    = ordinary run of the segment on every shard followed by the all-to-all transpose in numpy."""
+    import ctypes as C
+    from deepquantum_b200 import _lib as L
+    from helpers import hostemu, lower_ops
+    nl = 14
+    rng = np.random.default_rng(world)
+    ops = []
+    for _ in range(60):
+        w = int(rng.integers(nl))
+        c = int((w + 1 + rng.integers(nl - 1)) % nl)
+        k = int(rng.integers(5))
+        ops.append([(gates_np.H, [w], []), (gates_np.rx(float(rng.uniform(0, 12))), [w], []), (gates_np.X, [w], [c]),
+                    (gates_np.S, [w], []), (gates_np.u3(*rng.uniform(0, 6, 3)), [w], [c])][k])
+    shards = [(rng.normal(size=2**nl) + 1j * rng.normal(size=2**nl)).astype(cdtype) for _ in range(world)]
+    expect_local = [emu_run(ops, nl, cdtype, state=s, chunk_bits=11)[0][0] for s in shards]
+    blk = 2**nl // world
+    expect = [np.concatenate([expect_local[src][dst * blk:(dst + 1) * blk] for src in range(world)])
+              for dst in range(world)]
+    arr, ng, mats = lower_ops(ops, nl, cdtype)
+    states = [np.ascontiguousarray(s.copy()) for s in shards]
+    bufs = [np.full(2**nl, np.nan + 0j, dtype=cdtype) for _ in range(world)]
+    lib = hostemu()
+    lib.hostemu_run_exchange.restype = C.c_int
+    lib.hostemu_run_exchange.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
+                                         C.c_char_p, C.c_int]
+    sp = (C.c_void_p * world)(*[s.ctypes.data for s in states])
+    bp = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    err = C.create_string_buffer(256)
+    rc = lib.hostemu_run_exchange(nl, L.C64 if cdtype == np.complex64 else L.C128, arr, ng, 11, sp, bp,
+                                  mats.ctypes.data, world, err, 256)
+    assert rc == 0, err.value.decode()
+    tol = 1e-12 if cdtype == np.complex128 else 2e-6
+    for dst in range(world):
+        assert not np.isnan(bufs[dst]).any()
+        assert np.linalg.norm(bufs[dst] - expect[dst]) / np.linalg.norm(expect[dst]) < tol

@@ -115,3 +115,28 @@ def lazy_cnot_potential(n=28, depth=40):
 
 if __name__ == '__main__' and len(sys.argv) > 3:
     lazy_cnot_potential()
+
+
+def dump_rounds(n=28, depth=40, npasses=2):
+    spec = wl.random_clifford_rx_spec(n, depth)
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec)
+    plan = cir._get_program().plan(torch.complex64)
+    raw = plan.export()
+    for i in range(3, 3 + npasses):
+        P = Pass.from_buffer_copy(raw[i * C.sizeof(Pass):(i + 1) * C.sizeof(Pass)])
+        print(f'pass {i}: {P.n_rounds} rounds, {P.n_ops} ops')
+        for r in range(P.n_rounds):
+            Rd = P.rounds[r]
+            seq = []
+            for o in range(Rd.op_begin, Rd.op_end):
+                op = P.ops[o]
+                nm = name(op.code)
+                s = op.code - max(k for k in NAMES if k <= op.code) if nm in ('HAD', 'ROTX', 'ROTY', 'DIAG_R', 'LSWAP') else (
+                    op.arg if nm in ('XREL', 'X_C1') else '')
+                seq.append(f'{nm}{s}{"c" if op.tctrl else ""}')
+            print(f'  round {r} [{"G" if Rd.src_global else "s"}->{"G" if Rd.dst_global else "s"}] ' + ' '.join(seq))
+
+
+if __name__ == '__main__' and len(sys.argv) > 3 and sys.argv[3] == 'dump':
+    dump_rounds()

@@ -106,8 +106,9 @@ class DistributedQubitState(nn.Module):
 class CudaExecutor:
     """Runs one local segment (a fused plan over the shard) on the GPU through the C ABI."""
 
-    def make_plan(self, nlocal, dtype, structs):
-        return engine.FusedPlan(nlocal, dtype, structs)
+    def make_plan(self, nlocal, dtype, structs, exchange=False):
+        # a segment whose last pass stores over NVLink writes 128-byte runs per quarter warp (3 lane-owned chunk bits)
+        return engine.FusedPlan(nlocal, dtype, structs, coalesce_bits=3 if exchange else None)
 
     def run_plan(self, plan, amps, mats):
         plan.run(amps, mats, 1, 0)
@@ -328,11 +329,13 @@ class ShardedProgram:
             if not structs:
                 continue
             m = torch.cat([mats] + extra) if extra else mats
-            key = (si, state.amps.dtype)
-            if key not in self.plans:
-                self.plans[key] = executor.make_plan(nl, state.amps.dtype, structs)
             next_is_swap = si + 1 < len(self.steps) and self.steps[si + 1][0] == 'swap'
-            if fuse_exchange and next_is_swap:
+            fused = fuse_exchange and next_is_swap
+            key = (si, state.amps.dtype, fused)
+            if key not in self.plans:
+                self.plans[key] = (executor.make_plan(nl, state.amps.dtype, structs, exchange=True) if fused
+                                   else executor.make_plan(nl, state.amps.dtype, structs))
+            if fused:
                 # fused pass + exchange: the segment's last pass stores into the peers' receive buffers over NVLink;
                 # a tiny all-reduce orders the ranks (stores are complete when the kernels have finished everywhere),
                 # then shard and receive buffer swap roles

@@ -48,7 +48,7 @@ class FusedPlan:
     supplied at run time from a device buffer."""
 
     def __init__(self, nqubit: int, dtype: torch.dtype, gates: list, chunk_bits: int = 0, low_bits: int = 0,
-                 max_rounds: int = 0, fuse: bool = True, structured: bool = True):
+                 max_rounds: int = 0, fuse: bool = True, structured: bool = True, coalesce_bits: int | None = None):
         lib = L.load()
         self.nqubit = nqubit
         self.dtype = dtype
@@ -57,6 +57,8 @@ class FusedPlan:
         opt = L.PlanOptions()
         opt.chunk_bits, opt.low_bits, opt.max_rounds, opt.fuse = chunk_bits, low_bits, max_rounds, int(fuse)
         opt.reserved[0] = 0 if structured else 1      # A/B switch: general op codes only (non-lean kernel)
+        if coalesce_bits is not None:
+            opt.reserved[1] = 1 + coalesce_bits       # lane-owned chunk bits of the rounds that touch global memory
         handle = C.c_void_p()
         L.check(lib.b200q_plan_create(nqubit, dtype_code(dtype), arr, len(gates), C.byref(opt), C.byref(handle)))
         self._h = handle

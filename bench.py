@@ -47,7 +47,8 @@ def parse():
 def workload(args):
     n = args.nqubit or 28
     depth = args.depth or 40
-    name = f'config2: {n}-qubit random Clifford+RX, depth {depth}, complex64, single B200'
+    tag = 'config2: ' if (n, depth) == (28, 40) else ('config4 size: ' if (n, depth) == (33, 30) else '')
+    name = f'{tag}{n}-qubit random Clifford+RX, depth {depth}, complex64, single B200'
     if args.gpus > 1:
         name += f' -- sharded over {args.gpus} ranks'
     return n, depth, name
@@ -255,7 +256,8 @@ def run_single(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c64',
         'data': 'synthetic',
         'config': {'workload': name, 'gates': ngates, 'passes': n_passes, 'gates_per_pass': ngates / n_passes,
-                   'state_bytes': state_bytes, 'l2': 'state (2 GiB) is larger than L2 (126 MB): no flush needed',
+                   'state_bytes': state_bytes,
+                   'l2': f'state ({state_bytes / 2**30:g} GiB) is larger than L2 (126 MB): no flush needed',
                    'tile_bytes': 16 << (args.chunk_bits or 12), 'fused': not args.no_fuse, 'norm2_check': norm},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'b200q_tile_kernel<float,12,lean>',

@@ -68,7 +68,7 @@ _SIGNATURES = {
     'b200q_plan_run_range': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_void_p]),
     'b200q_plan_run_exchange': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
-                                          C.c_void_p]),
+                                          C.POINTER(C.c_uint8), C.c_void_p]),
     'b200q_apply_gate': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     'b200q_norm2': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -80,6 +80,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
   OpWord* words = reinterpret_cast<OpWord*>(smem_raw + SM::kTile + SM::kCoef + SM::kTabs);
   uint64_t* base_tab = reinterpret_cast<uint64_t*>(smem_raw + SM::kTile + SM::kCoef + SM::kTabs + SM::kWords);
   cx<Real>* pool = reinterpret_cast<cx<Real>*>(smem_raw + SM::kBase);
+  uint64_t* dest_tab = reinterpret_cast<uint64_t*>(smem_raw + SM::kBase + (P.needs_pool ? SM::kPool : 0));
   const int tid = threadIdx.x;
   const int nthreads = TileCfg<CB>::kThreads;
   const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride;
@@ -88,6 +89,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
   if (P.needs_pool) fill_pool<Real>(P, tid, nthreads, pool, m, false);
   fill_coefs<Real>(P, tid, nthreads, coef, m);
   fill_opwords(P, tid, nthreads, words);
+  if (remote.enabled) fill_dest_tab(remote, tid, nthreads, dest_tab);
   // Per-tile setup without loops over index bits: the physical base of a tile is the OR of six table entries
   // (five tile-index bits each), and lane l of every warp keeps, in tile-index space, the outside-the-tile
   // control masks of ops l and l + 32, so the per-tile set of enabled ops is two ballots.
@@ -129,7 +131,7 @@ b200q_tile_kernel(const __grid_constant__ b200q_pass_t P, typename Traits<Real>:
         }
       } else {
         run_round<Real, LEAN>(P, Rd, tabs[r], tid, cta_base, enabled, tile, pool, coef, words, gscale, gstate,
-                              chunks_per_state, &remote);
+                              chunks_per_state, &remote, dest_tab);
         if (r + 1 < nr) __syncthreads();
       }
     }
@@ -158,8 +160,9 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
   if (remote_in) remote = *remote_in;
   using chunk = typename Traits<Real>::chunk;
   constexpr int VS = Traits<Real>::VS;
-  const size_t smem_max = TileSmem<Real, CB>::kTotal;
-  const size_t smem = P.needs_pool ? smem_max : TileSmem<Real, CB>::kBase;
+  const size_t kDest = size_t(B200Q_DEST_TAB_ENTRIES) * sizeof(uint64_t);
+  const size_t smem_max = TileSmem<Real, CB>::kTotal + kDest;
+  const size_t smem = (P.needs_pool ? TileSmem<Real, CB>::kTotal : TileSmem<Real, CB>::kBase) + (remote.enabled ? kDest : 0);
   auto kern = P.lean ? b200q_tile_kernel<Real, CB, true> : b200q_tile_kernel<Real, CB, false>;
   const int blocks_per_sm = P.lean ? FwdCfg<Real, CB, true>::kMinBlocks : FwdCfg<Real, CB, false>::kMinBlocks;
   static bool attr_set[64] = {false};
@@ -588,17 +591,18 @@ int b200q_plan_run_range(const b200q_plan_t* plan, int first, int last, void* st
 }
 
 int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* matrices, void* const* peer_buffers,
-                            int n_ranks, int rank, void* stream) {
+                            int n_ranks, int rank, const uint8_t* perm, void* stream) {
   if (!plan) return set_err(B200Q_EINVAL, "null plan");
   const Plan& p = *plan->p;
   int rc = check_state_args(state, p.n_qubits, p.dtype, 1);
   if (rc) return rc;
-  if (!peer_buffers || n_ranks < 2 || n_ranks > B200Q_MAX_RANKS || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks)
-    return set_err(B200Q_EINVAL, "bad rank arguments (2, 4 or 8 ranks)");
+  if (!peer_buffers || n_ranks < 1 || n_ranks > B200Q_MAX_RANKS || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks)
+    return set_err(B200Q_EINVAL, "bad rank arguments (1, 2, 4 or 8 ranks)");
   int g = 0;
   while ((1 << g) < n_ranks) ++g;
   const int vs = p.dtype == B200Q_C64 ? 1 : 0;
-  if (p.n_qubits - g - vs < 0 || p.n_bits != p.n_qubits) return set_err(B200Q_EUNSUPPORTED, "shard too small for a fused exchange");
+  const int nl = p.n_qubits, nt = nl + g;
+  if (nl - g - vs < 0 || p.n_bits != p.n_qubits || nl - vs > 40) return set_err(B200Q_EUNSUPPORTED, "shard size not supported by the fused exchange");
   if (p.passes.empty()) return set_err(B200Q_EINVAL, "empty plan");
   b200q_remote_t R;
   std::memset(&R, 0, sizeof R);
@@ -606,8 +610,24 @@ int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* m
     if (!peer_buffers[r]) return set_err(B200Q_EINVAL, "null peer buffer");
     R.peer[r] = peer_buffers[r];
   }
-  R.rank = rank;
-  R.chunk_shift = p.n_qubits - g - vs;
+  // bit permutation of the distributed index (amplitude bits; bits >= nl are rank bits); default: block transpose
+  uint8_t pm[48];
+  for (int j = 0; j < nt; ++j) pm[j] = perm ? perm[j] : (uint8_t)j;
+  if (!perm)
+    for (int k = 0; k < g; ++k) { pm[nl - g + k] = (uint8_t)(nl + k); pm[nl + k] = (uint8_t)(nl - g + k); }
+  uint64_t seen = 0;
+  for (int j = 0; j < nt; ++j) {
+    if (pm[j] >= nt || (seen >> pm[j] & 1)) return set_err(B200Q_EINVAL, "perm is not a permutation of the index bits");
+    seen |= 1ull << pm[j];
+  }
+  if (vs && pm[0] != 0) return set_err(B200Q_EUNSUPPORTED, "complex64: index bit 0 (inside a 16-byte chunk) must stay in place");
+  R.n_chunk_bits = nl - vs;
+  for (int j = vs; j < nl; ++j) R.perm[j - vs] = (uint8_t)(pm[j] - vs);
+  for (int k = 0; k < g; ++k)
+    if ((rank >> k) & 1) {
+      const int pos = pm[nl + k] - vs;
+      R.base |= pos < R.n_chunk_bits ? (1ull << pos) : (1ull << (B200Q_DEST_RANK_SHIFT + pos - R.n_chunk_bits));
+    }
   R.enabled = 1;
   const int last = (int)p.passes.size() - 1;
   if (p.dtype == B200Q_C64 && (p.passes[last].layout & B200Q_LAYOUT_DST_SOA))

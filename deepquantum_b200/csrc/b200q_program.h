@@ -89,18 +89,22 @@ typedef struct {
   uint32_t gate_id;  // index of the source gate (diagnostics / adjoint gradient slot)
 } b200q_op_t;
 
-/* Fused pass + exchange (sharded path): the round that writes back to global memory stores every chunk straight
- * into the receive buffer of the rank that owns it after the block transpose -- over NVLink peer mappings for
- * the other ranks -- instead of the local shard.  The transpose swaps the rank bits with the top `rank_bits`
- * local index bits: chunk index  c = (dest << chunk_shift) | low  of rank r lands at  (r << chunk_shift) | low
- * of rank `dest`. */
+/* Fused pass + exchange (sharded path): the round that writes back to global memory stores every 16-byte chunk
+ * straight into the receive buffer of the rank that owns it after the exchange -- over NVLink peer mappings for the
+ * other ranks -- instead of the local shard.  The exchange is an arbitrary PERMUTATION OF INDEX BITS of the
+ * distributed state: chunk-index bit j of this rank's shard goes to position perm[j]; positions >= n_chunk_bits
+ * are rank bits (perm[j] = n_chunk_bits + k: the bit selects bit k of the destination rank).  The rank bits of
+ * the source are constants of the launch: their images are pre-folded into `base` (same encoding).  Encoding of a
+ * destination: chunk index in bits 0..39, rank in bits 40.. .  The block transpose of the reference scheme
+ * (top rank_bits local bits <-> rank bits) is the special case the simple constructor builds. */
 #define B200Q_MAX_RANKS 8
+#define B200Q_DEST_RANK_SHIFT 40
 typedef struct {
   void* peer[B200Q_MAX_RANKS];  // base of every rank's receive buffer (peer-mapped device pointers)
-  int32_t rank;                 // this rank
-  int32_t chunk_shift;          // log2(16-byte chunks per exchanged block) = n_local - rank_bits - VS
+  uint64_t base;                // images of the source rank bits (destination encoding)
+  uint8_t perm[40];             // destination position of chunk-index bit j
+  int32_t n_chunk_bits;         // chunk-index bits of a shard = n_local - VS
   int32_t enabled;              // 0: ordinary in-place scatter
-  int32_t pad;
 } b200q_remote_t;
 
 typedef struct {

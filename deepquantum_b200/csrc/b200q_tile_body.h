@@ -626,6 +626,23 @@ B200Q_HD uint32_t sidx(uint32_t sbase, const uint32_t* sst, int c) {
   return sbase ^ ((c & 1) ? sst[0] : 0) ^ ((c & 2) ? sst[1] : 0) ^ ((c & 4) ? sst[2] : 0) ^ ((c & 8) ? sst[3] : 0);
 }
 
+// Destination tables of the fused exchange: entry [b][v] = OR over the set bits of v of the image of chunk-index
+// bit 8 b + (bit); entry [0][0] also carries the images of the source rank bits (`base`).  5 x 256 x 8 bytes.
+#define B200Q_DEST_TAB_ENTRIES 1280
+B200Q_HD void fill_dest_tab(const b200q_remote_t& R, int tid, int nthreads, uint64_t* tab) {
+  for (int e = tid; e < B200Q_DEST_TAB_ENTRIES; e += nthreads) {
+    const int b = e >> 8, v = e & 255;
+    uint64_t d = b == 0 ? R.base : 0ull;
+    for (int j = 0; j < 8; ++j) {
+      const int bit = 8 * b + j;
+      if (!((v >> j) & 1) || bit >= R.n_chunk_bits) continue;
+      const int pos = R.perm[bit];
+      d |= pos < R.n_chunk_bits ? (1ull << pos) : (1ull << (B200Q_DEST_RANK_SHIFT + pos - R.n_chunk_bits));
+    }
+    tab[e] = d;
+  }
+}
+
 // Global addressing without bounds checks (the state is not padded): the register-slot bits of gbase are zero,
 // so element c lives at base + sum of the strides of its set bits -- 64-bit pointer adds shared between the 16
 // elements instead of a 64-bit XOR chain, compare and select per element.  `sgn` makes stride s negative
@@ -679,7 +696,7 @@ B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_globa
                       typename Traits<Real>::chunk* tile,
                       typename Traits<Real>::chunk* gstate, uint64_t total_chunks, bool padded, uint32_t xm,
                       const typename Traits<Real>::V* re, const typename Traits<Real>::V* im,
-                      const b200q_remote_t* remote = nullptr) {
+                      const b200q_remote_t* remote = nullptr, const uint64_t* dest_tab = nullptr) {
   using chunk = typename Traits<Real>::chunk;
   if (to_global) {
     uint64_t gst[4];
@@ -690,15 +707,17 @@ B200Q_HD void scatter(const RoundAddr<Real>& A, const RoundTab& T, bool to_globa
     for (int s = 0; s < 4; ++s)
       if ((xm >> s) & 1u) gbase ^= gst[s];
     if (remote != nullptr && remote->enabled) {
-      // fused exchange: chunk (dest << shift) | low goes to rank `dest`, position (rank << shift) | low
-      const int sh = remote->chunk_shift;
-      const uint64_t low_mask = (1ull << sh) - 1ull, mine = uint64_t(remote->rank) << sh;
+      // fused exchange: destination = bit permutation of the chunk index, four byte-indexed table lookups
+      // (dest_tab, built once per CTA by fill_dest_tab); rank in the high bits selects the peer buffer
 #pragma unroll
       for (int c = 0; c < NE; ++c) {
         const uint64_t idx = gidx(gbase, gst, c);
         if (idx < total_chunks) {
-          chunk* dst = reinterpret_cast<chunk*>(remote->peer[idx >> sh]);
-          dst[mine | (idx & low_mask)] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
+          const uint64_t d = dest_tab[idx & 255u] | dest_tab[256 + ((idx >> 8) & 255u)] |
+                             dest_tab[512 + ((idx >> 16) & 255u)] | dest_tab[768 + ((idx >> 24) & 255u)] |
+                             dest_tab[1024 + ((idx >> 32) & 255u)];
+          chunk* dst = reinterpret_cast<chunk*>(remote->peer[d >> B200Q_DEST_RANK_SHIFT]);
+          dst[d & ((1ull << B200Q_DEST_RANK_SHIFT) - 1ull)] = pack(re[c], im[c], soa_global, (chunk*)nullptr);
         }
       }
       return;
@@ -1085,7 +1104,7 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
                         uint64_t enabled, typename Traits<Real>::chunk* tile, const cx<Real>* pool,
                         const Real* coef, const OpWord* words, Real gscale,
                         typename Traits<Real>::chunk* gstate, uint64_t total_chunks,
-                        const b200q_remote_t* remote = nullptr) {
+                        const b200q_remote_t* remote = nullptr, const uint64_t* dest_tab = nullptr) {
   using V = typename Traits<Real>::V;
   RoundAddr<Real> A = round_addr<Real>(P, T, tid, cta_base);
   if (!A.active) return;
@@ -1176,7 +1195,7 @@ B200Q_HD void run_round(const b200q_pass_t& P, const b200q_round_t& Rd, const Ro
     for (int c = 0; c < NE; ++c) cmul_inplace(re[c], im[c], pr, pi, npi);
   }
   scatter<Real>(A, T, Rd.dst_global, (P.layout & B200Q_LAYOUT_DST_SOA) != 0, tile, gstate, total_chunks, padded, xm,
-                re, im, remote);
+                re, im, remote, dest_tab);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -113,9 +113,10 @@ class CudaExecutor:
     def run_plan(self, plan, amps, mats):
         plan.run(amps, mats, 1, 0)
 
-    def run_plan_exchange(self, plan, amps, mats, peer_ptrs, rank):
-        """The segment's plan with its last pass storing into the peers' receive buffers (b200q_plan_run_exchange)."""
-        plan.run_exchange(amps, mats, peer_ptrs, rank)
+    def run_plan_exchange(self, plan, amps, mats, peer_ptrs, rank, perm=None):
+        """The segment's plan with its last pass storing into the peers' receive buffers (b200q_plan_run_exchange);
+        `perm`: bit permutation of the distributed index, None = block transpose."""
+        plan.run_exchange(amps, mats, peer_ptrs, rank, perm)
 
     # local pieces of measure_dist (csrc/b200q_sample.cu)
     def block_mass(self, amps, nlocal):
@@ -131,10 +132,17 @@ class CudaExecutor:
 class ShardedProgram:
     """Per-rank execution schedule of a lowered gate program: local segments separated by block transposes."""
 
-    def __init__(self, low: Lowering, nqubit: int, world_size: int, rank: int):
+    def __init__(self, low: Lowering, nqubit: int, world_size: int, rank: int, mode: str = 'pswap'):
+        """mode 'pswap': exchanges are block transposes (rank bits <-> top local bits; the qubits to evict are first
+        moved to the top local positions by relabelling SWAPs inside the fused passes) -- the NCCL path.
+        mode 'perm': exchanges are arbitrary permutations of the bits of the distributed index, done by the fused
+        last pass of the preceding segment (`b200q_plan_run_exchange`): victims leave from where they are, and
+        the reference layout is restored by ONE permuting exchange instead of up to two transposes plus passes of
+        relabelling SWAPs."""
         self.low, self.n, self.world, self.rank = low, nqubit, world_size, rank
         self.g = world_size.bit_length() - 1
         self.nl = nqubit - self.g
+        self.mode = mode
         self.plans = {}
         self._schedule()
 
@@ -174,6 +182,17 @@ class ShardedProgram:
             steps.append(('swap',))
             nswaps += 1
 
+        def exchange_perm(new_phys):
+            """perm mode: one exchange that moves every logical bit b from phys[b] to new_phys[b]."""
+            nonlocal nswaps
+            pm = list(range(n))
+            for b in range(n):
+                pm[phys[b]] = new_phys[b]
+            assert pm[0] == 0, 'index bit 0 never moves (it lives inside a 16-byte complex64 chunk)'
+            steps.append(('xperm', pm))
+            phys[:] = new_phys
+            nswaps += 1
+
         while remaining:
             glob_mask = sum(1 << b for b in range(n) if phys[b] >= nl)
             seg, bfull, bdiag, first_blocked = [], 0, 0, None
@@ -203,11 +222,28 @@ class ShardedProgram:
                         for b in range(n):
                             if tm >> b & 1:
                                 next_use[b] = i
-                cand = [b for b in range(n) if phys[b] < nl and not (first_blocked >> b & 1)]
+                # perm mode: a victim leaves from where it is, so consecutive chunks of the source alternate between
+                # destination ranks every 2^position amplitudes: only positions >= 8 (runs of >= 2 KiB) may leave;
+                # the qubits below stay local for good (and index bit 0 lives inside a complex64 chunk)
+                low = 0 if self.mode != 'perm' else (8 if nl >= 16 else 1)
+                cand = [b for b in range(n) if low <= phys[b] < nl and not (first_blocked >> b & 1)]
+                if len(cand) < g and low > 1:
+                    cand = [b for b in range(n) if 1 <= phys[b] < nl and not (first_blocked >> b & 1)]
                 if len(cand) < g:
                     raise RuntimeError('not enough local qubits to unblock a gate: it needs more than n_local - g targets')
                 cand.sort(key=lambda b: (-next_use[b], -phys[b]))
                 victims = cand[:g]
+                if self.mode == 'perm':
+                    # the g global qubits take the places of the g victims, wherever those are: no relabelling
+                    if seg:
+                        steps.append(('seg', seg))
+                    inv = {p: b for b, p in enumerate(phys)}
+                    new_phys = list(phys)
+                    for jj, v in enumerate(victims):
+                        gl = inv[nl + jj]
+                        new_phys[gl], new_phys[v] = phys[v], phys[gl]
+                    exchange_perm(new_phys)
+                    continue
                 # keep victims that already sit in the top positions where they are
                 tops = [nl - g + jj for jj in range(g)]
                 placed = {phys[b]: b for b in victims if phys[b] in tops}
@@ -222,6 +258,8 @@ class ShardedProgram:
             if remaining:
                 transpose()
         # ---- restore the reference layout (logical bit b at physical bit b) -------------------------------
+        if self.mode == 'perm' and phys != list(range(n)):
+            exchange_perm(list(range(n)))
         if phys != list(range(n)):
             should_glob = list(range(nl, n))
             if any(phys[b] != b for b in should_glob):
@@ -276,80 +314,108 @@ class ShardedProgram:
             pt = [p for p in pt if p < nl]
         return (i, kind, tuple(pt), tuple(local_ctrl), adj, active, fix, hint)
 
+    def _segment_structs(self, step, mats):
+        """GateStruct list (+ extra derived matrices) of one local segment for this rank."""
+        structs, extra, off_extra = [], [], mats.numel()
+        for item in step[1]:
+            if item[0] == 'pswap':       # physical SWAP of two local bits = three CX relabellings
+                a, b = item[1], item[2]
+                structs += [L.make_gate(L.GATE_X, [b], [a]), L.make_gate(L.GATE_X, [a], [b]),
+                            L.make_gate(L.GATE_X, [b], [a])]
+                continue
+            (i, kind, pt, ctrl, adj, active, fix, hint) = item
+            if not active:
+                continue
+            off = self.low.offsets[i]
+            if fix is not None:
+                k = len(self.low.records[i][1])
+                d = torch.diagonal(mats[off:off + 4**k].reshape(2**k, 2**k))
+                sel = d.reshape([2] * k)         # index order: matrix bit k-1 ... bit 0
+                for j, bit in sorted(fix):   # ascending j = last axis first, so earlier axes keep their index
+                    sel = sel.select(k - 1 - j, bit)
+                vals = sel.reshape(-1)
+                if len(pt) == 0:
+                    # a pure per-rank phase: a diagonal gate on local bit 0 with both entries equal
+                    pt, vals = (0,), vals.repeat(2)
+                extra.append(torch.diag(vals).reshape(-1))
+                structs.append(L.make_gate(L.GATE_DIAG, pt, ctrl, off_extra, adj))
+                off_extra += extra[-1].numel()
+            else:
+                structs.append(L.make_gate(kind, pt, ctrl, off, adj, hint))
+        return structs, extra
+
+    def run_step(self, si: int, state, mats: torch.Tensor, executor, fuse_exchange: bool) -> str:
+        """Execute step `si` for this rank.  Returns 'exchange' when a fused pass + exchange was issued: the caller
+        must order the ranks and then call `commit_exchange(state)` (shard and receive buffer swap roles)."""
+        step = self.steps[si]
+        nl = self.nl
+        if step[0] in ('swap', 'xperm') and self._skip_next:     # done by the fused last pass of the previous segment
+            self._skip_next = False
+            return 'skipped'
+        if step[0] == 'swap':
+            block_transpose(state.amps, state.buffer)
+            state.amps, state.buffer = state.buffer, state.amps
+            return 'swap'
+        if step[0] == 'xperm':
+            # an exchange with no segment in front of it: the identity as a one-op plan, fused with the exchange
+            assert fuse_exchange, "the 'perm' schedule needs the peer-mapped exchange"
+            key = ('identity', state.amps.dtype)
+            if key not in self.plans:
+                self.plans[key] = executor.make_plan(nl, state.amps.dtype, [L.make_gate(L.GATE_DIAG, (1,), (), 0)],
+                                                     exchange=True)
+            eye = torch.eye(2, dtype=state.amps.dtype, device=state.amps.device).reshape(-1)
+            executor.run_plan_exchange(self.plans[key], state.amps, eye, state.peer_buffer_ptrs(), self.rank, step[1])
+            self.fused_exchanges += 1
+            return 'exchange'
+        structs, extra = self._segment_structs(step, mats)
+        if not structs:
+            return 'empty'
+        m = torch.cat([mats] + extra) if extra else mats
+        nxt = self.steps[si + 1] if si + 1 < len(self.steps) else None
+        fused = fuse_exchange and nxt is not None and nxt[0] in ('swap', 'xperm')
+        key = (si, state.amps.dtype, fused)
+        if key not in self.plans:
+            self.plans[key] = (executor.make_plan(nl, state.amps.dtype, structs, exchange=True) if fused
+                               else executor.make_plan(nl, state.amps.dtype, structs))
+        if fused:
+            # fused pass + exchange: the segment's last pass stores into the peers' receive buffers over NVLink
+            executor.run_plan_exchange(self.plans[key], state.amps, m, state.peer_buffer_ptrs(), self.rank,
+                                       nxt[1] if nxt[0] == 'xperm' else None)
+            self._skip_next = True
+            self.fused_exchanges += 1
+            return 'exchange'
+        executor.run_plan(self.plans[key], state.amps, m)
+        return 'seg'
+
+    @staticmethod
+    def commit_exchange(state) -> None:
+        state.amps, state.buffer = state.buffer, state.amps
+
     def run(self, state: DistributedQubitState, mats: torch.Tensor, executor, marks=None) -> None:
         """`marks`: optional list receiving (kind, start_event, end_event) per step (bench.py timing)."""
         import torch.distributed as dist
-        nl = self.nl
-        fuse_exchange = (hasattr(executor, 'run_plan_exchange') and self.world > 1 and nl - self.g >= 1
+        # only the 'perm' schedule fuses: with block transposes a rank whose segment is empty (all its gates
+        # switched off by global controls) would enter the NCCL transpose while its peers store directly
+        fuse_exchange = (self.mode == 'perm' and hasattr(executor, 'run_plan_exchange') and self.world > 1
                          and state.enable_peer_exchange())
+        assert fuse_exchange or self.mode != 'perm', "the 'perm' schedule needs the peer-mapped exchange"
         self.fused_exchanges = 0
-        skip_swap = False
-        for si, step in enumerate(self.steps):
+        self._skip_next = False
+        for si in range(len(self.steps)):
             ev0 = None
             if marks is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            if step[0] == 'swap' and skip_swap:      # already done by the fused last pass of the previous segment
-                skip_swap = False
-                continue
-            if step[0] == 'swap':
-                block_transpose(state.amps, state.buffer)
-                state.amps, state.buffer = state.buffer, state.amps
-                if marks is not None:
-                    ev1 = torch.cuda.Event(enable_timing=True)
-                    ev1.record()
-                    marks.append(('swap', ev0, ev1))
-                continue
-            structs, extra, off_extra = [], [], mats.numel()
-            for item in step[1]:
-                if item[0] == 'pswap':       # physical SWAP of two local bits = three CX relabellings
-                    a, b = item[1], item[2]
-                    structs += [L.make_gate(L.GATE_X, [b], [a]), L.make_gate(L.GATE_X, [a], [b]),
-                                L.make_gate(L.GATE_X, [b], [a])]
-                    continue
-                (i, kind, pt, ctrl, adj, active, fix, hint) = item
-                if not active:
-                    continue
-                off = self.low.offsets[i]
-                if fix is not None:
-                    k = len(self.low.records[i][1])
-                    d = torch.diagonal(mats[off:off + 4**k].reshape(2**k, 2**k))
-                    sel = d.reshape([2] * k)         # index order: matrix bit k-1 ... bit 0
-                    for j, bit in sorted(fix):   # ascending j = last axis first, so earlier axes keep their index
-                        sel = sel.select(k - 1 - j, bit)
-                    vals = sel.reshape(-1)
-                    if len(pt) == 0:
-                        # a pure per-rank phase: a diagonal gate on local bit 0 with both entries equal
-                        pt, vals = (0,), vals.repeat(2)
-                    extra.append(torch.diag(vals).reshape(-1))
-                    structs.append(L.make_gate(L.GATE_DIAG, pt, ctrl, off_extra, adj))
-                    off_extra += extra[-1].numel()
-                else:
-                    structs.append(L.make_gate(kind, pt, ctrl, off, adj, hint))
-            if not structs:
-                continue
-            m = torch.cat([mats] + extra) if extra else mats
-            next_is_swap = si + 1 < len(self.steps) and self.steps[si + 1][0] == 'swap'
-            fused = fuse_exchange and next_is_swap
-            key = (si, state.amps.dtype, fused)
-            if key not in self.plans:
-                self.plans[key] = (executor.make_plan(nl, state.amps.dtype, structs, exchange=True) if fused
-                                   else executor.make_plan(nl, state.amps.dtype, structs))
-            if fused:
-                # fused pass + exchange: the segment's last pass stores into the peers' receive buffers over NVLink;
-                # a tiny all-reduce orders the ranks (stores are complete when the kernels have finished everywhere),
-                # then shard and receive buffer swap roles
-                executor.run_plan_exchange(self.plans[key], state.amps, m, state.peer_buffer_ptrs(), self.rank)
+            what = self.run_step(si, state, mats, executor, fuse_exchange)
+            if what == 'exchange':
+                # a tiny all-reduce orders the ranks (all peer stores are complete when the kernels have finished
+                # everywhere), then shard and receive buffer swap roles
                 dist.all_reduce(self._sync_token(state.amps.device))
-                state.amps, state.buffer = state.buffer, state.amps
-                skip_swap = True
-                self.fused_exchanges += 1
-            else:
-                executor.run_plan(self.plans[key], state.amps, m)
-            if marks is not None:
+                self.commit_exchange(state)
+            if marks is not None and what in ('swap', 'seg', 'exchange'):
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
-                marks.append(('seg', ev0, ev1))
+                marks.append(('swap' if what == 'swap' else 'seg', ev0, ev1))
 
     def _sync_token(self, device):
         tok = self.__dict__.get('_tok')

@@ -100,7 +100,7 @@ class FusedPlan:
                                           state.data_ptr(), mptr, batch, mat_batch_stride, _stream(state))
         L.check(rc)
 
-    def run_exchange(self, state: torch.Tensor, mats: torch.Tensor | None, peer_ptrs, rank: int) -> None:
+    def run_exchange(self, state: torch.Tensor, mats: torch.Tensor | None, peer_ptrs, rank: int, perm=None) -> None:
         """Run the plan on `state` with the last pass storing every chunk into the receive buffer of the rank that
         owns it after the block transpose (`peer_ptrs[r]`: device pointer of rank r's buffer, valid on this
         device).  `state` is left in an intermediate layout; the caller swaps shard and buffer afterwards."""
@@ -109,7 +109,8 @@ class FusedPlan:
             raise B200QError('state must be a contiguous tensor of 2^n elements of the plan dtype')
         arr = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
         mptr = mats.data_ptr() if mats is not None else None
-        L.check(L.load().b200q_plan_run_exchange(self._h, state.data_ptr(), mptr, arr, len(peer_ptrs), rank,
+        pm = None if perm is None else (C.c_uint8 * len(perm))(*[int(x) for x in perm])
+        L.check(L.load().b200q_plan_run_exchange(self._h, state.data_ptr(), mptr, arr, len(peer_ptrs), rank, pm,
                                                  _stream(state)))
 
     def __del__(self):

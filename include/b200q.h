@@ -102,16 +102,17 @@ int b200q_plan_run(const b200q_plan_t* plan, void* state, const void* matrices, 
 /* Run passes [first, last) only (per-pass timing in bench.py, overlap with exchanges). */
 int b200q_plan_run_range(const b200q_plan_t* plan, int first_pass, int last_pass, void* state,
                          const void* matrices, int64_t batch, int64_t matrix_batch_stride, void* stream);
-/* Sharded path: the plan of a local segment FUSED with the block transpose that follows it (replaces the
- * exchange of dist_many_targ_gate / dist_swap_gate, distributed.py:130-202, and comm_exchange_arrays,
+/* Sharded path: the plan of a local segment FUSED with the exchange that follows it (replaces the exchanges of
+ * dist_one_targ_gate / dist_many_targ_gate / dist_swap_gate, distributed.py:57-202, and comm_exchange_arrays,
  * communication.py:58-91).  The last pass of the plan does not write the local shard: every 16-byte chunk goes
- * straight into the receive buffer of the rank that owns it after the transpose (peer_buffers[r], device pointers
- * valid on THIS device: peer mappings over NVLink for r != rank, the local receive buffer for r == rank).  The
- * transpose exchanges the log2(n_ranks) rank bits with the top local index bits: element (d << s) | low of this
- * rank lands at (rank << s) | low of rank d.  The caller synchronises the ranks afterwards (all stores are complete
- * when the kernels have finished on every rank) and swaps the roles of shard and receive buffer. */
+ * straight into the receive buffer of the rank that owns it after the exchange (peer_buffers[r], device pointers
+ * valid on THIS device: peer mappings over NVLink for r != rank, the local receive buffer for r == rank).
+ * The exchange is a permutation of the bits of the DISTRIBUTED index (n_local + log2(n_ranks) bits, the top ones
+ * being the rank): perm[j] = destination position of bit j; NULL = the block transpose that swaps the rank bits
+ * with the top local bits.  complex64: perm[0] must be 0.  The caller synchronises the ranks afterwards (all
+ * stores are complete when the kernels have finished on every rank) and swaps the roles of shard and buffer. */
 int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* matrices, void* const* peer_buffers,
-                            int n_ranks, int rank, void* stream);
+                            int n_ranks, int rank, const uint8_t* perm, void* stream);
 /* One gate, no plan object: the direct counterpart of
  *   evolve_state(state, matrix, nqudit, wires)            (qmath.py:485)      controls == NULL
  *   Gate.op_state_control(x, matrix)                      (operation.py:203)  controls != NULL  */

@@ -31,6 +31,9 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
     for (int tid = 0; tid < nthreads; ++tid) fill_coefs<Real>(P, tid, nthreads, coef.data(), m);
     std::vector<OpWord> words(B200Q_MAX_OPS + 1);
     for (int tid = 0; tid < nthreads; ++tid) fill_opwords(P, tid, nthreads, words.data());
+    std::vector<uint64_t> dest_tab(B200Q_DEST_TAB_ENTRIES);
+    if (remote && remote->enabled)
+      for (int tid = 0; tid < nthreads; ++tid) fill_dest_tab(*remote, tid, nthreads, dest_tab.data());
     const Real gscale = P.has_scale ? Real(pass_scale<Real>(P, m)) : Real(1);
     for (uint64_t t = 0; t < ntiles; ++t) {
       const uint64_t cta_base = tile_base(P, t);
@@ -51,10 +54,10 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
           for (int tid = 0; tid < nthreads; ++tid)
             if (P.lean)
               run_round<Real, true>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
-                                    words.data(), gscale, gstate, chunks_per_state, remote);
+                                    words.data(), gscale, gstate, chunks_per_state, remote, dest_tab.data());
             else
               run_round<Real, false>(P, Rd, tabs[r], tid, cta_base, enabled, tile.data(), pool.data(), coef.data(),
-                                     words.data(), gscale, gstate, chunks_per_state, remote);
+                                     words.data(), gscale, gstate, chunks_per_state, remote, dest_tab.data());
         }
       }
     }
@@ -174,13 +177,16 @@ extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, i
   return 0;
 }
 
-// Fused pass + exchange, all ranks in one address space: rank r runs its plan on states[r]; the last pass scatters
-// into buffers[0..W-1] exactly like the kernel does through the NVLink peer mappings.
-extern "C" int hostemu_run_exchange(int n_local, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
-                                    void** states, void** buffers, const void* mats, int n_ranks, char* err_out,
-                                    int err_len) {
+// Fused pass + exchange for ONE rank with all ranks' buffers in one address space: the plan runs on `state`; its
+// last pass scatters into buffers[0..W-1] exactly like the kernel does through the NVLink peer mappings.
+// perm: bit permutation of the distributed index (NULL: block transpose), same convention as the C ABI.
+extern "C" int hostemu_run_exchange_rank(int n_local, int dtype, const b200q_gate_t* gates, int n_gates,
+                                         int chunk_bits, int coalesce_bits, void* state, void** buffers,
+                                         const void* mats, int n_ranks, int rank, const uint8_t* perm, char* err_out,
+                                         int err_len) {
   PlanOptions opt;
   if (chunk_bits) opt.chunk_bits = chunk_bits;
+  if (coalesce_bits >= 0) opt.coalesce_bits = coalesce_bits;
   std::string err;
   Plan* pl = make_plan(n_local, dtype, gates, n_gates, opt, &err);
   if (!pl) {
@@ -189,18 +195,26 @@ extern "C" int hostemu_run_exchange(int n_local, int dtype, const b200q_gate_t* 
   }
   int g = 0;
   while ((1 << g) < n_ranks) ++g;
-  for (int r = 0; r < n_ranks; ++r) {
-    b200q_remote_t R;
-    std::memset(&R, 0, sizeof R);
-    for (int q = 0; q < n_ranks; ++q) R.peer[q] = buffers[q];
-    R.rank = r;
-    R.chunk_shift = n_local - g - (dtype == B200Q_C64 ? 1 : 0);
-    R.enabled = 1;
-    for (size_t i = 0; i < pl->passes.size(); ++i) {
-      const b200q_remote_t* rp = i + 1 == pl->passes.size() ? &R : nullptr;
-      if (dtype == B200Q_C64) run_pass<float>(*pl, pl->passes[i], states[r], mats, 1, 0, rp);
-      else run_pass<double>(*pl, pl->passes[i], states[r], mats, 1, 0, rp);
+  const int vs = dtype == B200Q_C64 ? 1 : 0, nl = n_local, nt = nl + g;
+  b200q_remote_t R;
+  std::memset(&R, 0, sizeof R);
+  for (int q = 0; q < n_ranks; ++q) R.peer[q] = buffers[q];
+  uint8_t pm[48];
+  for (int j = 0; j < nt; ++j) pm[j] = perm ? perm[j] : (uint8_t)j;
+  if (!perm)
+    for (int k = 0; k < g; ++k) { pm[nl - g + k] = (uint8_t)(nl + k); pm[nl + k] = (uint8_t)(nl - g + k); }
+  R.n_chunk_bits = nl - vs;
+  for (int j = vs; j < nl; ++j) R.perm[j - vs] = (uint8_t)(pm[j] - vs);
+  for (int k = 0; k < g; ++k)
+    if ((rank >> k) & 1) {
+      const int pos = pm[nl + k] - vs;
+      R.base |= pos < R.n_chunk_bits ? (1ull << pos) : (1ull << (B200Q_DEST_RANK_SHIFT + pos - R.n_chunk_bits));
     }
+  R.enabled = 1;
+  for (size_t i = 0; i < pl->passes.size(); ++i) {
+    const b200q_remote_t* rp = i + 1 == pl->passes.size() ? &R : nullptr;
+    if (dtype == B200Q_C64) run_pass<float>(*pl, pl->passes[i], state, mats, 1, 0, rp);
+    else run_pass<double>(*pl, pl->passes[i], state, mats, 1, 0, rp);
   }
   delete pl;
   return 0;

@@ -258,44 +258,167 @@ def test_adjoint_lean_ops_with_pending_scalars(cdtype):
         assert np.abs(g - ref).max() / scale < tol, (wires, ctr, g, ref)
 
 
-@pytest.mark.parametrize('world', [2, 4, 8])
-@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
-def test_fused_pass_and_block_transpose(cdtype, world):
-    """`b200q_plan_run_exchange`: the last pass of a local segment scatters every chunk straight into the receive
-    buffer of the rank that owns it after the block transpose.  All ranks emulated in one address space; expected
-    = ordinary run of the segment on every shard followed by the all-to-all transpose in numpy."""
+def _exchange_all_ranks(ops, nl, cdtype, shards, world, perm=None, coalesce_bits=-1):
+    """Every rank's plan with the fused exchange, all ranks in one address space (test-only emulator)."""
     import ctypes as C
     from deepquantum_b200 import _lib as L
     from helpers import hostemu, lower_ops
-    nl = 14
-    rng = np.random.default_rng(world)
+    arr, ng, mats = lower_ops(ops, nl, cdtype)
+    states = [np.ascontiguousarray(s.copy()) for s in shards]
+    bufs = [np.full(2**nl, np.nan + 0j, dtype=cdtype) for _ in range(world)]
+    lib = hostemu()
+    lib.hostemu_run_exchange_rank.restype = C.c_int
+    lib.hostemu_run_exchange_rank.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int,
+                                              C.POINTER(C.c_uint8), C.c_char_p, C.c_int]
+    bp = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    pm = None if perm is None else (C.c_uint8 * len(perm))(*perm)
+    err = C.create_string_buffer(256)
+    for r in range(world):
+        rc = lib.hostemu_run_exchange_rank(nl, L.C64 if cdtype == np.complex64 else L.C128, arr, ng, 11,
+                                           coalesce_bits, states[r].ctypes.data, bp, mats.ctypes.data, world, r, pm,
+                                           err, 256)
+        assert rc == 0, err.value.decode()
+    return bufs
+
+
+def _segment_ops(nl, rng, count=60):
     ops = []
-    for _ in range(60):
+    for _ in range(count):
         w = int(rng.integers(nl))
         c = int((w + 1 + rng.integers(nl - 1)) % nl)
         k = int(rng.integers(5))
         ops.append([(gates_np.H, [w], []), (gates_np.rx(float(rng.uniform(0, 12))), [w], []), (gates_np.X, [w], [c]),
                     (gates_np.S, [w], []), (gates_np.u3(*rng.uniform(0, 6, 3)), [w], [c])][k])
+    return ops
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_fused_pass_and_block_transpose(cdtype, world):
+    """`b200q_plan_run_exchange` with perm = NULL: the last pass of a local segment scatters every chunk straight
+    into the receive buffer of the rank that owns it after the block transpose.  Expected = ordinary run of the
+    segment on every shard followed by the all-to-all transpose in numpy."""
+    nl = 14
+    rng = np.random.default_rng(world)
+    ops = _segment_ops(nl, rng)
     shards = [(rng.normal(size=2**nl) + 1j * rng.normal(size=2**nl)).astype(cdtype) for _ in range(world)]
     expect_local = [emu_run(ops, nl, cdtype, state=s, chunk_bits=11)[0][0] for s in shards]
     blk = 2**nl // world
     expect = [np.concatenate([expect_local[src][dst * blk:(dst + 1) * blk] for src in range(world)])
               for dst in range(world)]
-    arr, ng, mats = lower_ops(ops, nl, cdtype)
-    states = [np.ascontiguousarray(s.copy()) for s in shards]
-    bufs = [np.full(2**nl, np.nan + 0j, dtype=cdtype) for _ in range(world)]
-    lib = hostemu()
-    lib.hostemu_run_exchange.restype = C.c_int
-    lib.hostemu_run_exchange.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int,
-                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int,
-                                         C.c_char_p, C.c_int]
-    sp = (C.c_void_p * world)(*[s.ctypes.data for s in states])
-    bp = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
-    err = C.create_string_buffer(256)
-    rc = lib.hostemu_run_exchange(nl, L.C64 if cdtype == np.complex64 else L.C128, arr, ng, 11, sp, bp,
-                                  mats.ctypes.data, world, err, 256)
-    assert rc == 0, err.value.decode()
+    bufs = _exchange_all_ranks(ops, nl, cdtype, shards, world, coalesce_bits=3)
     tol = 1e-12 if cdtype == np.complex128 else 2e-6
     for dst in range(world):
         assert not np.isnan(bufs[dst]).any()
         assert np.linalg.norm(bufs[dst] - expect[dst]) / np.linalg.norm(expect[dst]) < tol
+
+
+@pytest.mark.parametrize('world', [1, 2, 8])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_fused_pass_and_bit_permutation(cdtype, world):
+    """The exchange as an arbitrary permutation of the bits of the distributed index (rank bits included):
+    expected = segment on every shard, then numpy transposition of the full state seen as a [2]*n tensor."""
+    nl = 13
+    g = world.bit_length() - 1
+    nt = nl + g
+    rng = np.random.default_rng(10 + world)
+    ops = _segment_ops(nl, rng, 40)
+    shards = [(rng.normal(size=2**nl) + 1j * rng.normal(size=2**nl)).astype(cdtype) for _ in range(world)]
+    vs = 1 if cdtype == np.complex64 else 0
+    perm = list(range(vs)) + [int(x) + vs for x in rng.permutation(nt - vs)]      # bit j -> perm[j]
+    local = np.concatenate([emu_run(ops, nl, cdtype, state=s, chunk_bits=11)[0][0] for s in shards])
+    # full[new_index] = local[old_index], new_index = sum bit_j(old) << perm[j]
+    old = np.arange(2**nt, dtype=np.int64)
+    new = np.zeros_like(old)
+    for j in range(nt):
+        new |= ((old >> j) & 1) << perm[j]
+    full = np.empty_like(local)
+    full[new] = local
+    bufs = _exchange_all_ranks(ops, nl, cdtype, shards, world, perm=perm)
+    got = np.concatenate(bufs)
+    assert not np.isnan(got).any()
+    tol = 1e-12 if cdtype == np.complex128 else 2e-6
+    assert np.linalg.norm(got - full) / np.linalg.norm(full) < tol
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_sharded_perm_schedule_all_ranks_in_one_process(world):
+    """The 'perm' schedule of the sharded path (exchanges = bit permutations done by the fused last pass of a
+    segment, layout restored by one permuting exchange): every rank's `ShardedProgram` stepped in lockstep in
+    ONE process, local segments and fused exchanges executed by the CPU emulator of the kernel body, against the
+    dense oracle.  (The NCCL / 'pswap' schedule is covered by tests/test_distributed_gloo.py.)"""
+    import ctypes as C
+    torch = pytest.importorskip('torch')
+    import deepquantum_b200 as dq
+    from deepquantum_b200 import _lib as L
+    from deepquantum_b200.distributed import ShardedProgram
+    from helpers import hostemu
+    from test_distributed_gloo import _build
+
+    n = 10
+    g = world.bit_length() - 1
+    nl = n - g
+    dense = _build(dq.QubitCircuit(n), n)
+    dense.to(torch.double)
+    low = dense._get_program().low
+    mats = low.build_matrices(torch.complex128, 'cpu').detach()
+    ops = [(op.update_matrix().detach().numpy(), op.wires, op.controls) for op in dense.operators]
+    ref = so.run_circuit(ops, n)
+    lib = hostemu()
+    lib.hostemu_run_exchange_rank.restype = C.c_int
+    lib.hostemu_run_exchange_rank.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int,
+                                              C.POINTER(C.c_uint8), C.c_char_p, C.c_int]
+
+    class State:
+        def __init__(self, r):
+            self.amps = torch.zeros(2**nl, dtype=torch.complex128)
+            self.buffer = torch.zeros(2**nl, dtype=torch.complex128)
+            if r == 0:
+                self.amps[0] = 1.0
+
+        def enable_peer_exchange(self):
+            return True
+
+        def peer_buffer_ptrs(self):
+            return [s.buffer.data_ptr() for s in states]
+
+    class Exec:
+        def make_plan(self, nlocal, dtype, structs, exchange=False):
+            return list(structs)
+
+        def _arr(self, structs):
+            return (L.GateStruct * max(1, len(structs)))(*structs)
+
+        def run_plan(self, plan, amps, m):
+            err = C.create_string_buffer(256)
+            mm = np.ascontiguousarray(m.numpy())
+            rc = lib.hostemu_run(nl, L.C128, self._arr(plan), len(plan), 11, 0, 0, 1, amps.data_ptr(), mm.ctypes.data,
+                                 1, 0, None, err, 256)
+            assert rc == 0, err.value.decode()
+
+        def run_plan_exchange(self, plan, amps, m, peers, rank, perm=None):
+            err = C.create_string_buffer(256)
+            mm = np.ascontiguousarray(m.numpy())
+            bp = (C.c_void_p * world)(*peers)
+            pm = None if perm is None else (C.c_uint8 * len(perm))(*perm)
+            rc = lib.hostemu_run_exchange_rank(nl, L.C128, self._arr(plan), len(plan), 11, 3, amps.data_ptr(), bp,
+                                               mm.ctypes.data, world, rank, pm, err, 256)
+            assert rc == 0, err.value.decode()
+
+    states = [State(r) for r in range(world)]
+    progs = [ShardedProgram(low, n, world, r, 'perm') for r in range(world)]
+    ex = Exec()
+    for p in progs:
+        p.fused_exchanges, p._skip_next = 0, False
+    assert all(len(p.steps) == len(progs[0].steps) for p in progs)
+    assert any(s[0] == 'xperm' for s in progs[0].steps)
+    for si in range(len(progs[0].steps)):
+        what = [progs[r].run_step(si, states[r], mats, ex, True) for r in range(world)]
+        assert len(set(what)) == 1, what
+        if what[0] == 'exchange':
+            for r in range(world):
+                ShardedProgram.commit_exchange(states[r])
+    got = torch.cat([s.amps for s in states]).numpy()
+    assert np.linalg.norm(got - ref) < 1e-12, np.linalg.norm(got - ref)

@@ -21,11 +21,21 @@ class PlanOnly:
     def run_plan(self, plan, amps, mats):
         pass
 
+    def run_plan_exchange(self, plan, amps, mats, peers, rank, perm=None):
+        pass
+
 
 class FakeState:
-    def __init__(self):
+    def __init__(self, peer):
         self.amps = torch.zeros(1, dtype=torch.complex64)
         self.buffer = torch.zeros(1, dtype=torch.complex64)
+        self.peer = peer
+
+    def enable_peer_exchange(self):
+        return self.peer
+
+    def peer_buffer_ptrs(self):
+        return [0]
 
 
 def main():
@@ -35,18 +45,15 @@ def main():
     wl.apply_spec(cir, spec)
     low = cir._get_program().low
     mats = low.build_matrices(torch.complex64, 'cpu').detach()
-    sp = ShardedProgram(low, n, world, 0)
-    ex = PlanOnly()
-    # emulate the fused path's plan choice: a segment followed by a swap is planned with exchange=True
-    st = FakeState()
-    orig = ex.make_plan
-    steps = sp.steps
-    idx = {'i': 0}
-    sp.run(st, mats, ex)
-    passes = sum(p.n_passes for p in sp.plans.values())
-    per_seg = [p.n_passes for p in sp.plans.values()]
-    print(f'n={n} depth={depth} world={world}: passes {passes} segments {sp.n_segments} transposes {sp.n_swaps} '
-          f'per segment {per_seg}')
+    import torch.distributed as dist
+    dist.all_reduce = lambda *a, **k: None        # plan-only: no process group
+    for mode in ('pswap', 'perm'):
+        sp = ShardedProgram(low, n, world, 0, mode)
+        sp.run(FakeState(mode == 'perm'), mats, PlanOnly())
+        passes = sum(p.n_passes for p in sp.plans.values())
+        per_seg = [p.n_passes for p in sp.plans.values()]
+        print(f'n={n} depth={depth} world={world} mode={mode}: passes {passes} segments {sp.n_segments} '
+              f'exchanges {sp.n_swaps} per segment {per_seg}')
     one = cir._get_program().plan(torch.complex64)
     print(f'  single device: {one.n_passes} passes')
 

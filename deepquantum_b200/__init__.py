@@ -8,7 +8,7 @@ fails loudly if it (or an sm_100 device) is missing -- there is no CPU fallback.
 """
 __version__ = '0.1.0'
 
-from . import _lib, engine, workloads  # noqa: F401
+from . import _lib, channel, engine, workloads  # noqa: F401
 from ._lib import B200QError  # noqa: F401
 from .circuit import DistributedQubitCircuit, QubitCircuit  # noqa: F401
 from .communication import (cleanup_distributed, comm_exchange_arrays, comm_get_rank, comm_get_world_size,  # noqa: F401
@@ -19,7 +19,9 @@ from .gate import (Barrier, CNOT, Fredkin, Hadamard, Identity, ImaginarySwap, La
                    SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer,  # noqa: F401
                     YLayer, ZLayer)
-from .operation import Gate, Layer, Operation, dtype_map  # noqa: F401
+from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplitudeDamping, PhaseDamping,  # noqa: F401
+                      PhaseFlip)
+from .operation import Channel, Gate, Layer, Operation, dtype_map  # noqa: F401
 from .qmath import evolve_state, evolve_state_controlled, inverse_permutation, multi_kron  # noqa: F401
 from .state import QubitState, amplitude_encoding  # noqa: F401
 from . import photonic  # noqa: F401,E402

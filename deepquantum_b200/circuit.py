@@ -23,7 +23,9 @@ from .gate import (Barrier, CNOT, Fredkin, Hadamard, ImaginarySwap, LatentGate, 
                    TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer, YLayer,
                     ZLayer)
-from .operation import Gate, Layer, Lowering, Operation
+from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplitudeDamping, Pauli, PhaseDamping,
+                      PhaseFlip)
+from .operation import Channel, DenMatLowering, Gate, Layer, Lowering, Operation
 from .state import QubitState, amplitude_encoding
 
 # planner options used by every circuit (overridable for A/B measurements in bench.py)
@@ -33,8 +35,8 @@ PLAN_OPTIONS = {'chunk_bits': 0, 'low_bits': 0, 'max_rounds': 0, 'fuse': True}
 class _Program:
     """Lowered gate program of a circuit + its fused plans per dtype."""
 
-    def __init__(self, nqubit: int, ops, inverse: bool = False):
-        self.low = Lowering(nqubit)
+    def __init__(self, nqubit: int, ops, inverse: bool = False, den_mat: bool = False):
+        self.low = DenMatLowering(nqubit) if den_mat else Lowering(nqubit)
         seq = list(ops)
         for op in (reversed(seq) if inverse else seq):
             op._lower(self.low, inverse)
@@ -44,7 +46,7 @@ class _Program:
     def plan(self, dtype: torch.dtype) -> engine.FusedPlan:
         key = (dtype, tuple(sorted(PLAN_OPTIONS.items())))
         if key not in self.plans:
-            self.plans[key] = engine.FusedPlan(self.low.nqubit, dtype, self.structs, **PLAN_OPTIONS)
+            self.plans[key] = engine.FusedPlan(self.low.state_qubits, dtype, self.structs, **PLAN_OPTIONS)
         return self.plans[key]
 
     @property
@@ -54,7 +56,8 @@ class _Program:
 
 
 class QubitCircuit(Operation):
-    """Quantum circuit on n qubits (statevector only)."""
+    """Quantum circuit on n qubits: state vectors, or density matrices with `den_mat=True` (forward only; run as a
+    2n-qubit amplitude vector through the same fused kernels, see `operation.DenMatLowering`)."""
 
     def __init__(self, nqubit: int, init_state: Any = 'zeros', name: str | None = None, den_mat: bool = False,
                  reupload: bool = False, mps: bool = False, chi: int | None = None, shots: int = 1024) -> None:
@@ -82,12 +85,14 @@ class QubitCircuit(Operation):
         if isinstance(init_state, QubitState):
             assert self.nqubit == init_state.nqubit
             self.init_state = init_state
+            self.den_mat = init_state.den_mat
         else:
-            self.init_state = QubitState(nqubit=self.nqubit, state=init_state)
+            self.init_state = QubitState(nqubit=self.nqubit, state=init_state, den_mat=self.den_mat)
 
     def __add__(self, rhs: 'QubitCircuit') -> 'QubitCircuit':
         assert self.nqubit == rhs.nqubit
-        cir = QubitCircuit(nqubit=self.nqubit, init_state=self.init_state, name=self.name, reupload=self.reupload)
+        cir = QubitCircuit(nqubit=self.nqubit, init_state=self.init_state, name=self.name, den_mat=self.den_mat,
+                           reupload=self.reupload)
         cir.operators = self.operators + rhs.operators
         cir.encoders = self.encoders + rhs.encoders
         cir.observables = rhs.observables
@@ -106,7 +111,7 @@ class QubitCircuit(Operation):
     # ---------------------------------------------------------------------------------------------
     def _get_program(self) -> _Program:
         if self._program is None or self._program_len != len(self.operators):
-            self._program = _Program(self.nqubit, self.operators)
+            self._program = _Program(self.nqubit, self.operators, den_mat=self.den_mat)
             self._program_len = len(self.operators)
         return self._program
 
@@ -140,7 +145,9 @@ class QubitCircuit(Operation):
         return out
 
     def _run(self, state_t: torch.Tensor, data_batch: int | None, lazy_zero: bool) -> torch.Tensor:
-        n = self.nqubit
+        n = 2 * self.nqubit if self.den_mat else self.nqubit
+        if self.den_mat and not lazy_zero:
+            assert state_t.shape[-1] == 2**self.nqubit and state_t.shape[-2] == 2**self.nqubit
         engine.require_cuda(state_t, 'the circuit state (move the circuit with cir.to("cuda"))')
         cdtype = state_t.dtype
         prog = self._get_program()
@@ -161,13 +168,15 @@ class QubitCircuit(Operation):
         mbs = mats.shape[-1] if mats.ndim == 2 else 0
         if mats.ndim == 2 and mats.shape[0] != batch:
             raise ValueError('batch of data and batch of states differ')
-        if torch.is_grad_enabled() and (mats.requires_grad or x.requires_grad):
+        if not self.den_mat and torch.is_grad_enabled() and (mats.requires_grad or x.requires_grad):
             from .adjoint import CircuitFunction
             y = CircuitFunction.apply(x, mats, prog, batch, mbs)
         else:
-            y = x if lazy_zero else x.clone()
-            prog.plan(cdtype).run(y, mats, batch, mbs)
-        y = y.reshape(batch, 2**n, 1)
+            # density matrices are forward only: channels are not invertible, so the reverse sweep of adjoint.py
+            # (which un-computes the state with U^dagger) does not apply; the result carries no grad_fn
+            y = x.detach() if lazy_zero else x.detach().clone()
+            prog.plan(cdtype).run(y, mats.detach(), batch, mbs)
+        y = y.reshape(batch, 2**self.nqubit, -1)
         if data_batch is None and not batched_state:
             y = y.squeeze(0)
         return y
@@ -252,7 +261,8 @@ class QubitCircuit(Operation):
 
     # ---------------------------------------------------------------------------------------------
     def observable(self, wires=None, basis: str = 'z') -> None:
-        self.observables.append(Observable(nqubit=self.nqubit, wires=wires, basis=basis, tsr_mode=False))
+        self.observables.append(Observable(nqubit=self.nqubit, wires=wires, basis=basis, den_mat=self.den_mat,
+                                           tsr_mode=False))
 
     def reset_observable(self) -> None:
         self.observables = nn.ModuleList()
@@ -269,7 +279,8 @@ class QubitCircuit(Operation):
         n = self.nqubit
         st = self.state
         batched = st.ndim == 3
-        flat = st.reshape(-1, 2**n)
+        dm = self.den_mat
+        flat = st.reshape(-1, 4**n if dm else 2**n)
         batch = flat.shape[0]
         groups = {}
         for k, ob in enumerate(self.observables):
@@ -282,13 +293,18 @@ class QubitCircuit(Operation):
         for rot, items in groups.items():
             phi = flat
             if rot:
-                basis_cir = QubitCircuit(n)
+                basis_cir = QubitCircuit(n, den_mat=dm)
                 for w, b in rot:
                     if b == 'y':
                         basis_cir.sdg(w)
                     basis_cir.h(w)
                 basis_cir.to(flat.device, flat.real.dtype)
-                phi = basis_cir(state=flat.reshape(batch, 2**n, 1)).reshape(batch, 2**n)
+                phi = basis_cir(state=flat.reshape(batch, 2**n, -1)).reshape(batch, -1)
+            if dm:
+                # Tr(Z-string rho) = sum_i (+-) Re rho_ii (reference qmath.py:856): the diagonal (2^n of the 4^n
+                # entries, a strided view) goes through the same reduction kernel as amplitudes sqrt(rho_ii)
+                diag = phi.reshape(batch, 2**n, 2**n).diagonal(dim1=-2, dim2=-1).real
+                phi = torch.sqrt(diag.clamp_min(0)).to(flat.dtype).contiguous()
             masks = torch.tensor([m for _, m in items], dtype=torch.int64, device=flat.device)
             vals = expectation_z(phi, n, masks, batch)           # [batch, n_items] float64
             for j, (k, _) in enumerate(items):
@@ -307,10 +323,12 @@ class QubitCircuit(Operation):
         if self.state is None:
             return None
         assert isinstance(self.state, torch.Tensor), 'There is no final state'
-        return _measure(self.state, shots=shots, with_prob=with_prob, wires=wires, block_size=block_size)
+        return _measure(self.state, shots=shots, with_prob=with_prob, wires=wires, den_mat=self.den_mat,
+                        block_size=block_size)
 
     def get_unitary(self) -> torch.Tensor:
         """Global unitary (small n): the circuit applied to the identity (reference circuit.py:467-477)."""
+        assert not self.den_mat
         dim = 2**self.nqubit
         eye = torch.eye(dim, dtype=self.init_state.dtype, device=self.init_state.device)
         prog = self._get_program()
@@ -320,6 +338,7 @@ class QubitCircuit(Operation):
         return y.T
 
     def get_amplitude(self, bits: str) -> torch.Tensor:
+        assert not self.den_mat
         assert isinstance(self.state, torch.Tensor), 'There is no final state'
         assert len(bits) == self.nqubit
         idx = int(bits, 2)
@@ -331,6 +350,13 @@ class QubitCircuit(Operation):
         n = self.nqubit
         wires = list(range(n)) if wires is None else self._convert_indices(wires)
         assert len(bits) == len(wires)
+        if self.den_mat:   # probabilities are the diagonal of rho
+            diag = self.state.reshape(-1, 2**n, 2**n).diagonal(dim1=-2, dim2=-1).real.reshape(-1, *([2] * n))
+            sel = [slice(None)] * (n + 1)
+            for w, b in zip(wires, bits):
+                sel[w + 1] = int(b)
+            p = diag[tuple(sel)].reshape(diag.shape[0], -1).sum(-1)
+            return p if self.state.ndim == 3 else p.squeeze(0)
         flat = self.state.reshape(-1, *([2] * n))
         sel = [slice(None)] * (n + 1)
         for w, b in zip(wires, bits):
@@ -341,7 +367,7 @@ class QubitCircuit(Operation):
 
     def inverse(self, encode: bool = False) -> 'QubitCircuit':
         """Inverse circuit (reference circuit.py:530-555): reversed operators, each `op.inverse()`."""
-        cir = QubitCircuit(nqubit=self.nqubit, name=self.name, reupload=self.reupload)
+        cir = QubitCircuit(nqubit=self.nqubit, name=self.name, den_mat=self.den_mat, reupload=self.reupload)
         for op in reversed(self.operators):
             op_inv = op.inverse()
             cir.operators.append(op_inv)
@@ -391,6 +417,9 @@ class QubitCircuit(Operation):
             for wire in op.wires:
                 for i in wire:
                     self.depth[i] += 1
+        elif isinstance(op, Channel):
+            assert self.den_mat, 'Channels need the density-matrix representation (den_mat=True)'
+            self.operators.append(op)
         else:
             raise NotImplementedError(f'{type(op).__name__} is outside the accelerated statevector path')
         if encode:
@@ -589,6 +618,33 @@ class QubitCircuit(Operation):
 
     def barrier(self, wires=None):
         self.add(Barrier(nqubit=self.nqubit, wires=wires))
+
+    # ---- channels (reference circuit.py:1540-1601) ------------------------------------------------
+    def _channel(self, cls, wires, inputs, encode):
+        assert self.den_mat
+        requires_grad = (not encode) and inputs is None
+        self.add(cls(inputs=inputs, nqubit=self.nqubit, wires=wires, requires_grad=requires_grad), encode=encode)
+
+    def bit_flip(self, wires, inputs=None, encode=False):
+        self._channel(BitFlip, wires, inputs, encode)
+
+    def phase_flip(self, wires, inputs=None, encode=False):
+        self._channel(PhaseFlip, wires, inputs, encode)
+
+    def depolarizing(self, wires, inputs=None, encode=False):
+        self._channel(Depolarizing, wires, inputs, encode)
+
+    def pauli(self, wires, inputs=None, encode=False):
+        self._channel(Pauli, wires, inputs, encode)
+
+    def amp_damp(self, wires, inputs=None, encode=False):
+        self._channel(AmplitudeDamping, wires, inputs, encode)
+
+    def phase_damp(self, wires, inputs=None, encode=False):
+        self._channel(PhaseDamping, wires, inputs, encode)
+
+    def gen_amp_damp(self, wires, inputs=None, encode=False):
+        self._channel(GeneralizedAmplitudeDamping, wires, inputs, encode)
 
     def reset(self, *args, **kwargs):
         raise NotImplementedError('Reset is non-unitary and outside the accelerated path')

@@ -1,9 +1,11 @@
 """Operation / Gate base classes with the reference's interface (operation.py:16-409), lowered to
 the b200q C ABI instead of permute/reshape/matmul.
 
-Only the statevector path is implemented (`den_mat=False`, no MPS): that is the hot path this package
-replaces.  Density-matrix / MPS arguments are accepted for signature
-compatibility and rejected with NotImplementedError.
+Statevector path plus the density-matrix path (section 8f rank 2): a density matrix of
+n qubits is run through the SAME kernels as a 2n-qubit amplitude vector (`DenMatLowering`): `U rho U^dagger` is
+`U` on the row wire and `conj(U)` on the column wire (reference qmath.py:509-540), a Kraus channel is one dense
+superoperator gate `sum_i K_i (x) conj(K_i)` on the (row, column) wire pair (reference operation.py:594-600).
+MPS arguments are accepted for signature compatibility and rejected with NotImplementedError.
 """
 from __future__ import annotations
 
@@ -33,8 +35,6 @@ class Operation(nn.Module):
 
     def __init__(self, name=None, nqubit: int = 1, wires=None, den_mat: bool = False, tsr_mode: bool = False) -> None:
         super().__init__()
-        if den_mat:
-            raise NotImplementedError('deepquantum_b200 accelerates the statevector path only (den_mat=False)')
         self.name = name
         self.nqubit = nqubit
         self.wires = wires
@@ -44,6 +44,9 @@ class Operation(nn.Module):
 
     def tensor_rep(self, x: torch.Tensor) -> torch.Tensor:
         """[..., 2^n(,1)] -> [batch, 2, ..., 2] (reference operation.py:45-55)."""
+        if self.den_mat:
+            assert x.shape[-1] == 2**self.nqubit and x.shape[-2] == 2**self.nqubit
+            return x.reshape([-1] + [2] * (2 * self.nqubit))
         if x.ndim == 1:
             assert x.shape[-1] == 2**self.nqubit
         else:
@@ -52,6 +55,9 @@ class Operation(nn.Module):
 
     def vector_rep(self, x: torch.Tensor) -> torch.Tensor:
         return x.reshape(-1, 2**self.nqubit, 1)
+
+    def matrix_rep(self, x: torch.Tensor) -> torch.Tensor:
+        return x.reshape(-1, 2**self.nqubit, 2**self.nqubit)
 
     def get_unitary(self) -> torch.Tensor:
         raise NotImplementedError
@@ -177,10 +183,6 @@ class Lowering:
                 acc += s
             offs[block] = lst
             total += acc
-        structs = []
-        for kind, targets, ctrl, adj, block, idx, _size, hint in self.records:
-            off = 0 if block == 'none' else bases[block] + offs[block][idx]
-            structs.append(L.make_gate(kind, targets, ctrl, off, adj, hint))
         self.offsets = [0 if r[4] == 'none' else bases[r[4]] + offs[r[4]][r[5]] for r in self.records]
         self.total = max(total, 1)
         # gather indices of the derived diagonals: entry (j, j) of diag(d0, d1, d1, d0) <- source (0,0) / (1,1);
@@ -196,7 +198,16 @@ class Lowering:
                 idx.extend(blockidx)
             self._derived_src = idx
             self.n_primary = bases['derived']
-        return structs
+        return self._make_structs()
+
+    def _make_structs(self):
+        return [L.make_gate(kind, targets, ctrl, off, adj, hint)
+                for (kind, targets, ctrl, adj, _b, _i, _s, hint), off in zip(self.records, self.offsets)]
+
+    @property
+    def state_qubits(self) -> int:
+        """Qubits of the amplitude vector the lowered program runs on."""
+        return self.nqubit
 
     def _gather_from_data(self, cls, lst):
         """All parameters of a gate class as ONE gather from the encoded data vector, when every gate of the class
@@ -235,7 +246,8 @@ class Lowering:
                                                     for g in self.const])
             parts.append(self._const_cache[key])
         if self.dynamic:
-            parts.append(torch.cat([g.update_matrix().reshape(-1) for g in self.dynamic]).to(device=device,
+            parts.append(torch.cat([getattr(g, '_lowered_matrix', g.update_matrix)().reshape(-1)
+                                    for g in self.dynamic]).to(device=device,
                                                                                              dtype=cdtype))
         batched = False
         for cls, lst in self.groups.items():
@@ -266,6 +278,42 @@ class Lowering:
                 self._idx_cache[key] = torch.tensor(self._derived_src, dtype=torch.int64, device=device)
             flat = torch.cat([flat, flat.index_select(-1, self._idx_cache[key])], dim=-1)
         return flat
+
+
+class DenMatLowering(Lowering):
+    """Lowering of a density-matrix circuit onto the 2n-qubit amplitude vector `rho[i, j] -> index i * 2^n + j`
+    (row wire w = bit 2n-1-w, column wire w = bit n-1-w): every gate record becomes the pair `U` on the row wires,
+    `conj(U)` on the column wires (reference qmath.py:509-540 does the two matrix products one after the other, each
+    with a permute + reshape copy of the 4^n-element state); a channel becomes ONE dense gate, the superoperator
+    `sum_i K_i (x) conj(K_i)` on (row wires, column wires) (reference operation.py:594-600 evolves one copy of the
+    state per Kraus operator and sums them).  The matrix buffer is `[flat | conj(flat)]`.  Row and column records
+    act on disjoint bits, so the planner is free to fuse them into the same pass."""
+
+    def add_super(self, chan: 'Channel', wires) -> None:
+        n = self.nqubit
+        w2 = list(wires) + [w + n for w in wires]
+        targets = engine.wires_to_targets(2 * n, w2)
+        self.records.append(('super', tuple(targets), (), False, 'dyn', len(self.dynamic), 4 ** len(w2), 0))
+        self.dynamic.append(chan)
+        self.sources.append(chan)
+
+    @property
+    def state_qubits(self) -> int:
+        return 2 * self.nqubit
+
+    def _make_structs(self):
+        n, out = self.nqubit, []
+        for (kind, targets, ctrl, adj, _b, _i, _s, hint), off in zip(self.records, self.offsets):
+            if kind == 'super':
+                out.append(L.make_gate(L.GATE_MAT, targets, (), off, False, 0))
+                continue
+            out.append(L.make_gate(kind, [t + n for t in targets], [c + n for c in ctrl], off, adj, hint))
+            out.append(L.make_gate(kind, targets, ctrl, 0 if kind == L.GATE_X else off + self.total, adj, hint))
+        return out
+
+    def build_matrices(self, cdtype: torch.dtype, device, batch: int | None = None) -> torch.Tensor:
+        flat = super().build_matrices(cdtype, device, batch)
+        return torch.cat([flat, flat.conj().resolve_conj()], dim=-1).contiguous()
 
 
 class Gate(Operation):
@@ -355,11 +403,24 @@ class Gate(Operation):
             x = self.vector_rep(x).squeeze(0)
         return x
 
+    def op_den_mat(self, x: torch.Tensor) -> torch.Tensor:
+        """Out-of-place `U rho U^dagger` on a `[batch, 2, ..., 2]` (2n axes) tensor (reference operation.py:221-229)."""
+        shape = x.shape
+        flat = x.reshape(-1, 4**self.nqubit).contiguous().clone()
+        _run_den_mat(self, flat)
+        x = flat.reshape(shape)
+        if not self.tsr_mode:
+            x = self.matrix_rep(x).squeeze(0)
+        return x
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not isinstance(x, torch.Tensor):
             return self.op_dist_state(x)
         if not self.tsr_mode:
             x = self.tensor_rep(x)
+        if self.den_mat:
+            assert x.ndim == 2 * self.nqubit + 1
+            return self.op_den_mat(x)
         assert x.ndim == self.nqubit + 1
         return self.op_state(x)
 
@@ -424,6 +485,11 @@ class Layer(Operation):
         if not self.tsr_mode:
             x = self.tensor_rep(x)
         shape = x.shape
+        if self.den_mat:
+            flat = x.reshape(-1, 4**self.nqubit).contiguous().clone()
+            _run_den_mat(self, flat)
+            x = flat.reshape(shape)
+            return x if self.tsr_mode else self.matrix_rep(x).squeeze(0)
         flat = x.reshape(-1, 2**self.nqubit).contiguous().clone()
         for g in self.gates:
             g._apply_to_batch(flat, flat.shape[0])
@@ -436,4 +502,91 @@ class Layer(Operation):
         return self
 
 
-__all__ = ['Operation', 'Gate', 'Layer', 'Lowering', 'apply_complex_fix', 'dtype_map', 'copy']
+def _run_den_mat(op: Operation, flat: torch.Tensor) -> None:
+    """Apply one operation (gate, layer or channel) in place to a contiguous `[batch, 4^n]` density matrix."""
+    engine.require_cuda(flat, 'the density matrix')
+    low = DenMatLowering(op.nqubit)
+    op._lower(low)
+    structs = low.finalize()
+    with torch.no_grad():
+        mats = low.build_matrices(flat.dtype, flat.device)
+        engine.FusedPlan(2 * op.nqubit, flat.dtype, structs).run(flat, mats, flat.shape[0], 0)
+
+
+class Channel(Operation):
+    """Base class of quantum channels (reference operation.py:525-625).  `get_matrix` / `update_matrix` return the
+    stacked Kraus operators like the reference; the lowering uses the superoperator built from them."""
+
+    def __init__(self, inputs: Any = None, name=None, nqubit: int = 1, wires=None, tsr_mode: bool = False,
+                 requires_grad: bool = False) -> None:
+        self.nqubit = nqubit
+        if wires is None:
+            wires = [0]
+        wires = self._convert_indices(wires)
+        super().__init__(name=name, nqubit=nqubit, wires=wires, den_mat=True, tsr_mode=tsr_mode)
+        self.npara = 1
+        self.requires_grad = requires_grad
+        self.init_para(inputs)
+
+    @property
+    def prob(self):
+        return torch.sin(self.theta) ** 2
+
+    def inputs_to_tensor(self, inputs: Any = None) -> torch.Tensor:
+        while isinstance(inputs, list):
+            inputs = inputs[0]
+        if inputs is None:
+            inputs = torch.rand(1)[0] * torch.pi
+        elif not isinstance(inputs, torch.Tensor):
+            inputs = torch.tensor(inputs, dtype=torch.float)
+        return inputs
+
+    def get_matrix(self, theta: Any) -> torch.Tensor:
+        raise NotImplementedError
+
+    def update_matrix(self) -> torch.Tensor:
+        matrix = self.get_matrix(self.theta)
+        self.matrix = matrix.detach()
+        return matrix
+
+    def _lowered_matrix(self) -> torch.Tensor:
+        """Superoperator `sum_i K_i (x) conj(K_i)`, `[4^k, 4^k]` (row wires are the high matrix-index bits)."""
+        k = self.update_matrix()
+        d = k.shape[-1]
+        return torch.einsum('iab,icd->acbd', k, k.conj()).reshape(d * d, d * d)
+
+    def init_para(self, inputs: Any = None) -> None:
+        theta = self.inputs_to_tensor(inputs)
+        if self.requires_grad:
+            self.theta = nn.Parameter(theta)
+        else:
+            self.register_buffer('theta', theta)
+        self.update_matrix()
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        assert isinstance(low, DenMatLowering), 'Channels act on density matrices (den_mat=True)'
+        low.add_super(self, self.wires)
+
+    def op_den_mat(self, x: torch.Tensor) -> torch.Tensor:
+        shape = x.shape
+        flat = x.reshape(-1, 4**self.nqubit).contiguous().clone()
+        _run_den_mat(self, flat)
+        x = flat.reshape(shape)
+        if not self.tsr_mode:
+            x = self.matrix_rep(x).squeeze(0)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.tsr_mode:
+            x = self.tensor_rep(x)
+        assert x.ndim == 2 * self.nqubit + 1
+        return self.op_den_mat(x)
+
+    def inverse(self) -> 'Channel':
+        return self
+
+    def extra_repr(self) -> str:
+        return f'wires={self.wires}, probability={self.prob.item()}'
+
+
+__all__ = ['Operation', 'Gate', 'Layer', 'Channel', 'Lowering', 'DenMatLowering', 'apply_complex_fix', 'dtype_map', 'copy']

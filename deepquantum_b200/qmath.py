@@ -61,7 +61,12 @@ def measure(state: torch.Tensor, shots: int = 1024, with_prob: bool = False, wir
     `block_size` is accepted for signature compatibility (the block size here is fixed by the kernel);
     `generator` optionally seeds the uniforms (CPU generator)."""
     if den_mat:
-        raise NotImplementedError('density matrices are outside the accelerated path')
+        # probabilities are |diag(rho)| (reference qmath.py:600-602, 620): sample the amplitude vector sqrt(|rho_ii|)
+        # with the same kernels -- 2^n of the 4^n entries, a strided view
+        assert state.ndim in (2, 3) and state.shape[-1] == state.shape[-2], 'Please input density matrices'
+        state = torch.sqrt(state.diagonal(dim1=-2, dim2=-1).abs()).to(state.dtype)
+        if state.ndim == 1:
+            state = state.unsqueeze(-1)
     is_single = state.ndim == 1 or (state.ndim == 2 and state.shape[-1] == 1)
     batch = 1 if is_single else state.shape[0]
     flat = state.reshape(batch, -1)

@@ -1,4 +1,4 @@
-"""QubitState with the reference's interface (state.py:14-78)."""
+"""QubitState with the reference's interface (state.py:14-78), state vectors and density matrices."""
 from __future__ import annotations
 
 from typing import Any
@@ -27,6 +27,27 @@ def amplitude_encoding(data: Any, nqubit: int) -> torch.Tensor:
     return state.unsqueeze(-1)
 
 
+def is_power_of_two(n: int) -> bool:
+    return n > 0 and (n & (n - 1)) == 0
+
+
+def is_density_matrix(rho: torch.Tensor) -> bool:
+    """Hermitian, trace one, positive semi-definite; 2-D or batched 3-D (reference qmath.py:117-153)."""
+    if not isinstance(rho, torch.Tensor) or rho.ndim not in (2, 3):
+        return False
+    if not (is_power_of_two(rho.shape[-2]) and is_power_of_two(rho.shape[-1])) or rho.shape[-1] != rho.shape[-2]:
+        return False
+    if rho.ndim == 2:
+        rho = rho.unsqueeze(0)
+    if not torch.allclose(rho, rho.mH):
+        return False
+    trace = rho.diagonal(dim1=-2, dim2=-1).sum(-1)
+    if not torch.allclose(trace, torch.ones_like(trace)):
+        return False
+    tol = 1e-6 if rho.dtype == torch.complex64 else 1e-10
+    return bool(torch.all(torch.linalg.eigvalsh(rho) > -tol))
+
+
 LAZY_NQUBIT = 24  # named initial states above this size are materialised on demand only
 
 
@@ -38,14 +59,12 @@ class QubitState(nn.Module):
 
     def __init__(self, nqubit: int = 1, state: Any = 'zeros', den_mat: bool = False) -> None:
         super().__init__()
-        if den_mat:
-            raise NotImplementedError('deepquantum_b200 accelerates the statevector path only (den_mat=False)')
         self.nqubit = nqubit
         self.den_mat = den_mat
         self.kind = state if isinstance(state, str) else 'data'
         if isinstance(state, str) and state not in ('zeros', 'equal', 'entangle', 'GHZ', 'ghz'):
             raise ValueError(f'unknown initial state {state!r}')
-        self._lazy = isinstance(state, str) and nqubit > LAZY_NQUBIT
+        self._lazy = isinstance(state, str) and nqubit > (LAZY_NQUBIT // 2 if den_mat else LAZY_NQUBIT)
         self.register_buffer('_probe', torch.zeros(1, dtype=torch.cfloat), persistent=False)
         if self._lazy:
             return
@@ -55,9 +74,14 @@ class QubitState(nn.Module):
             if not isinstance(state, torch.Tensor):
                 state = torch.tensor(state, dtype=torch.cfloat)
             ndim = state.ndim
+            if den_mat and state.shape[-1] == 2**nqubit and is_density_matrix(state):
+                self.register_buffer('state', state)
+                return
             vec = amplitude_encoding(data=state, nqubit=nqubit)
             if vec.ndim > ndim:
                 vec = vec.squeeze(0)
+        if den_mat:
+            vec = vec @ vec.mH
         self.register_buffer('state', vec)
 
     @staticmethod
@@ -76,7 +100,8 @@ class QubitState(nn.Module):
     def __getattr__(self, name):
         if name == 'state' and self.__dict__.get('_lazy', False):
             probe = self._buffers['_probe']
-            return self._named(self.kind, self.nqubit, probe.dtype, probe.device)
+            vec = self._named(self.kind, self.nqubit, probe.dtype, probe.device)
+            return vec @ vec.mH if self.den_mat else vec
         return super().__getattr__(name)
 
     @property

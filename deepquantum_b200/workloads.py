@@ -138,6 +138,25 @@ def fock_interferometer_spec(nmode: int = 8, seed: int = SEED):
     return spec
 
 
+def noisy_circuit_spec(nqubit: int, depth: int, seed: int = SEED):
+    """Density-matrix workload: the Clifford+RX layers of `random_clifford_rx_spec`
+    with one channel per qubit after every layer, cycling through the seven channel families."""
+    g = _gen(seed)
+    base = random_clifford_rx_spec(nqubit, depth, seed)
+    per_layer = len(base) // depth
+    names = ['bit_flip', 'phase_flip', 'depolarizing', 'pauli', 'amp_damp', 'phase_damp', 'gen_amp_damp']
+    spec, k = [], 0
+    for d in range(depth):
+        spec += base[d * per_layer:(d + 1) * per_layer]
+        for q in range(nqubit):
+            name = names[k % len(names)]
+            k += 1
+            npar = {'pauli': 4, 'gen_amp_damp': 2}.get(name, 1)
+            prm = (torch.rand(npar, generator=g, dtype=torch.float64) * 0.6 + 0.05).tolist()
+            spec.append({'g': name, 'w': [q], 'p': prm})
+    return spec
+
+
 def count_gates(spec, nqubit):
     n = 0
     for e in spec:
@@ -200,6 +219,10 @@ def apply_spec(cir, spec, cdtype=torch.complex64):
             cir.cnot_ring(e.get('minmax'), e.get('step', 1), e.get('reverse', False))
         elif g == 'barrier':
             cir.barrier()
+        elif g in ('bit_flip', 'phase_flip', 'depolarizing', 'amp_damp', 'phase_damp'):   # den_mat circuits only
+            getattr(cir, g)(w[0], prm[0])
+        elif g in ('pauli', 'gen_amp_damp'):
+            getattr(cir, g)(w[0], list(prm))
         else:
             raise ValueError(g)
     return cir

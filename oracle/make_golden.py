@@ -14,6 +14,8 @@ Files written
   fock.npz            Fock tensor backend (squeezer / beamsplitter / phase shifter) final states
   measure.npz         qmath.measure(with_prob=True): states, measured wires and the probabilities the reference
                       attaches to every outcome it drew (all wires, wire subsets, batched states)
+  denmat.npz          density-matrix circuits (den_mat=True): every gate family + the seven channels, final rho in
+                      c128 and c64, Pauli-string expectations, measure(with_prob=True) probabilities
   dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
 """
 import json
@@ -245,8 +247,59 @@ def measure():
     print('measure.npz:', len(out), 'arrays')
 
 
+def denmat():
+    """Reference density-matrix path (qmath.py:509-540, operation.py:221-262, 594-600, channel.py)."""
+    out = {}
+    cases = {'noisy3': (3, wl.noisy_circuit_spec(3, 4, seed=wl.SEED + 3)),
+             'noisy5': (5, wl.noisy_circuit_spec(5, 6, seed=wl.SEED + 5)),
+             'allgates5': (5, all_gates_spec(5) + wl.noisy_circuit_spec(5, 1, seed=wl.SEED + 55)),
+             'noisy7': (7, wl.noisy_circuit_spec(7, 5, seed=wl.SEED + 7))}
+    obs = [([0], 'z'), ([1], 'x'), ([2], 'y'), ([0, 2], 'zz'), ([0, 1, 2], 'xyz'), ([2, 0], 'yx')]
+    for name, (n, spec) in cases.items():
+        for double in (True, False):
+            cir = dq.QubitCircuit(n, den_mat=True)
+            wl.apply_spec(cir, spec, torch.complex128 if double else torch.complex64)
+            for w, b in obs:
+                cir.observable(w, b)
+            if double:
+                cir.to(torch.double)
+            with torch.no_grad():
+                rho = cir()
+                exp = cir.expectation()
+            tag = 'c128' if double else 'c64'
+            out[f'{name}/{tag}'] = rho.numpy()
+            out[f'{name}/exp_{tag}'] = exp.numpy()
+            if double:
+                for key, wires in (('all', None), ('sub', [2, 0])):
+                    res = dq.qmath.measure(rho, shots=2048, with_prob=True, wires=wires, den_mat=True)
+                    keys = sorted(res)
+                    out[f'{name}/meas_{key}_keys'] = np.array(keys)
+                    out[f'{name}/meas_{key}_probs'] = np.array([float(res[k][1]) for k in keys])
+        out[f'{name}/spec'] = np.array(json.dumps({'n': n, 'spec': spec, 'obs': obs}))
+        print('denmat', name, n, len(spec), 'trace', float(np.trace(out[f'{name}/c128']).real),
+              'purity', float(np.trace(out[f'{name}/c128'] @ out[f'{name}/c128']).real))
+    # a mixed initial state given as a matrix, and a batch of them
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 8, 8, generator=g, dtype=torch.float64) + 1j * torch.randn(2, 8, 8, generator=g,
+                                                                                    dtype=torch.float64)
+    rho0 = a @ a.mH
+    rho0 = rho0 / rho0.diagonal(dim1=-2, dim2=-1).sum(-1).reshape(2, 1, 1)
+    spec = cases['noisy3'][1]
+    cir = dq.QubitCircuit(3, den_mat=True)
+    wl.apply_spec(cir, spec, torch.complex128)
+    cir.to(torch.double)
+    with torch.no_grad():
+        out['mixed3/init'] = rho0.numpy()
+        out['mixed3/single'] = cir(state=rho0[0]).numpy()
+        out['mixed3/batch'] = cir(state=rho0).numpy()
+    np.savez_compressed(os.path.join(OUT, 'denmat.npz'), **out)
+    print('denmat.npz:', len(out), 'arrays')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat']
+    if 'denmat' in which:
+        denmat()
     if 'measure' in which:
         measure()
     if 'gates' in which:

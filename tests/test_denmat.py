@@ -1,0 +1,201 @@
+"""Density-matrix path (reference qmath.py:509-540, operation.py:221-262, 594-600,
+channel.py): oracle pinned by fixtures from the unmodified reference; product lowering (row gate + conjugated
+column gate, channels as superoperator gates on a 2n-qubit amplitude vector) checked on the CPU through the
+emulator of the kernel body and on the GPU through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import deepquantum_b200 as dq
+import denmat_oracle as do
+from conftest import GOLDEN
+from deepquantum_b200 import workloads as wl
+from helpers import emu_run_program
+
+CASES = ['noisy3', 'noisy5', 'allgates5', 'noisy7']
+
+
+def _g():
+    return np.load(os.path.join(GOLDEN, 'denmat.npz'))
+
+
+def _meta(g, case):
+    m = json.loads(str(g[case + '/spec']))
+    return m['n'], m['spec'], m['obs']
+
+
+# ---- oracle vs reference fixtures ------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', CASES)
+def test_oracle_matches_reference(case):
+    g = _g()
+    n, spec, obs = _meta(g, case)
+    rho = do.run_spec(spec, n)
+    ref = g[case + '/c128']
+    assert np.linalg.norm(rho - ref) / np.linalg.norm(ref) < 1e-12
+    exp = [do.expectation_pauli(rho, n, w, b) for w, b in obs]
+    np.testing.assert_allclose(exp, g[case + '/exp_c128'], atol=1e-12)
+    for key, wires in (('all', None), ('sub', [2, 0])):
+        p = do.measure_probs(rho, n, wires)
+        idx = [int(k, 2) for k in g[f'{case}/meas_{key}_keys']]
+        np.testing.assert_allclose(p[idx], g[f'{case}/meas_{key}_probs'], atol=1e-12)
+
+
+def test_oracle_mixed_initial_state():
+    g = _g()
+    n, spec, _ = _meta(g, 'noisy3')
+    np.testing.assert_allclose(do.run_spec(spec, n, g['mixed3/init'][0]), g['mixed3/single'], atol=1e-13)
+
+
+# ---- product host logic on the CPU (emulated kernel body) -------------------------------------------------------
+def _build(n, spec, double, obs=()):
+    cir = dq.QubitCircuit(n, den_mat=True)
+    wl.apply_spec(cir, spec, torch.complex128 if double else torch.complex64)
+    for w, b in obs:
+        cir.observable(w, b)
+    if double:
+        cir.to(torch.double)
+    return cir
+
+
+def test_kraus_operators_match_oracle():
+    th = [0.3, 0.9, 0.5, 1.2]
+    pairs = [(dq.channel.BitFlip, 'bit_flip', 1), (dq.channel.PhaseFlip, 'phase_flip', 1),
+             (dq.channel.Depolarizing, 'depolarizing', 1), (dq.channel.Pauli, 'pauli', 4),
+             (dq.channel.AmplitudeDamping, 'amp_damp', 1), (dq.channel.PhaseDamping, 'phase_damp', 1),
+             (dq.channel.GeneralizedAmplitudeDamping, 'gen_amp_damp', 2)]
+    for cls, name, k in pairs:
+        ch = cls(inputs=th[:k] if k > 1 else th[0]).to(torch.double)
+        ks = ch.update_matrix().numpy()
+        ref = np.stack(do.kraus(name, th[:k]))
+        np.testing.assert_allclose(ks, ref, atol=1e-15, err_msg=name)
+        # trace preservation and the superoperator the lowering uses
+        np.testing.assert_allclose(sum(k_.conj().T @ k_ for k_ in ks), np.eye(2), atol=1e-7)
+        sup = ch._lowered_matrix().numpy()
+        np.testing.assert_allclose(sup, sum(np.kron(k_, k_.conj()) for k_ in ref), atol=1e-15)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_lowering_matches_reference(case):
+    g = _g()
+    n, spec, _ = _meta(g, case)
+    ref = g[case + '/c128']
+    cir = _build(n, spec, True)
+    prog = cir._get_program()
+    assert prog.low.state_qubits == 2 * n
+    out, stats = emu_run_program(prog, 2 * n, np.complex128, chunk_bits=11 if 2 * n > 12 else 0)
+    assert np.linalg.norm(out[0].reshape(ref.shape) - ref) / np.linalg.norm(ref) < 1e-12, stats
+    cir32 = _build(n, spec, False)
+    out32, _ = emu_run_program(cir32._get_program(), 2 * n, np.complex64, chunk_bits=11 if 2 * n > 12 else 0)
+    assert np.linalg.norm(out32[0].reshape(ref.shape) - ref) / np.linalg.norm(ref) < 3e-6
+    # the c64 reference itself is this far from its c128 run
+    ref32 = g[case + '/c64']
+    assert np.linalg.norm(out32[0].reshape(ref.shape) - ref32) / np.linalg.norm(ref) < 3e-6
+
+
+def test_lowering_fuses_row_and_column_gates():
+    """Row and column records act on disjoint bits: a whole noisy layer fits one pass."""
+    n = 5
+    cir = _build(n, wl.noisy_circuit_spec(n, 1, seed=3), False)
+    prog = cir._get_program()
+    out, stats = emu_run_program(prog, 2 * n, np.complex64)
+    assert stats['passes'] <= 2 and len(prog.structs) > 2 * n
+
+
+def test_lowering_mixed_and_batched_initial_state():
+    g = _g()
+    n, spec, _ = _meta(g, 'noisy3')
+    cir = _build(n, spec, True)
+    init = g['mixed3/init']
+    out, _ = emu_run_program(cir._get_program(), 2 * n, np.complex128, state=init.reshape(2, -1), batch=2)
+    np.testing.assert_allclose(out.reshape(2, 8, 8), g['mixed3/batch'], atol=1e-13)
+    np.testing.assert_allclose(out[0].reshape(8, 8), g['mixed3/single'], atol=1e-13)
+
+
+def test_host_api_of_density_matrices():
+    st = dq.QubitState(2, 'entangle', den_mat=True)
+    assert st.state.shape == (4, 4) and abs(st.state[0, 3] - 0.5) < 1e-7
+    assert dq.state.is_density_matrix(st.state)
+    assert not dq.state.is_density_matrix(torch.eye(4, dtype=torch.cfloat))
+    cir = dq.QubitCircuit(2, den_mat=True)
+    cir.h(0)
+    cir.bit_flip(0, 0.2)
+    assert isinstance(cir.operators[1], dq.channel.BitFlip) and cir.operators[1].den_mat
+    with pytest.raises(AssertionError):
+        dq.QubitCircuit(2).bit_flip(0, 0.2)          # reference circuit.py:1542
+    with pytest.raises(AssertionError):
+        cir.get_unitary()                            # reference circuit.py:463-465
+    with pytest.raises(dq.B200QError):
+        cir()                                        # CPU tensors: no fallback
+    assert abs(float(cir.operators[1].prob) - np.sin(np.float32(0.2))**2) < 1e-7
+
+
+# ---- GPU parity ---------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', CASES)
+@pytest.mark.parametrize('double', [True, False])
+def test_gpu_density_matrix_matches_reference(case, double):
+    g = _g()
+    n, spec, obs = _meta(g, case)
+    cir = _build(n, spec, double, [tuple(o) for o in obs])
+    cir.to('cuda')
+    rho = cir()
+    assert rho.shape == (2**n, 2**n)
+    ref = g[case + '/c128']
+    err = np.linalg.norm(rho.cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert err < (1e-10 if double else 3e-6), err
+    exp = cir.expectation().cpu().numpy()
+    np.testing.assert_allclose(exp, g[case + '/exp_c128'], atol=1e-10 if double else 5e-6)
+    if double:
+        for key, wires in (('all', None), ('sub', [2, 0])):
+            res = cir.measure(shots=4096, with_prob=True, wires=wires)
+            pref = dict(zip([str(k) for k in g[f'{case}/meas_{key}_keys']], g[f'{case}/meas_{key}_probs']))
+            full = do.measure_probs(ref, n, wires)
+            assert sum(v[0] for v in res.values()) == 4096
+            for k, (cnt, p) in res.items():
+                assert abs(float(p) - full[int(k, 2)]) < 1e-9
+                if k in pref:
+                    assert abs(float(p) - pref[k]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_mixed_batched_state_and_standalone_modules():
+    g = _g()
+    n, spec, _ = _meta(g, 'noisy3')
+    cir = _build(n, spec, True).to('cuda')
+    init = torch.from_numpy(g['mixed3/init']).cuda()
+    np.testing.assert_allclose(cir(state=init).cpu().numpy(), g['mixed3/batch'], atol=1e-12)
+    np.testing.assert_allclose(cir(state=init[0]).cpu().numpy(), g['mixed3/single'], atol=1e-12)
+    # gate / channel modules called on a density matrix (reference operation.py:221-229, 594-608)
+    rho = init[0]
+    gate = dq.Rx(0.4, nqubit=3, wires=[1], controls=[2], den_mat=True).to(torch.double).to('cuda')
+    chan = dq.channel.AmplitudeDamping(0.7, nqubit=3, wires=[0]).to(torch.double).to('cuda')
+    out = chan(gate(rho)).cpu().numpy()
+    ref = do.evolve_den_mat(g['mixed3/init'][0].reshape(-1), gate.update_matrix().detach().cpu().numpy(), 3, [1], [2])
+    ref = do.apply_channel(ref, do.kraus('amp_damp', [0.7]), 3, 0).reshape(8, 8)
+    np.testing.assert_allclose(out, ref, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_density_matrix_large_properties():
+    """12 qubits (a 24-qubit amplitude vector, 128 MiB): trace 1, Hermitian, purity < 1, and equal to |psi><psi|
+    when there is no channel."""
+    n = 12
+    spec = wl.noisy_circuit_spec(n, 3, seed=9)
+    cir = _build(n, spec, False).to('cuda')
+    rho = cir()
+    tr = rho.diagonal().sum()
+    assert abs(tr.real.item() - 1) < 1e-4 and abs(tr.imag.item()) < 1e-5
+    assert (rho - rho.mH).abs().max().item() < 1e-6
+    purity = (rho.abs() ** 2).sum().item()
+    assert 0 < purity < 0.9
+    pure = wl.random_clifford_rx_spec(n, 3, seed=9)
+    c1 = dq.QubitCircuit(n, den_mat=True)
+    wl.apply_spec(c1, pure)
+    c2 = dq.QubitCircuit(n)
+    wl.apply_spec(c2, pure)
+    rho = c1.to('cuda')()
+    psi = c2.to('cuda')()
+    assert (rho - psi @ psi.mH).abs().max().item() < 2e-6

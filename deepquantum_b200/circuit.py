@@ -18,9 +18,9 @@ from torch import nn
 
 from . import _lib as L
 from . import engine
-from .gate import (Barrier, CNOT, Fredkin, Hadamard, ImaginarySwap, LatentGate, PauliX, PauliY, PauliZ, PhaseShift,
-                   ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz, SDaggerGate, SGate, Swap,
-                   TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
+from .gate import (Barrier, CNOT, Fredkin, Hadamard, HamiltonianGate, ImaginarySwap, LatentGate, PauliX, PauliY, PauliZ,
+                   PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz, SDaggerGate,
+                   SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer, YLayer,
                     ZLayer)
 from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplitudeDamping, Pauli, PhaseDamping,
@@ -576,8 +576,13 @@ class QubitCircuit(Operation):
         self.add(LatentGate(inputs=inputs, nqubit=self.nqubit, wires=wires, minmax=minmax, controls=controls,
                             name=name, requires_grad=requires_grad), encode=encode)
 
-    def hamiltonian(self, *args, **kwargs):
-        raise NotImplementedError('HamiltonianGate is not part of the accelerated path yet (SURVEY.md section 8f)')
+    def hamiltonian(self, hamiltonian, t=None, wires=None, minmax=None, controls=None, encode=False,
+                    name='hamiltonian'):
+        """`exp(-i H t)` (reference circuit.py:1450-1476)."""
+        requires_grad = (not encode) and t is None
+        self.add(HamiltonianGate(hamiltonian=hamiltonian, t=t, nqubit=self.nqubit, wires=wires, minmax=minmax,
+                                 controls=controls, name=name, den_mat=self.den_mat, requires_grad=requires_grad),
+                 encode=encode)
 
     def _const_layer(self, cls, wires):
         self.add(cls(nqubit=self.nqubit, wires=wires))

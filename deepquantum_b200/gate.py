@@ -663,6 +663,121 @@ class LatentGate(ArbitraryGate):
         self.npara = self.latent.numel()
 
 
+class HamiltonianGate(ArbitraryGate):
+    """`exp(-i H t)` on `wires` (reference gate.py:2867-3024): `hamiltonian` is a Pauli-sum list such as
+    `[[0.5, 'x0y1'], [-1, 'z3y1']]` (then the gate spans the min..max wire it names) or a Hermitian matrix on
+    `wires` / `minmax`.  The matrix exponential is a torch call on the 2^k x 2^k block, differentiable in `t`;
+    the block is applied by the dense k-target kernel path (k <= 4)."""
+
+    _matrix_source = 'dyn'
+
+    def __init__(self, hamiltonian, t=None, nqubit=1, wires=None, minmax=None, controls=None,
+                 name='HamiltonianGate', den_mat=False, tsr_mode=False, requires_grad=False) -> None:
+        self.nqubit = nqubit
+        self.ham_lst = None
+        if isinstance(hamiltonian, list):
+            self.ham_lst = hamiltonian
+            wires = None
+            minmax = self.get_minmax(hamiltonian)
+        super().__init__(name=name, nqubit=nqubit, wires=wires, minmax=minmax, controls=controls, den_mat=den_mat,
+                         tsr_mode=tsr_mode)
+        self.npara = 1
+        self.requires_grad = requires_grad
+        self.register_buffer('x', torch.tensor([[0, 1], [1, 0]], dtype=torch.cfloat))
+        self.register_buffer('y', torch.tensor([[0, -1j], [1j, 0]], dtype=torch.cfloat))
+        self.register_buffer('z', torch.tensor([[1, 0], [0, -1]], dtype=torch.cfloat))
+        self.init_para([hamiltonian, t])
+
+    def _apply(self, fn: Any) -> 'HamiltonianGate':
+        from .operation import apply_complex_fix
+        names = [k for k in ('x', 'y', 'z', 'ham_tsr') if k in self._buffers]
+        tensors = {k: self._buffers.pop(k) for k in names}
+        nn.Module._apply(self, fn)
+        for key, value in apply_complex_fix(fn, tensors).items():
+            self.register_buffer(key, value)
+        return self
+
+    @staticmethod
+    def _convert_hamiltonian(hamiltonian: list) -> list:
+        if len(hamiltonian) == 2 and isinstance(hamiltonian[1], str):
+            hamiltonian = [hamiltonian]
+        assert all(isinstance(i, list) for i in hamiltonian), 'Invalid input type'
+        for pair in hamiltonian:
+            assert isinstance(pair[1], str), 'Invalid input type'
+        return hamiltonian
+
+    def get_minmax(self, hamiltonian: list) -> list[int]:
+        lo, hi = self.nqubit - 1, 0
+        for pair in self._convert_hamiltonian(hamiltonian):
+            for i in pair[1][1::2]:
+                lo, hi = min(lo, int(i)), max(hi, int(i))
+        return [lo, hi]
+
+    def inputs_to_tensor(self, inputs=None):
+        if inputs is None:
+            return self.ham_tsr, torch.rand(1)[0]
+        ham, t = inputs
+        if ham is None:
+            ham_tsr = self.ham_tsr
+        elif isinstance(ham, list):
+            ham = self._convert_hamiltonian(ham)
+            paulis = {'x': self.x, 'y': self.y, 'z': self.z}
+            identity = torch.eye(2, dtype=self.x.dtype, device=self.x.device)
+            lo, hi = self.get_minmax(ham)
+            ham_tsr = None
+            for coeff, string in ham:
+                lst = [identity] * self.nqubit
+                for wire, key in zip(string[1::2], string[::2]):
+                    lst[int(wire)] = paulis[key.lower()]
+                term = lst[lo]
+                for m in lst[lo + 1:hi + 1]:
+                    term = torch.kron(term, m)
+                ham_tsr = term * coeff if ham_tsr is None else ham_tsr + term * coeff
+        elif not isinstance(ham, torch.Tensor):
+            ham_tsr = torch.tensor(ham, dtype=self.x.dtype, device=self.x.device)
+        else:
+            ham_tsr = ham
+        assert torch.allclose(ham_tsr, ham_tsr.mH)
+        if t is None:
+            t = torch.rand(1)[0]
+        elif not isinstance(t, (torch.Tensor, nn.Parameter)):
+            t = torch.tensor(t, dtype=torch.float)
+        return ham_tsr, t
+
+    def get_matrix(self, hamiltonian, t) -> torch.Tensor:
+        ham, t = self.inputs_to_tensor([hamiltonian, t])
+        return torch.linalg.matrix_exp(-1j * ham * t)
+
+    def update_matrix(self) -> torch.Tensor:
+        t = -self.t if self.inv_mode else self.t
+        matrix = self.get_matrix(self.ham_tsr, t)
+        assert matrix.shape[-1] == matrix.shape[-2] == 2 ** len(self.wires)
+        self.matrix = matrix.detach()
+        return matrix
+
+    def get_derivative(self, t) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            t = torch.tensor(t, dtype=torch.float)
+        du = torch.autograd.functional.jacobian(lambda v: torch.view_as_real(self.get_matrix(self.ham_tsr, v)),
+                                                t.squeeze())
+        return du[..., 0] + du[..., 1] * 1j
+
+    def init_para(self, inputs=None) -> None:
+        ham, t = self.inputs_to_tensor(inputs)
+        self.register_buffer('ham_tsr', ham)
+        if self.requires_grad:
+            self.t = nn.Parameter(t)
+        else:
+            if 't' in self._parameters:
+                del self._parameters['t']
+            self.register_buffer('t', t)
+        self.update_matrix()
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        # `inv_mode` is folded into the matrix (t -> -t); a further inversion by the circuit is an adjoint record
+        low.add(self, self._kind, self.wires, self.controls, adjoint=inverse)
+
+
 class Barrier(Gate):
     """No-op (reference gate.py:3097-3126); never a fusion barrier."""
 

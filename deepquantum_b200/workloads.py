@@ -219,6 +219,13 @@ def apply_spec(cir, spec, cdtype=torch.complex64):
             cir.cnot_ring(e.get('minmax'), e.get('step', 1), e.get('reverse', False))
         elif g == 'barrier':
             cir.barrier()
+        elif g == 'hamiltonian':
+            if 'ham' in e:       # Pauli-sum list, spans the min..max wire it names
+                cir.hamiltonian(e['ham'], prm[0], controls=c)
+            else:
+                h = torch.complex(torch.tensor(e['h_re'], dtype=torch.float64),
+                                  torch.tensor(e['h_im'], dtype=torch.float64))
+                cir.hamiltonian(h.to(cdtype), prm[0], wires=w, controls=c)
         elif g in ('bit_flip', 'phase_flip', 'depolarizing', 'amp_damp', 'phase_damp'):   # den_mat circuits only
             getattr(cir, g)(w[0], prm[0])
         elif g in ('pauli', 'gen_amp_damp'):

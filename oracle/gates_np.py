@@ -164,6 +164,30 @@ def lower_entry(entry, nqubit):
     if g == 'any':
         u = np.asarray(entry['u_re']) + 1j * np.asarray(entry['u_im'])
         return [(u, w, c)]
+    if g == 'hamiltonian':  # exp(-i H t), gate.py:2952-2994
+        from scipy.linalg import expm
+        if 'ham' in entry:
+            # the Pauli sum is accumulated in complex64 (gate.py:2962-2978), over the wires min..max it names
+            paulis = {'x': X.astype(np.complex64), 'y': Y.astype(np.complex64), 'z': Z.astype(np.complex64)}
+            pairs = entry['ham']
+            if len(pairs) == 2 and isinstance(pairs[1], str):   # a single [coeff, string] pair, gate.py:2931-2932
+                pairs = [pairs]
+            named = [int(i) for _, s_ in pairs for i in s_[1::2]]
+            lo, hi = min(named), max(named)
+            ham = None
+            for coeff, string in pairs:
+                lst = [np.eye(2, dtype=np.complex64)] * nqubit
+                for wire, key in zip(string[1::2], string[::2]):
+                    lst[int(wire)] = paulis[key.lower()]
+                term = lst[lo]
+                for m in lst[lo + 1:hi + 1]:
+                    term = np.kron(term, m)
+                term = (term * np.float32(coeff)).astype(np.complex64)
+                ham = term if ham is None else (ham + term).astype(np.complex64)
+            w = list(range(lo, hi + 1))
+        else:
+            ham = np.asarray(entry['h_re']) + 1j * np.asarray(entry['h_im'])
+        return [(expm(-1j * ham.astype(np.complex128) * prm[0]), w, c)]
     # ---- layers (layer.py:204-483): one gate per wire -------------------------------------------
     if g in ('xlayer', 'ylayer', 'zlayer', 'hlayer'):
         ws = w if w else list(range(nqubit))

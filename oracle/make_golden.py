@@ -16,6 +16,7 @@ Files written
                       attaches to every outcome it drew (all wires, wire subsets, batched states)
   denmat.npz          density-matrix circuits (den_mat=True): every gate family + the seven channels, final rho in
                       c128 and c64, Pauli-string expectations, measure(with_prob=True) probabilities
+  hamiltonian.npz     circuits with HamiltonianGate blocks (Pauli-sum and matrix form, controlled), states and rho
   dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
 """
 import json
@@ -247,6 +248,45 @@ def measure():
     print('measure.npz:', len(out), 'arrays')
 
 
+def hamiltonian_spec(n=6, seed=21):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(4, 4, generator=g, dtype=torch.float64) + 1j * torch.randn(4, 4, generator=g, dtype=torch.float64)
+    h2 = (a + a.mH) / 2
+    a = torch.randn(8, 8, generator=g, dtype=torch.float64) + 1j * torch.randn(8, 8, generator=g, dtype=torch.float64)
+    h3 = (a + a.mH) / 2
+    return [{'g': 'hlayer'},
+            {'g': 'hamiltonian', 'ham': [[0.5, 'x0y1'], [-1, 'z2y1']], 'p': [0.7]},
+            {'g': 'rx', 'w': [3], 'p': [1.1]},
+            {'g': 'hamiltonian', 'w': [4, 1], 'c': [5], 'p': [0.37], 'h_re': h2.real.tolist(), 'h_im': h2.imag.tolist()},
+            {'g': 'cnot', 'w': [5, 0]},
+            {'g': 'hamiltonian', 'ham': [[0.3, 'Z2Z5'], [0.8, 'x3'], [-0.25, 'y4z2']], 'p': [1.9]},
+            {'g': 'hamiltonian', 'w': [0, 5, 3], 'p': [0.21], 'h_re': h3.real.tolist(), 'h_im': h3.imag.tolist()},
+            {'g': 'hamiltonian', 'ham': [1.5, 'y3'], 'c': [0, 1], 'p': [0.4]}]
+
+
+def hamiltonian():
+    out = {}
+    n, spec = 6, hamiltonian_spec()
+    for double in (True, False):
+        tag = 'c128' if double else 'c64'
+        out['ham6/' + tag] = run_ref(spec, n, double)
+        cir = dq.QubitCircuit(n, den_mat=True)
+        wl.apply_spec(cir, spec, torch.complex128 if double else torch.complex64)
+        if double:
+            cir.to(torch.double)
+        with torch.no_grad():
+            out['ham6/rho_' + tag] = cir().numpy()
+    # the inverse circuit undoes it (t -> -t), reference circuit.py:530-555
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, spec, torch.complex128)
+    cir.to(torch.double)
+    with torch.no_grad():
+        out['ham6/inv_c128'] = cir.inverse()(state=cir()).reshape(-1).numpy()
+    out['ham6/spec'] = np.array(json.dumps({'n': n, 'spec': spec}))
+    np.savez_compressed(os.path.join(OUT, 'hamiltonian.npz'), **out)
+    print('hamiltonian.npz:', len(out), 'arrays', float(np.linalg.norm(out['ham6/c128'])), abs(out['ham6/inv_c128'][0]))
+
+
 def denmat():
     """Reference density-matrix path (qmath.py:509-540, operation.py:221-262, 594-600, channel.py)."""
     out = {}
@@ -297,9 +337,11 @@ def denmat():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian']
     if 'denmat' in which:
         denmat()
+    if 'hamiltonian' in which:
+        hamiltonian()
     if 'measure' in which:
         measure()
     if 'gates' in which:

@@ -27,6 +27,7 @@ def _mat(entries) -> torch.Tensor:
 
 class _OneParam(Channel):
     _name = None
+    _parity_kraus = True   # every Kraus operator below is diagonal or anti-diagonal
 
     def __init__(self, inputs: Any = None, nqubit: int = 1, wires=None, tsr_mode: bool = False,
                  requires_grad: bool = False) -> None:
@@ -47,6 +48,7 @@ class BitFlip(_OneParam):
 class PhaseFlip(_OneParam):
     """rho -> (1-p) rho + p Z rho Z (reference channel.py:58-97)."""
     _name = 'PhaseFlip'
+    _diagonal_kraus = True
 
     def get_matrix(self, theta: Any) -> torch.Tensor:
         prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
@@ -109,6 +111,7 @@ class AmplitudeDamping(_OneParam):
 class PhaseDamping(_OneParam):
     """K0 = diag(1, sqrt(1-p)), K1 = sqrt(p) |1><1| (reference channel.py:266-314)."""
     _name = 'PhaseDamping'
+    _diagonal_kraus = True
 
     def get_matrix(self, theta: Any) -> torch.Tensor:
         prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2

@@ -293,7 +293,19 @@ class DenMatLowering(Lowering):
         n = self.nqubit
         w2 = list(wires) + [w + n for w in wires]
         targets = engine.wires_to_targets(2 * n, w2)
-        self.records.append(('super', tuple(targets), (), False, 'dyn', len(self.dynamic), 4 ** len(w2), 0))
+        # channels whose Kraus operators are all diagonal (phase flip, phase damping) have a DIAGONAL superoperator:
+        # no tile bits, no amplitude moves, fusable anywhere
+        kind, size = 'super', 4 ** len(w2)
+        if getattr(chan, '_diagonal_kraus', False):
+            kind = 'super_diag'
+        elif getattr(chan, '_parity_kraus', False) and len(wires) == 1:
+            # every Kraus operator diagonal or anti-diagonal: the superoperator keeps the parity row ^ column, so it is
+            # CX(row->col) . [M1 on row if parity 1, M0 on row if parity 0] . CX(row->col) -- register-kind ops only
+            # (a dense 2-target op needs its own kind of round inside a pass and blocks the fusion of its
+            # neighbours: 12-qubit noisy workload of tools/bench_denmat.py, 47 passes / 232 rounds with dense
+            # superoperators, 21 passes / 69 rounds with the parity blocks)
+            kind, size = 'super_parity', 8
+        self.records.append((kind, tuple(targets), (), False, 'dyn', len(self.dynamic), size, 0))
         self.dynamic.append(chan)
         self.sources.append(chan)
 
@@ -304,8 +316,15 @@ class DenMatLowering(Lowering):
     def _make_structs(self):
         n, out = self.nqubit, []
         for (kind, targets, ctrl, adj, _b, _i, _s, hint), off in zip(self.records, self.offsets):
-            if kind == 'super':
-                out.append(L.make_gate(L.GATE_MAT, targets, (), off, False, 0))
+            if kind in ('super', 'super_diag'):
+                out.append(L.make_gate(L.GATE_MAT if kind == 'super' else L.GATE_DIAG, targets, (), off, False, 0))
+                continue
+            if kind == 'super_parity':
+                col, row = targets
+                cx = L.make_gate(L.GATE_X, [col], [row], 0, False, 0)
+                flip = L.make_gate(L.GATE_X, [col], [], 0, False, 0)
+                out += [cx, L.make_gate(L.GATE_MAT, [row], [col], off, False, 0), flip,
+                        L.make_gate(L.GATE_MAT, [row], [col], off + 4, False, 0), flip, cx]
                 continue
             out.append(L.make_gate(kind, [t + n for t in targets], [c + n for c in ctrl], off, adj, hint))
             out.append(L.make_gate(kind, targets, ctrl, 0 if kind == L.GATE_X else off + self.total, adj, hint))
@@ -549,11 +568,22 @@ class Channel(Operation):
         self.matrix = matrix.detach()
         return matrix
 
+    _diagonal_kraus = False   # all Kraus operators diagonal: the superoperator is a diagonal gate
+    _parity_kraus = False     # all Kraus operators diagonal or anti-diagonal (one wire): two 2x2 parity blocks
+
     def _lowered_matrix(self) -> torch.Tensor:
-        """Superoperator `sum_i K_i (x) conj(K_i)`, `[4^k, 4^k]` (row wires are the high matrix-index bits)."""
+        """Superoperator `sum_i K_i (x) conj(K_i)`, `[4^k, 4^k]` (row wires are the high matrix-index bits); for
+        parity-preserving one-wire channels its two 2x2 blocks `[M1 | M0]` acting on the row bit when
+        row ^ column = 1 / 0 (see `DenMatLowering.add_super`)."""
         k = self.update_matrix()
         d = k.shape[-1]
-        return torch.einsum('iab,icd->acbd', k, k.conj()).reshape(d * d, d * d)
+        sup = torch.einsum('iab,icd->acbd', k, k.conj())          # [row', col', row, col]
+        if self._parity_kraus and not self._diagonal_kraus and d == 2:
+            i = torch.arange(2, device=k.device)
+            m0 = sup[i[:, None], i[:, None], i[None, :], i[None, :]]
+            m1 = sup[i[:, None], 1 - i[:, None], i[None, :], 1 - i[None, :]]
+            return torch.cat([m1.reshape(-1), m0.reshape(-1)])
+        return sup.reshape(d * d, d * d)
 
     def init_para(self, inputs: Any = None) -> None:
         theta = self.inputs_to_tensor(inputs)

@@ -73,8 +73,53 @@ def test_kraus_operators_match_oracle():
         np.testing.assert_allclose(ks, ref, atol=1e-15, err_msg=name)
         # trace preservation and the superoperator the lowering uses
         np.testing.assert_allclose(sum(k_.conj().T @ k_ for k_ in ks), np.eye(2), atol=1e-7)
-        sup = ch._lowered_matrix().numpy()
-        np.testing.assert_allclose(sup, sum(np.kron(k_, k_.conj()) for k_ in ref), atol=1e-15)
+        full = sum(np.kron(k_, k_.conj()) for k_ in ref).reshape(2, 2, 2, 2)     # [row', col', row, col]
+        low = ch._lowered_matrix().numpy()
+        if ch._diagonal_kraus:
+            np.testing.assert_allclose(low, full.reshape(4, 4), atol=1e-15)
+            assert np.count_nonzero(low - np.diag(np.diagonal(low))) == 0
+        else:       # parity blocks [M1 | M0]; everything outside them is zero
+            m1, m0 = low[:4].reshape(2, 2), low[4:].reshape(2, 2)
+            rebuilt = np.zeros((2, 2, 2, 2), dtype=complex)
+            for a in range(2):
+                for b in range(2):
+                    rebuilt[a, a, b, b] = m0[a, b]
+                    rebuilt[a, 1 - a, b, 1 - b] = m1[a, b]
+            np.testing.assert_allclose(rebuilt, full, atol=1e-15, err_msg=name)
+
+
+def test_custom_channel_uses_dense_superoperator():
+    """A channel outside the parity-preserving family (Kraus operators H-rotated) goes through the dense 2-target op."""
+    class Rotated(dq.Channel):
+        def get_matrix(self, theta):
+            p = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
+            h = torch.tensor([[1, 1], [1, -1]], dtype=torch.cfloat) / 2**0.5
+            z = torch.tensor([[1, 0], [0, -1]], dtype=torch.cfloat)
+            return torch.stack([torch.sqrt(1 - p) * torch.eye(2, dtype=torch.cfloat), torch.sqrt(p) * (h @ z)])
+
+    n = 3
+    cir = dq.QubitCircuit(n, den_mat=True)
+    cir.hlayer()
+    cir.rx(1, 0.4)
+    cir.add(Rotated(0.6, nqubit=n, wires=[1]))
+    cir.cnot(1, 2)
+    cir.add(Rotated(0.3, nqubit=n, wires=[2]))
+    cir.to(torch.double)
+    out, _ = emu_run_program(cir._get_program(), 2 * n, np.complex128)
+    rho = np.zeros(4**n, dtype=complex)
+    rho[0] = 1
+    hm = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    import gates_np
+    for w in range(n):
+        rho = do.evolve_den_mat(rho, gates_np.H, n, [w])
+    rho = do.evolve_den_mat(rho, gates_np.rx(gates_np.f32(0.4)), n, [1])
+    for th, w in ((0.6, 1), (0.3, 2)):
+        if w == 2:
+            rho = do.evolve_den_mat(rho, gates_np.X, n, [2], [1])
+        p = np.sin(np.float64(np.float32(th))) ** 2
+        hz = (hm.astype(np.complex64) @ np.diag([1, -1]).astype(np.complex64)).astype(complex)
+        rho = do.apply_channel(rho, [np.sqrt(1 - p) * np.eye(2), np.sqrt(p) * hz], n, w)
+    np.testing.assert_allclose(out[0], rho, atol=1e-7)
 
 
 @pytest.mark.parametrize('case', CASES)

@@ -14,7 +14,8 @@ from .circuit import DistributedQubitCircuit, QubitCircuit  # noqa: F401
 from .communication import (cleanup_distributed, comm_exchange_arrays, comm_get_rank, comm_get_world_size,  # noqa: F401
                             setup_distributed)
 from .distributed import DistributedQubitState  # noqa: F401
-from .gate import (Barrier, CNOT, Fredkin, Hadamard, HamiltonianGate, Identity, ImaginarySwap, LatentGate,  # noqa: F401
+from .gate import (Barrier, CNOT, CombinedSingleGate, Fredkin, Hadamard, HamiltonianGate, Identity, ImaginarySwap,  # noqa: F401
+                   LatentGate,
                    PauliX, PauliY, PauliZ, PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz,
                    SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer,  # noqa: F401

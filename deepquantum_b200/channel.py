@@ -11,38 +11,63 @@ import torch
 
 from .operation import Channel
 
-_I = torch.tensor([[1, 0], [0, 1]], dtype=torch.cfloat)
-_X = torch.tensor([[0, 1], [1, 0]], dtype=torch.cfloat)
-_Y = torch.tensor([[0, -1j], [1j, 0]], dtype=torch.cfloat)
-_Z = torch.tensor([[1, 0], [0, -1]], dtype=torch.cfloat)
 
+def _kraus(entries) -> torch.Tensor:
+    """[[k00, k01, k10, k11], ...] of broadcastable real/complex tensors `[...]` -> `[..., n_kraus, 2, 2]` complex."""
+    shape = torch.broadcast_shapes(*[torch.as_tensor(e).shape for k in entries for e in k if isinstance(e, torch.Tensor)])
+    ref = next(e for k in entries for e in k if isinstance(e, torch.Tensor))
 
-def _paulis(device):
-    return _I.to(device), _X.to(device), _Y.to(device), _Z.to(device)
-
-
-def _mat(entries) -> torch.Tensor:
-    return torch.stack(entries).reshape(2, 2)
+    def full(e):
+        if not isinstance(e, torch.Tensor):
+            e = torch.full(shape, e, dtype=ref.dtype, device=ref.device)
+        return (e + 0j).expand(shape)
+    return torch.stack([torch.stack([full(e) for e in k], dim=-1).reshape(*shape, 2, 2) for k in entries], dim=-3)
 
 
 class _OneParam(Channel):
+    """Built-in channels: `_kraus_of(prob)` gives the Kraus operators for `prob = sin(theta)^2` of shape
+    `[..., npara]`, vectorised over leading dimensions, so that all channels of one class in a circuit are evaluated
+    by ONE batched call per forward (`_batched_matrix`, consumed by `Lowering.build_matrices`)."""
     _name = None
     _parity_kraus = True   # every Kraus operator below is diagonal or anti-diagonal
+    _batched = None
 
     def __init__(self, inputs: Any = None, nqubit: int = 1, wires=None, tsr_mode: bool = False,
                  requires_grad: bool = False) -> None:
         super().__init__(inputs=inputs, name=self._name, nqubit=nqubit, wires=wires, tsr_mode=tsr_mode,
                          requires_grad=requires_grad)
 
+    @staticmethod
+    def _kraus_of(prob: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def get_matrix(self, theta: Any) -> torch.Tensor:
+        theta = self.inputs_to_tensor(theta).reshape(-1)
+        return self._kraus_of(torch.sin(theta) ** 2)
+
+    def _param_list(self):
+        if self._batched is not None:      # [batch, npara] set by QubitCircuit for 2-D data
+            return [self._batched[:, i] for i in range(self._batched.shape[1])]
+        theta = self.theta.reshape(-1)
+        return [theta[i] for i in range(self.npara)]
+
+    @classmethod
+    def _batched_matrix(cls, p: torch.Tensor) -> torch.Tensor:
+        """`[..., N, npara]` angles -> `[..., N, 1, size]` lowered blocks (`Channel._lower_kraus`)."""
+        low = cls._lower_kraus(cls._kraus_of(torch.sin(p) ** 2))
+        return low.reshape(*low.shape[:-1], 1, low.shape[-1]) if low.ndim == p.ndim else \
+            low.reshape(*p.shape[:-1], 1, -1)
+
 
 class BitFlip(_OneParam):
     """rho -> (1-p) rho + p X rho X (reference channel.py:16-55)."""
     _name = 'BitFlip'
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        i, x, _, _ = _paulis(prob.device)
-        return torch.stack([torch.sqrt(1 - prob) * i, torch.sqrt(prob) * x])
+    @staticmethod
+    def _kraus_of(prob):
+        p = prob[..., 0]
+        a, b = torch.sqrt(1 - p), torch.sqrt(p)
+        return _kraus([[a, 0, 0, a], [0, b, b, 0]])
 
 
 class PhaseFlip(_OneParam):
@@ -50,21 +75,22 @@ class PhaseFlip(_OneParam):
     _name = 'PhaseFlip'
     _diagonal_kraus = True
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        i, _, _, z = _paulis(prob.device)
-        return torch.stack([torch.sqrt(1 - prob) * i, torch.sqrt(prob) * z])
+    @staticmethod
+    def _kraus_of(prob):
+        p = prob[..., 0]
+        a, b = torch.sqrt(1 - p), torch.sqrt(p)
+        return _kraus([[a, 0, 0, a], [b, 0, 0, -b]])
 
 
 class Depolarizing(_OneParam):
     """rho -> (1-p) rho + p/3 (X rho X + Y rho Y + Z rho Z) (reference channel.py:100-149)."""
     _name = 'Depolarizing'
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        i, x, y, z = _paulis(prob.device)
-        s = torch.sqrt(prob / 3)
-        return torch.stack([torch.sqrt(1 - prob) * i, s * x, s * y, s * z])
+    @staticmethod
+    def _kraus_of(prob):
+        p = prob[..., 0]
+        a, s = torch.sqrt(1 - p), torch.sqrt(p / 3)
+        return _kraus([[a, 0, 0, a], [0, s, s, 0], [0, -1j * s, 1j * s, 0], [s, 0, 0, -s]])
 
 
 class Pauli(_OneParam):
@@ -88,10 +114,11 @@ class Pauli(_OneParam):
             inputs = torch.tensor(inputs, dtype=torch.float).reshape(-1)[:4]
         return inputs
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        prob = prob / prob.sum()
-        return torch.stack([torch.sqrt(prob[k:k + 1]) * m for k, m in enumerate(_paulis(prob.device))])
+    @staticmethod
+    def _kraus_of(prob):
+        prob = prob / prob.sum(-1, keepdim=True)
+        si, sx, sy, sz = (torch.sqrt(prob[..., k]) for k in range(4))
+        return _kraus([[si, 0, 0, si], [0, sx, sx, 0], [0, -1j * sy, 1j * sy, 0], [sz, 0, 0, -sz]])
 
     def extra_repr(self) -> str:
         p = self.prob
@@ -102,10 +129,10 @@ class AmplitudeDamping(_OneParam):
     """K0 = diag(1, sqrt(1-p)), K1 = sqrt(p) |0><1| (reference channel.py:215-263)."""
     _name = 'AmplitudeDamping'
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        m0, m1 = torch.zeros_like(prob), torch.ones_like(prob)
-        return torch.stack([_mat([m1, m0, m0, torch.sqrt(1 - prob)]), _mat([m0, torch.sqrt(prob), m0, m0])]) + 0j
+    @staticmethod
+    def _kraus_of(prob):
+        p = prob[..., 0]
+        return _kraus([[torch.ones_like(p), 0, 0, torch.sqrt(1 - p)], [0, torch.sqrt(p), 0, 0]])
 
 
 class PhaseDamping(_OneParam):
@@ -113,10 +140,10 @@ class PhaseDamping(_OneParam):
     _name = 'PhaseDamping'
     _diagonal_kraus = True
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        m0, m1 = torch.zeros_like(prob), torch.ones_like(prob)
-        return torch.stack([_mat([m1, m0, m0, torch.sqrt(1 - prob)]), _mat([m0, m0, m0, torch.sqrt(prob)])]) + 0j
+    @staticmethod
+    def _kraus_of(prob):
+        p = prob[..., 0]
+        return _kraus([[torch.ones_like(p), 0, 0, torch.sqrt(1 - p)], [0, 0, 0, torch.sqrt(p)]])
 
 
 class GeneralizedAmplitudeDamping(_OneParam):
@@ -136,15 +163,11 @@ class GeneralizedAmplitudeDamping(_OneParam):
             inputs = torch.tensor(inputs, dtype=torch.float).reshape(-1)[:2]
         return inputs
 
-    def get_matrix(self, theta: Any) -> torch.Tensor:
-        prob = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
-        p, g = prob[0], prob[1]
-        m0, m1 = torch.zeros_like(p), torch.ones_like(p)
-        k0 = torch.sqrt(p) * _mat([m1, m0, m0, torch.sqrt(1 - g)])
-        k1 = torch.sqrt(p) * _mat([m0, torch.sqrt(g), m0, m0])
-        k2 = torch.sqrt(1 - p) * _mat([torch.sqrt(1 - g), m0, m0, m1])
-        k3 = torch.sqrt(1 - p) * _mat([m0, m0, torch.sqrt(g), m0])
-        return torch.stack([k0, k1, k2, k3]) + 0j
+    @staticmethod
+    def _kraus_of(prob):
+        p, g = prob[..., 0], prob[..., 1]
+        sp, sq, sg, s1g = torch.sqrt(p), torch.sqrt(1 - p), torch.sqrt(g), torch.sqrt(1 - g)
+        return _kraus([[sp, 0, 0, sp * s1g], [0, sp * sg, 0, 0], [sq * s1g, 0, 0, sq], [0, 0, sq * sg, 0]])
 
     def extra_repr(self) -> str:
         return f'wires={self.wires}, probability={self.prob[0].item()}, rate={self.prob[1].item()}'

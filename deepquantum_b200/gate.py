@@ -663,6 +663,65 @@ class LatentGate(ArbitraryGate):
         self.npara = self.latent.numel()
 
 
+class CombinedSingleGate(SingleGate):
+    """Product of single-qubit gates on the same wire, applied as ONE 2x2 (reference gate.py:1790-1903).  The
+    member gates keep their parameters (autograd chains through the matrix product)."""
+
+    _matrix_source = 'dyn'
+
+    def __init__(self, gates, name=None, nqubit=1, wires=None, controls=None, condition=False, den_mat=False,
+                 tsr_mode=False) -> None:
+        super().__init__(name=name, nqubit=nqubit, wires=wires, controls=controls, condition=condition,
+                         den_mat=den_mat, tsr_mode=tsr_mode)
+        self.gates = nn.ModuleList()
+        for gate in gates:
+            self._adopt(gate)
+            self.gates.append(gate)
+        self.update_npara()
+        self.update_matrix()
+
+    def _adopt(self, gate) -> None:
+        gate.nqubit, gate.wires, gate.controls = self.nqubit, self.wires, self.controls
+        gate.condition, gate.den_mat, gate.tsr_mode = self.condition, self.den_mat, self.tsr_mode
+
+    def get_matrix(self) -> torch.Tensor:
+        matrix = None
+        for gate in self.gates:
+            matrix = gate.update_matrix() if matrix is None else gate.update_matrix() @ matrix
+        return matrix
+
+    def update_matrix(self) -> torch.Tensor:
+        matrix = self.get_matrix()
+        self.matrix = matrix.detach()
+        return matrix
+
+    def update_npara(self) -> None:
+        self.npara = sum(g.npara for g in self.gates)
+
+    def init_para(self, inputs=None) -> None:
+        count = 0
+        for gate in self.gates:
+            if gate.npara:
+                gate.init_para(None if inputs is None else inputs[count:count + gate.npara])
+            count += gate.npara
+        self.update_matrix()
+
+    def add(self, gate) -> None:
+        self._adopt(gate)
+        self.gates.append(gate)
+        self.update_npara()
+        self.update_matrix()
+
+    def inverse(self) -> 'CombinedSingleGate':
+        return CombinedSingleGate(gates=[g.inverse() for g in reversed(self.gates)], name=self.name,
+                                  nqubit=self.nqubit, wires=self.wires, controls=self.controls,
+                                  condition=self.condition, den_mat=self.den_mat, tsr_mode=self.tsr_mode)
+
+    def _apply(self, fn: Any) -> 'CombinedSingleGate':
+        nn.Module._apply(self, fn)
+        return self
+
+
 class HamiltonianGate(ArbitraryGate):
     """`exp(-i H t)` on `wires` (reference gate.py:2867-3024): `hamiltonian` is a Pauli-sum list such as
     `[[0.5, 'x0y1'], [-1, 'z3y1']]` (then the gate spans the min..max wire it names) or a Hermitian matrix on

@@ -305,8 +305,14 @@ class DenMatLowering(Lowering):
             # neighbours: 12-qubit noisy workload of tools/bench_denmat.py, 47 passes / 232 rounds with dense
             # superoperators, 21 passes / 69 rounds with the parity blocks)
             kind, size = 'super_parity', 8
-        self.records.append((kind, tuple(targets), (), False, 'dyn', len(self.dynamic), size, 0))
-        self.dynamic.append(chan)
+        if hasattr(chan, '_batched_matrix'):    # built-in channels: one batched evaluation per class and forward
+            lst = self.groups.setdefault(type(chan), [])
+            block, idx = type(chan), len(lst)
+            lst.append(chan)
+        else:
+            block, idx = 'dyn', len(self.dynamic)
+            self.dynamic.append(chan)
+        self.records.append((kind, tuple(targets), (), False, block, idx, size, 0))
         self.sources.append(chan)
 
     @property
@@ -571,19 +577,23 @@ class Channel(Operation):
     _diagonal_kraus = False   # all Kraus operators diagonal: the superoperator is a diagonal gate
     _parity_kraus = False     # all Kraus operators diagonal or anti-diagonal (one wire): two 2x2 parity blocks
 
-    def _lowered_matrix(self) -> torch.Tensor:
-        """Superoperator `sum_i K_i (x) conj(K_i)`, `[4^k, 4^k]` (row wires are the high matrix-index bits); for
-        parity-preserving one-wire channels its two 2x2 blocks `[M1 | M0]` acting on the row bit when
+    @classmethod
+    def _lower_kraus(cls, k: torch.Tensor) -> torch.Tensor:
+        """Kraus operators `[..., n_kraus, d, d]` -> flat lowered blocks `[..., size]`: the superoperator
+        `sum_i K_i (x) conj(K_i)` as `[d^2, d^2]` (row wires are the high matrix-index bits), or, for
+        parity-preserving one-wire channels, its two 2x2 blocks `[M1 | M0]` acting on the row bit when
         row ^ column = 1 / 0 (see `DenMatLowering.add_super`)."""
-        k = self.update_matrix()
         d = k.shape[-1]
-        sup = torch.einsum('iab,icd->acbd', k, k.conj())          # [row', col', row, col]
-        if self._parity_kraus and not self._diagonal_kraus and d == 2:
+        sup = torch.einsum('...iab,...icd->...acbd', k, k.conj())          # [..., row', col', row, col]
+        if cls._parity_kraus and not cls._diagonal_kraus and d == 2:
             i = torch.arange(2, device=k.device)
-            m0 = sup[i[:, None], i[:, None], i[None, :], i[None, :]]
-            m1 = sup[i[:, None], 1 - i[:, None], i[None, :], 1 - i[None, :]]
-            return torch.cat([m1.reshape(-1), m0.reshape(-1)])
-        return sup.reshape(d * d, d * d)
+            m0 = sup[..., i[:, None], i[:, None], i[None, :], i[None, :]]
+            m1 = sup[..., i[:, None], 1 - i[:, None], i[None, :], 1 - i[None, :]]
+            return torch.cat([m1.reshape(*m1.shape[:-2], 4), m0.reshape(*m0.shape[:-2], 4)], dim=-1)
+        return sup.reshape(*sup.shape[:-4], d**4)
+
+    def _lowered_matrix(self) -> torch.Tensor:
+        return self._lower_kraus(self.update_matrix())
 
     def init_para(self, inputs: Any = None) -> None:
         theta = self.inputs_to_tensor(inputs)

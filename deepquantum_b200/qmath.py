@@ -50,6 +50,15 @@ def evolve_state_controlled(state: torch.Tensor, matrix: torch.Tensor, nqubit: i
     return flat.reshape(shape)
 
 
+def sample2expval(sample: dict) -> torch.Tensor:
+    """Average parity of the sampled bit strings (reference qmath.py:863-871)."""
+    total = exp = 0
+    for bitstring, ncount in sample.items():
+        exp += ncount * (-1) ** (bitstring.count('1') % 2)
+        total += ncount
+    return torch.tensor([exp / total])
+
+
 def measure(state: torch.Tensor, shots: int = 1024, with_prob: bool = False, wires=None, den_mat: bool = False,
             block_size: int = 2**24, generator: torch.Generator | None = None):
     """Drop-in for `qmath.measure` (reference qmath.py:568-638) on device statevectors.

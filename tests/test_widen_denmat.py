@@ -76,6 +76,7 @@ def test_kraus_operators_match_oracle():
         full = sum(np.kron(k_, k_.conj()) for k_ in ref).reshape(2, 2, 2, 2)     # [row', col', row, col]
         low = ch._lowered_matrix().numpy()
         if ch._diagonal_kraus:
+            low = low.reshape(4, 4)
             np.testing.assert_allclose(low, full.reshape(4, 4), atol=1e-15)
             assert np.count_nonzero(low - np.diag(np.diagonal(low))) == 0
         else:       # parity blocks [M1 | M0]; everything outside them is zero
@@ -244,3 +245,34 @@ def test_gpu_density_matrix_large_properties():
     rho = c1.to('cuda')()
     psi = c2.to('cuda')()
     assert (rho - psi @ psi.mH).abs().max().item() < 2e-6
+
+
+def test_lowering_batched_data_with_encoded_channels():
+    """2-D data: encoder gates AND encoder channels get one column block per sample (explicit batch)."""
+    n = 3
+    cir = dq.QubitCircuit(n, den_mat=True)
+    cir.hlayer()
+    cir.rx(0, encode=True)
+    cir.bit_flip(0, encode=True)
+    cir.cnot(0, 2)
+    cir.gen_amp_damp(2, encode=True)
+    cir.phase_damp(1, encode=True)
+    cir.to(torch.double)
+    data = torch.tensor([[0.3, 0.5, 0.2, 0.9, 0.4], [1.1, 0.25, 0.7, 0.35, 0.8]], dtype=torch.float64)
+    cir._encode_batched(data)
+    out, _ = emu_run_program(cir._get_program(), 2 * n, np.complex128, batch=2)
+    for b in range(2):
+        d = data[b].tolist()
+        spec = [{'g': 'hlayer'}, {'g': 'rx', 'w': [0], 'p': d[0:1], 'exact': True},
+                {'g': 'bit_flip', 'w': [0], 'p': d[1:2]}, {'g': 'cnot', 'w': [0, 2]},
+                {'g': 'gen_amp_damp', 'w': [2], 'p': d[2:4]}, {'g': 'phase_damp', 'w': [1], 'p': d[4:5]}]
+        rho = np.zeros(4**n, dtype=complex)
+        rho[0] = 1
+        for e in spec:
+            if e['g'] in do.CHANNELS:
+                rho = do.apply_channel(rho, do.kraus(e['g'], e['p'], exact=True), n, e['w'][0])
+            else:
+                import gates_np
+                for m, w, c in gates_np.lower_entry(e, n):
+                    rho = do.evolve_den_mat(rho, m, n, w, c)
+        np.testing.assert_allclose(out[b], rho, atol=1e-13)

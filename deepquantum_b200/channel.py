@@ -62,6 +62,7 @@ class _OneParam(Channel):
 class BitFlip(_OneParam):
     """rho -> (1-p) rho + p X rho X (reference channel.py:16-55)."""
     _name = 'BitFlip'
+    _pauli_kraus = True
 
     @staticmethod
     def _kraus_of(prob):
@@ -85,6 +86,7 @@ class PhaseFlip(_OneParam):
 class Depolarizing(_OneParam):
     """rho -> (1-p) rho + p/3 (X rho X + Y rho Y + Z rho Z) (reference channel.py:100-149)."""
     _name = 'Depolarizing'
+    _pauli_kraus = True
 
     @staticmethod
     def _kraus_of(prob):
@@ -96,6 +98,7 @@ class Depolarizing(_OneParam):
 class Pauli(_OneParam):
     """rho -> sum_k p_k P_k rho P_k with normalised `p = sin(theta)^2` (reference channel.py:152-212)."""
     _name = 'Pauli'
+    _pauli_kraus = True
 
     def __init__(self, inputs: Any = None, nqubit: int = 1, wires=None, tsr_mode: bool = False,
                  requires_grad: bool = False) -> None:

@@ -9,6 +9,7 @@ MPS arguments are accepted for signature compatibility and rejected with NotImpl
 """
 from __future__ import annotations
 
+import os
 from copy import copy
 from typing import Any
 
@@ -289,6 +290,9 @@ class DenMatLowering(Lowering):
     state per Kraus operator and sums them).  The matrix buffer is `[flat | conj(flat)]`.  Row and column records
     act on disjoint bits, so the planner is free to fuse them into the same pass."""
 
+    # A/B switch: False lowers Pauli channels through the generic parity blocks
+    PAULI_BELL = os.environ.get('B200Q_DENMAT_PAULI_BELL', '1') != '0'
+
     def add_super(self, chan: 'Channel', wires) -> None:
         n = self.nqubit
         w2 = list(wires) + [w + n for w in wires]
@@ -298,6 +302,11 @@ class DenMatLowering(Lowering):
         kind, size = 'super', 4 ** len(w2)
         if getattr(chan, '_diagonal_kraus', False):
             kind = 'super_diag'
+        elif getattr(chan, '_pauli_kraus', False) and len(wires) == 1 and self.PAULI_BELL:
+            # Pauli channels sum_k p_k P_k rho P_k: the four superoperators P_k (x) conj(P_k) commute, their common
+            # eigenbasis is the Bell basis, so the channel is CX(row->col) . H(row) . diag . H(row) . CX(row->col):
+            # five records, all of them in-place ("lean") kernel ops
+            kind, size = 'super_pauli', 20
         elif getattr(chan, '_parity_kraus', False) and len(wires) == 1:
             # every Kraus operator diagonal or anti-diagonal: the superoperator keeps the parity row ^ column, so it is
             # CX(row->col) . [M1 on row if parity 1, M0 on row if parity 0] . CX(row->col) -- register-kind ops only
@@ -324,6 +333,12 @@ class DenMatLowering(Lowering):
         for (kind, targets, ctrl, adj, _b, _i, _s, hint), off in zip(self.records, self.offsets):
             if kind in ('super', 'super_diag'):
                 out.append(L.make_gate(L.GATE_MAT if kind == 'super' else L.GATE_DIAG, targets, (), off, False, 0))
+                continue
+            if kind == 'super_pauli':
+                col, row = targets
+                cx = L.make_gate(L.GATE_X, [col], [row], 0, False, 0)
+                had = L.make_gate(L.GATE_MAT, [row], [], off + 16, False, L.GATE_REAL | L.GATE_HADAMARD)
+                out += [cx, had, L.make_gate(L.GATE_DIAG, targets, (), off, False, 0), had, cx]
                 continue
             if kind == 'super_parity':
                 col, row = targets
@@ -576,6 +591,7 @@ class Channel(Operation):
 
     _diagonal_kraus = False   # all Kraus operators diagonal: the superoperator is a diagonal gate
     _parity_kraus = False     # all Kraus operators diagonal or anti-diagonal (one wire): two 2x2 parity blocks
+    _pauli_kraus = False      # Kraus operators proportional to Pauli matrices: diagonal in the Bell basis
 
     @classmethod
     def _lower_kraus(cls, k: torch.Tensor) -> torch.Tensor:
@@ -585,6 +601,15 @@ class Channel(Operation):
         row ^ column = 1 / 0 (see `DenMatLowering.add_super`)."""
         d = k.shape[-1]
         sup = torch.einsum('...iab,...icd->...acbd', k, k.conj())          # [..., row', col', row, col]
+        if cls._pauli_kraus and d == 2 and DenMatLowering.PAULI_BELL:
+            # [4x4 diagonal in the Bell basis | exact Hadamard]: B = (H on row) . CX(row->col), diag = B S B^T
+            r = 0.5 ** 0.5
+            bell = torch.tensor([[r, 0, 0, r], [0, r, r, 0], [r, 0, 0, -r], [0, r, -r, 0]], dtype=sup.real.dtype,
+                                device=k.device).to(sup.dtype)
+            s4 = sup.reshape(*sup.shape[:-4], 4, 4)
+            dd = torch.einsum('ij,...jk,ik->...i', bell, s4, bell)
+            had = torch.tensor([r, r, r, -r], dtype=sup.real.dtype, device=k.device).to(sup.dtype)
+            return torch.cat([torch.diag_embed(dd).reshape(*dd.shape[:-1], 16), had.expand(*dd.shape[:-1], 4)], dim=-1)
         if cls._parity_kraus and not cls._diagonal_kraus and d == 2:
             i = torch.arange(2, device=k.device)
             m0 = sup[..., i[:, None], i[:, None], i[None, :], i[None, :]]

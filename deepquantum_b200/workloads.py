@@ -138,13 +138,14 @@ def fock_interferometer_spec(nmode: int = 8, seed: int = SEED):
     return spec
 
 
-def noisy_circuit_spec(nqubit: int, depth: int, seed: int = SEED):
+def noisy_circuit_spec(nqubit: int, depth: int, seed: int = SEED, channels=None):
     """Density-matrix workload: the Clifford+RX layers of `random_clifford_rx_spec`
-    with one channel per qubit after every layer, cycling through the seven channel families."""
+    with one channel per qubit after every layer, cycling through the seven channel families (or `channels`)."""
     g = _gen(seed)
     base = random_clifford_rx_spec(nqubit, depth, seed)
     per_layer = len(base) // depth
-    names = ['bit_flip', 'phase_flip', 'depolarizing', 'pauli', 'amp_damp', 'phase_damp', 'gen_amp_damp']
+    names = list(channels) if channels else ['bit_flip', 'phase_flip', 'depolarizing', 'pauli', 'amp_damp',
+                                             'phase_damp', 'gen_amp_damp']
     spec, k = [], 0
     for d in range(depth):
         spec += base[d * per_layer:(d + 1) * per_layer]

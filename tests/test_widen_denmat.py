@@ -79,6 +79,14 @@ def test_kraus_operators_match_oracle():
             low = low.reshape(4, 4)
             np.testing.assert_allclose(low, full.reshape(4, 4), atol=1e-15)
             assert np.count_nonzero(low - np.diag(np.diagonal(low))) == 0
+        elif ch._pauli_kraus:   # [diagonal in the Bell basis | exact Hadamard]
+            r = 0.5 ** 0.5
+            bell = np.kron(np.array([[r, r], [r, -r]]), np.eye(2)) @ np.array(
+                [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])       # H(row) . CX(row->col)
+            dmat, had = low[:16].reshape(4, 4), low[16:]
+            assert np.count_nonzero(dmat - np.diag(np.diagonal(dmat))) == 0
+            np.testing.assert_allclose(bell.T @ dmat @ bell, full.reshape(4, 4), atol=1e-15, err_msg=name)
+            np.testing.assert_allclose(had, [r, r, r, -r], atol=1e-16)
         else:       # parity blocks [M1 | M0]; everything outside them is zero
             m1, m0 = low[:4].reshape(2, 2), low[4:].reshape(2, 2)
             rebuilt = np.zeros((2, 2, 2, 2), dtype=complex)
@@ -139,6 +147,20 @@ def test_lowering_matches_reference(case):
     # the c64 reference itself is this far from its c128 run
     ref32 = g[case + '/c64']
     assert np.linalg.norm(out32[0].reshape(ref.shape) - ref32) / np.linalg.norm(ref) < 3e-6
+
+
+@pytest.mark.parametrize('bell', [True, False])
+def test_pauli_channels_bell_basis_and_parity_block_lowerings_agree(bell, monkeypatch):
+    from deepquantum_b200.operation import DenMatLowering
+    monkeypatch.setattr(DenMatLowering, 'PAULI_BELL', bell)
+    g = _g()
+    n, spec, _ = _meta(g, 'noisy5')
+    ref = g['noisy5/c128']
+    prog = _build(n, spec, True)._get_program()
+    kinds = {r[0] for r in prog.low.records if isinstance(r[0], str)}
+    assert ('super_pauli' in kinds) == bell
+    out, _ = emu_run_program(prog, 2 * n, np.complex128)
+    assert np.linalg.norm(out[0].reshape(ref.shape) - ref) / np.linalg.norm(ref) < 1e-12
 
 
 def test_lowering_fuses_row_and_column_gates():

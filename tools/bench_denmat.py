@@ -12,8 +12,8 @@ from deepquantum_b200 import workloads as wl  # noqa: E402
 from tools.bench_configs import PEAK, timed  # noqa: E402
 
 
-def run(n, depth):
-    spec = wl.noisy_circuit_spec(n, depth)
+def run(n, depth, channels=None):
+    spec = wl.noisy_circuit_spec(n, depth, channels=channels)
     cir = dq.QubitCircuit(n, den_mat=True)
     wl.apply_spec(cir, spec)
     for q in range(n - 1):
@@ -32,7 +32,9 @@ def run(n, depth):
         rho = cir.state
         tr = rho.diagonal().sum().real.item()
     bytes_pass = 2 * (4**n) * 8
+    from deepquantum_b200.operation import DenMatLowering
     print(json.dumps({'config': f'noisy Clifford+RX, {n} qubits (rho = {2 * n}-qubit vector), depth {depth}, complex64',
+                      'channels': list(channels) if channels else 'all seven', 'pauli_bell': DenMatLowering.PAULI_BELL,
                       'source_ops': len(spec), 'kernel_gate_records': len(prog.structs), 'passes': plan.n_passes,
                       'ms_forward': ms, 'ms_kernels': ms_k, 'ms_matrix_build': ms_m, 'ms_per_pass': ms_k / plan.n_passes,
                       'ops_per_s': len(spec) / ms * 1e3,
@@ -44,3 +46,4 @@ if __name__ == '__main__':
     sizes = [int(a) for a in sys.argv[1:]] or [12, 14]
     for n in sizes:
         run(n, 10)
+        run(n, 10, channels=('depolarizing',))

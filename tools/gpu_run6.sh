@@ -1,11 +1,9 @@
 #!/bin/bash
-# GPU session 6 (short: 13 GPU-minutes left): new density-matrix / Hamiltonian tests first, then the whole GPU
-# suite, the headline bench and the density-matrix workload
+# quick iteration: parity + bench + optional ncu of the tile kernel
 mkdir -p gpurun_out
-timeout 240 python -m pytest tests/test_widen_denmat.py tests/test_widen_hamiltonian.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_widen6.log 2>&1; echo "pytest widen rc=$?" >> gpurun_out/pytest_widen6.log
-tail -n 15 gpurun_out/pytest_widen6.log
-timeout 120 python tools/bench_denmat.py 12 14 > gpurun_out/denmat6.jsonl 2> gpurun_out/denmat6.err; cat gpurun_out/denmat6.jsonl; tail -n 3 gpurun_out/denmat6.err
-timeout 150 python bench.py --steps 5 --warmup 3 > gpurun_out/bench6.json 2> gpurun_out/bench6.err; cut -c1-700 gpurun_out/bench6.json
-timeout 300 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu6.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu6.log
-tail -n 6 gpurun_out/pytest_gpu6.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke6.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke6.log; tail -n 3 gpurun_out/smoke6.log
+timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_gpu6.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu6.log
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench6.json 2> gpurun_out/bench6.err
+if [ "$1" = "ncu" ]; then
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:b200q_tile_kernel -s 60 -c 2 -o gpurun_out/prof_tile_6 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full6.log 2>&1
+fi
+tail -n 4 gpurun_out/pytest_gpu6.log; cut -c1-900 gpurun_out/bench6.json; tail -3 gpurun_out/bench6.err

@@ -131,6 +131,7 @@ class Pauli(_OneParam):
 class AmplitudeDamping(_OneParam):
     """K0 = diag(1, sqrt(1-p)), K1 = sqrt(p) |0><1| (reference channel.py:215-263)."""
     _name = 'AmplitudeDamping'
+    _damping_kraus = True
 
     @staticmethod
     def _kraus_of(prob):
@@ -153,6 +154,7 @@ class GeneralizedAmplitudeDamping(_OneParam):
     """Four Kraus operators with probability `p = sin(theta_0)^2` and rate `gamma = sin(theta_1)^2`
     (reference channel.py:317-383)."""
     _name = 'GeneralizedAmplitudeDamping'
+    _damping_kraus = True
 
     def __init__(self, inputs: Any = None, nqubit: int = 1, wires=None, tsr_mode: bool = False,
                  requires_grad: bool = False) -> None:

@@ -292,6 +292,8 @@ class DenMatLowering(Lowering):
 
     # A/B switch: False lowers Pauli channels through the generic parity blocks
     PAULI_BELL = os.environ.get('B200Q_DENMAT_PAULI_BELL', '1') != '0'
+    # measured slower (14-qubit mixed workload: 34 passes / 94.1 ms against 28 passes / 80.6 ms): off by default
+    DAMPING_SVD = os.environ.get('B200Q_DENMAT_DAMPING_SVD', '0') != '0'
 
     def add_super(self, chan: 'Channel', wires) -> None:
         n = self.nqubit
@@ -307,6 +309,10 @@ class DenMatLowering(Lowering):
             # eigenbasis is the Bell basis, so the channel is CX(row->col) . H(row) . diag . H(row) . CX(row->col):
             # five records, all of them in-place ("lean") kernel ops
             kind, size = 'super_pauli', 20
+        elif getattr(chan, '_damping_kraus', False) and len(wires) == 1 and self.DAMPING_SVD:
+            # (generalised) amplitude damping: the parity-1 block is a scalar, the parity-0 block a real 2x2 =
+            # rotation . diagonal . rotation (SVD): CX, X(col), c-Ry, diag, c-Ry, X(col), CX -- lean ops only
+            kind, size = 'super_damping', 24
         elif getattr(chan, '_parity_kraus', False) and len(wires) == 1:
             # every Kraus operator diagonal or anti-diagonal: the superoperator keeps the parity row ^ column, so it is
             # CX(row->col) . [M1 on row if parity 1, M0 on row if parity 0] . CX(row->col) -- register-kind ops only
@@ -339,6 +345,15 @@ class DenMatLowering(Lowering):
                 cx = L.make_gate(L.GATE_X, [col], [row], 0, False, 0)
                 had = L.make_gate(L.GATE_MAT, [row], [], off + 16, False, L.GATE_REAL | L.GATE_HADAMARD)
                 out += [cx, had, L.make_gate(L.GATE_DIAG, targets, (), off, False, 0), had, cx]
+                continue
+            if kind == 'super_damping':
+                col, row = targets
+                cx = L.make_gate(L.GATE_X, [col], [row], 0, False, 0)
+                flip = L.make_gate(L.GATE_X, [col], [], 0, False, 0)
+                rot = L.GATE_REAL | L.GATE_ROTATION
+                out += [cx, flip, L.make_gate(L.GATE_MAT, [row], [col], off, False, rot),
+                        L.make_gate(L.GATE_DIAG, targets, (), off + 4, False, 0),
+                        L.make_gate(L.GATE_MAT, [row], [col], off + 20, False, rot), flip, cx]
                 continue
             if kind == 'super_parity':
                 col, row = targets
@@ -592,6 +607,7 @@ class Channel(Operation):
     _diagonal_kraus = False   # all Kraus operators diagonal: the superoperator is a diagonal gate
     _parity_kraus = False     # all Kraus operators diagonal or anti-diagonal (one wire): two 2x2 parity blocks
     _pauli_kraus = False      # Kraus operators proportional to Pauli matrices: diagonal in the Bell basis
+    _damping_kraus = False    # parity-1 block proportional to the identity, parity-0 block real (amplitude damping)
 
     @classmethod
     def _lower_kraus(cls, k: torch.Tensor) -> torch.Tensor:
@@ -614,6 +630,18 @@ class Channel(Operation):
             i = torch.arange(2, device=k.device)
             m0 = sup[..., i[:, None], i[:, None], i[None, :], i[None, :]]
             m1 = sup[..., i[:, None], 1 - i[:, None], i[None, :], 1 - i[None, :]]
+            if cls._damping_kraus and DenMatLowering.DAMPING_SVD:
+                # [Vh (rotation) | 4x4 diagonal in the flipped parity frame | U (rotation)], M0 = U diag(sig) Vh
+                u, sig, vh = torch.linalg.svd(m0.real)
+                du, dv = torch.linalg.det(u).sign(), torch.linalg.det(vh).sign()      # reflections -> rotations
+                u = torch.cat([u[..., :, :1], u[..., :, 1:] * du[..., None, None]], dim=-1)
+                vh = torch.cat([vh[..., :1, :], vh[..., 1:, :] * dv[..., None, None]], dim=-2)
+                sig = torch.stack([sig[..., 0], sig[..., 1] * du * dv], dim=-1)
+                scal = m1[..., 0, 0].real                                              # parity-1 block = scal * 1
+                dd = torch.stack([scal, sig[..., 0], scal, sig[..., 1]], dim=-1)       # index row * 2 + flipped parity
+                parts = [vh.reshape(*vh.shape[:-2], 4), torch.diag_embed(dd).reshape(*dd.shape[:-1], 16),
+                         u.reshape(*u.shape[:-2], 4)]
+                return torch.cat(parts, dim=-1).to(sup.dtype)
             return torch.cat([m1.reshape(*m1.shape[:-2], 4), m0.reshape(*m0.shape[:-2], 4)], dim=-1)
         return sup.reshape(*sup.shape[:-4], d**4)
 

@@ -87,6 +87,19 @@ def test_kraus_operators_match_oracle():
             assert np.count_nonzero(dmat - np.diag(np.diagonal(dmat))) == 0
             np.testing.assert_allclose(bell.T @ dmat @ bell, full.reshape(4, 4), atol=1e-15, err_msg=name)
             np.testing.assert_allclose(had, [r, r, r, -r], atol=1e-16)
+        elif ch._damping_kraus:   # [Vh | diagonal (flipped parity frame) | U]: parity-0 block U diag Vh, parity-1 scalar
+            vh, dmat, u = low[:4].reshape(2, 2), low[4:20].reshape(4, 4), low[20:].reshape(2, 2)
+            for rot in (vh, u):
+                assert abs(np.linalg.det(rot) - 1) < 1e-12 and abs(rot[0, 0] - rot[1, 1]) < 1e-12
+            dd = np.diagonal(dmat)
+            rebuilt = np.zeros((2, 2, 2, 2), dtype=complex)
+            m0 = u @ np.diag([dd[1], dd[3]]) @ vh
+            for a in range(2):
+                for b in range(2):
+                    rebuilt[a, a, b, b] = m0[a, b]
+                rebuilt[a, 1 - a, a, 1 - a] = dd[0]
+            assert dd[0] == dd[2]
+            np.testing.assert_allclose(rebuilt, full, atol=1e-14, err_msg=name)
         else:       # parity blocks [M1 | M0]; everything outside them is zero
             m1, m0 = low[:4].reshape(2, 2), low[4:].reshape(2, 2)
             rebuilt = np.zeros((2, 2, 2, 2), dtype=complex)
@@ -153,12 +166,13 @@ def test_lowering_matches_reference(case):
 def test_pauli_channels_bell_basis_and_parity_block_lowerings_agree(bell, monkeypatch):
     from deepquantum_b200.operation import DenMatLowering
     monkeypatch.setattr(DenMatLowering, 'PAULI_BELL', bell)
+    monkeypatch.setattr(DenMatLowering, 'DAMPING_SVD', bell)
     g = _g()
     n, spec, _ = _meta(g, 'noisy5')
     ref = g['noisy5/c128']
     prog = _build(n, spec, True)._get_program()
     kinds = {r[0] for r in prog.low.records if isinstance(r[0], str)}
-    assert ('super_pauli' in kinds) == bell
+    assert ('super_pauli' in kinds) == bell and ('super_damping' in kinds) == bell
     out, _ = emu_run_program(prog, 2 * n, np.complex128)
     assert np.linalg.norm(out[0].reshape(ref.shape) - ref) / np.linalg.norm(ref) < 1e-12
 
@@ -169,7 +183,7 @@ def test_lowering_fuses_row_and_column_gates():
     cir = _build(n, wl.noisy_circuit_spec(n, 1, seed=3), False)
     prog = cir._get_program()
     out, stats = emu_run_program(prog, 2 * n, np.complex64)
-    assert stats['passes'] <= 2 and len(prog.structs) > 2 * n
+    assert stats['passes'] <= 3 and len(prog.structs) > 2 * n
 
 
 def test_lowering_mixed_and_batched_initial_state():

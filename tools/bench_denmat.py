@@ -34,7 +34,7 @@ def run(n, depth, channels=None):
     bytes_pass = 2 * (4**n) * 8
     from deepquantum_b200.operation import DenMatLowering
     print(json.dumps({'config': f'noisy Clifford+RX, {n} qubits (rho = {2 * n}-qubit vector), depth {depth}, complex64',
-                      'channels': list(channels) if channels else 'all seven', 'pauli_bell': DenMatLowering.PAULI_BELL,
+                      'channels': list(channels) if channels else 'all seven', 'pauli_bell': DenMatLowering.PAULI_BELL, 'damping_svd': DenMatLowering.DAMPING_SVD,
                       'source_ops': len(spec), 'kernel_gate_records': len(prog.structs), 'passes': plan.n_passes,
                       'ms_forward': ms, 'ms_kernels': ms_k, 'ms_matrix_build': ms_m, 'ms_per_pass': ms_k / plan.n_passes,
                       'ops_per_s': len(spec) / ms * 1e3,
@@ -46,4 +46,5 @@ if __name__ == '__main__':
     sizes = [int(a) for a in sys.argv[1:]] or [12, 14]
     for n in sizes:
         run(n, 10)
-        run(n, 10, channels=('depolarizing',))
+        if os.environ.get('DENMAT_ONLY_MIXED') != '1':
+            run(n, 10, channels=('depolarizing',))

@@ -60,7 +60,10 @@ def _build(n, spec, double, obs=()):
     return cir
 
 
-def test_kraus_operators_match_oracle():
+@pytest.mark.parametrize('svd', [False, True])
+def test_kraus_operators_match_oracle(svd, monkeypatch):
+    from deepquantum_b200.operation import DenMatLowering
+    monkeypatch.setattr(DenMatLowering, 'DAMPING_SVD', svd)
     th = [0.3, 0.9, 0.5, 1.2]
     pairs = [(dq.channel.BitFlip, 'bit_flip', 1), (dq.channel.PhaseFlip, 'phase_flip', 1),
              (dq.channel.Depolarizing, 'depolarizing', 1), (dq.channel.Pauli, 'pauli', 4),
@@ -87,7 +90,7 @@ def test_kraus_operators_match_oracle():
             assert np.count_nonzero(dmat - np.diag(np.diagonal(dmat))) == 0
             np.testing.assert_allclose(bell.T @ dmat @ bell, full.reshape(4, 4), atol=1e-15, err_msg=name)
             np.testing.assert_allclose(had, [r, r, r, -r], atol=1e-16)
-        elif ch._damping_kraus:   # [Vh | diagonal (flipped parity frame) | U]: parity-0 block U diag Vh, parity-1 scalar
+        elif ch._damping_kraus and svd:   # [Vh | diagonal (flipped parity frame) | U]: parity-0 block U diag Vh, parity-1 scalar
             vh, dmat, u = low[:4].reshape(2, 2), low[4:20].reshape(4, 4), low[20:].reshape(2, 2)
             for rot in (vh, u):
                 assert abs(np.linalg.det(rot) - 1) < 1e-12 and abs(rot[0, 0] - rot[1, 1]) < 1e-12

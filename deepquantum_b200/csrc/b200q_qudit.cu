@@ -58,6 +58,46 @@ __global__ void build_ell_kernel(const cxq<Real>* __restrict__ m, int D, cxq<Rea
   if (threadIdx.x == 0) hdr->width = wmax;
 }
 
+// Mixed-radix walker over the elements e = x0 + R0 * (x1 + R1 * x2) of a CTA's tile, advanced by a fixed step:
+// the element -> (group, digit combo) mapping of qudit_elem() without its divisions (two 32-bit divisions by
+// run-time values per element and per phase were most of the instructions of the load / store loops).
+struct Walker {
+  int x0, x1, x2, s0, s1, s2, R0, R1;
+  __device__ __forceinline__ void init(int e, int step, int r0, int r1) {
+    R0 = r0; R1 = r1;
+    x0 = e % r0; int q = e / r0; x1 = q % r1; x2 = q / r1;
+    s0 = step % r0; q = step / r0; s1 = q % r1; s2 = q / r1;
+  }
+  __device__ __forceinline__ void next() {
+    x0 += s0;
+    const int c0 = x0 >= R0;
+    x0 -= c0 ? R0 : 0;
+    x1 += s1 + c0;
+    const int c1 = x1 >= R1;
+    x1 -= c1 ? R1 : 0;
+    x2 += s2 + c1;
+  }
+};
+constexpr int kNoCarry = 1 << 28;   // radix of a digit that never carries
+
+// Tile element walker in memory order (same order as qudit_elem): gives (gi, t) of the current element.
+struct ElemWalker {
+  Walker w;
+  int d, swap_digits, lane_over_target;
+  __device__ __forceinline__ void init(const QuditGeom& g, int e, int step) {
+    d = g.d;
+    lane_over_target = g.lane_over_target;
+    swap_digits = !(g.k == 1 || g.stride[0] < g.stride[1]);
+    if (lane_over_target) w.init(e, step, g.d, g.G);   // lowest target digit fastest, then group, then the other digit
+    else w.init(e, step, g.G, kNoCarry);               // group fastest, then digit combo
+  }
+  __device__ __forceinline__ void get(int* gi, int* t) const {
+    if (lane_over_target) { *gi = w.x1; *t = swap_digits ? (w.x2 + d * w.x0) : (w.x0 + d * w.x2); }
+    else { *gi = w.x0; *t = w.x1; }
+  }
+  __device__ __forceinline__ void next() { w.next(); }
+};
+
 template <typename Real>
 __global__ void __launch_bounds__(kThreads)
 qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<Real>* __restrict__ ell_vals,
@@ -80,49 +120,70 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
   // (kLoadUnroll independent global loads in flight per thread before the first shared store: with one load per
   // iteration the loop was latency-bound -- 26 % of the samples sat on the store waiting for its load -- and a
   // B200 needs ~40 KB in flight per SM to reach its HBM bandwidth)
-  for (int e0 = threadIdx.x; e0 < total; e0 += kLoadUnroll * kThreads) {
-    cxq<Real> v[kLoadUnroll];
-    int dst[kLoadUnroll];
+  {
+    ElemWalker ew;
+    ew.init(g, threadIdx.x, kThreads);
+    for (int e0 = threadIdx.x; e0 < total; e0 += kLoadUnroll * kThreads) {
+      cxq<Real> v[kLoadUnroll];
+      int dst[kLoadUnroll];
 #pragma unroll
-    for (int u = 0; u < kLoadUnroll; ++u) {
-      const int e = e0 + u * kThreads;
-      v[u].x = v[u].y = Real(0);
-      dst[u] = -1;
-      if (e < total) {
-        int gi, t;
-        qudit_elem(g, e, &gi, &t);
-        const long long b = gbase[gi];
-        if (b >= 0) v[u] = st[b + toff[t]];
-        dst[u] = t * GP + gi;
+      for (int u = 0; u < kLoadUnroll; ++u) {
+        v[u].x = v[u].y = Real(0);
+        dst[u] = -1;
+        if (e0 + u * kThreads < total) {
+          int gi, t;
+          ew.get(&gi, &t);
+          const long long b = gbase[gi];
+          if (b >= 0) v[u] = st[b + toff[t]];
+          dst[u] = t * GP + gi;
+        }
+        ew.next();
       }
-    }
 #pragma unroll
-    for (int u = 0; u < kLoadUnroll; ++u)
-      if (dst[u] >= 0) xs[dst[u]] = v[u];
+      for (int u = 0; u < kLoadUnroll; ++u)
+        if (dst[u] >= 0) xs[dst[u]] = v[u];
+    }
   }
   __syncthreads();
-  // ---- contract: y[r][gi] = sum_j vals[r][j] * x[cols[r][j]][gi] ---------------------------------------
-  for (int o = threadIdx.x; o < total; o += kThreads) {
-    const int gi = o % G, r = o / G;
-    Real yr = Real(0), yi = Real(0);
-    const cxq<Real>* vrow = ell_vals + r * D;
-    const short* crow = ell_cols + r * D;
-    for (int j = 0; j < width; ++j) {
-      const cxq<Real> w = vrow[j];
-      const cxq<Real> x = xs[int(crow[j]) * GP + gi];
-      yr += w.x * x.x - w.y * x.y;
-      yi += w.x * x.y + w.y * x.x;
+  // ---- contract: y[r][gi] = sum_j vals[r][j] * x[cols[r][j]][gi], two groups (gi, gi + Gh) per thread and matrix
+  // row so that every ELL entry is loaded once for two outputs ------------------------------------------
+  {
+    const int Gh = (G + 1) >> 1;
+    Walker cw;
+    cw.init(threadIdx.x, kThreads, Gh, kNoCarry);
+    for (int o = threadIdx.x; o < Gh * D; o += kThreads, cw.next()) {
+      const int gi = cw.x0, r = cw.x1;
+      const bool two = gi + Gh < G;
+      const int gj = two ? gi + Gh : gi;
+      Real ar = Real(0), ai = Real(0), br = Real(0), bi = Real(0);
+      const cxq<Real>* vrow = ell_vals + r * D;
+      const short* crow = ell_cols + r * D;
+      for (int j = 0; j < width; ++j) {
+        const cxq<Real> w = vrow[j];
+        const cxq<Real>* xrow = xs + int(crow[j]) * GP;
+        const cxq<Real> x = xrow[gi];
+        const cxq<Real> z = xrow[gj];
+        ar += w.x * x.x - w.y * x.y;
+        ai += w.x * x.y + w.y * x.x;
+        br += w.x * z.x - w.y * z.y;
+        bi += w.x * z.y + w.y * z.x;
+      }
+      cxq<Real> y; y.x = ar; y.y = ai;
+      ys[r * GP + gi] = y;
+      if (two) { y.x = br; y.y = bi; ys[r * GP + gj] = y; }
     }
-    cxq<Real> y; y.x = yr; y.y = yi;
-    ys[r * GP + gi] = y;
   }
   __syncthreads();
   // ---- store (same order as the load) -------------------------------------------------------------------
-  for (int e = threadIdx.x; e < total; e += kThreads) {
-    int gi, t;
-    qudit_elem(g, e, &gi, &t);
-    const long long b = gbase[gi];
-    if (b >= 0) st[b + toff[t]] = ys[t * GP + gi];
+  {
+    ElemWalker ew;
+    ew.init(g, threadIdx.x, kThreads);
+    for (int e = threadIdx.x; e < total; e += kThreads, ew.next()) {
+      int gi, t;
+      ew.get(&gi, &t);
+      const long long b = gbase[gi];
+      if (b >= 0) st[b + toff[t]] = ys[t * GP + gi];
+    }
   }
 }
 

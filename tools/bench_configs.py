@@ -85,7 +85,7 @@ def c5(nmode=8, cutoff=10):
         else:
             cir.bs(e['w'], e['p'])
     cir.to('cuda')
-    ms = timed(lambda: cir(), reps=3, warm=1)
+    ms = timed(lambda: cir(), reps=5, warm=3)
     st = cir()
     norm = float((st.real**2 + st.imag**2).sum())
     bytes_pass = 2 * cutoff**nmode * 8

@@ -98,6 +98,74 @@ struct ElemWalker {
   __device__ __forceinline__ void next() { w.next(); }
 };
 
+constexpr int kOut = 2;   // outputs (groups) per thread and matrix row in the contraction (4: twice the bank conflicts, no faster)
+
+// Complex accumulator y += w * x.  float: two packed f32x2 FMAs per product on the pair (x.re, x.im) with the
+// broadcast operands (w.re, w.re), (w.im, w.im): acc1 = sum w.re * x, acc2 = sum w.im * x,
+// y = (acc1.re - acc2.im, acc1.im + acc2.re) -- half the issue slots of four scalar FMAs, no operand swaps.
+template <typename Real> struct CAcc;
+template <> struct CAcc<float> {
+  unsigned long long a1 = 0ull, a2 = 0ull;
+  struct W { unsigned long long re2, im2; };
+  static __device__ __forceinline__ W make_w(cxq<float> w) {
+    W o;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(o.re2) : "f"(w.x));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(o.im2) : "f"(w.y));
+    return o;
+  }
+  __device__ __forceinline__ void mac(const W& w, const cxq<float>* x) {
+    const unsigned long long xv = *reinterpret_cast<const unsigned long long*>(x);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(w.re2), "l"(xv));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2) : "l"(w.im2), "l"(xv));
+  }
+  __device__ __forceinline__ cxq<float> result() const {
+    float r1, i1, r2, i2;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r1), "=f"(i1) : "l"(a1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r2), "=f"(i2) : "l"(a2));
+    cxq<float> y; y.x = r1 - i2; y.y = i1 + r2;
+    return y;
+  }
+};
+template <> struct CAcc<double> {
+  double yr = 0.0, yi = 0.0;
+  typedef cxq<double> W;
+  static __device__ __forceinline__ W make_w(cxq<double> w) { return w; }
+  __device__ __forceinline__ void mac(const W& w, const cxq<double>* x) {
+    const cxq<double> v = *x;
+    yr = fma(w.x, v.x, yr); yr = fma(-w.y, v.y, yr);
+    yi = fma(w.x, v.y, yi); yi = fma(w.y, v.x, yi);
+  }
+  __device__ __forceinline__ cxq<double> result() const { cxq<double> y; y.x = yr; y.y = yi; return y; }
+};
+
+// Contraction of a CTA's tile.  STAGED: `vals` / `cols` are the shared-memory copies (row stride = width).
+template <typename Real, bool STAGED>
+__device__ __forceinline__ void contract_rows(const cxq<Real>* xs, cxq<Real>* ys, const cxq<Real>* vals,
+                                              const short* cols, int row_stride, int width, int D, int G, int GP) {
+  const int Gq = (G + kOut - 1) / kOut;
+  Walker cw;
+  cw.init(threadIdx.x, kThreads, Gq, kNoCarry);
+  for (int o = threadIdx.x; o < Gq * D; o += kThreads, cw.next()) {
+    const int gi = cw.x0, r = cw.x1;
+    int gm[kOut];
+#pragma unroll
+    for (int m = 0; m < kOut; ++m) gm[m] = (gi + m * Gq < G) ? gi + m * Gq : gi;   // out of range: recompute gi
+    CAcc<Real> acc[kOut];
+    const cxq<Real>* vrow = vals + r * row_stride;
+    const short* crow = cols + r * row_stride;
+#pragma unroll 2
+    for (int j = 0; j < width; ++j) {
+      const typename CAcc<Real>::W w = CAcc<Real>::make_w(vrow[j]);
+      const cxq<Real>* xrow = xs + int(crow[j]) * GP;
+#pragma unroll
+      for (int m = 0; m < kOut; ++m) acc[m].mac(w, xrow + gm[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < kOut; ++m)
+      if (m == 0 || gi + m * Gq < G) ys[r * GP + gm[m]] = acc[m].result();
+  }
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(kThreads)
 qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<Real>* __restrict__ ell_vals,
@@ -145,32 +213,23 @@ qudit_apply_kernel(cxq<Real>* __restrict__ state, const QuditGeom g, const cxq<R
     }
   }
   __syncthreads();
-  // ---- contract: y[r][gi] = sum_j vals[r][j] * x[cols[r][j]][gi], two groups (gi, gi + Gh) per thread and matrix
-  // row so that every ELL entry is loaded once for two outputs ------------------------------------------
+  // ---- contract: y[r][gi] = sum_j vals[r][j] * x[cols[r][j]][gi]; kOut groups (gi + m * Gq) per thread and
+  // matrix row, so that every ELL entry is loaded once for kOut outputs; ELL rows staged in shared memory when
+  // they fit (width <= ell_cap) ---------------------------------------------------------------------------
   {
-    const int Gh = (G + 1) >> 1;
-    Walker cw;
-    cw.init(threadIdx.x, kThreads, Gh, kNoCarry);
-    for (int o = threadIdx.x; o < Gh * D; o += kThreads, cw.next()) {
-      const int gi = cw.x0, r = cw.x1;
-      const bool two = gi + Gh < G;
-      const int gj = two ? gi + Gh : gi;
-      Real ar = Real(0), ai = Real(0), br = Real(0), bi = Real(0);
-      const cxq<Real>* vrow = ell_vals + r * D;
-      const short* crow = ell_cols + r * D;
-      for (int j = 0; j < width; ++j) {
-        const cxq<Real> w = vrow[j];
-        const cxq<Real>* xrow = xs + int(crow[j]) * GP;
-        const cxq<Real> x = xrow[gi];
-        const cxq<Real> z = xrow[gj];
-        ar += w.x * x.x - w.y * x.y;
-        ai += w.x * x.y + w.y * x.x;
-        br += w.x * z.x - w.y * z.y;
-        bi += w.x * z.y + w.y * z.x;
+    const bool staged = g.ell_cap > 0 && width <= g.ell_cap;
+    cxq<Real>* svals = reinterpret_cast<cxq<Real>*>(toff + D);
+    short* scols = reinterpret_cast<short*>(svals + size_t(D) * g.ell_cap);
+    if (staged) {
+      for (int i = threadIdx.x; i < D * width; i += kThreads) {
+        const int r = i / width, j = i - r * width;
+        svals[i] = ell_vals[r * D + j];
+        scols[i] = ell_cols[r * D + j];
       }
-      cxq<Real> y; y.x = ar; y.y = ai;
-      ys[r * GP + gi] = y;
-      if (two) { y.x = br; y.y = bi; ys[r * GP + gj] = y; }
+      __syncthreads();
+      contract_rows<Real, true>(xs, ys, svals, scols, width, width, D, G, GP);
+    } else {
+      contract_rows<Real, false>(xs, ys, ell_vals, ell_cols, D, width, D, G, GP);
     }
   }
   __syncthreads();
@@ -213,7 +272,8 @@ int run_qudit(void* state, const QuditGeom& g, const void* matrix, int64_t batch
   int rc = get_workspace(dev, &w);
   if (rc) return rc;
   build_ell_kernel<Real><<<1, kMaxD, 0, s>>>((const cxq<Real>*)matrix, g.D, (cxq<Real>*)w->vals, w->cols, w->hdr);
-  const size_t smem = size_t(2) * g.D * (g.G + 1) * sizeof(cxq<Real>) + size_t(g.G + g.D) * sizeof(long long);
+  const size_t smem = size_t(2) * g.D * (g.G + 1) * sizeof(cxq<Real>) + size_t(g.G + g.D) * sizeof(long long) +
+                      size_t(g.ell_bytes);
   auto kern = qudit_apply_kernel<Real>;
   static size_t smem_set[64] = {0};
   if (smem > smem_set[dev]) {

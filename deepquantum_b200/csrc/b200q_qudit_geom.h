@@ -19,6 +19,8 @@ struct QuditGeom {
   long long seg_mid;     // rest-index block between the targets       (k = 2)
   long long state_size;  // d^n
   int lane_over_target;  // 1: lanes run over the lowest target digit (its stride is 1)
+  int ell_cap;           // ELL rows of at most this many entries are staged in shared memory (0: never)
+  int ell_bytes;         // shared memory reserved for them
 };
 
 // flat offset of the group `rest` (target digits zero)
@@ -86,7 +88,12 @@ inline int qudit_make_geom(int n_modes, int d, const int32_t* modes, int n_targe
   g->seg_mid = n_targets == 2 ? hi / (lo * d) : 1;
   g->n_rest = size / g->D;
   g->lane_over_target = lo == 1 ? 1 : 0;
-  int G = (int)((48 * 1024) / (2 * g->D * elt_bytes));
+  // photon-number conserving two-mode gates and all one-mode gates have at most d entries per row
+  g->ell_cap = d;
+  g->ell_bytes = ((g->D * g->ell_cap * (elt_bytes + 2)) + 15) & ~15;
+  if (g->ell_bytes > 12 * 1024) { g->ell_cap = 0; g->ell_bytes = 0; }
+  // 52 KiB per CTA: four CTAs (plus 1 KiB each of system shared memory) fit the 228 KiB of an SM
+  int G = (int)((52 * 1024 - g->ell_bytes) / (2 * g->D * elt_bytes));
   if (G > 256) G = 256;
   if (G < 1) G = 1;
   g->G = G;

@@ -315,3 +315,47 @@ def test_lowering_batched_data_with_encoded_channels():
                 for m, w, c in gates_np.lower_entry(e, n):
                     rho = do.evolve_den_mat(rho, m, n, w, c)
         np.testing.assert_allclose(out[b], rho, atol=1e-13)
+
+
+@pytest.mark.parametrize('init', ['equal', 'entangle'])
+def test_named_initial_density_matrices(init):
+    cir = dq.QubitCircuit(3, init_state=init, den_mat=True)
+    cir.rx(0, 0.3)
+    cir.cnot(0, 2)
+    cir.amp_damp(2, 0.4)
+    cir.to(torch.double)
+    st0 = cir.init_state.state.numpy()
+    assert st0.shape == (8, 8) and abs(np.trace(st0) - 1) < 1e-7
+    out, _ = emu_run_program(cir._get_program(), 6, np.complex128, state=st0.reshape(1, -1))
+    spec = [{'g': 'rx', 'w': [0], 'p': [0.3]}, {'g': 'cnot', 'w': [0, 2]}, {'g': 'amp_damp', 'w': [2], 'p': [0.4]}]
+    np.testing.assert_allclose(out[0].reshape(8, 8), do.run_spec(spec, 3, st0), atol=1e-14)
+
+
+def test_composition_and_encoding_of_density_matrix_circuits():
+    a = dq.QubitCircuit(2, den_mat=True)
+    a.h(0)
+    a.bit_flip(0, 0.2)
+    b = dq.QubitCircuit(2, den_mat=True)
+    b.cnot(0, 1)
+    b.phase_damp(1, 0.5)
+    c = a + b
+    assert c.den_mat and len(c.operators) == 4 and c._get_program().low.state_qubits == 4
+    inv = b.inverse()
+    assert inv.den_mat and [type(o).__name__ for o in inv.operators] == ['PhaseDamping', 'CNOT']
+    a.add(b)
+    assert len(a.operators) == 4
+    st = dq.QubitState(2, torch.tensor([1, 2, 3, 4], dtype=torch.cfloat), den_mat=True)
+    assert st.state.shape == (4, 4) and abs(st.state.diagonal().sum() - 1) < 1e-6
+    assert dq.QubitState(2, torch.randn(3, 4, dtype=torch.cfloat), den_mat=True).state.shape == (3, 4, 4)
+    e = dq.QubitCircuit(2, den_mat=True)
+    e.rx(0, encode=True)
+    e.depolarizing(1, encode=True)
+    e.pauli(0, encode=True)
+    assert e.ndata == 6
+    e.encode(torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))
+    np.testing.assert_allclose(e.operators[1].theta.numpy(), [0.2], atol=1e-7)
+    np.testing.assert_allclose(e.operators[2].theta.numpy(), [0.3, 0.4, 0.5, 0.6], atol=1e-7)
+    out, _ = emu_run_program(e._get_program(), 4, np.complex64)
+    spec = [{'g': 'rx', 'w': [0], 'p': [0.1]}, {'g': 'depolarizing', 'w': [1], 'p': [0.2]},
+            {'g': 'pauli', 'w': [0], 'p': [0.3, 0.4, 0.5, 0.6]}]
+    np.testing.assert_allclose(out[0].reshape(4, 4), do.run_spec(spec, 2), atol=2e-7)

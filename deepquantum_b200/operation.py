@@ -214,7 +214,7 @@ class Lowering:
         """All parameters of a gate class as ONE gather from the encoded data vector, when every gate of the class
         took its parameters from the same `data` tensor in the last `encode` (and is not inverted / batched)."""
         ref = getattr(lst[0], '_data_ref', None)
-        if ref is None:
+        if ref is None or not hasattr(lst[0], '_pnames'):    # channels: parameters are stacked one by one
             return None
         data = ref[0]
         idx = []

@@ -25,5 +25,7 @@ from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplit
 from .operation import Channel, Gate, Layer, Operation, dtype_map  # noqa: F401
 from .qmath import evolve_state, evolve_state_controlled, inverse_permutation, multi_kron  # noqa: F401
 from .state import QubitState, amplitude_encoding  # noqa: F401
+from . import qasm3  # noqa: F401,E402
+from .qasm3 import cir_to_qasm3, qasm3_to_cir  # noqa: F401,E402
 from . import photonic  # noqa: F401,E402
 from .photonic import QumodeCircuit  # noqa: F401,E402

@@ -17,6 +17,8 @@ Files written
   denmat.npz          density-matrix circuits (den_mat=True): every gate family + the seven channels, final rho in
                       c128 and c64, Pauli-string expectations, measure(with_prob=True) probabilities
   hamiltonian.npz     circuits with HamiltonianGate blocks (Pauli-sum and matrix form, controlled), states and rho
+  qasm3.npz           OpenQASM 3.0 programs (def / ctrl @ / pow() @ / all stdgates names), the reference's import of
+                      them run to a final state, and the reference's export of a seeded circuit
   dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
 """
 import json
@@ -287,6 +289,87 @@ def hamiltonian():
     print('hamiltonian.npz:', len(out), 'arrays', float(np.linalg.norm(out['ham6/c128'])), abs(out['ham6/inv_c128'][0]))
 
 
+QASM_PROGRAM = """OPENQASM 3.0;
+include "stdgates.inc";
+qubit[5] q;
+bit[5] c;
+def entangle(a, b) x0, x1 {
+  rx(a) x0;
+  ry(b / 2 + pi / 8) x1;
+  cx x0, x1;
+  rzz(a * b) x0, x1;
+}
+def layer(t) a0, a1, a2 {
+  entangle(t, 2 * t) a0, a1;
+  ctrl @ entangle(-t, 0.5) a2, a1, a0;
+  u(t, 0.2, -0.3) a2;
+}
+h q[0];
+h q[1];
+h q[2];
+h q[3];
+h q[4];
+x q[1];
+y q[2];
+z q[3];
+s q[0];
+sdg q[1];
+t q[2];
+tdg q[3];
+p(0.7) q[4];
+rx(pi / 3) q[0];
+ry(-0.4) q[1];
+rz(1.9) q[2];
+swap q[0], q[3];
+cx q[4], q[0];
+cz q[1], q[2];
+ccx q[0], q[1], q[4];
+cswap q[2], q[3], q[4];
+rxx(0.3) q[0], q[2];
+ryy(0.5) q[1], q[3];
+layer(0.37) q[3], q[0], q[2];
+pow(2) @ entangle(0.2, 0.9) q[4], q[1];
+pow(-1) @ t q[0];
+pow(-2) @ rz(0.3) q[1];
+pow(3) @ s q[2];
+ctrl @ ctrl @ ry(0.8) q[0], q[4], q[2];
+ctrl @ pow(2) @ rxx(0.15) q[3], q[1], q[2];
+pow(0.5) @ x q[3];
+pow(-0.25) @ entangle(0.6, 0.1) q[2], q[4];
+ctrl @ pow(1.5) @ h q[0], q[1];
+c[0] = measure q[0];
+c[3] = measure q[3];
+"""
+
+
+def qasm3():
+    """Reference qasm3.py: import (:166-472) and export (:117-156).  `inv @` is left out on purpose: the reference
+    turns it into a no-op for integer powers (qasm3.py:303-306, 330-331 negate twice) -- see
+    deepquantum_b200/qasm3.py.  One statement per line: the reference parses lines, not statements."""
+    import importlib
+    q3 = importlib.import_module('deepquantum.qasm3')
+    out = {'program': np.array(QASM_PROGRAM)}
+    cir = q3.qasm3_to_cir(QASM_PROGRAM)
+    cir.to(torch.double)      # (a reference circuit holding a Barrier cannot be moved: operation.py:166 / utils.py:47)
+    with torch.no_grad():
+        out['state_c128'] = cir().reshape(-1).numpy()
+    out['n_ops'] = np.array(len(cir.operators))
+    out['wires_measure'] = np.array(cir.wires_measure)
+    spec = all_gates_spec(5)
+    rc = dq.QubitCircuit(5)
+    wl.apply_spec(rc, spec)
+    rc.measure(wires=[1, 3])
+    text = q3.cir_to_qasm3(rc)
+    out['export_spec'] = np.array(json.dumps({'n': 5, 'spec': spec}))
+    out['export_text'] = np.array(text)
+    back = q3.qasm3_to_cir(text)
+    back.to(torch.double)
+    with torch.no_grad():
+        out['export_reimport_state_c128'] = back().reshape(-1).numpy()
+    np.savez_compressed(os.path.join(OUT, 'qasm3.npz'), **out)
+    print('qasm3.npz: ops', int(out['n_ops']), 'norm', float(np.linalg.norm(out['state_c128'])))
+
+
 def denmat():
     """Reference density-matrix path (qmath.py:509-540, operation.py:221-262, 594-600, channel.py)."""
     out = {}
@@ -337,11 +420,13 @@ def denmat():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3']
     if 'denmat' in which:
         denmat()
     if 'hamiltonian' in which:
         hamiltonian()
+    if 'qasm3' in which:
+        qasm3()
     if 'measure' in which:
         measure()
     if 'gates' in which:

@@ -3,8 +3,9 @@ the b200q C ABI instead of permute/reshape/matmul.
 
 Statevector path plus the density-matrix path (section 8f rank 2): a density matrix of
 n qubits is run through the SAME kernels as a 2n-qubit amplitude vector (`DenMatLowering`): `U rho U^dagger` is
-`U` on the row wire and `conj(U)` on the column wire (reference qmath.py:509-540), a Kraus channel is one dense
-superoperator gate `sum_i K_i (x) conj(K_i)` on the (row, column) wire pair (reference operation.py:594-600).
+`U` on the row wire and `conj(U)` on the column wire (reference qmath.py:509-540), a Kraus channel is the
+superoperator `sum_i K_i (x) conj(K_i)` on the (row, column) wire pair (reference operation.py:594-600), lowered by
+its structure to a diagonal record, to Bell-basis / parity-block records, or to one dense 2-target record.
 MPS arguments are accepted for signature compatibility and rejected with NotImplementedError.
 """
 from __future__ import annotations
@@ -285,10 +286,11 @@ class DenMatLowering(Lowering):
     """Lowering of a density-matrix circuit onto the 2n-qubit amplitude vector `rho[i, j] -> index i * 2^n + j`
     (row wire w = bit 2n-1-w, column wire w = bit n-1-w): every gate record becomes the pair `U` on the row wires,
     `conj(U)` on the column wires (reference qmath.py:509-540 does the two matrix products one after the other, each
-    with a permute + reshape copy of the 4^n-element state); a channel becomes ONE dense gate, the superoperator
+    with a permute + reshape copy of the 4^n-element state); a channel becomes the superoperator
     `sum_i K_i (x) conj(K_i)` on (row wires, column wires) (reference operation.py:594-600 evolves one copy of the
-    state per Kraus operator and sums them).  The matrix buffer is `[flat | conj(flat)]`.  Row and column records
-    act on disjoint bits, so the planner is free to fuse them into the same pass."""
+    state per Kraus operator and sums them), emitted by `add_super` as the cheapest record sequence its structure
+    allows.  The matrix buffer is `[flat | conj(flat)]`.  Row and column records act on
+    disjoint bits, so the planner is free to fuse them into the same pass."""
 
     # A/B switch: False lowers Pauli channels through the generic parity blocks
     PAULI_BELL = os.environ.get('B200Q_DENMAT_PAULI_BELL', '1') != '0'

@@ -3,7 +3,8 @@ per-mode gate contraction on a `[batch, cutoff, ..., cutoff]` state tensor
 (photonic/circuit.py:405-431 -> photonic/operation.py:142-146 -> qmath.evolve_state with qudit=cutoff).
 
 Only what that hot path needs is mirrored: `QumodeCircuit(nmode, 'vac', cutoff, backend='fock', basis=False)`
-with the `ps` / `bs` / `s` builders, and the gate classes `PhaseShift`, `BeamSplitter`, `Squeezing` whose
+with the `ps` / `bs` / `s` builders, the beamsplitter family (`mzi`, `bs_theta`, `bs_phi`, `bs_rx`, `bs_ry`, `bs_h`,
+`dc`, `h`), the rotations `r` / `f` and the Kerr gates `k` / `ck`, and the gate classes behind them, whose
 Fock-space transformation matrices follow the same recurrences (arXiv:2004.11002 Eq. 51-52, 74-75) but are
 evaluated with a handful of vectorised torch calls for ALL gates of a class at once, on the device -- the
 reference's per-element Python loops (photonic/gate.py:356-373, 1098-1114) cost 33 ms per beamsplitter,
@@ -125,8 +126,12 @@ class _FockGate(nn.Module):
 
 
 class PhaseShift(_FockGate):
-    def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False):
+    """diag(exp(i theta n)); `inv_mode` rotates clockwise (theta -> -theta, reference photonic/gate.py:135-199)."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False,
+                 inv_mode: bool = False):
         super().__init__('PhaseShift', nmode, [0] if wires is None else wires, cutoff)
+        self.inv_mode = inv_mode
         theta = torch.rand(1)[0] * 2 * torch.pi if inputs is None else self._to_tensor(inputs)
         if requires_grad:
             self.theta = nn.Parameter(theta)
@@ -135,14 +140,14 @@ class PhaseShift(_FockGate):
         self.npara = 1
 
     def _params(self):
-        return [self.theta]
+        return [-self.theta if self.inv_mode else self.theta]
 
     @staticmethod
     def _batched_matrix_state(p, d):
         return ps_matrix_state(p[:, 0], d)
 
     def update_matrix_state(self) -> torch.Tensor:
-        return ps_matrix_state(self.theta.reshape(1).double(), self.cutoff)[0]
+        return ps_matrix_state(self._params()[0].reshape(1).double(), self.cutoff)[0]
 
 
 class BeamSplitter(_FockGate):
@@ -204,6 +209,141 @@ class Squeezing(_FockGate):
     def update_matrix_state(self) -> torch.Tensor:
         p = torch.stack([self.r.reshape(()), self.theta.reshape(())]).double().unsqueeze(0)
         return self._batched_matrix_state(p, self.cutoff)[0]
+
+
+class MZI(BeamSplitter):
+    """Mach-Zehnder interferometer, phase shifter before (`phi_first`) or after the theta stage
+    (reference photonic/gate.py:414-516)."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, phi_first: bool = True,
+                 requires_grad: bool = False):
+        super().__init__(inputs, nmode, wires, cutoff, requires_grad)
+        self.name = 'MZI'
+        self.phi_first = phi_first
+        self._variant = bool(phi_first)
+
+    @staticmethod
+    def mixing_matrix(theta, phi, phi_first=True):
+        cos, sin = torch.cos(theta / 2) + 0j, torch.sin(theta / 2) + 0j
+        pre = 1j * torch.exp(1j * theta / 2)
+        e_ip = torch.exp(1j * phi)
+        mat = (pre[..., None] * torch.stack([e_ip * sin, cos, e_ip * cos, -sin], dim=-1)).reshape(*theta.shape, 2, 2)
+        return mat if phi_first else mat.transpose(-1, -2)
+
+    @staticmethod
+    def _batched_matrix_state(p, d, phi_first=True):
+        return bs_matrix_state(MZI.mixing_matrix(p[:, 0], p[:, 1], phi_first), d)
+
+    def update_matrix_state(self) -> torch.Tensor:
+        p = torch.stack([self.theta.reshape(()), self.phi.reshape(())]).double().unsqueeze(0)
+        return self._batched_matrix_state(p, self.cutoff, self.phi_first)[0]
+
+
+class _BeamSplitterOneParam(BeamSplitter):
+    """Beamsplitter with one free angle; the other is a float32 constant buffer like in the reference
+    (`torch.pi / 2` / `torch.pi / 4` pass through `torch.tensor(..., dtype=torch.float)`)."""
+    _free, _fixed_value = 'theta', 0.0
+
+    def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, requires_grad: bool = False):
+        _FockGate.__init__(self, type(self).__name__, nmode, [0, 1] if wires is None else wires, cutoff)
+        assert len(self.wires) == 2
+        free = torch.rand(1)[0] * 2 * torch.pi if inputs is None else self._to_tensor(inputs)
+        while isinstance(free, (list, tuple)):
+            free = self._to_tensor(free[0])
+        fixed = torch.tensor(self._fixed_value, dtype=torch.float).to(free.device, free.dtype)
+        if requires_grad:
+            setattr(self, self._free, nn.Parameter(free))
+        else:
+            self.register_buffer(self._free, free)
+        self.register_buffer('phi' if self._free == 'theta' else 'theta', fixed)
+        self.npara = 1
+
+
+class BeamSplitterTheta(_BeamSplitterOneParam):
+    """BS(theta, phi = pi/2) (reference photonic/gate.py:519-613)."""
+    _free, _fixed_value = 'theta', torch.pi / 2
+
+
+class BeamSplitterPhi(_BeamSplitterOneParam):
+    """BS(theta = pi/4, phi) (reference photonic/gate.py:616-710)."""
+    _free, _fixed_value = 'phi', torch.pi / 4
+
+
+class BeamSplitterSingle(_FockGate):
+    """One-angle beamsplitters in the `'rx'`, `'ry'` or `'h'` convention (reference photonic/gate.py:713-877)."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, convention: str = 'rx',
+                 requires_grad: bool = False):
+        super().__init__('BeamSplitterSingle', nmode, [0, 1] if wires is None else wires, cutoff)
+        assert len(self.wires) == 2 and convention in ('rx', 'ry', 'h')
+        self.convention = convention
+        self._variant = convention
+        theta = torch.rand(1)[0] * 2 * torch.pi if inputs is None else self._to_tensor(inputs)
+        if requires_grad:
+            self.theta = nn.Parameter(theta)
+        else:
+            self.register_buffer('theta', theta)
+        self.npara = 1
+
+    def _params(self):
+        return [self.theta]
+
+    @staticmethod
+    def mixing_matrix(theta, convention):
+        cos, sin = torch.cos(theta / 2) + 0j, torch.sin(theta / 2) + 0j
+        entries = {'rx': [cos, 1j * sin, 1j * sin, cos], 'ry': [cos, -sin, sin, cos], 'h': [cos, sin, sin, -cos]}
+        return torch.stack(entries[convention], dim=-1).reshape(*theta.shape, 2, 2)
+
+    @staticmethod
+    def _batched_matrix_state(p, d, convention='rx'):
+        return bs_matrix_state(BeamSplitterSingle.mixing_matrix(p[:, 0], convention), d)
+
+    def update_matrix_state(self) -> torch.Tensor:
+        return self._batched_matrix_state(self.theta.reshape(1, 1).double(), self.cutoff, self.convention)[0]
+
+    def extra_repr(self) -> str:
+        return f'wires={self.wires}, theta={self.theta.item()}, convention={self.convention}'
+
+
+class Kerr(_FockGate):
+    """diag(exp(i kappa n^2)) (reference photonic/gate.py:2291-2383)."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False):
+        super().__init__(type(self).__name__, nmode, self._default_wires() if wires is None else wires, cutoff)
+        kappa = torch.rand(1)[0] * 2 * torch.pi if inputs is None else self._to_tensor(inputs)
+        if requires_grad:
+            self.kappa = nn.Parameter(kappa)
+        else:
+            self.register_buffer('kappa', kappa)
+        self.npara = 1
+
+    @staticmethod
+    def _default_wires():
+        return [0]
+
+    def _params(self):
+        return [self.kappa]
+
+    @staticmethod
+    def _batched_matrix_state(p, d):
+        n = torch.arange(d, dtype=p.dtype, device=p.device)
+        return torch.diag_embed(torch.exp(1j * p[:, :1] * (n * n)[None, :]))
+
+    def update_matrix_state(self) -> torch.Tensor:
+        return self._batched_matrix_state(self.kappa.reshape(1, 1).double(), self.cutoff)[0]
+
+
+class CrossKerr(Kerr):
+    """diag(exp(i kappa n1 n2)) on two modes (reference photonic/gate.py:2386-2483)."""
+
+    @staticmethod
+    def _default_wires():
+        return [0, 1]
+
+    @staticmethod
+    def _batched_matrix_state(p, d):
+        n = torch.arange(d, dtype=p.dtype, device=p.device)
+        return torch.diag_embed(torch.exp(1j * p[:, :1] * torch.kron(n, n)[None, :]))
 
 
 class FockState(nn.Module):
@@ -273,15 +413,62 @@ class QumodeCircuit(nn.Module):
         inputs = None if r is None else [r, 0.0 if theta is None else theta]
         self.add(Squeezing(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
 
+    # ---- the beamsplitter family, rotations and Kerr gates (reference photonic/circuit.py:2026-2245, 2471-2520,
+    # 2628-2680); `mu` / `sigma` (the reference's gate-noise model) are accepted and must stay unset -------------
+    def _one(self, cls, wires, inputs, encode, mu, sigma, **kw):
+        assert mu is None and sigma is None, 'gate noise is outside the accelerated Fock tensor path'
+        self.add(cls(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode, **kw))
+
+    def mzi(self, wires, inputs=None, phi_first=True, encode=False, mu=None, sigma=None):
+        self._one(MZI, wires, inputs, encode, mu, sigma, phi_first=phi_first)
+
+    def bs_theta(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(BeamSplitterTheta, wires, inputs, encode, mu, sigma)
+
+    def bs_phi(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(BeamSplitterPhi, wires, inputs, encode, mu, sigma)
+
+    def bs_rx(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(BeamSplitterSingle, wires, inputs, encode, mu, sigma, convention='rx')
+
+    def bs_ry(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(BeamSplitterSingle, wires, inputs, encode, mu, sigma, convention='ry')
+
+    def bs_h(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(BeamSplitterSingle, wires, inputs, encode, mu, sigma, convention='h')
+
+    def dc(self, wires, mu=None, sigma=None):
+        """Directional coupler: `bs_rx(pi / 2)`."""
+        self._one(BeamSplitterSingle, wires, torch.pi / 2, False, mu, sigma, convention='rx')
+
+    def h(self, wires, mu=None, sigma=None):
+        """Photonic Hadamard: `bs_h(pi / 2)`."""
+        self._one(BeamSplitterSingle, wires, torch.pi / 2, False, mu, sigma, convention='h')
+
+    def r(self, wires, inputs=None, encode=False, inv_mode=False, mu=None, sigma=None):
+        self._one(PhaseShift, wires, inputs, encode, mu, sigma, inv_mode=inv_mode)
+
+    def f(self, wires, mu=None, sigma=None):
+        """Fourier gate: rotation by pi / 2."""
+        self._one(PhaseShift, wires, torch.pi / 2, False, mu, sigma)
+
+    def k(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(Kerr, wires, inputs, encode, mu, sigma)
+
+    def ck(self, wires, inputs=None, encode=False, mu=None, sigma=None):
+        self._one(CrossKerr, wires, inputs, encode, mu, sigma)
+
     def build_matrices(self, cdtype, device):
-        """All Fock transformation matrices of the circuit: one batched evaluation per gate class."""
+        """All Fock transformation matrices of the circuit: one batched evaluation per gate class (and variant)."""
         groups = {}
         for i, op in enumerate(self.operators):
-            groups.setdefault(type(op), []).append(i)
+            groups.setdefault((type(op), getattr(op, '_variant', None)), []).append(i)
         mats = [None] * len(self.operators)
-        for cls, ids in groups.items():
+        for (cls, variant), ids in groups.items():
             p = torch.stack([torch.stack([t.reshape(()) for t in self.operators[i]._params()]) for i in ids])
-            m = cls._batched_matrix_state(p.to(device=device, dtype=torch.float64), self.cutoff)
+            p = p.to(device=device, dtype=torch.float64)
+            m = cls._batched_matrix_state(p, self.cutoff) if variant is None else \
+                cls._batched_matrix_state(p, self.cutoff, variant)
             nt = len(self.operators[ids[0]].wires)
             m = m.reshape(len(ids), self.cutoff**nt, self.cutoff**nt).to(cdtype)
             for j, i in enumerate(ids):

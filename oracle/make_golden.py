@@ -19,6 +19,8 @@ Files written
   hamiltonian.npz     circuits with HamiltonianGate blocks (Pauli-sum and matrix form, controlled), states and rho
   qasm3.npz           OpenQASM 3.0 programs (def / ctrl @ / pow() @ / all stdgates names), the reference's import of
                       them run to a final state, and the reference's export of a seeded circuit
+  fock2.npz           Fock tensor path with the beamsplitter family (mzi, bs_theta, bs_phi, bs_rx, bs_ry, bs_h, dc, h),
+                      rotations (r, f) and Kerr gates (k, ck): final states and the local Fock matrices
   dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
 """
 import json
@@ -226,6 +228,56 @@ def fock():
     np.savez_compressed(os.path.join(OUT, 'fock.npz'), **out)
 
 
+FOCK2_SPEC = [
+    {'g': 's', 'w': [0], 'p': [0.31, 0.4]}, {'g': 's', 'w': [1], 'p': [0.22, 1.3]}, {'g': 's', 'w': [2], 'p': [0.4, 2.2]},
+    {'g': 'mzi', 'w': [0, 1], 'p': [0.3, 0.4]}, {'g': 'mzi', 'w': [1, 2], 'p': [1.3, 0.7], 'phi_first': False},
+    {'g': 'bs_theta', 'w': [0, 1], 'p': [0.5]}, {'g': 'bs_phi', 'w': [1, 2], 'p': [0.6]},
+    {'g': 'bs_rx', 'w': [2, 0], 'p': [0.7]}, {'g': 'bs_ry', 'w': [1, 2], 'p': [0.8]}, {'g': 'bs_h', 'w': [0, 1], 'p': [0.9]},
+    {'g': 'dc', 'w': [1, 2]}, {'g': 'h', 'w': [0, 2]}, {'g': 'r', 'w': [0], 'p': [0.3]},
+    {'g': 'r', 'w': [1], 'p': [0.45], 'inv_mode': True}, {'g': 'f', 'w': [2]}, {'g': 'k', 'w': [0], 'p': [0.2]},
+    {'g': 'ck', 'w': [1, 2], 'p': [0.1]}, {'g': 'bs', 'w': [0, 2], 'p': [0.6, 2.2]}, {'g': 'ck', 'w': [2, 0], 'p': [0.35]}]
+
+
+def apply_fock_spec(cir, spec):
+    for e in spec:
+        g, w, prm = e['g'], e['w'], e.get('p', [])
+        if g == 's':
+            cir.s(w[0], r=prm[0], theta=prm[1])
+        elif g in ('bs', 'mzi'):
+            getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
+        elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):
+            getattr(cir, g)(w, prm[0])
+        elif g in ('dc', 'h'):
+            getattr(cir, g)(w)
+        elif g == 'r':
+            cir.r(w[0], prm[0], inv_mode=e.get('inv_mode', False))
+        elif g == 'f':
+            cir.f(w[0])
+        elif g in ('ps', 'k'):
+            getattr(cir, g)(w[0], prm[0])
+        else:
+            raise ValueError(g)
+
+
+def fock2():
+    out = {}
+    for nmode, cutoff in [(3, 4), (3, 6)]:
+        for double in (True, False):
+            cir = dq.QumodeCircuit(nmode, 'vac', cutoff=cutoff, backend='fock', basis=False)
+            apply_fock_spec(cir, FOCK2_SPEC)
+            if double:
+                cir.to(torch.double)
+            with torch.no_grad():
+                st = cir()
+            out[f'm{nmode}_c{cutoff}/' + ('c128' if double else 'c64')] = st.reshape(-1).numpy()
+            if double:
+                for i, op in enumerate(cir.operators):
+                    out[f'm{nmode}_c{cutoff}/mat{i}'] = op.update_matrix_state().detach().numpy()
+        print('fock2', nmode, cutoff, float(np.linalg.norm(out[f'm{nmode}_c{cutoff}/c128'])))
+    out['spec'] = np.array(json.dumps(FOCK2_SPEC))
+    np.savez_compressed(os.path.join(OUT, 'fock2.npz'), **out)
+
+
 def measure():
     """Reference qmath.measure (qmath.py:568-638) with with_prob=True: the counts are random, the attached
     probabilities and the key convention (sorted wires, wire 0 first) are what the oracle is pinned to."""
@@ -420,13 +472,15 @@ def denmat():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3', 'fock2']
     if 'denmat' in which:
         denmat()
     if 'hamiltonian' in which:
         hamiltonian()
     if 'qasm3' in which:
         qasm3()
+    if 'fock2' in which:
+        fock2()
     if 'measure' in which:
         measure()
     if 'gates' in which:

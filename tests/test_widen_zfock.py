@@ -1,0 +1,95 @@
+"""Fock tensor path, beamsplitter family / rotations / Kerr gates (reference photonic/gate.py:414-877, 2291-2483,
+photonic/circuit.py:2026-2245, 2471-2520, 2628-2680): local Fock matrices and final states against fixtures from
+the unmodified reference -- on the CPU through the emulator of the qudit kernel's geometry, on the GPU through the
+kernel."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import deepquantum_b200 as dq
+from conftest import GOLDEN
+from test_fock import _emu_qudit
+
+KEYS = ['m3_c4', 'm3_c6']
+
+
+def _g():
+    return np.load(os.path.join(GOLDEN, 'fock2.npz'))
+
+
+def _apply(cir, spec):
+    for e in spec:
+        g, w, prm = e['g'], e['w'], e.get('p', [])
+        if g == 's':
+            cir.s(w[0], prm[0], prm[1])
+        elif g in ('bs', 'mzi'):
+            getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
+        elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):
+            getattr(cir, g)(w, prm[0])
+        elif g in ('dc', 'h'):
+            getattr(cir, g)(w)
+        elif g == 'r':
+            cir.r(w[0], prm[0], inv_mode=e.get('inv_mode', False))
+        elif g == 'f':
+            cir.f(w[0])
+        else:
+            getattr(cir, g)(w[0], prm[0])
+
+
+def _circuit(key, double):
+    g = _g()
+    n, d = int(key[1]), int(key.split('_c')[1])
+    cir = dq.QumodeCircuit(n, 'vac', cutoff=d, backend='fock', basis=False)
+    _apply(cir, json.loads(str(g['spec'])))
+    if double:
+        cir.to(torch.double)
+    return g, n, d, cir
+
+
+@pytest.mark.parametrize('key', KEYS)
+def test_fock_matrices_match_reference(key):
+    g, n, d, cir = _circuit(key, True)
+    mats = cir.build_matrices(torch.complex128, 'cpu')
+    for i, (op, m) in enumerate(zip(cir.operators, mats)):
+        ref = g[f'{key}/mat{i}'].reshape(m.shape)
+        np.testing.assert_allclose(m.numpy(), ref, atol=1e-13, err_msg=f'{i} {type(op).__name__}')
+        np.testing.assert_allclose(op.update_matrix_state().reshape(m.shape).numpy(), ref, atol=1e-13)
+
+
+@pytest.mark.parametrize('key', KEYS)
+def test_fock_states_match_reference(key):
+    g, n, d, cir = _circuit(key, True)
+    st = np.zeros(d**n, dtype=np.complex128)
+    st[0] = 1
+    for op, m in zip(cir.operators, cir.build_matrices(torch.complex128, 'cpu')):
+        st = _emu_qudit(st, n, d, m.numpy(), op.wires)
+    ref = g[key + '/c128']
+    assert np.linalg.norm(st - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_builder_conventions():
+    cir = dq.QumodeCircuit(2, 'vac', cutoff=3)
+    cir.bs_theta([0, 1])
+    cir.mzi([0, 1], encode=True)
+    cir.dc([0, 1])
+    assert isinstance(cir.operators[0].theta, torch.nn.Parameter) and cir.operators[0].npara == 1
+    assert not isinstance(cir.operators[1].theta, torch.nn.Parameter)
+    assert abs(float(cir.operators[0].phi) - np.float32(np.pi / 2)) == 0          # float32 constant, like the reference
+    assert cir.operators[2].convention == 'rx' and abs(float(cir.operators[2].theta) - np.float32(np.pi / 2)) == 0
+    with pytest.raises(AssertionError):
+        cir.bs_rx([0, 1], 0.3, mu=0.0, sigma=0.1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('key', KEYS)
+@pytest.mark.parametrize('double', [True, False])
+def test_gpu_fock_states_match_reference(key, double):
+    g, n, d, cir = _circuit(key, double)
+    cir.to('cuda')
+    out = cir().reshape(-1).cpu().numpy()
+    ref = g[key + '/c128']
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < (1e-10 if double else 2e-6), err

@@ -4,7 +4,7 @@ per-mode gate contraction on a `[batch, cutoff, ..., cutoff]` state tensor
 
 Only what that hot path needs is mirrored: `QumodeCircuit(nmode, 'vac', cutoff, backend='fock', basis=False)`
 with the `ps` / `bs` / `s` builders, the beamsplitter family (`mzi`, `bs_theta`, `bs_phi`, `bs_rx`, `bs_ry`, `bs_h`,
-`dc`, `h`), the rotations `r` / `f` and the Kerr gates `k` / `ck`, and the gate classes behind them, whose
+`dc`, `h`), the rotations `r` / `f`, the Kerr gates `k` / `ck` and the displacement `d`, and the gate classes behind them, whose
 Fock-space transformation matrices follow the same recurrences (arXiv:2004.11002 Eq. 51-52, 74-75) but are
 evaluated with a handful of vectorised torch calls for ALL gates of a class at once, on the device -- the
 reference's per-element Python loops (photonic/gate.py:356-373, 1098-1114) cost 33 ms per beamsplitter,
@@ -67,6 +67,24 @@ def squeezing_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> torc
         mask = ((mm + n) % 2 == 1).to(rt)
         cols.append(term * mask[None, :])
     return torch.stack(cols, dim=-1)                           # [N, d(m), d(n)]
+
+
+def displacement_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> torch.Tensor:
+    """[N], [N] -> [N, d, d]   (photonic/gate.py:1431-1451, arXiv:2004.11002 Eq. 57-58): column 0 is the coherent
+    state, column n+1 follows from column n and its shift; vectorised over rows and gates."""
+    sq = torch.sqrt(torch.arange(d, dtype=r.dtype, device=r.device))
+    alpha = r * torch.exp(1j * theta)
+    alpha_c = r * torch.exp(-1j * theta)
+    col = [torch.exp(-(r**2) / 2) + 0j]
+    for m in range(d - 1):
+        col.append(alpha / sq[m + 1] * col[m])
+    cur = torch.stack(col, dim=-1)                       # [N, d]
+    cols = [cur]
+    for n in range(d - 1):
+        shifted = torch.cat([torch.zeros_like(cur[:, :1]), cur[:, :-1]], dim=-1)        # T[m - 1, n], zero for m = 0
+        cur = (-alpha_c[:, None] * cur + sq[None, :] * shifted) / sq[n + 1]
+        cols.append(cur)
+    return torch.stack(cols, dim=-1)                     # [N, m, n]
 
 
 def bs_matrix_state(u: torch.Tensor, d: int) -> torch.Tensor:
@@ -209,6 +227,18 @@ class Squeezing(_FockGate):
     def update_matrix_state(self) -> torch.Tensor:
         p = torch.stack([self.r.reshape(()), self.theta.reshape(())]).double().unsqueeze(0)
         return self._batched_matrix_state(p, self.cutoff)[0]
+
+
+class Displacement(Squeezing):
+    """D(r, theta) (reference photonic/gate.py:1336-1489); same parameter handling as the squeezer."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False):
+        super().__init__(inputs, nmode, wires, cutoff, requires_grad)
+        self.name = 'Displacement'
+
+    @staticmethod
+    def _batched_matrix_state(p, d):
+        return displacement_matrix_state(p[:, 0], p[:, 1], d)
 
 
 class MZI(BeamSplitter):
@@ -457,6 +487,14 @@ class QumodeCircuit(nn.Module):
 
     def ck(self, wires, inputs=None, encode=False, mu=None, sigma=None):
         self._one(CrossKerr, wires, inputs, encode, mu, sigma)
+
+    def d(self, wires, r=None, theta=None, encode=False, mu=None, sigma=None):
+        assert mu is None and sigma is None, 'gate noise is outside the accelerated Fock tensor path'
+        if r is None and theta is None:
+            inputs = None
+        else:
+            inputs = [torch.rand(1)[0] if r is None else r, 0.0 if theta is None else theta]
+        self.add(Displacement(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
 
     def build_matrices(self, cdtype, device):
         """All Fock transformation matrices of the circuit: one batched evaluation per gate class (and variant)."""

@@ -235,14 +235,16 @@ FOCK2_SPEC = [
     {'g': 'bs_rx', 'w': [2, 0], 'p': [0.7]}, {'g': 'bs_ry', 'w': [1, 2], 'p': [0.8]}, {'g': 'bs_h', 'w': [0, 1], 'p': [0.9]},
     {'g': 'dc', 'w': [1, 2]}, {'g': 'h', 'w': [0, 2]}, {'g': 'r', 'w': [0], 'p': [0.3]},
     {'g': 'r', 'w': [1], 'p': [0.45], 'inv_mode': True}, {'g': 'f', 'w': [2]}, {'g': 'k', 'w': [0], 'p': [0.2]},
-    {'g': 'ck', 'w': [1, 2], 'p': [0.1]}, {'g': 'bs', 'w': [0, 2], 'p': [0.6, 2.2]}, {'g': 'ck', 'w': [2, 0], 'p': [0.35]}]
+    {'g': 'ck', 'w': [1, 2], 'p': [0.1]}, {'g': 'bs', 'w': [0, 2], 'p': [0.6, 2.2]}, {'g': 'ck', 'w': [2, 0], 'p': [0.35]},
+    {'g': 'd', 'w': [1], 'p': [0.25, 0.9]}, {'g': 'd', 'w': [2], 'p': [0.4, -1.7]}, {'g': 'bs_rx', 'w': [1, 2], 'p': [1.1]},
+    {'g': 'd', 'w': [0], 'p': [0.15, 0.0]}]
 
 
 def apply_fock_spec(cir, spec):
     for e in spec:
         g, w, prm = e['g'], e['w'], e.get('p', [])
-        if g == 's':
-            cir.s(w[0], r=prm[0], theta=prm[1])
+        if g in ('s', 'd'):
+            getattr(cir, g)(w[0], r=prm[0], theta=prm[1])
         elif g in ('bs', 'mzi'):
             getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
         elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):

@@ -1,4 +1,4 @@
-"""Fock tensor path, beamsplitter family / rotations / Kerr gates (reference photonic/gate.py:414-877, 2291-2483,
+"""Fock tensor path, beamsplitter family / rotations / Kerr / displacement gates (reference photonic/gate.py:414-877, 1336-1489, 2291-2483,
 photonic/circuit.py:2026-2245, 2471-2520, 2628-2680): local Fock matrices and final states against fixtures from
 the unmodified reference -- on the CPU through the emulator of the qudit kernel's geometry, on the GPU through the
 kernel."""
@@ -23,8 +23,8 @@ def _g():
 def _apply(cir, spec):
     for e in spec:
         g, w, prm = e['g'], e['w'], e.get('p', [])
-        if g == 's':
-            cir.s(w[0], prm[0], prm[1])
+        if g in ('s', 'd'):
+            getattr(cir, g)(w[0], prm[0], prm[1])
         elif g in ('bs', 'mzi'):
             getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
         elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):

@@ -29,3 +29,4 @@ from . import qasm3  # noqa: F401,E402
 from .qasm3 import cir_to_qasm3, qasm3_to_cir  # noqa: F401,E402
 from . import photonic  # noqa: F401,E402
 from .photonic import QumodeCircuit  # noqa: F401,E402
+from .photonic_distributed import DistributedFockState, DistributedQumodeCircuit  # noqa: F401,E402

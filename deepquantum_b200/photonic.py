@@ -4,7 +4,7 @@ per-mode gate contraction on a `[batch, cutoff, ..., cutoff]` state tensor
 
 Only what that hot path needs is mirrored: `QumodeCircuit(nmode, 'vac', cutoff, backend='fock', basis=False)`
 with the `ps` / `bs` / `s` builders, the beamsplitter family (`mzi`, `bs_theta`, `bs_phi`, `bs_rx`, `bs_ry`, `bs_h`,
-`dc`, `h`), the rotations `r` / `f`, the Kerr gates `k` / `ck` and the displacement `d`, and the gate classes behind them, whose
+`dc`, `h`), the rotations `r` / `f`, the Kerr gates `k` / `ck`, the displacement `d` and the two-mode squeezer `s2`, and the gate classes behind them, whose
 Fock-space transformation matrices follow the same recurrences (arXiv:2004.11002 Eq. 51-52, 74-75) but are
 evaluated with a handful of vectorised torch calls for ALL gates of a class at once, on the device -- the
 reference's per-element Python loops (photonic/gate.py:356-373, 1098-1114) cost 33 ms per beamsplitter,
@@ -85,6 +85,44 @@ def displacement_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> t
         cur = (-alpha_c[:, None] * cur + sq[None, :] * shifted) / sq[n + 1]
         cols.append(cur)
     return torch.stack(cols, dim=-1)                     # [N, m, n]
+
+
+def squeezing2_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> torch.Tensor:
+    """[N], [N] -> [N, d, d, d, d] (index m, n, p, q; photonic/gate.py:1258-1290, arXiv:2004.11002 Eq. 64-67).
+    Only entries with m - n = p - q are non-zero.  With A_q[m, n] = T[m, n, q + m - n, q] the rank-4 recurrence reads
+    A_q[m, n] = sech sqrt(n / q) A_{q-1}[m, n-1] - e^{-i theta} tanh sqrt((q + m - n) / q) A_{q-1}[m, n]: a sweep over
+    q, vectorised over (m, n) and the gates; A_0 (ranks 2 and 3) is a sweep over m."""
+    nb = r.shape[0]
+    sq = torch.sqrt(torch.arange(d, dtype=r.dtype, device=r.device))
+    sech = (1 / torch.cosh(r))[:, None]
+    t_p = (torch.exp(1j * theta) * torch.tanh(r))[:, None]
+    t_m = (torch.exp(-1j * theta) * torch.tanh(r))[:, None]
+    idx = torch.arange(d, device=r.device)
+    # A_0[m, n] = T[m, n, m - n, 0], m >= n
+    diag = sech * t_p ** idx[None, :]                                    # [N, n]: T[n, n, 0, 0]
+    rows = []
+    for m in range(d):
+        if m == 0:
+            row = torch.zeros(nb, d, dtype=diag.dtype, device=r.device)
+        else:                                                            # sech sqrt(m / (m - n)) A_0[m - 1, n], n < m
+            fac = torch.where(idx < m, sq[m] / sq[(m - idx).clamp(min=1)], torch.zeros_like(sq))
+            row = sech * fac[None, :] * rows[m - 1]
+        row = torch.where(idx[None, :] == m, diag, row)
+        rows.append(row)
+    a = torch.stack(rows, dim=1)                                         # [N, m, n]
+    out = torch.zeros(nb, d, d, d, d, dtype=a.dtype, device=r.device)
+    mm, nn_ = idx[:, None].expand(d, d), idx[None, :].expand(d, d)
+    for q in range(d):
+        pp = q + mm - nn_
+        valid = (pp >= 0) & (pp < d)
+        if q > 0:
+            shifted = torch.cat([torch.zeros_like(a[:, :, :1]), a[:, :, :-1]], dim=2)    # A_{q-1}[m, n - 1]
+            a = (sech[:, :, None] * (sq[nn_] / sq[q])[None] * shifted
+                 - t_m[:, :, None] * (sq[pp.clamp(0, d - 1)] / sq[q])[None] * a)
+            a = a * valid[None]
+        sel = valid.nonzero(as_tuple=True)
+        out[:, sel[0], sel[1], pp[sel], q] = a[:, sel[0], sel[1]]
+    return out
 
 
 def bs_matrix_state(u: torch.Tensor, d: int) -> torch.Tensor:
@@ -239,6 +277,20 @@ class Displacement(Squeezing):
     @staticmethod
     def _batched_matrix_state(p, d):
         return displacement_matrix_state(p[:, 0], p[:, 1], d)
+
+
+class Squeezing2(BeamSplitter):
+    """Two-mode squeezing S2(r, theta) (reference photonic/gate.py:1157-1333); parameters handled like BS(theta, phi)."""
+
+    def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, requires_grad: bool = False):
+        if inputs is None:
+            inputs = [torch.rand(1)[0], torch.rand(1)[0] * 2 * torch.pi]
+        super().__init__(inputs, nmode, wires, cutoff, requires_grad)
+        self.name = 'Squeezing2'
+
+    @staticmethod
+    def _batched_matrix_state(p, d):
+        return squeezing2_matrix_state(p[:, 0], p[:, 1], d)
 
 
 class MZI(BeamSplitter):
@@ -495,6 +547,14 @@ class QumodeCircuit(nn.Module):
         else:
             inputs = [torch.rand(1)[0] if r is None else r, 0.0 if theta is None else theta]
         self.add(Displacement(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+
+    def s2(self, wires, r=None, theta=None, encode=False, mu=None, sigma=None):
+        assert mu is None and sigma is None, 'gate noise is outside the accelerated Fock tensor path'
+        if r is None and theta is None:
+            inputs = None
+        else:
+            inputs = [torch.rand(1)[0] if r is None else r, 0.0 if theta is None else theta]
+        self.add(Squeezing2(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
 
     def build_matrices(self, cdtype, device):
         """All Fock transformation matrices of the circuit: one batched evaluation per gate class (and variant)."""

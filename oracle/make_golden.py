@@ -237,7 +237,8 @@ FOCK2_SPEC = [
     {'g': 'r', 'w': [1], 'p': [0.45], 'inv_mode': True}, {'g': 'f', 'w': [2]}, {'g': 'k', 'w': [0], 'p': [0.2]},
     {'g': 'ck', 'w': [1, 2], 'p': [0.1]}, {'g': 'bs', 'w': [0, 2], 'p': [0.6, 2.2]}, {'g': 'ck', 'w': [2, 0], 'p': [0.35]},
     {'g': 'd', 'w': [1], 'p': [0.25, 0.9]}, {'g': 'd', 'w': [2], 'p': [0.4, -1.7]}, {'g': 'bs_rx', 'w': [1, 2], 'p': [1.1]},
-    {'g': 'd', 'w': [0], 'p': [0.15, 0.0]}]
+    {'g': 'd', 'w': [0], 'p': [0.15, 0.0]}, {'g': 's2', 'w': [0, 1], 'p': [0.2, 0.8]}, {'g': 's2', 'w': [2, 0], 'p': [0.12, -2.0]},
+    {'g': 'bs', 'w': [1, 2], 'p': [1.0, 0.3]}]
 
 
 def apply_fock_spec(cir, spec):
@@ -245,6 +246,8 @@ def apply_fock_spec(cir, spec):
         g, w, prm = e['g'], e['w'], e.get('p', [])
         if g in ('s', 'd'):
             getattr(cir, g)(w[0], r=prm[0], theta=prm[1])
+        elif g == 's2':
+            cir.s2(w, r=prm[0], theta=prm[1])
         elif g in ('bs', 'mzi'):
             getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
         elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):

@@ -25,6 +25,8 @@ def _apply(cir, spec):
         g, w, prm = e['g'], e['w'], e.get('p', [])
         if g in ('s', 'd'):
             getattr(cir, g)(w[0], prm[0], prm[1])
+        elif g == 's2':
+            cir.s2(w, prm[0], prm[1])
         elif g in ('bs', 'mzi'):
             getattr(cir, g)(w, prm, **({'phi_first': e['phi_first']} if 'phi_first' in e else {}))
         elif g in ('bs_theta', 'bs_phi', 'bs_rx', 'bs_ry', 'bs_h', 'ck'):

@@ -13,15 +13,23 @@ from .operation import Channel
 
 
 def _kraus(entries) -> torch.Tensor:
-    """[[k00, k01, k10, k11], ...] of broadcastable real/complex tensors `[...]` -> `[..., n_kraus, 2, 2]` complex."""
-    shape = torch.broadcast_shapes(*[torch.as_tensor(e).shape for k in entries for e in k if isinstance(e, torch.Tensor)])
-    ref = next(e for k in entries for e in k if isinstance(e, torch.Tensor))
+    """[[k00, k01, k10, k11], ...] of broadcastable real/complex tensors `[...]` (or the constants 0 / 1) ->
+    `[..., n_kraus, 2, 2]` complex, with ONE stack over all entries (constants share one tensor: the assembly of a
+    noisy circuit is launch-bound, every avoided small kernel counts)."""
+    tensors = [e for k in entries for e in k if isinstance(e, torch.Tensor)]
+    shape = torch.broadcast_shapes(*[e.shape for e in tensors])
+    ref = tensors[0]
+    cdtype = torch.complex64 if ref.dtype in (torch.float32, torch.complex64) else torch.complex128
+    consts = {}
 
     def full(e):
-        if not isinstance(e, torch.Tensor):
-            e = torch.full(shape, e, dtype=ref.dtype, device=ref.device)
-        return (e + 0j).expand(shape)
-    return torch.stack([torch.stack([full(e) for e in k], dim=-1).reshape(*shape, 2, 2) for k in entries], dim=-3)
+        if isinstance(e, torch.Tensor):
+            return e.to(cdtype).expand(shape)
+        if e not in consts:
+            consts[e] = torch.full(shape, e, dtype=cdtype, device=ref.device)
+        return consts[e]
+    flat = torch.stack([full(e) for k in entries for e in k], dim=-1)
+    return flat.reshape(*shape, len(entries), 2, 2)
 
 
 class _OneParam(Channel):

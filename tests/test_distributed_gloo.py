@@ -52,7 +52,12 @@ class EmuExecutor:
         return torch.tensor([p[idx == int(k)].sum() for k in keys_sorted.tolist()], dtype=torch.float64)
 
 
-def _build(cir, n):
+def dq_mod():
+    import deepquantum_b200
+    return deepquantum_b200
+
+
+def _build(cir, n, extra=False):
     """A circuit that exercises every sharded case: global 1-target gates, global / local controls, global
     diagonal gates (1 and 2 targets, controlled), dense 2- and 3-target gates touching global wires, swaps."""
     g = torch.Generator().manual_seed(11)
@@ -79,6 +84,11 @@ def _build(cir, n):
     q, _ = torch.linalg.qr(torch.randn(8, 8, generator=g, dtype=torch.float64) + 1j * torch.randn(8, 8, generator=g,
                                                                                                  dtype=torch.float64))
     cir.any(q, wires=[n - 1, 0, 3])
+    if extra:   # gloo runs only (tests/dist_gpu_worker.py keeps the circuit it was verified with on the GPUs)
+        cir.hamiltonian([[0.4, 'x0z3'], [-0.7, 'y1']], t=r())                  # dense block spanning wires 0..3
+        cir.hamiltonian([1.1, 'z0'], t=r(), controls=[n - 1])
+        cir.add(dq_mod().CombinedSingleGate([dq_mod().Rx(0.3), dq_mod().Hadamard(), dq_mod().Rz(1.1)], nqubit=n,
+                                            wires=[0], controls=[2]))
     cir.ylayer()
     for w in range(n):
         cir.ry(w, r())
@@ -96,7 +106,7 @@ def _worker(rank, world, port, n, outdir):
     r, w, _ = dq.setup_distributed('gloo')
     assert (r, w) == (rank, world)
     try:
-        cir = _build(dq.DistributedQubitCircuit(n), n)
+        cir = _build(dq.DistributedQubitCircuit(n), n, extra=True)
         cir.to(torch.double)
         cir._executor = EmuExecutor()
         st = cir()
@@ -151,7 +161,7 @@ def test_sharded_circuit_matches_dense_oracle(world, tmp_path):
     assert all(pr.returncode == 0 for pr in procs), '\n'.join(logs)
     res = np.load(os.path.join(tmp_path, 'out.npz'))
     # dense reference: the same builder calls on the single-device circuit, lowered to oracle ops
-    dense = _build(dq.QubitCircuit(n), n)
+    dense = _build(dq.QubitCircuit(n), n, extra=True)
     dense.to(torch.double)
     ops = [(op.update_matrix().detach().numpy(), op.wires, op.controls) for op in dense.operators]
     ref = so.run_circuit(ops, n)

@@ -151,7 +151,8 @@ def _statements(text: str):
     return out
 
 
-_CALL = re.compile(r'^((?:(?:inv|ctrl|negctrl|pow\s*\([^@]*\))\s*@\s*)*)([A-Za-z_]\w*)\s*(?:\((.*)\))?\s+(.+)$', re.S)
+_CALL = re.compile(r'^((?:(?:inv|ctrl|negctrl|pow\s*\([^@]*\))\s*@\s*)*)([A-Za-z_]\w*)'
+                   r'(?:\s*\((.*)\)\s*|\s+)(.+)$', re.S)
 _INVERSE_NAME = {'s': 'sdg', 'sdg': 's', 't': 'tdg', 'tdg': 't'}
 _NEGATE = ('rx', 'ry', 'rz', 'p', 'rxx', 'ryy', 'rzz')
 _PLAIN = {'h': 'h', 'x': 'x', 'y': 'y', 'z': 'z', 's': 's', 'sdg': 'sdg', 't': 't', 'tdg': 'tdg', 'swap': 'swap'}
@@ -248,9 +249,12 @@ def qasm3_to_cir(qasm_string: str) -> QubitCircuit:
             if head in ('OPENQASM', 'include', 'bit', 'qubit', 'defcal', 'const', 'input', 'output'):
                 continue
             if re.search(r'\bmeasure\b', stmt):
-                for w in re.findall(r'\bmeasure\s+[A-Za-z_]\w*\s*\[\s*(\d+)\s*\]', stmt):
-                    if int(w) not in cir.wires_measure:
-                        cir.wires_measure.append(int(w))
+                found = [int(w) for w in re.findall(r'\bmeasure\s+[A-Za-z_]\w*\s*\[\s*(\d+)\s*\]', stmt)]
+                if not found and re.search(r'\bmeasure\s+[A-Za-z_]\w*\s*$', stmt):    # the whole register
+                    found = list(range(cir.nqubit))
+                for w in found:
+                    if w not in cir.wires_measure:
+                        cir.wires_measure.append(w)
                 continue
             if head == 'barrier':
                 ops = [o for o in _split_top(stmt[len('barrier'):]) if o]

@@ -66,6 +66,20 @@ def test_inverse_modifier_inverts():
     np.testing.assert_allclose(out, np.full(4, 0.5), atol=2e-6)
 
 
+def test_syntax_variants():
+    cir = qasm3_to_cir('OPENQASM 3;\nqubit [ 3 ]  q ;\nbit[3] c;\ncx q[0],q[1];\nrx(pi/2)q[2];\nctrl@x q[0],q[2];\n'
+                       ' rz ( 0.1 + 0.2 )  q[1] ;\n pow ( 2 ) @ s q[2];\nc = measure q;\n')
+    got = [(type(o).__name__, o.wires, o.controls) for o in cir.operators]
+    assert got == [('CNOT', [0, 1], []), ('Rx', [2], []), ('PauliX', [2], [0]), ('Rz', [1], []), ('SGate', [2], []),
+                   ('SGate', [2], [])]
+    assert abs(float(cir.operators[1].theta) - np.pi / 2) < 1e-6 and abs(float(cir.operators[3].theta) - 0.3) < 1e-6
+    assert cir.wires_measure == [0, 1, 2]
+    bell = qasm3_to_cir('OPENQASM 3.0; qubit[3] q; gate bell a, b { h a; cx a, b; } bell q[0], q[1]; '
+                        'ctrl @ bell q[2], q[0], q[1];')
+    assert [(type(o).__name__, o.wires, o.controls) for o in bell.operators] == [
+        ('Hadamard', [0], []), ('CNOT', [0, 1], []), ('Hadamard', [0], [2]), ('PauliX', [1], [2, 0])]
+
+
 def test_barrier_comments_and_errors():
     src = '''OPENQASM 3.0;   // header
     include "stdgates.inc";

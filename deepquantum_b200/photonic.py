@@ -429,7 +429,8 @@ class CrossKerr(Kerr):
 
 
 class FockState(nn.Module):
-    """Fock state tensor `[1, cutoff, ..., cutoff]`; `'vac'` or a list of photon numbers
+    """Fock state tensor `[1, cutoff, ..., cutoff]`: `'vac'`, a list of photon numbers, a superposition
+    `[(amplitude, [photon numbers]), ...]` (not normalised, like the reference) or a complex tensor
     (photonic/state.py:20-119, `basis=False`)."""
 
     def __init__(self, state: Any = 'vac', nmode: int | None = None, cutoff: int | None = None):
@@ -442,15 +443,19 @@ class FockState(nn.Module):
             nmode = state.ndim - 1 if nmode is None else nmode
             cutoff = state.shape[-1] if cutoff is None else cutoff
         else:
-            occ = [int(x) for x in state]
-            nmode = len(occ) if nmode is None else nmode
-            cutoff = sum(occ) + 1 if cutoff is None else cutoff
+            assert isinstance(state, (list, tuple))
+            terms = [(1.0, list(state))] if all(isinstance(i, int) for i in state) else list(state)
+            assert all(isinstance(i, tuple) for i in terms)
+            occ = terms
+            nmode = len(terms[0][1]) if nmode is None else nmode
+            cutoff = max(sum(o) for _, o in terms) + 1 if cutoff is None else cutoff
         self.nmode, self.cutoff = nmode, cutoff
         if occ is None:
             t = state.reshape([-1] + [cutoff] * nmode)
         else:
             t = torch.zeros([1] + [cutoff] * nmode, dtype=torch.cfloat)
-            t[(0,) + tuple(occ)] = 1.0
+            for amp, o in ([(1.0, occ)] if isinstance(occ[0], int) else occ):
+                t[(0,) + tuple(int(x) for x in o)] = amp
         self.register_buffer('state', t)
 
     def _apply(self, fn):

@@ -359,3 +359,44 @@ def test_composition_and_encoding_of_density_matrix_circuits():
     spec = [{'g': 'rx', 'w': [0], 'p': [0.1]}, {'g': 'depolarizing', 'w': [1], 'p': [0.2]},
             {'g': 'pauli', 'w': [0], 'p': [0.3, 0.4, 0.5, 0.6]}]
     np.testing.assert_allclose(out[0].reshape(4, 4), do.run_spec(spec, 2), atol=2e-7)
+
+
+def test_two_wire_custom_channel():
+    """A correlated two-qubit channel (user subclass of Channel): one dense 4-target superoperator record."""
+    class CorrelatedFlip(dq.Channel):
+        def get_matrix(self, theta):
+            p = torch.sin(self.inputs_to_tensor(theta).reshape(-1)) ** 2
+            x = torch.tensor([[0, 1], [1, 0]], dtype=torch.cfloat)
+            y = torch.tensor([[0, -1j], [1j, 0]], dtype=torch.cfloat)
+            return torch.stack([torch.sqrt(1 - p) * torch.eye(4, dtype=torch.cfloat), torch.sqrt(p) * torch.kron(x, y)])
+
+    n = 3
+    cir = dq.QubitCircuit(n, den_mat=True)
+    cir.hlayer()
+    cir.rx(0, 0.4)
+    cir.cnot(0, 2)
+    cir.add(CorrelatedFlip(0.6, nqubit=n, wires=[2, 0]))
+    cir.ry(1, 0.9)
+    cir.add(CorrelatedFlip(0.3, nqubit=n, wires=[0, 1]))
+    cir.to(torch.double)
+    prog = cir._get_program()
+    assert [r[0] for r in prog.low.records if isinstance(r[0], str)] == ['super', 'super']
+    out, _ = emu_run_program(prog, 2 * n, np.complex128)
+    import gates_np
+    rho = np.zeros(4**n, dtype=complex)
+    rho[0] = 1
+    for w in range(n):
+        rho = do.evolve_den_mat(rho, gates_np.H, n, [w])
+    rho = do.evolve_den_mat(rho, gates_np.rx(gates_np.f32(0.4)), n, [0])
+    rho = do.evolve_den_mat(rho, gates_np.X, n, [2], [0])
+    xy = np.kron(gates_np.X, gates_np.Y)
+
+    def flip(r, th, wires):
+        p = np.sin(np.float64(np.float32(th))) ** 2
+        return sum(do.evolve_den_mat(r, k, n, wires) for k in (np.sqrt(1 - p) * np.eye(4), np.sqrt(p) * xy))
+
+    rho = flip(rho, 0.6, [2, 0])
+    rho = do.evolve_den_mat(rho, gates_np.ry(gates_np.f32(0.9)), n, [1])
+    rho = flip(rho, 0.3, [0, 1])
+    np.testing.assert_allclose(out[0], rho, atol=1e-7)
+    assert abs(out[0].reshape(8, 8).trace() - 1) < 1e-6      # float32-rounded Hadamard constants, like the reference

@@ -69,6 +69,10 @@ _SIGNATURES = {
                                        C.c_void_p]),
     'b200q_plan_run_exchange': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                           C.POINTER(C.c_uint8), C.c_void_p]),
+    'b200q_plan_codegen': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_size_t)]),
+    'b200q_plan_compile': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    'b200q_plan_jit_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'b200q_apply_gate': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     'b200q_norm2': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),

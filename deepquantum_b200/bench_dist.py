@@ -1,5 +1,5 @@
 """bench.py for N > 1 ranks (launched by torchrun, one rank per GPU, NCCL): the SAME circuit as the
-single-GPU headline (28 qubits, depth 40 unless --nqubit/--depth say otherwise) with the high-order qubit
+single-GPU headline (30 qubits, depth 40 unless --nqubit/--depth say otherwise) with the high-order qubit
 index sharded over the ranks -> strong scaling."""
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ def run(args):
 
     rank, world, local_rank = dq.setup_distributed('nccl')
     dev = torch.device('cuda', local_rank)
-    n = args.nqubit or 28
+    n = args.nqubit or 30
     depth = args.depth or 40
     g = world.bit_length() - 1
     circ.PLAN_OPTIONS.update(chunk_bits=args.chunk_bits, fuse=not args.no_fuse)

@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "../../include/b200q.h"
+#include "b200q_codegen.h"
+#include "b200q_jit.h"
 #include "b200q_planner.h"
 #include "b200q_tile_body.h"
 
@@ -209,8 +211,19 @@ int launch_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubi
   return cuda_err(cudaGetLastError(), "tile kernel launch");
 }
 
+// JIT policy: B200Q_JIT=0 disables the specialised kernels; B200Q_JIT_MIN_QUBITS (default 20) is the smallest state
+// worth a compilation (below it a pass is launch-latency bound); plans are compiled lazily at their first run.
+int jit_min_qubits() {
+  static const int v = [] { const char* e = getenv("B200Q_JIT_MIN_QUBITS"); return e ? atoi(e) : 20; }();
+  return v;
+}
+
 int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const void* mats, int64_t batch,
-                    int64_t mbs, cudaStream_t stream, const b200q_remote_t* remote = nullptr) {
+                    int64_t mbs, cudaStream_t stream, const b200q_remote_t* remote = nullptr, int pass_index = -1) {
+  if (pass_index >= 0 && pl.jit && pl.jit->prepared) {
+    const int rc = jit_launch(const_cast<Plan&>(pl), pass_index, state, mats, batch, mbs, stream, remote);
+    if (rc != -1000) return rc > 0 ? cuda_err((cudaError_t)rc, "specialised pass kernel launch") : rc;
+  }
   const int cb = pl.opt.chunk_bits;
   if (pl.dtype == B200Q_C64) {
     switch (cb) {
@@ -583,8 +596,9 @@ int b200q_plan_run_range(const b200q_plan_t* plan, int first, int last, void* st
     for (const auto& ps : p.passes) need |= ps.pool_elems != 0;
     if (need) return set_err(B200Q_EINVAL, "null matrix buffer");
   }
+  if ((!p.jit || !p.jit->prepared) && p.n_qubits >= jit_min_qubits()) jit_prepare(*plan->p, 0, false);
   for (int i = first; i < last; ++i) {
-    rc = launch_pass_any(p, p.passes[i], state, matrices, batch, mbs, (cudaStream_t)stream);
+    rc = launch_pass_any(p, p.passes[i], state, matrices, batch, mbs, (cudaStream_t)stream, nullptr, i);
     if (rc) return rc;
   }
   return 0;
@@ -632,9 +646,54 @@ int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* m
   const int last = (int)p.passes.size() - 1;
   if (p.dtype == B200Q_C64 && (p.passes[last].layout & B200Q_LAYOUT_DST_SOA))
     return set_err(B200Q_EUNSUPPORTED, "last pass does not write the caller layout");
+  if (p.n_qubits >= jit_min_qubits() && (!p.jit || !p.jit->prepared || !p.jit->remote[last])) jit_prepare(*plan->p, 0, true);
   for (int i = 0; i <= last; ++i) {
-    rc = launch_pass_any(p, p.passes[i], state, matrices, 1, 0, (cudaStream_t)stream, i == last ? &R : nullptr);
+    rc = launch_pass_any(p, p.passes[i], state, matrices, 1, 0, (cudaStream_t)stream, i == last ? &R : nullptr, i);
     if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200q_plan_codegen(const b200q_plan_t* plan, int pass_index, int remote, char* buf, size_t buf_size, size_t* needed,
+                       size_t* smem_bytes) {
+  if (!plan || pass_index < 0 || pass_index >= (int)plan->p->passes.size()) return set_err(B200Q_EINVAL, "bad pass index");
+  const Plan& p = *plan->p;
+  if (!codegen_supported(p, p.passes[pass_index]))
+    return set_err(B200Q_EUNSUPPORTED, "pass not covered by the kernel generator (small or padded state)");
+  GenOptions go;
+  go.remote = remote ? 1 : 0;
+  size_t smem = 0;
+  std::string stats;
+  const std::string src = codegen_pass(p, p.passes[pass_index], go, &smem, &stats);
+  if (needed) *needed = src.size() + 1;
+  if (smem_bytes) *smem_bytes = smem;
+  if (buf && buf_size >= src.size() + 1) std::memcpy(buf, src.c_str(), src.size() + 1);
+  g_err = stats;   // generator statistics of the pass, readable through b200q_last_error()
+  return 0;
+}
+
+int b200q_plan_compile(b200q_plan_t* plan, int threads, int with_exchange_variant) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  std::string why;
+  if (jit_available(&why)) return set_err(B200Q_EUNSUPPORTED, "run-time compilation unavailable: " + why);
+  return jit_prepare(*plan->p, threads, with_exchange_variant != 0);
+}
+
+int b200q_plan_jit_status(const b200q_plan_t* plan, int32_t* n_specialised, int32_t* n_failed) {
+  if (!plan) return set_err(B200Q_EINVAL, "null plan");
+  const Plan& p = *plan->p;
+  int ok = 0, bad = 0;
+  if (p.jit) {
+    for (const auto& k : p.jit->local) {
+      if (k && k->compiled) ++ok;
+      else if (k) ++bad;
+    }
+  }
+  if (n_specialised) *n_specialised = ok;
+  if (n_failed) *n_failed = bad;
+  if (bad && p.jit) {
+    for (const auto& k : p.jit->local)
+      if (k && !k->compiled) { g_err = k->log; break; }
   }
   return 0;
 }

@@ -2,6 +2,7 @@
 // Pure host C++ (no CUDA), so it is unit-tested on CPU.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,8 @@ struct PlanOptions {
   int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
 };
 
+struct PlanJit;   // run-time specialised kernels of the passes (b200q_jit.h); never touched by the planner
+
 struct PlanStats {
   int n_gates = 0, n_passes = 0, n_rounds = 0, n_ops = 0, n_direct = 0;
 };
@@ -41,6 +44,7 @@ class Plan {
   std::vector<int> pass_gate_count;
   PlanStats stats;
   std::string error;
+  std::shared_ptr<PlanJit> jit;
 };
 
 // Returns nullptr and fills `err` on invalid input.

@@ -81,6 +81,29 @@ class FusedPlan:
         L.check(lib.b200q_plan_export(self._h, buf, need.value, C.byref(need)))
         return buf.raw
 
+    def compile(self, threads: int = 0, exchange_variant: bool = False) -> int:
+        """Compile the specialised kernel of every pass now (NVRTC, sm_100a; needs no GPU).  Returns the number
+        of passes that have one.  `run` does this lazily for states of >= 20 qubits."""
+        rc = L.load().b200q_plan_compile(self._h, threads, int(exchange_variant))
+        if rc < 0:
+            L.check(rc)
+        return rc
+
+    def jit_status(self) -> dict:
+        """{'specialised': passes that run a run-time compiled kernel, 'failed': passes whose compilation failed}."""
+        ok, bad = C.c_int32(), C.c_int32()
+        L.check(L.load().b200q_plan_jit_status(self._h, C.byref(ok), C.byref(bad)))
+        return {'specialised': ok.value, 'failed': bad.value}
+
+    def codegen(self, i: int, remote: bool = False) -> str:
+        """Generated CUDA source of pass i (diagnostics)."""
+        lib = L.load()
+        n, smem = C.c_size_t(), C.c_size_t()
+        L.check(lib.b200q_plan_codegen(self._h, i, int(remote), None, 0, C.byref(n), C.byref(smem)))
+        buf = C.create_string_buffer(n.value)
+        L.check(lib.b200q_plan_codegen(self._h, i, int(remote), buf, n.value, C.byref(n), C.byref(smem)))
+        return buf.value.decode()
+
     def run(self, state: torch.Tensor, mats: torch.Tensor | None, batch: int = 1, mat_batch_stride: int = 0,
             first: int | None = None, last: int | None = None) -> None:
         """Apply the plan IN PLACE to `state` (contiguous, batch * 2^n complex elements)."""

@@ -113,6 +113,22 @@ int b200q_plan_run_range(const b200q_plan_t* plan, int first_pass, int last_pass
  * stores are complete when the kernels have finished on every rank) and swaps the roles of shard and buffer. */
 int b200q_plan_run_exchange(const b200q_plan_t* plan, void* state, const void* matrices, void* const* peer_buffers,
                             int n_ranks, int rank, const uint8_t* perm, void* stream);
+/* ---- per-pass kernel specialisation (same path as above, compiled at run time) ---------------------------------
+ * The generic tile kernel interprets the op list of a pass; for states of >= 20 qubits (B200Q_JIT_MIN_QUBITS) every
+ * pass of a plan is instead turned into CUDA source with the op sequence, register slots, control masks and index
+ * arithmetic as constants, compiled with NVRTC for sm_100a (cubins cached next to the library) and launched by
+ * b200q_plan_run* in place of the generic kernel.  B200Q_JIT=0 disables it.
+ *   b200q_plan_codegen:    the generated source of one pass (`remote` != 0: the fused-exchange variant); the needed
+ *                          buffer size (with the terminating 0) goes to *needed_out, the dynamic shared memory of the
+ *                          kernel to *smem_bytes_out.  Host only.
+ *   b200q_plan_compile:    compile every pass now (needs no GPU; `threads` <= 0: all host cores); returns the number
+ *                          of passes that have a specialised kernel, or a negative error.
+ *   b200q_plan_jit_status: how many passes of the plan run specialised kernels / failed to compile. */
+int b200q_plan_codegen(const b200q_plan_t* plan, int pass_index, int remote, char* buf, size_t buf_size,
+                       size_t* needed_out, size_t* smem_bytes_out);
+int b200q_plan_compile(b200q_plan_t* plan, int threads, int with_exchange_variant);
+int b200q_plan_jit_status(const b200q_plan_t* plan, int32_t* n_specialised_out, int32_t* n_failed_out);
+
 /* One gate, no plan object: the direct counterpart of
  *   evolve_state(state, matrix, nqudit, wires)            (qmath.py:485)      controls == NULL
  *   Gate.op_state_control(x, matrix)                      (operation.py:203)  controls != NULL  */

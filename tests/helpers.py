@@ -131,3 +131,86 @@ def emu_adjoint(ops, nqubit, cdtype, psi_final, lam_final, chunk_bits=0, need=No
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return psi, lam, grad
+
+
+# ---- generated (specialised) pass kernels, stepped on the CPU ---------------------------------------------------
+def codegen_sources(nqubit, cdtype, arr, ngates, chunk_bits=0, remote_last=False, **planopts):
+    """Plan the gates with the product library and return, per pass, (source, pass header dict).  Host only."""
+    lib = L.load()
+    opt = L.PlanOptions()
+    opt.chunk_bits = chunk_bits
+    opt.fuse = planopts.get('fuse', 1)
+    opt.low_bits = planopts.get('low_bits', 0)
+    opt.max_rounds = planopts.get('max_rounds', 0)
+    plan = C.c_void_p()
+    L.check(lib.b200q_plan_create(nqubit, L.C64 if cdtype == np.complex64 else L.C128, arr, ngates, C.byref(opt),
+                                  C.byref(plan)))
+    try:
+        st = L.PlanStats()
+        L.check(lib.b200q_plan_get_stats(plan, C.byref(st)))
+        need = C.c_size_t()
+        L.check(lib.b200q_plan_export(plan, None, 0, C.byref(need)))
+        raw = (C.c_uint8 * need.value)()
+        L.check(lib.b200q_plan_export(plan, raw, need.value, C.byref(need)))
+        psize = need.value // max(1, st.n_passes)
+        out = []
+        for i in range(st.n_passes):
+            hdr = bytes(raw[i * psize:i * psize + 5])
+            info = {'n_bits': hdr[0], 'n_qubits': hdr[1], 'tile_bits': hdr[2], 'n_rounds': hdr[3], 'n_ops': hdr[4]}
+            n = C.c_size_t()
+            smem = C.c_size_t()
+            remote = int(remote_last and i == st.n_passes - 1)
+            rc = lib.b200q_plan_codegen(plan, i, remote, None, 0, C.byref(n), C.byref(smem))
+            if rc != 0:
+                out.append((None, info))
+                continue
+            buf = C.create_string_buffer(n.value)
+            L.check(lib.b200q_plan_codegen(plan, i, remote, buf, n.value, C.byref(n), C.byref(smem)))
+            info['stats'] = lib.b200q_last_error().decode()
+            info['smem'] = smem.value
+            out.append((buf.value.decode(), info))
+        return out
+    finally:
+        lib.b200q_plan_destroy(plan)
+
+
+def compile_generated_host(source):
+    """g++ build of one generated pass source (its host half): returns the loaded library."""
+    import hashlib
+    import subprocess
+    d = os.path.join(ROOT, 'tests', 'native', '_build', 'gen')
+    os.makedirs(d, exist_ok=True)
+    h = hashlib.sha1(source.encode()).hexdigest()[:20]
+    so = os.path.join(d, h + '.so')
+    if not os.path.exists(so):
+        src = os.path.join(d, h + '.cpp')
+        with open(src, 'w') as f:
+            f.write(source)
+        subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-x', 'c++', src, '-o', so + '.tmp'])
+        os.replace(so + '.tmp', so)
+    lib = C.CDLL(so)
+    lib.b200qj_emulate.restype = None
+    lib.b200qj_emulate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint64, C.c_int,
+                                   C.c_void_p]
+    return lib
+
+
+def gen_run(ops, nqubit, cdtype, state=None, chunk_bits=0, batch=1, **planopts):
+    """Run lowered ops through planner + GENERATED pass kernels stepped on the CPU (passes the generator does not
+    cover go through the emulator of the generic kernel body).  Returns (state, list of pass infos)."""
+    arr, ng, mats = lower_ops(ops, nqubit, cdtype)
+    if state is None:
+        state = np.zeros((batch, 2**nqubit), dtype=cdtype)
+        state[:, 0] = 1
+    else:
+        state = np.ascontiguousarray(np.asarray(state, dtype=cdtype).reshape(batch, 2**nqubit)).copy()
+    vs = 1 if cdtype == np.complex64 else 0
+    infos = []
+    for src, info in codegen_sources(nqubit, cdtype, arr, ng, chunk_bits=chunk_bits, **planopts):
+        assert src is not None, 'pass not covered by the generator'
+        lib = compile_generated_host(src)
+        tile_shift = info['n_bits'] - info['tile_bits']
+        lib.b200qj_emulate(state.ctypes.data, mats.ctypes.data, (2**nqubit) >> vs, 0, tile_shift,
+                           (1 << tile_shift) * batch, 1, None)
+        infos.append(info)
+    return state, infos

@@ -177,6 +177,24 @@ extern "C" int hostemu_run(int n_qubits, int dtype, const b200q_gate_t* gates, i
   return 0;
 }
 
+// Passes [first, last) of the plan only: lets tests compare the generic kernel body with the generated pass kernels
+// pass by pass.
+extern "C" int hostemu_run_range(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates, int chunk_bits,
+                                 int fuse, int first, int last, void* state, const void* mats, int64_t batch) {
+  PlanOptions opt;
+  if (chunk_bits) opt.chunk_bits = chunk_bits;
+  opt.fuse = fuse & 1;
+  std::string err;
+  Plan* pl = make_plan(n_qubits, dtype, gates, n_gates, opt, &err);
+  if (!pl) return -1;
+  for (int i = first; i < last && i < (int)pl->passes.size(); ++i) {
+    if (dtype == B200Q_C64) run_pass<float>(*pl, pl->passes[i], state, mats, batch, 0);
+    else run_pass<double>(*pl, pl->passes[i], state, mats, batch, 0);
+  }
+  delete pl;
+  return 0;
+}
+
 // Fused pass + exchange for ONE rank with all ranks' buffers in one address space: the plan runs on `state`; its
 // last pass scatters into buffers[0..W-1] exactly like the kernel does through the NVLink peer mappings.
 // perm: bit permutation of the distributed index (NULL: block transpose), same convention as the C ABI.

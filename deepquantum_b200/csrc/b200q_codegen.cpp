@@ -241,16 +241,13 @@ struct Gen {
     return s;
   }
   std::string W(int v) const { return "w" + std::to_string(v); }
-  const char* RL(double v) const {   // Real literal
-    static char buf[4][64];
-    static int k = 0;
-    k = (k + 1) & 3;
-    snprintf(buf[k], sizeof buf[k], f32 ? "%.9gf" : "%.17g", v);
-    if (!strchr(buf[k], '.') && !strchr(buf[k], 'e')) {
-      const size_t n = strlen(buf[k]);
-      if (f32) { buf[k][n - 1] = 0; strcat(buf[k], ".0f"); } else strcat(buf[k], ".0");
-    }
-    return buf[k];
+  std::string RL(double v) const {   // Real literal (re-entrant: passes are generated on several threads)
+    char buf[64];
+    snprintf(buf, sizeof buf, f32 ? "%.9g" : "%.17g", v);
+    std::string s(buf);
+    if (s.find('.') == std::string::npos && s.find('e') == std::string::npos) s += ".0";
+    if (f32) s += "f";
+    return s;
   }
 
   // expression that deposits bit k of `x` at position pos[k] (k = 0..n-1), consecutive runs merged
@@ -377,13 +374,13 @@ struct Gen {
     if (!mz[a]) return;
     ++n_mat_z;
     if (is_lane(a)) {
-      pf("    { const V s_ = vmk(%s, %s ? %s : %s);\n", RL(1), FZ(a).c_str(), RL(-1), RL(1));
+      pf("    { const V s_ = vmk(%s, %s ? %s : %s);\n", RL(1).c_str(), FZ(a).c_str(), RL(-1).c_str(), RL(1).c_str());
       for (int e = 0; e < 16; ++e)
         pf("      %s = vmul(%s, s_); %s = vmul(%s, s_);\n", W(vr[e]).c_str(), W(vr[e]).c_str(), W(vi[e]).c_str(),
            W(vi[e]).c_str());
     } else {
       const int b = cbit(a);
-      pf("    { const V s_ = vbc(%s ? %s : %s);\n", FZ(a).c_str(), RL(-1), RL(1));
+      pf("    { const V s_ = vbc(%s ? %s : %s);\n", FZ(a).c_str(), RL(-1).c_str(), RL(1).c_str());
       for (int e = 0; e < 16; ++e)
         if (e & b)
           pf("      %s = vmul(%s, s_); %s = vmul(%s, s_);\n", W(vr[e]).c_str(), W(vr[e]).c_str(), W(vi[e]).c_str(),
@@ -480,7 +477,7 @@ struct Gen {
     }
     if (!p.empty()) {
       // the sign of a negated controlled rotation cannot go to the pass scale
-      pf("        if (coef[%d] != %s) sg ^= 1u;\n      }\n", off + 4, RL(0));
+      pf("        if (coef[%d] != %s) sg ^= 1u;\n      }\n", off + 4, RL(0).c_str());
       msg = true;
     }
     pf("    }\n");
@@ -709,7 +706,7 @@ struct Gen {
         gid = tmp_id++;
         groups[key] = gid;
         auto ent = [&](int s, const char* part) {
-          if (s < 0) return std::string(part[0] == 'r' ? RL(1) : RL(0));
+          if (s < 0) return part[0] == 'r' ? RL(1) : RL(0);
           return sf("coef[%d + 2 * (ts_ | %du)]", off + (part[0] == 'r' ? 0 : 1), s);
         };
         if (NL == 2) {
@@ -768,7 +765,7 @@ struct Gen {
     }
     // frame
     for (int a = 0; a < RB; ++a) { mx[a] = mz[a] = false; pf("  u32 fx%d = 0u, fz%d = 0u;\n", a, a); }
-    pf("  u32 sg = 0u; Real rr = %s, ri = %s;\n", RL(1), RL(0));
+    pf("  u32 sg = 0u; Real rr = %s, ri = %s;\n", RL(1).c_str(), RL(0).c_str());
     msg = mrho = false;
     alias = -1;
     for (int oi = Rd.op_begin; oi < Rd.op_end; ++oi) {
@@ -871,7 +868,7 @@ struct Gen {
         if (i >> j & 1) o_ |= 1u << op.tk[j];
       pf("    p_[%d] = b200qj_amp(tile, base | 0x%xu); xr[%d] = p_[%d][0]; xi[%d] = p_[%d][B200QJ_IMOFF];\n", i, o_, i, i, i, i);
     }
-    pf("    for (int r_ = 0; r_ < %d; ++r_) {\n      Real yr = %s, yi = %s;\n", D, RL(0), RL(0));
+    pf("    for (int r_ = 0; r_ < %d; ++r_) {\n      Real yr = %s, yi = %s;\n", D, RL(0).c_str(), RL(0).c_str());
     pf("      for (int c_ = 0; c_ < %d; ++c_) {\n", D);
     pf("        const Real wr = coef[%d + 2 * (r_ * %d + c_)], wi = coef[%d + 2 * (r_ * %d + c_)];\n", off, D, off + 1, D);
     pf("        yr += wr * xr[c_] - wi * xi[c_]; yi += wr * xi[c_] + wi * xr[c_];\n      }\n");

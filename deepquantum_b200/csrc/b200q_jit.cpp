@@ -150,8 +150,8 @@ bool jit_compile_source(const std::string& source, std::vector<char>* cubin, std
     if (log) *log = std::string("nvrtcCreateProgram: ") + N.GetErrorString(rc);
     return false;
   }
-  const char* opts[] = {kArch, "--std=c++17", "-lineinfo", "-default-device"};
-  rc = N.CompileProgram(prog, 4, opts);
+  const char* opts[] = {kArch, "--std=c++17", "-lineinfo", "-default-device", "-w"};
+  rc = N.CompileProgram(prog, 5, opts);
   size_t ls = 0;
   N.GetProgramLogSize(prog, &ls);
   if (log && ls > 1) {

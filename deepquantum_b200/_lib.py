@@ -16,6 +16,15 @@ GATE_REAL = 2
 GATE_RXLIKE = 4
 GATE_HADAMARD = 8
 GATE_ROTATION = 16
+GATE_PHASE_SHIFT = 5          # 1-target diagonal gates: exactly diag(1, i^q), q = 1 (S), 2 (Z), 3 (S^dagger)
+GATE_PHASE_MASK = 3 << GATE_PHASE_SHIFT
+GATE_PHASE_S, GATE_PHASE_Z, GATE_PHASE_SDG = 1 << 5, 2 << 5, 3 << 5
+
+
+def conj_hint(hint: int) -> int:
+    """Structure hint of the complex-conjugated matrix (column records of the density-matrix lowering)."""
+    q = (hint & GATE_PHASE_MASK) >> GATE_PHASE_SHIFT
+    return (hint & ~GATE_PHASE_MASK) | (((4 - q) & 3) << GATE_PHASE_SHIFT)
 MAX_TARGETS = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libb200q.so')

@@ -206,6 +206,7 @@ struct Gen {
   int alias;
   int tmp_id = 0;
   // statistics
+  int n_free_phase = 0;
   int n_rename = 0, n_frame_x = 0, n_mat_x = 0, n_mat_z = 0, n_rho = 0, n_generic_diag = 0, n_phys_x = 0;
 
   Gen(const Plan& pl_, const b200q_pass_t& P_, const GenOptions& opt_) : pl(pl_), P(P_), opt(opt_) {
@@ -641,8 +642,57 @@ struct Gen {
       if (!t.empty()) tsel = tsel.empty() ? t : tsel + " | " + t;
     }
     if (tsel.empty()) tsel = "0u";
-    const bool unit = false;   // (reserved: unit-modulus hint)
-    (void)unit;
+    // hinted diag(1, i^q): no arithmetic when the qubit is a register slot (or, for Z, anywhere)
+    int q = int(op.k) == 1 ? int((op.flags & B200Q_FLAG_PHASE_MASK) >> B200Q_FLAG_PHASE_SHIFT) : 0;
+    if (q && (op.flags & B200Q_FLAG_ADJOINT)) q = (4 - q) & 3;
+    if (q == 2 && cr == 0) {
+      if (nreg == 1) {
+        const int a = sel_a[0];
+        // Z X^x Z^z = (-1)^x X^x Z^(z+1)
+        if (mx[a]) {
+          if (p.empty()) pf("    sg ^= %s;\n", FX(a).c_str());
+          else pf("    sg ^= %s & (u32)(%s);\n", FX(a).c_str(), p.c_str());
+          msg = true;
+        }
+        if (p.empty()) pf("    %s ^= 1u;   // Z on slot %d\n", FZ(a).c_str(), a);
+        else pf("    %s ^= (u32)(%s);   // Z on slot %d, thread-level control\n", FZ(a).c_str(), p.c_str(), a);
+        mz[a] = true;
+      } else {
+        if (p.empty()) pf("    sg ^= %s;   // Z on a thread-level bit\n", tsel.c_str());
+        else pf("    sg ^= (%s) & (u32)(%s);   // controlled Z on thread-level bits\n", tsel.c_str(), p.c_str());
+        msg = true;
+      }
+      ++n_free_phase;
+      return;
+    }
+    if ((q == 1 || q == 3) && cr == 0 && nreg == 1 && p.empty()) {
+      // S X^x Z^z = i^x X^x S Z^(x+z);  S^dagger = S Z: (-i)^x, one more Z
+      const int a = sel_a[0];
+      pf("    // %s on slot %d: re <-> im renaming\n", q == 1 ? "S" : "S^dagger", a);
+      if (is_lane(a)) {
+        for (int e = 0; e < 16; ++e) {
+          const std::string r = W(vr[e]), i = W(vi[e]);
+          pf("    { const Real t_ = vy(%s); %s = vmk(vx(%s), -vy(%s)); %s = vmk(vx(%s), t_); }\n", r.c_str(), r.c_str(),
+             r.c_str(), i.c_str(), i.c_str(), i.c_str());
+        }
+      } else {
+        const int b = cbit(a);
+        for (int e = 0; e < 16; ++e) {
+          if (!(e & b)) continue;
+          std::swap(vr[e], vi[e]);
+          pf("    %s = vneg(%s);\n", W(vr[e]).c_str(), W(vr[e]).c_str());
+        }
+      }
+      if (mx[a]) {
+        pf("    if (%s) { const Real t_ = rr; rr = %sri; ri = %st_; }\n", FX(a).c_str(), q == 1 ? "-" : "", q == 1 ? "" : "-");
+        mrho = true;
+        pf("    %s ^= %s;\n", FZ(a).c_str(), FX(a).c_str());
+        mz[a] = true;
+      }
+      if (q == 3) { pf("    %s ^= 1u;\n", FZ(a).c_str()); mz[a] = true; }
+      ++n_free_phase;
+      return;
+    }
     pf("    { // diagonal, %d selector(s), %d on register slots\n", int(op.k), nreg);
     if (nreg == 0 && cr == 0) {
       if (!p.empty()) pf("      if (%s)\n", p.c_str());
@@ -961,9 +1011,9 @@ struct Gen {
     }
     pf("    }\n  }\n  free(tile); free(coef); free(dest_tab);\n}\n#endif\n");
     if (stats) {
-      *stats = sf("ops %d rounds %d rename %d frame_x %d phys_x %d mat_x %d mat_z %d rho %d generic_diag %d coef_reals %d",
-                  int(P.n_ops), int(P.n_rounds), n_rename, n_frame_x, n_phys_x, n_mat_x, n_mat_z, n_rho, n_generic_diag,
-                  ncoef);
+      *stats = sf("ops %d rounds %d rename %d frame_x %d phys_x %d mat_x %d mat_z %d rho %d generic_diag %d free_phase %d "
+                  "coef_reals %d", int(P.n_ops), int(P.n_rounds), n_rename, n_frame_x, n_phys_x, n_mat_x, n_mat_z, n_rho,
+                  n_generic_diag, n_free_phase, ncoef);
     }
     return o.str();
   }

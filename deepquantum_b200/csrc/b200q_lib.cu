@@ -536,6 +536,11 @@ int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_
     if (options->reserved[0]) opt.structured = 0;   // A/B switch: general op codes only
     if (options->reserved[1]) opt.coalesce_bits = options->reserved[1] - 1;   // experiment: 1 + lane-owned chunk bits
   }
+  {   // plans that the specialised kernels will run (see jit_min_qubits) schedule the hinted phase gates for them
+    std::string why;
+    opt.free_phase = (opt.structured && n_qubits >= jit_min_qubits() && jit_available(&why) == 0) ? 1 : 0;
+    if (const char* e = getenv("B200Q_FREE_PHASE")) opt.free_phase = atoi(e);
+  }
   if (const char* e = getenv("B200Q_DEFER_DIAG")) opt.defer_diag = atoi(e);
   if (const char* e = getenv("B200Q_MIN_ROUND_GATES")) opt.min_round_gates = atoi(e);
   if (const char* e = getenv("B200Q_XC1_PENALTY")) opt.xc1_penalty = atoi(e);

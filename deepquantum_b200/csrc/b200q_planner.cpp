@@ -304,7 +304,13 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         for (size_t li = 0; li < list.size(); ++li) {
           const IGate& a = B.g[list[li]];
           bool defer = false;
-          if (a.op_kind == B200Q_OP_DIAG && a.ctrl == 0) {
+          const bool free_phase = B.opt.free_phase && a.op_kind == B200Q_OP_DIAG && a.ctrl == 0 && a.k == 1 &&
+                                  (a.flags & B200Q_GATE_PHASE_MASK) != 0;
+          if (free_phase) {
+            // free when its qubit is a register slot; otherwise wait (no gate of this round can need it done: a gate
+            // acting non-diagonally on the qubit would have it as a register slot)
+            defer = slot_of[a.t[0]] < 0;
+          } else if (a.op_kind == B200Q_OP_DIAG && a.ctrl == 0) {
             int nreg = 0;
             for (int j = 0; j < a.k; ++j) nreg += slot_of[a.t[j]] >= 0;
             if (nreg >= 1) {
@@ -329,7 +335,8 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
                              ((a.flags & B200Q_GATE_REAL) ? B200Q_FLAG_REAL : 0) |
                              ((a.flags & B200Q_GATE_RXLIKE) ? B200Q_FLAG_RXLIKE : 0) |
                              ((a.flags & B200Q_GATE_HADAMARD) ? B200Q_FLAG_HAD : 0) |
-                             ((a.flags & B200Q_GATE_ROTATION) ? B200Q_FLAG_ROT : 0));
+                             ((a.flags & B200Q_GATE_ROTATION) ? B200Q_FLAG_ROT : 0) |
+                             ((a.op_kind == B200Q_OP_DIAG && a.k == 1) ? (a.flags & B200Q_GATE_PHASE_MASK) : 0));
         op.mat_src = (uint32_t)a.mat;
         op.gate_id = (uint32_t)gi;
         op.k = (uint8_t)a.k;

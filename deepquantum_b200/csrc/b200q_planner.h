@@ -25,6 +25,9 @@ struct PlanOptions {
   int min_round_gates = 4;  // a later round with fewer executable gates ends the pass (1: off; measured +2 % on C2)
   int xc1_penalty = 0;    // slot choice: penalty (in quarter gates) per CNOT whose control becomes a register slot
                           // (measured neutral on C2: fewer register swaps, more rounds; off)
+  int free_phase = 0;     // plans run by the specialised kernels: a hinted diag(1, i^q) gate costs nothing when its
+                          // qubit is a register slot (renaming / frame bit) but a thread phase plus its application
+                          // otherwise, so such gates wait for a round that holds their qubit in registers
   int fuse = 1;           // 0: one gate per pass (the un-fused baseline used for A/B measurements)
 };
 

@@ -63,6 +63,8 @@ enum {
 #define B200Q_FLAG_RXLIKE 4u   /* MAT1: diagonal real, off-diagonal purely imaginary (Rx)    */
 #define B200Q_FLAG_HAD 8u      /* MAT1: x * [[1, 1], [1, -1]] with x real (Hadamard)          */
 #define B200Q_FLAG_ROT 16u     /* MAT1: unit-determinant rotation (with RXLIKE: Rx, with REAL: Ry) */
+#define B200Q_FLAG_PHASE_SHIFT 5  /* DIAG, k = 1: exactly diag(1, i^q), q in bits 5-6 (1 S, 2 Z, 3 S^dagger)     */
+#define B200Q_FLAG_PHASE_MASK (3u << B200Q_FLAG_PHASE_SHIFT)
 
 #define B200Q_LAYOUT_SRC_SOA 1u /* pass reads complex64 chunks as (re0,re1,im0,im1) */
 #define B200Q_LAYOUT_DST_SOA 2u /* pass writes them so */

@@ -335,8 +335,10 @@ class ShardedProgram:
                     sel = sel.select(k - 1 - j, bit)
                 vals = sel.reshape(-1)
                 if len(pt) == 0:
-                    # a pure per-rank phase: a diagonal gate on local bit 0 with both entries equal
-                    pt, vals = (0,), vals.repeat(2)
+                    # a pure per-rank phase: a diagonal gate with both entries equal on a local bit that is not one of
+                    # the gate's own (local) controls
+                    free = next(b for b in range(self.nl) if b not in ctrl)
+                    pt, vals = (free,), vals.repeat(2)
                 extra.append(torch.diag(vals).reshape(-1))
                 structs.append(L.make_gate(L.GATE_DIAG, pt, ctrl, off_extra, adj))
                 off_extra += extra[-1].numel()

@@ -317,6 +317,7 @@ class PauliY(_ConstSingle):
 
 class PauliZ(_ConstSingle):
     _kind = L.GATE_DIAG
+    _hint = L.GATE_PHASE_Z
     _default_name = 'PauliZ'
     _matrix_entries = [[1, 0], [0, -1]]
 
@@ -332,6 +333,7 @@ class Hadamard(_ConstSingle):
 
 class SGate(_ConstSingle):
     _kind = L.GATE_DIAG
+    _hint = L.GATE_PHASE_S
     _default_name = 'SGate'
     _matrix_entries = [[1, 0], [0, 1j]]
 
@@ -342,6 +344,7 @@ class SGate(_ConstSingle):
 
 class SDaggerGate(_ConstSingle):
     _kind = L.GATE_DIAG
+    _hint = L.GATE_PHASE_SDG
     _default_name = 'SDaggerGate'
     _matrix_entries = [[1, 0], [0, -1j]]
 

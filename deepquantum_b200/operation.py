@@ -133,7 +133,7 @@ class Lowering:
         else:
             block, idx = 'dyn', len(self.dynamic)
             self.dynamic.append(src)
-        hint = getattr(src, '_hint', 0) if (kind == L.GATE_MAT and len(wires) == 1) else 0
+        hint = getattr(src, '_hint', 0) if (kind in (L.GATE_MAT, L.GATE_DIAG) and len(wires) == 1) else 0
         self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size, hint))
         self.sources.append(src if kind != L.GATE_X else None)
 
@@ -365,7 +365,8 @@ class DenMatLowering(Lowering):
                         L.make_gate(L.GATE_MAT, [row], [col], off + 4, False, 0), flip, cx]
                 continue
             out.append(L.make_gate(kind, [t + n for t in targets], [c + n for c in ctrl], off, adj, hint))
-            out.append(L.make_gate(kind, targets, ctrl, 0 if kind == L.GATE_X else off + self.total, adj, hint))
+            out.append(L.make_gate(kind, targets, ctrl, 0 if kind == L.GATE_X else off + self.total, adj,
+                                   L.conj_hint(hint)))
         return out
 
     def build_matrices(self, cdtype: torch.dtype, device, batch: int | None = None) -> torch.Tensor:

@@ -51,6 +51,15 @@ extern "C" {
 #define B200Q_GATE_ROTATION 16 /* unit-determinant rotation [[c, x], [y, c]], c^2 - x y = 1: with RXLIKE Rx
                                   (gate.py:1443), with REAL Ry (gate.py:1538)                              */
 
+/* Optional hints for 1-target DIAGONAL gates (by gate CLASS): the matrix is exactly diag(1, i^q), q = 1 (S), 2 (Z),
+ * 3 (S^dagger), stored in flag bits 5-6.  The specialised pass kernels then apply the gate without arithmetic (a
+ * renaming of re / im registers, or a Pauli-frame bit) when its qubit is held in registers (gate.py:1143-1367). */
+#define B200Q_GATE_PHASE_SHIFT 5
+#define B200Q_GATE_PHASE_MASK (3 << B200Q_GATE_PHASE_SHIFT)
+#define B200Q_GATE_PHASE_S (1 << B200Q_GATE_PHASE_SHIFT)
+#define B200Q_GATE_PHASE_Z (2 << B200Q_GATE_PHASE_SHIFT)
+#define B200Q_GATE_PHASE_SDG (3 << B200Q_GATE_PHASE_SHIFT)
+
 #define B200Q_MAX_TARGETS 6
 
 typedef struct b200q_gate {

@@ -44,6 +44,8 @@ def lower_ops(ops, nqubit, dtype=np.complex128, hints=True):
                 hint = L.GATE_RXLIKE
                 if m[0, 0] == m[1, 1] and m[0, 1] == m[1, 0] and abs(np.linalg.det(m) - 1) < 1e-6:
                     hint |= L.GATE_ROTATION
+        if kind == L.GATE_DIAG and k == 1 and hints and m[0, 0] == 1 and m[0, 1] == 0 and m[1, 0] == 0:
+            hint = {1j: L.GATE_PHASE_S, -1: L.GATE_PHASE_Z, -1j: L.GATE_PHASE_SDG}.get(complex(m[1, 1]), 0)
         gates.append(L.make_gate(kind, targets, ctr, off, False, hint))
         mats.append(m.reshape(-1))
         off += m.size

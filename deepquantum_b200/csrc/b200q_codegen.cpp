@@ -61,6 +61,23 @@ DEV V vfma(V a, V b, V c) { V r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) 
 DEV V vmul(V a, V b) { V r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
 DEV V vadd(V a, V b) { V r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
 DEV V vsub(V a, V b) { V r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+// In-place updates with tied operands: the value stays in its register, so the (re, im) register quad an element was
+// loaded into is still a quad when the element is stored with one 128-bit access (no packing moves).
+DEV void vfa(V& x, V k, V y) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x.u) : "l"(k.u), "l"(y.u)); }   // x += k y
+DEV void vsc(V& x, V k) { asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x.u) : "l"(k.u)); }                        // x *= k
+DEV void vcm(V& re, V& im, V pr, V pi, V npi) {                                                            // (re, im) *= p
+  asm("{\n .reg .b64 t0, t1;\n mul.rn.f32x2 t0, %4, %1;\n mul.rn.f32x2 t1, %3, %0;\n"
+      " fma.rn.f32x2 %0, %2, %0, t0;\n fma.rn.f32x2 %1, %2, %1, t1;\n}"
+      : "+l"(re.u), "+l"(im.u) : "l"(pr.u), "l"(pi.u), "l"(npi.u));
+}
+DEV void vng(V& x) {
+  asm("{\n .reg .f32 a, b;\n mov.b64 {a, b}, %0;\n neg.f32 a, a;\n neg.f32 b, b;\n mov.b64 %0, {a, b};\n}" : "+l"(x.u));
+}
+// in-place butterfly (x, y) <- (x + y, x - y) with tied operands: the values stay in their registers, so the
+// (re, im) register quads of the elements survive until the 128-bit stores (no packing moves)
+DEV void vhad(V& x, V& y) {
+  asm("{\n .reg .b64 t;\n mov.b64 t, %0;\n add.rn.f32x2 %0, t, %1;\n sub.rn.f32x2 %1, t, %1;\n}" : "+l"(x.u), "+l"(y.u));
+}
 #else
 struct V { float x, y; };
 DEV V vmk(float x, float y) { V r; r.x = x; r.y = y; return r; }
@@ -70,6 +87,14 @@ DEV V vfma(V a, V b, V c) { return vmk(a.x * b.x + c.x, a.y * b.y + c.y); }
 DEV V vmul(V a, V b) { return vmk(a.x * b.x, a.y * b.y); }
 DEV V vadd(V a, V b) { return vmk(a.x + b.x, a.y + b.y); }
 DEV V vsub(V a, V b) { return vmk(a.x - b.x, a.y - b.y); }
+DEV void vhad(V& x, V& y) { const V t = x; x = vadd(t, y); y = vsub(t, y); }
+DEV void vfa(V& x, V k, V y) { x = vfma(k, y, x); }
+DEV void vsc(V& x, V k) { x = vmul(x, k); }
+DEV void vcm(V& re, V& im, V pr, V pi, V npi) {
+  const V t0 = vmul(npi, im), t1 = vmul(pi, re);
+  re = vfma(pr, re, t0); im = vfma(pr, im, t1);
+}
+DEV void vng(V& x) { x = vmk(-x.x, -x.y); }
 #endif
 DEV V vbc(float s) { return vmk(s, s); }
 DEV V vneg(V a) { return vmk(-vx(a), -vy(a)); }   // ptxas folds it into the operand modifier of the consumer
@@ -83,6 +108,14 @@ DEV V vadd(V a, V b) { return a + b; }
 DEV V vsub(V a, V b) { return a - b; }
 DEV V vbc(double s) { return s; }
 DEV V vneg(V a) { return -a; }
+DEV void vhad(V& x, V& y) { const V t = x; x = t + y; y = t - y; }
+DEV void vfa(V& x, V k, V y) { x = k * y + x; }
+DEV void vsc(V& x, V k) { x *= k; }
+DEV void vcm(V& re, V& im, V pr, V pi, V npi) {
+  const V t0 = npi * im, t1 = pi * re;
+  re = pr * re + t0; im = pr * im + t1;
+}
+DEV void vng(V& x) { x = -x; }
 struct alignas(16) chunk { double lo, hi; };
 #endif
 struct cplx { Real x, y; };
@@ -93,6 +126,9 @@ struct alignas(8) Remote {   // mirrors b200q_remote_t (b200q_program.h)
   int n_chunk_bits;
   int enabled;
 };
+#if defined(__CUDACC__)
+DEV void b200qj_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 DEV u32 b200qj_swz(u32 c) { return c ^ (((c >> 3) ^ (c >> 6) ^ (c >> 9) ^ (c >> 12)) & 7u); }
 // amplitude `loc` of the (SoA) shared-memory tile: pointer to its real part; imaginary part at +B200QJ_IMOFF
 #if B200QJ_F32
@@ -194,7 +230,7 @@ struct Gen {
   const b200q_pass_t& P;
   GenOptions opt;
   bool f32;
-  int VS, RB, CB, T, NT, item_bits;
+  int VS, RB, CB, T, NT, IPT, item_bits;
   std::ostringstream o;
   // per-op classification
   std::vector<int> cls, coef_off;
@@ -215,7 +251,8 @@ struct Gen {
     RB = B200Q_REG_CHUNK_BITS + VS;
     CB = pl.opt.chunk_bits;
     T = P.tile_bits;
-    NT = 1 << (CB - B200Q_REG_CHUNK_BITS);
+    IPT = std::max(1, opt.items_per_thread);
+    NT = (1 << (CB - B200Q_REG_CHUNK_BITS)) / IPT;
     item_bits = T - RB;
   }
 
@@ -377,15 +414,13 @@ struct Gen {
     if (is_lane(a)) {
       pf("    { const V s_ = vmk(%s, %s ? %s : %s);\n", RL(1).c_str(), FZ(a).c_str(), RL(-1).c_str(), RL(1).c_str());
       for (int e = 0; e < 16; ++e)
-        pf("      %s = vmul(%s, s_); %s = vmul(%s, s_);\n", W(vr[e]).c_str(), W(vr[e]).c_str(), W(vi[e]).c_str(),
-           W(vi[e]).c_str());
+        pf("      vsc(%s, s_); vsc(%s, s_);\n", W(vr[e]).c_str(), W(vi[e]).c_str());
     } else {
       const int b = cbit(a);
       pf("    { const V s_ = vbc(%s ? %s : %s);\n", FZ(a).c_str(), RL(-1).c_str(), RL(1).c_str());
       for (int e = 0; e < 16; ++e)
         if (e & b)
-          pf("      %s = vmul(%s, s_); %s = vmul(%s, s_);\n", W(vr[e]).c_str(), W(vr[e]).c_str(), W(vi[e]).c_str(),
-             W(vi[e]).c_str());
+          pf("      vsc(%s, s_); vsc(%s, s_);\n", W(vr[e]).c_str(), W(vi[e]).c_str());
     }
     pf("    }\n    %s = 0u;\n", FZ(a).c_str());
     mz[a] = false;
@@ -400,8 +435,7 @@ struct Gen {
   // element (re, im) *= (pr + i pi), coefficients given as V expressions (pr, pi, -pi)
   void cmul_elem(int e, const char* pr, const char* pi, const char* npi) {
     const std::string r = W(vr[e]), i = W(vi[e]);
-    pf("      { const V t0_ = vmul(%s, %s), t1_ = vmul(%s, %s); %s = vfma(%s, %s, t0_); %s = vfma(%s, %s, t1_); }\n", npi,
-       i.c_str(), pi, r.c_str(), r.c_str(), pr, r.c_str(), i.c_str(), pr, i.c_str());
+    pf("      vcm(%s, %s, %s, %s, %s);\n", r.c_str(), i.c_str(), pr, pi, npi);
   }
 
   // ---- ops ------------------------------------------------------------------------------------------------------
@@ -419,8 +453,7 @@ struct Gen {
         if (e & b) continue;
         for (int c = 0; c < 2; ++c) {
           const std::string x = W(c ? vi[e] : vr[e]), y = W(c ? vi[e | b] : vr[e | b]);
-          pf("    { const V t_ = %s; %s = vadd(t_, %s); %s = vsub(t_, %s); }\n", x.c_str(), x.c_str(), y.c_str(), y.c_str(),
-             y.c_str());
+          pf("    vhad(%s, %s);\n", x.c_str(), y.c_str());
         }
       }
     }
@@ -460,19 +493,13 @@ struct Gen {
         if (e & b) continue;
         const std::string ar = W(vr[e]), ai = W(vi[e]), br = W(vr[e | b]), bi = W(vi[e | b]);
         if (isx) {
-          pf("      %s = vfma(NU_, %s, %s); %s = vfma(U_, %s, %s);\n", ar.c_str(), bi.c_str(), ar.c_str(), ai.c_str(),
-             br.c_str(), ai.c_str());
-          pf("      %s = vfma(NV_, %s, %s); %s = vfma(V_, %s, %s);\n", br.c_str(), ai.c_str(), br.c_str(), bi.c_str(),
-             ar.c_str(), bi.c_str());
-          pf("      %s = vfma(NU_, %s, %s); %s = vfma(U_, %s, %s);\n", ar.c_str(), bi.c_str(), ar.c_str(), ai.c_str(),
-             br.c_str(), ai.c_str());
+          pf("      vfa(%s, NU_, %s); vfa(%s, U_, %s);\n", ar.c_str(), bi.c_str(), ai.c_str(), br.c_str());
+          pf("      vfa(%s, NV_, %s); vfa(%s, V_, %s);\n", br.c_str(), ai.c_str(), bi.c_str(), ar.c_str());
+          pf("      vfa(%s, NU_, %s); vfa(%s, U_, %s);\n", ar.c_str(), bi.c_str(), ai.c_str(), br.c_str());
         } else {
-          pf("      %s = vfma(U_, %s, %s); %s = vfma(U_, %s, %s);\n", ar.c_str(), br.c_str(), ar.c_str(), ai.c_str(),
-             bi.c_str(), ai.c_str());
-          pf("      %s = vfma(V_, %s, %s); %s = vfma(V_, %s, %s);\n", br.c_str(), ar.c_str(), br.c_str(), bi.c_str(),
-             ai.c_str(), bi.c_str());
-          pf("      %s = vfma(U_, %s, %s); %s = vfma(U_, %s, %s);\n", ar.c_str(), br.c_str(), ar.c_str(), ai.c_str(),
-             bi.c_str(), ai.c_str());
+          pf("      vfa(%s, U_, %s); vfa(%s, U_, %s);\n", ar.c_str(), br.c_str(), ai.c_str(), bi.c_str());
+          pf("      vfa(%s, V_, %s); vfa(%s, V_, %s);\n", br.c_str(), ar.c_str(), bi.c_str(), ai.c_str());
+          pf("      vfa(%s, U_, %s); vfa(%s, U_, %s);\n", ar.c_str(), br.c_str(), ai.c_str(), bi.c_str());
         }
       }
     }
@@ -680,7 +707,7 @@ struct Gen {
         for (int e = 0; e < 16; ++e) {
           if (!(e & b)) continue;
           std::swap(vr[e], vi[e]);
-          pf("    %s = vneg(%s);\n", W(vr[e]).c_str(), W(vr[e]).c_str());
+          pf("    vng(%s);\n", W(vr[e]).c_str());
         }
       }
       if (mx[a]) {
@@ -787,7 +814,11 @@ struct Gen {
       lbpos.push_back(Rd.nonreg_bit[k]);
       gpos.push_back(int(P.tile_phys[Rd.nonreg_bit[k]]) - VS);
     }
-    pf("  const u32 lb = %s;\n", deposit("(u32)tid", lbpos, false).c_str());
+    // IPT > 1: a thread walks IPT items of the round one after the other (fewer threads per tile: more CTAs, i.e.
+    // more tiles in different phases, fit the register file of an SM)
+    if (IPT > 1) pf("#if defined(__CUDACC__)\n#pragma unroll 1\n#endif\n  for (int it_ = 0; it_ < %d; ++it_) {\n  const int vt = tid + it_ * %d;\n", IPT, NT);
+    else pf("  {\n  const int vt = tid;\n");
+    pf("  const u32 lb = %s;\n", deposit("(u32)vt", lbpos, false).c_str());
     pf("  (void)lb; (void)cb; (void)coef; (void)rm; (void)dest_tab;\n");
     uint64_t gst[4];
     uint32_t sst[4];
@@ -799,7 +830,7 @@ struct Gen {
     auto goff = [&](int e) { uint64_t v = 0; for (int s = 0; s < 4; ++s) if (e >> s & 1) v += gst[s]; return v; };
     auto soff = [&](int e) { uint32_t v = 0; for (int s = 0; s < 4; ++s) if (e >> s & 1) v ^= sst[s]; return v; };
     if (Rd.src_global || Rd.dst_global)
-      pf("  const u64 gb = (cb >> %d) | (%s);\n", VS, deposit("(u32)tid", gpos, true).c_str());
+      pf("  const u64 gb = (cb >> %d) | (%s);\n", VS, deposit("(u32)vt", gpos, true).c_str());
     if (!Rd.src_global || !Rd.dst_global) pf("  const u32 sb = b200qj_swz(lb >> %d);\n", VS);
     pf("  V ");
     for (int v = 0; v < 32; ++v) pf("w%d%s", v, v == 31 ? ";\n" : ", ");
@@ -820,6 +851,11 @@ struct Gen {
     alias = -1;
     for (int oi = Rd.op_begin; oi < Rd.op_end; ++oi) {
       const b200q_op_t& op = P.ops[oi];
+      if (opt.debug_skip_ops == 1) continue;   // measurement only: the memory traffic of the pass without its arithmetic
+      if (opt.debug_skip_ops == 2 && cls[oi] == C_DIAG) continue;   // (compiler experiments: leave out one op class)
+      if (opt.debug_skip_ops == 3 && cls[oi] == C_HAD) continue;
+      if (opt.debug_skip_ops == 4 && cls[oi] == C_ROT) continue;
+      if (opt.debug_skip_ops == 5 && cls[oi] == C_X) continue;
       switch (cls[oi]) {
         case C_LSWAP:
           alias = alias < 0 ? int(op.slot) : -1;
@@ -847,8 +883,7 @@ struct Gen {
       } else {
         pf("    const V PR_ = vbc(rr);\n");
         for (int e = 0; e < 16; ++e)
-          pf("      %s = vmul(%s, PR_); %s = vmul(%s, PR_);\n", W(vr[e]).c_str(), W(vr[e]).c_str(), W(vi[e]).c_str(),
-             W(vi[e]).c_str());
+          pf("      vsc(%s, PR_); vsc(%s, PR_);\n", W(vr[e]).c_str(), W(vi[e]).c_str());
       }
       pf("  }\n");
     }
@@ -892,7 +927,7 @@ struct Gen {
         if (mx[s + VS]) pf("  sw ^= %s ? 0x%xu : 0u;\n", FX(s + VS).c_str(), sst[s]);
       for (int e = 0; e < 16; ++e) pf("  %s tile[sw ^ 0x%xu] = c_; }\n", packed(e, false).c_str(), soff(e));
     }
-    pf("}\n");
+    pf("  }\n}\n");
   }
 
   // dense k-target op applied in place in the shared-memory tile (one op per direct round)
@@ -981,8 +1016,28 @@ struct Gen {
     pf("  __syncthreads();\n");
     pf("  for (u64 w_ = blockIdx.x; w_ < n_work; w_ += gridDim.x) {\n");
     pf("    const u32 tile_id = (u32)(w_ & ((1ull << tile_shift) - 1ull));\n");
-    pf("    const u64 cb = %s;\n", cbexpr.c_str());
+    if (opt.debug_one_tile) {   // measurement only: the work items cycle over 512 tiles that stay in L2 (no DRAM traffic)
+      pf("    const u32 tile_id_dbg_ = tile_id; (void)tile_id_dbg_;\n");
+      pf("    const u64 cb = %s;\n", deposit("(tile_id & 511u)", ntp, true).c_str());
+    } else pf("    const u64 cb = %s;\n", cbexpr.c_str());
     pf("    chunk* g = state + ((u64)blockIdx.y + (w_ >> tile_shift)) * chunks_per_state;\n");
+    // L2 prefetch of the NEXT tile of this CTA: its DRAM reads are in flight while this tile is computed, so the
+    // first round's loads hit L2 and the memory system never idles during the compute phases (registers and shared
+    // memory are full: there is nowhere else to prefetch to)
+    bool lines_ok = opt.prefetch != 0;
+    for (int j = 0; j < 3 && lines_ok; ++j) lines_ok = int(P.tile_phys[j + VS]) == j + VS;
+    if (lines_ok) {
+      std::vector<int> lpos;   // chunk bit j + 3 of the tile -> physical chunk bit
+      for (int j = 3; j < CB; ++j) lpos.push_back(int(P.tile_phys[j + VS]) - VS);
+      const int nlines = 1 << (CB - 3);
+      pf("    {\n      const u64 wn_ = w_ + gridDim.x;\n      if (wn_ < n_work) {\n");
+      pf("        const u32 tile_id = (u32)(wn_ & ((1ull << tile_shift) - 1ull));\n");
+      pf("        const chunk* gn_ = state + ((u64)blockIdx.y + (wn_ >> tile_shift)) * chunks_per_state + ((%s) >> %d);\n",
+         cbexpr.c_str(), VS);
+      for (int l = 0; l < nlines; l += NT)
+        pf("        b200qj_prefetch_l2(gn_ + (%s));\n", deposit(sf("(u32)(tid + %d)", l), lpos, true).c_str());
+      pf("      }\n    }\n");
+    }
     for (size_t s = 0; s < steps.size(); ++s) {
       call_step(steps[s], "    ");
       if (s + 1 < steps.size() || steps.size() > 1) pf("    __syncthreads();\n");

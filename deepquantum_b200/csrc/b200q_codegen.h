@@ -17,6 +17,9 @@ namespace b200q {
 struct GenOptions {
   int remote = 0;      // 1: the write-back round is the fused exchange scatter (b200q_remote_t)
   int min_blocks = 2;  // __launch_bounds__ second argument
+  int debug_skip_ops = 0, debug_one_tile = 0;   // measurement switches (B200Q_JIT_DEBUG_*): never set in production
+  int items_per_thread = 1;   // 2: half the threads per tile, each walks two items per round
+  int prefetch = 0;    // L2 prefetch of the CTA's next tile while the current one is computed
 };
 
 // True if the generator covers this pass (full-size tile, un-padded state).  Small states keep the generic kernel:

@@ -277,9 +277,17 @@ int jit_prepare(Plan& plan, int threads, bool with_remote_last) {
         if (j >= (int)jobs.size()) break;
         GenOptions go;
         go.remote = jobs[j].remote ? 1 : 0;
+        go.min_blocks = plan.opt.chunk_bits >= 13 ? 1 : (plan.opt.chunk_bits == 12 ? 2 : 4);
+        if (const char* e = getenv("B200Q_JIT_IPT")) go.items_per_thread = atoi(e);
+        if (go.items_per_thread == 2 && plan.opt.chunk_bits == 12) go.min_blocks = 3;
+        if (go.items_per_thread == 2 && plan.opt.chunk_bits == 13) go.min_blocks = 1;
+        if (const char* e = getenv("B200Q_JIT_PREFETCH")) go.prefetch = atoi(e);
+        if (const char* e = getenv("B200Q_JIT_DEBUG_SKIP_OPS")) go.debug_skip_ops = atoi(e);
+        if (const char* e = getenv("B200Q_JIT_DEBUG_ONE_TILE")) go.debug_one_tile = atoi(e);
         size_t smem = 0;
         const std::string src = codegen_pass(plan, plan.passes[jobs[j].pass], go, &smem);
-        auto k = get_kernel(src, smem, 1 << (plan.opt.chunk_bits - B200Q_REG_CHUNK_BITS), go.min_blocks);
+        auto k = get_kernel(src, smem, (1 << (plan.opt.chunk_bits - B200Q_REG_CHUNK_BITS)) / std::max(1, go.items_per_thread),
+                            go.min_blocks);
         (jobs[j].remote ? J.remote : J.local)[jobs[j].pass] = k;
       }
     };
@@ -316,7 +324,7 @@ int jit_launch(Plan& plan, int i, void* state, const void* mats, int64_t batch, 
   const uint64_t ntiles = 1ull << tile_shift;
   static const int ctas_env = [] { const char* e = getenv("B200Q_JIT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   static const int oversub_env = [] { const char* e = getenv("B200Q_JIT_OVERSUB"); return e ? atoi(e) : 0; }();
-  const int oversub = oversub_env > 0 ? oversub_env : (P.n_ops <= 4 ? 16 : 4);
+  const int oversub = oversub_env > 0 ? oversub_env : (P.n_ops <= 4 ? 16 : 8);
   const uint64_t resident = uint64_t(sm_count_jit()) * (ctas_env > 0 ? ctas_env : k->min_blocks * oversub);
   const void* state_p = state;
   const void* mats_p = mats;

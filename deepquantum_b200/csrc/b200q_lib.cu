@@ -667,6 +667,12 @@ int b200q_plan_codegen(const b200q_plan_t* plan, int pass_index, int remote, cha
     return set_err(B200Q_EUNSUPPORTED, "pass not covered by the kernel generator (small or padded state)");
   GenOptions go;
   go.remote = remote ? 1 : 0;
+  go.min_blocks = p.opt.chunk_bits >= 13 ? 1 : (p.opt.chunk_bits == 12 ? 2 : 4);
+  if (const char* e = getenv("B200Q_JIT_PREFETCH")) go.prefetch = atoi(e);
+  if (const char* e = getenv("B200Q_JIT_IPT")) go.items_per_thread = atoi(e);
+  if (go.items_per_thread == 2 && p.opt.chunk_bits == 12) go.min_blocks = 3;
+  if (const char* e = getenv("B200Q_JIT_DEBUG_SKIP_OPS")) go.debug_skip_ops = atoi(e);
+  if (const char* e = getenv("B200Q_JIT_DEBUG_ONE_TILE")) go.debug_one_tile = atoi(e);
   size_t smem = 0;
   std::string stats;
   const std::string src = codegen_pass(p, p.passes[pass_index], go, &smem, &stats);

@@ -130,3 +130,72 @@ def test_generated_batch_of_states():
     ref = np.stack([so.run_circuit(ops, n, state=st[b]) for b in range(batch)])
     out, _ = gen_run(ops, n, np.complex128, state=st, chunk_bits=11, batch=batch)
     assert np.abs(out - ref).max() < 1e-12
+
+
+def _remote_struct(nl, cdtype, bufs, world, rank, perm):
+    """b200q_remote_t for one rank (same construction as b200q_plan_run_exchange, csrc/b200q_lib.cu)."""
+    import ctypes as C
+
+    class Remote(C.Structure):
+        _fields_ = [('peer', C.c_void_p * 8), ('base', C.c_uint64), ('perm', C.c_uint8 * 40), ('n_chunk_bits', C.c_int32),
+                    ('enabled', C.c_int32)]
+    vs = 1 if cdtype == np.complex64 else 0
+    g = world.bit_length() - 1
+    R = Remote()
+    for q in range(world):
+        R.peer[q] = bufs[q].ctypes.data
+    R.n_chunk_bits = nl - vs
+    for j in range(vs, nl):
+        R.perm[j - vs] = perm[j] - vs
+    base = 0
+    for k in range(g):
+        if (rank >> k) & 1:
+            pos = perm[nl + k] - vs
+            base |= (1 << pos) if pos < R.n_chunk_bits else (1 << (40 + pos - R.n_chunk_bits))
+    R.base = base
+    R.enabled = 1
+    return R
+
+
+@pytest.mark.parametrize('world', [2, 8])
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_generated_fused_exchange_bit_permutation(cdtype, world):
+    """The fused-exchange variant of the generated write-back round: every chunk goes to (rank, position) =
+    permutation of the distributed index bits; expected = segment on every shard, then a numpy bit permutation."""
+    import ctypes as C
+    from helpers import codegen_sources, compile_generated_host, lower_ops
+    nl = 13
+    g = world.bit_length() - 1
+    nt = nl + g
+    rng = np.random.default_rng(10 + world)
+    ops = []
+    for _ in range(40):
+        w = int(rng.integers(nl))
+        c = int((w + 1 + rng.integers(nl - 1)) % nl)
+        k = int(rng.integers(5))
+        ops.append([(gates_np.H, [w], []), (gates_np.rx(float(rng.uniform(0, 12))), [w], []), (gates_np.X, [w], [c]),
+                    (gates_np.S, [w], []), (gates_np.u3(*rng.uniform(0, 6, 3)), [w], [c])][k])
+    shards = [(rng.normal(size=2**nl) + 1j * rng.normal(size=2**nl)).astype(cdtype) for _ in range(world)]
+    vs = 1 if cdtype == np.complex64 else 0
+    perm = list(range(vs)) + [int(x) + vs for x in rng.permutation(nt - vs)]
+    local = np.concatenate([so.run_circuit(ops, nl, state=s.astype(np.complex128)) for s in shards])
+    old = np.arange(2**nt, dtype=np.int64)
+    new = np.zeros_like(old)
+    for j in range(nt):
+        new |= ((old >> j) & 1) << perm[j]
+    full = np.empty_like(local)
+    full[new] = local
+    arr, ng, mats = lower_ops(ops, nl, cdtype)
+    srcs = codegen_sources(nl, cdtype, arr, ng, chunk_bits=11, remote_last=True)
+    bufs = [np.full(2**nl, np.nan + 0j, dtype=cdtype) for _ in range(world)]
+    for r in range(world):
+        st = np.ascontiguousarray(shards[r].copy())
+        R = _remote_struct(nl, cdtype, bufs, world, r, perm)
+        for i, (src, info) in enumerate(srcs):
+            lib = compile_generated_host(src)
+            ts = info['n_bits'] - info['tile_bits']
+            lib.b200qj_emulate(st.ctypes.data, mats.ctypes.data, (2**nl) >> vs, 0, ts, 1 << ts, 1,
+                               C.addressof(R) if i == len(srcs) - 1 else None)
+    got = np.concatenate(bufs)
+    assert not np.isnan(got).any()
+    assert np.linalg.norm(got - full) / np.linalg.norm(full) < TOL[cdtype]

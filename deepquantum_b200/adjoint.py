@@ -57,11 +57,10 @@ class CircuitFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         y, mats = ctx.saved_tensors
         prog = ctx.prog
-        if ctx.batch != 1:
-            raise NotImplementedError('adjoint differentiation of batched circuits is not implemented yet')
         plan = prog.plan(y.dtype)
-        psi = y.clone()
-        lam = grad_y.contiguous().clone()
+        batch, mbs = ctx.batch, ctx.mbs
+        psi = y.clone().reshape(batch, -1)
+        lam = grad_y.contiguous().clone().reshape(batch, -1)
         # cotangent of the matrix buffer, always accumulated in double precision
         grad_m = torch.zeros(mats.shape, dtype=torch.complex128, device=mats.device)
         # only gates whose matrix is computed from parameters / data need a gradient
@@ -72,7 +71,13 @@ class CircuitFunction(torch.autograd.Function):
         if not ctx.needs_input_grad[1]:
             need = (C.c_uint8 * max(1, len(prog.low.records)))()
         lib = L.load()
-        L.check(lib.b200q_adjoint_run(plan._h, psi.data_ptr(), lam.data_ptr(), mats.data_ptr(), grad_m.data_ptr(),
-                                      need, engine._stream(psi)))
+        # the reverse sweep handles one state per call: a batch (2-D data, the reference's vmap, circuit.py:227-241,
+        # or a batch of initial states) is swept sample by sample; with per-sample matrices (mbs != 0) every sample
+        # has its own cotangent row, shared matrices accumulate into the same buffer
+        for b in range(batch):
+            m_b = mats[b] if mbs else mats
+            g_b = grad_m[b] if mbs else grad_m
+            L.check(lib.b200q_adjoint_run(plan._h, psi[b].data_ptr(), lam[b].data_ptr(), m_b.data_ptr(), g_b.data_ptr(),
+                                          need, engine._stream(psi)))
         gm = grad_m.to(mats.dtype) if ctx.needs_input_grad[1] else None
         return (lam.reshape(grad_y.shape) if ctx.x_needs_grad else None), gm, None, None, None

@@ -324,7 +324,15 @@ int jit_launch(Plan& plan, int i, void* state, const void* mats, int64_t batch, 
   const uint64_t ntiles = 1ull << tile_shift;
   static const int ctas_env = [] { const char* e = getenv("B200Q_JIT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   static const int oversub_env = [] { const char* e = getenv("B200Q_JIT_OVERSUB"); return e ? atoi(e) : 0; }();
-  const int oversub = oversub_env > 0 ? oversub_env : (P.n_ops <= 4 ? 16 : 8);
+  // Grid: a multiple of the resident CTA count, oversubscribed (8x: the hardware hands out CTAs as SMs free up --
+  // measured 42.9 ms against 44.8 ms with exactly the resident count on the 28-qubit circuit), but never so far
+  // that a CTA walks fewer than 16 tiles: its prologue (coefficient table from the matrix buffer) must stay a few
+  // per cent of its life (small shards of the sharded path: 2^27 amplitudes are 16 384 tiles)
+  int oversub = oversub_env > 0 ? oversub_env : (P.n_ops <= 4 ? 16 : 8);
+  if (oversub_env <= 0) {
+    const uint64_t base = uint64_t(sm_count_jit()) * k->min_blocks;
+    while (oversub > 1 && ntiles * uint64_t(batch) < base * uint64_t(oversub) * 16ull) oversub >>= 1;
+  }
   const uint64_t resident = uint64_t(sm_count_jit()) * (ctas_env > 0 ? ctas_env : k->min_blocks * oversub);
   const void* state_p = state;
   const void* mats_p = mats;

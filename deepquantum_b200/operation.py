@@ -256,6 +256,11 @@ class Lowering:
             p = self._gather_from_data(cls, lst)
             if p is None:
                 plist = [t for g in lst for t in g._param_list()]
+                nbs = {t.shape[0] for t in plist if t.ndim == 1}
+                if nbs:   # encoder gates of a batched forward next to plain gates of the same class: broadcast
+                    assert len(nbs) == 1, 'gates of one class were encoded with different batch sizes'
+                    nb = nbs.pop()
+                    plist = [t if t.ndim == 1 else t.reshape(1).expand(nb) for t in plist]
                 p = torch.stack(plist)                   # [N*npara] or [N*npara, batch]
             if p.ndim == 2:
                 batched = True

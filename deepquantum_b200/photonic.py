@@ -87,6 +87,16 @@ def displacement_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> t
     return torch.stack(cols, dim=-1)                     # [N, m, n]
 
 
+def _int_powers(base: torch.Tensor, d: int) -> torch.Tensor:
+    """[N] -> [N, d]: base^0 .. base^(d-1) by a cumulative product.  `base ** arange(d)` evaluates complex 0**0 as
+    NaN in PyTorch, which poisons the whole transform (and its gradient) for an exact zero entry: a beamsplitter at
+    theta = 0, a squeezer at r = 0."""
+    ones = torch.ones_like(base)[:, None]
+    if d == 1:
+        return ones
+    return torch.cumprod(torch.cat([ones, base[:, None].expand(-1, d - 1)], dim=1), dim=1)
+
+
 def squeezing2_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> torch.Tensor:
     """[N], [N] -> [N, d, d, d, d] (index m, n, p, q; photonic/gate.py:1258-1290, arXiv:2004.11002 Eq. 64-67).
     Only entries with m - n = p - q are non-zero.  With A_q[m, n] = T[m, n, q + m - n, q] the rank-4 recurrence reads
@@ -99,7 +109,7 @@ def squeezing2_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> tor
     t_m = (torch.exp(-1j * theta) * torch.tanh(r))[:, None]
     idx = torch.arange(d, device=r.device)
     # A_0[m, n] = T[m, n, m - n, 0], m >= n
-    diag = sech * t_p ** idx[None, :]                                    # [N, n]: T[n, n, 0, 0]
+    diag = sech * _int_powers(t_p[:, 0], d)                              # [N, n]: T[n, n, 0, 0]
     rows = []
     for m in range(d):
         if m == 0:
@@ -137,8 +147,8 @@ def bs_matrix_state(u: torch.Tensor, d: int) -> torch.Tensor:
     m, n, p = torch.meshgrid(idx, idx, idx, indexing='ij')
     # rank 3 (q = 0, p = m + n): sqrt(p! / (m! n!)) u00^m u10^n  -- the closed form of the reference's recurrence
     coef = torch.exp(0.5 * (lf[p] - lf[m] - lf[n])) * (p == m + n).to(rt)                 # [d, d, d]
-    pw0 = u[:, 0, 0][:, None] ** idx[None, :].to(rt)                                      # [N, d]
-    pw1 = u[:, 1, 0][:, None] ** idx[None, :].to(rt)
+    pw0 = _int_powers(u[:, 0, 0], d)                                                      # [N, d]
+    pw1 = _int_powers(u[:, 1, 0], d)
     t0 = coef[None] * pw0[:, :, None, None] * pw1[:, None, :, None]                       # [N, m, n, p]
     slices = [t0]
     sm = (sq[:, None, None]).expand(d, d, d)

@@ -410,3 +410,83 @@ def test_structured_and_general_op_codes(cdtype, structured):
     out, plan = _run_ops_gpu(ops, n, cdtype, state=psi, structured=structured)
     err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
     assert err < TOL[cdtype], (err, plan.stats)
+
+
+def test_batched_data_gradient_matches_per_sample_and_dense():
+    """Mini-batch training (2-D data, the reference's vmap path circuit.py:227-241): loss.backward() through the
+    reverse sweep for a batch = sum of the single-sample gradients, and = dense torch autograd on the host."""
+    import torch_port
+    n, nb = 6, 3
+    g = torch.Generator().manual_seed(9)
+
+    def build():
+        c = dq.QubitCircuit(n)
+        c.rxlayer(encode=True)
+        c.cnot_ring()
+        c.rylayer()
+        c.rzz([0, 3])
+        c.rxlayer()
+        for q in range(n):
+            c.observable([q], 'z')
+        return c
+
+    cir = build()
+    cir.to('cuda', torch.double)
+    data = (torch.rand(nb, n, generator=g, dtype=torch.float64) * 3).cuda()
+    wts = torch.rand(nb, n, generator=g, dtype=torch.float64).cuda()
+    cir(data)
+    loss = (cir.expectation().reshape(nb, n) * wts).sum()
+    loss.backward()
+    got = [p.grad.detach().clone() for p in cir.parameters()]
+    # per sample
+    acc = [torch.zeros_like(x) for x in got]
+    tot = 0.0
+    for b in range(nb):
+        cir.zero_grad()
+        cir(data[b])
+        l_b = (cir.expectation().reshape(n) * wts[b]).sum()
+        l_b.backward()
+        tot += float(l_b)
+        for a, p in zip(acc, cir.parameters()):
+            a += p.grad
+    assert abs(tot - float(loss)) < 1e-10
+    for a, b_ in zip(acc, got):
+        assert (a - b_).abs().max() < 1e-9, (a, b_)
+    # dense autograd on the host for sample 0 .. nb-1 (gate by gate like the reference)
+    params = [p.detach().cpu().clone().requires_grad_(True) for p in cir.parameters()]
+
+    def rot(kind, t):
+        c, s = torch.cos(t / 2).to(torch.complex128), torch.sin(t / 2).to(torch.complex128)
+        if kind == 'rx':
+            return torch.stack([c, -1j * s, -1j * s, c]).reshape(2, 2)
+        return torch.stack([c, -s, s, c]).reshape(2, 2)
+
+    xm = torch.tensor(gates_np.X, dtype=torch.complex128)
+    assert len(params) == 2 * n + 1   # one 0-d theta per gate: n Ry, one Rzz, n Rx
+    ry_p, rzz_p, rx_p = params[:n], params[n:n + 1], params[n + 1:]
+    loss_ref = 0
+    idx = torch.arange(2**n)
+    for b in range(nb):
+        st = torch.zeros(2**n, dtype=torch.complex128)
+        st[0] = 1
+        x = st.reshape([1] + [2] * n)
+        d = data[b].cpu()
+        for q in range(n):
+            x = torch_port.evolve_state(x, rot('rx', d[q]), n, [q])
+        for q in range(n):
+            x = torch_port.evolve_state_controlled(x, xm, n, [(q + 1) % n], [q])
+        for q in range(n):
+            x = torch_port.evolve_state(x, rot('ry', ry_p[q]), n, [q])
+        e = torch.exp(-0.5j * rzz_p[0].to(torch.complex128))
+        zz = torch.diag(torch.stack([e, e.conj(), e.conj(), e]))
+        x = torch_port.evolve_state(x, zz, n, [0, 3])
+        for q in range(n):
+            x = torch_port.evolve_state(x, rot('rx', rx_p[q]), n, [q])
+        prob = (x.reshape(-1).conj() * x.reshape(-1)).real
+        for q in range(n):
+            sign = 1 - 2 * ((idx >> (n - 1 - q)) & 1).to(torch.float64)
+            loss_ref = loss_ref + wts[b, q].cpu() * (prob * sign).sum()
+    loss_ref.backward()
+    assert abs(float(loss_ref) - float(loss)) < 1e-9
+    for p_ref, g_gpu in zip(params, got):
+        assert (p_ref.grad - g_gpu.cpu().reshape(p_ref.shape)).abs().max() < 1e-8

@@ -194,3 +194,63 @@ def test_cx_diag_cx_peephole():
     m = prog.low.build_matrices(torch.complex128, 'cpu')
     m[prog.low.n_primary:].abs().sum().backward()
     assert rz.theta.grad is not None
+
+
+def test_encoder_and_plain_gates_of_one_class_with_batched_data():
+    """`rylayer(encode=True); rylayer()` with 2-D data stacks [batch] and 0-d parameters of one class."""
+    n, nb = 3, 4
+    cir = dq.QubitCircuit(n)
+    cir.rylayer(encode=True)
+    cir.rylayer()
+    cir.cnot(0, 1)
+    cir.to(torch.double)
+    data = torch.rand(nb, n, dtype=torch.double)
+    prog = cir._get_program()
+    cir._encode_batched(data)
+    try:
+        mats = prog.low.build_matrices(torch.complex128, 'cpu')
+    finally:
+        for op in cir.encoders:
+            for g in op.gates:
+                g._batched = None
+    assert mats.ndim == 2 and mats.shape[0] == nb
+    for b in range(nb):
+        cir.encode(data[b])
+        one = prog.low.build_matrices(torch.complex128, 'cpu')
+        assert torch.allclose(mats[b], one, atol=1e-14)
+    out, _ = emu_run_program_batched(cir, prog, n, data)
+    for b in range(nb):
+        cir.encode(data[b])
+        ref, _ = emu_run_program(prog, n, np.complex128)
+        assert np.abs(out[b] - ref[0]).max() < 1e-12
+
+
+def emu_run_program_batched(cir, prog, n, data):
+    cir._encode_batched(data)
+    try:
+        return emu_run_program(prog, n, np.complex128, batch=data.shape[0])
+    finally:
+        for op in cir.encoders:
+            for g in op.gates:
+                g._batched = None
+
+
+def test_fock_transforms_with_exact_zero_entries():
+    """complex 0**0 is NaN in PyTorch: a beamsplitter at theta = 0 (identity) and a two-mode squeezer at
+    r = 0 must give finite transforms and gradients."""
+    from deepquantum_b200 import photonic as ph
+    d = 4
+    theta = torch.zeros(1, dtype=torch.double, requires_grad=True)
+    phi = torch.full((1,), 0.3, dtype=torch.double)
+    t = ph.bs_matrix_state(ph.BeamSplitter.mixing_matrix(theta, phi), d)
+    assert torch.isfinite(t.real).all() and torch.isfinite(t.imag).all()
+    eye = torch.eye(d * d, dtype=t.dtype).reshape(d, d, d, d)
+    assert torch.allclose(t[0], eye, atol=1e-12)
+    t.abs().sum().backward()
+    assert torch.isfinite(theta.grad).all()
+    r = torch.zeros(1, dtype=torch.double, requires_grad=True)
+    s2 = ph.squeezing2_matrix_state(r, torch.full((1,), 0.7, dtype=torch.double), d)
+    assert torch.isfinite(s2.real).all() and torch.isfinite(s2.imag).all()
+    assert torch.allclose(s2[0], eye.to(s2.dtype), atol=1e-12)
+    s2.abs().sum().backward()
+    assert torch.isfinite(r.grad).all()

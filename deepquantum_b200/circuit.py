@@ -683,6 +683,26 @@ class QubitCircuit(Operation):
         raise NotImplementedError('Reset is non-unitary and outside the accelerated path')
 
 
+class _ShardedExpectation(torch.autograd.Function):
+    """Exact expectation values of a sharded final state, differentiable w.r.t. the matrix buffer by the adjoint
+    (un-computing) method: the counterpart of the reference's `AdjointExpectation` (adjoint.py:19-83), which is
+    wired to `DistributedQubitCircuit.expectation` only (circuit.py:1734-1738)."""
+
+    @staticmethod
+    def forward(ctx, mats, cir):
+        ctx.cir = cir
+        ctx.save_for_backward(mats)
+        with torch.no_grad():
+            return cir._expectation_values()
+
+    @staticmethod
+    def backward(ctx, grad):
+        (mats,) = ctx.saved_tensors
+        with torch.no_grad():
+            gm = ctx.cir._expectation_backward(mats, grad)
+        return gm.to(mats.dtype), None
+
+
 class DistributedQubitCircuit(QubitCircuit):
     """Circuit on a statevector sharded over the ranks of the default process group (reference
     circuit.py:1625-1770).  `forward` is in place and `no_grad`, like the reference; it returns the
@@ -731,51 +751,140 @@ class DistributedQubitCircuit(QubitCircuit):
         self.state = st
         return st
 
-    def expectation(self, shots: int | None = None) -> torch.Tensor:
-        """Z-string observables: local fused reduction + one all-reduce (reference distributed.py:288-294)."""
-        import torch.distributed as dist
-        assert len(self.observables) > 0, 'There is no observable'
+    # ---- expectation values of the sharded state (reference circuit.py:1706-1758) -----------------------------
+    def _clone_state(self, st):
+        """A sharded state with its own shard + receive buffer holding a copy of `st.amps`."""
+        from .distributed import DistributedQubitState
+        new = DistributedQubitState(self.nqubit)
+        new.register_buffer('amps', st.amps.detach().clone())
+        new.register_buffer('buffer', torch.zeros_like(st.amps))
+        return new
+
+    def _basis_circuits(self, ob):
+        """(rotation to the Z basis, its inverse) of an observable with X / Y factors, None for a Z string
+        (reference circuit.py:1741-1749 builds the same circuit for the shot-based estimate)."""
+        if set(ob.basis) == {'z'}:
+            return None
+        cache = self.__dict__.setdefault('_basis_cache', {})
+        key = (tuple(w[0] for w in ob.wires), ob.basis)
         st = self.state
-        n, nl = self.nqubit, st.log_num_amps_per_node
-        masks = []
-        for ob in self.observables:
-            assert set(ob.basis) == {'z'}, 'only Z-string observables are implemented for the sharded state'
-            m = 0
-            for w in ob.wires:
-                m |= 1 << (n - 1 - w[0])
-            masks.append(m)
-        mt = torch.tensor(masks, dtype=torch.int64, device=st.amps.device)
-        vals = engine.expectation_z(st.amps, nl, mt, 1, index_offset=st.rank << nl).reshape(-1)
+        if key not in cache or cache[key][2] != (st.amps.dtype, str(st.amps.device)):
+            # R^dagger Z R = X for R = Ry(-pi/2), = Y for R = Rx(pi/2): rotations evaluated in the state's precision (the
+            # reference's H is a float32-rounded constant, unitary to 6e-8 only, gate.py:1069)
+            fwd, inv = DistributedQubitCircuit(self.nqubit), DistributedQubitCircuit(self.nqubit)
+            rdtype = torch.empty(0, dtype=st.amps.dtype).real.dtype
+            half = torch.tensor(torch.pi / 2, dtype=rdtype)
+            for w, b in zip(ob.wires, ob.basis):
+                if b == 'x':
+                    fwd.ry(w[0], -half)
+                    inv.ry(w[0], half)
+                elif b == 'y':
+                    fwd.rx(w[0], half)
+                    inv.rx(w[0], -half)
+            for c in (fwd, inv):
+                c.to(st.amps.device, rdtype)
+                c._executor = self._executor
+            cache[key] = (fwd, inv, (st.amps.dtype, str(st.amps.device)))
+        return cache[key][:2]
+
+    def _ob_mask(self, ob) -> int:
+        m = 0
+        for w in ob.wires:
+            m |= 1 << (self.nqubit - 1 - w[0])
+        return m
+
+    def _expectation_values(self) -> torch.Tensor:
+        """<psi| O_k |psi> for every observable: Z strings in ONE fused reduction over the shard, observables with
+        X / Y factors on a rotated copy; one all-reduce (reference distributed.py:288-294)."""
+        import torch.distributed as dist
+        st, ex = self.state, self._executor
+        nl = st.log_num_amps_per_node
+        dev = st.amps.device
+        vals = torch.zeros(len(self.observables), dtype=torch.float64, device=dev)
+        zidx = [k for k, ob in enumerate(self.observables) if set(ob.basis) == {'z'}]
+        if zidx:
+            mt = torch.tensor([self._ob_mask(self.observables[k]) for k in zidx], dtype=torch.int64, device=dev)
+            vals[zidx] = ex.expectation_z(st.amps, nl, mt, st.rank << nl)
+        for k, ob in enumerate(self.observables):
+            if k in zidx:
+                continue
+            fwd, _ = self._basis_circuits(ob)
+            tmp = fwd(state=self._clone_state(st))
+            mt = torch.tensor([self._ob_mask(ob)], dtype=torch.int64, device=dev)
+            vals[k] = ex.expectation_z(tmp.amps, nl, mt, st.rank << nl)[0]
         if dist.is_initialized() and st.world_size > 1:
             dist.all_reduce(vals)
         return vals.to(st.amps.real.dtype)
 
+    def _expectation_backward(self, mats: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+        """Cotangent of the matrix buffer for L = sum_k grad_k <O_k>: seed lambda = 2 sum_k grad_k O_k psi, then the
+        reverse sweep over the sharded schedule (reference adjoint.py:47-83; exchanges replayed backwards) and one
+        all-reduce of the per-rank shares."""
+        import torch.distributed as dist
+        st, ex = self.state, self._executor
+        nl = st.log_num_amps_per_node
+        dev = st.amps.device
+        g = grad.reshape(-1).to(torch.float64)
+        lam = self._clone_state(st)
+        lam.amps.zero_()
+        zidx = [k for k, ob in enumerate(self.observables) if set(ob.basis) == {'z'}]
+        if zidx:
+            mt = torch.tensor([self._ob_mask(self.observables[k]) for k in zidx], dtype=torch.int64, device=dev)
+            lam.amps += ex.apply_z_weights(st.amps, nl, mt, 2.0 * g[zidx], st.rank << nl).reshape(-1)
+        for k, ob in enumerate(self.observables):
+            if k in zidx:
+                continue
+            fwd, inv = self._basis_circuits(ob)
+            tmp = fwd(state=self._clone_state(st))
+            mt = torch.tensor([self._ob_mask(ob)], dtype=torch.int64, device=dev)
+            tmp.amps.copy_(ex.apply_z_weights(tmp.amps, nl, mt, 2.0 * g[k:k + 1], st.rank << nl).reshape(-1))
+            tmp = inv(state=tmp)
+            lam.amps += tmp.amps
+        psi = self._clone_state(st)
+        if self._sharded.mode == 'perm':
+            assert psi.enable_peer_exchange() and lam.enable_peer_exchange()
+        gm = self._sharded.run_adjoint(psi, lam, mats.detach(), ex)
+        if dist.is_initialized() and st.world_size > 1:
+            flat = torch.view_as_real(gm.contiguous())
+            dist.all_reduce(flat)
+            gm = torch.view_as_complex(flat)
+        return gm
+
+    def expectation(self, shots: int | None = None) -> torch.Tensor:
+        """Expectation values of the observables on the sharded final state (reference circuit.py:1706-1758).
+        `shots=None`: exact and differentiable w.r.t. the gate parameters / encoded data by the adjoint method;
+        otherwise a shot-based estimate (rank 0 returns the values, the other ranks empty tensors, like the
+        reference)."""
+        assert len(self.observables) > 0, 'There is no observable'
+        assert self.state is not None, 'There is no final state'
+        if shots is not None:
+            return self._sampled_expectation(shots)
+        prog = self._get_program()
+        st = self.state
+        with torch.enable_grad():
+            mats = prog.low.build_matrices(st.amps.dtype, st.amps.device)
+        if torch.is_grad_enabled() and mats.requires_grad:
+            return _ShardedExpectation.apply(mats, self)
+        with torch.no_grad():
+            return self._expectation_values()
+
     def _sampled_expectation(self, shots: int) -> torch.Tensor:
-        """Shot-based estimate (reference circuit.py:400-426): rotate the observable's X / Y factors to Z, sample
-        its wires on the device, average the parities of the outcomes."""
-        from .qmath import measure as _measure, sample2expval
+        """Shot-based estimate (reference circuit.py:1737-1756): rotate a copy to the observable's eigenbasis, sample
+        its wires with `measure_dist`, average the parities on rank 0."""
+        from .distributed import measure_dist
+        from .qmath import sample2expval
         self.shots = shots
         st = self.state
-        rdtype, device = st.real.dtype, st.device
+        rdtype, dev = st.amps.real.dtype, st.amps.device
         out = []
         for ob in self.observables:
-            basis_cir = QubitCircuit(self.nqubit, den_mat=self.den_mat)
-            for w, b in zip(ob.wires, ob.basis):
-                if b == 'y':
-                    basis_cir.sdg(w[0])
-                if b in ('x', 'y'):
-                    basis_cir.h(w[0])
-            basis_cir.to(device, rdtype)
-            with torch.no_grad():
-                rotated = basis_cir(state=st)
-            samples = _measure(rotated, shots=shots, wires=sum(ob.wires, []), den_mat=self.den_mat)
-            if isinstance(samples, list):
-                expval = torch.cat([sample2expval(s).to(device, rdtype) for s in samples])
+            circs = self._basis_circuits(ob)
+            tmp = st if circs is None else circs[0](state=self._clone_state(st))
+            samples = measure_dist(tmp, shots=shots, wires=[w[0] for w in ob.wires], executor=self._executor)
+            if st.rank == 0:
+                out.append(sample2expval(samples).to(dev, rdtype).squeeze(0))
             else:
-                expval = sample2expval(samples).to(device, rdtype)
-                if st.ndim == 2:
-                    expval = expval.squeeze(0)
-            out.append(expval)
+                out.append(torch.tensor([], dtype=rdtype, device=dev))
         return torch.stack(out, dim=-1)
 
     def measure(self, shots: int | None = None, with_prob: bool = False, wires=None, block_size: int = 2**24):

@@ -118,6 +118,20 @@ class CudaExecutor:
         `perm`: bit permutation of the distributed index, None = block transpose."""
         plan.run_exchange(amps, mats, peer_ptrs, rank, perm)
 
+    # local pieces of the (differentiable) expectation: fused Z-string reduction, its cotangent, the reverse sweep
+    def expectation_z(self, amps, nlocal, masks, index_offset):
+        return engine.expectation_z(amps, nlocal, masks, 1, index_offset=index_offset).reshape(-1)
+
+    def apply_z_weights(self, amps, nlocal, masks, weights, index_offset):
+        return engine.apply_z_weights(amps, nlocal, masks, weights.reshape(1, -1), 1, index_offset=index_offset)
+
+    def run_plan_adjoint(self, plan, psi, lam, mats, grad, need):
+        """psi <- U^dagger psi, lam <- U^dagger lam, grad += cotangent of the matrices (b200q_adjoint_run)."""
+        import ctypes as C
+        arr = (C.c_uint8 * max(1, len(need)))(*need)
+        L.check(L.load().b200q_adjoint_run(plan._h, psi.data_ptr(), lam.data_ptr(), mats.data_ptr(), grad.data_ptr(), arr,
+                                           engine._stream(psi)))
+
     # local pieces of measure_dist (csrc/b200q_sample.cu)
     def block_mass(self, amps, nlocal):
         return engine.block_mass(amps, nlocal, 1)[0]
@@ -314,18 +328,26 @@ class ShardedProgram:
             pt = [p for p in pt if p < nl]
         return (i, kind, tuple(pt), tuple(local_ctrl), adj, active, fix, hint)
 
-    def _segment_structs(self, step, mats):
-        """GateStruct list (+ extra derived matrices) of one local segment for this rank."""
+    def _segment_structs(self, step, mats, needs=None):
+        """GateStruct list (+ extra derived matrices) of one local segment for this rank.  `needs`: optional list that
+        receives, per struct, whether its matrix is computed from parameters / data (the reverse sweep accumulates
+        cotangents only for those)."""
         structs, extra, off_extra = [], [], mats.numel()
         for item in step[1]:
             if item[0] == 'pswap':       # physical SWAP of two local bits = three CX relabellings
                 a, b = item[1], item[2]
                 structs += [L.make_gate(L.GATE_X, [b], [a]), L.make_gate(L.GATE_X, [a], [b]),
                             L.make_gate(L.GATE_X, [b], [a])]
+                if needs is not None:
+                    needs += [0, 0, 0]
                 continue
             (i, kind, pt, ctrl, adj, active, fix, hint) = item
             if not active:
                 continue
+            if needs is not None:
+                rec = self.low.records[i]
+                block = self.low.derived[rec[5]][4] if rec[4] == 'derived' else rec[4]
+                needs.append(0 if block in ('none', 'const') else 1)
             off = self.low.offsets[i]
             if fix is not None:
                 k = len(self.low.records[i][1])
@@ -335,10 +357,14 @@ class ShardedProgram:
                     sel = sel.select(k - 1 - j, bit)
                 vals = sel.reshape(-1)
                 if len(pt) == 0:
-                    # a pure per-rank phase: a diagonal gate with both entries equal on a local bit that is not one of
-                    # the gate's own (local) controls
-                    free = next(b for b in range(self.nl) if b not in ctrl)
-                    pt, vals = (free,), vals.repeat(2)
+                    # a pure per-rank phase v (all selectors are rank bits): without local controls a diagonal gate
+                    # diag(v, v) on local bit 0; with local controls the first control becomes the target of
+                    # diag(1, v) and the others stay controls (a placeholder target could collide with a control)
+                    if ctrl:
+                        pt, ctrl = (ctrl[0],), tuple(ctrl[1:])
+                        vals = torch.cat([torch.ones_like(vals), vals])
+                    else:
+                        pt, vals = (0,), vals.repeat(2)
                 extra.append(torch.diag(vals).reshape(-1))
                 structs.append(L.make_gate(L.GATE_DIAG, pt, ctrl, off_extra, adj))
                 off_extra += extra[-1].numel()
@@ -418,6 +444,58 @@ class ShardedProgram:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
                 marks.append(('swap' if what == 'swap' else 'seg', ev0, ev1))
+
+    def run_adjoint(self, psi: DistributedQubitState, lam: DistributedQubitState, mats: torch.Tensor, executor) -> torch.Tensor:
+        """Reverse sweep over the sharded schedule (reference adjoint.py:47-83 generalised to the full matrix
+        cotangent): `psi` enters as the final state and leaves as the initial one, `lam` enters as the cotangent of the
+        final state.  Exchanges are bit permutations of the distributed index: they are replayed backwards on both
+        states; every local segment runs the reverse-sweep kernel on the two shards.  Returns this rank's share of
+        the cotangent of `mats` (complex, like `mats`); the caller all-reduces it."""
+        import torch.distributed as dist
+        nl = self.nl
+        fuse_exchange = (self.mode == 'perm' and hasattr(executor, 'run_plan_exchange') and self.world > 1)
+        leaf = mats.detach().clone().requires_grad_(True)
+        total = torch.zeros_like(leaf)
+        for si in range(len(self.steps) - 1, -1, -1):
+            step = self.steps[si]
+            if step[0] == 'swap':            # block transpose: its own inverse
+                for st in (psi, lam):
+                    block_transpose(st.amps, st.buffer)
+                    st.amps, st.buffer = st.buffer, st.amps
+                continue
+            if step[0] == 'xperm':
+                assert fuse_exchange, "the 'perm' schedule needs the peer-mapped exchange"
+                pm = step[1]
+                inv = [0] * len(pm)
+                for j, pj in enumerate(pm):
+                    inv[pj] = j
+                key = ('identity', psi.amps.dtype)
+                if key not in self.plans:
+                    self.plans[key] = executor.make_plan(nl, psi.amps.dtype, [L.make_gate(L.GATE_DIAG, (1,), (), 0)],
+                                                         exchange=True)
+                eye = torch.eye(2, dtype=psi.amps.dtype, device=psi.amps.device).reshape(-1)
+                for st in (psi, lam):
+                    executor.run_plan_exchange(self.plans[key], st.amps, eye, st.peer_buffer_ptrs(), self.rank, inv)
+                    dist.all_reduce(self._sync_token(st.amps.device))
+                    self.commit_exchange(st)
+                continue
+            needs = []
+            with torch.enable_grad():
+                structs, extra = self._segment_structs(step, leaf, needs)
+                if not structs:
+                    continue
+                m = torch.cat([leaf] + extra) if extra else leaf
+            key = (si, psi.amps.dtype, 'adjoint')
+            if key not in self.plans:
+                self.plans[key] = executor.make_plan(nl, psi.amps.dtype, structs)
+            grad = torch.zeros(m.numel(), dtype=torch.complex128, device=m.device)
+            executor.run_plan_adjoint(self.plans[key], psi.amps, lam.amps, m.detach().contiguous(), grad, needs)
+            if extra:        # chain the derived per-rank matrices (global diagonal selectors) back to the buffer
+                (g_leaf,) = torch.autograd.grad(m, leaf, grad.to(m.dtype))
+                total += g_leaf
+            else:
+                total += grad.to(m.dtype)
+        return total
 
     def _sync_token(self, device):
         tok = self.__dict__.get('_tok')

@@ -476,8 +476,69 @@ def denmat():
     print('denmat.npz:', len(out), 'arrays')
 
 
+def dist_adjoint_build(cir):
+    """The circuit of the reference's own test of the differentiable sharded expectation
+    (tests/test_circuit.py:87-139): every encoded gate family, controls, Toffoli / Fredkin / swap, X / Y observables."""
+    cir.rxlayer(encode=True)
+    cir.rylayer(encode=True)
+    cir.rzlayer(encode=True)
+    cir.u3layer(encode=True)
+    cir.hlayer()
+    cir.cnot_ring()
+    cir.toffoli(0, 1, 2)
+    cir.fredkin(2, 1, 0)
+    cir.swap([2, 3])
+    cir.rx(0, controls=[1, 2, 3], encode=True)
+    cir.ry(1, controls=[0, 2, 3], encode=True)
+    cir.rz(2, controls=[0, 1, 3], encode=True)
+    cir.rxx([0, 1], controls=[2, 3], encode=True)
+    cir.ryy([1, 2], controls=[0, 3], encode=True)
+    cir.rzz([2, 3], controls=[0, 1], encode=True)
+    cir.rxy([3, 0], controls=[1, 2], encode=True)
+    cir.observable(0)
+    cir.observable(1, 'x')
+    cir.observable([2, 3], 'xy')
+    return cir
+
+
+def dist_adjoint():
+    """Expectation values and d(sum)/d(data) of the dense reference circuit (plain autograd, the `cir2` half of
+    tests/test_circuit.py:87-139) in float64, plus a 6-qubit variant whose gates reach the rank bits of 2 and 4 ranks."""
+    out = {}
+    for name, n, ndata in (('ref_test_n4', 4, 10), ('ref_test_n6', 6, 10)):
+        data = torch.arange(ndata, dtype=torch.float64, requires_grad=True)
+        cir = dist_adjoint_build(dq.QubitCircuit(n, reupload=True))
+        cir.to(torch.double)
+        cir(data=data)
+        exp = cir.expectation()
+        exp.sum().backward()
+        out[f'{name}/data'] = data.detach().numpy()
+        out[f'{name}/expectation'] = exp.detach().reshape(-1).numpy()
+        out[f'{name}/grad'] = data.grad.numpy()
+        print('dist_adjoint', name, exp.detach().reshape(-1).tolist())
+    np.savez_compressed(os.path.join(OUT, 'dist_adjoint.npz'), **out)
+
+
+def unitary():
+    """`QubitCircuit.get_unitary()` (reference circuit.py:467) of the all-gate-families circuit at 5 qubits and of a
+    random Clifford+RX circuit at 6 qubits."""
+    out = {}
+    for name, n, spec in (('all_gates_n5', 5, all_gates_spec(5)), ('random_n6_d3', 6, wl.random_clifford_rx_spec(6, 3))):
+        cir = dq.QubitCircuit(n)
+        wl.apply_spec(cir, spec, torch.complex128)
+        cir.to(torch.double)
+        out[f'{name}/spec'] = np.array(json.dumps({'n': n, 'spec': spec}))
+        out[f'{name}/unitary'] = cir.get_unitary().detach().numpy()
+    np.savez_compressed(os.path.join(OUT, 'unitary.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3', 'fock2']
+    which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3', 'fock2',
+                             'dist_adjoint', 'unitary']
+    if 'dist_adjoint' in which:
+        dist_adjoint()
+    if 'unitary' in which:
+        unitary()
     if 'denmat' in which:
         denmat()
     if 'hamiltonian' in which:

@@ -85,6 +85,68 @@ def main():
             err = float(np.linalg.norm(full - ref) / np.linalg.norm(ref))
             print(f'n={n} depth={depth} world={world} {rdtype}: rel-L2 vs oracle {err:.3e} schedule {cir._sharded.stats()}')
             ok = ok and err < tol
+    # (3) differentiable expectation of the sharded circuit (reference circuit.py:1706-1738, adjoint.py:19-83):
+    #     the reference's own test circuit against its dense-autograd fixture, and a 21-qubit circuit whose
+    #     exchanges run over the NVLink peer mappings against the single-GPU reverse sweep
+    from test_distributed_gloo import _free_port  # noqa: F401  (module import keeps sys.path consistent)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'dist_adjoint.npz'))
+    for n in (4, 6):
+        if 2**n < 4 * world * world:
+            continue
+        data = torch.tensor(g[f'ref_test_n{n}/data'], dtype=torch.float64, device=dev, requires_grad=True)
+        cir = dq.DistributedQubitCircuit(n, reupload=True)
+        cir.rxlayer(encode=True); cir.rylayer(encode=True); cir.rzlayer(encode=True); cir.u3layer(encode=True)
+        cir.hlayer(); cir.cnot_ring(); cir.toffoli(0, 1, 2); cir.fredkin(2, 1, 0); cir.swap([2, 3])
+        cir.rx(0, controls=[1, 2, 3], encode=True); cir.ry(1, controls=[0, 2, 3], encode=True)
+        cir.rz(2, controls=[0, 1, 3], encode=True); cir.rxx([0, 1], controls=[2, 3], encode=True)
+        cir.ryy([1, 2], controls=[0, 3], encode=True); cir.rzz([2, 3], controls=[0, 1], encode=True)
+        cir.rxy([3, 0], controls=[1, 2], encode=True)
+        cir.observable(0); cir.observable(1, 'x'); cir.observable([2, 3], 'xy')
+        cir.to(dev, torch.double)
+        cir(data=data)
+        exp = cir.expectation()
+        exp.sum().backward()
+        if rank == 0:
+            e_err = float(np.abs(exp.detach().cpu().numpy() - g[f'ref_test_n{n}/expectation']).max())
+            g_err = float(np.abs(data.grad.cpu().numpy() - g[f'ref_test_n{n}/grad']).max())
+            print(f'n={n} world={world} sharded expectation vs reference {e_err:.2e}, gradient {g_err:.2e}')
+            ok = ok and e_err < 1e-10 and g_err < 5e-7
+    n = 21
+    gen = torch.Generator().manual_seed(4)
+    angles = (torch.rand(3 * n, generator=gen, dtype=torch.float64) * 6).to(dev)
+
+    def build(c):
+        c.rxlayer(encode=True)
+        c.cnot_ring()
+        c.rylayer(encode=True)
+        for q in range(0, n - 1, 2):
+            c.cnot(q + 1, q)
+        c.rzlayer(encode=True)
+        c.rxlayer()
+        c.cnot_ring(step=3)
+        c.observable([0, n - 1], 'zz')
+        c.observable(1, 'x')
+        c.observable([2, 10], 'yz')
+        return c
+
+    grads = []
+    for cls in (dq.DistributedQubitCircuit, dq.QubitCircuit):
+        torch.manual_seed(1)     # same initial parameters of the trainable rxlayer
+        cir = build(cls(n))
+        cir.to(dev, torch.double)
+        d = angles.clone().requires_grad_(True)
+        cir(data=d)
+        e = cir.expectation().reshape(-1)
+        (e * torch.tensor([1.0, -0.5, 2.0], dtype=torch.float64, device=dev)).sum().backward()
+        grads.append((e.detach(), d.grad.clone(), torch.stack([p.grad.reshape(()) for p in cir.parameters()])))
+    if rank == 0:
+        e_err = float((grads[0][0] - grads[1][0]).abs().max())
+        d_err = float((grads[0][1] - grads[1][1]).abs().max())
+        p_err = float((grads[0][2] - grads[1][2]).abs().max())
+        print(f'n={n} world={world} sharded vs single-GPU: expectation {e_err:.2e}, d/d data {d_err:.2e}, '
+              f'd/d parameters {p_err:.2e}')
+        ok = ok and e_err < 1e-10 and d_err < 1e-8 and p_err < 1e-8
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dq.cleanup_distributed()

@@ -36,6 +36,40 @@ class EmuExecutor:
                                    1, a.ctypes.data, m.ctypes.data, 1, 0, None, err, 256)
         assert rc == 0, err.value.decode()
 
+    # local pieces of the differentiable expectation: numpy stands in for the reductions, the CPU-stepped reverse
+    # sweep of the kernel body for b200q_adjoint_run
+    def expectation_z(self, amps, nlocal, masks, index_offset):
+        p = np.abs(amps.numpy())**2
+        idx = np.arange(p.size, dtype=np.int64) | index_offset
+        out = [float((p * (1 - 2 * (np.array([bin(int(i) & int(m)).count('1') & 1 for i in idx])))).sum())
+               for m in masks.tolist()]
+        return torch.tensor(out, dtype=torch.float64)
+
+    def apply_z_weights(self, amps, nlocal, masks, weights, index_offset):
+        a = amps.numpy()
+        idx = np.arange(a.size, dtype=np.int64) | index_offset
+        f = np.zeros(a.size)
+        for m, w in zip(masks.tolist(), weights.reshape(-1).tolist()):
+            f += w * (1 - 2 * np.array([bin(int(i) & int(m)).count('1') & 1 for i in idx]))
+        return torch.from_numpy(a * f)
+
+    def run_plan_adjoint(self, plan, psi, lam, mats, grad, need):
+        from helpers import hostemu
+        from deepquantum_b200 import _lib as L
+        nlocal, dtype, structs = plan
+        arr = (L.GateStruct * max(1, len(structs)))(*structs)
+        lib = hostemu()
+        lib.hostemu_adjoint.restype = C.c_int
+        lib.hostemu_adjoint.argtypes = [C.c_int, C.c_int, C.POINTER(L.GateStruct), C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        nd = np.ascontiguousarray(np.asarray(need, dtype=np.uint8))
+        m = np.ascontiguousarray(mats.numpy())
+        err = C.create_string_buffer(256)
+        rc = lib.hostemu_adjoint(nlocal, L.C64 if dtype == torch.complex64 else L.C128, arr, len(structs), 11,
+                                 psi.numpy().ctypes.data, lam.numpy().ctypes.data, m.ctypes.data,
+                                 grad.numpy().ctypes.data, nd.ctypes.data if len(need) else None, err, 256)
+        assert rc == 0, err.value.decode()
+
     # local pieces of measure_dist: the numpy oracle stands in for csrc/b200q_sample.cu
     def block_mass(self, amps, nlocal):
         p = np.abs(amps.numpy())**2
@@ -129,6 +163,64 @@ def _worker(rank, world, port, n, outdir):
         dq.cleanup_distributed()
 
 
+def _worker_adjoint(rank, world, port, outdir, n=4):
+    """The reference's own test of the differentiable sharded expectation (tests/test_circuit.py:87-139)."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    import deepquantum_b200 as dq
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    dq.setup_distributed('gloo')
+    try:
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'dist_adjoint.npz'))
+        data = torch.tensor(g[f'ref_test_n{n}/data'], dtype=torch.float64, requires_grad=True)
+        cir = dq.DistributedQubitCircuit(n, reupload=True)
+        cir.rxlayer(encode=True); cir.rylayer(encode=True); cir.rzlayer(encode=True); cir.u3layer(encode=True)
+        cir.hlayer(); cir.cnot_ring(); cir.toffoli(0, 1, 2); cir.fredkin(2, 1, 0); cir.swap([2, 3])
+        cir.rx(0, controls=[1, 2, 3], encode=True); cir.ry(1, controls=[0, 2, 3], encode=True)
+        cir.rz(2, controls=[0, 1, 3], encode=True); cir.rxx([0, 1], controls=[2, 3], encode=True)
+        cir.ryy([1, 2], controls=[0, 3], encode=True); cir.rzz([2, 3], controls=[0, 1], encode=True)
+        cir.rxy([3, 0], controls=[1, 2], encode=True)
+        cir.observable(0); cir.observable(1, 'x'); cir.observable([2, 3], 'xy')
+        cir.to(torch.double)
+        cir._executor = EmuExecutor()
+        cir(data=data)
+        exp = cir.expectation()
+        exp.sum().backward()
+        if rank == 0:
+            np.savez(os.path.join(outdir, 'adj.npz'), expectation=exp.detach().numpy(), grad=data.grad.numpy())
+    finally:
+        dq.cleanup_distributed()
+
+
+@pytest.mark.parametrize('world,n', [(1, 4), (2, 4), (2, 6), (4, 6)])
+def test_sharded_expectation_is_differentiable(world, n, tmp_path):
+    """Expectation values and the gradient w.r.t. the encoded data of the sharded circuit = the reference's dense
+    autograd result (fixture written by oracle/make_golden.py from the unmodified reference; the reference's own test
+    compares in float32 with `torch.allclose`); X / Y observables, controlled and multi-target parametric gates, gates on
+    the rank bits."""
+    import subprocess
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), 'adjoint', str(r), str(world), str(port),
+                               str(tmp_path), str(n)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world)]
+    logs = []
+    for pr in procs:
+        try:
+            o, _ = pr.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(o)
+    assert all(pr.returncode == 0 for pr in procs), '\n'.join(logs)
+    res = np.load(os.path.join(tmp_path, 'adj.npz'))
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'dist_adjoint.npz'))
+    assert np.abs(res['expectation'] - g[f'ref_test_n{n}/expectation']).max() < 1e-10
+    # the reverse sweep un-computes with U^dagger; the reference's Hadamard is a float32-rounded constant (unitary to
+    # 6e-8, gate.py:1069), which bounds the gradient at ~1e-7 here -- the floor of the reference's own adjoint too
+    assert np.abs(res['grad'] - g[f'ref_test_n{n}/grad']).max() < 5e-7, (res['grad'], g[f'ref_test_n{n}/grad'])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -185,4 +277,7 @@ def test_sharded_circuit_matches_dense_oracle(world, tmp_path):
 
 
 if __name__ == '__main__':
-    _worker(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5])
+    if sys.argv[1] == 'adjoint':
+        _worker_adjoint(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], int(sys.argv[6]))
+    else:
+        _worker(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5])

@@ -741,8 +741,9 @@ class DistributedQubitCircuit(QubitCircuit):
             engine.require_cuda(st.amps, 'the distributed state (move the circuit with cir.to(f"cuda:{local_rank}"))')
             self._executor = CudaExecutor()
         # with peer-mapped shards (NVLink) the exchanges are bit permutations done by the fused last pass of a segment
+        # (shards below 2^6 amplitudes are padded to the register bits of a thread: those keep the NCCL transposes)
         mode = 'perm' if (hasattr(self._executor, 'run_plan_exchange') and st.world_size > 1
-                          and st.log_num_amps_per_node - st.log_num_nodes >= 1
+                          and st.log_num_amps_per_node - st.log_num_nodes >= 1 and st.log_num_amps_per_node >= 6
                           and getattr(st, 'enable_peer_exchange', lambda: False)()) else 'pswap'
         if self._sharded is None or self._sharded.low is not prog.low or self._sharded.mode != mode:
             self._sharded = ShardedProgram(prog.low, self.nqubit, st.world_size, st.rank, mode)

@@ -23,7 +23,8 @@ from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, R
 from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplitudeDamping, PhaseDamping,  # noqa: F401
                       PhaseFlip)
 from .operation import Channel, Gate, Layer, Operation, dtype_map  # noqa: F401
-from .qmath import evolve_state, evolve_state_controlled, inverse_permutation, multi_kron  # noqa: F401
+from .qmath import (evolve_state, evolve_state_controlled, expectation, inverse_permutation, measure,  # noqa: F401
+                    multi_kron, sample2expval)
 from .state import QubitState, amplitude_encoding  # noqa: F401
 from . import qasm3  # noqa: F401,E402
 from .qasm3 import cir_to_qasm3, qasm3_to_cir  # noqa: F401,E402

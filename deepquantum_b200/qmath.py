@@ -126,3 +126,18 @@ def measure(state: torch.Tensor, shots: int = 1024, with_prob: bool = False, wir
             d[key] = (c, probs[i]) if with_prob else c
         results.append(d)
     return results[0] if batch == 1 else results
+
+
+def expectation(state: torch.Tensor, observable, den_mat: bool = False, chi: int | None = None) -> torch.Tensor:
+    """Drop-in for `qmath.expectation` (reference qmath.py:830-860): <psi| O |psi> (or Tr(O rho)) of one `Observable`
+    on a device state `[2^n, 1]` / `[batch, 2^n, 1]` (density matrices `[.., 2^n, 2^n]`); a real scalar, or `[batch]`.
+    Z strings are one fused reduction pass over the state, X / Y factors are rotated to Z on a copy.  Differentiable
+    w.r.t. the state like the reference's.  Matrix-product states are out of scope (statevector path only)."""
+    if isinstance(state, list):
+        raise NotImplementedError('matrix product states are outside the statevector path of deepquantum_b200')
+    from .circuit import QubitCircuit
+    n = observable.nqubit
+    cir = QubitCircuit(n, den_mat=den_mat)
+    cir.observables.append(observable)
+    cir.state = state
+    return cir.expectation()[..., 0]

@@ -21,7 +21,9 @@ Files written
                       them run to a final state, and the reference's export of a seeded circuit
   fock2.npz           Fock tensor path with the beamsplitter family (mzi, bs_theta, bs_phi, bs_rx, bs_ry, bs_h, dc, h),
                       rotations (r, f) and Kerr gates (k, ck): final states and the local Fock matrices
-  dist_w{2,4,8}.npz   DistributedQubitCircuit shards from gloo ranks (written by make_golden_dist.py)
+  dist_adjoint.npz    the reference's own test circuit of the differentiable sharded expectation
+                      (tests/test_circuit.py:87-139), dense autograd: expectation values and d/d(data), n = 4 and 6
+  unitary.npz         QubitCircuit.get_unitary() of the all-gate-families circuit (5 qubits) and a random circuit
 """
 import json
 import math
@@ -523,7 +525,10 @@ def unitary():
     """`QubitCircuit.get_unitary()` (reference circuit.py:467) of the all-gate-families circuit at 5 qubits and of a
     random Clifford+RX circuit at 6 qubits."""
     out = {}
-    for name, n, spec in (('all_gates_n5', 5, all_gates_spec(5)), ('random_n6_d3', 6, wl.random_clifford_rx_spec(6, 3))):
+    # the reference's get_unitary() of a CONTROLLED UAnyGate disagrees with its own forward pass (probe: forward =
+    # oracle to 2e-16, get_unitary() off by 0.5); those entries are left out of this fixture
+    all_gates = [e for e in all_gates_spec(5) if not (e['g'] in ('any', 'latent') and e.get('c'))]
+    for name, n, spec in (('all_gates_n5', 5, all_gates), ('random_n6_d3', 6, wl.random_clifford_rx_spec(6, 3))):
         cir = dq.QubitCircuit(n)
         wl.apply_spec(cir, spec, torch.complex128)
         cir.to(torch.double)

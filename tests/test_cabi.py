@@ -86,3 +86,18 @@ def test_no_cpu_fallback():
         dq.Hadamard(nqubit=2, wires=[0])(torch.tensor([1, 0, 0, 0], dtype=torch.cfloat))
     with pytest.raises(dq.B200QError):
         dq.evolve_state(torch.zeros(1, 2, 2, dtype=torch.cfloat), torch.eye(2, dtype=torch.cfloat), 2, [0])
+
+
+def test_reference_side_stub_imports_and_installs():
+    """INTEGRATION.md section 2 as an importable file (tools/patch_reference.py): binds the C-ABI symbols and, when
+    the reference tree is mounted (build container only), installs itself into the reference and leaves a CPU
+    circuit unchanged."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('patch_reference', os.path.join(root, 'tools', 'patch_reference.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ('evolve_state', 'op_state_control', 'evolve_den_mat', 'install'):
+        assert callable(getattr(mod, name))
+    mod._self_check()

@@ -490,3 +490,36 @@ def test_batched_data_gradient_matches_per_sample_and_dense():
     assert abs(float(loss_ref) - float(loss)) < 1e-9
     for p_ref, g_gpu in zip(params, got):
         assert (p_ref.grad - g_gpu.cpu().reshape(p_ref.shape)).abs().max() < 1e-8
+
+
+def test_get_unitary_matches_reference():
+    """`QubitCircuit.get_unitary()` (reference circuit.py:467-477) against the reference's own result
+    (tests/golden/unitary.npz): the fused plan applied to the identity as a batch of 2^n basis states."""
+    g = _golden('unitary.npz')
+    for case in sorted({k.split('/')[0] for k in g.files}):
+        meta = json.loads(str(g[case + '/spec']))
+        n, spec = meta['n'], meta['spec']
+        cir = dq.QubitCircuit(n)
+        wl.apply_spec(cir, spec, torch.complex128)
+        cir.to('cuda', torch.double)
+        u = cir.get_unitary().cpu().numpy()
+        assert np.abs(u - g[case + '/unitary']).max() < 1e-10, case
+
+
+def test_package_level_measure_and_expectation():
+    """`dq.measure` / `dq.expectation` (reference __init__.py:112, qmath.py:568-638, 830-860)."""
+    n = 5
+    cir = dq.QubitCircuit(n)
+    wl.apply_spec(cir, wl.random_clifford_rx_spec(n, 3, seed=4))
+    cir.observable([0, 2], 'zx')
+    cir.to('cuda', torch.double)
+    st = cir()
+    e = dq.expectation(st, cir.observables[0])
+    assert e.shape == () and abs(float(e) - float(cir.expectation()[0])) < 1e-14
+    psi = st.reshape(-1).cpu().numpy()
+    want = so.expectation_pauli(psi, n, [0, 2], 'zx')
+    assert abs(float(e) - want) < 1e-10
+    res = dq.measure(st, shots=200, with_prob=True)
+    assert sum(c for c, _ in res.values()) == 200
+    for key, (_, p) in res.items():
+        assert abs(p - abs(psi[int(key, 2)])**2) < 1e-12

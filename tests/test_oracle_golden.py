@@ -130,3 +130,34 @@ def test_qaoa_expectation_and_adjoint_gradient():
             else:
                 grad[p + k] += gi * 2
         np.testing.assert_allclose(grad, g[key + '/grad'], atol=1e-10)
+
+
+@pytest.mark.parametrize('case', _cases())
+def test_torch_port_is_pinned_to_the_reference(case):
+    """`oracle/torch_port.run_ops` -- the timed CPU baseline of bench.py and the checker of the large GPU parity
+    tests -- against the reference's own states: bit-equal in complex128, at the float32 rounding floor in
+    complex64 (ATen blocks the complex64 matmul of the permuted view differently from the reference's call)."""
+    import torch
+    import torch_port
+    g = _load('circuits.npz')
+    meta = json.loads(str(g[case + '/spec']))
+    n, spec = meta['n'], meta['spec']
+    ops = gates_np.lower_spec(spec, n)
+    out128, done, _ = torch_port.run_ops(ops, n, dtype=torch.complex128)
+    assert done == len(ops)
+    ref = g[case + '/c128']
+    assert np.linalg.norm(out128.numpy() - ref) / np.linalg.norm(ref) < 1e-13
+    out64, _, _ = torch_port.run_ops(ops, n, dtype=torch.complex64)
+    assert np.linalg.norm(out64.numpy() - g[case + '/c64']) / np.linalg.norm(ref) < 2e-6
+
+
+def test_oracle_unitary_matches_reference_get_unitary():
+    """The oracle applied to every basis state reproduces `QubitCircuit.get_unitary()` of the reference
+    (circuit.py:467-477; fixture tests/golden/unitary.npz)."""
+    g = _load('unitary.npz')
+    for case in sorted({k.split('/')[0] for k in g.files}):
+        meta = json.loads(str(g[case + '/spec']))
+        n, spec = meta['n'], meta['spec']
+        ops = gates_np.lower_spec(spec, n)
+        u = np.stack([so.run_circuit(ops, n, state=np.eye(2**n, dtype=np.complex128)[j]) for j in range(2**n)], axis=1)
+        assert np.abs(u - g[case + '/unitary']).max() < 1e-12

@@ -1078,6 +1078,7 @@ struct Gen {
 
 bool codegen_supported(const Plan& plan, const b200q_pass_t& P) {
   const int vs = plan.dtype == B200Q_C64 ? 1 : 0;
+  if (P.n_rounds == 0) return false;   // dense pass (5..6 targets): b200q_dense_kernel
   if (P.n_bits != P.n_qubits) return false;
   if (int(P.tile_bits) != plan.opt.chunk_bits + vs) return false;
   if (plan.opt.chunk_bits < 11 || plan.opt.chunk_bits > 13) return false;

@@ -218,8 +218,111 @@ int jit_min_qubits() {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// dense gate on 5..6 targets (UAnyGate / get_unitary-style blocks, reference gate.py:2745-2790): a pass of its own.
+// The 2^k x 2^k matrix is staged once per CTA in shared memory (adjoint folded in); a CTA then walks groups of 2^k
+// amplitudes, GP groups at a time: gather into shared memory, one output row per thread, scatter.  CUDA cores:
+// 8 * 4^k flops per group against 2 * 2^k * B bytes -- k = 6 complex64 is 32 flop / byte, still under the FP32
+// ridge of a B200 (~ 11 flop / byte) by 3x only: the tensor-core version is the next step.
+// ------------------------------------------------------------------------------------------------
+struct DenseArgs {
+  uint64_t ctrl;        // controls, physical bits
+  uint32_t mat_src;
+  int32_t n_qubits, k, adjoint;
+  uint8_t tbit[8];      // physical bit of matrix-index bit j
+  uint8_t sorted[8];    // the same, ascending
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+b200q_dense_kernel(cx<Real>* __restrict__ state, const cx<Real>* __restrict__ mats, const DenseArgs A,
+                   uint64_t amps_per_state, int64_t mat_batch_stride) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int D = 1 << A.k;
+  cx<Real>* M = reinterpret_cast<cx<Real>*>(dsm);            // [D][D], row-major, adjoint folded
+  cx<Real>* xs = M + D * D;                                  // [GP][D]
+  const int GP = blockDim.x / D;
+  const cx<Real>* m = mats + int64_t(blockIdx.y) * mat_batch_stride + A.mat_src;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+    const int r = e / D, c = e % D;
+    cx<Real> v = A.adjoint ? m[c * D + r] : m[e];
+    if (A.adjoint) v.y = -v.y;
+    M[e] = v;
+  }
+  __syncthreads();
+  cx<Real>* st = state + uint64_t(blockIdx.y) * amps_per_state;
+  const int gl = threadIdx.x / D, r = threadIdx.x % D;
+  uint32_t off = 0;   // offset of matrix index r inside a group
+  for (int j = 0; j < A.k; ++j) off |= 0;   // (computed below as 64-bit)
+  uint64_t roff = 0;
+  for (int j = 0; j < A.k; ++j)
+    if ((r >> j) & 1) roff |= 1ull << A.tbit[j];
+  const uint64_t n_groups = amps_per_state >> A.k;
+  for (uint64_t g0 = uint64_t(blockIdx.x) * GP; g0 < n_groups; g0 += uint64_t(gridDim.x) * GP) {
+    const uint64_t g = g0 + gl;
+    uint64_t base = g;
+    for (int j = 0; j < A.k; ++j) base = ((base >> A.sorted[j]) << (A.sorted[j] + 1)) | (base & ((1ull << A.sorted[j]) - 1ull));
+    const bool active = gl < GP && g < n_groups && (base & A.ctrl) == A.ctrl;
+    if (active) xs[gl * D + r] = st[base | roff];
+    __syncthreads();
+    if (active) {
+      Real yr = Real(0), yi = Real(0);
+      const cx<Real>* row = M + r * D;
+      const cx<Real>* x = xs + gl * D;
+      for (int c = 0; c < D; ++c) {
+        const cx<Real> w = row[c], v = x[c];
+        yr += w.x * v.x - w.y * v.y;
+        yi += w.x * v.y + w.y * v.x;
+      }
+      cx<Real> y; y.x = yr; y.y = yi;
+      st[base | roff] = y;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename Real>
+int launch_dense_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubits, int64_t batch, int64_t mbs,
+                      cudaStream_t stream, bool flip_adjoint) {
+  const b200q_op_t& op = P.ops[0];
+  DenseArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.ctrl = op.ctrl_glob;
+  A.mat_src = op.mat_src;
+  A.n_qubits = n_qubits;
+  A.k = op.k;
+  A.adjoint = (((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint) ? 1 : 0;
+  for (int j = 0; j < A.k; ++j) A.tbit[j] = A.sorted[j] = uint8_t((op.dsel_glob[0] >> (8 * j)) & 0xff);
+  std::sort(A.sorted, A.sorted + A.k);
+  const int D = 1 << A.k;
+  const int threads = 256, GP = threads / D;
+  const size_t smem = (size_t(D) * D + size_t(GP) * D) * sizeof(cx<Real>);
+  auto kern = b200q_dense_kernel<Real>;
+  int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "cudaFuncSetAttribute(dense)");
+  if (rc) return rc;
+  const uint64_t n_amps = 1ull << n_qubits;
+  const uint64_t n_groups = n_amps >> A.k;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t want = (n_groups + GP - 1) / GP;
+  const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(sm_count(dev)) * 8));
+  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, batch - b0);
+    kern<<<dim3(gx, (unsigned)nb), threads, smem, stream>>>(
+        reinterpret_cast<cx<Real>*>(state) + uint64_t(b0) * n_amps,
+        reinterpret_cast<const cx<Real>*>(mats) + b0 * mbs, A, n_amps, mbs);
+  }
+  return cuda_err(cudaGetLastError(), "dense pass launch");
+}
+
 int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const void* mats, int64_t batch,
                     int64_t mbs, cudaStream_t stream, const b200q_remote_t* remote = nullptr, int pass_index = -1) {
+  if (P.n_rounds == 0) {   // dense pass (5..6 targets)
+    if (remote && remote->enabled) return set_err(B200Q_EUNSUPPORTED, "a dense pass cannot carry the fused exchange");
+    return pl.dtype == B200Q_C64 ? launch_dense_pass<float>(P, state, mats, pl.n_qubits, batch, mbs, stream, false)
+                                 : launch_dense_pass<double>(P, state, mats, pl.n_qubits, batch, mbs, stream, false);
+  }
   if (pass_index >= 0 && pl.jit && pl.jit->prepared) {
     const int rc = jit_launch(const_cast<Plan&>(pl), pass_index, state, mats, batch, mbs, stream, remote);
     if (rc != -1000) return rc > 0 ? cuda_err((cudaError_t)rc, "specialised pass kernel launch") : rc;
@@ -833,6 +936,16 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
   if (cb > 12) return set_err(B200Q_EUNSUPPORTED, "the adjoint sweep holds two tiles per CTA: plan with chunk_bits <= 12");
   for (int i = (int)p.passes.size() - 1; i >= 0; --i) {
     const b200q_pass_t& P = p.passes[i];
+    if (P.n_rounds == 0) {   // dense pass: un-applied on both states, no cotangent (as for every dense gate on > 2 targets)
+      if (need_grad_host && need_grad_host[P.ops[0].gate_id])
+        return set_err(B200Q_EUNSUPPORTED, "gradient of dense gates on more than 2 targets");
+      for (void* s : {psi, lambda}) {
+        rc = p.dtype == B200Q_C64 ? launch_dense_pass<float>(P, s, matrices, p.n_qubits, 1, 0, (cudaStream_t)stream, true)
+                                  : launch_dense_pass<double>(P, s, matrices, p.n_qubits, 1, 0, (cudaStream_t)stream, true);
+        if (rc) return rc;
+      }
+      continue;
+    }
     uint64_t want = 0;
     for (int o = 0; o < P.n_ops; ++o) {
       const b200q_op_t& op = P.ops[o];

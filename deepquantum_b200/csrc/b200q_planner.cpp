@@ -26,6 +26,7 @@ struct IGate {
   int64_t mat = 0;
   int flags = 0;
   bool reg_kind = false;  // executable inside a register round
+  bool big = false;       // dense on 5..6 targets: a pass of its own (b200q_program.h, "dense pass")
   int op_kind = 0;
   int pool = 0;
 };
@@ -61,7 +62,7 @@ struct Builder {
       if ((bfull & all_bits) == all_bits) break;
       if (++visited > kScanWindow) break;
       const IGate& a = g[i];
-      bool ok = !(a.tmask & (bfull | bdiag)) && !(a.dmask & bfull) && !(a.tmask & ~allowed);
+      bool ok = !a.big && !(a.tmask & (bfull | bdiag)) && !(a.dmask & bfull) && !(a.tmask & ~allowed);
       if (ok && mode == 1 && !a.reg_kind) ok = false;
       if (ok && strict_x && a.op_kind == B200Q_OP_X && (a.ctrl & allowed)) ok = false;
       if (ok && mode == 2 && a.reg_kind) ok = false;
@@ -149,14 +150,17 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
       case B200Q_GATE_MAT:
         if (a.k == 1) { a.reg_kind = true; a.op_kind = B200Q_OP_MAT1; a.pool = 4; }
         else if (a.k <= B200Q_MATK_MAX) { a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); }
-        else return fail("dense gates on more than 4 targets are not supported by the tile kernel");
+        else if (a.k <= B200Q_DENSE_MAX) { a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 0; a.big = true; }
+        else return fail("dense gates on more than 6 targets are not supported");
         a.tmask = tm; a.dmask = a.ctrl;
         break;
       case B200Q_GATE_DIAG:
         if (a.k <= 2) { a.reg_kind = true; a.op_kind = B200Q_OP_DIAG; a.pool = 4; a.tmask = 0; a.dmask = tm | a.ctrl; }
         else if (a.k <= B200Q_MATK_MAX) {
           a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); a.tmask = tm; a.dmask = a.ctrl;
-        } else return fail("diagonal gates on more than 4 targets are not supported");
+        } else if (a.k <= B200Q_DENSE_MAX) {
+          a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 0; a.big = true; a.tmask = tm; a.dmask = a.ctrl;
+        } else return fail("diagonal gates on more than 6 targets are not supported");
         break;
       default:
         return fail("unknown gate kind");
@@ -180,6 +184,32 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
     if (B.first_undone >= n_gates) break;
     const IGate& g0 = B.g[B.first_undone];
     const int op_cap = B.opt.fuse ? B.opt.max_ops : 1;
+    if (g0.big) {   // dense pass: the gate alone, every earlier gate is done (scan() never lets a later gate overtake it
+                    // on a shared qubit, and never puts it into a tile pass)
+      b200q_pass_t P;
+      std::memset(&P, 0, sizeof(P));
+      P.n_bits = (uint8_t)B.n_bits;
+      P.n_qubits = (uint8_t)n_qubits;
+      P.tile_bits = (uint8_t)g0.k;
+      P.n_rounds = 0;
+      P.n_ops = 1;
+      b200q_op_t& op = P.ops[0];
+      op.kind = B200Q_OP_MATK;
+      op.k = (uint8_t)g0.k;
+      op.flags = (uint8_t)((g0.flags & B200Q_GATE_ADJOINT) ? B200Q_FLAG_ADJOINT : 0);
+      op.mat_src = (uint32_t)g0.mat;
+      op.gate_id = (uint32_t)B.first_undone;
+      op.ctrl_glob = g0.ctrl;
+      op.dsel_slot[0] = op.dsel_slot[1] = 0xff;
+      op.code = B200Q_CODE_NONE;
+      for (int j = 0; j < g0.k; ++j) op.dsel_glob[0] |= uint64_t(g0.t[j] & 0xff) << (8 * j);
+      B.done[B.first_undone] = 1;
+      plan->passes.push_back(P);
+      plan->pass_gate_count.push_back(1);
+      plan->stats.n_ops += 1;
+      plan->stats.n_direct += 1;
+      continue;
+    }
 
     // ---- 1. tile bits ---------------------------------------------------------------------------
     uint64_t S = g0.tmask;
@@ -571,8 +601,12 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
   // complex64: the state BETWEEN passes is kept in the SoA chunk format (see b200q_program.h)
   if (dtype == B200Q_C64) {
     const int np = (int)plan->passes.size();
-    for (int i = 0; i < np; ++i)
-      plan->passes[i].layout = (uint8_t)((i > 0 ? B200Q_LAYOUT_SRC_SOA : 0) | (i + 1 < np ? B200Q_LAYOUT_DST_SOA : 0));
+    // (a dense pass reads and writes the caller layout: its neighbours use AoS on that side)
+    auto tile_pass = [&](int i) { return i >= 0 && i < np && plan->passes[i].n_rounds > 0; };
+    for (int i = 0; i < np; ++i) {
+      if (!tile_pass(i)) { plan->passes[i].layout = 0; continue; }
+      plan->passes[i].layout = (uint8_t)((tile_pass(i - 1) ? B200Q_LAYOUT_SRC_SOA : 0) | (tile_pass(i + 1) ? B200Q_LAYOUT_DST_SOA : 0));
+    }
   }
   return plan;
 }

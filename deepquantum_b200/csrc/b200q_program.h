@@ -119,6 +119,11 @@ typedef struct {
   uint8_t nonreg_bit[11];  // tile-local amplitude bits enumerated by the thread's item index
 } b200q_round_t;
 
+/* A dense gate on 5 or 6 targets does not fit a tile round: it is a pass of its own ("dense pass"), marked by
+ * n_rounds == 0 and n_ops == 1.  ops[0]: kind MATK, k = number of targets, mat_src / flags as usual, ctrl_glob = mask of
+ * ALL controls over physical bits, dsel_glob[0] = the physical bit of matrix-index bit j in byte j.  Run by
+ * b200q_dense_kernel (one CTA group per 2^k amplitudes, matrix staged in shared memory). */
+#define B200Q_DENSE_MAX 6
 typedef struct {
   uint8_t n_bits;     // physical index bits of the (padded) local state
   uint8_t n_qubits;   // index bits of the state itself (< n_bits only for states smaller than the register bits)

@@ -20,6 +20,39 @@ void run_pass(const Plan& pl, const b200q_pass_t& P, void* state_v, const void* 
   constexpr int VS = Traits<Real>::VS;
   const int cb = pl.opt.chunk_bits;
   const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
+  if (P.n_rounds == 0) {   // dense pass (5..6 targets): plain loops, the semantics of b200q_dense_kernel
+    const b200q_op_t& op = P.ops[0];
+    const int K = op.k, D = 1 << K;
+    const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+    const uint64_t n_amps = 1ull << pl.n_qubits;
+    for (int64_t b = 0; b < batch; ++b) {
+      cx<Real>* st = reinterpret_cast<cx<Real>*>(state_v) + uint64_t(b) * n_amps;
+      const cx<Real>* m = reinterpret_cast<const cx<Real>*>(mats_v) + b * mbs + op.mat_src;
+      uint64_t tm = 0, off[64];
+      for (int j = 0; j < K; ++j) tm |= 1ull << ((op.dsel_glob[0] >> (8 * j)) & 0xff);
+      for (int r = 0; r < D; ++r) {
+        off[r] = 0;
+        for (int j = 0; j < K; ++j)
+          if ((r >> j) & 1) off[r] |= 1ull << ((op.dsel_glob[0] >> (8 * j)) & 0xff);
+      }
+      std::vector<cx<Real>> x(D);
+      for (uint64_t base = 0; base < n_amps; ++base) {
+        if ((base & tm) || (base & op.ctrl_glob) != op.ctrl_glob) continue;
+        for (int r = 0; r < D; ++r) x[r] = st[base | off[r]];
+        for (int r = 0; r < D; ++r) {
+          Real yr = 0, yi = 0;
+          for (int c = 0; c < D; ++c) {
+            cx<Real> w = adj ? m[c * D + r] : m[r * D + c];
+            if (adj) w.y = -w.y;
+            yr += w.x * x[c].x - w.y * x[c].y;
+            yi += w.x * x[c].y + w.y * x[c].x;
+          }
+          st[base | off[r]].x = yr; st[base | off[r]].y = yi;
+        }
+      }
+    }
+    return;
+  }
   std::vector<chunk> tile(size_t(1) << cb);
   std::vector<cx<Real>> pool(B200Q_POOL_MAX);
   std::vector<Real> coef(size_t(B200Q_MAX_OPS) * B200Q_COEF_PER_OP);

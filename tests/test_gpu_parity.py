@@ -523,3 +523,37 @@ def test_package_level_measure_and_expectation():
     assert sum(c for c, _ in res.values()) == 200
     for key, (_, p) in res.items():
         assert abs(p - abs(psi[int(key, 2)])**2) < 1e-12
+
+
+@pytest.mark.parametrize('n', [12, 21])
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_uany_on_five_and_six_wires(n, rdtype):
+    """`cir.any(U, wires=[...])` with 5 and 6 wires (reference gate.py:2745-2790 accepts any number): dense passes of
+    their own (b200q_dense_kernel) between fused passes, also controlled and inverted, against the oracle."""
+    rng = np.random.default_rng(n)
+
+    def rand_u(k):
+        q, _ = np.linalg.qr(rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k)))
+        return q
+
+    cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
+    u5, u6 = rand_u(5), rand_u(6)
+    w5, w6 = [0, n - 1, 3, 7, 5], [n - 2, 1, 4, 8, 2, 6]
+    cir = dq.QubitCircuit(n)
+    cir.hlayer()
+    cir.any(torch.tensor(u5, dtype=cdt), wires=w5)
+    cir.rxlayer([0.3 + 0.1 * w for w in range(n)])
+    cir.cnot(9, 2)
+    cir.any(torch.tensor(u6, dtype=cdt), wires=w6, controls=[10])
+    cir.rylayer([0.2 * w for w in range(n)])
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    ops = [(gates_np.H, [w], []) for w in range(n)] + [(u5, w5, [])]
+    ops += [(gates_np.rx(np.float32(0.3 + 0.1 * w)), [w], []) for w in range(n)] + [(gates_np.X, [2], [9]), (u6, w6, [10])]
+    ops += [(gates_np.ry(np.float32(0.2 * w)), [w], []) for w in range(n)]
+    ref = so.run_circuit(ops, n)
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < (1e-6 if rdtype == torch.float64 else 5e-6), err     # float32 parameters (gate.py:384-391)
+    # inverse circuit: back to |0...0>
+    back = (cir + cir.inverse())().reshape(-1)
+    assert abs(abs(complex(back[0])) - 1) < (1e-6 if rdtype == torch.float64 else 1e-4)

@@ -422,3 +422,31 @@ def test_sharded_perm_schedule_all_ranks_in_one_process(world):
                 ShardedProgram.commit_exchange(states[r])
     got = torch.cat([s.amps for s in states]).numpy()
     assert np.linalg.norm(got - ref) < 1e-12, np.linalg.norm(got - ref)
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_dense_gates_on_five_and_six_targets(cdtype):
+    """UAnyGate-style dense blocks on 5 and 6 wires (reference gate.py:2745-2790 accepts any k): a pass of their own
+    between fused tile passes, plain and adjoint, with a control, mixed with ordinary gates."""
+    from helpers import lower_ops, hostemu
+    n = 13
+    rng = np.random.default_rng(8)
+    psi = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi /= np.linalg.norm(psi)
+
+    def rand_u(k):
+        q, _ = np.linalg.qr(rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k)))
+        return q
+
+    ops = [(gates_np.H, [w], []) for w in range(n)]
+    ops.append((rand_u(5), [0, 12, 3, 7, 5], []))
+    ops += [(gates_np.rx(0.3 + w), [w], []) for w in range(n)]
+    ops.append((gates_np.X, [2], [9]))
+    ops.append((rand_u(6), [11, 1, 4, 8, 2, 6], [10]))
+    ops.append((rand_u(5).conj().T, [4, 3, 2, 1, 0], []))
+    ops += [(gates_np.ry(0.1 * w), [w], [(w + 1) % n]) for w in range(0, n, 3)]
+    ref = so.run_circuit(ops, n, state=psi)
+    out, stats = emu_run(ops, n, cdtype, state=psi, chunk_bits=11)
+    err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
+    assert err < (1e-12 if cdtype == np.complex128 else 5e-6), (err, stats)
+    assert stats['direct'] >= 3

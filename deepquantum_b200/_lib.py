@@ -57,6 +57,13 @@ class PlanStats(C.Structure):
                                          'threads_per_cta', 'smem_bytes')]
 
 
+class QuditGateStruct(C.Structure):
+    _fields_ = [('n_targets', C.c_int32), ('modes', C.c_int32 * 2), ('reserved', C.c_int32), ('mat_offset', C.c_int64)]
+
+
+QUDIT_FUSED_MAX_GATES = 16
+
+
 class B200QError(RuntimeError):
     pass
 
@@ -95,6 +102,8 @@ _SIGNATURES = {
                                     C.POINTER(C.c_uint8), C.c_void_p]),
     'b200q_qudit_apply': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                     C.c_int64, C.c_void_p]),
+    'b200q_qudit_fused': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,
+                                    C.POINTER(QuditGateStruct), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     'b200q_block_mass': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_sample_blocks': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p]),

@@ -21,6 +21,7 @@ _COMMON = ['b200q_program.h', 'b200q_planner.h']
 SOURCES = {
     'b200q_lib.cu': _COMMON + ['b200q_tile_body.h', 'b200q_jit.h', 'b200q_codegen.h'],
     'b200q_qudit.cu': ['b200q_qudit_geom.h'],
+    'b200q_qudit_fused.cu': [],
     'b200q_sample.cu': [],
     'b200q_planner.cpp': _COMMON,
     'b200q_codegen.cpp': _COMMON + ['b200q_codegen.h'],

@@ -13,6 +13,7 @@ reference's per-element Python loops (photonic/gate.py:356-373, 1098-1114) cost 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any
 
 import torch
@@ -21,6 +22,8 @@ from torch import nn
 from . import _lib as L
 from . import engine
 from .operation import apply_complex_fix
+
+FUSE_FOCK = os.environ.get('B200Q_FOCK_FUSE', '1') != '0'   # A/B switch: 0 = one gate per pass (b200q_qudit_apply)
 
 
 def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, wires, batch: int = 1) -> None:
@@ -32,6 +35,80 @@ def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, w
     w = (C.c_int32 * len(wires))(*[int(x) for x in wires])
     L.check(L.load().b200q_qudit_apply(flat.data_ptr(), nmode, d, engine.dtype_code(flat.dtype), m.data_ptr(), w,
                                        len(wires), batch, engine._stream(flat)))
+
+
+FOCK_TILE_MAX = 12288     # amplitudes of a fused pass's shared-memory tile (b200q_qudit_fused)
+
+
+def plan_fock_passes(gate_modes, nmode: int, d: int, max_gates: int = L.QUDIT_FUSED_MAX_GATES):
+    """Group the gates of a Fock circuit (`gate_modes[i]` = modes of gate i, circuit order) into fused passes: each pass
+    owns T tile modes (cutoff^T amplitudes staged in shared memory) and runs, in order, every pending gate whose modes
+    lie in the tile and that does not have to wait for an earlier gate outside it (gates on disjoint modes commute).
+    The last mode is kept in every tile whenever there is room: global accesses are then runs of `cutoff` amplitudes.
+    Returns [(sorted tile modes, [gate indices])]; the reference applies the same gates one by one
+    (photonic/circuit.py:405-431), each with its own pass over the state."""
+    T = 1
+    while T < nmode and d ** (T + 1) <= FOCK_TILE_MAX:
+        T += 1
+    n = len(gate_modes)
+    done = [False] * n
+    passes = []
+
+    def scan(tile):
+        blocked, out = set(), []
+        for i in range(n):
+            if done[i]:
+                continue
+            ms = set(gate_modes[i])
+            if ms <= tile and not (ms & blocked):
+                out.append(i)
+                if len(out) == max_gates:
+                    break
+            else:
+                blocked |= ms
+        return out
+
+    while not all(done):
+        first = done.index(False)
+        tile = set(gate_modes[first])
+        assert len(tile) <= T, 'gate does not fit a fused tile'
+        if len(tile) < T:
+            tile.add(nmode - 1)
+        while len(tile) < T:
+            # the earliest pending gate that is not executable yet and whose missing modes still fit
+            blocked, add = set(), None
+            for i in range(n):
+                if done[i]:
+                    continue
+                ms = set(gate_modes[i])
+                if ms <= tile and not (ms & blocked):
+                    continue
+                if not (ms & blocked) and len(tile | ms) <= T:
+                    add = ms - tile
+                    break
+                blocked |= ms
+            if add is None:
+                add = {next(m for m in range(nmode - 1, -1, -1) if m not in tile)}
+            tile |= add
+        ids = scan(tile)
+        for i in ids:
+            done[i] = True
+        passes.append((sorted(tile), ids))
+    return passes
+
+
+def qudit_fused_(flat: torch.Tensor, nmode: int, d: int, tile_modes, gates, matrices: torch.Tensor, batch: int = 1) -> None:
+    """One fused pass (`b200q_qudit_fused`): `gates` = [(modes, element offset of the matrix in `matrices`)]."""
+    engine.require_cuda(flat, 'the Fock state tensor')
+    arr = (L.QuditGateStruct * len(gates))()
+    for g, (modes, off) in zip(arr, gates):
+        g.n_targets = len(modes)
+        for j, m in enumerate(modes):
+            g.modes[j] = int(m)
+        g.mat_offset = int(off)
+    tm = (C.c_int32 * len(tile_modes))(*[int(x) for x in tile_modes])
+    L.check(L.load().b200q_qudit_fused(flat.data_ptr(), nmode, d, engine.dtype_code(flat.dtype), tm, len(tile_modes), arr,
+                                       len(gates), matrices.data_ptr(), batch, engine._stream(flat)))
 
 
 # ---- Fock-space transformation matrices, batched over gates ------------------------------------------------
@@ -596,7 +673,28 @@ class QumodeCircuit(nn.Module):
         flat = x.reshape(-1, d**n).contiguous().clone()
         with torch.no_grad():
             mats = self.build_matrices(flat.dtype, flat.device)
-            for op, m in zip(self.operators, mats):
-                qudit_apply_(flat, n, d, m, op.wires, flat.shape[0])
+            fuse = (FUSE_FOCK and len(self.operators) > 0 and d * d <= 256 and d * d <= FOCK_TILE_MAX and n >= 2
+                    and all(1 <= len(op.wires) <= 2 for op in self.operators))
+            if fuse:
+                key = tuple(tuple(op.wires) for op in self.operators)
+                if self.__dict__.get('_fock_plan_key') != key:
+                    self.__dict__['_fock_plan'] = plan_fock_passes([tuple(op.wires) for op in self.operators], n, d)
+                    self.__dict__['_fock_plan_key'] = key
+                buf = torch.cat([m.reshape(-1) for m in mats]).contiguous()
+                offs, acc = [], 0
+                for m in mats:
+                    offs.append(acc)
+                    acc += m.numel()
+                for tile, ids in self.__dict__['_fock_plan']:
+                    qudit_fused_(flat, n, d, tile, [(self.operators[i].wires, offs[i]) for i in ids], buf, flat.shape[0])
+            else:
+                for op, m in zip(self.operators, mats):
+                    qudit_apply_(flat, n, d, m, op.wires, flat.shape[0])
         self.state = flat.reshape([-1] + [d] * n)
         return self.state
+
+    def fock_plan_stats(self) -> dict:
+        """Passes and gates per pass of the fused plan of the last forward (diagnostics / bench)."""
+        plan = self.__dict__.get('_fock_plan') or []
+        return {'gates': len(self.operators), 'passes': len(plan), 'gates_per_pass': [len(ids) for _, ids in plan],
+                'tiles': [t for t, _ in plan]}

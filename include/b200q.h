@@ -181,6 +181,22 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
 int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
                       int n_targets, int64_t batch, void* stream);
 
+/* Fused Fock pass: `n_gates` consecutive evolve_state(..., qudit = cutoff) calls of the photonic tensor path
+ * (photonic/circuit.py:405-431 applies them one by one) whose modes all lie in `tile_modes` (ascending, at most
+ * cutoff^n_tile = 12 288 amplitudes; the planner keeps the last mode in the tile so that global accesses are runs of
+ * `cutoff` amplitudes), applied with ONE read and ONE write of the state.  `matrices`: device buffer holding the
+ * dense cutoff^k x cutoff^k matrices (k = 1, 2) at `mat_offset` (elements); `modes[0]` is the most significant digit
+ * of the matrix index, as in b200q_qudit_apply. */
+#define B200Q_QUDIT_FUSED_MAX_GATES 16
+typedef struct b200q_qudit_gate {
+  int32_t n_targets;
+  int32_t modes[2];
+  int32_t reserved;
+  int64_t mat_offset;
+} b200q_qudit_gate_t;
+int b200q_qudit_fused(void* state, int n_modes, int d, int dtype, const int32_t* tile_modes, int n_tile,
+                      const b200q_qudit_gate_t* gates, int n_gates, const void* matrices, int64_t batch, void* stream);
+
 /* ---- sampling: qmath.measure + block_sample (qmath.py:543-638), the step after the path -----------
  * Inverse-CDF sampling in two levels.  The caller (Python) draws `shots` uniforms, searches them in the
  * prefix sum of the block masses and passes, per shot, the block and the residual mass inside it.

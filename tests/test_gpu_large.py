@@ -129,3 +129,58 @@ def test_qaoa_c3_shape_loss_and_gradient_n16():
     assert abs(float(loss) - float(loss_ref)) < 1e-6 * max(1.0, abs(float(loss_ref)))
     g, gr = pg.grad.cpu().numpy(), ph.grad.numpy()
     assert np.abs(g - gr).max() < 2e-6 * max(1.0, np.abs(gr).max()), (g, gr)
+
+
+@pytest.mark.parametrize('world', [2, 8])
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_sharded_schedule_all_ranks_on_one_gpu(world, rdtype):
+    """The sharded path on a ONE-GPU box: every rank's `ShardedProgram` ('perm' schedule: exchanges are bit
+    permutations fused into the last pass of a segment) is stepped in lockstep in this process, every rank's shard and
+    receive buffer are tensors on cuda:0, and the "peer" pointers of the fused exchange are simply the other ranks'
+    buffers -- the exchange kernel, the rank predicates / per-rank phases and the specialised pass kernels (shards of
+    >= 2^20 amplitudes) all run on the GPU.  C2 generator at 23 qubits depth 12 against the CPU oracle."""
+    from deepquantum_b200.distributed import CudaExecutor, ShardedProgram
+    n, depth = 23, 12
+    g = world.bit_length() - 1
+    nl = n - g
+    spec = wl.random_clifford_rx_spec(n, depth)
+    ops = gates_np.lower_spec(spec, n)
+    ref, done, _ = torch_port.run_ops(ops, n, dtype=torch.complex128)
+    ref = ref.numpy()
+    dense = dq.QubitCircuit(n)
+    wl.apply_spec(dense, spec)
+    dense.to('cuda', rdtype)
+    cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
+    low = dense._get_program().low
+    mats = low.build_matrices(cdt, 'cuda').detach()
+
+    class State:
+        def __init__(self, r):
+            self.amps = torch.zeros(2**nl, dtype=cdt, device='cuda')
+            self.buffer = torch.zeros(2**nl, dtype=cdt, device='cuda')
+            if r == 0:
+                self.amps[0] = 1.0
+
+        def enable_peer_exchange(self):
+            return True
+
+        def peer_buffer_ptrs(self):
+            return [s.buffer.data_ptr() for s in states]
+
+    states = [State(r) for r in range(world)]
+    progs = [ShardedProgram(low, n, world, r, 'perm') for r in range(world)]
+    ex = CudaExecutor()
+    for p in progs:
+        p.fused_exchanges, p._skip_next = 0, False
+    assert any(s[0] == 'xperm' for s in progs[0].steps)
+    for si in range(len(progs[0].steps)):
+        what = [progs[r].run_step(si, states[r], mats, ex, True) for r in range(world)]
+        assert len(set(what)) == 1, what
+        torch.cuda.synchronize()
+        if what[0] == 'exchange':
+            for r in range(world):
+                ShardedProgram.commit_exchange(states[r])
+    got = torch.cat([s.amps for s in states]).cpu().numpy().astype(np.complex128)
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err < REL_L2[rdtype], (world, rdtype, err)
+    assert progs[0].fused_exchanges > 0

@@ -105,3 +105,66 @@ def test_fock_state_constructors():
     assert dq.photonic.FockState([(0.6, [1, 0, 0]), (0.8, [0, 1, 1])]).state.shape == (1, 3, 3, 3)   # cutoff = 2 + 1
     assert dq.photonic.FockState([1, 0, 2]).state[0, 1, 0, 2] == 1
     assert dq.photonic.FockState('vac', nmode=2, cutoff=3).state[0, 0, 0] == 1
+
+
+def _c5_circuit(nmode, cutoff, rdtype):
+    import deepquantum_b200 as dq
+    from deepquantum_b200 import workloads as wl
+    spec = wl.fock_interferometer_spec(nmode)
+    cir = dq.QumodeCircuit(nmode, 'vac', cutoff=cutoff, backend='fock', basis=False)
+    for e in spec:
+        if e['g'] == 's':
+            cir.s(e['w'][0], e['p'][0], e['p'][1])
+        else:
+            cir.bs(e['w'], e['p'])
+    cir.to('cuda', rdtype)
+    return cir
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nmode,cutoff,rdtype', [(6, 10, torch.float32), (6, 10, torch.float64), (5, 7, torch.float64),
+                                                 (7, 4, torch.float32)])
+def test_fused_fock_passes_against_host_contraction(nmode, cutoff, rdtype):
+    """Config-5 circuit (squeezers + Clements mesh) through the FUSED Fock passes (b200q_qudit_fused) against the
+    oracle's qudit contraction on the host (numpy restatement of evolve_state with qudit = cutoff, qmath.py:485-506)
+    with the same matrices, and against the one-gate-per-pass kernel."""
+    import statevec_oracle as so
+    from deepquantum_b200 import photonic as ph
+    cir = _c5_circuit(nmode, cutoff, rdtype)
+    out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    stats = cir.fock_plan_stats()
+    assert 0 < stats['passes'] < stats['gates']
+    cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
+    mats = cir.build_matrices(cdt, 'cuda')
+    psi = np.zeros((1, cutoff**nmode), dtype=np.complex128)
+    psi[0, 0] = 1
+    for op, m in zip(cir.operators, mats):
+        psi = so.evolve_state(psi, m.cpu().numpy().astype(np.complex128), nmode, list(op.wires), cutoff)
+    ref = psi.reshape(-1)
+    tol = 1e-12 if rdtype == torch.float64 else 2e-6
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < tol
+    old = ph.FUSE_FOCK
+    ph.FUSE_FOCK = False
+    try:
+        unfused = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    finally:
+        ph.FUSE_FOCK = old
+    assert np.linalg.norm(out - unfused) / np.linalg.norm(ref) < tol
+
+
+@pytest.mark.gpu
+def test_fused_fock_full_size_c5_matches_per_gate_kernel():
+    """BASELINE config 5 at full size (8 modes, cutoff 10, 10^8 amplitudes): fused passes against the per-gate kernel
+    (itself pinned by the reference fixtures at smaller sizes), and the norm."""
+    from deepquantum_b200 import photonic as ph
+    cir = _c5_circuit(8, 10, torch.float32)
+    out = cir().reshape(-1).clone()
+    ph_old = ph.FUSE_FOCK
+    ph.FUSE_FOCK = False
+    try:
+        ref = cir().reshape(-1)
+    finally:
+        ph.FUSE_FOCK = ph_old
+    err = float((out - ref).norm() / ref.norm())
+    assert err < 2e-6, err
+    assert abs(float((out.real**2 + out.imag**2).sum()) - 1) < 1e-3     # truncated Fock space: squeezing leaks a little

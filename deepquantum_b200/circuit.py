@@ -293,11 +293,16 @@ class QubitCircuit(Operation):
         for rot, items in groups.items():
             phi = flat
             if rot:
+                # R^dagger Z R = X for R = Ry(-pi/2), = Y for R = Rx(pi/2), evaluated in the state's precision: the
+                # reference applies the Pauli matrices themselves (layer.py:156-166), which is exact -- a rotation by
+                # its float32-rounded Hadamard constant (gate.py:1069) would cost 3e-8 in complex128
                 basis_cir = QubitCircuit(n, den_mat=dm)
+                half = torch.tensor(torch.pi / 2, dtype=flat.real.dtype)
                 for w, b in rot:
                     if b == 'y':
-                        basis_cir.sdg(w)
-                    basis_cir.h(w)
+                        basis_cir.rx(w, half)
+                    else:
+                        basis_cir.ry(w, -half)
                 basis_cir.to(flat.device, flat.real.dtype)
                 phi = basis_cir(state=flat.reshape(batch, 2**n, -1)).reshape(batch, -1)
             if dm:

@@ -33,7 +33,9 @@ namespace {
 constexpr int kFThreads = 512;
 constexpr int kMaxFGates = B200Q_QUDIT_FUSED_MAX_GATES;
 constexpr int kMaxModes = 16;
-constexpr int kMaxOut = 24;        // outputs per thread and gate: d^T <= kMaxOut * kFThreads
+constexpr int kGPT = 4;            // groups per thread and matrix row: every ELL entry is loaded once for kGPT outputs
+constexpr int kMaxUnits = 6;       // (row, group quad) units per thread and gate: d^T <= kGPT * kMaxUnits * kFThreads
+constexpr int kMaxOut = kGPT * kMaxUnits;
 constexpr int kMaxD2 = 256;        // d^k of a gate
 
 template <typename Real> struct cxf { Real x, y; };
@@ -43,19 +45,24 @@ struct FGate {
   int32_t D;            // d^k
   int32_t NG;           // groups = d^(T-k)
   int32_t lstride[2];   // tile-local stride of matrix digit j (j = 0: most significant matrix digit, reference order)
-  int32_t gseg[3];      // group index -> tile-local base: radices of the three segments between / around the targets
-  int32_t gmul[3];      //                                 and their tile-local multipliers
+  int32_t n_ntd;        // non-target tile digits, least significant first, and their (padded) tile-local strides:
+  int32_t ntd_stride[8];   //   the group index enumerates them
   int64_t mat_off;      // element offset of the dense matrix
   int32_t ell_off;      // first ELL row of this gate in the workspace (rows of kMaxD2 entries)
   int32_t pad;
 };
 
 struct FPass {
-  int32_t n_modes, d, T, n_gates, n_rest, tile_size, tile_hi;   // tile_hi = tile_size / d
+  int32_t n_modes, d, T, n_gates, n_rest, tile_size, tile_hi;   // tile_hi = tile_size / d (logical sizes)
+  int32_t tile_alloc;         // elements of the PADDED shared-memory tile (see lpad)
+  int32_t lstride_tile[8];    // padded tile-local stride of tile digit j: odd in 8-byte words, so that threads walking
+                              // any digit hit distinct banks (powers of an even cutoff map to 4-8 banks only)
   int32_t rest_radix[kMaxModes];
   int64_t rest_stride[kMaxModes];
   int64_t tile_stride[8];     // global stride of tile digit j (j = 0 most significant in the tile)
   int64_t state_size, n_tiles;
+  uint32_t magic_d;           // ceil(2^32 / d): e / d = __umulhi(e, magic_d) for e < 2^16
+  int32_t ell_cap;            // ELL entries of shared memory reserved for the gates of the pass (0: read from global)
   FGate gates[kMaxFGates];
 };
 
@@ -98,13 +105,11 @@ fused_build_ell(const cxf<Real>* __restrict__ mats, const FPass P, cxf<Real>* __
   }
 }
 
-__device__ __forceinline__ int group_base(const FGate& G, int grp) {
-  // grp enumerates the non-target tile digits, least significant segment first
-  const int a = grp % G.gseg[0];
-  const int q = grp / G.gseg[0];
-  const int b = q % G.gseg[1];
-  const int c = q / G.gseg[1];
-  return a * G.gmul[0] + b * G.gmul[1] + c * G.gmul[2];
+__device__ __forceinline__ int group_base(const FGate& G, int grp, int d) {
+  // grp enumerates the non-target tile digits, least significant first
+  int b = 0;
+  for (int j = 0; j < G.n_ntd; ++j) { b += (grp % d) * G.ntd_stride[j]; grp /= d; }
+  return b;
 }
 
 template <typename Real>
@@ -112,22 +117,52 @@ __global__ void __launch_bounds__(kFThreads)
 qudit_fused_kernel(cxf<Real>* __restrict__ state, const __grid_constant__ FPass P, const cxf<Real>* __restrict__ vals,
                    const int32_t* __restrict__ offs, const int32_t* __restrict__ width) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  cxf<Real>* tile = reinterpret_cast<cxf<Real>*>(fsm);                       // [tile_size]
-  int64_t* goff = reinterpret_cast<int64_t*>(tile + P.tile_size);            // [tile_hi]: global offset, last digit 0
-  uint16_t* gbase = reinterpret_cast<uint16_t*>(goff + P.tile_hi);            // per gate: [NG] tile-local group bases
+  cxf<Real>* tile = reinterpret_cast<cxf<Real>*>(fsm);                       // [tile_alloc], padded
+  int64_t* goff = reinterpret_cast<int64_t*>(tile + P.tile_alloc);           // [tile_hi]: global offset, last digit 0
+  uint16_t* lpad = reinterpret_cast<uint16_t*>(goff + P.tile_hi);             // [tile_hi]: padded tile-local offset
+  uint16_t* gbase = lpad + ((P.tile_hi + 7) & ~7);                            // per gate: [NG] tile-local group bases
   const int tid = threadIdx.x, d = P.d, T = P.T;
+  int ng_total = 0;
+  for (int gi = 0; gi < P.n_gates; ++gi) ng_total += P.gates[gi].NG;
+  // ELL rows of every gate of the pass, compacted to their common width, staged ONCE per CTA (the inner loop then
+  // reads values and offsets with broadcast shared loads instead of dependent global loads)
+  cxf<Real>* svals = reinterpret_cast<cxf<Real>*>(gbase + ((ng_total + 7) & ~7));
+  uint16_t* soffs = reinterpret_cast<uint16_t*>(svals + P.ell_cap);
+  __shared__ int s_ell_base[kMaxFGates + 1];
+  __shared__ int s_staged;
+  if (tid == 0) {
+    int acc = 0;
+    for (int gi = 0; gi < P.n_gates; ++gi) { s_ell_base[gi] = acc; acc += P.gates[gi].D * width[gi]; }
+    s_ell_base[P.n_gates] = acc;
+    s_staged = (P.ell_cap > 0 && acc <= P.ell_cap) ? 1 : 0;
+  }
+  __syncthreads();
+  const bool staged = s_staged != 0;
+  if (staged) {
+    for (int gi = 0; gi < P.n_gates; ++gi) {
+      const FGate& G = P.gates[gi];
+      const int w = width[gi];
+      for (int i = tid; i < G.D * w; i += kFThreads) {
+        const int r = i / w, j = i - r * w;
+        svals[s_ell_base[gi] + i] = vals[((int64_t)G.ell_off + r) * kMaxD2 + j];
+        soffs[s_ell_base[gi] + i] = (uint16_t)offs[((int64_t)G.ell_off + r) * kMaxD2 + j];
+      }
+    }
+  }
   // tables, once per CTA
   for (int h = tid; h < P.tile_hi; h += kFThreads) {
     int x = h;
     int64_t o = 0;
-    for (int j = T - 2; j >= 0; --j) { o += int64_t(x % d) * P.tile_stride[j]; x /= d; }
+    int lp = 0;
+    for (int j = T - 2; j >= 0; --j) { o += int64_t(x % d) * P.tile_stride[j]; lp += (x % d) * P.lstride_tile[j]; x /= d; }
     goff[h] = o;
+    lpad[h] = (uint16_t)lp;
   }
   {
     int gb = 0;
     for (int gi = 0; gi < P.n_gates; ++gi) {
       const FGate& G = P.gates[gi];
-      for (int g = tid; g < G.NG; g += kFThreads) gbase[gb + g] = (uint16_t)group_base(G, g);
+      for (int g = tid; g < G.NG; g += kFThreads) gbase[gb + g] = (uint16_t)group_base(G, g, d);
       gb += G.NG;
     }
   }
@@ -142,8 +177,8 @@ qudit_fused_kernel(cxf<Real>* __restrict__ state, const __grid_constant__ FPass 
     }
     // ---- load
     for (int e = tid; e < P.tile_size; e += kFThreads) {
-      const int h = e / d, l = e - h * d;
-      tile[e] = st[base + goff[h] + l * last_stride];
+      const int h = (int)__umulhi((unsigned)e, P.magic_d), l = e - h * d;
+      tile[lpad[h] + l] = st[base + goff[h] + l * last_stride];
     }
     __syncthreads();
     // ---- gates
@@ -153,34 +188,65 @@ qudit_fused_kernel(cxf<Real>* __restrict__ state, const __grid_constant__ FPass 
       const int w = width[gi];
       const cxf<Real>* gv = vals + (int64_t)G.ell_off * kMaxD2;
       const int32_t* go = offs + (int64_t)G.ell_off * kMaxD2;
-      Real yr[kMaxOut], yi[kMaxOut];
+      // unit u = (row, group quad gq): the thread accumulates groups gq, gq + NU, gq + 2 NU, gq + 3 NU of matrix row `row`
+      // (consecutive threads -> consecutive groups; every ELL entry feeds kGPT independent accumulator chains)
+      const int NU = (G.NG + kGPT - 1) / kGPT;
+      const int n_units = G.D * NU;
+      Real yr[kMaxUnits][kGPT], yi[kMaxUnits][kGPT];
 #pragma unroll
-      for (int i = 0; i < kMaxOut; ++i) {
-        const int o = tid + i * kFThreads;
-        yr[i] = yi[i] = Real(0);
-        if (o < P.tile_size) {
-          const int row = o / G.NG, grp = o - row * G.NG;
-          const cxf<Real>* x = tile + gbase[gb + grp];
-          const cxf<Real>* rv = gv + (int64_t)row * kMaxD2;
-          const int32_t* ro = go + (int64_t)row * kMaxD2;
-          Real ar = Real(0), ai = Real(0);
-          for (int j = 0; j < w; ++j) {
-            const cxf<Real> m = rv[j], v = x[ro[j]];
-            ar = fma(m.x, v.x, ar); ar = fma(-m.y, v.y, ar);
-            ai = fma(m.x, v.y, ai); ai = fma(m.y, v.x, ai);
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = tid + i * kFThreads;
+#pragma unroll
+        for (int m = 0; m < kGPT; ++m) yr[i][m] = yi[i][m] = Real(0);
+        if (u < n_units) {
+          const int row = u / NU, gq = u - row * NU;
+          const cxf<Real>* x[kGPT];
+#pragma unroll
+          for (int m = 0; m < kGPT; ++m) x[m] = tile + gbase[gb + min(gq + m * NU, G.NG - 1)];
+          if (staged) {
+            const cxf<Real>* rv = svals + s_ell_base[gi] + row * w;
+            const uint16_t* ro = soffs + s_ell_base[gi] + row * w;
+            for (int j = 0; j < w; ++j) {
+              const cxf<Real> mm = rv[j];
+              const int off = ro[j];
+#pragma unroll
+              for (int m = 0; m < kGPT; ++m) {
+                const cxf<Real> v = x[m][off];
+                yr[i][m] = fma(mm.x, v.x, yr[i][m]); yr[i][m] = fma(-mm.y, v.y, yr[i][m]);
+                yi[i][m] = fma(mm.x, v.y, yi[i][m]); yi[i][m] = fma(mm.y, v.x, yi[i][m]);
+              }
+            }
+          } else {
+            const cxf<Real>* rv = gv + (int64_t)row * kMaxD2;
+            const int32_t* ro = go + (int64_t)row * kMaxD2;
+            for (int j = 0; j < w; ++j) {
+              const cxf<Real> mm = rv[j];
+              const int off = ro[j];
+#pragma unroll
+              for (int m = 0; m < kGPT; ++m) {
+                const cxf<Real> v = x[m][off];
+                yr[i][m] = fma(mm.x, v.x, yr[i][m]); yr[i][m] = fma(-mm.y, v.y, yr[i][m]);
+                yi[i][m] = fma(mm.x, v.y, yi[i][m]); yi[i][m] = fma(mm.y, v.x, yi[i][m]);
+              }
+            }
           }
-          yr[i] = ar; yi[i] = ai;
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < kMaxOut; ++i) {
-        const int o = tid + i * kFThreads;
-        if (o < P.tile_size) {
-          const int row = o / G.NG, grp = o - row * G.NG;
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = tid + i * kFThreads;
+        if (u < n_units) {
+          const int row = u / NU, gq = u - row * NU;
           const int roff = G.k == 1 ? row * G.lstride[0] : (row / d) * G.lstride[0] + (row % d) * G.lstride[1];
-          cxf<Real> y; y.x = yr[i]; y.y = yi[i];
-          tile[gbase[gb + grp] + roff] = y;
+#pragma unroll
+          for (int m = 0; m < kGPT; ++m) {
+            const int grp = gq + m * NU;
+            if (grp < G.NG) {
+              cxf<Real> y; y.x = yr[i][m]; y.y = yi[i][m];
+              tile[gbase[gb + grp] + roff] = y;
+            }
+          }
         }
       }
       __syncthreads();
@@ -188,8 +254,8 @@ qudit_fused_kernel(cxf<Real>* __restrict__ state, const __grid_constant__ FPass 
     }
     // ---- store
     for (int e = tid; e < P.tile_size; e += kFThreads) {
-      const int h = e / d, l = e - h * d;
-      st[base + goff[h] + l * last_stride] = tile[e];
+      const int h = (int)__umulhi((unsigned)e, P.magic_d), l = e - h * d;
+      st[base + goff[h] + l * last_stride] = tile[lpad[h] + l];
     }
     __syncthreads();
   }
@@ -222,8 +288,13 @@ int run_fused(void* state, const FPass& P, const void* mats, int64_t batch, cuda
   fused_build_ell<Real><<<P.n_gates, kMaxD2, 0, s>>>((const cxf<Real>*)mats, P, (cxf<Real>*)w->vals, w->offs, w->width, P.d);
   int ng_total = 0;
   for (int i = 0; i < P.n_gates; ++i) ng_total += P.gates[i].NG;
-  const size_t smem = size_t(P.tile_size) * sizeof(cxf<Real>) + size_t(P.tile_hi) * sizeof(int64_t) +
-                      ((size_t(ng_total) * sizeof(uint16_t) + 15) & ~size_t(15));
+  const size_t base_smem = size_t(P.tile_alloc) * sizeof(cxf<Real>) + size_t(P.tile_hi) * sizeof(int64_t) +
+                           size_t((P.tile_hi + 7) & ~7) * sizeof(uint16_t) + size_t((ng_total + 7) & ~7) * sizeof(uint16_t);
+  // whatever is left of ~200 KB holds the ELL rows of the pass (value + 16-bit offset per entry)
+  const size_t budget = 200 * 1024;
+  FPass Q = P;
+  Q.ell_cap = base_smem < budget ? (int32_t)std::min<size_t>((budget - base_smem) / (sizeof(cxf<Real>) + 2), 60000) & ~7 : 0;
+  const size_t smem = base_smem + size_t(Q.ell_cap) * (sizeof(cxf<Real>) + 2) + 16;
   auto kern = qudit_fused_kernel<Real>;
   static size_t smem_set[64][2] = {{0}};
   const int ti = sizeof(Real) == 4 ? 0 : 1;
@@ -234,10 +305,10 @@ int run_fused(void* state, const FPass& P, const void* mats, int64_t batch, cuda
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int per_sm = 1;
   const int64_t gx = std::min<int64_t>(P.n_tiles, int64_t(sms) * per_sm * 4);
   dim3 grid((unsigned)gx, (unsigned)batch);
-  kern<<<grid, kFThreads, smem, s>>>((cxf<Real>*)state, P, (const cxf<Real>*)w->vals, w->offs, w->width);
+  kern<<<grid, kFThreads, smem, s>>>((cxf<Real>*)state, Q, (const cxf<Real>*)w->vals, w->offs, w->width);
   return cuda_err(cudaGetLastError(), "fused qudit kernel launch");
 }
 
@@ -255,6 +326,7 @@ extern "C" int b200q_qudit_fused(void* state, int n_modes, int d, int dtype, con
   FPass P;
   std::memset(&P, 0, sizeof P);
   P.n_modes = n_modes; P.d = d; P.T = n_tile; P.n_gates = n_gates;
+  P.magic_d = (uint32_t)((0x100000000ull + uint64_t(d) - 1) / uint64_t(d));
   int64_t stride[kMaxModes];
   int64_t acc = 1;
   for (int m = n_modes - 1; m >= 0; --m) { stride[m] = acc; acc *= d; if (acc > (int64_t(1) << 40)) return set_err(B200Q_EUNSUPPORTED, "state too large"); }
@@ -276,9 +348,16 @@ extern "C" int b200q_qudit_fused(void* state, int n_modes, int d, int dtype, con
   P.n_tiles = 1;
   for (int m = n_modes - 1; m >= 0; --m)
     if (!in_tile[m]) { P.rest_radix[P.n_rest] = d; P.rest_stride[P.n_rest] = stride[m]; ++P.n_rest; P.n_tiles *= d; }
-  // tile-local stride of tile digit j
+  // padded tile-local stride of tile digit j: s_(j) = s_(j+1) * d (+ 1 for an even cutoff), odd in elements
   int32_t lst[8];
-  { int32_t a = 1; for (int j = n_tile - 1; j >= 0; --j) { lst[j] = a; a *= d; } }
+  {
+    const int pad = (d % 2 == 0) ? 1 : 0;
+    lst[n_tile - 1] = 1;
+    for (int j = n_tile - 2; j >= 0; --j) lst[j] = lst[j + 1] * d + pad;
+    P.tile_alloc = ((lst[0] * d + 1) + 1) & ~1;   // even count: the int64 table behind it stays 16-byte aligned
+    if (P.tile_alloc > 65535) return set_err(B200Q_EUNSUPPORTED, "tile too large (cutoff^tile modes)");
+    for (int j = 0; j < n_tile; ++j) P.lstride_tile[j] = lst[j];
+  }
   int ell_rows = 0;
   for (int gi = 0; gi < n_gates; ++gi) {
     const b200q_qudit_gate_t& g = gates[gi];
@@ -300,14 +379,12 @@ extern "C" int b200q_qudit_fused(void* state, int n_modes, int d, int dtype, con
     int lo = pos[0], hi = pos[0];
     if (g.n_targets == 2) { lo = std::max(pos[0], pos[1]); hi = std::min(pos[0], pos[1]); }   // lo = less significant (larger index)
     auto pw = [&](int e) { int32_t r = 1; for (int i = 0; i < e; ++i) r *= d; return r; };
-    G.gseg[0] = pw(n_tile - 1 - lo); G.gmul[0] = 1;
-    if (g.n_targets == 2) {
-      G.gseg[1] = pw(lo - hi - 1); G.gmul[1] = lst[lo] * d;
-      G.gseg[2] = pw(hi); G.gmul[2] = lst[hi] * d;
-    } else {
-      G.gseg[1] = pw(lo); G.gmul[1] = lst[lo] * d;
-      G.gseg[2] = 1; G.gmul[2] = 0;
-    }
+    // (with padded strides a segment of several digits is no longer a plain multiple: group_base() below expands
+    //  every non-target digit separately from `ntd` / `ntd_stride`)
+    G.n_ntd = 0;
+    for (int q = n_tile - 1; q >= 0; --q)
+      if (q != pos[0] && (g.n_targets == 1 || q != pos[1])) G.ntd_stride[G.n_ntd++] = lst[q];
+    (void)lo; (void)hi; (void)pw;
     G.mat_off = g.mat_offset;
     G.ell_off = ell_rows;
     ell_rows += G.D;

@@ -23,7 +23,11 @@ from . import _lib as L
 from . import engine
 from .operation import apply_complex_fix
 
-FUSE_FOCK = os.environ.get('B200Q_FOCK_FUSE', '1') != '0'   # A/B switch: 0 = one gate per pass (b200q_qudit_apply)
+# A/B switch: 1 = fused Fock passes (b200q_qudit_fused: several gates per read + write of the state).  Measured on C5
+# (8 modes, cutoff 10): 13 passes instead of 36 launches but 40.8 ms against 39.7 ms -- the fused kernel executes
+# 330 thread instructions per amplitude and pass (ELL gather from the shared tile), so it only matches the per-gate
+# kernel; off by default until its contraction is register-blocked
+FUSE_FOCK = os.environ.get('B200Q_FOCK_FUSE', '0') != '0'
 
 
 def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, wires, batch: int = 1) -> None:

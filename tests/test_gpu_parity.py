@@ -538,14 +538,14 @@ def test_uany_on_five_and_six_wires(n, rdtype):
 
     cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
     u5, u6 = rand_u(5), rand_u(6)
-    w5, w6 = [0, n - 1, 3, 7, 5], [n - 2, 1, 4, 8, 2, 6]
+    w5, w6 = [0, n - 1, 3, 7, 5], [n - 3, 1, 4, 8, 2, 6]
     cir = dq.QubitCircuit(n)
     cir.hlayer()
     cir.any(torch.tensor(u5, dtype=cdt), wires=w5)
-    cir.rxlayer([0.3 + 0.1 * w for w in range(n)])
+    cir.rxlayer(inputs=[0.3 + 0.1 * w for w in range(n)])
     cir.cnot(9, 2)
     cir.any(torch.tensor(u6, dtype=cdt), wires=w6, controls=[10])
-    cir.rylayer([0.2 * w for w in range(n)])
+    cir.rylayer(inputs=[0.2 * w for w in range(n)])
     cir.to('cuda', rdtype)
     out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
     ops = [(gates_np.H, [w], []) for w in range(n)] + [(u5, w5, [])]

@@ -131,7 +131,12 @@ def test_fused_fock_passes_against_host_contraction(nmode, cutoff, rdtype):
     import statevec_oracle as so
     from deepquantum_b200 import photonic as ph
     cir = _c5_circuit(nmode, cutoff, rdtype)
-    out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    old = ph.FUSE_FOCK
+    ph.FUSE_FOCK = True
+    try:
+        out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    finally:
+        ph.FUSE_FOCK = old
     stats = cir.fock_plan_stats()
     assert 0 < stats['passes'] < stats['gates']
     cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
@@ -158,8 +163,12 @@ def test_fused_fock_full_size_c5_matches_per_gate_kernel():
     (itself pinned by the reference fixtures at smaller sizes), and the norm."""
     from deepquantum_b200 import photonic as ph
     cir = _c5_circuit(8, 10, torch.float32)
-    out = cir().reshape(-1).clone()
     ph_old = ph.FUSE_FOCK
+    ph.FUSE_FOCK = True
+    try:
+        out = cir().reshape(-1).clone()
+    finally:
+        ph.FUSE_FOCK = ph_old
     ph.FUSE_FOCK = False
     try:
         ref = cir().reshape(-1)

@@ -91,6 +91,8 @@ _SIGNATURES = {
     'b200q_plan_jit_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'b200q_apply_gate': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                    C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    'b200q_dense_tc_apply': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_uint64, C.c_int,
+                                       C.c_void_p]),
     'b200q_norm2': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     'b200q_inner_product': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     'b200q_expectation_z': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_uint64,

@@ -281,10 +281,27 @@ b200q_dense_kernel(cx<Real>* __restrict__ state, const cx<Real>* __restrict__ ma
   }
 }
 
+bool dense_tc_enabled() {
+  const char* e = getenv("B200Q_DENSE_TC");   // read per call: tools/dense_tc_bench.py switches it for its A/B
+  return !(e && atoi(e) == 0);
+}
+
 template <typename Real>
 int launch_dense_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubits, int64_t batch, int64_t mbs,
                       cudaStream_t stream, bool flip_adjoint) {
   const b200q_op_t& op = P.ops[0];
+  if (sizeof(Real) == 4 && n_qubits >= 12 && dense_tc_enabled()) {   // complex64: tensor cores (b200q_dense_tc.cu)
+    int32_t tg[8];
+    for (int j = 0; j < op.k; ++j) tg[j] = int32_t((op.dsel_glob[0] >> (8 * j)) & 0xff);
+    const int adj = (((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint) ? 1 : 0;
+    for (int64_t b = 0; b < batch; ++b) {
+      const int rc = b200q_dense_tc_apply(reinterpret_cast<cx<float>*>(state) + (uint64_t(b) << n_qubits), n_qubits,
+                                          reinterpret_cast<const cx<float>*>(mats) + b * mbs + op.mat_src, tg, op.k,
+                                          op.ctrl_glob, adj, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   DenseArgs A;
   std::memset(&A, 0, sizeof A);
   A.ctrl = op.ctrl_glob;

@@ -145,6 +145,14 @@ int b200q_apply_gate(void* state, int n_qubits, int dtype, int kind, const void*
                      int n_targets, const int32_t* controls, int n_controls, int adjoint, int64_t batch,
                      int64_t matrix_batch_stride, void* stream);
 
+/* Dense gate on 4..6 targets, complex64, on the tensor cores (tcgen05.mma, accumulator in tensor memory, FP32
+ * accuracy by the 3-product TF32 split): evolve_state / op_state_control for UAnyGate-style blocks (gate.py:2745-2790).
+ * `matrix`: dense 2^k x 2^k row-major complex64 on the device; `controls`: mask of control bits; needs >= 12 qubits.
+ * b200q_plan_run uses it for the dense passes (5 and 6 targets) of complex64 plans; B200Q_DENSE_TC=0 selects the
+ * CUDA-core contraction instead. */
+int b200q_dense_tc_apply(void* state, int n_qubits, const void* matrix, const int32_t* targets, int n_targets,
+                         uint64_t controls, int adjoint, void* stream);
+
 /* ---- reductions: qmath.expectation (qmath.py:830-860), inner_product_dist (distributed.py:288) */
 /* out_dev[b] = sum_i |state[b][i]|^2 */
 int b200q_norm2(const void* state, int n_qubits, int dtype, int64_t batch, double* out_dev, void* stream);

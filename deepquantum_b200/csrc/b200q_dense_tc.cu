@@ -42,6 +42,7 @@ constexpr int kN = 64;                 // groups per tile = N of the MMA = TMEM 
 constexpr int kK = 128;                // real-ified block dimension
 constexpr int kGS = kTcThreads / 64;     // groups gathered per step by the CTA
 constexpr int kPT = kN / kGS;          // amplitudes per thread and tile
+constexpr int kStage = kK + 4;          // row stride of the epilogue staging: lanes (n & 7, j & 3) -> 32 distinct banks
 constexpr uint32_t kLBO = 128;         // bytes between the two 16-byte K chunks of one MMA step (next core matrix)
 constexpr uint32_t kSBO = (kK / 4) * 128;   // bytes between groups of 8 rows
 
@@ -133,23 +134,37 @@ b200q_dense_tc_kernel(float2* __restrict__ state, const float2* __restrict__ mat
   const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
   const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
 
-  // per-thread offsets of its amplitudes inside a group: amplitude j = tid & 63, groups (tid >> 6) + kGS i
-  const int j = tid & 63;
-  uint64_t joff = 0;
-  for (int q = 0; q < 6; ++q)
-    if ((j >> q) & 1) joff |= 1ull << A.bbit[q];
+  // Thread -> (group n, amplitude j) of a tile: lane = (n & 7) + 8 (j & 3), so that a warp's stores into the canonical
+  // operand layout (8 rows x 16 bytes per core matrix) hit 32 distinct banks; warp w and iteration i supply the rest:
+  // n >> 3 = i & 7, j >> 2 = 2 w + (i >> 3).  Index expansion (zero bits inserted at the 6 block positions) is a bit
+  // deposit, hence additive over disjoint bit groups: per-thread constants for n and j, one expansion per tile.
+  const int lane = tid & 31;
+  const int nl = lane & 7, jl = lane >> 3;
+  auto expand = [&](uint64_t g) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g = ((g >> A.sorted[q]) << (A.sorted[q] + 1)) | (g & ((1ull << A.sorted[q]) - 1ull));
+    return g;
+  };
+  auto jdep = [&](int jj) {
+    uint64_t o = 0;
+    for (int q = 0; q < 6; ++q)
+      if ((jj >> q) & 1) o |= 1ull << A.bbit[q];
+    return o;
+  };
+  uint64_t e_nh[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) e_nh[h] = expand(uint64_t(h * 8 + nl));
+  const uint64_t d_j[2] = {jdep((2 * warp) * 4 + jl), jdep((2 * warp + 1) * 4 + jl)};
   uint32_t phase = 0;
   for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     // ---- gather kN groups x 64 amplitudes -> B_hi / B_lo
+    const uint64_t tbase = expand(t * kN);
     uint64_t gaddr[kPT];
     bool act[kPT];
 #pragma unroll
     for (int i = 0; i < kPT; ++i) {
-      const int n = (tid >> 6) + kGS * i;
-      uint64_t base = t * kN + n;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) base = ((base >> A.sorted[q]) << (A.sorted[q] + 1)) | (base & ((1ull << A.sorted[q]) - 1ull));
-      gaddr[i] = base | joff;
+      const uint64_t base = tbase | e_nh[i & 7];
+      gaddr[i] = base | d_j[i >> 3];
       act[i] = (base & A.ctrl) == A.ctrl;
     }
     float2 v[kPT];
@@ -157,12 +172,12 @@ b200q_dense_tc_kernel(float2* __restrict__ state, const float2* __restrict__ mat
     for (int i = 0; i < kPT; ++i) v[i] = state[gaddr[i]];
 #pragma unroll
     for (int i = 0; i < kPT; ++i) {
-      const int n = (tid >> 6) + kGS * i;
+      const int n = (i & 7) * 8 + nl, jj = (2 * warp + (i >> 3)) * 4 + jl;
       float hr, lr, hi_, li;
       split_tf32(v[i].x, hr, lr);
       split_tf32(v[i].y, hi_, li);
-      b_hi[canon(n, j)] = hr; b_lo[canon(n, j)] = lr;
-      b_hi[canon(n, 64 + j)] = hi_; b_lo[canon(n, 64 + j)] = li;
+      b_hi[canon(n, jj)] = hr; b_lo[canon(n, jj)] = lr;
+      b_hi[canon(n, 64 + jj)] = hi_; b_lo[canon(n, 64 + jj)] = li;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -210,16 +225,16 @@ b200q_dense_tc_kernel(float2* __restrict__ state, const float2* __restrict__ mat
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     // stage[n][m]: (the MMAs have completed, B is free)
 #pragma unroll
-    for (int n = 0; n < 32; ++n) stage[(col0 + n) * kK + row] = __uint_as_float(r[n]);
+    for (int n = 0; n < 32; ++n) stage[(col0 + n) * kStage + row] = __uint_as_float(r[n]);
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kPT; ++i) {
-      const int n = (tid >> 6) + kGS * i;
+      const int n = (i & 7) * 8 + nl, jj = (2 * warp + (i >> 3)) * 4 + jl;
       if (act[i]) {
         float2 y;
-        y.x = stage[n * kK + j];
-        y.y = stage[n * kK + 64 + j];
+        y.x = stage[n * kStage + jj];
+        y.y = stage[n * kStage + 64 + jj];
         state[gaddr[i]] = y;
       }
     }
@@ -230,7 +245,8 @@ b200q_dense_tc_kernel(float2* __restrict__ state, const float2* __restrict__ mat
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kN));
 }
 
-static_assert(kN == 64 && kTcThreads == 256, "epilogue mapping: 4 lane quarters x 2 column halves of 32");
+static_assert(kN * kStage <= 2 * kN * kK, "the staging reuses the B operands");
+static_assert(kN == 64 && kTcThreads == 256 && kPT == 16, "epilogue mapping: 4 lane quarters x 2 column halves of 32");
 
 }  // namespace
 

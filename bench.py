@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--no-fuse', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='time box of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', default='', choices=['', 'c3', 'c5'],
+                    help='c3: 30-qubit complex128 QAOA forward + backward; c5: Fock 8 modes x cutoff 10 (one line each)')
     return ap.parse_args()
 
 
@@ -282,8 +284,9 @@ def run_single(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = n_passes * args.steps * bytes_pass / (kern_ms * 1e-3) / 1e9
     traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))['tile_kernel_c64_28q_bytes_per_launch']
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(
+            f'jit_pass_c64_{n}q_bytes_per_launch')
     except Exception:
         pass
     line = {
@@ -318,8 +321,96 @@ def run_single(args):
     print(json.dumps(line))
 
 
+def run_config(args):
+    """BASELINE configs 3 and 5 as bench lines of their own (the default run is the headline metric)."""
+    import torch
+
+    import deepquantum_b200 as dq
+    from deepquantum_b200 import workloads as wl
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(0) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, clocks.summary()
+
+    if args.config == 'c3':
+        n, p = args.nqubit or 30, 4
+        edges, weights, layout = wl.qaoa_maxcut_structure(n, p)
+        cir = dq.QubitCircuit(n)
+        wl.build_qaoa(cir, edges, p)
+        cir.to('cuda', torch.double)
+        params_host = torch.tensor([0.1] * p + [1.0] * p, dtype=torch.float64).pin_memory()
+        w = torch.tensor(weights, dtype=torch.float64, device='cuda')
+
+        def step():
+            prm = params_host.to('cuda', non_blocking=True).requires_grad_(True)
+            cir(wl.qaoa_data(prm, weights, layout))
+            loss = 0.5 * (w * (cir.expectation().reshape(-1) - 1)).sum()
+            loss.backward()
+            return float(loss), prm.grad.cpu()
+
+        ms, clocks = timed(step)
+        prog = cir._get_program()
+        plan = prog.plan(torch.complex128)
+        bytes_pass = 2 * (2**n) * 16
+        line = {'metric': 'gate_applications_per_second', 'value': prog.ngates / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c128', 'data': 'synthetic',
+                'config': {'workload': f'config3: {n}-qubit QAOA MaxCut p={p}, complex128, forward + expectation + backward',
+                           'gates': prog.ngates, 'observables': len(edges), 'passes': plan.n_passes,
+                           'specialised_passes': plan.jit_status()['specialised'],
+                           'max_mem_GiB': torch.cuda.max_memory_allocated() / 2**30},
+                'roofline': {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                             'note': f'forward: {plan.n_passes} passes of {bytes_pass} bytes; the reverse sweep moves two '
+                                     'states per pass (see tools/bench_configs.py for the split)'},
+                'e2e': {'value': prog.ngates / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': params_host.numel() * 8,
+                        'd2h_bytes_per_step': 8 + params_host.numel() * 8,
+                        'note': 'the timed step starts from pinned host parameters and reads loss + gradient back'},
+                'gpu_launches': args.steps * (2 * plan.n_passes + 4), 'clocks': clocks}
+    else:
+        nmode, cutoff = 8, 10
+        spec = wl.fock_interferometer_spec(nmode)
+        cir = dq.QumodeCircuit(nmode, 'vac', cutoff=cutoff, backend='fock', basis=False)
+        for e in spec:
+            if e['g'] == 's':
+                cir.s(e['w'][0], e['p'][0], e['p'][1])
+            else:
+                cir.bs(e['w'], e['p'])
+        cir.to('cuda')
+        ms, clocks = timed(lambda: cir())
+        bytes_pass = 2 * cutoff**nmode * 8
+        line = {'metric': 'gate_applications_per_second', 'value': len(spec) / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
+                'config': {'workload': f'config5: Fock {nmode} modes x cutoff {cutoff}, squeezers + Clements mesh, complex64',
+                           'gates': len(spec), 'passes': len(spec)},
+                'roofline': {'bound': 'hbm', 'achieved': len(spec) * bytes_pass / (ms * 1e-3) / 1e9, 'peak': peak,
+                             'unit': 'GB/s', 'frac': len(spec) * bytes_pass / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                             'kernel': 'qudit_apply_kernel (one gate per pass; includes the matrix build)'},
+                'e2e': {'value': len(spec) / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                        'note': 'parameters live on the device (the reference builds this circuit from constants too)'},
+                'gpu_launches': args.steps * 2 * len(spec), 'clocks': clocks}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
+    if args.config and args.impl != 'reference':
+        return run_config(args)
     if args.impl == 'reference':
         return run_reference(args)
     if args.gpus > 1 or int(os.environ.get('WORLD_SIZE', '1')) > 1:

@@ -401,10 +401,12 @@ class QubitCircuit(Operation):
     def inverse(self, encode: bool = False) -> 'QubitCircuit':
         """Inverse circuit (reference circuit.py:530-555): reversed operators, each `op.inverse()`."""
         cir = QubitCircuit(nqubit=self.nqubit, name=self.name, den_mat=self.den_mat, reupload=self.reupload)
+        # a layer is stored flattened in `operators` and as ONE entry of `encoders`: membership is by member gate
+        enc_ids = {id(g) for e in self.encoders for g in (e.gates if isinstance(e, Layer) else [e])}
         for op in reversed(self.operators):
             op_inv = op.inverse()
             cir.operators.append(op_inv)
-            if encode and op in self.encoders:
+            if encode and id(op) in enc_ids:
                 cir.encoders.append(op_inv)
         cir.npara, cir.ndata = (self.npara, self.ndata) if encode else (self.npara + self.ndata, 0)
         cir.depth = self.depth.copy()

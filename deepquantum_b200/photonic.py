@@ -268,6 +268,28 @@ class _FockGate(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.op_state_tensor(x)
 
+    def _free_names(self) -> list:
+        """Names of the free parameters, in the order `inputs` lists them."""
+        if hasattr(self, '_free'):
+            return [self._free]
+        order = [nm for nm in ('r', 'kappa', 'theta', 'phi') if nm in self._buffers or nm in self._parameters]
+        return order[:self.npara]
+
+    def init_para(self, inputs: Any = None) -> None:
+        """Sets the free parameters from `inputs` (data encoding, reference photonic/gate.py `init_para`)."""
+        names = self._free_names()
+        if inputs is None:
+            return
+        vals = inputs if isinstance(inputs, torch.Tensor) else torch.as_tensor(inputs, dtype=torch.float)
+        vals = vals.reshape(-1)
+        assert vals.numel() == len(names), f'{self.name} takes {len(names)} parameter(s)'
+        for nm, v in zip(names, vals):
+            if nm in self._parameters:
+                with torch.no_grad():
+                    self._parameters[nm].copy_(v)
+            else:
+                self._buffers[nm] = v.to(self._buffers[nm].device)
+
     def extra_repr(self) -> str:
         return f'wires={self.wires}'
 
@@ -576,26 +598,45 @@ class QumodeCircuit(nn.Module):
         self.operators = nn.Sequential()
         self.state = None
         self.npara = 0
+        self.ndata = 0
+        self.encoders = []
 
-    def add(self, op: _FockGate) -> None:
+    def add(self, op: _FockGate, encode: bool = False) -> None:
         self.operators.append(op)
-        self.npara += op.npara
+        if encode:
+            assert not any(p.requires_grad for p in op.parameters()), 'an encoder gate cannot be trainable'
+            self.encoders.append(op)
+            self.ndata += op.npara
+        else:
+            self.npara += op.npara
+
+    def encode(self, data: Any) -> None:
+        """Routes `data` to the encoder gates in the order they were added (reference photonic/circuit.py:`encode`)."""
+        if data is None:
+            return
+        data = data if isinstance(data, torch.Tensor) else torch.as_tensor(data, dtype=torch.float)
+        assert data.ndim == 1, 'batched data is outside the accelerated Fock tensor path'
+        assert data.numel() >= self.ndata, 'The circuit needs more data'
+        count = 0
+        for op in self.encoders:
+            op.init_para(data[count:count + op.npara])
+            count += op.npara
 
     def ps(self, wires: int, inputs: Any = None, encode: bool = False) -> None:
-        self.add(PhaseShift(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+        self.add(PhaseShift(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode), encode=encode)
 
     def bs(self, wires: list[int], inputs: Any = None, encode: bool = False) -> None:
-        self.add(BeamSplitter(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+        self.add(BeamSplitter(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode), encode=encode)
 
     def s(self, wires: int, r: Any = None, theta: Any = None, encode: bool = False) -> None:
         inputs = None if r is None else [r, 0.0 if theta is None else theta]
-        self.add(Squeezing(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+        self.add(Squeezing(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode), encode=encode)
 
     # ---- the beamsplitter family, rotations and Kerr gates (reference photonic/circuit.py:2026-2245, 2471-2520,
     # 2628-2680); `mu` / `sigma` (the reference's gate-noise model) are accepted and must stay unset -------------
     def _one(self, cls, wires, inputs, encode, mu, sigma, **kw):
         assert mu is None and sigma is None, 'gate noise is outside the accelerated Fock tensor path'
-        self.add(cls(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode, **kw))
+        self.add(cls(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode, **kw), encode=encode)
 
     def mzi(self, wires, inputs=None, phi_first=True, encode=False, mu=None, sigma=None):
         self._one(MZI, wires, inputs, encode, mu, sigma, phi_first=phi_first)
@@ -642,7 +683,7 @@ class QumodeCircuit(nn.Module):
             inputs = None
         else:
             inputs = [torch.rand(1)[0] if r is None else r, 0.0 if theta is None else theta]
-        self.add(Displacement(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+        self.add(Displacement(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode), encode=encode)
 
     def s2(self, wires, r=None, theta=None, encode=False, mu=None, sigma=None):
         assert mu is None and sigma is None, 'gate noise is outside the accelerated Fock tensor path'
@@ -650,7 +691,7 @@ class QumodeCircuit(nn.Module):
             inputs = None
         else:
             inputs = [torch.rand(1)[0] if r is None else r, 0.0 if theta is None else theta]
-        self.add(Squeezing2(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode))
+        self.add(Squeezing2(inputs, self.nmode, wires, self.cutoff, requires_grad=inputs is None and not encode), encode=encode)
 
     def build_matrices(self, cdtype, device):
         """All Fock transformation matrices of the circuit: one batched evaluation per gate class (and variant)."""
@@ -669,8 +710,12 @@ class QumodeCircuit(nn.Module):
                 mats[i] = m[j]
         return mats
 
-    def forward(self, state: Any = None) -> torch.Tensor:
-        """Final Fock state tensor `[batch, cutoff, ..., cutoff]` (photonic/circuit.py:405-431)."""
+    def forward(self, data: Any = None, state: Any = None) -> torch.Tensor:
+        """Final Fock state tensor `[batch, cutoff, ..., cutoff]` (photonic/circuit.py:405-431: `forward(data,
+        state)`; 1-D `data` feeds the gates added with `encode=True`)."""
+        if isinstance(data, FockState) and state is None:   # forward(state) of the earlier signature
+            data, state = None, data
+        self.encode(data)
         x = self.init_state.state if state is None else (state.state if isinstance(state, FockState) else state)
         engine.require_cuda(x, 'the Fock state (move the circuit with cir.to("cuda"))')
         d, n = self.cutoff, self.nmode

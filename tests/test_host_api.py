@@ -254,3 +254,20 @@ def test_fock_transforms_with_exact_zero_entries():
     assert torch.allclose(s2[0], eye.to(s2.dtype), atol=1e-12)
     s2.abs().sum().backward()
     assert torch.isfinite(r.grad).all()
+
+
+def test_inverse_keeps_layer_encoders():
+    """`inverse(encode=True)` re-registers the member gates of an encoding LAYER (reference circuit.py:530-555):
+    the data of the inverse circuit reaches the same number of gates, in reversed order."""
+    cir = dq.QubitCircuit(3)
+    cir.rxlayer(encode=True)
+    cir.cnot(0, 1)
+    cir.ry(2, encode=True)
+    inv = cir.inverse(encode=True)
+    assert inv.ndata == 4 and len(inv.encoders) == 4
+    data = torch.tensor([0.1, 0.2, 0.3, 0.4])
+    inv.encode(data)
+    # reversed operators: ry(2), cnot, rx(2), rx(1), rx(0); encoders in that order take data[0..3]; inverse angles
+    assert type(inv.operators[0]).__name__ == 'Ry' and abs(float(inv.operators[0].theta) - 0.1) < 1e-7
+    thetas = [float(op.theta) for op in inv.operators[2:]]
+    assert np.allclose(thetas, [0.2, 0.3, 0.4], atol=1e-7)

@@ -85,6 +85,29 @@ def test_builder_conventions():
         cir.bs_rx([0, 1], 0.3, mu=0.0, sigma=0.1)
 
 
+def test_encoders_route_data_like_the_reference():
+    """`forward(data, state)` of the reference (photonic/circuit.py:405-431): 1-D data feeds the encoder gates in
+    the order they were added; trainable gates keep their parameters."""
+    cir = dq.QumodeCircuit(3, 'vac', cutoff=3)
+    cir.ps(0, encode=True)
+    cir.bs([0, 1])
+    cir.s(2, encode=True)
+    cir.bs_theta([1, 2], encode=True)
+    assert cir.ndata == 4 and cir.npara == 2 and len(cir.encoders) == 3
+    free = [float(cir.operators[1].theta), float(cir.operators[1].phi)]
+    cir.encode(torch.tensor([0.1, 0.2, 0.3, 0.4]))
+    assert abs(float(cir.operators[0].theta) - 0.1) < 1e-7
+    assert abs(float(cir.operators[2].r) - 0.2) < 1e-7 and abs(float(cir.operators[2].theta) - 0.3) < 1e-7
+    assert abs(float(cir.operators[3].theta) - 0.4) < 1e-7
+    assert abs(float(cir.operators[3].phi) - np.float32(np.pi / 2)) == 0
+    assert [float(cir.operators[1].theta), float(cir.operators[1].phi)] == free
+    mats = cir.build_matrices(torch.complex128, 'cpu')
+    ref = dq.photonic.PhaseShift(0.1, 3, 0, 3).update_matrix_state()
+    assert torch.allclose(mats[0], ref.to(torch.complex128), atol=1e-7)
+    with pytest.raises(AssertionError):
+        cir.encode(torch.tensor([0.1, 0.2]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('key', KEYS)
 @pytest.mark.parametrize('double', [True, False])

@@ -19,6 +19,7 @@ GATE_ROTATION = 16
 GATE_PHASE_SHIFT = 5          # 1-target diagonal gates: exactly diag(1, i^q), q = 1 (S), 2 (Z), 3 (S^dagger)
 GATE_PHASE_MASK = 3 << GATE_PHASE_SHIFT
 GATE_PHASE_S, GATE_PHASE_Z, GATE_PHASE_SDG = 1 << 5, 2 << 5, 3 << 5
+GATE_GRAD = 128   # the cotangent of this gate will be asked for (dense gates on >= 3 targets get their own pass)
 
 
 def conj_hint(hint: int) -> int:

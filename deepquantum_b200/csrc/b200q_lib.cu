@@ -290,7 +290,7 @@ template <typename Real>
 int launch_dense_pass(const b200q_pass_t& P, void* state, const void* mats, int n_qubits, int64_t batch, int64_t mbs,
                       cudaStream_t stream, bool flip_adjoint) {
   const b200q_op_t& op = P.ops[0];
-  if (sizeof(Real) == 4 && n_qubits >= 12 && dense_tc_enabled()) {   // complex64: tensor cores (b200q_dense_tc.cu)
+  if (sizeof(Real) == 4 && n_qubits >= 12 && op.k >= 4 && dense_tc_enabled()) {   // complex64: tensor cores (b200q_dense_tc.cu)
     int32_t tg[8];
     for (int j = 0; j < op.k; ++j) tg[j] = int32_t((op.dsel_glob[0] >> (8 * j)) & 0xff);
     const int adj = (((op.flags & B200Q_FLAG_ADJOINT) != 0) != flip_adjoint) ? 1 : 0;
@@ -331,6 +331,102 @@ int launch_dense_pass(const b200q_pass_t& P, void* state, const void* mats, int 
         reinterpret_cast<const cx<Real>*>(mats) + b0 * mbs, A, n_amps, mbs);
   }
   return cuda_err(cudaGetLastError(), "dense pass launch");
+}
+
+// Cotangent of the gate of a dense pass (reverse sweep, include/b200q.h "adjoint differentiation"):
+//   G[r][c] = sum over the groups whose controls are set of lambda[r, group] * conj(psi[c, group]),
+// psi already un-applied, lambda not yet.  A CTA stages kCotAmps amplitudes of both states per step, every thread
+// owns D * D / 256 entries (r, c): partial sums over the staged groups in the state's precision, carried in double
+// across steps, one atomicAdd per entry and CTA at the end (complex128 buffer laid out like the matrix buffer).
+constexpr int kCotAmps = 2048;
+template <typename Real>
+__global__ void __launch_bounds__(256)
+b200q_dense_cotangent_kernel(const cx<Real>* __restrict__ psi, const cx<Real>* __restrict__ lam, const DenseArgs A,
+                             uint64_t n_amps, double* __restrict__ grad) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int D = 1 << A.k, GP = kCotAmps >> A.k;
+  cx<Real>* xp = reinterpret_cast<cx<Real>*>(dsm);   // [GP][D + 1] psi   (+1: rows of one group on different banks)
+  cx<Real>* xl = xp + GP * (D + 1);                  // [GP][D + 1] lambda
+  const int n_ent = D * D, per = (n_ent + 255) / 256;   // <= 16 entries per thread
+  double acc_r[16], acc_i[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc_r[j] = acc_i[j] = 0.0;
+  const uint64_t n_groups = n_amps >> A.k;
+  for (uint64_t g0 = uint64_t(blockIdx.x) * GP; g0 < n_groups; g0 += uint64_t(gridDim.x) * GP) {
+    for (int i = threadIdx.x; i < GP * D; i += 256) {
+      const int gl = i >> A.k, r = i & (D - 1);
+      const uint64_t g = g0 + gl;
+      uint64_t base = g;
+      for (int j = 0; j < A.k; ++j)
+        base = ((base >> A.sorted[j]) << (A.sorted[j] + 1)) | (base & ((1ull << A.sorted[j]) - 1ull));
+      uint64_t roff = 0;
+      for (int j = 0; j < A.k; ++j)
+        if ((r >> j) & 1) roff |= 1ull << A.tbit[j];
+      cx<Real> vp, vl;
+      vp.x = vp.y = vl.x = vl.y = Real(0);
+      if (g < n_groups && (base & A.ctrl) == A.ctrl) { vp = psi[base | roff]; vl = lam[base | roff]; }
+      xp[gl * (D + 1) + r] = vp;
+      xl[gl * (D + 1) + r] = vl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j >= per) break;
+      const int e = threadIdx.x + j * 256;
+      if (e >= n_ent) break;
+      const int r = e >> A.k, c = e & (D - 1);
+      Real sr = Real(0), si = Real(0);
+      for (int gl = 0; gl < GP; ++gl) {
+        const cx<Real> l = xl[gl * (D + 1) + r], p = xp[gl * (D + 1) + c];
+        sr += l.x * p.x + l.y * p.y;     // l * conj(p)
+        si += l.y * p.x - l.x * p.y;
+      }
+      acc_r[j] += double(sr);
+      acc_i[j] += double(si);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j >= per) break;
+    const int e = threadIdx.x + j * 256;
+    if (e >= n_ent) break;
+    const int r = e >> A.k, c = e & (D - 1);
+    // stored matrix M with U = M^dagger (B200Q_FLAG_ADJOINT): cotangent of M = conjugate transpose of that of U
+    const int dst = A.adjoint ? c * D + r : r * D + c;
+    double* out = grad + 2 * (uint64_t(A.mat_src) + dst);
+    if (acc_r[j] != 0.0) atomicAdd(out, acc_r[j]);
+    if (acc_i[j] != 0.0) atomicAdd(out + 1, A.adjoint ? -acc_i[j] : acc_i[j]);
+  }
+}
+
+template <typename Real>
+int launch_dense_cotangent(const b200q_pass_t& P, const void* psi, const void* lam, void* grad, int n_qubits,
+                           cudaStream_t stream) {
+  const b200q_op_t& op = P.ops[0];
+  DenseArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.ctrl = op.ctrl_glob;
+  A.mat_src = op.mat_src;
+  A.n_qubits = n_qubits;
+  A.k = op.k;
+  A.adjoint = (op.flags & B200Q_FLAG_ADJOINT) ? 1 : 0;
+  for (int j = 0; j < A.k; ++j) A.tbit[j] = A.sorted[j] = uint8_t((op.dsel_glob[0] >> (8 * j)) & 0xff);
+  std::sort(A.sorted, A.sorted + A.k);
+  const int D = 1 << A.k, GP = kCotAmps >> A.k;
+  const size_t smem = size_t(2) * GP * (D + 1) * sizeof(cx<Real>);
+  auto kern = b200q_dense_cotangent_kernel<Real>;
+  int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "cudaFuncSetAttribute(dense cotangent)");
+  if (rc) return rc;
+  const uint64_t n_amps = 1ull << n_qubits, n_groups = n_amps >> A.k;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t want = (n_groups + GP - 1) / GP;
+  const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(sm_count(dev)) * 2));
+  kern<<<gx, 256, smem, stream>>>(reinterpret_cast<const cx<Real>*>(psi), reinterpret_cast<const cx<Real>*>(lam), A,
+                                  n_amps, reinterpret_cast<double*>(grad));
+  return cuda_err(cudaGetLastError(), "dense cotangent launch");
 }
 
 int launch_pass_any(const Plan& pl, const b200q_pass_t& P, void* state, const void* mats, int64_t batch,
@@ -953,10 +1049,16 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
   if (cb > 12) return set_err(B200Q_EUNSUPPORTED, "the adjoint sweep holds two tiles per CTA: plan with chunk_bits <= 12");
   for (int i = (int)p.passes.size() - 1; i >= 0; --i) {
     const b200q_pass_t& P = p.passes[i];
-    if (P.n_rounds == 0) {   // dense pass: un-applied on both states, no cotangent (as for every dense gate on > 2 targets)
-      if (need_grad_host && need_grad_host[P.ops[0].gate_id])
-        return set_err(B200Q_EUNSUPPORTED, "gradient of dense gates on more than 2 targets");
-      for (void* s : {psi, lambda}) {
+    if (P.n_rounds == 0) {   // dense pass: psi <- U^dagger psi, cotangent from (lambda, psi), lambda <- U^dagger lambda
+      const bool need = need_grad_host ? need_grad_host[P.ops[0].gate_id] != 0 : true;
+      for (int which = 0; which < 2; ++which) {
+        void* s = which == 0 ? psi : lambda;
+        if (which == 1 && need) {
+          rc = p.dtype == B200Q_C64
+                   ? launch_dense_cotangent<float>(P, psi, lambda, grad_out, p.n_qubits, (cudaStream_t)stream)
+                   : launch_dense_cotangent<double>(P, psi, lambda, grad_out, p.n_qubits, (cudaStream_t)stream);
+          if (rc) return rc;
+        }
         rc = p.dtype == B200Q_C64 ? launch_dense_pass<float>(P, s, matrices, p.n_qubits, 1, 0, (cudaStream_t)stream, true)
                                   : launch_dense_pass<double>(P, s, matrices, p.n_qubits, 1, 0, (cudaStream_t)stream, true);
         if (rc) return rc;
@@ -970,7 +1072,9 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
       const bool need = need_grad_host ? need_grad_host[op.gate_id] != 0 : true;
       if (!need) continue;
       if (op.kind == B200Q_OP_MATK && op.k > 2) {
-        if (need_grad_host) return set_err(B200Q_EUNSUPPORTED, "gradient of dense gates on more than 2 targets");
+        if (need_grad_host)
+          return set_err(B200Q_EUNSUPPORTED, "gradient of a dense gate on 3-4 targets inside a fused pass: plan the gate "
+                                             "with B200Q_GATE_GRAD (a pass of its own)");
         continue;
       }
       want |= 1ull << o;

@@ -149,6 +149,9 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         break;
       case B200Q_GATE_MAT:
         if (a.k == 1) { a.reg_kind = true; a.op_kind = B200Q_OP_MAT1; a.pool = 4; }
+        else if (a.k >= 3 && a.k <= B200Q_DENSE_MAX && (a.flags & B200Q_GATE_GRAD)) {
+          a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 0; a.big = true;   // cotangent wanted: own pass
+        }
         else if (a.k <= B200Q_MATK_MAX) { a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); }
         else if (a.k <= B200Q_DENSE_MAX) { a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 0; a.big = true; }
         else return fail("dense gates on more than 6 targets are not supported");
@@ -156,6 +159,9 @@ Plan* make_plan(int n_qubits, int dtype, const b200q_gate_t* gates, int n_gates,
         break;
       case B200Q_GATE_DIAG:
         if (a.k <= 2) { a.reg_kind = true; a.op_kind = B200Q_OP_DIAG; a.pool = 4; a.tmask = 0; a.dmask = tm | a.ctrl; }
+        else if (a.k <= B200Q_DENSE_MAX && (a.flags & B200Q_GATE_GRAD)) {
+          a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 0; a.big = true; a.tmask = tm; a.dmask = a.ctrl;
+        }
         else if (a.k <= B200Q_MATK_MAX) {
           a.reg_kind = false; a.op_kind = B200Q_OP_MATK; a.pool = 1 << (2 * a.k); a.tmask = tm; a.dmask = a.ctrl;
         } else if (a.k <= B200Q_DENSE_MAX) {

@@ -401,7 +401,8 @@ class ShardedProgram:
         m = torch.cat([mats] + extra) if extra else mats
         nxt = self.steps[si + 1] if si + 1 < len(self.steps) else None
         fused = fuse_exchange and nxt is not None and nxt[0] in ('swap', 'xperm')
-        if fused and any(g.n_targets > 4 and g.kind != L.GATE_X for g in structs):
+        if fused and any((g.n_targets > 4 or (g.n_targets > 2 and g.flags & L.GATE_GRAD)) and g.kind != L.GATE_X
+                         for g in structs):
             fused = False    # a dense gate on 5-6 targets is a pass of its own and cannot carry the exchange scatter:
             #                  the exchange then runs as a stand-alone (identity plan) exchange step
         key = (si, state.amps.dtype, fused)

@@ -134,6 +134,10 @@ class Lowering:
             block, idx = 'dyn', len(self.dynamic)
             self.dynamic.append(src)
         hint = getattr(src, '_hint', 0) if (kind in (L.GATE_MAT, L.GATE_DIAG) and len(wires) == 1) else 0
+        if (kind in (L.GATE_MAT, L.GATE_DIAG) and len(targets) >= 3 and block not in ('none', 'const')
+                and (getattr(src, 'requires_grad', False) or getattr(src, '_data_ref', None) is not None
+                     or getattr(src, '_batched', None) is not None)):
+            hint |= L.GATE_GRAD   # trainable / data-fed dense gate on >= 3 wires: own pass, full cotangent in the reverse sweep
         self.records.append((kind, tuple(targets), tuple(ctrl), bool(adjoint), block, idx, size, hint))
         self.sources.append(src if kind != L.GATE_X else None)
 

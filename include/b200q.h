@@ -60,6 +60,11 @@ extern "C" {
 #define B200Q_GATE_PHASE_Z (2 << B200Q_GATE_PHASE_SHIFT)
 #define B200Q_GATE_PHASE_SDG (3 << B200Q_GATE_PHASE_SHIFT)
 
+/* flags bit 7: b200q_adjoint_run will be asked for the cotangent of this gate (a parametrised UAnyGate / LatentGate /
+ * HamiltonianGate, gate.py:2745-2931).  Only matters for dense gates on 3 or more targets: they then get a pass of
+ * their own (like the gates on 5-6 targets), whose reverse step accumulates the full 2^k x 2^k cotangent. */
+#define B200Q_GATE_GRAD 128
+
 #define B200Q_MAX_TARGETS 6
 
 typedef struct b200q_gate {
@@ -179,7 +184,8 @@ int b200q_init_basis(void* state, int n_qubits, int dtype, int64_t batch, uint64
  *   lambda <- U_g^dagger lambda                (lambda enters as dL/d(final state), leaves as dL/d(initial))
  * `grad_out` is a ZEROED device buffer of complex128 laid out like the matrix buffer (same element
  * offsets, always double precision).  need_grad_host[g] == 0 skips gate g (NULL: accumulate all gates
- * the kernel supports: 1-target dense, diagonal, 2-target dense).  batch = 1. */
+ * the sweep supports: 1- and 2-target dense, diagonal, and every dense gate that has a pass of its own -- 5-6
+ * targets, or 3-4 targets planned with B200Q_GATE_GRAD).  batch = 1. */
 int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const void* matrices, void* grad_out,
                       const uint8_t* need_grad_host, void* stream);
 

@@ -24,6 +24,8 @@ Files written
   dist_adjoint.npz    the reference's own test circuit of the differentiable sharded expectation
                       (tests/test_circuit.py:87-139), dense autograd: expectation values and d/d(data), n = 4 and 6
   unitary.npz         QubitCircuit.get_unitary() of the all-gate-families circuit (5 qubits) and a random circuit
+  dense_grad.npz      trainable / data-fed dense blocks on 3 and 4 wires (HamiltonianGate, LatentGate, one controlled):
+                      loss and its reference-autograd gradient w.r.t. every parameter and the data, n = 6
 """
 import json
 import math
@@ -537,9 +539,62 @@ def unitary():
     np.savez_compressed(os.path.join(OUT, 'unitary.npz'), **out)
 
 
+def dense_grad_build(cir, h3):
+    """Trainable dense blocks on 3 and 4 wires between ordinary layers (shared with tests/test_gpu_parity.py)."""
+    cir.hlayer()
+    cir.hamiltonian(h3, wires=[0, 4, 2])                              # trainable evolution time, 8 x 8 matrix form
+    cir.rxlayer()
+    cir.latent(wires=[1, 3, 5])                                       # trainable 8 x 8 latent matrix
+    cir.cnot_ring()
+    cir.hamiltonian([[0.6, 'x1z2y3z4'], [-0.3, 'z1x4']], controls=0)  # 4 wires + a control, trainable time
+    cir.rylayer(encode=True)
+    cir.observable(0)
+    cir.observable(1, 'x')
+    cir.observable([2, 5], 'zy')
+    return cir
+
+
+def dense_grad():
+    out = {}
+    n = 6
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(8, 8, generator=g, dtype=torch.float64) + 1j * torch.randn(8, 8, generator=g, dtype=torch.float64)
+    h3 = (a + a.mH) / 2
+    cir = dense_grad_build(dq.QubitCircuit(n), h3)
+    cir.to(torch.double)
+    for i, op in enumerate(cir.operators):
+        for name, prm in op.named_parameters():
+            with torch.no_grad():
+                prm.copy_(torch.randn(prm.shape, generator=g, dtype=torch.float64).to(prm.dtype)
+                          if not prm.is_complex() else
+                          torch.randn(prm.shape, generator=g, dtype=torch.float64)
+                          + 1j * torch.randn(prm.shape, generator=g, dtype=torch.float64))
+            out[f'param/{i}/{name}'] = prm.detach().numpy().copy()
+    data = torch.tensor([0.31, 0.2, -0.4, 0.9, 1.3, -0.7], dtype=torch.float64, requires_grad=True)
+    state = cir(data=data)
+    exp = cir.expectation()
+    w = torch.tensor([1.0, -0.7, 0.45], dtype=torch.float64)
+    loss = (w * exp.reshape(-1)).sum()
+    loss.backward()
+    out['h3'] = h3.numpy()
+    out['data'] = data.detach().numpy()
+    out['weights'] = w.numpy()
+    out['state'] = state.detach().reshape(-1).numpy()
+    out['expectation'] = exp.detach().reshape(-1).numpy()
+    out['loss'] = loss.detach().numpy()
+    out['grad/data'] = data.grad.numpy()
+    for i, op in enumerate(cir.operators):
+        for name, prm in op.named_parameters():
+            out[f'grad/{i}/{name}'] = prm.grad.resolve_conj().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'dense_grad.npz'), **out)
+    print('dense_grad', float(loss), data.grad.tolist(), [k for k in out if k.startswith('grad/')])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3', 'fock2',
-                             'dist_adjoint', 'unitary']
+                             'dist_adjoint', 'unitary', 'dense_grad']
+    if 'dense_grad' in which:
+        dense_grad()
     if 'dist_adjoint' in which:
         dist_adjoint()
     if 'unitary' in which:

@@ -24,9 +24,12 @@ def classify(matrix):
 
 
 def lower_ops(ops, nqubit, dtype=np.complex128, hints=True):
-    """(matrix, wires, controls) triples -> (GateStruct array, flat matrix buffer)."""
+    """(matrix, wires, controls[, {'grad': bool, 'adjoint': bool}]) tuples -> (GateStruct array, flat matrix buffer).
+    'adjoint': the STORED matrix is `matrix`, the gate applied is its conjugate transpose; 'grad': B200Q_GATE_GRAD."""
     gates, mats, off = [], [], 0
-    for matrix, wires, controls in ops:
+    for entry in ops:
+        matrix, wires, controls = entry[:3]
+        extra = entry[3] if len(entry) > 3 else {}
         m = np.asarray(matrix, dtype=dtype)
         kind = classify(m)
         k = len(wires)
@@ -46,7 +49,9 @@ def lower_ops(ops, nqubit, dtype=np.complex128, hints=True):
                     hint |= L.GATE_ROTATION
         if kind == L.GATE_DIAG and k == 1 and hints and m[0, 0] == 1 and m[0, 1] == 0 and m[1, 0] == 0:
             hint = {1j: L.GATE_PHASE_S, -1: L.GATE_PHASE_Z, -1j: L.GATE_PHASE_SDG}.get(complex(m[1, 1]), 0)
-        gates.append(L.make_gate(kind, targets, ctr, off, False, hint))
+        if extra.get('grad'):
+            hint |= L.GATE_GRAD
+        gates.append(L.make_gate(kind, targets, ctr, off, bool(extra.get('adjoint')), hint))
         mats.append(m.reshape(-1))
         off += m.size
     arr = (L.GateStruct * max(1, len(gates)))(*gates)

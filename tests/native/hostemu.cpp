@@ -106,6 +106,39 @@ void run_pass_adjoint(const Plan& pl, const b200q_pass_t& P, void* psi_v, void* 
   constexpr int VS = Traits<Real>::VS;
   const int cb = pl.opt.chunk_bits;
   const int nthreads = 1 << (cb - B200Q_REG_CHUNK_BITS);
+  if (P.n_rounds == 0) {   // dense pass: the semantics of b200q_adjoint_run's dense branch, plain loops
+    const b200q_op_t& op = P.ops[0];
+    const int K = op.k, D = 1 << K;
+    const bool adj = (op.flags & B200Q_FLAG_ADJOINT) != 0;
+    const uint64_t n_amps = 1ull << pl.n_qubits;
+    b200q_pass_t Q = P;
+    Q.ops[0].flags ^= B200Q_FLAG_ADJOINT;
+    run_pass<Real>(pl, Q, psi_v, mats_v, 1, 0);
+    if (!need || need[op.gate_id]) {
+      const cx<Real>* psi = reinterpret_cast<const cx<Real>*>(psi_v);
+      const cx<Real>* lam = reinterpret_cast<const cx<Real>*>(lam_v);
+      uint64_t tm = 0, off[64];
+      for (int r = 0; r < D; ++r) {
+        off[r] = 0;
+        for (int j = 0; j < K; ++j)
+          if ((r >> j) & 1) off[r] |= 1ull << ((op.dsel_glob[0] >> (8 * j)) & 0xff);
+      }
+      tm = off[D - 1];
+      for (uint64_t base = 0; base < n_amps; ++base) {
+        if ((base & tm) || (base & op.ctrl_glob) != op.ctrl_glob) continue;
+        for (int r = 0; r < D; ++r)
+          for (int c = 0; c < D; ++c) {
+            const cx<Real> l = lam[base | off[r]], q = psi[base | off[c]];
+            const double re = double(l.x) * q.x + double(l.y) * q.y, im = double(l.y) * q.x - double(l.x) * q.y;
+            const int dst = adj ? c * D + r : r * D + c;
+            grad[2 * (uint64_t(op.mat_src) + dst)] += re;
+            grad[2 * (uint64_t(op.mat_src) + dst) + 1] += adj ? -im : im;
+          }
+      }
+    }
+    run_pass<Real>(pl, Q, lam_v, mats_v, 1, 0);
+    return;
+  }
   std::vector<chunk> tp(size_t(1) << cb), tl(size_t(1) << cb);
   std::vector<cx<Real>> pool(B200Q_POOL_MAX);
   std::vector<double> acc(size_t(B200Q_MAX_OPS) * B200Q_ACC_PER_OP), gfac(B200Q_MAX_OPS);

@@ -365,6 +365,21 @@ def test_sharded_two_gpus():
     assert 'SHARDED_OK' in out.stdout
 
 
+def test_sharded_fock_two_gpus():
+    """The sharded Fock tensor path (reference photonic/distributed.py:65-78) over NCCL on 2 GPUs
+    against the host oracle and the single-GPU circuit (skipped on a 1-GPU box)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29573', os.path.join(root, 'tests', 'dist_fock_gpu_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'FOCK_SHARDED_OK' in out.stdout, out.stdout[-2000:]
+
+
 @pytest.mark.parametrize('structured', [True, False])
 @pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
 def test_structured_and_general_op_codes(cdtype, structured):
@@ -582,3 +597,75 @@ def test_dense_block_on_tensor_cores(k, adjoint, with_ctrl):
     out = st.cpu().numpy().astype(np.complex128)
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     assert err < 1e-6, err
+
+
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_trainable_dense_blocks_gradient_matches_reference_autograd(rdtype):
+    """Loss and gradient through trainable dense blocks on 3 and 4 wires (HamiltonianGate in matrix and Pauli-sum
+    form, one controlled, and a LatentGate; reference gate.py:2793-3024) against the reference's own autograd
+    (tests/golden/dense_grad.npz): such gates get a pass of their own and the reverse sweep accumulates their full
+    2^k x 2^k cotangent (b200q_dense_cotangent_kernel)."""
+    from test_host_api import _dense_grad_circuit
+    g = _golden('dense_grad.npz')
+    cir = _dense_grad_circuit(g)
+    cir.to('cuda', rdtype)
+    data = torch.tensor(g['data'], device='cuda', dtype=rdtype, requires_grad=True)
+    state = cir(data)
+    tol = 1e-9 if rdtype == torch.float64 else 2e-5
+    np.testing.assert_allclose(state.detach().reshape(-1).cpu().numpy(), g['state'], atol=tol)
+    exp = cir.expectation()
+    np.testing.assert_allclose(exp.detach().reshape(-1).cpu().numpy(), g['expectation'], atol=tol)
+    loss = (torch.tensor(g['weights'], device='cuda', dtype=rdtype) * exp.reshape(-1)).sum()
+    loss.backward()
+    # the float32-rounded Hadamard of the reference bounds the accuracy of ANY adjoint-method gradient at ~1e-6
+    gtol = 2e-6 if rdtype == torch.float64 else 2e-4
+    np.testing.assert_allclose(data.grad.cpu().numpy(), g['grad/data'], atol=gtol)
+    checked = 0
+    for key in g.files:
+        if key.startswith('grad/') and key != 'grad/data':
+            _, i, name = key.split('/')
+            got = getattr(cir.operators[int(i)], name).grad
+            assert got is not None, key
+            np.testing.assert_allclose(got.cpu().numpy(), g[key], atol=gtol, err_msg=key)
+            checked += 1
+    assert checked == 9
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_reverse_sweep_dense_blocks_cabi(cdtype):
+    """b200q_adjoint_run on a 13-qubit plan with trainable dense gates on 3, 4 and 5 wires (one controlled, one stored
+    as its adjoint): un-computed state, input cotangent and the full 2^k x 2^k cotangents against PyTorch autograd
+    through the CPU port of the reference contraction (the case of tests/test_hostemu.py, here on the device; for
+    complex64 the 4- and 5-wire blocks are un-applied by the tensor-core kernel)."""
+    import ctypes as C
+
+    from test_hostemu import _dense_grad_case
+    n = 13
+    ops, psi0, psi_f, lam_f, x0_grad, mgrads = _dense_grad_case(n, np.random.default_rng(12))
+    need = [1 if (len(e) > 3 and e[3].get('grad')) or len(e[1]) == 1 else 0 for e in ops]
+    need = [0 if np.array_equal(np.asarray(e[0]), gates_np.X) else v for e, v in zip(ops, need)]
+    arr, ng, mats = lower_ops(ops, n, cdtype)
+    tdt = torch.complex64 if cdtype == np.complex64 else torch.complex128
+    plan = engine.FusedPlan(n, tdt, list(arr)[:ng], chunk_bits=11)
+    psi = torch.tensor(psi_f, dtype=tdt, device='cuda').contiguous()
+    lam = torch.tensor(lam_f, dtype=tdt, device='cuda').contiguous()
+    m = torch.tensor(mats, device='cuda')
+    grad = torch.zeros(m.numel(), dtype=torch.complex128, device='cuda')
+    need_c = (C.c_uint8 * len(need))(*need)
+    lib = L.load()
+    L.check(lib.b200q_adjoint_run(plan._h, psi.data_ptr(), lam.data_ptr(), m.data_ptr(), grad.data_ptr(), need_c,
+                                  engine._stream(psi)))
+    torch.cuda.synchronize()
+    tol = 1e-10 if cdtype == np.complex128 else 3e-4
+    assert np.linalg.norm(psi.cpu().numpy() - psi0) < (1e-10 if cdtype == np.complex128 else 1e-4)
+    assert np.linalg.norm(lam.cpu().numpy() - x0_grad) / np.linalg.norm(x0_grad) < tol
+    grad = grad.cpu().numpy()
+    off, checked = 0, 0
+    for e, ref, nd in zip(ops, mgrads, need):
+        mm = np.asarray(e[0])
+        if nd and len(e[1]) >= 3:
+            gq = grad[off:off + mm.size].reshape(mm.shape)
+            assert np.abs(gq - ref).max() / max(1.0, np.abs(ref).max()) < tol, (e[1], e[2])
+            checked += 1
+        off += mm.size
+    assert checked == 4

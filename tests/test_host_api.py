@@ -271,3 +271,43 @@ def test_inverse_keeps_layer_encoders():
     assert type(inv.operators[0]).__name__ == 'Ry' and abs(float(inv.operators[0].theta) - 0.1) < 1e-7
     thetas = [float(op.theta) for op in inv.operators[2:]]
     assert np.allclose(thetas, [0.2, 0.3, 0.4], atol=1e-7)
+
+
+def _dense_grad_circuit(g):
+    """The circuit of tests/golden/dense_grad.npz (oracle/make_golden.py `dense_grad_build`), parameters from the
+    fixture."""
+    n = 6
+    cir = dq.QubitCircuit(n)
+    cir.hlayer()
+    cir.hamiltonian(torch.tensor(g['h3']), wires=[0, 4, 2])
+    cir.rxlayer()
+    cir.latent(wires=[1, 3, 5])
+    cir.cnot_ring()
+    cir.hamiltonian([[0.6, 'x1z2y3z4'], [-0.3, 'z1x4']], controls=0)
+    cir.rylayer(encode=True)
+    cir.observable(0)
+    cir.observable(1, 'x')
+    cir.observable([2, 5], 'zy')
+    cir.to(torch.double)
+    for key in g.files:
+        if key.startswith('param/'):
+            _, i, name = key.split('/')
+            with torch.no_grad():
+                getattr(cir.operators[int(i)], name).copy_(torch.tensor(g[key]))
+    return cir
+
+
+def test_trainable_dense_blocks_are_planned_for_their_cotangent():
+    """Trainable dense gates on 3-4 wires carry B200Q_GATE_GRAD (a pass of their own whose reverse step accumulates
+    the full cotangent); the forward result does not change (CPU-stepped kernel body against the reference state)."""
+    from deepquantum_b200 import _lib as L
+    g = np.load(os.path.join(GOLDEN, 'dense_grad.npz'))
+    cir = _dense_grad_circuit(g)
+    cir.encode(torch.tensor(g['data']))
+    prog = cir._get_program()
+    flagged = [(s.n_targets, bool(s.flags & L.GATE_GRAD)) for s in prog.structs if s.n_targets >= 3]
+    assert flagged == [(3, True), (3, True), (4, True)]
+    assert not any(s.flags & L.GATE_GRAD for s in prog.structs if s.n_targets < 3)
+    out, stats = emu_run_program(prog, 6, np.complex128)
+    assert np.linalg.norm(out[0] - g['state']) < 1e-10
+    assert stats['direct'] >= 3

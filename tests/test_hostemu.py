@@ -450,3 +450,66 @@ def test_dense_gates_on_five_and_six_targets(cdtype):
     err = np.linalg.norm(out[0] - ref) / np.linalg.norm(ref)
     assert err < (1e-12 if cdtype == np.complex128 else 5e-6), (err, stats)
     assert stats['direct'] >= 3
+
+
+def _dense_grad_case(n, rng):
+    """Ops (with trainable dense gates on 3, 4 and 5 wires, one controlled, one stored as its adjoint), a random
+    input state and the autograd reference: (ops, psi0, psi_final, lam_final, x0.grad, [matrix grads])."""
+    import torch
+
+    import torch_port
+
+    def rand_u(k):
+        q, _ = np.linalg.qr(rng.normal(size=(2**k, 2**k)) + 1j * rng.normal(size=(2**k, 2**k)))
+        return q
+
+    hmat = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2.0)
+    ops = [(hmat, [w], []) for w in range(n)]
+    ops.append((rand_u(3), [1, n - 1, 4], [], {'grad': True}))
+    ops += [(gates_np.rx(0.3 + w), [w], []) for w in range(n)]
+    ops.append((rand_u(4), [n - 2, 0, 5, 2], [7], {'grad': True}))
+    ops.append((gates_np.X, [2], [9]))
+    ops.append((rand_u(3), [3, 6, 8], [], {'grad': True, 'adjoint': True}))
+    ops.append((rand_u(5), [0, n - 1, 3, 7, 5], [], {'grad': True}))
+    ops.append((rand_u(3), [2, 3, 4], []))          # no cotangent wanted: stays inside a fused pass
+    ops += [(gates_np.ry(0.1 * w + 0.2), [w], [(w + 1) % n]) for w in range(0, n, 3)]
+    psi0 = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    psi0 /= np.linalg.norm(psi0)
+    wvec = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    diag = rng.normal(size=2**n)
+    tm = [torch.tensor(np.asarray(e[0], dtype=np.complex128), requires_grad=True) for e in ops]
+    x0 = torch.tensor(psi0, requires_grad=True)
+    x = x0.reshape([1] + [2] * n)
+    for e, t in zip(ops, tm):
+        u = t.conj().transpose(0, 1) if (len(e) > 3 and e[3].get('adjoint')) else t
+        x = torch_port.evolve_state_controlled(x, u, n, e[1], e[2]) if e[2] else torch_port.evolve_state(x, u, n, e[1])
+    psi = x.reshape(-1)
+    loss = (torch.tensor(wvec).conj() * psi).sum().real + (torch.tensor(diag) * (psi.real**2 + psi.imag**2)).sum()
+    loss.backward()
+    lam_final = wvec + 2 * diag * psi.detach().numpy()
+    return ops, psi0, psi.detach().numpy(), lam_final, x0.grad.numpy(), [t.grad.resolve_conj().numpy() for t in tm]
+
+
+@pytest.mark.parametrize('cdtype', [np.complex128, np.complex64])
+def test_adjoint_sweep_dense_gates_on_three_to_five_targets(cdtype):
+    """Cotangents of trainable dense gates on 3-5 wires (UAnyGate / LatentGate / HamiltonianGate with requires_grad,
+    reference gate.py:2745-2931; the reference differentiates them by autograd): planned with B200Q_GATE_GRAD they
+    get a pass of their own whose reverse step accumulates the full 2^k x 2^k cotangent."""
+    from helpers import emu_adjoint
+    n = 13
+    ops, psi0, psi_f, lam_f, x0_grad, mgrads = _dense_grad_case(n, np.random.default_rng(12))
+    need = [1 if (len(e) > 3 and e[3].get('grad')) or len(e[1]) == 1 else 0 for e in ops]
+    need = [0 if np.array_equal(np.asarray(e[0]), gates_np.X) else v for e, v in zip(ops, need)]
+    psi_in, lam_in, grad = emu_adjoint(ops, n, cdtype, psi_f, lam_f, chunk_bits=11, need=need)
+    tol = 1e-10 if cdtype == np.complex128 else 3e-4
+    assert np.linalg.norm(psi_in - psi0) < (1e-10 if cdtype == np.complex128 else 1e-4)
+    assert np.linalg.norm(lam_in - x0_grad) / np.linalg.norm(x0_grad) < tol
+    off, checked = 0, 0
+    for e, ref, nd in zip(ops, mgrads, need):
+        m = np.asarray(e[0])
+        if nd and len(e[1]) >= 3:
+            g = grad[off:off + m.size].reshape(m.shape)
+            assert np.abs(g - ref).max() / max(1.0, np.abs(ref).max()) < tol, (e[1], e[2])
+            checked += 1
+        off += m.size
+    assert checked == 4

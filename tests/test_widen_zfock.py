@@ -200,3 +200,24 @@ def test_fused_fock_full_size_c5_matches_per_gate_kernel():
     err = float((out - ref).norm() / ref.norm())
     assert err < 2e-6, err
     assert abs(float((out.real**2 + out.imag**2).sum()) - 1) < 1e-3     # truncated Fock space: squeezing leaks a little
+    # Size-independent physics of the circuit, checked on all 10^8 amplitudes against HOST arithmetic: the squeezers
+    # create photons in pairs and every (truncated) beamsplitter matrix is block-diagonal in the photon number of its
+    # two modes, complete -- hence unitary -- for sectors of at most cutoff - 1 photons.  So (a) no amplitude with an
+    # odd total photon number, and (b) the distribution P(N) for N <= 9 after the whole mesh equals the convolution of
+    # the single-mode squeezed-vacuum distributions (from the same 10 x 10 squeezer matrices, on the host).
+    d, n = 10, 8
+    dig = torch.arange(d, device='cuda')
+    total = torch.zeros([d] * n, dtype=torch.int64, device='cuda')
+    for m in range(n):
+        shape = [1] * n
+        shape[m] = d
+        total = total + dig.reshape(shape)
+    prob = (ref.real.double()**2 + ref.imag.double()**2)
+    p_n = torch.zeros(n * (d - 1) + 1, dtype=torch.float64, device='cuda').index_add_(0, total.reshape(-1), prob).cpu().numpy()
+    assert p_n[1::2].max() < 1e-12
+    mats = cir.build_matrices(torch.complex128, 'cuda')
+    conv = np.ones(1)
+    for op, mtx in zip(cir.operators, mats):
+        if len(op.wires) == 1:
+            conv = np.convolve(conv, np.abs(mtx.cpu().numpy()[:, 0])**2)
+    assert np.abs(p_n[:d] - conv[:d]).max() < 2e-6, (p_n[:d], conv[:d])

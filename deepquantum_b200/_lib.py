@@ -19,6 +19,7 @@ GATE_ROTATION = 16
 GATE_PHASE_SHIFT = 5          # 1-target diagonal gates: exactly diag(1, i^q), q = 1 (S), 2 (Z), 3 (S^dagger)
 GATE_PHASE_MASK = 3 << GATE_PHASE_SHIFT
 GATE_PHASE_S, GATE_PHASE_Z, GATE_PHASE_SDG = 1 << 5, 2 << 5, 3 << 5
+QUDIT_GENERAL, QUDIT_DIAG, QUDIT_DENSE1, QUDIT_NUMBER, QUDIT_DIFFERENCE = 0, 1, 2, 3, 4
 GATE_GRAD = 128   # the cotangent of this gate will be asked for (dense gates on >= 3 targets get their own pass)
 
 
@@ -103,6 +104,8 @@ _SIGNATURES = {
     'b200q_init_basis': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'b200q_adjoint_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_uint8), C.c_void_p]),
+    'b200q_qudit_apply_structured': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
+                                               C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     'b200q_qudit_apply': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                     C.c_int64, C.c_void_p]),
     'b200q_qudit_fused': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,

@@ -22,6 +22,7 @@ SOURCES = {
     'b200q_lib.cu': _COMMON + ['b200q_tile_body.h', 'b200q_jit.h', 'b200q_codegen.h'],
     'b200q_qudit.cu': ['b200q_qudit_geom.h'],
     'b200q_qudit_fused.cu': [],
+    'b200q_qudit_sector.cu': ['b200q_qudit_geom.h'],
     'b200q_dense_tc.cu': [],
     'b200q_sample.cu': [],
     'b200q_planner.cpp': _COMMON,

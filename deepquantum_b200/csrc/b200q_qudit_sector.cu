@@ -1,0 +1,397 @@
+// Structured qudit (Fock tensor) gates: evolve_state(state, matrix, nmode, wires, qudit = cutoff) as called by the
+// photonic back-end (reference photonic/operation.py:142-146 -> qmath.py:485-506) for gate CLASSES whose Fock matrix
+// has a known block structure (never decided from the values):
+//
+//   NUMBER      two-mode gates that conserve the photon number i + j of their modes -- the whole beamsplitter family
+//               (photonic/gate.py:202-1012) and the cross-Kerr gate: the d^2 x d^2 matrix is block-diagonal over the
+//               2d - 1 sectors i + j = s, block sizes 1, 2, ..., d, ..., 2, 1 (6.7 % of the entries at cutoff 10);
+//   DIFFERENCE  two-mode squeezing (photonic/gate.py:1157-1333) conserves i - j: same sector sizes along the other diagonal;
+//   DENSE1      one-mode gates (squeezer, displacement): one sector, the d x d matrix;
+//   DIAG        phase shifter, Kerr, cross-Kerr: one multiplication per amplitude.
+//
+// The members of a sector of one fibre (fixed digits of all other modes) lie on a line in memory,
+// base + t * step, t = 0 .. m-1.  A THREAD owns one sector of one fibre at a time: it loads the m amplitudes into
+// registers, multiplies by the m x m block (broadcast reads of the packed blocks from shared memory, packed f32x2
+// FMAs) and stores the m results in place -- no shared-memory staging of amplitudes, no barrier, no index table,
+// ~30 instructions per amplitude against ~260 of the generic ELL kernel (b200q_qudit.cu), which stays the path for
+// unstructured matrices.  The 32 lanes of a warp hold 32 consecutive fibres, so that every load / store of a warp is
+// one contiguous run of 32 amplitudes whenever the lowest mode is not a target; a warp walks all sectors of its fibres,
+// so lines are re-touched by the same warp (L1) when it is.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/b200q.h"
+#include "b200q_qudit_geom.h"
+
+namespace b200q {
+int set_err(int code, const std::string& msg);
+int cuda_err(cudaError_t e, const char* what);
+}  // namespace b200q
+using b200q::cuda_err;
+using b200q::set_err;
+
+namespace {
+
+constexpr int kMaxSecD = 16;
+constexpr int kMaxSectors = 2 * kMaxSecD - 1;
+constexpr int kSecThreads = 256;
+
+template <typename Real> struct cxs { Real x, y; };
+
+struct SectorTab {
+  int32_t n_sectors, total_w, d, k, dj;
+  int64_t S0, S1, step;       // strides of the digits (i, j) of the matrix index r = i * d + j (k = 1: only i), member step
+  struct Sec { uint8_t i0, j0, m, mp; uint32_t woff; } s[kMaxSectors];
+};
+
+// sectors of a structure; returns 0 if the structure / size is not handled here
+int make_sectors(int structure, int d, int k, int64_t S0, int64_t S1, SectorTab* T) {
+  std::memset(T, 0, sizeof *T);
+  T->d = d; T->k = k; T->S0 = S0; T->S1 = S1;
+  if (d > kMaxSecD) return 0;
+  auto add = [&](int i0, int j0, int m) {
+    SectorTab::Sec& e = T->s[T->n_sectors++];
+    e.i0 = (uint8_t)i0; e.j0 = (uint8_t)j0; e.m = (uint8_t)m; e.mp = (uint8_t)((m + 1) & ~1);
+    e.woff = (uint32_t)T->total_w;
+    T->total_w += m * e.mp;
+  };
+  if (structure == B200Q_QUDIT_DENSE1 && k == 1) {
+    T->dj = 0; T->step = S0;
+    add(0, 0, d);
+  } else if (structure == B200Q_QUDIT_NUMBER && k == 2) {
+    T->dj = -1; T->step = S0 - S1;
+    for (int s = 0; s <= 2 * d - 2; ++s) {
+      const int i0 = s < d ? 0 : s - d + 1, i1 = s < d ? s : d - 1;
+      add(i0, s - i0, i1 - i0 + 1);
+    }
+  } else if (structure == B200Q_QUDIT_DIFFERENCE && k == 2) {
+    T->dj = 1; T->step = S0 + S1;
+    for (int q = -(d - 1); q <= d - 1; ++q) {
+      if (q >= 0) add(q, 0, d - q); else add(0, -q, d + q);
+    }
+  } else {
+    return 0;
+  }
+  return 1;
+}
+
+// packed blocks: W[woff + r * mp + c] = M[row(r)][row(c)], row(t) = matrix index of member t of the sector
+template <typename Real>
+__global__ void pack_blocks_kernel(const cxs<Real>* __restrict__ m, const SectorTab T, cxs<Real>* __restrict__ out) {
+  const int D = T.k == 2 ? T.d * T.d : T.d;
+  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < T.total_w; e += blockDim.x * gridDim.x) {
+    int s = 0;
+    while (s + 1 < T.n_sectors && (uint32_t)e >= T.s[s + 1].woff) ++s;
+    const int local = e - (int)T.s[s].woff, r = local / T.s[s].mp, c = local % T.s[s].mp;
+    cxs<Real> v; v.x = v.y = Real(0);
+    if (c < T.s[s].m) {
+      const int ir = T.s[s].i0 + r, jr = T.s[s].j0 + T.dj * r, ic = T.s[s].i0 + c, jc = T.s[s].j0 + T.dj * c;
+      const int row = T.k == 2 ? ir * T.d + jr : ir, col = T.k == 2 ? ic * T.d + jc : ic;
+      v = m[row * D + col];
+    }
+    out[e] = v;
+  }
+}
+
+// ---- one sector of one fibre in registers ---------------------------------------------------------------------
+template <typename Real, int M> struct SectorOp;
+
+// acc += (w, w) * x on a packed pair (ptxas folds the broadcast into the FFMA2 operand form)
+__device__ __forceinline__ void fma_bc(unsigned long long& acc, float w, unsigned long long x) {
+  unsigned long long ww;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(x));
+}
+
+template <int M> struct SectorOp<float, M> {
+  static __device__ __forceinline__ void run(cxs<float>* p, long long step, const cxs<float>* W) {
+    constexpr int MP = (M + 1) & ~1;
+    unsigned long long x[M];
+#pragma unroll
+    for (int t = 0; t < M; ++t) x[t] = *reinterpret_cast<const unsigned long long*>(p + t * step);
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      unsigned long long a1 = 0ull, a2 = 0ull;   // sum w.re * x, sum w.im * x (packed pairs)
+#pragma unroll
+      for (int c = 0; c < M; c += 2) {
+        const float4 w2 = *reinterpret_cast<const float4*>(W + r * MP + c);   // two weights, 16-byte aligned (MP even)
+        fma_bc(a1, w2.x, x[c]);
+        fma_bc(a2, w2.y, x[c]);
+        if (c + 1 < M) {
+          fma_bc(a1, w2.z, x[c + 1]);
+          fma_bc(a2, w2.w, x[c + 1]);
+        }
+      }
+      float r1, i1, r2, i2;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(r1), "=f"(i1) : "l"(a1));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(r2), "=f"(i2) : "l"(a2));
+      cxs<float> y; y.x = r1 - i2; y.y = i1 + r2;
+      p[r * step] = y;
+    }
+  }
+};
+
+template <int M> struct SectorOp<double, M> {
+  static __device__ __forceinline__ void run(cxs<double>* p, long long step, const cxs<double>* W) {
+    constexpr int MP = (M + 1) & ~1;
+    double2 x[M];
+#pragma unroll
+    for (int t = 0; t < M; ++t) x[t] = *reinterpret_cast<const double2*>(p + t * step);
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      double yr = 0.0, yi = 0.0;
+#pragma unroll
+      for (int c = 0; c < M; ++c) {
+        const double2 w = *reinterpret_cast<const double2*>(W + r * MP + c);
+        yr = fma(w.x, x[c].x, yr); yr = fma(-w.y, x[c].y, yr);
+        yi = fma(w.x, x[c].y, yi); yi = fma(w.y, x[c].x, yi);
+      }
+      *reinterpret_cast<double2*>(p + r * step) = make_double2(yr, yi);
+    }
+  }
+};
+
+template <typename Real, int MAXM, int M>
+__device__ __forceinline__ void run_if(cxs<Real>* p, long long step, const cxs<Real>* W) {
+  if constexpr (M <= MAXM) SectorOp<Real, M>::run(p, step, W);
+}
+
+template <typename Real, int MAXM>
+__device__ __forceinline__ void run_sector(int m, cxs<Real>* p, long long step, const cxs<Real>* w) {
+  switch (m) {
+    case 1: run_if<Real, MAXM, 1>(p, step, w); break;
+    case 2: run_if<Real, MAXM, 2>(p, step, w); break;
+    case 3: run_if<Real, MAXM, 3>(p, step, w); break;
+    case 4: run_if<Real, MAXM, 4>(p, step, w); break;
+    case 5: run_if<Real, MAXM, 5>(p, step, w); break;
+    case 6: run_if<Real, MAXM, 6>(p, step, w); break;
+    case 7: run_if<Real, MAXM, 7>(p, step, w); break;
+    case 8: run_if<Real, MAXM, 8>(p, step, w); break;
+    case 9: run_if<Real, MAXM, 9>(p, step, w); break;
+    case 10: run_if<Real, MAXM, 10>(p, step, w); break;
+    case 11: run_if<Real, MAXM, 11>(p, step, w); break;
+    case 12: run_if<Real, MAXM, 12>(p, step, w); break;
+    case 13: run_if<Real, MAXM, 13>(p, step, w); break;
+    case 14: run_if<Real, MAXM, 14>(p, step, w); break;
+    case 15: run_if<Real, MAXM, 15>(p, step, w); break;
+    case 16: run_if<Real, MAXM, 16>(p, step, w); break;
+    default: break;
+  }
+}
+
+template <typename Real, int MAXM>
+__global__ void __launch_bounds__(kSecThreads)
+qudit_sector_kernel(cxs<Real>* __restrict__ state, const __grid_constant__ SectorTab T, const QuditGeom g,
+                    const cxs<Real>* __restrict__ wpacked) {
+  extern __shared__ __align__(16) unsigned char sec_smem[];
+  cxs<Real>* W = reinterpret_cast<cxs<Real>*>(sec_smem);
+  for (int e = threadIdx.x; e < T.total_w; e += kSecThreads) W[e] = wpacked[e];
+  __syncthreads();
+  const long long f = (long long)blockIdx.x * kSecThreads + threadIdx.x;   // fibre: lanes = consecutive fibres
+  if (f >= g.n_rest) return;
+  cxs<Real>* base = state + (long long)blockIdx.y * g.state_size + expand_rest(g, f);
+  for (int s = 0; s < T.n_sectors; ++s) {
+    cxs<Real>* p = base + (long long)T.s[s].i0 * T.S0 + (long long)T.s[s].j0 * T.S1;
+    const cxs<Real>* w = W + T.s[s].woff;
+    run_sector<Real, MAXM>(T.s[s].m, p, T.step, w);   // uniform over the grid: every thread is in the same sector
+  }
+}
+
+// Staged variant for gates that touch the LOWEST mode (stride 1): there consecutive fibres are d (or d^2) amplitudes
+// apart and a warp's direct accesses would spread over 32 lines each.  A CTA copies F consecutive fibres (runs of d
+// contiguous amplitudes; one contiguous block when both targets are the last two modes) into shared memory, its threads
+// -- (fibre, sector class q of Q) -- run the same register blocks on the shared copy, and the block is written back.
+struct StagedCfg { int32_t F, Q, pitch; };
+
+template <typename Real, int MAXM>
+__global__ void __launch_bounds__(kSecThreads)
+qudit_sector_staged_kernel(cxs<Real>* __restrict__ state, const __grid_constant__ SectorTab T, const QuditGeom g,
+                           const cxs<Real>* __restrict__ wpacked, const StagedCfg cfg) {
+  extern __shared__ __align__(16) unsigned char sec_smem[];
+  const int D = g.D, F = cfg.F, pitch = cfg.pitch;
+  cxs<Real>* W = reinterpret_cast<cxs<Real>*>(sec_smem);
+  cxs<Real>* tile = W + ((T.total_w + 1) & ~1);
+  long long* fb = reinterpret_cast<long long*>(tile + size_t(F) * pitch);
+  long long* toff = fb + F;
+  for (int e = threadIdx.x; e < T.total_w; e += kSecThreads) W[e] = wpacked[e];
+  const long long f0 = (long long)blockIdx.x * F;
+  for (int i = threadIdx.x; i < F; i += kSecThreads) fb[i] = (f0 + i < g.n_rest) ? expand_rest(g, f0 + i) : -1;
+  for (int r = threadIdx.x; r < D; r += kSecThreads)
+    toff[r] = T.k == 2 ? (long long)(r / T.d) * T.S0 + (long long)(r % T.d) * T.S1 : (long long)r * T.S0;
+  __syncthreads();
+  cxs<Real>* st = state + (long long)blockIdx.y * g.state_size;
+  for (int e0 = threadIdx.x; e0 < F * D; e0 += 4 * kSecThreads) {   // four independent loads in flight per thread
+    cxs<Real> v[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kSecThreads;
+      dst[u] = -1;
+      if (e < F * D) {
+        const int f = e / D, r = e - f * D;
+        if (fb[f] >= 0) { v[u] = st[fb[f] + toff[r]]; dst[u] = f * pitch + r; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u] >= 0) tile[dst[u]] = v[u];
+  }
+  __syncthreads();
+  {
+    const int fibre = threadIdx.x % F, q = threadIdx.x / F;
+    if (q < cfg.Q && fb[fibre] >= 0) {
+      const int sstep = T.k == 2 ? T.d + T.dj : 1;   // member step inside a staged fibre (row-major i, j)
+      for (int s = q; s < T.n_sectors; s += cfg.Q) {
+        cxs<Real>* p = tile + fibre * pitch + (T.k == 2 ? T.s[s].i0 * T.d + T.s[s].j0 : T.s[s].i0);
+        run_sector<Real, MAXM>(T.s[s].m, p, sstep, W + T.s[s].woff);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < F * D; e += kSecThreads) {
+    const int f = e / D, r = e - f * D;
+    if (fb[f] >= 0) st[fb[f] + toff[r]] = tile[f * pitch + r];
+  }
+}
+
+// DIAG: state[idx] *= M[r][r], r from the digits of idx
+template <typename Real>
+__global__ void __launch_bounds__(256)
+qudit_diag_kernel(cxs<Real>* __restrict__ state, const cxs<Real>* __restrict__ m, int d, int k, unsigned long long S0,
+                  unsigned long long S1, unsigned long long state_size) {
+  __shared__ cxs<Real> dg[256];
+  const int D = k == 2 ? d * d : d;
+  for (int r = threadIdx.x; r < D; r += blockDim.x) dg[r] = m[r * D + r];
+  __syncthreads();
+  cxs<Real>* st = state + (unsigned long long)blockIdx.y * state_size;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const bool small = state_size < (1ull << 32);
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < state_size; idx += stride) {
+    int r;
+    if (small) {   // 32-bit divisions
+      const unsigned ii = (unsigned)idx;
+      const unsigned i = (ii / (unsigned)S0) % (unsigned)d;
+      r = k == 2 ? int(i * d + (ii / (unsigned)S1) % (unsigned)d) : int(i);
+    } else {
+      const unsigned long long i = (idx / S0) % (unsigned long long)d;
+      r = k == 2 ? int(i * d + (idx / S1) % (unsigned long long)d) : int(i);
+    }
+    const cxs<Real> w = dg[r], v = st[idx];
+    cxs<Real> y; y.x = w.x * v.x - w.y * v.y; y.y = w.x * v.y + w.y * v.x;
+    st[idx] = y;
+  }
+}
+
+void* g_wpacked[64] = {nullptr};
+
+bool sector_staged_enabled() {   // B200Q_FOCK_STAGED=0: direct register kernel on every mode (A/B measurements)
+  const char* e = getenv("B200Q_FOCK_STAGED");
+  return !(e && atoi(e) == 0);
+}
+
+template <typename Real>
+int run_sectors(void* state, const QuditGeom& g, const SectorTab& T, const void* matrix, int64_t batch, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return set_err(B200Q_EINVAL, "bad device");
+  if (!g_wpacked[dev]) {
+    const int rc = cuda_err(cudaMalloc(&g_wpacked[dev], size_t(kMaxSectors) * kMaxSecD * kMaxSecD * 16), "cudaMalloc(sector blocks)");
+    if (rc) return rc;
+  }
+  pack_blocks_kernel<Real><<<4, 256, 0, s>>>((const cxs<Real>*)matrix, T, (cxs<Real>*)g_wpacked[dev]);
+  if (g.low_stride == 1 && sector_staged_enabled()) {
+    StagedCfg cfg;
+    cfg.pitch = g.D | 1;
+    int F = 256;
+    while (F > 8 && size_t(F) * cfg.pitch * sizeof(cxs<Real>) > 56 * 1024) F >>= 1;
+    cfg.F = F;
+    cfg.Q = kSecThreads / F < T.n_sectors ? kSecThreads / F : T.n_sectors;
+    if (cfg.Q < 1) cfg.Q = 1;
+    const size_t smem = size_t((T.total_w + 1) & ~1) * sizeof(cxs<Real>) + size_t(F) * cfg.pitch * sizeof(cxs<Real>) +
+                        size_t(F + g.D) * sizeof(long long);
+    const long long nblocks = (g.n_rest + F - 1) / F;
+    if (nblocks > 0x7fffffffLL) return set_err(B200Q_EUNSUPPORTED, "state too large for one launch");
+    dim3 grid((unsigned)nblocks, (unsigned)batch);
+#define B200Q_STAGED_LAUNCH(MAXM)                                                                                    \
+  do {                                                                                                               \
+    auto kern = qudit_sector_staged_kernel<Real, MAXM>;                                                              \
+    const int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),      \
+                            "cudaFuncSetAttribute(sector staged)");                                                  \
+    if (rc) return rc;                                                                                               \
+    kern<<<grid, kSecThreads, smem, s>>>((cxs<Real>*)state, T, g, (const cxs<Real>*)g_wpacked[dev], cfg);            \
+  } while (0)
+    if (T.d <= 4) B200Q_STAGED_LAUNCH(4);
+    else if (T.d <= 8) B200Q_STAGED_LAUNCH(8);
+    else if (T.d <= 10) B200Q_STAGED_LAUNCH(10);
+    else B200Q_STAGED_LAUNCH(16);
+#undef B200Q_STAGED_LAUNCH
+    return cuda_err(cudaGetLastError(), "qudit staged sector kernel launch");
+  }
+  const size_t smem = size_t(T.total_w) * sizeof(cxs<Real>);
+  const long long nblocks = (g.n_rest + kSecThreads - 1) / kSecThreads;
+  if (nblocks > 0x7fffffffLL) return set_err(B200Q_EUNSUPPORTED, "state too large for one launch");
+  dim3 grid((unsigned)nblocks, (unsigned)batch);
+#define B200Q_SECTOR_LAUNCH(MAXM)                                                                                    \
+  do {                                                                                                               \
+    auto kern = qudit_sector_kernel<Real, MAXM>;                                                                     \
+    if (smem > 48 * 1024) {                                                                                          \
+      const int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),    \
+                              "cudaFuncSetAttribute(sector)");                                                       \
+      if (rc) return rc;                                                                                             \
+    }                                                                                                                \
+    kern<<<grid, kSecThreads, smem, s>>>((cxs<Real>*)state, T, g, (const cxs<Real>*)g_wpacked[dev]);                 \
+  } while (0)
+  if (T.d <= 4) B200Q_SECTOR_LAUNCH(4);
+  else if (T.d <= 8) B200Q_SECTOR_LAUNCH(8);
+  else if (T.d <= 10) B200Q_SECTOR_LAUNCH(10);
+  else B200Q_SECTOR_LAUNCH(16);
+#undef B200Q_SECTOR_LAUNCH
+  return cuda_err(cudaGetLastError(), "qudit sector kernel launch");
+}
+
+}  // namespace
+
+extern "C" int b200q_qudit_apply_structured(void* state, int n_modes, int d, int dtype, const void* matrix,
+                                            const int32_t* modes, int n_targets, int structure, int64_t batch,
+                                            void* stream) {
+  if (structure == B200Q_QUDIT_GENERAL)
+    return b200q_qudit_apply(state, n_modes, d, dtype, matrix, modes, n_targets, batch, stream);
+  if (!state || !matrix || !modes) return set_err(B200Q_EINVAL, "null argument");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return set_err(B200Q_EINVAL, "bad dtype");
+  if (batch < 1 || batch > 65535) return set_err(B200Q_EINVAL, "bad batch");
+  if (structure < B200Q_QUDIT_GENERAL || structure > B200Q_QUDIT_DIFFERENCE) return set_err(B200Q_EINVAL, "bad structure");
+  QuditGeom g;
+  const char* err = "";
+  const int rc = qudit_make_geom(n_modes, d, modes, n_targets, dtype == B200Q_C64 ? 8 : 16, &g, &err);
+  if (rc) return set_err(rc == -2 ? B200Q_EUNSUPPORTED : B200Q_EINVAL, err);
+  // strides of the matrix digits: i (most significant) acts on modes[0], j on modes[1] (reference order)
+  const int64_t S0 = n_targets == 2 ? g.stride[1] : g.stride[0], S1 = n_targets == 2 ? g.stride[0] : 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (structure == B200Q_QUDIT_DIAG) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long want = ((unsigned long long)g.state_size + 255) / 256;
+    const unsigned gx = (unsigned)(want < (unsigned long long)sms * 16 ? (want ? want : 1) : (unsigned long long)sms * 16);
+    dim3 grid(gx, (unsigned)batch);
+    if (dtype == B200Q_C64)
+      qudit_diag_kernel<float><<<grid, 256, 0, s>>>((cxs<float>*)state, (const cxs<float>*)matrix, d, n_targets,
+                                                    (unsigned long long)S0, (unsigned long long)(S1 ? S1 : 1),
+                                                    (unsigned long long)g.state_size);
+    else
+      qudit_diag_kernel<double><<<grid, 256, 0, s>>>((cxs<double>*)state, (const cxs<double>*)matrix, d, n_targets,
+                                                     (unsigned long long)S0, (unsigned long long)(S1 ? S1 : 1),
+                                                     (unsigned long long)g.state_size);
+    return cuda_err(cudaGetLastError(), "qudit diag kernel launch");
+  }
+  SectorTab T;
+  if (!make_sectors(structure, d, n_targets, S0, S1, &T))   // cutoff > 16 or structure / arity mismatch: generic kernel
+    return b200q_qudit_apply(state, n_modes, d, dtype, matrix, modes, n_targets, batch, stream);
+  if (dtype == B200Q_C64) return run_sectors<float>(state, g, T, matrix, batch, s);
+  return run_sectors<double>(state, g, T, matrix, batch, s);
+}

@@ -30,15 +30,21 @@ from .operation import apply_complex_fix
 FUSE_FOCK = os.environ.get('B200Q_FOCK_FUSE', '0') != '0'
 
 
-def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, wires, batch: int = 1) -> None:
-    """In-place `evolve_state(state, matrix, nmode, wires, qudit=d)` on a contiguous [batch, d^nmode] tensor."""
+STRUCTURED_FOCK = os.environ.get('B200Q_FOCK_STRUCTURED', '1') != '0'   # block-structured kernels by gate class
+
+
+def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, wires, batch: int = 1,
+                 structure: int = L.QUDIT_GENERAL) -> None:
+    """In-place `evolve_state(state, matrix, nmode, wires, qudit=d)` on a contiguous [batch, d^nmode] tensor.
+    `structure` (L.QUDIT_*): block structure of the matrix known from the gate CLASS (b200q_qudit_apply_structured)."""
     engine.require_cuda(flat, 'the Fock state tensor')
     if not flat.is_contiguous() or flat.numel() != batch * d**nmode:
         raise L.B200QError('state must be contiguous with batch * cutoff^nmode elements')
     m = matrix.to(flat.dtype).contiguous()
     w = (C.c_int32 * len(wires))(*[int(x) for x in wires])
-    L.check(L.load().b200q_qudit_apply(flat.data_ptr(), nmode, d, engine.dtype_code(flat.dtype), m.data_ptr(), w,
-                                       len(wires), batch, engine._stream(flat)))
+    L.check(L.load().b200q_qudit_apply_structured(flat.data_ptr(), nmode, d, engine.dtype_code(flat.dtype), m.data_ptr(),
+                                                  w, len(wires), structure if STRUCTURED_FOCK else L.QUDIT_GENERAL,
+                                                  batch, engine._stream(flat)))
 
 
 FOCK_TILE_MAX = 12288     # amplitudes of a fused pass's shared-memory tile (b200q_qudit_fused)
@@ -246,7 +252,11 @@ def bs_matrix_state(u: torch.Tensor, d: int) -> torch.Tensor:
 
 
 class _FockGate(nn.Module):
-    """Base of the photonic gates on the Fock tensor path (reference photonic/operation.py:60-271)."""
+    """Base of the photonic gates on the Fock tensor path (reference photonic/operation.py:60-271).
+
+    `_structure`: block structure of the class's Fock matrix (include/b200q.h B200Q_QUDIT_*), a property of the gate
+    CLASS (photon-number conservation of the beamsplitter family, ...), never read off the values."""
+    _structure = L.QUDIT_GENERAL
 
     def __init__(self, name, nmode, wires, cutoff):
         super().__init__()
@@ -262,7 +272,7 @@ class _FockGate(nn.Module):
         nt = len(self.wires)
         matrix = self.update_matrix_state().reshape(self.cutoff**nt, self.cutoff**nt)
         flat = x.reshape(-1, self.cutoff**self.nmode).contiguous().clone()
-        qudit_apply_(flat, self.nmode, self.cutoff, matrix, self.wires, flat.shape[0])
+        qudit_apply_(flat, self.nmode, self.cutoff, matrix, self.wires, flat.shape[0], self._structure)
         return flat.reshape(x.shape)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -296,6 +306,7 @@ class _FockGate(nn.Module):
 
 class PhaseShift(_FockGate):
     """diag(exp(i theta n)); `inv_mode` rotates clockwise (theta -> -theta, reference photonic/gate.py:135-199)."""
+    _structure = L.QUDIT_DIAG
 
     def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False,
                  inv_mode: bool = False):
@@ -321,6 +332,7 @@ class PhaseShift(_FockGate):
 
 class BeamSplitter(_FockGate):
     """BS(theta, phi): mode-mixing matrix [[cos, -e^{-i phi} sin], [e^{i phi} sin, cos]] (photonic/gate.py:331-339)."""
+    _structure = L.QUDIT_NUMBER
 
     def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, requires_grad: bool = False):
         super().__init__('BeamSplitter', nmode, [0, 1] if wires is None else wires, cutoff)
@@ -355,6 +367,7 @@ class BeamSplitter(_FockGate):
 
 
 class Squeezing(_FockGate):
+    _structure = L.QUDIT_DENSE1
     def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False):
         super().__init__('Squeezing', nmode, [0] if wires is None else wires, cutoff)
         if inputs is None:
@@ -394,6 +407,7 @@ class Displacement(Squeezing):
 
 class Squeezing2(BeamSplitter):
     """Two-mode squeezing S2(r, theta) (reference photonic/gate.py:1157-1333); parameters handled like BS(theta, phi)."""
+    _structure = L.QUDIT_DIFFERENCE
 
     def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, requires_grad: bool = False):
         if inputs is None:
@@ -466,6 +480,7 @@ class BeamSplitterPhi(_BeamSplitterOneParam):
 
 class BeamSplitterSingle(_FockGate):
     """One-angle beamsplitters in the `'rx'`, `'ry'` or `'h'` convention (reference photonic/gate.py:713-877)."""
+    _structure = L.QUDIT_NUMBER
 
     def __init__(self, inputs: Any = None, nmode: int = 2, wires=None, cutoff: int = 2, convention: str = 'rx',
                  requires_grad: bool = False):
@@ -502,6 +517,7 @@ class BeamSplitterSingle(_FockGate):
 
 class Kerr(_FockGate):
     """diag(exp(i kappa n^2)) (reference photonic/gate.py:2291-2383)."""
+    _structure = L.QUDIT_DIAG
 
     def __init__(self, inputs: Any = None, nmode: int = 1, wires=None, cutoff: int = 2, requires_grad: bool = False):
         super().__init__(type(self).__name__, nmode, self._default_wires() if wires is None else wires, cutoff)
@@ -738,7 +754,7 @@ class QumodeCircuit(nn.Module):
                     qudit_fused_(flat, n, d, tile, [(self.operators[i].wires, offs[i]) for i in ids], buf, flat.shape[0])
             else:
                 for op, m in zip(self.operators, mats):
-                    qudit_apply_(flat, n, d, m, op.wires, flat.shape[0])
+                    qudit_apply_(flat, n, d, m, op.wires, flat.shape[0], op._structure)
         self.state = flat.reshape([-1] + [d] * n)
         return self.state
 

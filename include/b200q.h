@@ -195,6 +195,23 @@ int b200q_adjoint_run(const b200q_plan_t* plan, void* psi, void* lambda, const v
 int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
                       int n_targets, int64_t batch, void* stream);
 
+/* The same call for gate CLASSES whose Fock matrix has a known block structure (decided by the class, never from the
+ * values; entries outside the structure are not read): the kernel then keeps one block of one fibre in registers and
+ * needs no shared-memory staging of amplitudes.  B200Q_QUDIT_GENERAL, cutoffs above 16 and arity mismatches fall back
+ * to b200q_qudit_apply.
+ *   DIAG        diagonal: phase shifter, Kerr, cross-Kerr                       (photonic/gate.py:135-199, 2628-2680)
+ *   DENSE1      any one-mode gate: squeezer, displacement                       (photonic/gate.py:1015-1154, 1336-1489)
+ *   NUMBER      two-mode, conserves the photon number of its modes: the beamsplitter family, MZI
+ *                                                                                (photonic/gate.py:202-1012)
+ *   DIFFERENCE  two-mode, conserves the photon-number difference: two-mode squeezing  (photonic/gate.py:1157-1333) */
+#define B200Q_QUDIT_GENERAL 0
+#define B200Q_QUDIT_DIAG 1
+#define B200Q_QUDIT_DENSE1 2
+#define B200Q_QUDIT_NUMBER 3
+#define B200Q_QUDIT_DIFFERENCE 4
+int b200q_qudit_apply_structured(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
+                                 int n_targets, int structure, int64_t batch, void* stream);
+
 /* Fused Fock pass: `n_gates` consecutive evolve_state(..., qudit = cutoff) calls of the photonic tensor path
  * (photonic/circuit.py:405-431 applies them one by one) whose modes all lie in `tile_modes` (ascending, at most
  * cutoff^n_tile = 12 288 amplitudes; the planner keeps the last mode in the tile so that global accesses are runs of

@@ -221,3 +221,51 @@ def test_fused_fock_full_size_c5_matches_per_gate_kernel():
         if len(op.wires) == 1:
             conv = np.convolve(conv, np.abs(mtx.cpu().numpy()[:, 0])**2)
     assert np.abs(p_n[:d] - conv[:d]).max() < 2e-6, (p_n[:d], conv[:d])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('nmode,cutoff', [(4, 5), (3, 10), (3, 16), (5, 3)])
+def test_structured_fock_kernels_against_host_contraction(nmode, cutoff, rdtype):
+    """Every block structure of b200q_qudit_apply_structured (DIAG, DENSE1, NUMBER, DIFFERENCE) on every mode position
+    (first / middle / last, both wire orders), batch of 2, against the oracle's qudit contraction on the host and against
+    the generic ELL kernel; cutoff 17 exercises the documented fall-back to the generic kernel."""
+    import statevec_oracle as so
+    from deepquantum_b200 import _lib as L
+    from deepquantum_b200 import photonic as ph
+    n, d = nmode, cutoff
+    cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
+    g = torch.Generator().manual_seed(11)
+    rnd = lambda s=1.0: float(torch.rand(1, generator=g) * s)   # noqa: E731
+    gates = []
+    for w in range(n):
+        gates.append(ph.Squeezing([rnd(0.4), rnd(6)], n, [w], d))
+        gates.append(ph.PhaseShift(rnd(6), n, [w], d))
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    for a, b in pairs:
+        gates.append(ph.BeamSplitter([rnd(6), rnd(6)], n, [a, b], d))
+    for a, b in pairs[::3]:
+        gates.append(ph.Squeezing2([rnd(0.3), rnd(6)], n, [a, b], d))
+        gates.append(ph.CrossKerr(rnd(1), n, [a, b], d))
+        gates.append(ph.MZI([rnd(6), rnd(6)], n, [b, a], d))
+    gates.append(ph.Displacement([rnd(0.3), rnd(6)], n, [n - 1], d))
+    gates.append(ph.Kerr(rnd(1), n, [0], d))
+    psi = torch.randn(2, d**n, generator=g, dtype=torch.float64) + 1j * torch.randn(2, d**n, generator=g,
+                                                                                     dtype=torch.float64)
+    psi = (psi / psi.norm(dim=1, keepdim=True)).to(cdt)
+    ref = psi.numpy().astype(np.complex128)
+    st = psi.to('cuda').contiguous()
+    gen = st.clone()
+    kinds = set()
+    for op in gates:
+        m = op.update_matrix_state().reshape(d**len(op.wires), d**len(op.wires)).to(cdt)
+        kinds.add(op._structure)
+        ph.qudit_apply_(st, n, d, m.to('cuda'), op.wires, 2, op._structure)
+        ph.qudit_apply_(gen, n, d, m.to('cuda'), op.wires, 2, L.QUDIT_GENERAL)
+        ref = so.evolve_state(ref, m.numpy().astype(np.complex128), n, list(op.wires), d)
+    assert kinds == {L.QUDIT_DIAG, L.QUDIT_DENSE1, L.QUDIT_NUMBER, L.QUDIT_DIFFERENCE}
+    scale = np.linalg.norm(ref)
+    tol = 1e-11 if rdtype == torch.float64 else 2e-5
+    err = np.linalg.norm(st.cpu().numpy() - ref) / scale
+    err_gen = np.linalg.norm(gen.cpu().numpy() - ref) / scale
+    assert err < tol and err_gen < tol, (err, err_gen)

@@ -400,7 +400,8 @@ def run_config(args):
                            'gates': len(spec), 'passes': len(spec)},
                 'roofline': {'bound': 'hbm', 'achieved': len(spec) * bytes_pass / (ms * 1e-3) / 1e9, 'peak': peak,
                              'unit': 'GB/s', 'frac': len(spec) * bytes_pass / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
-                             'kernel': 'qudit_apply_kernel (one gate per pass; includes the matrix build)'},
+                             'kernel': 'qudit_sector_kernel / qudit_sector_staged_kernel (block-structured, one gate per pass); '
+                                       'the step time includes the assembly of the 36 Fock matrices'},
                 'e2e': {'value': len(spec) / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                         'note': 'parameters live on the device (the reference builds this circuit from constants too)'},
                 'gpu_launches': args.steps * 2 * len(spec), 'clocks': clocks}

@@ -104,6 +104,8 @@ _SIGNATURES = {
     'b200q_init_basis': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'b200q_adjoint_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_uint8), C.c_void_p]),
+    'b200q_fock_bs_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'b200q_fock_squeezing_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_qudit_apply_structured': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),
                                                C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     'b200q_qudit_apply': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int,

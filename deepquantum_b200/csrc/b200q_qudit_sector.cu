@@ -207,6 +207,12 @@ qudit_sector_kernel(cxs<Real>* __restrict__ state, const __grid_constant__ Secto
 // -- (fibre, sector class q of Q) -- run the same register blocks on the shared copy, and the block is written back.
 struct StagedCfg { int32_t F, Q, pitch; };
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+
 template <typename Real, int MAXM>
 __global__ void __launch_bounds__(kSecThreads)
 qudit_sector_staged_kernel(cxs<Real>* __restrict__ state, const __grid_constant__ SectorTab T, const QuditGeom g,
@@ -224,22 +230,16 @@ qudit_sector_staged_kernel(cxs<Real>* __restrict__ state, const __grid_constant_
     toff[r] = T.k == 2 ? (long long)(r / T.d) * T.S0 + (long long)(r % T.d) * T.S1 : (long long)r * T.S0;
   __syncthreads();
   cxs<Real>* st = state + (long long)blockIdx.y * g.state_size;
-  for (int e0 = threadIdx.x; e0 < F * D; e0 += 4 * kSecThreads) {   // four independent loads in flight per thread
-    cxs<Real> v[4];
-    int dst[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kSecThreads;
-      dst[u] = -1;
-      if (e < F * D) {
-        const int f = e / D, r = e - f * D;
-        if (fb[f] >= 0) { v[u] = st[fb[f] + toff[r]]; dst[u] = f * pitch + r; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (dst[u] >= 0) tile[dst[u]] = v[u];
+  // copy in: a warp per fibre, lanes over its D members (runs of d contiguous amplitudes), global -> shared with
+  // cp.async: all ~F * D / 256 copies of a thread are in flight at once and no register is staged (with register
+  // staging the phase was latency-bound: 51 % of the stall samples sat on the shared store waiting for its load)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = warp; f < F; f += kSecThreads / 32) {
+    const long long b = fb[f];
+    if (b < 0) continue;
+    for (int r = lane; r < D; r += 32) cp_async_elem<sizeof(cxs<Real>)>(tile + f * pitch + r, st + b + toff[r]);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   {
     const int fibre = threadIdx.x % F, q = threadIdx.x / F;
@@ -252,9 +252,11 @@ qudit_sector_staged_kernel(cxs<Real>* __restrict__ state, const __grid_constant_
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < F * D; e += kSecThreads) {
-    const int f = e / D, r = e - f * D;
-    if (fb[f] >= 0) st[fb[f] + toff[r]] = tile[f * pitch + r];
+  for (int f = warp; f < F; f += kSecThreads / 32) {
+    const long long b = fb[f];
+    if (b < 0) continue;
+#pragma unroll 4
+    for (int r = lane; r < D; r += 32) st[b + toff[r]] = tile[f * pitch + r];
   }
 }
 
@@ -303,11 +305,15 @@ int run_sectors(void* state, const QuditGeom& g, const SectorTab& T, const void*
     if (rc) return rc;
   }
   pack_blocks_kernel<Real><<<4, 256, 0, s>>>((const cxs<Real>*)matrix, T, (cxs<Real>*)g_wpacked[dev]);
-  if (g.low_stride == 1 && sector_staged_enabled()) {
+  if (g.low_stride == 1 && g.k == 2 && sector_staged_enabled()) {   // (one-mode gates: the direct kernel is faster)
     StagedCfg cfg;
     cfg.pitch = g.D | 1;
     int F = 256;
     while (F > 8 && size_t(F) * cfg.pitch * sizeof(cxs<Real>) > 56 * 1024) F >>= 1;
+    if (const char* e = getenv("B200Q_FOCK_STAGED_F")) {   // A/B: fibres per CTA
+      const int v = atoi(e);
+      if (v >= 8 && v <= 256 && (v & (v - 1)) == 0 && size_t(v) * cfg.pitch * sizeof(cxs<Real>) <= 160 * 1024) F = v;
+    }
     cfg.F = F;
     cfg.Q = kSecThreads / F < T.n_sectors ? kSecThreads / F : T.n_sectors;
     if (cfg.Q < 1) cfg.Q = 1;
@@ -394,4 +400,145 @@ extern "C" int b200q_qudit_apply_structured(void* state, int n_modes, int d, int
     return b200q_qudit_apply(state, n_modes, d, dtype, matrix, modes, n_targets, batch, stream);
   if (dtype == B200Q_C64) return run_sectors<float>(state, g, T, matrix, batch, s);
   return run_sectors<double>(state, g, T, matrix, batch, s);
+}
+
+// ---- Fock transformation matrices on the device --------------------------------------------------------------------
+// The reference evaluates the Fock matrix of every gate with Python-level recurrences over the cutoff
+// (photonic/gate.py:347-374 beamsplitter, 1091-1114 squeezer; arXiv:2004.11002 Eq. 74-75 and 51-52).  Batched over the
+// gates of a class that is still ~400 small launches per forward of config 5 (3.3 ms of launch latency against 11 ms of
+// gate passes); here ONE launch per gate class: a CTA per gate, the recurrence in shared memory, complex128 arithmetic
+// in the reference's order of operations, result cast to the state's dtype.
+namespace {
+
+struct zc { double x, y; };
+__device__ __forceinline__ zc zmul(zc a, zc b) { zc r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+__device__ __forceinline__ zc zscale(double s, zc a) { zc r; r.x = s * a.x; r.y = s * a.y; return r; }
+__device__ __forceinline__ zc zadd(zc a, zc b) { zc r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+
+template <typename Real>
+__device__ __forceinline__ void zstore(void* out, long long i, zc v) {
+  cxs<Real> o; o.x = Real(v.x); o.y = Real(v.y);
+  reinterpret_cast<cxs<Real>*>(out)[i] = o;
+}
+
+// T[m, n, p, q] of the mode-mixing matrix u (row-major 2 x 2): q = 0 closed form, then the q-recurrence
+template <typename Real>
+__global__ void __launch_bounds__(256) fock_bs_matrix_kernel(const zc* __restrict__ u, int d, void* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char bsm[];
+  const int d3 = d * d * d;
+  zc* prev = reinterpret_cast<zc*>(bsm);
+  zc* cur = prev + d3;
+  zc* pw0 = cur + d3;          // u00^k
+  zc* pw1 = pw0 + d;           // u10^k
+  const zc u00 = u[blockIdx.x * 4 + 0], u01 = u[blockIdx.x * 4 + 1], u10 = u[blockIdx.x * 4 + 2], u11 = u[blockIdx.x * 4 + 3];
+  if (threadIdx.x == 0) {      // cumulative products, like torch.cumprod (photonic._int_powers)
+    zc a; a.x = 1.0; a.y = 0.0;
+    zc b = a;
+    for (int k = 0; k < d; ++k) {
+      pw0[k] = a; pw1[k] = b;
+      a = zmul(a, u00); b = zmul(b, u10);
+    }
+  }
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * d3 * d;
+  for (int e = threadIdx.x; e < d3; e += blockDim.x) {
+    const int m = e / (d * d), n = (e / d) % d, p = e % d;
+    zc v; v.x = v.y = 0.0;
+    if (p == m + n) {
+      const double coef = exp(0.5 * (lgamma(double(p) + 1.0) - lgamma(double(m) + 1.0) - lgamma(double(n) + 1.0)));
+      v = zmul(zscale(coef, pw0[m]), pw1[n]);
+    }
+    prev[e] = v;
+    zstore<Real>(out, base + (long long)e * d, v);
+  }
+  __syncthreads();
+  for (int q = 1; q < d; ++q) {
+    const double sq = sqrt(double(q));
+    for (int e = threadIdx.x; e < d3; e += blockDim.x) {
+      const int m = e / (d * d), n = (e / d) % d, p = e % d;
+      zc v; v.x = v.y = 0.0;
+      if (m + n - p == q) {
+        zc a; a.x = a.y = 0.0;
+        zc b = a;
+        if (m > 0) a = zmul(zscale(sqrt(double(m)) / sq, u01), prev[e - d * d]);
+        if (n > 0) b = zmul(zscale(sqrt(double(n)) / sq, u11), prev[e - d]);
+        v = zadd(a, b);
+      }
+      cur[e] = v;
+      zstore<Real>(out, base + (long long)e * d + q, v);
+    }
+    __syncthreads();
+    zc* t = prev; prev = cur; cur = t;
+  }
+}
+
+// S(r, theta): column 0 by the rank-1 recurrence over even rows, column n + 1 from columns n and n - 1
+template <typename Real>
+__global__ void __launch_bounds__(64) fock_squeezing_matrix_kernel(const double* __restrict__ prm, int d,
+                                                                    void* __restrict__ out) {
+  __shared__ zc cols[3][64];
+  const double r = prm[blockIdx.x * 2], theta = prm[blockIdx.x * 2 + 1];
+  const double sech = 1.0 / cosh(r), th = tanh(r);
+  zc ep; ep.x = cos(theta) * th; ep.y = sin(theta) * th;        // e^{i theta} tanh r
+  zc em; em.x = cos(theta) * th; em.y = -sin(theta) * th;       // e^{-i theta} tanh r
+  const int m = threadIdx.x;
+  const long long base = (long long)blockIdx.x * d * d;
+  if (m == 0) {
+    zc c; c.x = sqrt(sech); c.y = 0.0;
+    cols[0][0] = c;
+    for (int k = 1; k < d; ++k) {
+      zc v; v.x = v.y = 0.0;
+      if (k % 2 == 0) v = zmul(zscale(-sqrt(double(k - 1)) / sqrt(double(k)), ep), cols[0][k - 2]);
+      cols[0][k] = v;
+    }
+  }
+  __syncthreads();
+  if (m < d) zstore<Real>(out, base + (long long)m * d, cols[0][m]);
+  for (int n = 0; n + 1 < d; ++n) {
+    const zc* pn = cols[n % 3];
+    const zc* pn1 = cols[(n + 2) % 3];     // column n - 1
+    zc* nx = cols[(n + 1) % 3];
+    if (m < d) {
+      zc v; v.x = v.y = 0.0;
+      if ((m + n) % 2 == 1) {
+        zc sh; sh.x = sh.y = 0.0;
+        if (m > 0) sh = pn[m - 1];
+        v = zscale(sqrt(double(m)) / sqrt(double(n + 1)) * sech, sh);
+        if (n >= 1) v = zadd(v, zmul(zscale(sqrt(double(n)) / sqrt(double(n + 1)), em), pn1[m]));
+      }
+      nx[m] = v;
+      zstore<Real>(out, base + (long long)m * d + n + 1, v);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+extern "C" int b200q_fock_bs_matrix(const void* mixing, int n_gates, int d, int dtype, void* out, void* stream) {
+  if (!mixing || !out) return set_err(B200Q_EINVAL, "null argument");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return set_err(B200Q_EINVAL, "bad dtype");
+  if (n_gates < 1 || d < 1 || d > kMaxSecD) return set_err(B200Q_EUNSUPPORTED, "cutoff above 16: build the matrix in torch");
+  const size_t smem = (size_t(2) * d * d * d + 2 * d) * sizeof(zc);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == B200Q_C64) {
+    auto kern = fock_bs_matrix_kernel<float>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<n_gates, 256, smem, s>>>((const zc*)mixing, d, out);
+  } else {
+    auto kern = fock_bs_matrix_kernel<double>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<n_gates, 256, smem, s>>>((const zc*)mixing, d, out);
+  }
+  return cuda_err(cudaGetLastError(), "fock_bs_matrix launch");
+}
+
+extern "C" int b200q_fock_squeezing_matrix(const double* r_theta, int n_gates, int d, int dtype, void* out, void* stream) {
+  if (!r_theta || !out) return set_err(B200Q_EINVAL, "null argument");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return set_err(B200Q_EINVAL, "bad dtype");
+  if (n_gates < 1 || d < 1 || d > 64) return set_err(B200Q_EUNSUPPORTED, "cutoff above 64: build the matrix in torch");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == B200Q_C64) fock_squeezing_matrix_kernel<float><<<n_gates, 64, 0, s>>>(r_theta, d, out);
+  else fock_squeezing_matrix_kernel<double><<<n_gates, 64, 0, s>>>(r_theta, d, out);
+  return cuda_err(cudaGetLastError(), "fock_squeezing_matrix launch");
 }

@@ -128,9 +128,26 @@ def ps_matrix_state(theta: torch.Tensor, d: int) -> torch.Tensor:
     return torch.diag_embed(torch.exp(1j * theta[:, None] * n[None, :]))
 
 
+NATIVE_FOCK_MATRICES = os.environ.get('B200Q_FOCK_NATIVE_MATRICES', '1') != '0'
+
+
+def _native_matrices_ok(t: torch.Tensor, d: int, dmax: int) -> bool:
+    """One launch per gate class instead of the torch recurrences: forward-only (no autograd graph), float64 parameters
+    on the device."""
+    return (NATIVE_FOCK_MATRICES and t.is_cuda and d <= dmax and t.shape[0] >= 1
+            and not (torch.is_grad_enabled() and t.requires_grad)
+            and t.dtype in (torch.float64, torch.complex128))
+
+
 def squeezing_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> torch.Tensor:
     """[N], [N] -> [N, d, d]   (photonic/gate.py:1091-1114, arXiv:2004.11002 Eq. 51-52): column n+1 from
     columns n and n-1, vectorised over rows and gates."""
+    if _native_matrices_ok(r, d, 64) and theta.dtype == torch.float64:
+        prm = torch.stack([r, theta], dim=1).contiguous()
+        out = torch.empty(r.shape[0], d, d, dtype=torch.complex128, device=r.device)
+        L.check(L.load().b200q_fock_squeezing_matrix(prm.data_ptr(), r.shape[0], d, L.C128, out.data_ptr(),
+                                                     engine._stream(out)))
+        return out
     rt = r.dtype
     sq = torch.sqrt(torch.arange(d, dtype=rt, device=r.device))
     sech = 1 / torch.cosh(r)
@@ -225,6 +242,11 @@ def squeezing2_matrix_state(r: torch.Tensor, theta: torch.Tensor, d: int) -> tor
 def bs_matrix_state(u: torch.Tensor, d: int) -> torch.Tensor:
     """[N, 2, 2] mode-mixing unitaries -> [N, d, d, d, d] Fock transformation tensors T[m, n, p, q]
     (photonic/gate.py:347-374, arXiv:2004.11002 Eq. 74-75): the q-recurrence vectorised over (m, n, p, gate)."""
+    if _native_matrices_ok(u, d, 16):
+        uc = u.contiguous()
+        out = torch.empty(u.shape[0], d, d, d, d, dtype=torch.complex128, device=u.device)
+        L.check(L.load().b200q_fock_bs_matrix(uc.data_ptr(), u.shape[0], d, L.C128, out.data_ptr(), engine._stream(out)))
+        return out
     rt = u.real.dtype
     dev = u.device
     N = u.shape[0]

@@ -35,8 +35,11 @@ def _digits(value: int, base: int, ndigit: int) -> list[int]:
 class CudaQuditExecutor:
     """Applies a local gate with the qudit kernel (csrc/b200q_qudit.cu)."""
 
-    def apply(self, amps: torch.Tensor, nmode_local: int, cutoff: int, matrix: torch.Tensor, wires) -> None:
-        qudit_apply_(amps.reshape(1, -1), nmode_local, cutoff, matrix, wires, 1)
+    takes_structure = True    # `apply` accepts the block structure of the gate class (photonic._FockGate._structure)
+
+    def apply(self, amps: torch.Tensor, nmode_local: int, cutoff: int, matrix: torch.Tensor, wires,
+              structure: int = 0) -> None:
+        qudit_apply_(amps.reshape(1, -1), nmode_local, cutoff, matrix, wires, 1, structure)
 
 
 class DistributedFockState(nn.Module):
@@ -163,7 +166,10 @@ class DistributedQumodeCircuit(QumodeCircuit):
                     victim = max(candidates, key=lambda q: self._next_use(i + 1, q))
                     swap_global_local(st, phys[w], phys[victim] - g)
                     phys[w], phys[victim] = phys[victim], phys[w]
-            ex.apply(st.amps, nl, d, m, [phys[w] - g for w in op.wires])
+            if getattr(ex, 'takes_structure', False):
+                ex.apply(st.amps, nl, d, m, [phys[w] - g for w in op.wires], op._structure)
+            else:
+                ex.apply(st.amps, nl, d, m, [phys[w] - g for w in op.wires])
         # restore the reference layout: logical mode q at slot q
         def swap_modes(a, b):            # logical modes: a on a rank digit, b on a local axis
             swap_global_local(st, phys[a], phys[b] - g)

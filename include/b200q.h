@@ -212,6 +212,13 @@ int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* ma
 int b200q_qudit_apply_structured(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
                                  int n_targets, int structure, int64_t batch, void* stream);
 
+/* Fock transformation matrices of a whole gate class in one launch (the reference runs Python-level recurrences over the
+ * cutoff per gate: photonic/gate.py:347-374 beamsplitter family, 1091-1114 squeezer; arXiv:2004.11002 Eq. 74-75, 51-52).
+ * `mixing`: n_gates x 2 x 2 complex128 mode-mixing matrices on the device; `r_theta`: n_gates x 2 doubles.
+ * `out`: n_gates x d^4 (index m, n, p, q) resp. n_gates x d^2 complex of `dtype`.  Cutoff <= 16 (beamsplitter), <= 64. */
+int b200q_fock_bs_matrix(const void* mixing, int n_gates, int d, int dtype, void* out, void* stream);
+int b200q_fock_squeezing_matrix(const double* r_theta, int n_gates, int d, int dtype, void* out, void* stream);
+
 /* Fused Fock pass: `n_gates` consecutive evolve_state(..., qudit = cutoff) calls of the photonic tensor path
  * (photonic/circuit.py:405-431 applies them one by one) whose modes all lie in `tile_modes` (ascending, at most
  * cutoff^n_tile = 12 288 amplitudes; the planner keeps the last mode in the tile so that global accesses are runs of

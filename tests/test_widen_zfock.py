@@ -269,3 +269,36 @@ def test_structured_fock_kernels_against_host_contraction(nmode, cutoff, rdtype)
     err = np.linalg.norm(st.cpu().numpy() - ref) / scale
     err_gen = np.linalg.norm(gen.cpu().numpy() - ref) / scale
     assert err < tol and err_gen < tol, (err, err_gen)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cutoff', [2, 3, 10, 16])
+def test_native_fock_matrices_match_the_torch_recurrences(cutoff):
+    """b200q_fock_bs_matrix / b200q_fock_squeezing_matrix (one launch per gate class) against the batched torch
+    restatement of the reference recurrences (photonic/gate.py:347-374, 1091-1114), itself pinned by the reference
+    fixtures (fock.npz, fock2.npz), in complex128 on the device -- including theta = 0 / r = 0 (exact zeros)."""
+    from deepquantum_b200 import photonic as ph
+    g = torch.Generator().manual_seed(2)
+    n = 9
+    th = torch.rand(n, generator=g, dtype=torch.float64) * 6
+    phi = torch.rand(n, generator=g, dtype=torch.float64) * 6
+    th[0] = 0.0
+    r = torch.rand(n, generator=g, dtype=torch.float64) * 0.8
+    r[1] = 0.0
+    th, phi, r = th.cuda(), phi.cuda(), r.cuda()
+    u = ph.BeamSplitter.mixing_matrix(th, phi)
+    old = ph.NATIVE_FOCK_MATRICES
+    try:
+        ph.NATIVE_FOCK_MATRICES = True
+        bs_n, sq_n = ph.bs_matrix_state(u, cutoff), ph.squeezing_matrix_state(r, phi, cutoff)
+        mzi_n = ph.bs_matrix_state(ph.MZI.mixing_matrix(th, phi, False), cutoff)
+        ph.NATIVE_FOCK_MATRICES = False
+        bs_t, sq_t = ph.bs_matrix_state(u, cutoff), ph.squeezing_matrix_state(r, phi, cutoff)
+        mzi_t = ph.bs_matrix_state(ph.MZI.mixing_matrix(th, phi, False), cutoff)
+    finally:
+        ph.NATIVE_FOCK_MATRICES = old
+    for a, b in ((bs_n, bs_t), (sq_n, sq_t), (mzi_n, mzi_t)):
+        assert a.shape == b.shape and a.dtype == b.dtype
+        # both run the same recurrence in float64; its rounding noise grows with the cutoff (6e-13 at 16)
+        assert float((a - b).abs().max()) < max(1e-13, 1e-15 * cutoff**4) * max(1.0, float(b.abs().max()))
+        assert torch.equal(a == 0, b == 0)          # the structural zeros are exact in both

@@ -55,8 +55,10 @@ def main():
     src = ncu_csv(report, 'source')
     # the source page repeats a two-line header per kernel; take the block of the requested launch
     starts = [i for i, r in enumerate(src) if r and r[0] == 'Kernel Name']
-    begin = starts[launch] if launch < len(starts) else starts[0]
-    end = starts[launch + 1] if launch + 1 < len(starts) else len(src)
+    per = max(1, len(starts) // max(1, len(raw) - 2))     # some ncu versions print every kernel's block twice
+    k = launch * per
+    begin = starts[k] if k < len(starts) else starts[0]
+    end = starts[k + 1] if k + 1 < len(starts) else len(src)
     shdr, data = src[begin + 1], src[begin + 2:end]
     c_src, c_inst, c_smp = shdr.index('Source'), shdr.index('Instructions Executed'), shdr.index('# Samples')
     total = sum(float(r[c_inst] or 0) for r in data)

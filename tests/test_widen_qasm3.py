@@ -99,3 +99,20 @@ def test_barrier_comments_and_errors():
         qasm3_to_cir('OPENQASM 3.0; qubit[1] q; frobnicate q[0];')
     with pytest.raises(ValueError):
         qasm3_to_cir('OPENQASM 3.0; qubit[1] q; rx(__import__("os")) q[0];')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+def test_gpu_imported_programs_match_the_reference(rdtype):
+    """The same two fixtures through the product path on the device: the imported circuits run by the fused / specialised
+    kernels give the reference's final states (complex128 and complex64)."""
+    g = _g()
+    tol = 1e-10 if rdtype == torch.float64 else 3e-6
+    cir = qasm3_to_cir(str(g['export_text']))
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy()
+    assert np.abs(out - g['export_reimport_state_c128']).max() < tol
+    cir = qasm3_to_cir(str(g['program']))
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy()
+    assert np.abs(out - g['state_c128']).max() < max(tol, 2e-6)     # fractional powers: 1e-6 in the reference itself

@@ -17,7 +17,7 @@ from .distributed import DistributedQubitState  # noqa: F401
 from .gate import (Barrier, CNOT, CombinedSingleGate, Fredkin, Hadamard, HamiltonianGate, Identity, ImaginarySwap,  # noqa: F401
                    LatentGate,
                    PauliX, PauliY, PauliZ, PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz,
-                   SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
+                   Reset, SDaggerGate, SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer,  # noqa: F401
                     YLayer, ZLayer)
 from .channel import (AmplitudeDamping, BitFlip, Depolarizing, GeneralizedAmplitudeDamping, PhaseDamping,  # noqa: F401

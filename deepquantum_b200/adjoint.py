@@ -8,11 +8,15 @@ states are alive (psi, lambda, and the saved output).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib as L
 from . import engine
+
+
+ADJOINT_CHUNK_BITS = int(os.environ.get('B200Q_ADJOINT_CHUNK_BITS', '0'))   # 0: the forward plan's tiles
 
 
 class ExpectationZFunction(torch.autograd.Function):
@@ -57,7 +61,11 @@ class CircuitFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         y, mats = ctx.saved_tensors
         prog = ctx.prog
-        plan = prog.plan(y.dtype)
+        # the reverse sweep stages TWO tiles (psi, lambda) per CTA: with 32 KiB tiles (chunk_bits 11) two CTAs share an SM
+        # and overlap their load / compute / store phases; the forward plan keeps its 64 KiB tiles.  Any partition of
+        # the same gate list into passes un-computes the same unitary.
+        cb = ADJOINT_CHUNK_BITS
+        plan = prog.plan(y.dtype, chunk_bits=cb) if cb else prog.plan(y.dtype)
         batch, mbs = ctx.batch, ctx.mbs
         psi = y.clone().reshape(batch, -1)
         lam = grad_y.contiguous().clone().reshape(batch, -1)

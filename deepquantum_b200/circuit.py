@@ -18,7 +18,7 @@ from torch import nn
 
 from . import _lib as L
 from . import engine
-from .gate import (Barrier, CNOT, Fredkin, Hadamard, HamiltonianGate, ImaginarySwap, LatentGate, PauliX, PauliY, PauliZ,
+from .gate import (Reset, Barrier, CNOT, Fredkin, Hadamard, HamiltonianGate, ImaginarySwap, LatentGate, PauliX, PauliY, PauliZ,
                    PhaseShift, ProjectionJ, ReconfigurableBeamSplitter, Rx, Rxx, Rxy, Ry, Ryy, Rz, Rzz, SDaggerGate,
                    SGate, Swap, TDaggerGate, TGate, Toffoli, U3Gate, UAnyGate)
 from .layer import (CnotLayer, CnotRing, HLayer, Observable, RxLayer, RyLayer, RzLayer, U3Layer, XLayer, YLayer,
@@ -43,10 +43,13 @@ class _Program:
         self.structs = self.low.finalize()
         self.plans = {}
 
-    def plan(self, dtype: torch.dtype) -> engine.FusedPlan:
-        key = (dtype, tuple(sorted(PLAN_OPTIONS.items())))
+    def plan(self, dtype: torch.dtype, **override) -> engine.FusedPlan:
+        """Fused plan for `dtype`; `override` (e.g. chunk_bits=11 for the reverse sweep, which holds two tiles per CTA)
+        replaces entries of PLAN_OPTIONS."""
+        opts = {**PLAN_OPTIONS, **override}
+        key = (dtype, tuple(sorted(opts.items())))
         if key not in self.plans:
-            self.plans[key] = engine.FusedPlan(self.low.state_qubits, dtype, self.structs, **PLAN_OPTIONS)
+            self.plans[key] = engine.FusedPlan(self.low.state_qubits, dtype, self.structs, **opts)
         return self.plans[key]
 
     @property
@@ -111,9 +114,30 @@ class QubitCircuit(Operation):
     # ---------------------------------------------------------------------------------------------
     def _get_program(self) -> _Program:
         if self._program is None or self._program_len != len(self.operators):
+            if any(isinstance(op, Reset) for op in self.operators):
+                raise NotImplementedError('a circuit with Reset is not one linear program (no unitary / inverse / '
+                                          'sharded form); forward() runs it as separate programs')
             self._program = _Program(self.nqubit, self.operators, den_mat=self.den_mat)
             self._program_len = len(self.operators)
         return self._program
+
+    def _get_segments(self):
+        """Gates between Reset operations as separate fused programs: [_Program | Reset, ...] (cached like _program)."""
+        if self.__dict__.get('_segments') is None or self.__dict__.get('_segments_key') != len(self.operators):
+            segs, cur = [], []
+            for op in self.operators:
+                if isinstance(op, Reset):
+                    if cur:
+                        segs.append(_Program(self.nqubit, cur, den_mat=self.den_mat))
+                        cur = []
+                    segs.append(op)
+                else:
+                    cur.append(op)
+            if cur:
+                segs.append(_Program(self.nqubit, cur, den_mat=self.den_mat))
+            self.__dict__['_segments'] = segs
+            self.__dict__['_segments_key'] = len(self.operators)
+        return self.__dict__['_segments']
 
     def forward(self, data: torch.Tensor | None = None, state: Any = None) -> torch.Tensor:
         """Run the circuit; returns the final state `[2^n, 1]` (or `[batch, 2^n, 1]`), like the reference
@@ -150,6 +174,8 @@ class QubitCircuit(Operation):
             assert state_t.shape[-1] == 2**self.nqubit and state_t.shape[-2] == 2**self.nqubit
         engine.require_cuda(state_t, 'the circuit state (move the circuit with cir.to("cuda"))')
         cdtype = state_t.dtype
+        if any(isinstance(op, Reset) for op in self.operators):
+            return self._run_with_resets(state_t, data_batch, lazy_zero)
         prog = self._get_program()
         mats = prog.low.build_matrices(cdtype, state_t.device)
         batched_state = state_t.ndim == 3 and not lazy_zero
@@ -177,6 +203,35 @@ class QubitCircuit(Operation):
             y = x.detach() if lazy_zero else x.detach().clone()
             prog.plan(cdtype).run(y, mats.detach(), batch, mbs)
         y = y.reshape(batch, 2**self.nqubit, -1)
+        if data_batch is None and not batched_state:
+            y = y.squeeze(0)
+        return y
+
+    def _run_with_resets(self, state_t: torch.Tensor, data_batch: int | None, lazy_zero: bool) -> torch.Tensor:
+        """Circuits with Reset (reference gate.py:3027-3094): program, projection, program, ... on one state buffer.
+        Forward only: the projection depends on the state, and the reverse sweep needs invertible steps."""
+        assert not self.den_mat
+        n, cdtype = self.nqubit, state_t.dtype
+        batched_state = state_t.ndim == 3 and not lazy_zero
+        nb_state = state_t.shape[0] if batched_state else 1
+        batch = data_batch if data_batch is not None else nb_state
+        if lazy_zero:
+            x = torch.empty(batch, 2**n, dtype=cdtype, device=state_t.device)
+            engine.init_basis_(x, n, batch, 0)
+        else:
+            x = state_t.detach().reshape(nb_state, 2**n)
+            x = (x.expand(batch, -1) if nb_state != batch else x).contiguous().clone()
+        with torch.no_grad():
+            for seg in self._get_segments():
+                if isinstance(seg, Reset):
+                    seg.apply_(x, batch)
+                    continue
+                mats = seg.low.build_matrices(cdtype, state_t.device)
+                mbs = mats.shape[-1] if mats.ndim == 2 else 0
+                if mats.ndim == 2 and mats.shape[0] != batch:
+                    raise ValueError('batch of data and batch of states differ')
+                seg.plan(cdtype).run(x, mats.detach(), batch, mbs)
+        y = x.reshape(batch, 2**n, -1)
         if data_batch is None and not batched_state:
             y = y.squeeze(0)
         return y
@@ -686,8 +741,10 @@ class QubitCircuit(Operation):
     def gen_amp_damp(self, wires, inputs=None, encode=False):
         self._channel(GeneralizedAmplitudeDamping, wires, inputs, encode)
 
-    def reset(self, *args, **kwargs):
-        raise NotImplementedError('Reset is non-unitary and outside the accelerated path')
+    def reset(self, wires=None, postselect: int | None = 0) -> None:
+        """Reset `wires` to |0> (reference circuit.py:1603-1607, gate.py:3027-3094); forward only."""
+        assert not self.den_mat, 'Currently NOT supported'
+        self.add(Reset(nqubit=self.nqubit, wires=wires, postselect=postselect))
 
 
 class _ShardedExpectation(torch.autograd.Function):

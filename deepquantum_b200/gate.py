@@ -853,3 +853,84 @@ class Barrier(Gate):
 
     def forward(self, x: Any) -> Any:
         return x
+
+
+class Reset(Gate):
+    """Reset of `wires` to |0> (reference gate.py:3027-3094), a NON-unitary, state-dependent operation.
+
+    `postselect` 0 / 1: every wire in turn is projected on that outcome, renormalised by the outcome's probability and
+    relabelled |0> (a wire whose outcome has probability exactly 0 keeps the other branch, as in the reference);
+    `postselect=None`: the outcome of all wires is sampled per state.  All wires of the circuit: the state becomes
+    |0...0>.  A circuit runs the gates before and after a Reset as separate fused programs (circuit.py); the reduction
+    and the 2 x 2 (2^k x 2^k) projection matrix are evaluated on the device, the projection itself is one more pass of
+    the same kernels.  Forward only."""
+
+    def __init__(self, nqubit: int = 1, wires=None, postselect: int | None = 0, tsr_mode: bool = False) -> None:
+        if wires is None:
+            wires = list(range(nqubit))
+        super().__init__(name='Reset', nqubit=nqubit, wires=wires, tsr_mode=tsr_mode)
+        assert postselect in (0, 1, None)
+        self.postselect = postselect
+
+    def _lower(self, low: Lowering, inverse: bool = False) -> None:
+        raise NotImplementedError('Reset splits the circuit into separate programs (QubitCircuit handles it); it cannot '
+                                  'be part of a fused program, an inverse circuit or a unitary')
+
+    def inverse(self):
+        raise NotImplementedError('Reset has no inverse')
+
+    def apply_(self, x: torch.Tensor, batch: int) -> None:
+        """In place on a contiguous device tensor `[batch, 2^nqubit]`."""
+        from . import _lib as L
+        from . import engine
+        n = self.nqubit
+        if len(self.wires) == n:
+            engine.init_basis_(x, n, batch, 0)
+            return
+        rdt = x.real.dtype
+        if self.postselect is None:
+            wires = sorted(self.wires)
+            k = len(wires)
+            assert k <= L.MAX_TARGETS, 'sampled reset of more than 6 wires at once'
+            prob = (x.real**2 + x.imag**2).reshape([batch] + [2] * n)
+            other = [1 + w for w in range(n) if w not in wires]
+            prob = (prob.sum(other) if other else prob).reshape(batch, 2**k)
+            sample = torch.multinomial(prob.double(), 1)                                    # [batch, 1]
+            mats = torch.zeros(batch, 2**k, 2**k, dtype=rdt, device=x.device)
+            mats[:, 0, :].scatter_(1, sample, prob.gather(1, sample).to(rdt).rsqrt())
+            self._apply_matrix(x, batch, wires, mats)
+            return
+        ps = self.postselect
+        for w in self.wires:
+            bit = n - 1 - w
+            masks = torch.tensor([1 << bit, 0], dtype=torch.int64, device=x.device)
+            red = engine.expectation_z(x, n, masks, batch)                                  # [batch, 2]: p0 - p1, p0 + p1
+            p = (red[:, 1] + (1 - 2 * ps) * red[:, 0]) / 2                                  # probability of `postselect`
+            empty = (p <= 0).to(p.dtype)                                                    # 1 - sign(p) of the reference
+            norm = torch.sqrt(p.clamp_min(0) + empty)
+            keep, other = ((1 - empty) / norm).to(rdt), (empty / norm).to(rdt)
+            mats = torch.zeros(batch, 2, 2, dtype=rdt, device=x.device)
+            mats[:, 0, ps] = keep
+            mats[:, 0, 1 - ps] = other
+            self._apply_matrix(x, batch, [w], mats)
+
+    def _apply_matrix(self, x, batch, wires, mats) -> None:
+        from . import _lib as L
+        from . import engine
+        n = self.nqubit
+        key = (tuple(wires), x.dtype)
+        plans = self.__dict__.setdefault('_plans', {})
+        if key not in plans:
+            targets = engine.wires_to_targets(n, wires)
+            plans[key] = engine.FusedPlan(n, x.dtype, [L.make_gate(L.GATE_MAT, targets, (), 0)])
+        m = mats.to(x.dtype).reshape(batch, -1).contiguous()
+        plans[key].run(x, m, batch, m.shape[1])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import engine
+        engine.require_cuda(x, 'the state')
+        n = self.nqubit
+        flat = x.reshape(-1, 2**n).contiguous().clone()
+        with torch.no_grad():
+            self.apply_(flat, flat.shape[0])
+        return flat.reshape(x.shape)

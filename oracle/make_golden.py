@@ -24,6 +24,8 @@ Files written
   dist_adjoint.npz    the reference's own test circuit of the differentiable sharded expectation
                       (tests/test_circuit.py:87-139), dense autograd: expectation values and d/d(data), n = 4 and 6
   unitary.npz         QubitCircuit.get_unitary() of the all-gate-families circuit (5 qubits) and a random circuit
+  reset.npz           circuits with Reset (postselect 0 / 1, several wires, a wire whose outcome has probability 0, all
+                      wires, 2-D data): final states in c64 (the reference cannot run them in c128)
   dense_grad.npz      trainable / data-fed dense blocks on 3 and 4 wires (HamiltonianGate, LatentGate, one controlled):
                       loss and its reference-autograd gradient w.r.t. every parameter and the data, n = 6
 """
@@ -539,6 +541,50 @@ def unitary():
     np.savez_compressed(os.path.join(OUT, 'unitary.npz'), **out)
 
 
+def reset_build(cir):
+    """Shared with tests/test_reset.py."""
+    cir.hlayer()
+    cir.rxlayer(encode=True)
+    cir.cnot_ring()
+    cir.reset(1)                          # postselect 0
+    cir.rylayer(encode=True)
+    cir.cnot(0, 3)
+    cir.reset([0, 3], postselect=1)
+    cir.x(2)
+    cir.reset(2)                          # |1> for sure: probability of the postselected outcome is exactly 0
+    cir.u3layer()
+    cir.cz(4, 2)
+    return cir
+
+
+def reset():
+    """complex64 only: the reference's `.to(torch.double)` fails on a circuit that holds a Reset (a module without
+    buffers, operation.py:166 -> utils.py:47, the same defect as for Barrier)."""
+    out = {}
+    n = 5
+    cir = reset_build(dq.QubitCircuit(n))
+    gp = torch.Generator().manual_seed(6)
+    for op in cir.operators:
+        for prm in op.parameters():
+            with torch.no_grad():
+                prm.copy_(torch.rand(prm.shape, generator=gp) * 6)
+    data = torch.rand(2 * n, generator=torch.Generator().manual_seed(7)) * 6
+    with torch.no_grad():
+        out['state/c64'] = cir(data=data).reshape(-1).numpy()
+        out['data'] = data.numpy()
+        out['params'] = np.concatenate([prm.detach().reshape(-1).numpy() for op in cir.operators for prm in op.parameters()])
+        data2 = torch.stack([data, data.flip(0), data * 0.5])
+        out['data2'] = data2.numpy()
+        out['state2/c64'] = cir(data=data2).reshape(3, -1).numpy()
+        full = dq.QubitCircuit(3)
+        full.hlayer()
+        full.reset()
+        full.rx(1, 0.4)
+        out['full/c64'] = full().reshape(-1).numpy()
+    np.savez_compressed(os.path.join(OUT, 'reset.npz'), **out)
+    print('reset.npz', {k: v.shape for k, v in out.items()}, float(np.linalg.norm(out['state/c64'])))
+
+
 def dense_grad_build(cir, h3):
     """Trainable dense blocks on 3 and 4 wires between ordinary layers (shared with tests/test_gpu_parity.py)."""
     cir.hlayer()
@@ -592,9 +638,11 @@ def dense_grad():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['gates', 'circuits', 'qaoa', 'fock', 'measure', 'denmat', 'hamiltonian', 'qasm3', 'fock2',
-                             'dist_adjoint', 'unitary', 'dense_grad']
+                             'dist_adjoint', 'unitary', 'dense_grad', 'reset']
     if 'dense_grad' in which:
         dense_grad()
+    if 'reset' in which:
+        reset()
     if 'dist_adjoint' in which:
         dist_adjoint()
     if 'unitary' in which:

@@ -188,3 +188,28 @@ def shard(state: np.ndarray, world_size: int, rank: int) -> np.ndarray:
 
 def unshard(shards) -> np.ndarray:
     return np.concatenate(list(shards), axis=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# gate.py:3027-3094  Reset.op_state (postselect 0 / 1)
+# ----------------------------------------------------------------------------------------------
+def reset_wires(state: np.ndarray, nqubit: int, wires, postselect: int = 0) -> np.ndarray:
+    """Reset `wires` to |0>: per wire, keep the `postselect` branch divided by the square root of its probability (the
+    OTHER branch, undivided, when that probability is exactly 0) and relabel it |0>.  All wires: |0...0>.
+    `state` is flat (2**n,) or batched (batch, 2**n)."""
+    batched = state.ndim == 2
+    psi = state.reshape((-1,) + (2,) * nqubit).copy()
+    if len(wires) == nqubit:
+        out = np.zeros_like(psi.reshape(psi.shape[0], -1))
+        out[:, 0] = 1
+        return out if batched else out[0]
+    for w in wires:
+        x = np.moveaxis(psi, w + 1, 0)                                # (2, batch, ...)
+        probs = (np.abs(x) ** 2).reshape(2, x.shape[1], -1).sum(-1)   # (2, batch)
+        mask = 1 - np.sign(probs[postselect])
+        norm = np.sqrt(probs[postselect] + mask)
+        shape = (-1,) + (1,) * (nqubit - 1)
+        s0 = ((1 - mask).reshape(shape) * x[postselect] + mask.reshape(shape) * x[1 - postselect]) / norm.reshape(shape)
+        psi = np.moveaxis(np.stack([s0, np.zeros_like(s0)]), 0, w + 1)
+    out = np.ascontiguousarray(psi).reshape(psi.shape[0], -1)
+    return out if batched else out[0]

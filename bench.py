@@ -393,18 +393,21 @@ def run_config(args):
         cir.to('cuda')
         ms, clocks = timed(lambda: cir())
         bytes_pass = 2 * cutoff**nmode * 8
+        passes = cir.fock_plan_stats()['passes']      # a two-mode gate + the one-mode gates around it share a pass
         line = {'metric': 'gate_applications_per_second', 'value': len(spec) / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
                 'config': {'workload': f'config5: Fock {nmode} modes x cutoff {cutoff}, squeezers + Clements mesh, complex64',
-                           'gates': len(spec), 'passes': len(spec)},
-                'roofline': {'bound': 'hbm', 'achieved': len(spec) * bytes_pass / (ms * 1e-3) / 1e9, 'peak': peak,
-                             'unit': 'GB/s', 'frac': len(spec) * bytes_pass / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
-                             'kernel': 'qudit_sector_kernel / qudit_sector_staged_kernel (block-structured, one gate per pass); '
-                                       'the step time includes the assembly of the 36 Fock matrices'},
+                           'gates': len(spec), 'passes': passes,
+                           'frac_if_every_gate_were_a_pass': len(spec) * bytes_pass / (ms * 1e-3) / 1e9 / peak},
+                'roofline': {'bound': 'hbm', 'achieved': passes * bytes_pass / (ms * 1e-3) / 1e9, 'peak': peak,
+                             'unit': 'GB/s', 'frac': passes * bytes_pass / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                             'kernel': 'qudit_sector_kernel / qudit_sector_staged_kernel / qudit_group_kernel (block-'
+                                       'structured register kernels); the step time includes the assembly of the Fock '
+                                       'matrices'},
                 'e2e': {'value': len(spec) / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                         'note': 'parameters live on the device (the reference builds this circuit from constants too)'},
-                'gpu_launches': args.steps * 2 * len(spec), 'clocks': clocks}
+                'gpu_launches': args.steps * 3 * passes, 'clocks': clocks}
     print(json.dumps(line))
 
 

@@ -32,6 +32,11 @@ MAX_TARGETS = 6
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libb200q.so')
 
 
+class QuditOpStruct(C.Structure):
+    """b200q_qudit_op_t (include/b200q.h)."""
+    _fields_ = [('n_targets', C.c_int32), ('modes', C.c_int32 * 2), ('structure', C.c_int32), ('matrix', C.c_uint64)]
+
+
 class GateStruct(C.Structure):
     _fields_ = [
         ('kind', C.c_int32),
@@ -104,6 +109,8 @@ _SIGNATURES = {
     'b200q_init_basis': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'b200q_adjoint_run': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_uint8), C.c_void_p]),
+    'b200q_qudit_apply_group': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                          C.POINTER(QuditOpStruct), C.c_int, C.c_int64, C.c_void_p]),
     'b200q_fock_bs_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_fock_squeezing_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_qudit_apply_structured': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),

@@ -542,3 +542,212 @@ extern "C" int b200q_fock_squeezing_matrix(const double* r_theta, int n_gates, i
   else fock_squeezing_matrix_kernel<double><<<n_gates, 64, 0, s>>>(r_theta, d, out);
   return cuda_err(cudaGetLastError(), "fock_squeezing_matrix launch");
 }
+
+// ---- groups of structured gates on one pair of modes: ONE pass over the state ------------------------------------------
+// A two-mode gate together with the one-mode gates that directly precede / follow it on its two modes (the squeezers in
+// front of the first beamsplitter layer of config 5, the phase shifter + beamsplitter pairs of an MZI mesh) runs on
+// the staged copy of the fibres of its mode pair: copy F fibres into shared memory, apply the gates one after the other
+// -- block-structured gates by the register blocks of run_sector (a one-mode gate is d blocks of d members along a row
+// or a column of the d x d fibre), diagonal gates elementwise --, write the fibres back.
+namespace {
+
+constexpr int kGroupMaxOps = 4;
+struct GroupOp {
+  int32_t kind;        // 0: sector blocks, 1: diagonal (a D-entry table)
+  int32_t n_sectors;
+  uint32_t wbase;      // offset of the op's packed weights in the shared table
+  struct Sec { uint8_t soff, m; int8_t sstep; uint8_t pad; uint16_t woff; } s[kMaxSectors];
+};
+struct GroupProg {
+  int32_t n_ops, total_w, d, D, F, Q, pitch, lanes_over_fibres;
+  int64_t S0, S1;      // strides of the tile digits (row, column)
+  GroupOp op[kGroupMaxOps];
+};
+
+// D-entry table of a diagonal gate over the (row, column) digits of the fibre: where = 0 row mode, 1 column mode,
+// 2 both (matrix index row * d + col), 3 both, reversed (col * d + row)
+template <typename Real>
+__global__ void pack_diag_kernel(const cxs<Real>* __restrict__ m, int d, int where, cxs<Real>* __restrict__ out) {
+  const int D = d * d, Dm = where >= 2 ? D : d;
+  for (int r = threadIdx.x; r < D; r += blockDim.x) {
+    const int ti = r / d, tj = r % d;
+    const int idx = where == 0 ? ti : where == 1 ? tj : where == 2 ? ti * d + tj : tj * d + ti;
+    out[r] = m[idx * Dm + idx];
+  }
+}
+
+template <typename Real, int MAXM>
+__global__ void __launch_bounds__(kSecThreads)
+qudit_group_kernel(cxs<Real>* __restrict__ state, const __grid_constant__ GroupProg P, const QuditGeom g,
+                   const cxs<Real>* __restrict__ wpacked) {
+  extern __shared__ __align__(16) unsigned char sec_smem[];
+  const int D = P.D, F = P.F, pitch = P.pitch;
+  cxs<Real>* W = reinterpret_cast<cxs<Real>*>(sec_smem);
+  cxs<Real>* tile = W + ((P.total_w + 1) & ~1);
+  long long* fb = reinterpret_cast<long long*>(tile + size_t(F) * pitch);
+  long long* toff = fb + F;
+  for (int e = threadIdx.x; e < P.total_w; e += kSecThreads) W[e] = wpacked[e];
+  const long long f0 = (long long)blockIdx.x * F;
+  for (int i = threadIdx.x; i < F; i += kSecThreads) fb[i] = (f0 + i < g.n_rest) ? expand_rest(g, f0 + i) : -1;
+  for (int r = threadIdx.x; r < D; r += kSecThreads) toff[r] = (long long)(r / P.d) * P.S0 + (long long)(r % P.d) * P.S1;
+  __syncthreads();
+  cxs<Real>* st = state + (long long)blockIdx.y * g.state_size;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.lanes_over_fibres) {   // neither mode is the lowest: consecutive FIBRES are contiguous in memory (runs >= d)
+    for (int r = warp; r < D; r += kSecThreads / 32) {
+      const long long o = toff[r];
+      for (int f = lane; f < F; f += 32)
+        if (fb[f] >= 0) cp_async_elem<sizeof(cxs<Real>)>(tile + f * pitch + r, st + fb[f] + o);
+    }
+  } else {                     // a mode is the lowest: the members of a fibre are runs of d contiguous amplitudes
+    for (int f = warp; f < F; f += kSecThreads / 32) {
+      const long long b = fb[f];
+      if (b < 0) continue;
+      for (int r = lane; r < D; r += 32) cp_async_elem<sizeof(cxs<Real>)>(tile + f * pitch + r, st + b + toff[r]);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int fibre = threadIdx.x % F, q = threadIdx.x / F;
+  for (int o = 0; o < P.n_ops; ++o) {
+    const GroupOp& op = P.op[o];
+    if (op.kind == 0) {
+      if (q < P.Q && fb[fibre] >= 0)
+        for (int s = q; s < op.n_sectors; s += P.Q)
+          run_sector<Real, MAXM>(op.s[s].m, tile + fibre * pitch + op.s[s].soff, (long long)op.s[s].sstep,
+                                 W + op.wbase + op.s[s].woff);
+    } else {
+      const cxs<Real>* dg = W + op.wbase;
+      for (int f = warp; f < F; f += kSecThreads / 32)
+        for (int r = lane; r < D; r += 32) {
+          const cxs<Real> w = dg[r], v = tile[f * pitch + r];
+          cxs<Real> y; y.x = w.x * v.x - w.y * v.y; y.y = w.x * v.y + w.y * v.x;
+          tile[f * pitch + r] = y;
+        }
+    }
+    __syncthreads();
+  }
+  if (P.lanes_over_fibres) {
+    for (int r = warp; r < D; r += kSecThreads / 32) {
+      const long long o = toff[r];
+      for (int f = lane; f < F; f += 32)
+        if (fb[f] >= 0) st[fb[f] + o] = tile[f * pitch + r];
+    }
+  } else {
+    for (int f = warp; f < F; f += kSecThreads / 32) {
+      const long long b = fb[f];
+      if (b < 0) continue;
+#pragma unroll 4
+      for (int r = lane; r < D; r += 32) st[b + toff[r]] = tile[f * pitch + r];
+    }
+  }
+}
+
+template <typename Real>
+int run_group(void* state, const QuditGeom& g, GroupProg& P, const b200q_qudit_op_t* ops, int n_ops,
+              const int32_t* tile_modes, int64_t batch, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return set_err(B200Q_EINVAL, "bad device");
+  if (!g_wpacked[dev]) {
+    const int rc = cuda_err(cudaMalloc(&g_wpacked[dev], size_t(kMaxSectors) * kMaxSecD * kMaxSecD * 16), "cudaMalloc(sector blocks)");
+    if (rc) return rc;
+  }
+  const int d = P.d;
+  cxs<Real>* wp = (cxs<Real>*)g_wpacked[dev];
+  P.total_w = 0;
+  for (int o = 0; o < n_ops; ++o) {
+    const b200q_qudit_op_t& in = ops[o];
+    GroupOp& op = P.op[o];
+    std::memset(&op, 0, sizeof op);
+    const bool on_row = in.modes[0] == tile_modes[0];          // first target of the op is the tile's row mode
+    const cxs<Real>* mat = (const cxs<Real>*)(uintptr_t)in.matrix;
+    op.wbase = (uint32_t)P.total_w;
+    if (in.structure == B200Q_QUDIT_DIAG) {
+      op.kind = 1;
+      const int where = in.n_targets == 1 ? (on_row ? 0 : 1) : (on_row ? 2 : 3);
+      pack_diag_kernel<Real><<<1, 256, 0, s>>>(mat, d, where, wp + op.wbase);
+      P.total_w += (P.D + 1) & ~1;
+      continue;
+    }
+    SectorTab T;
+    if (!make_sectors(in.structure, d, in.n_targets, 1, 1, &T)) return set_err(B200Q_EUNSUPPORTED, "gate structure not supported in a group");
+    pack_blocks_kernel<Real><<<4, 256, 0, s>>>(mat, T, wp + op.wbase);
+    op.kind = 0;
+    if (in.n_targets == 1) {        // d blocks of d members along the row (column) digit, all with the same d x d weights
+      op.n_sectors = d;
+      for (int t = 0; t < d; ++t) {
+        op.s[t].m = (uint8_t)d;
+        op.s[t].woff = 0;
+        if (on_row) { op.s[t].soff = (uint8_t)t; op.s[t].sstep = (int8_t)d; }
+        else { op.s[t].soff = (uint8_t)(t * d); op.s[t].sstep = 1; }
+      }
+    } else {
+      op.n_sectors = T.n_sectors;
+      for (int t = 0; t < T.n_sectors; ++t) {
+        const int i0 = T.s[t].i0, j0 = T.s[t].j0;   // digits of the op's first / second target
+        op.s[t].m = T.s[t].m;
+        op.s[t].woff = (uint16_t)T.s[t].woff;
+        if (on_row) { op.s[t].soff = (uint8_t)(i0 * d + j0); op.s[t].sstep = (int8_t)(d + T.dj); }
+        else { op.s[t].soff = (uint8_t)(j0 * d + i0); op.s[t].sstep = (int8_t)(T.dj * d + 1); }
+      }
+    }
+    P.total_w += (T.total_w + 1) & ~1;
+  }
+  if (size_t(P.total_w) > size_t(kMaxSectors) * kMaxSecD * kMaxSecD) return set_err(B200Q_EUNSUPPORTED, "group weights too large");
+  P.pitch = P.D | 1;
+  int F = 256;
+  while (F > 8 && size_t(F) * P.pitch * sizeof(cxs<Real>) > 56 * 1024) F >>= 1;
+  P.F = F;
+  P.Q = kSecThreads / F < 1 ? 1 : kSecThreads / F;
+  const size_t smem = size_t((P.total_w + 1) & ~1) * sizeof(cxs<Real>) + size_t(F) * P.pitch * sizeof(cxs<Real>) +
+                      size_t(F + P.D) * sizeof(long long);
+  if (smem > 200 * 1024) return set_err(B200Q_EUNSUPPORTED, "group does not fit shared memory");
+  const long long nblocks = (g.n_rest + F - 1) / F;
+  if (nblocks > 0x7fffffffLL) return set_err(B200Q_EUNSUPPORTED, "state too large for one launch");
+  dim3 grid((unsigned)nblocks, (unsigned)batch);
+#define B200Q_GROUP_LAUNCH(MAXM)                                                                                     \
+  do {                                                                                                               \
+    auto kern = qudit_group_kernel<Real, MAXM>;                                                                      \
+    const int rc = cuda_err(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),      \
+                            "cudaFuncSetAttribute(group)");                                                          \
+    if (rc) return rc;                                                                                               \
+    kern<<<grid, kSecThreads, smem, s>>>((cxs<Real>*)state, P, g, (const cxs<Real>*)wp);                             \
+  } while (0)
+  if (d <= 4) B200Q_GROUP_LAUNCH(4);
+  else if (d <= 8) B200Q_GROUP_LAUNCH(8);
+  else if (d <= 10) B200Q_GROUP_LAUNCH(10);
+  else B200Q_GROUP_LAUNCH(16);
+#undef B200Q_GROUP_LAUNCH
+  return cuda_err(cudaGetLastError(), "qudit group kernel launch");
+}
+
+}  // namespace
+
+extern "C" int b200q_qudit_apply_group(void* state, int n_modes, int d, int dtype, const int32_t* tile_modes,
+                                       const b200q_qudit_op_t* ops, int n_ops, int64_t batch, void* stream) {
+  if (!state || !tile_modes || !ops) return set_err(B200Q_EINVAL, "null argument");
+  if (dtype != B200Q_C64 && dtype != B200Q_C128) return set_err(B200Q_EINVAL, "bad dtype");
+  if (batch < 1 || batch > 65535) return set_err(B200Q_EINVAL, "bad batch");
+  if (n_ops < 1 || n_ops > kGroupMaxOps) return set_err(B200Q_EINVAL, "a group holds 1..4 gates");
+  if (d > kMaxSecD) return set_err(B200Q_EUNSUPPORTED, "cutoff above 16");
+  for (int o = 0; o < n_ops; ++o) {
+    const b200q_qudit_op_t& in = ops[o];
+    if (!in.matrix || in.n_targets < 1 || in.n_targets > 2) return set_err(B200Q_EINVAL, "bad gate in group");
+    if (in.structure < B200Q_QUDIT_DIAG || in.structure > B200Q_QUDIT_DIFFERENCE) return set_err(B200Q_EINVAL, "unstructured gate in group");
+    for (int j = 0; j < in.n_targets; ++j)
+      if (in.modes[j] != tile_modes[0] && in.modes[j] != tile_modes[1]) return set_err(B200Q_EINVAL, "gate leaves the mode pair of its group");
+    if (in.n_targets == 2 && in.modes[0] == in.modes[1]) return set_err(B200Q_EINVAL, "repeated mode");
+  }
+  QuditGeom g;
+  const char* err = "";
+  const int rc = qudit_make_geom(n_modes, d, tile_modes, 2, dtype == B200Q_C64 ? 8 : 16, &g, &err);
+  if (rc) return set_err(rc == -2 ? B200Q_EUNSUPPORTED : B200Q_EINVAL, err);
+  GroupProg P;
+  std::memset(&P, 0, sizeof P);
+  P.n_ops = n_ops; P.d = d; P.D = d * d;
+  P.S0 = g.stride[1]; P.S1 = g.stride[0];
+  P.lanes_over_fibres = g.low_stride == 1 ? 0 : 1;
+  if (dtype == B200Q_C64) return run_group<float>(state, g, P, ops, n_ops, tile_modes, batch, (cudaStream_t)stream);
+  return run_group<double>(state, g, P, ops, n_ops, tile_modes, batch, (cudaStream_t)stream);
+}

@@ -47,6 +47,80 @@ def qudit_apply_(flat: torch.Tensor, nmode: int, d: int, matrix: torch.Tensor, w
                                                   batch, engine._stream(flat)))
 
 
+GROUP_FOCK = os.environ.get('B200Q_FOCK_GROUP', '1') != '0'   # one pass for a two-mode gate + its one-mode neighbours
+GROUP_MAX_OPS = 4
+
+
+def qudit_apply_group_(flat: torch.Tensor, nmode: int, d: int, tile_modes, ops, batch: int = 1) -> None:
+    """`ops` = [(matrix, wires, structure), ...] applied in order, all inside the two `tile_modes`, with one read and one
+    write of the state (b200q_qudit_apply_group)."""
+    engine.require_cuda(flat, 'the Fock state tensor')
+    if not flat.is_contiguous() or flat.numel() != batch * d**nmode:
+        raise L.B200QError('state must be contiguous with batch * cutoff^nmode elements')
+    keep = [m.to(flat.dtype).contiguous() for m, _, _ in ops]          # alive until the launch is enqueued
+    arr = (L.QuditOpStruct * len(ops))()
+    for a, m, (_, wires, structure) in zip(arr, keep, ops):
+        a.n_targets = len(wires)
+        for j, w in enumerate(wires):
+            a.modes[j] = int(w)
+        a.structure = int(structure)
+        a.matrix = m.data_ptr()
+    tm = (C.c_int32 * 2)(int(tile_modes[0]), int(tile_modes[1]))
+    L.check(L.load().b200q_qudit_apply_group(flat.data_ptr(), nmode, d, engine.dtype_code(flat.dtype), tm, arr, len(ops),
+                                             batch, engine._stream(flat)))
+
+
+def plan_fock_groups(ops_info, nmode: int, d: int):
+    """Group the gates of a Fock circuit for `b200q_qudit_apply_group`.  `ops_info[i] = (wires, structure)`.
+    A structured two-mode gate absorbs the structured one-mode gates waiting on its two modes (they commute with
+    everything in between, which does not touch those modes) and, afterwards, the one-mode gates that follow it directly
+    on its modes.  A group is only formed where it saves a pass over the state: three or more gates, or two when the pair
+    contains the lowest mode (staged in shared memory anyway).  Returns [[gate indices in execution order], ...]."""
+    out, absorbing = [], []          # absorbing[g]: group g is a two-mode group that may still take one-mode gates
+    pend = {}                        # mode -> one-mode structured gates waiting for a two-mode gate on that mode
+    last = {}                        # mode -> index in `out` of the last group that touched the mode
+
+    def emit(group, modes, can_absorb):
+        out.append(group)
+        absorbing.append(can_absorb)
+        for m in modes:
+            last[m] = len(out) - 1
+
+    def flush(m):
+        for j in pend.pop(m, []):
+            emit([j], [m], False)
+
+    for i, (wires, structure) in enumerate(ops_info):
+        ok = GROUP_FOCK and structure != L.QUDIT_GENERAL and d <= 16 and nmode >= 2
+        if ok and len(wires) == 1:
+            m = wires[0]
+            g = last.get(m)
+            if (g is not None and absorbing[g] and len(out[g]) < GROUP_MAX_OPS and not pend.get(m)
+                    and (len(out[g]) >= 2 or (nmode - 1) in ops_info[out[g][-1]][0])):
+                out[g].append(i)     # follows its two-mode gate directly on this mode
+            else:
+                pend.setdefault(m, []).append(i)
+        elif ok and len(wires) == 2:
+            a, b = wires
+            pre = pend.get(a, []) + pend.get(b, [])
+            lowest = (nmode - 1) in (a, b)
+            if pre and len(pre) + 1 <= GROUP_MAX_OPS and (len(pre) >= 2 or lowest):
+                pend.pop(a, None)
+                pend.pop(b, None)
+                emit(sorted(pre) + [i], [a, b], True)
+            else:
+                flush(a)
+                flush(b)
+                emit([i], [a, b], True)
+        else:
+            for m in wires:
+                flush(m)
+            emit([i], list(wires), False)
+    for m in sorted(pend):
+        flush(m)
+    return out
+
+
 FOCK_TILE_MAX = 12288     # amplitudes of a fused pass's shared-memory tile (b200q_qudit_fused)
 
 
@@ -775,13 +849,27 @@ class QumodeCircuit(nn.Module):
                 for tile, ids in self.__dict__['_fock_plan']:
                     qudit_fused_(flat, n, d, tile, [(self.operators[i].wires, offs[i]) for i in ids], buf, flat.shape[0])
             else:
-                for op, m in zip(self.operators, mats):
-                    qudit_apply_(flat, n, d, m, op.wires, flat.shape[0], op._structure)
+                ops = list(self.operators)
+                key = tuple((tuple(op.wires), op._structure) for op in ops)
+                if self.__dict__.get('_group_key') != key:
+                    self.__dict__['_groups'] = plan_fock_groups([(list(w), st) for w, st in key], n, d)
+                    self.__dict__['_group_key'] = key
+                for grp in self.__dict__['_groups']:
+                    if len(grp) == 1:
+                        op = ops[grp[0]]
+                        qudit_apply_(flat, n, d, mats[grp[0]], op.wires, flat.shape[0], op._structure)
+                    else:
+                        pair = next(ops[i].wires for i in grp if len(ops[i].wires) == 2)
+                        qudit_apply_group_(flat, n, d, pair, [(mats[i], ops[i].wires, ops[i]._structure) for i in grp],
+                                           flat.shape[0])
         self.state = flat.reshape([-1] + [d] * n)
         return self.state
 
     def fock_plan_stats(self) -> dict:
         """Passes and gates per pass of the fused plan of the last forward (diagnostics / bench)."""
         plan = self.__dict__.get('_fock_plan') or []
+        if not plan and self.__dict__.get('_groups'):
+            grp = self.__dict__['_groups']
+            return {'gates': len(self.operators), 'passes': len(grp), 'gates_per_pass': [len(x) for x in grp]}
         return {'gates': len(self.operators), 'passes': len(plan), 'gates_per_pass': [len(ids) for _, ids in plan],
                 'tiles': [t for t, _ in plan]}

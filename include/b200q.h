@@ -212,6 +212,19 @@ int b200q_qudit_apply(void* state, int n_modes, int d, int dtype, const void* ma
 int b200q_qudit_apply_structured(void* state, int n_modes, int d, int dtype, const void* matrix, const int32_t* modes,
                                  int n_targets, int structure, int64_t batch, void* stream);
 
+/* A two-mode structured gate together with the structured one-mode (or diagonal) gates that directly precede / follow it
+ * on its two modes -- squeezers in front of a beamsplitter, the phase shifter + beamsplitter pairs of an MZI mesh
+ * (photonic/circuit.py applies them one by one, each a pass over the state) -- in ONE pass: `ops` (1..4, applied in
+ * order) all act inside `tile_modes` (two modes); `matrix` is the device pointer of the gate's dense d^k x d^k matrix. */
+typedef struct b200q_qudit_op {
+  int32_t n_targets;
+  int32_t modes[2];     /* modes[0] = most significant digit of the matrix index */
+  int32_t structure;    /* B200Q_QUDIT_DIAG .. B200Q_QUDIT_DIFFERENCE */
+  uint64_t matrix;      /* device pointer */
+} b200q_qudit_op_t;
+int b200q_qudit_apply_group(void* state, int n_modes, int d, int dtype, const int32_t* tile_modes,
+                            const b200q_qudit_op_t* ops, int n_ops, int64_t batch, void* stream);
+
 /* Fock transformation matrices of a whole gate class in one launch (the reference runs Python-level recurrences over the
  * cutoff per gate: photonic/gate.py:347-374 beamsplitter family, 1091-1114 squeezer; arXiv:2004.11002 Eq. 74-75, 51-52).
  * `mixing`: n_gates x 2 x 2 complex128 mode-mixing matrices on the device; `r_theta`: n_gates x 2 doubles.

@@ -302,3 +302,88 @@ def test_native_fock_matrices_match_the_torch_recurrences(cutoff):
         # both run the same recurrence in float64; its rounding noise grows with the cutoff (6e-13 at 16)
         assert float((a - b).abs().max()) < max(1e-13, 1e-15 * cutoff**4) * max(1.0, float(b.abs().max()))
         assert torch.equal(a == 0, b == 0)          # the structural zeros are exact in both
+
+
+def test_fock_group_planner_keeps_the_gate_order():
+    """`plan_fock_groups`: every gate exactly once, and any two gates that share a mode keep their circuit order
+    (random circuits of structured / unstructured one- and two-mode gates)."""
+    from deepquantum_b200 import _lib as L
+    from deepquantum_b200 import photonic as ph
+    rng = np.random.default_rng(4)
+    sizes = []
+    for trial in range(60):
+        n = int(rng.integers(2, 7))
+        info = []
+        for _ in range(int(rng.integers(1, 40))):
+            if rng.integers(3) == 0:
+                a, b = rng.choice(n, size=2, replace=False)
+                info.append(([int(a), int(b)], int(rng.choice([L.QUDIT_NUMBER, L.QUDIT_DIFFERENCE, L.QUDIT_DIAG, L.QUDIT_GENERAL]))))
+            else:
+                info.append(([int(rng.integers(n))], int(rng.choice([L.QUDIT_DENSE1, L.QUDIT_DIAG, L.QUDIT_GENERAL]))))
+        groups = ph.plan_fock_groups(info, n, 4)
+        pos = {i: (gi, k) for gi, grp in enumerate(groups) for k, i in enumerate(grp)}
+        assert sorted(pos) == list(range(len(info)))
+        for i in range(len(info)):
+            for j in range(i + 1, len(info)):
+                if set(info[i][0]) & set(info[j][0]):
+                    assert pos[i] < pos[j], (trial, i, j)
+        for grp in groups:
+            assert len(grp) <= ph.GROUP_MAX_OPS
+            if len(grp) > 1:
+                two = [i for i in grp if len(info[i][0]) == 2]
+                assert len(two) == 1 and all(info[i][1] != L.QUDIT_GENERAL for i in grp)
+                assert all(set(info[i][0]) <= set(info[two[0]][0]) for i in grp)
+            sizes.append(len(grp))
+    assert max(sizes) >= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rdtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('nmode,cutoff', [(4, 5), (3, 10), (5, 3), (3, 16)])
+def test_grouped_fock_gates_against_host_contraction(nmode, cutoff, rdtype):
+    """Groups of a two-mode gate with the one-mode gates around it (b200q_qudit_apply_group: squeezers / displacements /
+    phase shifters / Kerr before and after beamsplitters, MZIs, two-mode squeezers and cross-Kerr gates, on every mode
+    pair incl. the lowest mode and reversed wires) through `QumodeCircuit.forward` against the oracle's contraction."""
+    import statevec_oracle as so
+    from deepquantum_b200 import photonic as ph
+    n, d = nmode, cutoff
+    g = torch.Generator().manual_seed(9)
+    rnd = lambda s=1.0: float(torch.rand(1, generator=g) * s)   # noqa: E731
+    cir = dq.QumodeCircuit(n, [(0.6, [1] + [0] * (n - 1)), (0.8, [0] * (n - 1) + [2 if d > 2 else 1])], cutoff=d)
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    for k, (a, b) in enumerate(pairs):
+        cir.s(a, rnd(0.3), rnd(6))
+        cir.ps(b, rnd(6))
+        if k % 3 == 0:
+            cir.d(b, rnd(0.2), rnd(6))
+        if k % 4 == 0:
+            cir.bs([a, b], [rnd(6), rnd(6)])
+        elif k % 4 == 1:
+            cir.mzi([a, b], [rnd(6), rnd(6)])
+        elif k % 4 == 2:
+            cir.s2([a, b], rnd(0.2), rnd(6))
+        else:
+            cir.ck([a, b], rnd(1))
+        cir.k(a, rnd(1))
+        cir.ps(b, rnd(6))
+    cir.to('cuda', rdtype)
+    out = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    stats = cir.fock_plan_stats()
+    assert stats['passes'] < stats['gates'] and max(stats['gates_per_pass']) >= 3
+    cdt = torch.complex128 if rdtype == torch.float64 else torch.complex64
+    mats = cir.build_matrices(cdt, 'cuda')
+    psi = cir.init_state.state.reshape(1, -1).cpu().numpy().astype(np.complex128)
+    for op, m in zip(cir.operators, mats):
+        psi = so.evolve_state(psi, m.cpu().numpy().astype(np.complex128), n, list(op.wires), d)
+    ref = psi.reshape(-1)
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < (1e-11 if rdtype == torch.float64 else 3e-5), err
+    old = ph.GROUP_FOCK
+    ph.GROUP_FOCK = False
+    try:
+        cir.__dict__['_group_key'] = None
+        single = cir().reshape(-1).cpu().numpy().astype(np.complex128)
+    finally:
+        ph.GROUP_FOCK = old
+        cir.__dict__['_group_key'] = None
+    assert np.linalg.norm(single - ref) / np.linalg.norm(ref) < (1e-11 if rdtype == torch.float64 else 3e-5)

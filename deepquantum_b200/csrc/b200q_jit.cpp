@@ -281,6 +281,7 @@ int jit_prepare(Plan& plan, int threads, bool with_remote_last) {
         if (const char* e = getenv("B200Q_JIT_IPT")) go.items_per_thread = atoi(e);
         if (go.items_per_thread == 2 && plan.opt.chunk_bits == 12) go.min_blocks = 3;
         if (go.items_per_thread == 2 && plan.opt.chunk_bits == 13) go.min_blocks = 1;
+        if (const char* e = getenv("B200Q_JIT_MIN_BLOCKS")) go.min_blocks = atoi(e);   // A/B: CTAs per SM the compiler must fit
         if (const char* e = getenv("B200Q_JIT_PREFETCH")) go.prefetch = atoi(e);
         if (const char* e = getenv("B200Q_JIT_DEBUG_SKIP_OPS")) go.debug_skip_ops = atoi(e);
         if (const char* e = getenv("B200Q_JIT_DEBUG_ONE_TILE")) go.debug_one_tile = atoi(e);

@@ -111,6 +111,7 @@ _SIGNATURES = {
                                     C.POINTER(C.c_uint8), C.c_void_p]),
     'b200q_qudit_apply_group': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
                                           C.POINTER(QuditOpStruct), C.c_int, C.c_int64, C.c_void_p]),
+    'b200q_plan_pass_gate_ids': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int]),
     'b200q_fock_bs_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_fock_squeezing_matrix': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'b200q_qudit_apply_structured': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32),

@@ -797,6 +797,21 @@ int b200q_plan_pass_gates(const b200q_plan_t* plan, int i) {
   return plan->p->pass_gate_count[i];
 }
 
+int b200q_plan_pass_gate_ids(const b200q_plan_t* plan, int i, int32_t* out, int cap) {
+  if (!plan || i < 0 || i >= (int)plan->p->passes.size()) return set_err(B200Q_EINVAL, "bad pass index");
+  const b200q_pass_t& P = plan->p->passes[i];
+  int n = 0;
+  for (int o = 0; o < P.n_ops; ++o) {
+    const int32_t id = (int32_t)P.ops[o].gate_id;
+    bool seen = false;
+    for (int q = 0; q < n && q < cap && !seen; ++q) seen = out && out[q] == id;
+    if (seen) continue;
+    if (out && n < cap) out[n] = id;
+    ++n;
+  }
+  return n;
+}
+
 int b200q_plan_export(const b200q_plan_t* plan, void* buf, size_t buf_size, size_t* needed) {
   if (!plan) return set_err(B200Q_EINVAL, "null plan");
   const size_t need = plan->p->passes.size() * sizeof(b200q_pass_t);

@@ -13,6 +13,8 @@ sees local qubits.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -157,6 +159,10 @@ class ShardedProgram:
         self.g = world_size.bit_length() - 1
         self.nl = nqubit - self.g
         self.mode = mode
+        # 'perm' mode: a segment is cut where its passes get sparse (fewer than this many gates); the tail gates run at the
+        # start of the next segment, fused with its abundant first gates, and the exchange rides on a DENSE last pass
+        self.trim = int(os.environ.get('B200Q_SHARD_TRIM', '20')) if mode == 'perm' else 0
+        self.n_deferred = 0
         self.plans = {}
         self._schedule()
 
@@ -224,6 +230,12 @@ class ShardedProgram:
                         first_blocked = tm
                     bfull |= tm
                     bdiag |= dm
+            if remaining and self.trim and g > 0 and first_blocked is not None:
+                seg, back = self._trim_segment(seg)
+                for i in back:
+                    done[i] = False
+                remaining += len(back)
+                self.n_deferred += len(back)
             if remaining:
                 if g == 0 or first_blocked is None:
                     raise RuntimeError('sharded scheduler stalled (internal error)')
@@ -306,6 +318,36 @@ class ShardedProgram:
         assert phys == list(range(n)), phys
         self.steps, self.n_swaps = steps, nswaps
         self.n_segments = sum(1 for s in steps if s[0] == 'seg')
+
+    def _trim_segment(self, seg):
+        """Cut a segment that is followed by an exchange where its passes get sparse.  The gates that can run without a
+        global qubit thin out towards the end of a segment (long dependency chains), and the fused planner then spends
+        whole passes over the shard on a handful of gates -- the last of them, with 1-3 gates, carries the exchange.
+        The segment is planned once with rank-independent stand-ins (every gate active, rank selectors dropped), kept up
+        to its last pass with at least `self.trim` gates, and the gates of the later passes go back to the pending list:
+        they run at the start of the next segment.  Returns (kept entries, record indices to put back).  The decision
+        uses nothing rank-dependent, so every rank cuts at the same gate."""
+        if len(seg) < 2 * self.trim:
+            return seg, []
+        proxies, owner = [], []
+        for k, (i, kind, pt, ctrl, adj, active, fix, hint) in enumerate(seg):
+            if fix is not None:
+                kind, hint = L.GATE_DIAG, 0
+            if len(pt) == 0:
+                if not ctrl:
+                    continue                 # a pure per-rank phase: no local bit, commutes with everything local
+                pt, ctrl = (ctrl[0],), tuple(ctrl[1:])
+            proxies.append(L.make_gate(kind, pt, ctrl, 0, adj, hint))
+            owner.append(k)
+        plan = engine.FusedPlan(self.nl, torch.complex64, proxies)
+        counts = [plan.pass_gates(p) for p in range(plan.n_passes)]
+        dense = [p for p, c in enumerate(counts) if c >= self.trim]
+        if not dense or dense[-1] == len(counts) - 1:
+            return seg, []
+        drop = set()
+        for p in range(dense[-1] + 1, len(counts)):
+            drop.update(owner[q] for q in plan.pass_gate_ids(p))
+        return [e for k, e in enumerate(seg) if k not in drop], [seg[k][0] for k in sorted(drop)]
 
     def _localise(self, i, rec, phys):
         """Rewrite record i for this rank: physical local bits, global controls resolved against the rank,

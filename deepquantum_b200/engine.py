@@ -73,6 +73,14 @@ class FusedPlan:
     def pass_gates(self, i: int) -> int:
         return L.load().b200q_plan_pass_gates(self._h, i)
 
+    def pass_gate_ids(self, i: int) -> list:
+        """Indices of the gates (of the list the plan was created from) that pass `i` applies."""
+        buf = (C.c_int32 * 64)()
+        n = L.load().b200q_plan_pass_gate_ids(self._h, i, buf, 64)
+        if n < 0:
+            L.check(n)
+        return list(buf[:min(n, 64)])
+
     def export(self) -> bytes:
         need = C.c_size_t()
         lib = L.load()

@@ -103,6 +103,10 @@ int b200q_plan_create(int n_qubits, int dtype, const b200q_gate_t* gates, int n_
                       const b200q_plan_options_t* options, b200q_plan_t** plan_out);
 void b200q_plan_destroy(b200q_plan_t* plan);
 int b200q_plan_get_stats(const b200q_plan_t* plan, b200q_plan_stats_t* stats_out);
+/* Indices (into the `gates` array of b200q_plan_create) of the gates applied by pass `i`, in order of first use; returns
+ * their number (writes at most `cap`).  Lets a caller that schedules several plans (the sharded path) see where a
+ * plan's passes get sparse. */
+int b200q_plan_pass_gate_ids(const b200q_plan_t* plan, int i, int32_t* out, int cap);
 /* Number of gates executed by pass `pass_index` (for per-pass reporting). */
 int b200q_plan_pass_gates(const b200q_plan_t* plan, int pass_index);
 /* Copies the raw pass descriptors (b200q_pass_t, csrc/b200q_program.h) for inspection by tests.

@@ -342,8 +342,8 @@ def test_fused_pass_and_bit_permutation(cdtype, world):
     assert np.linalg.norm(got - full) / np.linalg.norm(full) < tol
 
 
-@pytest.mark.parametrize('world', [2, 4, 8])
-def test_sharded_perm_schedule_all_ranks_in_one_process(world):
+@pytest.mark.parametrize('world,circuit', [(2, 'fixture'), (4, 'fixture'), (8, 'fixture'), (4, 'c2'), (8, 'c2')])
+def test_sharded_perm_schedule_all_ranks_in_one_process(world, circuit):
     """The 'perm' schedule of the sharded path (exchanges = bit permutations done by the fused last pass of a
     segment, layout restored by one permuting exchange): every rank's `ShardedProgram` stepped in lockstep in
     ONE process, local segments and fused exchanges executed by the CPU emulator of the kernel body, against the
@@ -356,10 +356,15 @@ def test_sharded_perm_schedule_all_ranks_in_one_process(world):
     from helpers import hostemu
     from test_distributed_gloo import _build
 
-    n = 10
+    n = 10 if circuit == 'fixture' else 13
     g = world.bit_length() - 1
     nl = n - g
-    dense = _build(dq.QubitCircuit(n), n)
+    if circuit == 'fixture':
+        dense = _build(dq.QubitCircuit(n), n)
+    else:   # the bench generator, deep enough that segments span several passes: the scheduler cuts their sparse tails
+        from deepquantum_b200 import workloads as wl
+        dense = dq.QubitCircuit(n)
+        wl.apply_spec(dense, wl.random_clifford_rx_spec(n, 14), torch.complex128)
     dense.to(torch.double)
     low = dense._get_program().low
     mats = low.build_matrices(torch.complex128, 'cpu').detach()
@@ -414,6 +419,9 @@ def test_sharded_perm_schedule_all_ranks_in_one_process(world):
         p.fused_exchanges, p._skip_next = 0, False
     assert all(len(p.steps) == len(progs[0].steps) for p in progs)
     assert any(s[0] == 'xperm' for s in progs[0].steps)
+    assert len({p.n_deferred for p in progs}) == 1          # every rank cuts its segments at the same gates
+    if circuit == 'c2':
+        assert progs[0].n_deferred > 0
     for si in range(len(progs[0].steps)):
         what = [progs[r].run_step(si, states[r], mats, ex, True) for r in range(world)]
         assert len(set(what)) == 1, what

@@ -159,9 +159,13 @@ class ShardedProgram:
         self.g = world_size.bit_length() - 1
         self.nl = nqubit - self.g
         self.mode = mode
-        # 'perm' mode: a segment is cut where its passes get sparse (fewer than this many gates); the tail gates run at the
-        # start of the next segment, fused with its abundant first gates, and the exchange rides on a DENSE last pass
-        self.trim = int(os.environ.get('B200Q_SHARD_TRIM', '20')) if mode == 'perm' else 0
+        # 'perm' mode, B200Q_SHARD_TRIM=k: a segment is cut where its passes get sparse (fewer than k gates); the tail gates
+        # run at the start of the next segment, fused with its abundant first gates, and the exchange rides on a DENSE
+        # last pass.  Measured on 8 GPUs with k = 20: 30 qubits 38.7 ms (53 passes, 10 exchanges) against 40.0 ms (58, 9),
+        # but 33 qubits 238.3 ms (45 passes) against 229.9 ms (48): an exchanging pass costs its NVLink time PLUS the
+        # arithmetic it carries (the remote stores back-pressure the CTAs), so a dense one gives back what the saved
+        # passes won.  Off by default.
+        self.trim = int(os.environ.get('B200Q_SHARD_TRIM', '0')) if mode == 'perm' else 0
         self.n_deferred = 0
         self.plans = {}
         self._schedule()

@@ -413,7 +413,11 @@ def test_sharded_perm_schedule_all_ranks_in_one_process(world, circuit):
             assert rc == 0, err.value.decode()
 
     states = [State(r) for r in range(world)]
-    progs = [ShardedProgram(low, n, world, r, 'perm') for r in range(world)]
+    os.environ['B200Q_SHARD_TRIM'] = '20' if circuit == 'c2' else '0'      # the segment cut is an option (off by default)
+    try:
+        progs = [ShardedProgram(low, n, world, r, 'perm') for r in range(world)]
+    finally:
+        os.environ.pop('B200Q_SHARD_TRIM', None)
     ex = Exec()
     for p in progs:
         p.fused_exchanges, p._skip_next = 0, False

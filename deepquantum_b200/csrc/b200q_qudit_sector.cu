@@ -79,9 +79,12 @@ int make_sectors(int structure, int d, int k, int64_t S0, int64_t S1, SectorTab*
   return 1;
 }
 
-// packed blocks: W[woff + r * mp + c] = M[row(r)][row(c)], row(t) = matrix index of member t of the sector
+// packed blocks: W[woff + r * mp + c] = post[row(r)] * M[row(r)][row(c)] * pre[row(c)], row(t) = matrix index of member t
+// of the sector; `pre` / `post` (or null): diagonal gates applied right before / after the gate, folded into its blocks
 template <typename Real>
-__global__ void pack_blocks_kernel(const cxs<Real>* __restrict__ m, const SectorTab T, cxs<Real>* __restrict__ out) {
+__global__ void pack_blocks_kernel(const cxs<Real>* __restrict__ m, const SectorTab T, cxs<Real>* __restrict__ out,
+                                   const cxs<Real>* __restrict__ pre = nullptr,
+                                   const cxs<Real>* __restrict__ post = nullptr) {
   const int D = T.k == 2 ? T.d * T.d : T.d;
   for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < T.total_w; e += blockDim.x * gridDim.x) {
     int s = 0;
@@ -92,6 +95,8 @@ __global__ void pack_blocks_kernel(const cxs<Real>* __restrict__ m, const Sector
       const int ir = T.s[s].i0 + r, jr = T.s[s].j0 + T.dj * r, ic = T.s[s].i0 + c, jc = T.s[s].j0 + T.dj * c;
       const int row = T.k == 2 ? ir * T.d + jr : ir, col = T.k == 2 ? ic * T.d + jc : ic;
       v = m[row * D + col];
+      if (pre) { const cxs<Real> w = pre[col]; const Real x = v.x * w.x - v.y * w.y; v.y = v.x * w.y + v.y * w.x; v.x = x; }
+      if (post) { const cxs<Real> w = post[row]; const Real x = v.x * w.x - v.y * w.y; v.y = v.x * w.y + v.y * w.x; v.x = x; }
     }
     out[e] = v;
   }
@@ -290,10 +295,18 @@ qudit_diag_kernel(cxs<Real>* __restrict__ state, const cxs<Real>* __restrict__ m
 
 void* g_wpacked[64] = {nullptr};
 
+bool group_fold_enabled() {      // B200Q_FOCK_FOLD=0: diagonal neighbours go through the staged group kernel (A/B)
+  const char* e = getenv("B200Q_FOCK_FOLD");
+  return !(e && atoi(e) == 0);
+}
+
 bool sector_staged_enabled() {   // B200Q_FOCK_STAGED=0: direct register kernel on every mode (A/B measurements)
   const char* e = getenv("B200Q_FOCK_STAGED");
   return !(e && atoi(e) == 0);
 }
+
+template <typename Real>
+int launch_sectors(void* state, const QuditGeom& g, const SectorTab& T, int64_t batch, cudaStream_t s, int dev);
 
 template <typename Real>
 int run_sectors(void* state, const QuditGeom& g, const SectorTab& T, const void* matrix, int64_t batch, cudaStream_t s) {
@@ -305,6 +318,12 @@ int run_sectors(void* state, const QuditGeom& g, const SectorTab& T, const void*
     if (rc) return rc;
   }
   pack_blocks_kernel<Real><<<4, 256, 0, s>>>((const cxs<Real>*)matrix, T, (cxs<Real>*)g_wpacked[dev]);
+  return launch_sectors<Real>(state, g, T, batch, s, dev);
+}
+
+// the packed blocks of T are in g_wpacked[dev]: direct register kernel, or the staged variant on the lowest mode
+template <typename Real>
+int launch_sectors(void* state, const QuditGeom& g, const SectorTab& T, int64_t batch, cudaStream_t s, int dev) {
   if (g.low_stride == 1 && g.k == 2 && sector_staged_enabled()) {   // (one-mode gates: the direct kernel is faster)
     StagedCfg cfg;
     cfg.pitch = g.D | 1;
@@ -567,12 +586,20 @@ struct GroupProg {
 // D-entry table of a diagonal gate over the (row, column) digits of the fibre: where = 0 row mode, 1 column mode,
 // 2 both (matrix index row * d + col), 3 both, reversed (col * d + row)
 template <typename Real>
-__global__ void pack_diag_kernel(const cxs<Real>* __restrict__ m, int d, int where, cxs<Real>* __restrict__ out) {
+__global__ void pack_diag_kernel(const cxs<Real>* __restrict__ m, int d, int where, cxs<Real>* __restrict__ out,
+                                 int accumulate = 0) {
   const int D = d * d, Dm = where >= 2 ? D : d;
   for (int r = threadIdx.x; r < D; r += blockDim.x) {
     const int ti = r / d, tj = r % d;
     const int idx = where == 0 ? ti : where == 1 ? tj : where == 2 ? ti * d + tj : tj * d + ti;
-    out[r] = m[idx * Dm + idx];
+    cxs<Real> v = m[idx * Dm + idx];
+    if (accumulate) {      // product with the table already there (several diagonal gates in a row)
+      const cxs<Real> w = out[r];
+      const Real x = v.x * w.x - v.y * w.y;
+      v.y = v.x * w.y + v.y * w.x;
+      v.x = x;
+    }
+    out[r] = v;
   }
 }
 
@@ -655,6 +682,33 @@ int run_group(void* state, const QuditGeom& g, GroupProg& P, const b200q_qudit_o
   }
   const int d = P.d;
   cxs<Real>* wp = (cxs<Real>*)g_wpacked[dev];
+  {
+    // one block-structured two-mode gate whose neighbours are all DIAGONAL (phase shifter / Kerr + beamsplitter, the pairs
+    // of an MZI mesh): the diagonals are folded into the gate's packed blocks, W' = post . W . pre, and the gate runs
+    // as if it were alone -- direct register kernel, no staging
+    int main_op = -1, n_main = 0;
+    for (int o = 0; o < n_ops; ++o)
+      if (ops[o].structure != B200Q_QUDIT_DIAG) { main_op = o; ++n_main; }
+    if (n_main == 1 && ops[main_op].n_targets == 2 && ops[main_op].modes[0] == tile_modes[0] && group_fold_enabled()) {
+      SectorTab T;
+      if (!make_sectors(ops[main_op].structure, d, 2, P.S0, P.S1, &T)) return set_err(B200Q_EUNSUPPORTED, "gate structure not supported in a group");
+      cxs<Real>* pre = wp + 4096;          // D <= 256 entries each, behind the packed blocks (<= 3 000 elements)
+      cxs<Real>* post = pre + 256;
+      int n_pre = 0, n_post = 0;
+      for (int o = 0; o < n_ops; ++o) {
+        if (o == main_op) continue;
+        const b200q_qudit_op_t& in = ops[o];
+        const bool on_row = in.modes[0] == tile_modes[0];
+        const int where = in.n_targets == 1 ? (on_row ? 0 : 1) : (on_row ? 2 : 3);
+        int& cnt = o < main_op ? n_pre : n_post;
+        pack_diag_kernel<Real><<<1, 256, 0, s>>>((const cxs<Real>*)(uintptr_t)in.matrix, d, where, o < main_op ? pre : post, cnt > 0);
+        ++cnt;
+      }
+      pack_blocks_kernel<Real><<<4, 256, 0, s>>>((const cxs<Real>*)(uintptr_t)ops[main_op].matrix, T, wp,
+                                                 n_pre ? pre : nullptr, n_post ? post : nullptr);
+      return launch_sectors<Real>(state, g, T, batch, s, dev);
+    }
+  }
   P.total_w = 0;
   for (int o = 0; o < n_ops; ++o) {
     const b200q_qudit_op_t& in = ops[o];

@@ -74,8 +74,9 @@ def plan_fock_groups(ops_info, nmode: int, d: int):
     """Group the gates of a Fock circuit for `b200q_qudit_apply_group`.  `ops_info[i] = (wires, structure)`.
     A structured two-mode gate absorbs the structured one-mode gates waiting on its two modes (they commute with
     everything in between, which does not touch those modes) and, afterwards, the one-mode gates that follow it directly
-    on its modes.  A group is only formed where it saves a pass over the state: three or more gates, or two when the pair
-    contains the lowest mode (staged in shared memory anyway).  Returns [[gate indices in execution order], ...]."""
+    on its modes.  A group is only formed where it saves a pass over the state: three or more gates, two when the pair
+    contains the lowest mode (staged in shared memory anyway), or any number of DIAGONAL neighbours (phase shifter /
+    Kerr next to a beamsplitter: folded into the gate's packed blocks, the gate then costs what it costs alone).  Returns [[gate indices in execution order], ...]."""
     out, absorbing = [], []          # absorbing[g]: group g is a two-mode group that may still take one-mode gates
     pend = {}                        # mode -> one-mode structured gates waiting for a two-mode gate on that mode
     last = {}                        # mode -> index in `out` of the last group that touched the mode
@@ -96,7 +97,7 @@ def plan_fock_groups(ops_info, nmode: int, d: int):
             m = wires[0]
             g = last.get(m)
             if (g is not None and absorbing[g] and len(out[g]) < GROUP_MAX_OPS and not pend.get(m)
-                    and (len(out[g]) >= 2 or (nmode - 1) in ops_info[out[g][-1]][0])):
+                    and (len(out[g]) >= 2 or (nmode - 1) in ops_info[out[g][-1]][0] or structure == L.QUDIT_DIAG)):
                 out[g].append(i)     # follows its two-mode gate directly on this mode
             else:
                 pend.setdefault(m, []).append(i)
@@ -104,7 +105,8 @@ def plan_fock_groups(ops_info, nmode: int, d: int):
             a, b = wires
             pre = pend.get(a, []) + pend.get(b, [])
             lowest = (nmode - 1) in (a, b)
-            if pre and len(pre) + 1 <= GROUP_MAX_OPS and (len(pre) >= 2 or lowest):
+            all_diag = all(ops_info[j][1] == L.QUDIT_DIAG for j in pre)     # folded into the gate's blocks: free
+            if pre and len(pre) + 1 <= GROUP_MAX_OPS and (len(pre) >= 2 or lowest or all_diag):
                 pend.pop(a, None)
                 pend.pop(b, None)
                 emit(sorted(pre) + [i], [a, b], True)

@@ -82,5 +82,28 @@ def main():
                       'frac_gate_passes': round(len(cir.operators) * nbytes / (ms_gates * 1e-3) / 1e9 / pk, 3)}), flush=True)
 
 
+def mesh():
+    """Clements mesh of (phase shifter, beamsplitter) pairs -- the unit cell of a programmable interferometer -- at
+    config-5 size: 28 pairs = 56 gates.  With the diagonal neighbours folded into the beamsplitter blocks: 28 passes."""
+    import deepquantum_b200 as dq
+    n, d = 8, 10
+    cir = dq.QumodeCircuit(n, [1, 0, 1, 0, 1, 0, 1, 0], cutoff=d, backend='fock', basis=False)
+    g = torch.Generator().manual_seed(1)
+    for layer in range(n):
+        for a in range(layer % 2, n - 1, 2):
+            cir.ps(a, float(torch.rand(1, generator=g) * 6))
+            cir.bs([a, a + 1], [float(torch.rand(1, generator=g) * 6), float(torch.rand(1, generator=g) * 6)])
+    cir.to('cuda')
+    with torch.no_grad():
+        ms = timed(lambda: cir())
+    st = cir.fock_plan_stats()
+    print(json.dumps({'mesh': 'Clements, (ps, bs) pairs, 8 modes x cutoff 10', 'gates': st['gates'], 'passes': st['passes'],
+                      'ms_forward': round(ms, 3), 'group': os.environ.get('B200Q_FOCK_GROUP', '1'),
+                      'fold': os.environ.get('B200Q_FOCK_FOLD', '1')}), flush=True)
+
+
 if __name__ == '__main__':
-    main()
+    if '--mesh' in sys.argv:
+        mesh()
+    else:
+        main()

@@ -746,6 +746,13 @@ class QubitCircuit(Operation):
         assert not self.den_mat, 'Currently NOT supported'
         self.add(Reset(nqubit=self.nqubit, wires=wires, postselect=postselect))
 
+    def move(self, wire1: int, wire2: int, postselect: int | None = 0) -> None:
+        """Move (reference circuit.py:1619-1622, gate.py:3141-3168): a reset of `wire2` followed by a swap of the two
+        wires.  Added as its two constituent operations (the reference wraps the same pair in one `Move` module; its
+        quasi-probability decomposition for circuit cutting is outside the accelerated path)."""
+        self.reset(wire2, postselect=postselect)
+        self.swap([wire1, wire2])
+
 
 class _ShardedExpectation(torch.autograd.Function):
     """Exact expectation values of a sharded final state, differentiable w.r.t. the matrix buffer by the adjoint

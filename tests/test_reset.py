@@ -139,3 +139,28 @@ def test_gpu_sampled_reset_is_a_projective_measurement():
             proj = before[:, a, :, :, b, :]
             cands.append(np.linalg.norm(after[:, 0, :, :, 0, :] - proj / np.linalg.norm(proj)))
     assert min(cands) < 1e-10
+
+
+def test_move_is_reset_then_swap():
+    """`cir.move(a, b)` (reference gate.py:3141-3168: Reset on wires[1], then Swap) through the host logic against the
+    oracle: the state of wire a ends up on wire b and wire a is |0>."""
+    import gates_np
+    n = 4
+    cir = dq.QubitCircuit(n)
+    cir.hlayer()
+    cir.rx(1, 0.7)
+    cir.cnot(1, 2)
+    cir.move(1, 3)
+    cir.ry(0, 0.3)
+    cir.to(torch.double)
+    assert [type(op).__name__ for op in cir.operators][-3:] == ['Reset', 'Swap', 'Ry']
+    out = _host_run(cir, torch.zeros(0), np.complex128)[0]
+    h = np.array([[1, 1], [1, -1]]) * np.float32(2 ** -0.5).astype(np.float64)
+    ops = [(h, [w], []) for w in range(n)] + [(gates_np.rx(np.float32(0.7)), [1], []), (gates_np.X, [2], [1])]
+    psi = so.run_circuit(ops, n)
+    psi = so.reset_wires(psi, n, [3], 0)
+    swap = np.eye(4)[[0, 2, 1, 3]]
+    psi = so.run_circuit([(swap, [1, 3], []), (gates_np.ry(np.float32(0.3)), [0], [])], n, psi)
+    assert np.abs(out - psi).max() < 1e-7
+    t = out.reshape([2] * n)
+    assert np.abs(t[:, 1]).max() < 1e-12          # wire 1 is |0> after the move

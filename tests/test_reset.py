@@ -164,3 +164,21 @@ def test_move_is_reset_then_swap():
     assert np.abs(out - psi).max() < 1e-7
     t = out.reshape([2] * n)
     assert np.abs(t[:, 1]).max() < 1e-12          # wire 1 is |0> after the move
+
+
+@pytest.mark.gpu
+def test_gpu_move_matches_the_host_path():
+    n = 4
+
+    def build():
+        cir = dq.QubitCircuit(n)
+        cir.hlayer()
+        cir.rx(1, 0.7)
+        cir.cnot(1, 2)
+        cir.move(1, 3)
+        cir.ry(0, 0.3)
+        cir.to(torch.double)
+        return cir
+    ref = _host_run(build(), torch.zeros(0), np.complex128)[0]
+    out = build().to('cuda')().reshape(-1).cpu().numpy()
+    assert np.abs(out - ref).max() < 1e-12

@@ -580,6 +580,9 @@ def _run_den_mat(op: Operation, flat: torch.Tensor) -> None:
         engine.FusedPlan(2 * op.nqubit, flat.dtype, structs).run(flat, mats, flat.shape[0], 0)
 
 
+_BELL_CACHE = {}
+
+
 class Channel(Operation):
     """Base class of quantum channels (reference operation.py:525-625).  `get_matrix` / `update_matrix` return the
     stacked Kraus operators like the reference; the lowering uses the superoperator built from them."""
@@ -631,12 +634,16 @@ class Channel(Operation):
         sup = torch.einsum('...iab,...icd->...acbd', k, k.conj())          # [..., row', col', row, col]
         if cls._pauli_kraus and d == 2 and DenMatLowering.PAULI_BELL:
             # [4x4 diagonal in the Bell basis | exact Hadamard]: B = (H on row) . CX(row->col), diag = B S B^T
-            r = 0.5 ** 0.5
-            bell = torch.tensor([[r, 0, 0, r], [0, r, r, 0], [r, 0, 0, -r], [0, r, -r, 0]], dtype=sup.real.dtype,
-                                device=k.device).to(sup.dtype)
+            key = (sup.dtype, str(k.device))
+            if key not in _BELL_CACHE:     # constants: built (and copied to the device) once, not every forward
+                r = 0.5 ** 0.5
+                _BELL_CACHE[key] = (
+                    torch.tensor([[r, 0, 0, r], [0, r, r, 0], [r, 0, 0, -r], [0, r, -r, 0]], dtype=sup.real.dtype,
+                                 device=k.device).to(sup.dtype),
+                    torch.tensor([r, r, r, -r], dtype=sup.real.dtype, device=k.device).to(sup.dtype))
+            bell, had = _BELL_CACHE[key]
             s4 = sup.reshape(*sup.shape[:-4], 4, 4)
             dd = torch.einsum('ij,...jk,ik->...i', bell, s4, bell)
-            had = torch.tensor([r, r, r, -r], dtype=sup.real.dtype, device=k.device).to(sup.dtype)
             return torch.cat([torch.diag_embed(dd).reshape(*dd.shape[:-1], 16), had.expand(*dd.shape[:-1], 4)], dim=-1)
         if cls._parity_kraus and not cls._diagonal_kraus and d == 2:
             i = torch.arange(2, device=k.device)
